@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the MPTRAC time-step path on B200 (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+
+One "step" = one model time step (mptrac_run_timestep restricted to the path) over every parcel of the
+workload.  Default workload = BASELINE.json configs[1] ("c2"): 1 M parcels, 1 deg x 1 deg x 60-level synthetic
+ERA5-shaped met (361 x 181 x 60 after the periodic wrap column), RK4 advection only, fp64.
+
+Printed JSON (one line, rank 0):
+  value         particle-steps/s with parcels + met resident in HBM, CUDA-event timed per step, L2 flushed
+                between steps (a 256 MiB device memset outside the timed events)
+  e2e           the same metric through the C ABI with HOST (pinned) parcel buffers: every step uploads
+                time/p/lon/lat, runs the step and downloads them again inside the timed region
+  roofline      algorithmic bytes (64 B per parcel-step + the u,v,w grids of both time levels once per
+                step) / average step-kernel time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own OpenMP code (oracle/_ref harness) or the C port (oracle/) on this host's cores,
+                on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (parcels per GPU, nlon, nlat, nlev, ctl overrides, algorithmic bytes per parcel-step excluding met, met fields)
+    "c2": dict(np=1_000_000, grid=(360, 181, 60), ctl=dict(advect=4, diffusion=0), state_bytes=64, met_fields=3,
+               desc="1M parcels, 1x1 deg x 60 levels (361x181x60), RK4 advection only"),
+    "c3": dict(np=10_000_000, grid=(720, 361, 137), ctl=dict(advect=4, diffusion=1, turb_dx_pbl=0, turb_dx_trop=0,
+                                                              turb_dz_strat=0, qnt_rp=0, qnt_rhop=1, nq=2),
+               state_bytes=104, met_fields=4,
+               desc="10M parcels, 0.5x0.5 deg x 137 levels (721x361x137), RK4 + mesoscale diffusion + sedimentation"),
+}
+DT_MOD = 300.0
+DT_MET = 21600.0
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return json.loads(f.read_text())["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(wl, rank, world):
+    from mptrac_b200 import Ctl, synth
+    nlon, nlat, nlev = wl["grid"]
+    m0, m1 = synth.make_met_pair(nlon, nlat, nlev, t0=0.0, dt_met=DT_MET)
+    n = wl["np"]
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, seed=123 + rank)
+    kw = dict(nq=0, t_start=0.0, t_stop=1e9, dt_mod=DT_MOD, dt_met=DT_MET)
+    kw.update(wl["ctl"])
+    ctl = Ctl(**kw)
+    q = None
+    if ctl.nq:
+        q = np.zeros((ctl.nq, n))
+        q[0], q[1] = 1.0, 1500.0   # rp = 1 micron, rhop = 1500 kg/m3
+    return ctl, m0, m1, (tm, p, lon, lat, q)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mptrac_b200 import Engine, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = WORKLOADS[args.workload]
+    ctl, m0, m1, (tm, p, lon, lat, q) = build_inputs(wl, rank, world)
+    n = wl["np"]
+
+    eng = Engine(n, nq=ctl.nq, device=local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_ctl(ctl)
+    eng.set_clim_tropo(*synth.make_clim_tropo())
+    eng.set_met(0, m0)
+    eng.set_met(1, m1)
+    eng.set_shard(rank * n, world * n)
+
+    # pinned host buffers = what a host driver (trac) owns
+    host = {k: torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for k, a in zip(("time", "p", "lon", "lat"), (tm, p, lon, lat))}
+    hq = torch.from_numpy(q).pin_memory() if q is not None else None
+    hn = {k: v.numpy() for k, v in host.items()}
+    hqn = hq.numpy() if hq is not None else None
+
+    def upload():
+        eng.set_atm(hn["time"], hn["p"], hn["lon"], hn["lat"], hqn)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing: per-step events, L2 flushed between steps ----------------
+    upload()
+    t_model = DT_MOD  # first step with dt != 0
+    for _ in range(W):
+        eng.run_timestep(t_model)
+        t_model += DT_MOD
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = eng.launch_count
+    barrier()
+    with ClockSampler(local) as clk:
+        wall0 = time.perf_counter()
+        for k in range(K):
+            flush.zero_()
+            ev[k][0].record(stream)
+            eng.run_timestep(t_model)
+            ev[k][1].record(stream)
+            t_model += DT_MOD
+        barrier()
+        wall1 = time.perf_counter()
+        launches = eng.launch_count - launches0
+        # the timed region lasts only milliseconds; keep the identical load running (untimed) for ~1 s so that the
+        # 100 ms nvidia-smi sampler sees the clocks this kernel runs at
+        t_end = time.perf_counter() + (0.0 if os.environ.get("MPB_BENCH_NO_SUSTAIN") else max(0.0, 1.0 - (wall1 - wall0)))
+        while time.perf_counter() < t_end:
+            for _ in range(50):
+                eng.run_timestep(t_model)
+                t_model += DT_MOD
+            torch.cuda.synchronize()
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(step_ms.sum())
+
+    # ---------------- back-to-back (no flush), one bracket ----------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for k in range(K):
+        eng.run_timestep(t_model)
+        t_model += DT_MOD
+    e1.record(stream)
+    barrier()
+    b2b_ms = e0.elapsed_time(e1)
+
+    # ---------------- end to end through the C ABI with host buffers ----------------
+    out = {"time": hn["time"], "p": hn["p"], "lon": hn["lon"], "lat": hn["lat"], "q": hqn}
+    for _ in range(max(W, 3)):
+        upload(); eng.run_timestep(t_model); eng.get_atm(out); hn["time"][:] = t_model - DT_MOD
+    barrier()
+    e0.record(stream)
+    for k in range(K):
+        hn["time"][:] = t_model - DT_MOD   # parcels are "at" the previous model time so that dt = DT_MOD
+        upload()
+        eng.run_timestep(t_model)
+        eng.get_atm(out)                    # synchronous D2H of the result
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    bytes_io = 32 * n + (8 * ctl.nq * n)
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    total_ms, b2b_ms, e2e_ms = allmax(total_ms), allmax(b2b_ms), allmax(e2e_ms)
+    units = float(n) * world * K
+    value = units / (total_ms * 1e-3)
+
+    # ---------------- roofline of the dominant (only) kernel ----------------
+    nx, ny, nz = wl["grid"][0] + 1, wl["grid"][1], wl["grid"][2]
+    met_bytes = wl["met_fields"] * 2 * nx * ny * nz * 4
+    algo_bytes = wl["state_bytes"] * n + met_bytes
+    kern_ms = total_ms / K
+    peak, peak_src = peaks()
+    achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get(args.workload)
+        except Exception:
+            traffic = None
+
+    line = {
+        "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[{1 if args.workload == 'c2' else 2}]: {wl['desc']}", "parcels_per_gpu": n,
+                   "dt_mod_s": DT_MOD, "l2": "flushed between steps (256 MiB memset outside the per-step events)",
+                   "parallelism": f"parcels sharded contiguously over {world} GPU(s), no data-path collective"},
+        "back_to_back": {"value": units / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / K, "note": "no L2 flush, one event bracket around K steps"},
+        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io,
+                "ms_per_step": e2e_ms / K},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": algo_bytes, "kernel": "step_kernel", "peak_source": peak_src},
+        "clocks": clk.summary(),
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_budget)
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(workload, budget_s=20.0, steps=None):
+    """The reference's own CPU code (oracle/_ref) -- or the C port when _ref is absent -- on a bounded sample."""
+    from oracle.oracle import Oracle, Parcels, Reference, reference_available
+    from mptrac_b200 import synth
+    wl = WORKLOADS[workload]
+    ctl, m0, m1, (tm, p, lon, lat, q) = build_inputs(wl, 0, 1)
+    n_sample = min(wl["np"], 1_000_000)
+    sl = slice(0, n_sample)
+    atm = Parcels(tm[sl], p[sl], lon[sl], lat[sl], None if q is None else q[:, sl])
+    cores = os.cpu_count() or 1
+    if reference_available():
+        kind = "reference"
+        ref = Reference()
+        names = ["rp", "rhop"] if ctl.nq else []
+        ref.read_ctl(names, "")
+        ref.set_met(m0, m1)
+        run = lambda t, k: ref.run("timestep", ctl, atm, t=t, nsteps=k)   # noqa: E731
+    else:
+        kind = "port"
+        orc = Oracle()
+        clim = synth.make_clim_tropo()
+        run = lambda t, k: orc.run("timestep", ctl, clim, m0, m1, atm, t=t, nsteps=k)   # noqa: E731
+    run(0.0, 1)                 # dt = 0 step: touches everything once
+    t0 = time.perf_counter(); run(DT_MOD, 1); one = time.perf_counter() - t0
+    k = steps or int(max(2, min(200, budget_s / max(one, 1e-3))))
+    t0 = time.perf_counter(); run(2 * DT_MOD, k); el = time.perf_counter() - t0
+    return {"value": n_sample * k / el, "unit": "particle-steps/s", "cores": cores, "kind": kind,
+            "sample": f"{n_sample} parcels x {k} steps of the same workload ({el:.1f} s, OMP threads = {cores})"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = WORKLOADS[args.workload]
+    if args.warmup > 0:
+        cpu_baseline(args.workload, steps=1)
+    # each "step" of this arm is a bounded sample: one model step over min(np, 1M) parcels on all host cores
+    per = max(1, min(args.steps, 10))
+    base = cpu_baseline(args.workload, steps=per)
+    v = base["value"]
+    n_sample = min(wl["np"], 1_000_000)
+    line = {"impl": "reference", "metric": "particle-steps/sec", "value": v, "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": n_sample / v * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[{1 if args.workload == 'c2' else 2}]: {wl['desc']}",
+                       "note": "reference CPU arm: host cores only, rank 0 only"},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

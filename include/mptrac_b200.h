@@ -1,0 +1,151 @@
+/*
+ * mptrac_b200.h -- C ABI of the B200-native particle time-step engine.
+ *
+ * This is the drop-in boundary for MPTRAC's per-particle time-step path.  Every entry
+ * point takes plain pointers / sizes (no torch, no CUDA types) and is what a binding of
+ * the reference (its C driver `trac`, the Fortran `bind(c)` wrapper, or ctypes) links
+ * against.  The reference interface each function stands in for is cited as
+ * file:line relative to the slcs-jsc/mptrac tree.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; mpb_last_error()
+ *     then holds a one-line message (the reference itself aborts through ERRMSG,
+ *     src/mptrac.h:2406-2410; the shim in mptrac_b200/csrc/shim turns a non-zero
+ *     status into exactly that behaviour).
+ *   - all work is enqueued on the context's CUDA stream and is asynchronous unless
+ *     stated otherwise; mpb_sync() waits for it.
+ *   - there is no CPU fallback: without a CUDA device mpb_create() fails.
+ */
+#ifndef MPTRAC_B200_H
+#define MPTRAC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPB_ABI_VERSION 1
+#define MPB_MIX_MAXQ 23  /* number of mixable quantities, src/mptrac.c:5222-5230 */
+
+typedef struct mpb_ctx mpb_ctx;
+
+/* Scalar control parameters read on the path.  Field names and meaning are those of
+ * ctl_t (src/mptrac.h:2494 ff.); defaults are set by mptrac_read_ctl (src/mptrac.c:6723 ff.). */
+typedef struct mpb_ctl {
+  int32_t direction;          /* +1 forward, -1 backward                    ctl->direction       */
+  int32_t met_coord_type;     /* 0 lon/lat degrees, 1 Cartesian metres       ctl->met_coord_type  */
+  int32_t advect;             /* 0 off, 1 Euler, 2 midpoint, 4 RK4           ctl->advect          */
+  int32_t advect_vert_coord;  /* only 0 (pressure levels, omega) is on device ctl->advect_vert_coord */
+  int32_t rng_type;           /* only 1 (Squares counter RNG) is on device    ctl->rng_type        */
+  int32_t diffusion;          /* master switch of both diffusion modules      ctl->diffusion       */
+  int32_t turb_pbl_scheme;    /* >0: diff_turb skips parcels inside the PBL   ctl->turb_pbl_scheme */
+  int32_t nq;                 /* number of quantities                         ctl->nq              */
+  int32_t qnt_rp;             /* quantity index of particle radius or -1      ctl->qnt_rp          */
+  int32_t qnt_rhop;           /* quantity index of particle density or -1     ctl->qnt_rhop        */
+  int32_t qnt_ens;            /* quantity index of ensemble id or -1          ctl->qnt_ens         */
+  int32_t nens;               /* number of ensembles (0 = off)                ctl->nens            */
+  int32_t mixing_nx, mixing_ny, mixing_nz;
+  int32_t n_mix_qnt;                  /* how many entries of mix_qnt are valid */
+  int32_t mix_qnt[MPB_MIX_MAXQ];      /* quantity indices relaxed by module_mixing, in reference order */
+  int32_t _pad;
+  double t_start, t_stop;     /* ctl->t_start (after module_timesteps_init), ctl->t_stop */
+  double dt_mod, dt_met;
+  double met_utm_ref_lat;
+  double sort_dt;
+  double turb_dx_pbl, turb_dx_trop, turb_dx_strat;
+  double turb_dz_pbl, turb_dz_trop, turb_dz_strat;
+  double turb_mesox, turb_mesoz;
+  double turb_pbl_trans;
+  double mixing_dt, mixing_trop, mixing_strat;
+  double mixing_lon0, mixing_lon1, mixing_lat0, mixing_lat1, mixing_z0, mixing_z1;
+} mpb_ctl_t;
+
+/* Host view of one met_t time level (src/mptrac.h:3844-4014).  3-D element (ix,iy,iz) lives at
+ * base[ix*sx + iy*sy + iz]; 2-D element (ix,iy) at base[ix*sx2 + iy].  For the reference structs
+ * sx = EY*EP, sy = EP, sx2 = EY.  t and pbl may be NULL (treated as 0). */
+typedef struct mpb_met_view {
+  double time;
+  int32_t coord_type, nx, ny, np;
+  const double *lon, *lat, *p;
+  const float *u, *v, *w, *t;
+  const float *ps, *pbl;
+  int64_t sx, sy, sx2;
+} mpb_met_view_t;
+
+/* Parameters of the gridded-output binning (write_grid, src/mptrac.c:13752 ff.). */
+typedef struct mpb_grid {
+  int32_t nx, ny, nz, _pad;
+  double lon0, lon1, lat0, lat1, z0, z1;
+  double t0, t1;              /* time window t -/+ 0.5 dt_mod, src/mptrac.c:13824-13825 */
+} mpb_grid_t;
+
+const char *mpb_last_error(void);
+int mpb_abi_version(void);
+int mpb_device_count(void);
+
+/* --- lifetime: stands in for mptrac_alloc / mptrac_free (src/mptrac.c:6294, :6377) --- */
+int mpb_create(mpb_ctx **ctx, int device, int64_t np_max, int nq);
+int mpb_destroy(mpb_ctx *ctx);
+int mpb_set_stream(mpb_ctx *ctx, void *cuda_stream);   /* run on a caller-owned stream (0 = own stream) */
+int mpb_sync(mpb_ctx *ctx);
+
+/* --- host -> device: stands in for mptrac_update_device (src/mptrac.c:8005) --- */
+int mpb_set_ctl(mpb_ctx *ctx, const mpb_ctl_t *ctl);
+int mpb_set_clim_tropo(mpb_ctx *ctx, int ntime, int nlat, const double *time,
+                       const double *lat, const double *tropo /* [ntime][nlat] */);
+int mpb_set_met(mpb_ctx *ctx, int slot /* 0 = met0, 1 = met1 */, const mpb_met_view_t *met);
+int mpb_swap_met(mpb_ctx *ctx);   /* the pointer swap of mptrac_get_met, src/mptrac.c:6489-6491 */
+int mpb_set_atm(mpb_ctx *ctx, int64_t np, const double *time, const double *p,
+                const double *lon, const double *lat, const double *q, int64_t q_stride);
+int mpb_set_uvwp(mpb_ctx *ctx, const float *uvwp /* [np][3], cache_t::uvwp */);
+
+/* --- device -> host: stands in for mptrac_update_host (src/mptrac.c:8061) --- */
+int mpb_get_atm(mpb_ctx *ctx, double *time, double *p, double *lon, double *lat,
+                double *q, int64_t q_stride);
+int mpb_get_uvwp(mpb_ctx *ctx, float *uvwp);
+int mpb_get_dt(mpb_ctx *ctx, double *dt /* cache_t::dt */);
+int64_t mpb_get_np(mpb_ctx *ctx);
+
+/* --- multi-GPU: this context owns parcels [offset, offset+np) of a run with global_np parcels.
+ *     Random numbers are addressed by GLOBAL parcel index, so a sharded run reproduces the
+ *     single-device stream (src/mptrac.c:5797-5826). --- */
+int mpb_set_shard(mpb_ctx *ctx, int64_t global_offset, int64_t global_np);
+int mpb_set_rng_ctr(mpb_ctx *ctx, uint64_t ctr);   /* static rng_ctr, src/mptrac.c:35 */
+uint64_t mpb_get_rng_ctr(mpb_ctx *ctx);
+
+/* --- the step: stands in for mptrac_run_timestep (src/mptrac.c:7851-8001) restricted to the
+ *     modules on the path; all enabled modules run fused in ONE kernel per step. --- */
+int mpb_run_timestep(mpb_ctx *ctx, double t);
+
+/* --- single modules (same symbols the reference exports, src/mptrac.h:6140-7132); each is the
+ *     same fused kernel restricted to one module and reads cache->dt from device memory. --- */
+int mpb_module_timesteps(mpb_ctx *ctx, double t);   /* src/mptrac.c:5999 */
+int mpb_module_position(mpb_ctx *ctx);              /* src/mptrac.c:5435 */
+int mpb_module_advect(mpb_ctx *ctx);                /* src/mptrac.c:3598 */
+int mpb_module_diff_turb(mpb_ctx *ctx);             /* src/mptrac.c:4588 */
+int mpb_module_diff_meso(mpb_ctx *ctx);             /* src/mptrac.c:4266 */
+int mpb_module_sedi(mpb_ctx *ctx);                  /* src/mptrac.c:5859 */
+int mpb_module_sort(mpb_ctx *ctx);                  /* src/mptrac.c:5887 */
+int mpb_module_mixing(mpb_ctx *ctx, double t);      /* src/mptrac.c:5169 (single device) */
+int mpb_module_rng(mpb_ctx *ctx, double *rs_host, int64_t n, int method); /* src/mptrac.c:5753; fills host array, advances counter */
+
+/* --- mixing / gridded output split for multi-GPU runs: accumulate local partial box arrays,
+ *     let the caller sum them over ranks (NCCL), then apply. --- */
+int mpb_mixing_begin(mpb_ctx *ctx, double t);                      /* box index per parcel */
+int mpb_mixing_accumulate(mpb_ctx *ctx, int iq);                   /* -> box sum / count    */
+int mpb_mixing_apply(mpb_ctx *ctx, int iq);                        /* mean + relaxation     */
+int64_t mpb_mixing_nbox(mpb_ctx *ctx);
+int mpb_grid_accumulate(mpb_ctx *ctx, const mpb_grid_t *grid);      /* -> count[nbox], sum[nq][nbox], sumsq[nq][nbox] on device */
+int mpb_grid_fetch(mpb_ctx *ctx, int *count, double *sum, double *sumsq);   /* copy them to the host (any may be NULL) */
+
+/* --- introspection --- */
+void *mpb_device_ptr(mpb_ctx *ctx, const char *name);   /* "time","p","lon","lat","q","dt","uvwp","mix_sum","mix_cnt","grid_cnt","grid_sum","grid_sq" */
+int64_t mpb_launch_count(mpb_ctx *ctx);                  /* kernels launched by this context so far */
+int mpb_met_bytes(mpb_ctx *ctx, int64_t *bytes);         /* packed device bytes of both met levels */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPTRAC_B200_H */

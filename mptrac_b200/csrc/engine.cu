@@ -1,0 +1,961 @@
+// engine.cu -- device context, kernels and the C ABI (include/mptrac_b200.h) of the B200-native
+// MPTRAC time-step engine.  sm_100a only; no CPU fallback: every entry point needs a CUDA device.
+//
+// Data layout in HBM
+//   parcels   SoA fp64: time[np], p[np], lon[np], lat[np], q[nq][np_max]; dt[np]; uvwp float[np][3]
+//             (+ a second copy of the SoA used as the gather target of module_sort, then swapped)
+//   met       two time levels, each float4 node {u,v,w,T} [nx][ny][nz] (z fastest, 16 B/node: the two
+//             z-neighbours of a stencil column are one 32 B sector) and float2 {ps,pbl} [nx][ny];
+//             axes lon/lat/p fp64
+//   clim      tropopause table fp64 [ntime][nlat] + its axes
+//
+// One fused kernel per model step does timesteps -> position -> advect -> diff_turb -> diff_meso ->
+// sedi -> position for one parcel per thread (the order of mptrac_run_timestep, src/mptrac.c:7877-7919).
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mptrac_b200.h"
+#include "physics.cuh"
+
+using namespace mpb;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_));               \
+  } while (0)
+
+#define REQUIRE(cond, msg)                                                                        \
+  do {                                                                                            \
+    if (!(cond)) throw std::runtime_error(msg);                                                   \
+  } while (0)
+
+#define API_BEGIN try {
+#define API_END                                                                                   \
+  return 0;                                                                                       \
+  }                                                                                               \
+  catch (const std::exception &ex) {                                                              \
+    g_err = ex.what();                                                                            \
+    return 1;                                                                                     \
+  }
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+struct StepArgs {
+  MetView met;
+  ClimView clim;
+  CtlView ctl;
+  double *time, *lon, *lat, *p, *dt;
+  float *uvwp;
+  const double *rp, *rhop;
+  long long np;
+  long long ig0;  // global index of local parcel 0
+  unsigned modules;
+};
+
+constexpr unsigned PHYS_TURB = 1, PHYS_MESO = 2, PHYS_SEDI = 4;
+constexpr int kBlock = 128;
+
+template <int ADVECT, unsigned PHYS>
+__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ StepArgs A) {
+  const long long ip = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (ip >= A.np) return;
+
+  Parcel a;
+  a.time = A.time[ip];
+  a.lon = A.lon[ip];
+  a.lat = A.lat[ip];
+  a.p = A.p[ip];
+
+  double dt;
+  if (A.modules & MOD_TIMESTEPS) {
+    dt = parcel_dt(A.met, A.ctl, a);
+    if (A.modules & MOD_STORE_DT) A.dt[ip] = dt;
+  } else {
+    dt = A.dt[ip];
+  }
+  if (dt == 0) return;  // PARTICLE_LOOP(check_dt = 1), src/mptrac.h:1754-1759
+
+  const unsigned long long ig = (unsigned long long)(A.ig0 + ip);
+
+  if (A.modules & MOD_POS_PRE) fix_position(A.met, a);
+  if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a);
+  if (PHYS & PHYS_TURB) diffuse_turbulent(A.met, A.clim, A.ctl, dt, ig, a);
+  if (PHYS & PHYS_MESO) {
+    float *s = A.uvwp + 3 * ip;
+    float up = s[0], vp = s[1], wp = s[2];
+    diffuse_mesoscale(A.met, A.ctl, dt, ig, a, up, vp, wp);
+    s[0] = up; s[1] = vp; s[2] = wp;
+  }
+  if (PHYS & PHYS_SEDI) sediment(A.met, dt, A.rp[ip], A.rhop[ip], a);
+  if (A.modules & MOD_POS_POST) fix_position(A.met, a);
+
+  if (ADVECT > 0) A.time[ip] = a.time;
+  A.lon[ip] = a.lon;
+  A.lat[ip] = a.lat;
+  A.p[ip] = a.p;
+}
+
+typedef void (*step_fn)(const StepArgs);
+
+template <int ADVECT>
+static step_fn pick_phys(unsigned phys) {
+  switch (phys) {
+    case 0: return step_kernel<ADVECT, 0>;
+    case 1: return step_kernel<ADVECT, 1>;
+    case 2: return step_kernel<ADVECT, 2>;
+    case 3: return step_kernel<ADVECT, 3>;
+    case 4: return step_kernel<ADVECT, 4>;
+    case 5: return step_kernel<ADVECT, 5>;
+    case 6: return step_kernel<ADVECT, 6>;
+    default: return step_kernel<ADVECT, 7>;
+  }
+}
+
+static step_fn pick_step(int advect, unsigned phys) {
+  switch (advect) {
+    case 0: return pick_phys<0>(phys);
+    case 1: return pick_phys<1>(phys);
+    case 2: return pick_phys<2>(phys);
+    case 4: return pick_phys<4>(phys);
+    default: throw std::runtime_error("ADVECT must be 0, 1, 2 or 4");
+  }
+}
+
+// interleave four dense fields [n] into float4 nodes
+__global__ void pack_nodes_kernel(const float *u, const float *v, const float *w, const float *t,
+                                  float4 *out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float4(u[i], v[i], w[i], t ? t[i] : 0.f);
+}
+__global__ void pack_surface_kernel(const float *ps, const float *pbl, float2 *out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float2(ps ? ps[i] : 0.f, pbl ? pbl[i] : 0.f);
+}
+
+__global__ void sort_keys_kernel(MetView met, const double *lon, const double *lat, const double *p,
+                                 int *keys, int *idx, long long np) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= np) return;
+  keys[ip] = cell_key(met, lon[ip], lat[ip], p[ip]);
+  idx[ip] = (int)ip;
+}
+
+// dst[a][ip] = src[a][perm[ip]] for narr arrays spaced `stride` doubles apart
+__global__ void gather_kernel(const double *__restrict__ src, double *__restrict__ dst,
+                              const int *__restrict__ perm, long long np, long long stride, int narr) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= np) return;
+  const int j = perm[ip];
+  for (int a = 0; a < narr; a++) dst[a * stride + ip] = src[a * stride + j];
+}
+
+struct BoxArgs {
+  double t0, t1, lon0, lon1, lat0, lat1, z0, z1;
+  int nx, ny, nz;
+};
+
+__global__ void box_index_kernel(BoxArgs b, const double *time, const double *lon, const double *lat,
+                                 const double *p, int *box, long long np) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= np) return;
+  box[ip] = box_index(time[ip], lon[ip], lat[ip], p[ip], b.t0, b.t1, b.lon0, b.lon1, b.lat0, b.lat1,
+                      b.z0, b.z1, b.nx, b.ny, b.nz);
+}
+
+// src/mptrac.c:5287-5303
+__global__ void mix_accumulate_kernel(const int *box, const double *q, const double *ens, int ngrid,
+                                      double *sum, int *cnt, long long np) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= np) return;
+  const int b = box[ip];
+  if (b < 0) return;
+  const int idx = (ens ? (int)ens[ip] : 0) * ngrid + b;
+  atomicAdd(sum + idx, q[ip]);
+  atomicAdd(cnt + idx, 1);
+}
+
+// src/mptrac.c:5307-5335
+__global__ void mix_apply_kernel(ClimView clim, const int *box, double *q, const double *ens,
+                                 const double *time, const double *lat, const double *p, int ngrid,
+                                 const double *sum, const int *cnt, double mix_trop, double mix_strat,
+                                 int latlon, double utm_ref_lat, long long np) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= np) return;
+  const int b = box[ip];
+  if (b < 0) return;
+  const int idx = (ens ? (int)ens[ip] : 0) * ngrid + b;
+  double mixparam = 1.0;
+  if (mix_trop < 1 || mix_strat < 1) {
+    const double pt = tropopause_pressure(clim, time[ip], latlon ? lat[ip] : utm_ref_lat);
+    const double w = weight_tropo(pt, p[ip]);
+    mixparam = w * mix_trop + (1.0 - w) * mix_strat;
+  }
+  const int n = cnt[idx];
+  double mean = sum[idx];
+  if (n > 0) mean /= n;
+  const double qq = q[ip];
+  q[ip] = qq + (mean - qq) * mixparam;
+}
+
+// src/mptrac.c:13862-13872 with kernel weight 1 (no GRID_KERNEL file)
+__global__ void grid_accumulate_kernel(const int *box, const double *q, long long q_stride, int nq,
+                                       long long nbox, int *cnt, double *sum, double *sq, long long np) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= np) return;
+  const int b = box[ip];
+  if (b < 0) return;
+  atomicAdd(cnt + b, 1);
+  for (int iq = 0; iq < nq; iq++) {
+    const double x = q[iq * q_stride + ip];
+    atomicAdd(sum + iq * nbox + b, x);
+    atomicAdd(sq + iq * nbox + b, x * x);
+  }
+}
+
+// uniform / normal stream of module_rng into an array (src/mptrac.c:5784-5828); test + shim support
+__global__ void rng_fill_kernel(unsigned long long ctr0, double *rs, long long n, int method) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (method == 0) {
+    rs[i] = squares_uniform(ctr0 + (unsigned long long)i);
+  } else {
+    const unsigned long long pa = (unsigned long long)i & ~1ull;
+    const double r = sqrt(-2.0 * log(squares_uniform(ctr0 + pa)));
+    const double u1 = squares_uniform(ctr0 + pa + 1);
+    const float phi = (float)(2.0 * kPi * u1);
+    if (i == n) {
+      // slot n only ever holds a uniform, or the sine of the last pair when n is odd
+      rs[i] = (n & 1) ? r * sinf(phi) : squares_uniform(ctr0 + (unsigned long long)i);
+    } else {
+      rs[i] = (i & 1) ? r * sinf(phi) : r * cosf(phi);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct MetLevel {
+  float4 *f = nullptr;
+  float2 *s = nullptr;
+  double time = 0;
+  bool valid = false;
+};
+
+struct mpb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  long long np_max = 0, np = 0;
+  int nq = 0;
+  long long ig0 = 0, global_np = -1;
+  unsigned long long rng_ctr = 0;
+  long long launches = 0;
+
+  // parcels: [time | p | lon | lat | q0 .. q(nq-1)] each np_max doubles, two copies
+  double *soa[2] = {nullptr, nullptr};
+  int cur = 0;
+  double *dt = nullptr;
+  float *uvwp = nullptr;
+
+  // sort scratch
+  int *keys[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
+  void *cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+
+  // met
+  MetLevel lev[2];
+  double *ax_lon = nullptr, *ax_lat = nullptr, *ax_p = nullptr;
+  std::vector<double> h_lon, h_lat, h_p;
+  int nx = 0, ny = 0, nz = 0, coord_type = 0;
+  size_t node_cap = 0, col_cap = 0;
+  float *stage_h = nullptr;  // pinned, 4 dense fields
+  float *stage_d = nullptr;
+  size_t stage_cap = 0;
+
+  // clim
+  double *cl_time = nullptr, *cl_lat = nullptr, *cl_tropo = nullptr;
+  int cl_ntime = 0, cl_nlat = 0;
+
+  // mixing / grid boxes
+  int *box = nullptr;
+  double *mix_sum = nullptr;
+  int *mix_cnt = nullptr;
+  long long mix_cap = 0;
+  double *grid_sum = nullptr, *grid_sq = nullptr;
+  int *grid_cnt = nullptr;
+  long long grid_cap = 0, grid_nbox = 0;
+
+  mpb_ctl_t ctl;
+  bool have_ctl = false;
+
+  double *arr(int which) const { return soa[cur] + (size_t)which * np_max; }  // 0 time 1 p 2 lon 3 lat 4+ q
+  double *time() const { return arr(0); }
+  double *p() const { return arr(1); }
+  double *lon() const { return arr(2); }
+  double *lat() const { return arr(3); }
+  double *q(int iq) const { return arr(4 + iq); }
+};
+
+static inline unsigned nblocks(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+static void use(mpb_ctx *c) {
+  REQUIRE(c != nullptr, "null context");
+  CK(cudaSetDevice(c->device));
+}
+
+static MetView met_view(const mpb_ctx *c) {
+  REQUIRE(c->lev[0].valid && c->lev[1].valid, "both met levels must be set before stepping");
+  MetView g;
+  g.f0 = c->lev[0].f; g.f1 = c->lev[1].f;
+  g.s0 = c->lev[0].s; g.s1 = c->lev[1].s;
+  g.lon = c->ax_lon; g.lat = c->ax_lat; g.p = c->ax_p;
+  g.t0 = c->lev[0].time; g.t1 = c->lev[1].time;
+  g.nx = c->nx; g.ny = c->ny; g.nz = c->nz;
+  g.coord_type = c->coord_type;
+  g.lon_first = c->h_lon[0];
+  g.lon_last = c->h_lon[c->nx - 1];
+  g.lon_d = c->h_lon[1] - c->h_lon[0];
+  g.lat_lo = *std::min_element(c->h_lat.begin(), c->h_lat.end());
+  g.lat_hi = *std::max_element(c->h_lat.begin(), c->h_lat.end());
+  g.lon_asc = c->h_lon[0] < c->h_lon[c->nx - 1];
+  // direction test at the bisection midpoint, as the reference does (src/mptrac.c:3504)
+  { const int m = (c->ny - 1) >> 1; g.lat_asc = c->h_lat[m] < c->h_lat[m + 1]; }
+  { const int m = (c->nz - 1) >> 1; g.p_asc = c->h_p[m] < c->h_p[m + 1]; }
+  g.local = std::fabs(c->h_lon[c->nx - 1] - c->h_lon[0] - 360.0) >= 0.01;
+  return g;
+}
+
+static ClimView clim_view(const mpb_ctx *c) {
+  ClimView v;
+  v.time = c->cl_time; v.lat = c->cl_lat; v.tropo = c->cl_tropo;
+  v.ntime = c->cl_ntime; v.nlat = c->cl_nlat;
+  return v;
+}
+
+static CtlView ctl_view(const mpb_ctx *c, double t) {
+  const mpb_ctl_t &k = c->ctl;
+  CtlView v;
+  v.t = t; v.t_start = k.t_start; v.t_stop = k.t_stop; v.dt_met = k.dt_met;
+  v.utm_ref_lat = k.met_utm_ref_lat;
+  v.dx_pbl = k.turb_dx_pbl; v.dx_trop = k.turb_dx_trop; v.dx_strat = k.turb_dx_strat;
+  v.dz_pbl = k.turb_dz_pbl; v.dz_trop = k.turb_dz_trop; v.dz_strat = k.turb_dz_strat;
+  v.mesox = k.turb_mesox; v.mesoz = k.turb_mesoz; v.pbl_trans = k.turb_pbl_trans;
+  v.ctr_turb = 0; v.ctr_meso = 0;
+  v.direction = k.direction; v.pbl_scheme = k.turb_pbl_scheme;
+  return v;
+}
+
+static bool turb_enabled(const mpb_ctl_t &k) {  // src/mptrac.c:7891-7895
+  return k.diffusion && (k.turb_dx_pbl > 0 || k.turb_dz_pbl > 0 || k.turb_dx_trop > 0 ||
+                         k.turb_dz_trop > 0 || k.turb_dx_strat > 0 || k.turb_dz_strat > 0);
+}
+static bool meso_enabled(const mpb_ctl_t &k) {  // src/mptrac.c:7902
+  return k.diffusion && (k.turb_mesox > 0 || k.turb_mesoz > 0);
+}
+static bool sedi_enabled(const mpb_ctl_t &k) { return k.qnt_rp >= 0 && k.qnt_rhop >= 0; }  // :7911
+
+static unsigned long long rng_draw(mpb_ctx *c) {  // one module_rng(…, 3*np, …) call
+  const unsigned long long start = c->rng_ctr;
+  const long long n = c->global_np >= 0 ? c->global_np : c->np;
+  c->rng_ctr += 3ull * (unsigned long long)n + 1ull;
+  return start;
+}
+
+static void launch_step(mpb_ctx *c, double t, int advect, unsigned phys, unsigned modules) {
+  REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
+  StepArgs A;
+  A.met = met_view(c);
+  A.clim = clim_view(c);
+  A.ctl = ctl_view(c, t);
+  if (phys & PHYS_TURB) {
+    REQUIRE(c->cl_tropo != nullptr, "diff_turb needs the tropopause climatology (mpb_set_clim_tropo)");
+    A.ctl.ctr_turb = rng_draw(c);
+  }
+  if (phys & PHYS_MESO) A.ctl.ctr_meso = rng_draw(c);
+  if (phys & (PHYS_TURB | PHYS_MESO)) REQUIRE(c->ctl.rng_type == 1, "only RNG_TYPE 1 (Squares) runs on the device");
+  A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p();
+  A.dt = c->dt; A.uvwp = c->uvwp;
+  A.rp = A.rhop = nullptr;
+  if (phys & PHYS_SEDI) {
+    REQUIRE(c->ctl.qnt_rp >= 0 && c->ctl.qnt_rp < c->nq && c->ctl.qnt_rhop >= 0 && c->ctl.qnt_rhop < c->nq,
+            "sedimentation needs quantities rp and rhop");
+    A.rp = c->q(c->ctl.qnt_rp); A.rhop = c->q(c->ctl.qnt_rhop);
+  }
+  A.np = c->np; A.ig0 = c->ig0; A.modules = modules;
+  if (advect > 0) REQUIRE(c->ctl.advect_vert_coord == 0, "only ADVECT_VERT_COORD 0 runs on the device");
+  if (c->np == 0) return;
+  step_fn fn = pick_step(advect, phys);
+  fn<<<nblocks(c->np, kBlock), kBlock, 0, c->stream>>>(A);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
+static void ensure_boxes(mpb_ctx *c) {
+  if (!c->box) CK(cudaMalloc(&c->box, sizeof(int) * (size_t)std::max<long long>(c->np_max, 1)));
+}
+
+static void do_sort(mpb_ctx *c) {
+  if (c->np == 0) return;
+  const long long np = c->np;
+  MetView g = met_view(c);
+  if (!c->keys[0]) {
+    for (int i = 0; i < 2; i++) {
+      CK(cudaMalloc(&c->keys[i], sizeof(int) * (size_t)c->np_max));
+      CK(cudaMalloc(&c->perm[i], sizeof(int) * (size_t)c->np_max));
+    }
+    if (!c->soa[1]) CK(cudaMalloc(&c->soa[1], sizeof(double) * (size_t)c->np_max * (size_t)(4 + c->nq)));
+  }
+  sort_keys_kernel<<<nblocks(np, 256), 256, 0, c->stream>>>(g, c->lon(), c->lat(), c->p(), c->keys[0], c->perm[0], np);
+  CK(cudaGetLastError());
+  c->launches++;
+  const long long ncell = (long long)g.nx * g.ny * g.nz;
+  int bits = 1;
+  while ((1ll << bits) < ncell && bits < 31) bits++;
+  size_t need = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, need, c->keys[0], c->keys[1], c->perm[0], c->perm[1], (int)np, 0, bits, c->stream));
+  if (need > c->cub_tmp_bytes) {
+    if (c->cub_tmp) CK(cudaFree(c->cub_tmp));
+    CK(cudaMalloc(&c->cub_tmp, need));
+    c->cub_tmp_bytes = need;
+  }
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, need, c->keys[0], c->keys[1], c->perm[0], c->perm[1], (int)np, 0, bits, c->stream));
+  c->launches += 3;  // cub: histogram + onesweep passes (>= 3 launches)
+  gather_kernel<<<nblocks(np, 256), 256, 0, c->stream>>>(c->soa[c->cur], c->soa[c->cur ^ 1], c->perm[1], np, c->np_max, 4 + c->nq);
+  CK(cudaGetLastError());
+  c->launches++;
+  c->cur ^= 1;
+}
+
+static void mixing_begin(mpb_ctx *c, double t) {
+  const mpb_ctl_t &k = c->ctl;
+  ensure_boxes(c);
+  BoxArgs b;
+  b.t0 = t - 0.5 * k.dt_mod; b.t1 = t + 0.5 * k.dt_mod;
+  b.lon0 = k.mixing_lon0; b.lon1 = k.mixing_lon1; b.lat0 = k.mixing_lat0; b.lat1 = k.mixing_lat1;
+  b.z0 = k.mixing_z0; b.z1 = k.mixing_z1; b.nx = k.mixing_nx; b.ny = k.mixing_ny; b.nz = k.mixing_nz;
+  const long long total = (long long)k.mixing_nx * k.mixing_ny * k.mixing_nz * (k.nens > 0 ? k.nens : 1);
+  REQUIRE(total > 0 && total < (1ll << 31), "mixing grid size out of range");
+  if (total > c->mix_cap) {
+    if (c->mix_sum) { CK(cudaFree(c->mix_sum)); CK(cudaFree(c->mix_cnt)); }
+    CK(cudaMalloc(&c->mix_sum, sizeof(double) * (size_t)total));
+    CK(cudaMalloc(&c->mix_cnt, sizeof(int) * (size_t)total));
+    c->mix_cap = total;
+  }
+  if (c->np == 0) return;
+  box_index_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(b, c->time(), c->lon(), c->lat(), c->p(), c->box, c->np);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
+static long long mixing_total(const mpb_ctx *c) {
+  const mpb_ctl_t &k = c->ctl;
+  return (long long)k.mixing_nx * k.mixing_ny * k.mixing_nz * (k.nens > 0 ? k.nens : 1);
+}
+
+static void mixing_accumulate(mpb_ctx *c, int iq) {
+  REQUIRE(iq >= 0 && iq < c->nq, "mixing quantity index out of range");
+  REQUIRE(c->mix_sum != nullptr, "mpb_mixing_begin has not been called");
+  const mpb_ctl_t &k = c->ctl;
+  const long long total = mixing_total(c);
+  CK(cudaMemsetAsync(c->mix_sum, 0, sizeof(double) * (size_t)total, c->stream));
+  CK(cudaMemsetAsync(c->mix_cnt, 0, sizeof(int) * (size_t)total, c->stream));
+  if (c->np == 0) return;
+  const double *ens = (k.nens > 0 && k.qnt_ens >= 0) ? c->q(k.qnt_ens) : nullptr;
+  mix_accumulate_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(
+      c->box, c->q(iq), ens, k.mixing_nx * k.mixing_ny * k.mixing_nz, c->mix_sum, c->mix_cnt, c->np);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
+static void mixing_apply(mpb_ctx *c, int iq) {
+  REQUIRE(iq >= 0 && iq < c->nq, "mixing quantity index out of range");
+  const mpb_ctl_t &k = c->ctl;
+  if (c->np == 0) return;
+  if (k.mixing_trop < 1 || k.mixing_strat < 1)
+    REQUIRE(c->cl_tropo != nullptr, "mixing needs the tropopause climatology (mpb_set_clim_tropo)");
+  const double *ens = (k.nens > 0 && k.qnt_ens >= 0) ? c->q(k.qnt_ens) : nullptr;
+  mix_apply_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(
+      clim_view(c), c->box, c->q(iq), ens, c->time(), c->lat(), c->p(),
+      k.mixing_nx * k.mixing_ny * k.mixing_nz, c->mix_sum, c->mix_cnt, k.mixing_trop, k.mixing_strat,
+      k.met_coord_type == 0, k.met_utm_ref_lat, c->np);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
+static bool hits(double t, double every) { return std::fmod(t, every) == 0; }
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *mpb_last_error(void) { return g_err.c_str(); }
+int mpb_abi_version(void) { return MPB_ABI_VERSION; }
+
+int mpb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int mpb_create(mpb_ctx **out, int device, int64_t np_max, int nq) {
+  API_BEGIN
+  REQUIRE(out != nullptr, "null output pointer");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw std::runtime_error("no CUDA device: mptrac_b200 has no CPU fallback");
+  }
+  REQUIRE(device >= 0 && device < ndev, "device index out of range");
+  REQUIRE(np_max >= 0 && np_max < (1ll << 31), "np_max out of range (parcel indices are int)");
+  REQUIRE(nq >= 0, "nq must be >= 0");
+  CK(cudaSetDevice(device));
+  mpb_ctx *c = new mpb_ctx();
+  c->device = device; c->np_max = std::max<long long>(np_max, 1); c->nq = nq;
+  std::memset(&c->ctl, 0, sizeof(c->ctl));
+  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  CK(cudaMalloc(&c->soa[0], sizeof(double) * (size_t)c->np_max * (size_t)(4 + nq)));
+  CK(cudaMalloc(&c->dt, sizeof(double) * (size_t)c->np_max));
+  CK(cudaMalloc(&c->uvwp, sizeof(float) * 3 * (size_t)c->np_max));
+  CK(cudaMemsetAsync(c->dt, 0, sizeof(double) * (size_t)c->np_max, c->stream));
+  CK(cudaMemsetAsync(c->uvwp, 0, sizeof(float) * 3 * (size_t)c->np_max, c->stream));
+  *out = c;
+  API_END
+}
+
+int mpb_destroy(mpb_ctx *c) {
+  API_BEGIN
+  if (!c) return 0;
+  use(c);
+  CK(cudaStreamSynchronize(c->stream));
+  void *ptrs[] = {c->soa[0], c->soa[1], c->dt, c->uvwp, c->keys[0], c->keys[1], c->perm[0], c->perm[1],
+                  c->cub_tmp, c->lev[0].f, c->lev[0].s, c->lev[1].f, c->lev[1].s, c->ax_lon, c->ax_lat,
+                  c->ax_p, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_sum, c->mix_cnt,
+                  c->grid_sum, c->grid_sq, c->grid_cnt};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  if (c->stage_h) cudaFreeHost(c->stage_h);
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+  API_END
+}
+
+int mpb_set_stream(mpb_ctx *c, void *s) {
+  API_BEGIN
+  use(c);
+  CK(cudaStreamSynchronize(c->stream));
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  API_END
+}
+
+int mpb_sync(mpb_ctx *c) {
+  API_BEGIN
+  use(c);
+  CK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int mpb_set_ctl(mpb_ctx *c, const mpb_ctl_t *ctl) {
+  API_BEGIN
+  use(c);
+  REQUIRE(ctl != nullptr, "null ctl");
+  REQUIRE(ctl->nq == c->nq, "ctl.nq differs from the context's nq");
+  REQUIRE(ctl->advect == 0 || ctl->advect == 1 || ctl->advect == 2 || ctl->advect == 4, "ADVECT must be 0, 1, 2 or 4");
+  REQUIRE(ctl->n_mix_qnt >= 0 && ctl->n_mix_qnt <= MPB_MIX_MAXQ, "n_mix_qnt out of range");
+  c->ctl = *ctl;
+  c->have_ctl = true;
+  API_END
+}
+
+int mpb_set_clim_tropo(mpb_ctx *c, int ntime, int nlat, const double *time, const double *lat, const double *tropo) {
+  API_BEGIN
+  use(c);
+  REQUIRE(ntime >= 2 && nlat >= 2 && time && lat && tropo, "bad tropopause table");
+  if (c->cl_time) { CK(cudaFree(c->cl_time)); CK(cudaFree(c->cl_lat)); CK(cudaFree(c->cl_tropo)); }
+  CK(cudaMalloc(&c->cl_time, sizeof(double) * ntime));
+  CK(cudaMalloc(&c->cl_lat, sizeof(double) * nlat));
+  CK(cudaMalloc(&c->cl_tropo, sizeof(double) * (size_t)ntime * nlat));
+  CK(cudaMemcpyAsync(c->cl_time, time, sizeof(double) * ntime, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->cl_lat, lat, sizeof(double) * nlat, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->cl_tropo, tropo, sizeof(double) * (size_t)ntime * nlat, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->cl_ntime = ntime; c->cl_nlat = nlat;
+  API_END
+}
+
+int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
+  API_BEGIN
+  use(c);
+  REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  REQUIRE(m && m->lon && m->lat && m->p && m->u && m->v && m->w, "met view lacks axes or wind fields");
+  REQUIRE(m->nx >= 2 && m->ny >= 2 && m->np >= 2, "met grid needs at least 2 nodes per axis");
+  const size_t nnode = (size_t)m->nx * m->ny * m->np, ncol = (size_t)m->nx * m->ny;
+  const bool regrid = (m->nx != c->nx || m->ny != c->ny || m->np != c->nz);
+  if (regrid) {
+    // a new grid shape invalidates the other level (src/mptrac.c:6545-6558 demands identical grids)
+    c->lev[0].valid = c->lev[1].valid = false;
+    c->nx = m->nx; c->ny = m->ny; c->nz = m->np;
+    if (nnode > c->node_cap) {
+      for (int i = 0; i < 2; i++) { if (c->lev[i].f) CK(cudaFree(c->lev[i].f)); CK(cudaMalloc(&c->lev[i].f, sizeof(float4) * nnode)); }
+      c->node_cap = nnode;
+    }
+    if (ncol > c->col_cap) {
+      for (int i = 0; i < 2; i++) { if (c->lev[i].s) CK(cudaFree(c->lev[i].s)); CK(cudaMalloc(&c->lev[i].s, sizeof(float2) * ncol)); }
+      c->col_cap = ncol;
+    }
+    if (4 * nnode > c->stage_cap) {
+      if (c->stage_h) CK(cudaFreeHost(c->stage_h));
+      if (c->stage_d) CK(cudaFree(c->stage_d));
+      CK(cudaMallocHost(&c->stage_h, sizeof(float) * 4 * nnode));
+      CK(cudaMalloc(&c->stage_d, sizeof(float) * 4 * nnode));
+      c->stage_cap = 4 * nnode;
+    }
+    if (c->ax_lon) { CK(cudaFree(c->ax_lon)); CK(cudaFree(c->ax_lat)); CK(cudaFree(c->ax_p)); }
+    CK(cudaMalloc(&c->ax_lon, sizeof(double) * m->nx));
+    CK(cudaMalloc(&c->ax_lat, sizeof(double) * m->ny));
+    CK(cudaMalloc(&c->ax_p, sizeof(double) * m->np));
+  }
+  CK(cudaStreamSynchronize(c->stream));  // staging buffers are reused
+  c->coord_type = m->coord_type;
+  c->h_lon.assign(m->lon, m->lon + m->nx);
+  c->h_lat.assign(m->lat, m->lat + m->ny);
+  c->h_p.assign(m->p, m->p + m->np);
+  CK(cudaMemcpyAsync(c->ax_lon, c->h_lon.data(), sizeof(double) * m->nx, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->ax_lat, c->h_lat.data(), sizeof(double) * m->ny, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->ax_p, c->h_p.data(), sizeof(double) * m->np, cudaMemcpyHostToDevice, c->stream));
+
+  // compact the strided host fields into the pinned staging area (columns are contiguous runs of np floats)
+  const float *src3[4] = {m->u, m->v, m->w, m->t};
+  const size_t row = sizeof(float) * (size_t)m->np;
+  for (int f = 0; f < 4; f++) {
+    if (!src3[f]) continue;
+    float *dst = c->stage_h + (size_t)f * nnode;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int ix = 0; ix < m->nx; ix++)
+      for (int iy = 0; iy < m->ny; iy++)
+        std::memcpy(dst + ((size_t)ix * m->ny + iy) * m->np, src3[f] + (size_t)ix * m->sx + (size_t)iy * m->sy, row);
+    CK(cudaMemcpyAsync(c->stage_d + (size_t)f * nnode, dst, sizeof(float) * nnode, cudaMemcpyHostToDevice, c->stream));
+  }
+  pack_nodes_kernel<<<nblocks((long long)nnode, 256), 256, 0, c->stream>>>(
+      c->stage_d, c->stage_d + nnode, c->stage_d + 2 * nnode, m->t ? c->stage_d + 3 * nnode : nullptr, c->lev[slot].f, nnode);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+
+  // surface fields reuse the (now idle) staging area
+  const float *src2[2] = {m->ps, m->pbl};
+  for (int f = 0; f < 2; f++) {
+    if (!src2[f]) continue;
+    float *dst = c->stage_h + (size_t)f * ncol;
+    for (int ix = 0; ix < m->nx; ix++)
+      std::memcpy(dst + (size_t)ix * m->ny, src2[f] + (size_t)ix * m->sx2, sizeof(float) * (size_t)m->ny);
+    CK(cudaMemcpyAsync(c->stage_d + (size_t)f * ncol, dst, sizeof(float) * ncol, cudaMemcpyHostToDevice, c->stream));
+  }
+  pack_surface_kernel<<<nblocks((long long)ncol, 256), 256, 0, c->stream>>>(
+      m->ps ? c->stage_d : nullptr, m->pbl ? c->stage_d + ncol : nullptr, c->lev[slot].s, ncol);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  c->launches += 2;
+  c->lev[slot].time = m->time;
+  c->lev[slot].valid = true;
+  API_END
+}
+
+int mpb_swap_met(mpb_ctx *c) {
+  API_BEGIN
+  use(c);
+  std::swap(c->lev[0], c->lev[1]);
+  API_END
+}
+
+int mpb_set_atm(mpb_ctx *c, int64_t np, const double *time, const double *p, const double *lon,
+                const double *lat, const double *q, int64_t q_stride) {
+  API_BEGIN
+  use(c);
+  REQUIRE(np >= 0 && np <= c->np_max, "np exceeds the context capacity");
+  REQUIRE(np == 0 || (time && p && lon && lat), "null parcel array");
+  REQUIRE(c->nq == 0 || np == 0 || q != nullptr, "null quantity array");
+  c->np = np;
+  const size_t bytes = sizeof(double) * (size_t)np;
+  if (np > 0) {
+    CK(cudaMemcpyAsync(c->time(), time, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->p(), p, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->lon(), lon, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->lat(), lat, bytes, cudaMemcpyHostToDevice, c->stream));
+    for (int iq = 0; iq < c->nq; iq++)
+      CK(cudaMemcpyAsync(c->q(iq), q + (size_t)iq * q_stride, bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  API_END
+}
+
+int mpb_set_uvwp(mpb_ctx *c, const float *uvwp) {
+  API_BEGIN
+  use(c);
+  REQUIRE(uvwp != nullptr, "null uvwp");
+  if (c->np > 0) CK(cudaMemcpyAsync(c->uvwp, uvwp, sizeof(float) * 3 * (size_t)c->np, cudaMemcpyHostToDevice, c->stream));
+  API_END
+}
+
+int mpb_get_atm(mpb_ctx *c, double *time, double *p, double *lon, double *lat, double *q, int64_t q_stride) {
+  API_BEGIN
+  use(c);
+  const size_t bytes = sizeof(double) * (size_t)c->np;
+  if (c->np > 0) {
+    if (time) CK(cudaMemcpyAsync(time, c->time(), bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (p) CK(cudaMemcpyAsync(p, c->p(), bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (lon) CK(cudaMemcpyAsync(lon, c->lon(), bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (lat) CK(cudaMemcpyAsync(lat, c->lat(), bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (q)
+      for (int iq = 0; iq < c->nq; iq++)
+        CK(cudaMemcpyAsync(q + (size_t)iq * q_stride, c->q(iq), bytes, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int mpb_get_uvwp(mpb_ctx *c, float *uvwp) {
+  API_BEGIN
+  use(c);
+  if (c->np > 0) CK(cudaMemcpyAsync(uvwp, c->uvwp, sizeof(float) * 3 * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int mpb_get_dt(mpb_ctx *c, double *dt) {
+  API_BEGIN
+  use(c);
+  if (c->np > 0) CK(cudaMemcpyAsync(dt, c->dt, sizeof(double) * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int64_t mpb_get_np(mpb_ctx *c) { return c ? c->np : -1; }
+
+int mpb_set_shard(mpb_ctx *c, int64_t off, int64_t global_np) {
+  API_BEGIN
+  use(c);
+  REQUIRE(off >= 0 && global_np >= 0, "bad shard");
+  c->ig0 = off; c->global_np = global_np;
+  API_END
+}
+
+int mpb_set_rng_ctr(mpb_ctx *c, uint64_t ctr) {
+  API_BEGIN
+  use(c);
+  c->rng_ctr = ctr;
+  API_END
+}
+uint64_t mpb_get_rng_ctr(mpb_ctx *c) { return c ? c->rng_ctr : 0; }
+
+int mpb_run_timestep(mpb_ctx *c, double t) {
+  API_BEGIN
+  use(c);
+  REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
+  const mpb_ctl_t &k = c->ctl;
+  unsigned phys = 0;
+  if (turb_enabled(k)) phys |= PHYS_TURB;
+  if (meso_enabled(k)) phys |= PHYS_MESO;
+  if (sedi_enabled(k)) phys |= PHYS_SEDI;
+  unsigned modules = MOD_POS_PRE | MOD_POS_POST;
+  if (k.sort_dt > 0 && hits(t, k.sort_dt)) {
+    // the reference computes dt BEFORE it permutes the parcels and leaves cache->dt in slot order
+    // (src/mptrac.c:7877-7881): do the same with a dt-only launch, then sort, then read dt from memory
+    launch_step(c, t, 0, 0, MOD_TIMESTEPS | MOD_STORE_DT);
+    // a dt-only launch of parcels with dt != 0 rewrites lon/lat/p unchanged: harmless
+    do_sort(c);
+  } else {
+    modules |= MOD_TIMESTEPS;
+  }
+  launch_step(c, t, k.advect, phys, modules);
+  if (k.mixing_trop >= 0 && k.mixing_strat >= 0 && (k.mixing_dt <= 0 || hits(t, k.mixing_dt))) {  // :7943-7945
+    mixing_begin(c, t);
+    for (int i = 0; i < k.n_mix_qnt; i++)
+      if (k.mix_qnt[i] >= 0) { mixing_accumulate(c, k.mix_qnt[i]); mixing_apply(c, k.mix_qnt[i]); }
+  }
+  API_END
+}
+
+int mpb_module_timesteps(mpb_ctx *c, double t) {
+  API_BEGIN
+  use(c);
+  // dt-only pass; position arrays of active parcels are rewritten with identical values
+  launch_step(c, t, 0, 0, MOD_TIMESTEPS | MOD_STORE_DT);
+  API_END
+}
+int mpb_module_position(mpb_ctx *c) {
+  API_BEGIN
+  use(c);
+  launch_step(c, 0.0, 0, 0, MOD_POS_PRE);
+  API_END
+}
+int mpb_module_advect(mpb_ctx *c) {
+  API_BEGIN
+  use(c);
+  REQUIRE(c->ctl.advect > 0, "ADVECT is 0");
+  launch_step(c, 0.0, c->ctl.advect, 0, 0);
+  API_END
+}
+int mpb_module_diff_turb(mpb_ctx *c) {
+  API_BEGIN
+  use(c);
+  launch_step(c, 0.0, 0, PHYS_TURB, 0);
+  API_END
+}
+int mpb_module_diff_meso(mpb_ctx *c) {
+  API_BEGIN
+  use(c);
+  launch_step(c, 0.0, 0, PHYS_MESO, 0);
+  API_END
+}
+int mpb_module_sedi(mpb_ctx *c) {
+  API_BEGIN
+  use(c);
+  launch_step(c, 0.0, 0, PHYS_SEDI, 0);
+  API_END
+}
+int mpb_module_sort(mpb_ctx *c) {
+  API_BEGIN
+  use(c);
+  do_sort(c);
+  API_END
+}
+
+int mpb_mixing_begin(mpb_ctx *c, double t) {
+  API_BEGIN
+  use(c);
+  REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
+  mixing_begin(c, t);
+  API_END
+}
+int mpb_mixing_accumulate(mpb_ctx *c, int iq) {
+  API_BEGIN
+  use(c);
+  mixing_accumulate(c, iq);
+  API_END
+}
+int mpb_mixing_apply(mpb_ctx *c, int iq) {
+  API_BEGIN
+  use(c);
+  mixing_apply(c, iq);
+  API_END
+}
+int64_t mpb_mixing_nbox(mpb_ctx *c) { return c && c->have_ctl ? mixing_total(c) : -1; }
+
+int mpb_module_mixing(mpb_ctx *c, double t) {
+  API_BEGIN
+  use(c);
+  REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
+  mixing_begin(c, t);
+  for (int i = 0; i < c->ctl.n_mix_qnt; i++)
+    if (c->ctl.mix_qnt[i] >= 0) { mixing_accumulate(c, c->ctl.mix_qnt[i]); mixing_apply(c, c->ctl.mix_qnt[i]); }
+  API_END
+}
+
+int mpb_module_rng(mpb_ctx *c, double *rs_host, int64_t n, int method) {
+  API_BEGIN
+  use(c);
+  REQUIRE(n >= 0 && (method == 0 || method == 1), "bad rng request");
+  const unsigned long long start = c->rng_ctr;
+  c->rng_ctr += (unsigned long long)n + 1ull;  // src/mptrac.c:5812
+  if (rs_host) {
+    double *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double) * (size_t)(n + 1)));
+    rng_fill_kernel<<<nblocks(n + 1, 256), 256, 0, c->stream>>>(start, d, n, method);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaMemcpyAsync(rs_host, d, sizeof(double) * (size_t)(n + 1), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(d));
+  }
+  API_END
+}
+
+int mpb_grid_accumulate(mpb_ctx *c, const mpb_grid_t *g) {
+  API_BEGIN
+  use(c);
+  REQUIRE(g && g->nx > 0 && g->ny > 0 && g->nz > 0, "bad grid");
+  const long long nbox = (long long)g->nx * g->ny * g->nz;
+  REQUIRE(nbox < (1ll << 31), "grid too large");
+  ensure_boxes(c);
+  const long long need = nbox * std::max(c->nq, 1);
+  if (need > c->grid_cap) {
+    if (c->grid_sum) { CK(cudaFree(c->grid_sum)); CK(cudaFree(c->grid_sq)); CK(cudaFree(c->grid_cnt)); }
+    CK(cudaMalloc(&c->grid_sum, sizeof(double) * (size_t)need));
+    CK(cudaMalloc(&c->grid_sq, sizeof(double) * (size_t)need));
+    CK(cudaMalloc(&c->grid_cnt, sizeof(int) * (size_t)need));
+    c->grid_cap = need;
+  }
+  c->grid_nbox = nbox;
+  CK(cudaMemsetAsync(c->grid_sum, 0, sizeof(double) * (size_t)need, c->stream));
+  CK(cudaMemsetAsync(c->grid_sq, 0, sizeof(double) * (size_t)need, c->stream));
+  CK(cudaMemsetAsync(c->grid_cnt, 0, sizeof(int) * (size_t)nbox, c->stream));
+  if (c->np == 0) return 0;
+  BoxArgs b;
+  b.t0 = g->t0; b.t1 = g->t1; b.lon0 = g->lon0; b.lon1 = g->lon1; b.lat0 = g->lat0; b.lat1 = g->lat1;
+  b.z0 = g->z0; b.z1 = g->z1; b.nx = g->nx; b.ny = g->ny; b.nz = g->nz;
+  box_index_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(b, c->time(), c->lon(), c->lat(), c->p(), c->box, c->np);
+  CK(cudaGetLastError());
+  grid_accumulate_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(
+      c->box, c->nq ? c->q(0) : nullptr, c->np_max, c->nq, nbox, c->grid_cnt, c->grid_sum, c->grid_sq, c->np);
+  CK(cudaGetLastError());
+  c->launches += 2;
+  API_END
+}
+
+int mpb_grid_fetch(mpb_ctx *c, int *count, double *sum, double *sq) {
+  API_BEGIN
+  use(c);
+  REQUIRE(c->grid_nbox > 0, "mpb_grid_accumulate has not been called");
+  const size_t nb = (size_t)c->grid_nbox;
+  if (count) CK(cudaMemcpyAsync(count, c->grid_cnt, sizeof(int) * nb, cudaMemcpyDeviceToHost, c->stream));
+  if (sum) CK(cudaMemcpyAsync(sum, c->grid_sum, sizeof(double) * nb * c->nq, cudaMemcpyDeviceToHost, c->stream));
+  if (sq) CK(cudaMemcpyAsync(sq, c->grid_sq, sizeof(double) * nb * c->nq, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+void *mpb_device_ptr(mpb_ctx *c, const char *name) {
+  if (!c || !name) return nullptr;
+  const std::string n(name);
+  if (n == "time") return c->time();
+  if (n == "p") return c->p();
+  if (n == "lon") return c->lon();
+  if (n == "lat") return c->lat();
+  if (n == "q") return c->nq ? c->q(0) : nullptr;
+  if (n == "dt") return c->dt;
+  if (n == "uvwp") return c->uvwp;
+  if (n == "mix_sum") return c->mix_sum;
+  if (n == "mix_cnt") return c->mix_cnt;
+  if (n == "grid_sum") return c->grid_sum;
+  if (n == "grid_sq") return c->grid_sq;
+  if (n == "grid_cnt") return c->grid_cnt;
+  return nullptr;
+}
+
+int64_t mpb_launch_count(mpb_ctx *c) { return c ? c->launches : -1; }
+
+int mpb_met_bytes(mpb_ctx *c, int64_t *bytes) {
+  API_BEGIN
+  REQUIRE(c && bytes, "null argument");
+  *bytes = 2ll * ((long long)c->nx * c->ny * c->nz * (long long)sizeof(float4) + (long long)c->nx * c->ny * (long long)sizeof(float2));
+  API_END
+}
+
+}  // extern "C"

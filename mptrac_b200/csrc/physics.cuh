@@ -1,0 +1,600 @@
+// physics.cuh -- per-parcel physics of the MPTRAC time-step path, written for one CUDA thread
+// per parcel.  Everything here is __host__ __device__ so that tests/_hostemu can execute the very
+// same source on the CPU of the (GPU-less) development container; the shipped library only ever
+// calls it from kernels (see step_kernels.cu).
+//
+// Behavioural contract = the reference's module_* functions; the citations below are
+// file:line in slcs-jsc/mptrac (src/mptrac.c unless stated otherwise).  Precision rules that are
+// part of the contract: parcel state is fp64, met fields are fp32 and the FIRST subtraction of a
+// lerp happens in fp32 (3023-3043), mesoscale statistics accumulate in fp32 in a fixed order
+// (4288-4311), Box-Muller takes cosf/sinf of a float angle (5821-5826).
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#define MPB_HD __host__ __device__ __forceinline__
+
+namespace mpb {
+
+// ----------------------------------------------------------------------------------------------
+// constants (src/mptrac.h:265-340)
+// ----------------------------------------------------------------------------------------------
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kG0 = 9.80665;
+constexpr double kH0 = 7.0;
+constexpr double kKB = 1.3806504e-23;
+constexpr double kMA = 28.9644;
+constexpr double kP0 = 1013.25;
+constexpr double kRI = 8.3144598;
+constexpr double kRA = 1e3 * kRI / kMA;
+constexpr double kRE = 6367.421;
+constexpr double kMAirMolecule = 4.8096e-26;
+constexpr double kYear = 365.25 * 86400.;
+
+// module bits of one fused launch
+enum : unsigned {
+  MOD_TIMESTEPS = 1u << 0,  // compute dt in-kernel (otherwise read cache dt from memory)
+  MOD_POS_PRE = 1u << 1,
+  MOD_ADVECT = 1u << 2,
+  MOD_TURB = 1u << 3,
+  MOD_MESO = 1u << 4,
+  MOD_SEDI = 1u << 5,
+  MOD_POS_POST = 1u << 6,
+  MOD_STORE_DT = 1u << 7,  // also write dt back (cache_t::dt for callers that need it)
+};
+
+// ----------------------------------------------------------------------------------------------
+// device views
+// ----------------------------------------------------------------------------------------------
+struct MetView {
+  const float4 *f0, *f1;  // [nx][ny][nz] nodes {u, v, w, T} of met0 / met1
+  const float2 *s0, *s1;  // [nx][ny] nodes {ps, pbl}
+  const double *lon, *lat, *p;  // axes
+  double t0, t1;          // met0->time, met1->time
+  double lon_first, lon_last, lon_d;   // lon[0], lon[nx-1], lon[1]-lon[0]
+  double lat_lo, lat_hi;  // min / max of the latitude axis
+  int nx, ny, nz;
+  int coord_type;         // 0 lon/lat, 1 Cartesian
+  int lon_asc, lat_asc, p_asc;
+  int local;              // met domain is not global (5999-6012)
+};
+
+struct ClimView {
+  const double *time;   // [ntime]
+  const double *lat;    // [nlat]
+  const double *tropo;  // [ntime][nlat]
+  int ntime, nlat;
+};
+
+struct CtlView {
+  double t, t_start, t_stop, dt_met;
+  double utm_ref_lat;
+  double dx_pbl, dx_trop, dx_strat, dz_pbl, dz_trop, dz_strat;
+  double mesox, mesoz, pbl_trans;
+  uint64_t ctr_turb, ctr_meso;  // Squares counters at the start of the two module_rng calls
+  int direction;
+  int pbl_scheme;
+};
+
+struct Parcel {
+  double time, lon, lat, p;
+};
+
+// ----------------------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+MPB_HD T ldg(const T *ptr) {
+#ifdef __CUDA_ARCH__
+  return __ldg(ptr);
+#else
+  return *ptr;
+#endif
+}
+
+// fp32 arithmetic with exactly one rounding per operation (no FMA contraction)
+MPB_HD float f_add(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+MPB_HD float f_sub(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+MPB_HD float f_mul(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+
+// x - trunc(x / y) * y with the quotient truncated through int (src/mptrac.h:1121-1122)
+MPB_HD double mod_trunc(double x, double y) { return x - (int)(x / y) * y; }
+
+// y0 + (y1 - y0) / (x1 - x0) * (x - x0)  (src/mptrac.h:1351)
+MPB_HD double lin(double x0, double y0, double x1, double y1, double x) {
+  return y0 + (y1 - y0) / (x1 - x0) * (x - x0);
+}
+
+// km -> hPa at pressure p (src/mptrac.h:941)
+MPB_HD double dz2dp(double dz, double p) { return -dz * p / kH0; }
+
+// metres east / north -> coordinate increment (src/mptrac.h:904-906, 922-923, 966, 989)
+MPB_HD double dx2coord(int coord_type, double dx, double lat) {
+  if (coord_type != 0) return dx;
+  if (lat < -89.999 || lat > 89.999) return 0.0;
+  return (dx / 1000.0) * 180. / (kPi * kRE * cos(lat * (kPi / 180.0)));
+}
+MPB_HD double dy2coord(int coord_type, double dy) {
+  if (coord_type != 0) return dy;
+  return (dy / 1000.0) * 180. / (kPi * kRE);
+}
+
+// Interval search on a monotone axis; same result as the reference bisection (3495-3521):
+// ascending: largest i <= n-2 with xx[i] <= x (0 if none); descending: largest i with xx[i] > x.
+MPB_HD int find_interval(const double *xx, int n, int ascending, double x) {
+  int lo = 0, hi = n - 1;
+  if (ascending) {
+    while (hi > lo + 1) {
+      const int mid = (hi + lo) >> 1;
+      if (ldg(xx + mid) > x) hi = mid; else lo = mid;
+    }
+  } else {
+    while (hi > lo + 1) {
+      const int mid = (hi + lo) >> 1;
+      if (ldg(xx + mid) <= x) hi = mid; else lo = mid;
+    }
+  }
+  return lo;
+}
+
+// Regular-axis index by division, clamped to [0, n-2] (3559-3574)
+MPB_HD int find_regular(double x0, double dx, int n, double x) {
+  const int i = (int)((x - x0) / dx);
+  return i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
+}
+
+// horizontal range check before a lookup (2755-2803)
+MPB_HD void clamp_horizontal(const MetView &g, double lon, double lat, double &lon2, double &lat2) {
+  if (g.coord_type == 0) {
+    lon2 = mod_trunc(lon, 360.);
+    if (lon2 < g.lon_first) lon2 += 360;
+    else if (lon2 > g.lon_last) lon2 -= 360;
+    lat2 = fmin(fmax(lat, g.lat_lo), g.lat_hi);
+  } else {
+    const double xlo = g.lon_asc ? g.lon_first : g.lon_last;
+    const double xhi = g.lon_asc ? g.lon_last : g.lon_first;
+    lon2 = fmin(fmax(lon, xlo), xhi);
+    lat2 = fmin(fmax(lat, g.lat_lo), g.lat_hi);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// met lookups
+// ----------------------------------------------------------------------------------------------
+struct Stencil {
+  int ix, iy, iz;
+  double wx, wy, wz;  // weight of the LOWER index node along each axis (3015-3020)
+};
+
+MPB_HD void stencil_2d(const MetView &g, double lon, double lat, Stencil &s) {
+  double lon2, lat2;
+  clamp_horizontal(g, lon, lat, lon2, lat2);
+  s.ix = find_regular(g.lon_first, g.lon_d, g.nx, lon2);
+  s.iy = find_interval(g.lat, g.ny, g.lat_asc, lat2);
+  const double x0 = ldg(g.lon + s.ix), x1 = ldg(g.lon + s.ix + 1);
+  const double y0 = ldg(g.lat + s.iy), y1 = ldg(g.lat + s.iy + 1);
+  s.wx = (x1 - lon2) / (x1 - x0);
+  s.wy = (y1 - lat2) / (y1 - y0);
+}
+
+MPB_HD void stencil_3d(const MetView &g, double lon, double lat, double p, Stencil &s) {
+  stencil_2d(g, lon, lat, s);
+  s.iz = find_interval(g.p, g.nz, g.p_asc, p);
+  const double p0 = ldg(g.p + s.iz), p1 = ldg(g.p + s.iz + 1);
+  s.wz = (p1 - p) / (p1 - p0);
+}
+
+// w * (lo - hi) + hi with the difference taken in fp32 first (3023-3038)
+MPB_HD double lerp_f32(double w, float lo, float hi) { return w * (double)f_sub(lo, hi) + (double)hi; }
+MPB_HD double lerp_f64(double w, double lo, double hi) { return w * (lo - hi) + hi; }
+
+struct Cube {  // the 8 corner nodes of one time level
+  float4 n000, n001, n010, n011, n100, n101, n110, n111;  // index order: x, y, z
+};
+
+MPB_HD void load_cube(const float4 *f, const MetView &g, const Stencil &s, Cube &c) {
+  const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * (size_t)g.nz;
+  const float4 *b = f + ((size_t)s.ix * sx + (size_t)s.iy * sy + (size_t)s.iz);
+  c.n000 = ldg(b);
+  c.n001 = ldg(b + 1);
+  c.n010 = ldg(b + sy);
+  c.n011 = ldg(b + sy + 1);
+  c.n100 = ldg(b + sx);
+  c.n101 = ldg(b + sx + 1);
+  c.n110 = ldg(b + sx + sy);
+  c.n111 = ldg(b + sx + sy + 1);
+}
+
+#define MPB_TRILERP(member)                                              \
+  lerp_f64(s.wx,                                                         \
+           lerp_f64(s.wy, lerp_f32(s.wz, c.n000.member, c.n001.member),  \
+                    lerp_f32(s.wz, c.n010.member, c.n011.member)),       \
+           lerp_f64(s.wy, lerp_f32(s.wz, c.n100.member, c.n101.member),  \
+                    lerp_f32(s.wz, c.n110.member, c.n111.member)))
+
+// time weight of met0 (3133)
+MPB_HD double time_weight(const MetView &g, double ts) { return (g.t1 - ts) / (g.t1 - g.t0); }
+
+// u, v, w at (ts, p, lon, lat): intpol_met_time_3d x3 sharing one stencil (3112-3137, 3638-3643)
+MPB_HD void wind_at(const MetView &g, double ts, double lon, double lat, double p,
+                    double &u, double &v, double &w) {
+  Stencil s;
+  stencil_3d(g, lon, lat, p, s);
+  Cube c;
+  load_cube(g.f0, g, s, c);
+  const double u0 = MPB_TRILERP(x), v0 = MPB_TRILERP(y), w0 = MPB_TRILERP(z);
+  load_cube(g.f1, g, s, c);
+  const double u1 = MPB_TRILERP(x), v1 = MPB_TRILERP(y), w1 = MPB_TRILERP(z);
+  const double wt = time_weight(g, ts);
+  u = lerp_f64(wt, u0, u1);
+  v = lerp_f64(wt, v0, v1);
+  w = lerp_f64(wt, w0, w1);
+}
+
+// temperature at (ts, p, lon, lat)
+MPB_HD double temperature_at(const MetView &g, double ts, double lon, double lat, double p) {
+  Stencil s;
+  stencil_3d(g, lon, lat, p, s);
+  Cube c;
+  load_cube(g.f0, g, s, c);
+  const double a0 = MPB_TRILERP(w);
+  load_cube(g.f1, g, s, c);
+  const double a1 = MPB_TRILERP(w);
+  return lerp_f64(time_weight(g, ts), a0, a1);
+}
+
+// bilinear value of 4 corners with the nearest-neighbour rule for non-finite data (3084-3107)
+MPB_HD double bilerp_guarded(double wx, double wy, double a00, double a01, double a10, double a11) {
+  if (isfinite(a00) && isfinite(a01) && isfinite(a10) && isfinite(a11))
+    return lerp_f64(wx, lerp_f64(wy, a00, a01), lerp_f64(wy, a10, a11));
+  if (wy < 0.5) return wx < 0.5 ? a11 : a01;
+  return wx < 0.5 ? a10 : a00;
+}
+
+// time blend with the same guard (3163-3169)
+MPB_HD double time_blend_guarded(double wt, double a0, double a1) {
+  if (isfinite(a0) && isfinite(a1)) return lerp_f64(wt, a0, a1);
+  return wt < 0.5 ? a1 : a0;
+}
+
+// ps and pbl at the parcel position (INTPOL_2D(pbl,1); INTPOL_2D(ps,0), 4606-4617)
+MPB_HD void surface_at(const MetView &g, double ts, double lon, double lat, double &ps, double &pbl) {
+  Stencil s;
+  stencil_2d(g, lon, lat, s);
+  const size_t b = (size_t)s.ix * (size_t)g.ny + (size_t)s.iy;
+  const size_t sx = (size_t)g.ny;
+  const double wt = time_weight(g, ts);
+  float2 a00 = ldg(g.s0 + b), a01 = ldg(g.s0 + b + 1), a10 = ldg(g.s0 + b + sx), a11 = ldg(g.s0 + b + sx + 1);
+  const double ps0 = bilerp_guarded(s.wx, s.wy, a00.x, a01.x, a10.x, a11.x);
+  const double pb0 = bilerp_guarded(s.wx, s.wy, a00.y, a01.y, a10.y, a11.y);
+  a00 = ldg(g.s1 + b); a01 = ldg(g.s1 + b + 1); a10 = ldg(g.s1 + b + sx); a11 = ldg(g.s1 + b + sx + 1);
+  const double ps1 = bilerp_guarded(s.wx, s.wy, a00.x, a01.x, a10.x, a11.x);
+  const double pb1 = bilerp_guarded(s.wx, s.wy, a00.y, a01.y, a10.y, a11.y);
+  ps = time_blend_guarded(wt, ps0, ps1);
+  pbl = time_blend_guarded(wt, pb0, pb1);
+}
+
+// ----------------------------------------------------------------------------------------------
+// module_timesteps (5999-6042)
+// ----------------------------------------------------------------------------------------------
+MPB_HD double parcel_dt(const MetView &g, const CtlView &c, const Parcel &a) {
+  const double dir = (double)c.direction;
+  double dt = 0.0;
+  if (dir * (a.time - c.t_start) >= 0 && dir * (a.time - c.t_stop) <= 0 && dir * (a.time - c.t) < 0)
+    dt = c.t - a.time;
+  if (g.local && (a.lon <= g.lon_first || a.lon >= g.lon_last || a.lat <= g.lat_lo || a.lat >= g.lat_hi))
+    dt = 0.0;
+  return dt;
+}
+
+// ----------------------------------------------------------------------------------------------
+// module_position (5435-5489)
+// NB the reference looks up ps with a *fresh* (zeroed) stencil and init = 0 (5483): the value it
+// gets is the time-blended surface pressure of grid node [1][1], not of the parcel's column.
+// That is what the reference's outputs contain, so it is reproduced here.
+// ----------------------------------------------------------------------------------------------
+MPB_HD void fix_position(const MetView &g, Parcel &a) {
+  if (g.coord_type == 0) {
+    a.lon = mod_trunc(a.lon, 360.);
+    a.lat = mod_trunc(a.lat, 360.);
+    while (a.lat < -90 || a.lat > 90) {
+      if (a.lat > 90) { a.lat = 180 - a.lat; a.lon += 180; }
+      if (a.lat < -90) { a.lat = -180 - a.lat; a.lon += 180; }
+    }
+    while (a.lon < -180) a.lon += 360;
+    while (a.lon >= 180) a.lon -= 360;
+  } else {
+    double x, y;
+    clamp_horizontal(g, a.lon, a.lat, x, y);
+    a.lon = x; a.lat = y;
+  }
+  const double ptop = ldg(g.p + g.nz - 1);
+  if (a.p < ptop) {
+    a.p = ptop * ptop / a.p;
+  } else if (a.p > 300.) {
+    const size_t n11 = (size_t)g.ny + 1;
+    const double ps = time_blend_guarded(time_weight(g, a.time), (double)ldg(g.s0 + n11).x, (double)ldg(g.s1 + n11).x);
+    if (a.p > ps) a.p = ps * ps / a.p;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// module_advect, pressure-level branch (3612-3677)
+// ----------------------------------------------------------------------------------------------
+template <int ORDER>
+MPB_HD void advect(const MetView &g, double dt, Parcel &a) {
+  double um = 0, vm = 0, wm = 0;
+  double u = 0, v = 0, w = 0;
+  double lat_stage = a.lat;
+#pragma unroll
+  for (int i = 0; i < ORDER; i++) {
+    double x, y, z, dts;
+    if (i == 0) {
+      dts = 0.0; x = a.lon; y = a.lat; z = a.p;
+    } else {
+      dts = (i == 3 ? 1.0 : 0.5) * dt;
+      x = a.lon + dx2coord(g.coord_type, dts * u, a.lat);
+      y = a.lat + dy2coord(g.coord_type, dts * v);
+      z = a.p + dts * w;
+    }
+    lat_stage = y;
+    wind_at(g, a.time + dts, x, y, z, u, v, w);
+    double k = 1.0;
+    if (ORDER == 2) k = (i == 0 ? 0.0 : 1.0);
+    else if (ORDER == 4) k = (i == 0 || i == 3 ? 1.0 / 6.0 : 2.0 / 6.0);
+    um += k * u; vm += k * v; wm += k * w;
+  }
+  a.time += dt;
+  a.lon += dx2coord(g.coord_type, dt * um, ORDER == 2 ? lat_stage : a.lat);
+  a.lat += dy2coord(g.coord_type, dt * vm);
+  a.p += dt * wm;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Squares counter RNG + Box-Muller (5784-5828)
+// ----------------------------------------------------------------------------------------------
+MPB_HD double squares_uniform(uint64_t ctr) {
+  const uint64_t key = 0xc8e4fd154ce32f6dull;
+  uint64_t x, y, z, t;
+  y = x = ctr * key;
+  z = y + key;
+  x = x * x + y; x = (x >> 32) | (x << 32);
+  x = x * x + z; x = (x >> 32) | (x << 32);
+  x = x * x + y; x = (x >> 32) | (x << 32);
+  t = x = x * x + z; x = (x >> 32) | (x << 32);
+  const uint64_t r = t ^ ((x * x + y) >> 32);
+  return (double)r / 18446744073709551616.0;   // (double) UINT64_MAX == 2^64
+}
+
+// The three normals rs[3*ig], rs[3*ig+1], rs[3*ig+2] of a module_rng(…, 3*np, 1) call whose
+// uniform stream started at counter ctr0.  Normal j is made from the uniform pair (j & ~1, +1):
+// even j takes the cosine, odd j the sine.
+MPB_HD void normals3(uint64_t ctr0, uint64_t ig, double &r0, double &r1, double &r2) {
+  const uint64_t j0 = 3 * ig;
+  const uint64_t pa = j0 & ~1ull;       // pair that holds j0
+  const uint64_t pb = pa + 2;           // pair that holds j0+2 (and j0+1 when j0 is odd)
+  const double ra = sqrt(-2.0 * log(squares_uniform(ctr0 + pa)));
+  const float fa = (float)(2.0 * kPi * squares_uniform(ctr0 + pa + 1));
+  const double rb = sqrt(-2.0 * log(squares_uniform(ctr0 + pb)));
+  const float fb = (float)(2.0 * kPi * squares_uniform(ctr0 + pb + 1));
+  if ((j0 & 1ull) == 0) {
+    r0 = ra * cosf(fa); r1 = ra * sinf(fa); r2 = rb * cosf(fb);
+  } else {
+    r0 = ra * sinf(fa); r1 = rb * cosf(fb); r2 = rb * sinf(fb);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// climatological tropopause + weights (213-237, 8358-8376, 12748-12770)
+// ----------------------------------------------------------------------------------------------
+MPB_HD double tropopause_pressure(const ClimView &cl, double t, double lat) {
+  double sec = mod_trunc(t, kYear);
+  while (sec < 0) sec += kYear;
+  const int it = find_interval(cl.time, cl.ntime, 1, sec);
+  const double la0 = ldg(cl.lat), la1 = ldg(cl.lat + 1);
+  const int il = find_regular(la0, la1 - la0, cl.nlat, lat);
+  const double y0 = ldg(cl.lat + il), y1 = ldg(cl.lat + il + 1);
+  const double *row0 = cl.tropo + (size_t)it * cl.nlat + il;
+  const double *row1 = row0 + cl.nlat;
+  const double p0 = lin(y0, ldg(row0), y1, ldg(row0 + 1), lat);
+  const double p1 = lin(y0, ldg(row1), y1, ldg(row1 + 1), lat);
+  return lin(ldg(cl.time + it), p0, ldg(cl.time + it + 1), p1, sec);
+}
+
+MPB_HD double ramp_weight(double p_full, double p_none, double p) {
+  if (p > p_full) return 1;
+  if (p < p_none) return 0;
+  return lin(p_full, 1.0, p_none, 0.0, p);
+}
+
+MPB_HD double weight_pbl(const CtlView &c, double p, double pbl, double ps) {
+  return ramp_weight(pbl, pbl - c.pbl_trans * (ps - pbl), p);
+}
+
+MPB_HD double weight_tropo(double pt, double p) { return ramp_weight(pt / 0.866877899, pt * 0.866877899, p); }
+
+// ----------------------------------------------------------------------------------------------
+// module_diff_turb (4588-4734)
+// ----------------------------------------------------------------------------------------------
+MPB_HD void diffuse_turbulent(const MetView &g, const ClimView &cl, const CtlView &c, double dt,
+                              uint64_t ig, Parcel &a) {
+  double ps, pbl;
+  surface_at(g, a.time, a.lon, a.lat, ps, pbl);
+  if (c.pbl_scheme > 0 && a.p >= pbl) return;
+
+  const double ptop = ldg(g.p + g.nz - 1);
+  const bool latlon = (g.coord_type == 0);
+
+  double pt = tropopause_pressure(cl, a.time, latlon ? a.lat : c.utm_ref_lat);
+  const double wpbl = weight_pbl(c, a.p, pbl, ps);
+  const double wtrop = weight_tropo(pt, a.p) * (1.0 - wpbl);
+  const double wstrat = 1.0 - wpbl - wtrop;
+  const double Kx = wpbl * c.dx_pbl + wtrop * c.dx_trop + wstrat * c.dx_strat;
+  const double Kz = wpbl * c.dz_pbl + wtrop * c.dz_trop + wstrat * c.dz_strat;
+  const double dt_abs = fabs(dt);
+
+  double r0, r1, r2;
+  normals3(c.ctr_turb, ig, r0, r1, r2);
+
+  if (Kx > 0) {
+    const double sigma_h = sqrt(2.0 * Kx * dt_abs);
+    a.lon += dx2coord(g.coord_type, r0 * sigma_h, a.lat);
+    a.lat += dy2coord(g.coord_type, r1 * sigma_h);
+  }
+
+  if (Kz > 0) {
+    const double sigma_z = sqrt(2.0 * Kz * dt_abs) * 1e-3;
+    const double p_save = a.p;
+    const double eps_km = 0.01;
+    const double p_up = fmax(ptop, fmin(ps, p_save + dz2dp(eps_km, p_save)));
+    const double p_dn = fmax(ptop, fmin(ps, p_save + dz2dp(-eps_km, p_save)));
+
+    // the latitude may just have moved: the tropopause is looked up again (12753-12757)
+    if (latlon && Kx > 0) pt = tropopause_pressure(cl, a.time, a.lat);
+
+    const double wpbl_up = weight_pbl(c, p_up, pbl, ps);
+    const double wtrop_up = weight_tropo(pt, p_up) * (1.0 - wpbl_up);
+    const double wstrat_up = 1.0 - wpbl_up - wtrop_up;
+    const double Kz_up = wpbl_up * c.dz_pbl + wtrop_up * c.dz_trop + wstrat_up * c.dz_strat;
+
+    const double wpbl_dn = weight_pbl(c, p_dn, pbl, ps);
+    const double wtrop_dn = weight_tropo(pt, p_dn) * (1.0 - wpbl_dn);
+    const double wstrat_dn = 1.0 - wpbl_dn - wtrop_dn;
+    const double Kz_dn = wpbl_dn * c.dz_pbl + wtrop_dn * c.dz_trop + wstrat_dn * c.dz_strat;
+
+    const double dKz_dz = (Kz_up - Kz_dn) / (2.0 * eps_km * 1e3);
+    const double dlnrho_dz = -1.0 / (1e3 * kH0);
+    const double w_drift = dKz_dz + Kz * dlnrho_dz;
+    const double dz_drift = w_drift * dt_abs * 1e-3;
+    const double dz_tot = r2 * sigma_z + dz_drift;
+
+    double ptrial = p_save + dz2dp(dz_tot, p_save);
+    for (int iter = 0; iter < 10; iter++) {
+      if (ptrial > ps) ptrial = ps * ps / ptrial;
+      else if (ptrial < ptop) ptrial = ptop * ptop / ptrial;
+      else break;
+    }
+    a.p = fmax(ptop, fmin(ps, ptrial));
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// module_diff_meso (4266-4339)
+// ----------------------------------------------------------------------------------------------
+struct Moments {
+  float m, q;
+  MPB_HD void add(float x) { m = f_add(m, x); q = f_add(q, f_mul(x, x)); }
+  MPB_HD float sigma() const {
+    const float mean = m / 16.f;
+    const float var = f_sub(q / 16.f, f_mul(mean, mean));
+    return var > 0 ? sqrtf(var) : 0.f;
+  }
+};
+
+MPB_HD void diffuse_mesoscale(const MetView &g, const CtlView &c, double dt, uint64_t ig,
+                              Parcel &a, float &up, float &vp, float &wp) {
+  // raw index search at the parcel position: no wrap / clamp helper here (4283-4285)
+  Stencil s;
+  s.ix = find_regular(g.lon_first, g.lon_d, g.nx, a.lon);
+  s.iy = find_interval(g.lat, g.ny, g.lat_asc, a.lat);
+  s.iz = find_interval(g.p, g.nz, g.p_asc, a.p);
+
+  Cube c0, c1;
+  load_cube(g.f0, g, s, c0);
+  load_cube(g.f1, g, s, c1);
+  Moments mu = {0.f, 0.f}, mv = {0.f, 0.f}, mw = {0.f, 0.f};
+#define MPB_ACC(node)                                              \
+  mu.add(c0.node.x); mv.add(c0.node.y); mw.add(c0.node.z);         \
+  mu.add(c1.node.x); mv.add(c1.node.y); mw.add(c1.node.z);
+  MPB_ACC(n000) MPB_ACC(n001) MPB_ACC(n010) MPB_ACC(n011)
+  MPB_ACC(n100) MPB_ACC(n101) MPB_ACC(n110) MPB_ACC(n111)
+#undef MPB_ACC
+  const float usig = mu.sigma(), vsig = mv.sigma(), wsig = mw.sigma();
+
+  const double r = 1 - 2 * fabs(dt) / c.dt_met;
+  const double r2 = sqrt(1 - r * r);
+
+  double n0, n1, n2;
+  normals3(c.ctr_meso, ig, n0, n1, n2);
+
+  if (c.mesox > 0) {
+    up = (float)(r * up + r2 * n0 * c.mesox * usig);
+    a.lon += dx2coord(g.coord_type, up * dt, a.lat);
+    vp = (float)(r * vp + r2 * n1 * c.mesox * vsig);
+    a.lat += dy2coord(g.coord_type, vp * dt);
+  }
+  if (c.mesoz > 0) {
+    wp = (float)(r * wp + r2 * n2 * c.mesoz * wsig);
+    a.p += wp * dt;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// module_sedi + sedi (5859-5883, 12506-12535)
+// ----------------------------------------------------------------------------------------------
+MPB_HD double settling_velocity(double p, double T, double rp, double rhop) {
+  const double rp_m = rp * 1e-6;
+  const double rho = 100. * p / (kRA * T);
+  const double eta = 1.8325e-5 * (416.16 / (T + 120.)) * pow(T / 296.16, 1.5);
+  const double v = sqrt(8. * kKB * T / (kPi * kMAirMolecule));
+  const double lambda = 2. * eta / (rho * v);
+  const double K = lambda / rp_m;
+  const double G = 1. + K * (1.249 + 0.42 * exp(-0.87 / K));
+  return 2. * (rp_m * rp_m) * (rhop - rho) * kG0 / (9. * eta) * G;
+}
+
+MPB_HD void sediment(const MetView &g, double dt, double rp, double rhop, Parcel &a) {
+  const double T = temperature_at(g, a.time, a.lon, a.lat, a.p);
+  const double vs = settling_velocity(a.p, T, rp, rhop);
+  a.p += dz2dp(vs * dt / 1000., a.p);
+}
+
+// ----------------------------------------------------------------------------------------------
+// cell key of module_sort (5909-5919): raw index searches, no wrap
+// ----------------------------------------------------------------------------------------------
+MPB_HD int cell_key(const MetView &g, double lon, double lat, double p) {
+  const int ix = find_regular(g.lon_first, g.lon_d, g.nx, lon);
+  const int iy = find_interval(g.lat, g.ny, g.lat_asc, lat);
+  const int iz = find_interval(g.p, g.nz, g.p_asc, p);
+  return (ix * g.ny + iy) * g.nz + iz;
+}
+
+// altitude of a pressure (src/mptrac.h:2243)
+MPB_HD double altitude(double p) { return kH0 * log(kP0 / p); }
+
+// box index of module_mixing / write_grid (5201-5218, 13844-13860); -1 = outside
+MPB_HD int box_index(double time, double lon, double lat, double p, double t0, double t1,
+                     double lon0, double lon1, double lat0, double lat1, double z0, double z1,
+                     int nx, int ny, int nz) {
+  const double z = altitude(p);
+  if (time < t0 || time > t1 || lon < lon0 || lon >= lon1 || lat < lat0 || lat >= lat1 || z < z0 || z >= z1)
+    return -1;
+  const double dlon = (lon1 - lon0) / nx, dlat = (lat1 - lat0) / ny, dz = (z1 - z0) / nz;
+  const int ix = (int)((lon - lon0) / dlon);
+  const int iy = (int)((lat - lat0) / dlat);
+  const int iz = (int)((z - z0) / dz);
+  if (ix >= nx || iy >= ny || iz >= nz) return -1;
+  return (ix * ny + iy) * nz + iz;
+}
+
+}  // namespace mpb

@@ -1,0 +1,436 @@
+"""Host-side mirror of the reference interface for the time-step path (ctypes over the C ABI).
+
+Names follow the reference: :class:`Ctl` carries the ``ctl_t`` fields the path reads (defaults are the
+ones ``mptrac_read_ctl`` sets, src/mptrac.c:6723 ff.), :class:`Met` is one ``met_t`` time level,
+:class:`Engine` owns the device mirror of ``atm_t``/``cache_t``/``met_t`` and exposes
+``run_timestep`` (= ``mptrac_run_timestep``, src/mptrac.c:7851) and the single ``module_*`` calls.
+
+Nothing here computes: every method forwards to ``libmptrac_b200.so``.  If that library or a CUDA
+device is missing the constructor raises :class:`MpbError` -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+MIX_MAXQ = 23
+_LIBDIR = Path(__file__).resolve().parent / "_lib"
+
+
+class MpbError(RuntimeError):
+    pass
+
+
+class _CtlStruct(C.Structure):
+    _fields_ = (
+        [(n, C.c_int32) for n in (
+            "direction", "met_coord_type", "advect", "advect_vert_coord", "rng_type", "diffusion",
+            "turb_pbl_scheme", "nq", "qnt_rp", "qnt_rhop", "qnt_ens", "nens",
+            "mixing_nx", "mixing_ny", "mixing_nz", "n_mix_qnt")]
+        + [("mix_qnt", C.c_int32 * MIX_MAXQ), ("_pad", C.c_int32)]
+        + [(n, C.c_double) for n in (
+            "t_start", "t_stop", "dt_mod", "dt_met", "met_utm_ref_lat", "sort_dt",
+            "turb_dx_pbl", "turb_dx_trop", "turb_dx_strat", "turb_dz_pbl", "turb_dz_trop", "turb_dz_strat",
+            "turb_mesox", "turb_mesoz", "turb_pbl_trans",
+            "mixing_dt", "mixing_trop", "mixing_strat",
+            "mixing_lon0", "mixing_lon1", "mixing_lat0", "mixing_lat1", "mixing_z0", "mixing_z1")]
+    )
+
+
+class _MetViewStruct(C.Structure):
+    _fields_ = [
+        ("time", C.c_double),
+        ("coord_type", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("np", C.c_int32),
+        ("lon", C.c_void_p), ("lat", C.c_void_p), ("p", C.c_void_p),
+        ("u", C.c_void_p), ("v", C.c_void_p), ("w", C.c_void_p), ("t", C.c_void_p),
+        ("ps", C.c_void_p), ("pbl", C.c_void_p),
+        ("sx", C.c_int64), ("sy", C.c_int64), ("sx2", C.c_int64),
+    ]
+
+
+class _GridStruct(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("_pad", C.c_int32)] + [
+        (n, C.c_double) for n in ("lon0", "lon1", "lat0", "lat1", "z0", "z1", "t0", "t1")]
+
+
+@dataclass
+class Ctl:
+    """The ``ctl_t`` fields read on the path, with the reference defaults."""
+    direction: int = 1
+    met_coord_type: int = 0
+    advect: int = 2
+    advect_vert_coord: int = 0
+    rng_type: int = 1
+    diffusion: int = 0
+    turb_pbl_scheme: int = 0
+    nq: int = 0
+    qnt_rp: int = -1
+    qnt_rhop: int = -1
+    qnt_ens: int = -1
+    nens: int = 0
+    mixing_nx: int = 360
+    mixing_ny: int = 180
+    mixing_nz: int = 90
+    mix_qnt: Sequence[int] = field(default_factory=list)
+    t_start: float = 0.0
+    t_stop: float = 1e100
+    dt_mod: float = 180.0
+    dt_met: float = 3600.0
+    met_utm_ref_lat: float = 0.0
+    sort_dt: float = -999.0
+    turb_dx_pbl: float = 50.0
+    turb_dx_trop: float = 50.0
+    turb_dx_strat: float = 0.0
+    turb_dz_pbl: float = 0.0
+    turb_dz_trop: float = 0.0
+    turb_dz_strat: float = 0.1
+    turb_mesox: float = 0.16
+    turb_mesoz: float = 0.16
+    turb_pbl_trans: float = 0.0
+    mixing_dt: float = 3600.0
+    mixing_trop: float = -999.0
+    mixing_strat: float = -999.0
+    mixing_lon0: float = -180.0
+    mixing_lon1: float = 180.0
+    mixing_lat0: float = -90.0
+    mixing_lat1: float = 90.0
+    mixing_z0: float = -5.0
+    mixing_z1: float = 85.0
+
+    def to_struct(self) -> _CtlStruct:
+        s = _CtlStruct()
+        for name, _ in _CtlStruct._fields_:
+            if name in ("mix_qnt", "_pad", "n_mix_qnt"):
+                continue
+            setattr(s, name, getattr(self, name))
+        mq = list(self.mix_qnt)
+        if len(mq) > MIX_MAXQ:
+            raise ValueError("too many mixing quantities")
+        s.n_mix_qnt = len(mq)
+        for i, v in enumerate(mq):
+            s.mix_qnt[i] = int(v)
+        return s
+
+
+@dataclass
+class Met:
+    """One met_t time level as dense host arrays: 3-D fields [nx][ny][np] float32, 2-D [nx][ny]."""
+    time: float
+    lon: np.ndarray
+    lat: np.ndarray
+    p: np.ndarray
+    u: np.ndarray
+    v: np.ndarray
+    w: np.ndarray
+    t: Optional[np.ndarray] = None
+    ps: Optional[np.ndarray] = None
+    pbl: Optional[np.ndarray] = None
+    coord_type: int = 0
+
+    def __post_init__(self):
+        self.lon = np.ascontiguousarray(self.lon, dtype=np.float64)
+        self.lat = np.ascontiguousarray(self.lat, dtype=np.float64)
+        self.p = np.ascontiguousarray(self.p, dtype=np.float64)
+        shp3 = (self.lon.size, self.lat.size, self.p.size)
+        for n in ("u", "v", "w", "t"):
+            a = getattr(self, n)
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                if a.shape != shp3:
+                    raise ValueError(f"met field {n} has shape {a.shape}, expected {shp3}")
+                setattr(self, n, a)
+        for n in ("ps", "pbl"):
+            a = getattr(self, n)
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                if a.shape != shp3[:2]:
+                    raise ValueError(f"met field {n} has shape {a.shape}, expected {shp3[:2]}")
+                setattr(self, n, a)
+
+    def view(self) -> _MetViewStruct:
+        nx, ny, nz = self.lon.size, self.lat.size, self.p.size
+        s = _MetViewStruct()
+        s.time = float(self.time)
+        s.coord_type, s.nx, s.ny, s.np = int(self.coord_type), nx, ny, nz
+        for n in ("lon", "lat", "p", "u", "v", "w", "t", "ps", "pbl"):
+            a = getattr(self, n)
+            setattr(s, n, a.ctypes.data if a is not None else None)
+        s.sx, s.sy, s.sx2 = ny * nz, nz, ny
+        return s
+
+
+_lib_cache = {}
+
+
+def load_library(strict: bool = False) -> C.CDLL:
+    """dlopen the in-tree C-ABI library (``strict`` = the -fmad=false build used for tight parity)."""
+    name = "libmptrac_b200_strict.so" if strict else "libmptrac_b200.so"
+    if name in _lib_cache:
+        return _lib_cache[name]
+    path = Path(os.environ.get("MPTRAC_B200_LIBDIR", _LIBDIR)) / name
+    if not path.exists():
+        raise MpbError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    lib = C.CDLL(str(path))
+    vp, i32, i64, u64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
+    P = C.POINTER
+    sig = {
+        "mpb_last_error": (C.c_char_p, []),
+        "mpb_abi_version": (i32, []),
+        "mpb_device_count": (i32, []),
+        "mpb_create": (i32, [P(vp), i32, i64, i32]),
+        "mpb_destroy": (i32, [vp]),
+        "mpb_set_stream": (i32, [vp, vp]),
+        "mpb_sync": (i32, [vp]),
+        "mpb_set_ctl": (i32, [vp, P(_CtlStruct)]),
+        "mpb_set_clim_tropo": (i32, [vp, i32, i32, vp, vp, vp]),
+        "mpb_set_met": (i32, [vp, i32, P(_MetViewStruct)]),
+        "mpb_swap_met": (i32, [vp]),
+        "mpb_set_atm": (i32, [vp, i64, vp, vp, vp, vp, vp, i64]),
+        "mpb_set_uvwp": (i32, [vp, vp]),
+        "mpb_get_atm": (i32, [vp, vp, vp, vp, vp, vp, i64]),
+        "mpb_get_uvwp": (i32, [vp, vp]),
+        "mpb_get_dt": (i32, [vp, vp]),
+        "mpb_get_np": (i64, [vp]),
+        "mpb_set_shard": (i32, [vp, i64, i64]),
+        "mpb_set_rng_ctr": (i32, [vp, u64]),
+        "mpb_get_rng_ctr": (u64, [vp]),
+        "mpb_run_timestep": (i32, [vp, dbl]),
+        "mpb_module_timesteps": (i32, [vp, dbl]),
+        "mpb_module_position": (i32, [vp]),
+        "mpb_module_advect": (i32, [vp]),
+        "mpb_module_diff_turb": (i32, [vp]),
+        "mpb_module_diff_meso": (i32, [vp]),
+        "mpb_module_sedi": (i32, [vp]),
+        "mpb_module_sort": (i32, [vp]),
+        "mpb_module_mixing": (i32, [vp, dbl]),
+        "mpb_module_rng": (i32, [vp, vp, i64, i32]),
+        "mpb_mixing_begin": (i32, [vp, dbl]),
+        "mpb_mixing_accumulate": (i32, [vp, i32]),
+        "mpb_mixing_apply": (i32, [vp, i32]),
+        "mpb_mixing_nbox": (i64, [vp]),
+        "mpb_grid_accumulate": (i32, [vp, P(_GridStruct)]),
+        "mpb_grid_fetch": (i32, [vp, vp, vp, vp]),
+        "mpb_device_ptr": (vp, [vp, C.c_char_p]),
+        "mpb_launch_count": (i64, [vp]),
+        "mpb_met_bytes": (i32, [vp, P(i64)]),
+    }
+    for fn, (res, args) in sig.items():
+        f = getattr(lib, fn)   # AttributeError here = the library does not export what the header declares
+        f.restype, f.argtypes = res, args
+    lib._mpb_symbols = tuple(sig)
+    _lib_cache[name] = lib
+    return lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class Engine:
+    """Device mirror of one simulation's ``atm_t`` / ``cache_t`` / ``met_t`` pair (one per GPU)."""
+
+    def __init__(self, np_max: int, nq: int = 0, device: int = 0, strict: bool = False):
+        self._lib = load_library(strict)
+        self._h = C.c_void_p()
+        self.nq = int(nq)
+        self.np_max = int(np_max)
+        rc = self._lib.mpb_create(C.byref(self._h), int(device), int(np_max), int(nq))
+        if rc:
+            self._h = C.c_void_p()
+            raise MpbError(self._lib.mpb_last_error().decode())
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _ck(self, rc: int):
+        if rc:
+            raise MpbError(self._lib.mpb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.mpb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self._lib.mpb_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self._ck(self._lib.mpb_sync(self._h))
+
+    # -- update_device --------------------------------------------------------------------------
+    def set_ctl(self, ctl: Ctl):
+        if ctl.nq != self.nq:
+            raise ValueError("ctl.nq must equal the engine's nq")
+        s = ctl.to_struct()
+        self._ck(self._lib.mpb_set_ctl(self._h, C.byref(s)))
+        self.ctl = ctl
+
+    def set_clim_tropo(self, time: np.ndarray, lat: np.ndarray, tropo: np.ndarray):
+        time = np.ascontiguousarray(time, np.float64)
+        lat = np.ascontiguousarray(lat, np.float64)
+        tropo = np.ascontiguousarray(tropo, np.float64)
+        if tropo.shape != (time.size, lat.size):
+            raise ValueError("tropo must be [ntime][nlat]")
+        self._ck(self._lib.mpb_set_clim_tropo(self._h, time.size, lat.size, _ptr(time), _ptr(lat), _ptr(tropo)))
+
+    def set_met(self, slot: int, met: Met):
+        v = met.view()
+        self._ck(self._lib.mpb_set_met(self._h, int(slot), C.byref(v)))
+
+    def swap_met(self):
+        self._ck(self._lib.mpb_swap_met(self._h))
+
+    def set_atm(self, time, p, lon, lat, q: Optional[np.ndarray] = None):
+        """Upload parcels.  Arrays may be pinned torch-backed numpy views; q is [nq][np]."""
+        arrs = [np.ascontiguousarray(a, np.float64) for a in (time, p, lon, lat)]
+        n = arrs[0].size
+        if any(a.size != n for a in arrs):
+            raise ValueError("ragged parcel arrays")
+        stride = 0
+        if self.nq:
+            if q is None:
+                raise ValueError("q is required when nq > 0")
+            q = np.asarray(q, np.float64)
+            if q.ndim != 2 or q.shape[0] != self.nq or q.shape[1] < n or q.strides[1] != 8:
+                raise ValueError("q must be [nq][>=np] float64 with contiguous rows")
+            stride = q.strides[0] // 8
+        self._keep = (arrs, q)
+        self._ck(self._lib.mpb_set_atm(self._h, n, *[_ptr(a) for a in arrs], _ptr(q) if self.nq else None, stride))
+
+    def set_uvwp(self, uvwp: np.ndarray):
+        uvwp = np.ascontiguousarray(uvwp, np.float32)
+        if uvwp.shape != (self.np, 3):
+            raise ValueError("uvwp must be [np][3]")
+        self._ck(self._lib.mpb_set_uvwp(self._h, _ptr(uvwp)))
+        self.sync()
+
+    def set_shard(self, global_offset: int, global_np: int):
+        self._ck(self._lib.mpb_set_shard(self._h, int(global_offset), int(global_np)))
+
+    # -- update_host ----------------------------------------------------------------------------
+    @property
+    def np(self) -> int:
+        return int(self._lib.mpb_get_np(self._h))
+
+    def get_atm(self, out=None):
+        """Download parcels -> dict(time, p, lon, lat, q).  ``out`` may hold preallocated (pinned) arrays."""
+        n = self.np
+        if out is None:
+            out = {k: np.empty(n, np.float64) for k in ("time", "p", "lon", "lat")}
+            out["q"] = np.empty((self.nq, n), np.float64)
+        q = out.get("q")
+        stride = q.strides[0] // 8 if (q is not None and self.nq) else 0
+        self._ck(self._lib.mpb_get_atm(self._h, _ptr(out["time"]), _ptr(out["p"]), _ptr(out["lon"]), _ptr(out["lat"]),
+                                       _ptr(q) if self.nq else None, stride))
+        return out
+
+    def get_uvwp(self) -> np.ndarray:
+        a = np.empty((self.np, 3), np.float32)
+        self._ck(self._lib.mpb_get_uvwp(self._h, _ptr(a)))
+        return a
+
+    def get_dt(self) -> np.ndarray:
+        a = np.empty(self.np, np.float64)
+        self._ck(self._lib.mpb_get_dt(self._h, _ptr(a)))
+        return a
+
+    # -- rng ------------------------------------------------------------------------------------
+    @property
+    def rng_ctr(self) -> int:
+        return int(self._lib.mpb_get_rng_ctr(self._h))
+
+    @rng_ctr.setter
+    def rng_ctr(self, v: int):
+        self._ck(self._lib.mpb_set_rng_ctr(self._h, int(v)))
+
+    def module_rng(self, n: int, method: int) -> np.ndarray:
+        rs = np.empty(n + 1, np.float64)
+        self._ck(self._lib.mpb_module_rng(self._h, _ptr(rs), int(n), int(method)))
+        return rs
+
+    # -- the step -------------------------------------------------------------------------------
+    def run_timestep(self, t: float):
+        self._ck(self._lib.mpb_run_timestep(self._h, float(t)))
+
+    def module_timesteps(self, t: float):
+        self._ck(self._lib.mpb_module_timesteps(self._h, float(t)))
+
+    def module_position(self):
+        self._ck(self._lib.mpb_module_position(self._h))
+
+    def module_advect(self):
+        self._ck(self._lib.mpb_module_advect(self._h))
+
+    def module_diff_turb(self):
+        self._ck(self._lib.mpb_module_diff_turb(self._h))
+
+    def module_diff_meso(self):
+        self._ck(self._lib.mpb_module_diff_meso(self._h))
+
+    def module_sedi(self):
+        self._ck(self._lib.mpb_module_sedi(self._h))
+
+    def module_sort(self):
+        self._ck(self._lib.mpb_module_sort(self._h))
+
+    def module_mixing(self, t: float):
+        self._ck(self._lib.mpb_module_mixing(self._h, float(t)))
+
+    def mixing_begin(self, t: float):
+        self._ck(self._lib.mpb_mixing_begin(self._h, float(t)))
+
+    def mixing_accumulate(self, iq: int):
+        self._ck(self._lib.mpb_mixing_accumulate(self._h, int(iq)))
+
+    def mixing_apply(self, iq: int):
+        self._ck(self._lib.mpb_mixing_apply(self._h, int(iq)))
+
+    @property
+    def mixing_nbox(self) -> int:
+        return int(self._lib.mpb_mixing_nbox(self._h))
+
+    def grid_accumulate(self, nx, ny, nz, lon0, lon1, lat0, lat1, z0, z1, t0, t1):
+        g = _GridStruct(nx, ny, nz, 0, lon0, lon1, lat0, lat1, z0, z1, t0, t1)
+        self._ck(self._lib.mpb_grid_accumulate(self._h, C.byref(g)))
+        self._grid_nbox = nx * ny * nz
+
+    def grid_fetch(self):
+        nb = self._grid_nbox
+        cnt = np.empty(nb, np.int32)
+        s = np.empty((self.nq, nb), np.float64)
+        sq = np.empty((self.nq, nb), np.float64)
+        self._ck(self._lib.mpb_grid_fetch(self._h, _ptr(cnt), _ptr(s), _ptr(sq)))
+        return cnt, s, sq
+
+    # -- introspection --------------------------------------------------------------------------
+    def device_ptr(self, name: str) -> int:
+        p = self._lib.mpb_device_ptr(self._h, name.encode())
+        if not p:
+            raise MpbError(f"no device array named {name!r}")
+        return int(p)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mpb_launch_count(self._h))
+
+    @property
+    def met_bytes(self) -> int:
+        b = C.c_int64()
+        self._ck(self._lib.mpb_met_bytes(self._h, C.byref(b)))
+        return int(b.value)

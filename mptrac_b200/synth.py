@@ -1,0 +1,83 @@
+"""Synthetic inputs of the shapes BASELINE.json names: ERA5-shaped met grids and parcel clouds.
+
+Pure data generation (numpy): no model physics lives here.  The met fields are smooth analytic
+functions (a zonal jet with planetary waves, a meridional overturning, a standard-atmosphere
+temperature profile, undulating surface / boundary-layer pressures) plus a deterministic small-scale
+hash perturbation so that the 16-point wind standard deviation of the mesoscale module is not zero.
+Longitudes run 0..360 with the periodic wrap column appended (what read_met_periodic produces,
+src/mptrac.c:11714-11771); latitude order is selectable because ERA files run north->south.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .host import Met
+
+H0 = 7.0
+P0 = 1013.25
+
+
+def _hash_noise(shape, seed):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal(shape, dtype=np.float32)
+
+
+def make_met(nlon=360, nlat=181, nlev=60, time=0.0, phase=0.0, ztop=60.0, lat_descending=False, seed=1,
+             noise=0.5) -> Met:
+    """One met time level on a (nlon+1) x nlat x nlev grid; `phase` shifts the wave pattern (radians)."""
+    lon = np.linspace(0.0, 360.0, nlon + 1)
+    lat = np.linspace(-90.0, 90.0, nlat)
+    if lat_descending:
+        lat = lat[::-1].copy()
+    z = np.linspace(0.0, ztop, nlev)
+    p = P0 * np.exp(-z / H0)
+    lam = np.deg2rad(lon)[:, None, None]
+    phi = np.deg2rad(lat)[None, :, None]
+    zz = z[None, None, :]
+    jet = np.exp(-((zz - 11.0) / 6.0) ** 2)
+    u = (10.0 + 35.0 * jet) * np.cos(phi) * (1.0 + 0.3 * np.sin(3 * lam + phase)) + 5.0 * np.sin(2 * phi)
+    v = 8.0 * np.cos(phi) * np.sin(2 * lam + phase) * (0.3 + jet)
+    w = 0.02 * np.sin(lam + phase) * np.cos(2 * phi) * np.sin(np.pi * zz / ztop) * (p[None, None, :] / P0 + 0.05)
+    t = np.where(zz < 11.0, 288.15 - 6.5 * zz, 216.65 + 1.0 * np.maximum(zz - 20.0, 0.0)) + 3.0 * np.cos(lam) * np.cos(phi)
+    u, v, w, t = (np.broadcast_to(a, (nlon + 1, nlat, nlev)).astype(np.float32) for a in (u, v, w, t))
+    if noise > 0:
+        u = u + noise * _hash_noise(u.shape, seed)
+        v = v + noise * _hash_noise(v.shape, seed + 1)
+        w = w + 1e-3 * noise * _hash_noise(w.shape, seed + 2)
+    lam2, phi2 = lam[:, :, 0], phi[:, :, 0]
+    ps = 985.0 + 25.0 * np.sin(2 * lam2 + phase) * np.cos(phi2) - 60.0 * np.exp(-((phi2 - 0.6) / 0.3) ** 2) * (1 + np.cos(lam2))
+    pbl = ps - 60.0 - 40.0 * np.cos(phi2) * (1.0 + 0.5 * np.cos(lam2 + phase))
+    ps = np.broadcast_to(ps, (nlon + 1, nlat)).astype(np.float32)
+    pbl = np.broadcast_to(pbl, (nlon + 1, nlat)).astype(np.float32)
+    out = [np.array(a) for a in (u, v, w, t)]
+    for a in out:            # periodic wrap column = column 0
+        a[-1] = a[0]
+    ps, pbl = np.array(ps), np.array(pbl)
+    ps[-1], pbl[-1] = ps[0], pbl[0]
+    return Met(time=time, lon=lon, lat=lat, p=p, u=out[0], v=out[1], w=out[2], t=out[3], ps=ps, pbl=pbl, coord_type=0)
+
+
+def make_met_pair(nlon=360, nlat=181, nlev=60, t0=0.0, dt_met=21600.0, **kw):
+    m0 = make_met(nlon, nlat, nlev, time=t0, phase=0.0, seed=1, **kw)
+    m1 = make_met(nlon, nlat, nlev, time=t0 + dt_met, phase=0.35, seed=11, **kw)
+    return m0, m1
+
+
+def make_parcels(n, t0=0.0, seed=123, zmin=1.0, zmax=30.0):
+    """Parcels uniform on the sphere and in log-pressure height: time, p, lon, lat."""
+    rng = np.random.default_rng(seed)
+    lon = rng.uniform(-180.0, 180.0, n)
+    lat = np.rad2deg(np.arcsin(rng.uniform(-1.0, 1.0, n)))
+    z = rng.uniform(zmin, zmax, n)
+    p = P0 * np.exp(-z / H0)
+    time = np.full(n, float(t0))
+    return time, p, lon, lat
+
+
+def make_clim_tropo():
+    """A smooth stand-in for the tropopause climatology table ([12 months][73 latitudes], hPa)."""
+    time = (np.arange(12) + 0.5) * (365.25 * 86400.0 / 12.0)
+    lat = np.linspace(-90.0, 90.0, 73)
+    season = np.cos(2 * np.pi * (time[:, None] / (365.25 * 86400.0)))
+    tropo = 300.0 - 200.0 * np.exp(-(lat[None, :] / 35.0) ** 2) + 15.0 * season * np.sin(np.deg2rad(lat))[None, :]
+    return time, lat, np.ascontiguousarray(tropo)

@@ -1,0 +1,605 @@
+/*
+ * mptrac_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see mptrac_oracle.h).
+ *
+ * CPU restatement of the time-step path of slcs-jsc/mptrac.  Every function names the reference
+ * lines (src/mptrac.c unless noted) whose behaviour it restates.  It is organised like the
+ * reference -- one pass over all parcels per module, a materialised random-number array, a dt
+ * array -- which is deliberately NOT how the CUDA engine is organised (one fused kernel, in-register
+ * counters), so the two are independent statements of the same arithmetic.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared  (no FMA contraction: the reference's
+ * x86-64 build has none either).
+ */
+#include "mptrac_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* constants, src/mptrac.h:265-340 */
+#define C_G0 9.80665
+#define C_H0 7.0
+#define C_KB 1.3806504e-23
+#define C_MA 28.9644
+#define C_P0 1013.25
+#define C_RI 8.3144598
+#define C_RA (1e3 * C_RI / C_MA)
+#define C_RE 6367.421
+#define C_MAIR 4.8096e-26
+
+/* ---------------------------------------------------------------------------------------------
+ * scalar helpers
+ * ------------------------------------------------------------------------------------------- */
+
+/* FMOD macro, src/mptrac.h:1121: quotient truncated through an int cast */
+static double tmod(double x, double y) { return x - (int)(x / y) * y; }
+
+/* LIN macro, src/mptrac.h:1351 */
+static double linear(double x0, double y0, double x1, double y1, double x) {
+  return y0 + (y1 - y0) / (x1 - x0) * (x - x0);
+}
+
+/* DZ2DP, src/mptrac.h:941 */
+static double km2hpa(double dz, double p) { return -dz * p / C_H0; }
+
+/* DX2COORD / DX2DEG, src/mptrac.h:904-906, 966 */
+static double east_m_to_coord(int coord_type, double dx, double lat) {
+  if (coord_type != 0) return dx;
+  const double km = dx / 1000.0;
+  if (lat < -89.999 || lat > 89.999) return 0;
+  return km * 180. / (M_PI * C_RE * cos(lat * (M_PI / 180.0)));
+}
+
+/* DY2COORD / DY2DEG, src/mptrac.h:922-923, 989 */
+static double north_m_to_coord(int coord_type, double dy) {
+  if (coord_type != 0) return dy;
+  return (dy / 1000.0) * 180. / (M_PI * C_RE);
+}
+
+/* locate_irr, 3495-3521 */
+static int bisect(const double *xx, int n, double x) {
+  int lo = 0, hi = n - 1;
+  const int m = (hi + lo) >> 1;
+  if (xx[m] < xx[m + 1]) {
+    while (hi > lo + 1) {
+      const int i = (hi + lo) >> 1;
+      if (xx[i] > x) hi = i; else lo = i;
+    }
+  } else {
+    while (hi > lo + 1) {
+      const int i = (hi + lo) >> 1;
+      if (xx[i] <= x) hi = i; else lo = i;
+    }
+  }
+  return lo;
+}
+
+/* locate_reg, 3559-3574 */
+static int regular_index(const double *xx, int n, double x) {
+  const int i = (int)((x - xx[0]) / (xx[1] - xx[0]));
+  if (i < 0) return 0;
+  if (i > n - 2) return n - 2;
+  return i;
+}
+
+static double clampd(double x, double a, double b) {  /* MIN(MAX(x, lo), hi) with lo = min(a, b) */
+  const double lo = a < b ? a : b, hi = a < b ? b : a;
+  double r = x > lo ? x : lo;
+  return r < hi ? r : hi;
+}
+
+/* intpol_check_lon_lat / intpol_check_cartesian, 2755-2803 */
+static void horizontal_check(const orc_met_t *m, double lon, double lat, double *lon2, double *lat2) {
+  if (m->coord_type == 0) {
+    double l = tmod(lon, 360.);
+    if (l < m->lon[0]) l += 360;
+    else if (l > m->lon[m->nx - 1]) l -= 360;
+    *lon2 = l;
+  } else {
+    *lon2 = clampd(lon, m->lon[0], m->lon[m->nx - 1]);
+  }
+  *lat2 = clampd(lat, m->lat[0], m->lat[m->ny - 1]);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * interpolation; the cache (ci, cw) of the reference becomes an explicit struct
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int ip, ix, iy;        /* ci[0], ci[1], ci[2] */
+  double wp, wx, wy;     /* cw[0], cw[1], cw[2]: weight of the lower-index node */
+} cell_t;
+
+static const cell_t CELL_ZERO = {0, 0, 0, 0.0, 0.0, 0.0};  /* INTPOL_INIT, src/mptrac.h:1174 */
+
+static size_t at3(const orc_met_t *m, int ix, int iy, int ip) {
+  return ((size_t)ix * (size_t)m->ny + (size_t)iy) * (size_t)m->np + (size_t)ip;
+}
+static size_t at2(const orc_met_t *m, int ix, int iy) { return (size_t)ix * (size_t)m->ny + (size_t)iy; }
+
+/* the init part of intpol_met_space_3d / _2d, 2997-3021 and 3061-3078 */
+static void locate_cell(const orc_met_t *m, int with_p, double p, double lon, double lat, cell_t *c) {
+  double lon2, lat2;
+  horizontal_check(m, lon, lat, &lon2, &lat2);
+  if (with_p) {
+    c->ip = bisect(m->p, m->np, p);
+    c->wp = (m->p[c->ip + 1] - p) / (m->p[c->ip + 1] - m->p[c->ip]);
+  }
+  c->ix = regular_index(m->lon, m->nx, lon2);
+  c->iy = bisect(m->lat, m->ny, lat2);
+  c->wx = (m->lon[c->ix + 1] - lon2) / (m->lon[c->ix + 1] - m->lon[c->ix]);
+  c->wy = (m->lat[c->iy + 1] - lat2) / (m->lat[c->iy + 1] - m->lat[c->iy]);
+}
+
+/* vertical leg: the difference is taken in float before promotion, 3023-3038 */
+static double column_value(const orc_met_t *m, const float *f, const cell_t *c, int dx, int dy) {
+  const float lo = f[at3(m, c->ix + dx, c->iy + dy, c->ip)];
+  const float hi = f[at3(m, c->ix + dx, c->iy + dy, c->ip + 1)];
+  return c->wp * (lo - hi) + hi;
+}
+
+/* intpol_met_space_3d body, 3023-3043 */
+static double space3(const orc_met_t *m, const float *f, const cell_t *c) {
+  const double v00 = column_value(m, f, c, 0, 0), v01 = column_value(m, f, c, 0, 1);
+  const double v10 = column_value(m, f, c, 1, 0), v11 = column_value(m, f, c, 1, 1);
+  const double a0 = c->wy * (v00 - v01) + v01;
+  const double a1 = c->wy * (v10 - v11) + v11;
+  return c->wx * (a0 - a1) + a1;
+}
+
+/* intpol_met_space_2d body, 3080-3107 */
+static double space2(const orc_met_t *m, const float *f, const cell_t *c) {
+  const double v00 = f[at2(m, c->ix, c->iy)], v01 = f[at2(m, c->ix, c->iy + 1)];
+  const double v10 = f[at2(m, c->ix + 1, c->iy)], v11 = f[at2(m, c->ix + 1, c->iy + 1)];
+  if (isfinite(v00) && isfinite(v01) && isfinite(v10) && isfinite(v11)) {
+    const double a0 = c->wy * (v00 - v01) + v01;
+    const double a1 = c->wy * (v10 - v11) + v11;
+    return c->wx * (a0 - a1) + a1;
+  }
+  if (c->wy < 0.5) return c->wx < 0.5 ? v11 : v01;
+  return c->wx < 0.5 ? v10 : v00;
+}
+
+/* intpol_met_time_3d, 3112-3137 (init: locate on met0, reuse for met1) */
+static double time3(const orc_met_t *m0, const float *f0, const orc_met_t *m1, const float *f1, double ts,
+                    double p, double lon, double lat, cell_t *c, int init) {
+  if (init) locate_cell(m0, 1, p, lon, lat, c);
+  const double a = space3(m0, f0, c), b = space3(m1, f1, c);
+  const double wt = (m1->time - ts) / (m1->time - m0->time);
+  return wt * (a - b) + b;
+}
+
+/* intpol_met_time_2d, 3141-3170 */
+static double time2(const orc_met_t *m0, const float *f0, const orc_met_t *m1, const float *f1, double ts,
+                    double lon, double lat, cell_t *c, int init) {
+  if (init) locate_cell(m0, 0, 0.0, lon, lat, c);
+  const double a = space2(m0, f0, c), b = space2(m1, f1, c);
+  const double wt = (m1->time - ts) / (m1->time - m0->time);
+  if (isfinite(a) && isfinite(b)) return wt * (a - b) + b;
+  return wt < 0.5 ? b : a;
+}
+
+void orc_intpol_met_time_3d(const orc_met_t *met0, const orc_met_t *met1, const float *f0, const float *f1,
+                            double ts, double p, double lon, double lat, double *var) {
+  cell_t c = CELL_ZERO;
+  *var = time3(met0, f0, met1, f1, ts, p, lon, lat, &c, 1);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * module_timesteps, 5999-6042
+ * ------------------------------------------------------------------------------------------- */
+void orc_module_timesteps(const orc_ctl_t *ctl, const orc_met_t *met0, orc_atm_t *atm, double t) {
+  double latmin = met0->lat[0], latmax = met0->lat[0];
+  for (int i = 1; i < met0->ny; i++) {
+    if (met0->lat[i] < latmin) latmin = met0->lat[i];
+    if (met0->lat[i] > latmax) latmax = met0->lat[i];
+  }
+  const int local = fabs(met0->lon[met0->nx - 1] - met0->lon[0] - 360.0) >= 0.01;
+  const double lon_w = met0->lon[0], lon_e = met0->lon[met0->nx - 1];
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    const double tp = atm->time[ip];
+    const int active = ctl->direction * (tp - ctl->t_start) >= 0 && ctl->direction * (tp - ctl->t_stop) <= 0 &&
+                       ctl->direction * (tp - t) < 0;
+    double dt = active ? t - tp : 0.0;
+    if (local && (atm->lon[ip] <= lon_w || atm->lon[ip] >= lon_e || atm->lat[ip] <= latmin || atm->lat[ip] >= latmax))
+      dt = 0.0;
+    atm->dt[ip] = dt;
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * module_position, 5435-5489.  The surface-pressure lookup at 5483 runs with init = 0 on a freshly
+ * zeroed cache, i.e. on cell (0,0) with zero weights: it yields node [1][1].  Restated as written.
+ * ------------------------------------------------------------------------------------------- */
+void orc_module_position(const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm) {
+  const double ptop = met0->p[met0->np - 1];
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    if (atm->dt[ip] == 0) continue;
+    double lon = atm->lon[ip], lat = atm->lat[ip], p = atm->p[ip];
+    if (met0->coord_type == 0) {
+      lon = tmod(lon, 360.);
+      lat = tmod(lat, 360.);
+      while (lat < -90 || lat > 90) {
+        if (lat > 90) { lat = 180 - lat; lon += 180; }
+        if (lat < -90) { lat = -180 - lat; lon += 180; }
+      }
+      while (lon < -180) lon += 360;
+      while (lon >= 180) lon -= 360;
+    } else {
+      const double x = clampd(lon, met0->lon[0], met0->lon[met0->nx - 1]);
+      const double y = clampd(lat, met0->lat[0], met0->lat[met0->ny - 1]);
+      lon = x; lat = y;
+    }
+    if (p < ptop) {
+      p = ptop * ptop / p;
+    } else if (p > 300.) {
+      cell_t c = CELL_ZERO;
+      const double ps = time2(met0, met0->ps, met1, met1->ps, atm->time[ip], lon, lat, &c, 0);
+      if (p > ps) p = ps * ps / p;
+    }
+    atm->lon[ip] = lon; atm->lat[ip] = lat; atm->p[ip] = p;
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * module_advect, pressure-level branch, 3612-3677
+ * ------------------------------------------------------------------------------------------- */
+void orc_module_advect(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm) {
+  const int n = ctl->advect, ct = met0->coord_type;
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    const double dt = atm->dt[ip];
+    if (dt == 0) continue;
+    const double lon0 = atm->lon[ip], lat0 = atm->lat[ip], p0 = atm->p[ip], t0 = atm->time[ip];
+    double u[4], v[4], w[4], um = 0, vm = 0, wm = 0, pos[3] = {0, 0, 0};
+    for (int i = 0; i < n; i++) {
+      double dts = 0.0;
+      if (i == 0) {
+        pos[0] = lon0; pos[1] = lat0; pos[2] = p0;
+      } else {
+        dts = (i == 3 ? 1.0 : 0.5) * dt;
+        pos[0] = lon0 + east_m_to_coord(ct, dts * u[i - 1], lat0);
+        pos[1] = lat0 + north_m_to_coord(ct, dts * v[i - 1]);
+        pos[2] = p0 + dts * w[i - 1];
+      }
+      const double tm = t0 + dts;
+      cell_t c = CELL_ZERO;
+      u[i] = time3(met0, met0->u, met1, met1->u, tm, pos[2], pos[0], pos[1], &c, 1);
+      v[i] = time3(met0, met0->v, met1, met1->v, tm, pos[2], pos[0], pos[1], &c, 0);
+      w[i] = time3(met0, met0->w, met1, met1->w, tm, pos[2], pos[0], pos[1], &c, 0);
+      double k = 1.0;
+      if (n == 2) k = (i == 0 ? 0.0 : 1.0);
+      else if (n == 4) k = (i == 0 || i == 3 ? 1.0 / 6.0 : 2.0 / 6.0);
+      um += k * u[i]; vm += k * v[i]; wm += k * w[i];
+    }
+    atm->time[ip] = t0 + dt;
+    atm->lon[ip] = lon0 + east_m_to_coord(ct, dt * um, n == 2 ? pos[1] : lat0);
+    atm->lat[ip] = lat0 + north_m_to_coord(ct, dt * vm);
+    atm->p[ip] = p0 + dt * wm;
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * module_rng, Squares branch, 5784-5828 (Widynski's squares64 with the reference's fixed key)
+ * ------------------------------------------------------------------------------------------- */
+static uint64_t rot32(uint64_t x) { return (x >> 32) | (x << 32); }
+
+static double squares_u01(uint64_t counter) {
+  const uint64_t key = 0xc8e4fd154ce32f6dULL;
+  uint64_t y = counter * key, z = y + key, x = y, t;
+  x = rot32(x * x + y);
+  x = rot32(x * x + z);
+  x = rot32(x * x + y);
+  t = x = x * x + z;
+  x = rot32(x);
+  return (double)(t ^ ((x * x + y) >> 32)) / (double)UINT64_MAX;
+}
+
+void orc_module_rng(double *rs, int64_t n, int method, uint64_t *ctr) {
+#pragma omp parallel for
+  for (int64_t i = 0; i < n + 1; i++) rs[i] = squares_u01(*ctr + (uint64_t)i);
+  *ctr += (uint64_t)n + 1;
+  if (method == 1) {
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; i += 2) {
+      const double r = sqrt(-2.0 * log(rs[i]));
+      const double phi = 2.0 * M_PI * rs[i + 1];
+      rs[i] = r * cosf((float)phi);
+      rs[i + 1] = r * sinf((float)phi);
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * clim_tropo 213-237, pbl_weight 8358-8376, tropo_weight 12748-12770
+ * ------------------------------------------------------------------------------------------- */
+double orc_clim_tropo(const orc_clim_t *cl, double t, double lat) {
+  const double year = 365.25 * 86400.;
+  double sec = tmod(t, year);
+  while (sec < 0) sec += year;
+  const int it = bisect(cl->time, cl->ntime, sec);
+  const int il = regular_index(cl->lat, cl->nlat, lat);
+  const double *r0 = cl->tropo + (size_t)it * cl->nlat, *r1 = r0 + cl->nlat;
+  const double a = linear(cl->lat[il], r0[il], cl->lat[il + 1], r0[il + 1], lat);
+  const double b = linear(cl->lat[il], r1[il], cl->lat[il + 1], r1[il + 1], lat);
+  return linear(cl->time[it], a, cl->time[it + 1], b, sec);
+}
+
+static double ramp(double p_one, double p_zero, double p) {
+  if (p > p_one) return 1;
+  if (p < p_zero) return 0;
+  return linear(p_one, 1.0, p_zero, 0.0, p);
+}
+
+static double w_pbl(const orc_ctl_t *ctl, double p, double pbl, double ps) {
+  return ramp(pbl, pbl - ctl->turb_pbl_trans * (ps - pbl), p);
+}
+
+static double w_tropo(const orc_ctl_t *ctl, const orc_clim_t *cl, double time, double lat, double p) {
+  const double pt = orc_clim_tropo(cl, time, ctl->met_coord_type == 0 ? lat : ctl->met_utm_ref_lat);
+  return ramp(pt / 0.866877899, pt * 0.866877899, p);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * module_diff_turb, 4588-4734
+ * ------------------------------------------------------------------------------------------- */
+static double kz_at(const orc_ctl_t *ctl, const orc_clim_t *cl, double time, double lat, double p, double pbl,
+                    double ps, double *kx) {
+  const double a = w_pbl(ctl, p, pbl, ps);
+  const double b = w_tropo(ctl, cl, time, lat, p) * (1.0 - a);
+  const double c = 1.0 - a - b;
+  if (kx) *kx = a * ctl->turb_dx_pbl + b * ctl->turb_dx_trop + c * ctl->turb_dx_strat;
+  return a * ctl->turb_dz_pbl + b * ctl->turb_dz_trop + c * ctl->turb_dz_strat;
+}
+
+void orc_module_diff_turb(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_met_t *met0,
+                          const orc_met_t *met1, orc_atm_t *atm, uint64_t *ctr) {
+  orc_module_rng(atm->rs, 3 * atm->np, 1, ctr);
+  const double ptop = met0->p[met0->np - 1];
+  const int ct = met0->coord_type;
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    const double dt = atm->dt[ip];
+    if (dt == 0) continue;
+    cell_t c = CELL_ZERO;
+    const double pbl = time2(met0, met0->pbl, met1, met1->pbl, atm->time[ip], atm->lon[ip], atm->lat[ip], &c, 1);
+    if (ctl->turb_pbl_scheme > 0 && atm->p[ip] >= pbl) continue;
+    const double ps = time2(met0, met0->ps, met1, met1->ps, atm->time[ip], atm->lon[ip], atm->lat[ip], &c, 0);
+
+    double Kx;
+    const double Kz = kz_at(ctl, clim, atm->time[ip], atm->lat[ip], atm->p[ip], pbl, ps, &Kx);
+    const double dta = fabs(dt);
+
+    if (Kx > 0) {
+      const double sh = sqrt(2.0 * Kx * dta);
+      atm->lon[ip] += east_m_to_coord(ct, atm->rs[3 * ip] * sh, atm->lat[ip]);
+      atm->lat[ip] += north_m_to_coord(ct, atm->rs[3 * ip + 1] * sh);
+    }
+    if (Kz > 0) {
+      const double sz = sqrt(2.0 * Kz * dta) * 1e-3;
+      const double p = atm->p[ip], eps = 0.01;
+      const double pu = fmax(ptop, fmin(ps, p + km2hpa(eps, p)));
+      const double pd = fmax(ptop, fmin(ps, p + km2hpa(-eps, p)));
+      const double Ku = kz_at(ctl, clim, atm->time[ip], atm->lat[ip], pu, pbl, ps, NULL);
+      const double Kd = kz_at(ctl, clim, atm->time[ip], atm->lat[ip], pd, pbl, ps, NULL);
+      const double dKdz = (Ku - Kd) / (2.0 * eps * 1e3);
+      const double drift = dKdz + Kz * (-1.0 / (1e3 * C_H0));
+      const double dz = atm->rs[3 * ip + 2] * sz + drift * dta * 1e-3;
+      double pt = p + km2hpa(dz, p);
+      for (int it = 0; it < 10; it++) {
+        if (pt > ps) pt = ps * ps / pt;
+        else if (pt < ptop) pt = ptop * ptop / pt;
+        else break;
+      }
+      atm->p[ip] = fmax(ptop, fmin(ps, pt));
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * module_diff_meso, 4266-4339: fp32 running sums over the 16 surrounding nodes in the order
+ * x-offset, y-offset, z-offset, (met0, met1)
+ * ------------------------------------------------------------------------------------------- */
+static float sd16(float sum, float sumsq) {
+  const float var = sumsq / 16.f - (sum / 16.f) * (sum / 16.f);
+  return var > 0 ? sqrtf(var) : 0;
+}
+
+void orc_module_diff_meso(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1,
+                          orc_atm_t *atm, uint64_t *ctr) {
+  orc_module_rng(atm->rs, 3 * atm->np, 1, ctr);
+  const int ct = met0->coord_type;
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    const double dt = atm->dt[ip];
+    if (dt == 0) continue;
+    const int ix = regular_index(met0->lon, met0->nx, atm->lon[ip]);
+    const int iy = bisect(met0->lat, met0->ny, atm->lat[ip]);
+    const int iz = bisect(met0->p, met0->np, atm->p[ip]);
+    float s[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+    const float *f0[3] = {met0->u, met0->v, met0->w}, *f1[3] = {met1->u, met1->v, met1->w};
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 2; j++)
+        for (int k = 0; k < 2; k++) {
+          const size_t o = at3(met0, ix + i, iy + j, iz + k);
+          for (int f = 0; f < 3; f++) { const float a = f0[f][o]; s[f] += a; s2[f] += a * a; }
+          for (int f = 0; f < 3; f++) { const float a = f1[f][o]; s[f] += a; s2[f] += a * a; }
+        }
+    const float sig[3] = {sd16(s[0], s2[0]), sd16(s[1], s2[1]), sd16(s[2], s2[2])};
+    const double r = 1 - 2 * fabs(dt) / ctl->dt_met;
+    const double r2 = sqrt(1 - r * r);
+    float *uvw = atm->uvwp + 3 * ip;
+    if (ctl->turb_mesox > 0) {
+      uvw[0] = (float)(r * uvw[0] + r2 * atm->rs[3 * ip] * ctl->turb_mesox * sig[0]);
+      atm->lon[ip] += east_m_to_coord(ct, uvw[0] * dt, atm->lat[ip]);
+      uvw[1] = (float)(r * uvw[1] + r2 * atm->rs[3 * ip + 1] * ctl->turb_mesox * sig[1]);
+      atm->lat[ip] += north_m_to_coord(ct, uvw[1] * dt);
+    }
+    if (ctl->turb_mesoz > 0) {
+      uvw[2] = (float)(r * uvw[2] + r2 * atm->rs[3 * ip + 2] * ctl->turb_mesoz * sig[2]);
+      atm->p[ip] += uvw[2] * dt;
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * sedi 12506-12535, module_sedi 5859-5883
+ * ------------------------------------------------------------------------------------------- */
+double orc_sedi(double p, double T, double rp, double rhop) {
+  const double r = rp * 1e-6;
+  const double rho = 100. * p / (C_RA * T);
+  const double eta = 1.8325e-5 * (416.16 / (T + 120.)) * pow(T / 296.16, 1.5);
+  const double vth = sqrt(8. * C_KB * T / (M_PI * C_MAIR));
+  const double mfp = 2. * eta / (rho * vth);
+  const double Kn = mfp / r;
+  const double slip = 1. + Kn * (1.249 + 0.42 * exp(-0.87 / Kn));
+  return 2. * (r * r) * (rhop - rho) * C_G0 / (9. * eta) * slip;
+}
+
+void orc_module_sedi(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm) {
+  const double *rp = atm->q + (size_t)ctl->qnt_rp * atm->q_stride;
+  const double *rhop = atm->q + (size_t)ctl->qnt_rhop * atm->q_stride;
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    const double dt = atm->dt[ip];
+    if (dt == 0) continue;
+    cell_t c = CELL_ZERO;
+    const double T = time3(met0, met0->t, met1, met1->t, atm->time[ip], atm->p[ip], atm->lon[ip], atm->lat[ip], &c, 1);
+    const double vs = orc_sedi(atm->p[ip], T, rp[ip], rhop[ip]);
+    atm->p[ip] += km2hpa(vs * dt / 1000., atm->p[ip]);
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * module_sort 5887-5958.  The reference orders by gsl_sort_index (heapsort, NOT stable) or Thrust
+ * (stable); the order inside one cell is therefore unspecified.  This restatement uses a stable
+ * order (ties by original index), which is what Thrust's radix sort gives.
+ * ------------------------------------------------------------------------------------------- */
+void orc_sort_keys(const orc_met_t *met0, const orc_atm_t *atm, int32_t *keys) {
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++)
+    keys[ip] = (regular_index(met0->lon, met0->nx, atm->lon[ip]) * met0->ny + bisect(met0->lat, met0->ny, atm->lat[ip])) *
+                   met0->np + bisect(met0->p, met0->np, atm->p[ip]);
+}
+
+typedef struct { int32_t key, idx; } kv_t;
+static int kv_cmp(const void *a, const void *b) {
+  const kv_t *x = (const kv_t *)a, *y = (const kv_t *)b;
+  if (x->key != y->key) return x->key < y->key ? -1 : 1;
+  return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+
+void orc_module_sort(const orc_ctl_t *ctl, const orc_met_t *met0, orc_atm_t *atm) {
+  const int64_t n = atm->np;
+  int32_t *keys = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n ? n : 1));
+  kv_t *kv = (kv_t *)malloc(sizeof(kv_t) * (size_t)(n ? n : 1));
+  double *tmp = (double *)malloc(sizeof(double) * (size_t)(n ? n : 1));
+  orc_sort_keys(met0, atm, keys);
+  for (int64_t i = 0; i < n; i++) { kv[i].key = keys[i]; kv[i].idx = (int32_t)i; }
+  qsort(kv, (size_t)n, sizeof(kv_t), kv_cmp);
+  double *arrays[4 + 64];
+  int na = 0;
+  arrays[na++] = atm->time; arrays[na++] = atm->p; arrays[na++] = atm->lon; arrays[na++] = atm->lat;
+  for (int iq = 0; iq < ctl->nq && iq < 64; iq++) arrays[na++] = atm->q + (size_t)iq * atm->q_stride;
+  for (int a = 0; a < na; a++) {
+    for (int64_t i = 0; i < n; i++) tmp[i] = arrays[a][kv[i].idx];
+    memcpy(arrays[a], tmp, sizeof(double) * (size_t)n);
+  }
+  free(keys); free(kv); free(tmp);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * module_mixing 5169-5347 (sums run serially in parcel order, like the CPU reference)
+ * ------------------------------------------------------------------------------------------- */
+static int box_of(double time, double lon, double lat, double p, double t0, double t1, double lon0, double lon1,
+                  double lat0, double lat1, double z0, double z1, int nx, int ny, int nz) {
+  const double z = C_H0 * log(C_P0 / p);
+  if (time < t0 || time > t1 || lon < lon0 || lon >= lon1 || lat < lat0 || lat >= lat1 || z < z0 || z >= z1) return -1;
+  const double dlon = (lon1 - lon0) / nx, dlat = (lat1 - lat0) / ny, dz = (z1 - z0) / nz;
+  const int ix = (int)((lon - lon0) / dlon), iy = (int)((lat - lat0) / dlat), iz = (int)((z - z0) / dz);
+  if (ix >= nx || iy >= ny || iz >= nz) return -1;
+  return (ix * ny + iy) * nz + iz;
+}
+
+void orc_module_mixing(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm, double t) {
+  const int64_t n = atm->np;
+  const int ngrid = ctl->mixing_nx * ctl->mixing_ny * ctl->mixing_nz;
+  const int nens = ctl->nens > 0 ? ctl->nens : 1;
+  const size_t total = (size_t)ngrid * (size_t)nens;
+  int32_t *box = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n ? n : 1));
+  double *mean = (double *)malloc(sizeof(double) * total);
+  int32_t *cnt = (int32_t *)malloc(sizeof(int32_t) * total);
+  const double t0 = t - 0.5 * ctl->dt_mod, t1 = t + 0.5 * ctl->dt_mod;
+  const double *ens = (ctl->nens > 0) ? atm->q + (size_t)ctl->qnt_ens * atm->q_stride : NULL;
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < n; ip++)
+    box[ip] = box_of(atm->time[ip], atm->lon[ip], atm->lat[ip], atm->p[ip], t0, t1, ctl->mixing_lon0, ctl->mixing_lon1,
+                     ctl->mixing_lat0, ctl->mixing_lat1, ctl->mixing_z0, ctl->mixing_z1, ctl->mixing_nx,
+                     ctl->mixing_ny, ctl->mixing_nz);
+  for (int k = 0; k < ctl->n_mix_qnt; k++) {
+    if (ctl->mix_qnt[k] < 0) continue;
+    double *q = atm->q + (size_t)ctl->mix_qnt[k] * atm->q_stride;
+    memset(mean, 0, sizeof(double) * total);
+    memset(cnt, 0, sizeof(int32_t) * total);
+    for (int64_t ip = 0; ip < n; ip++)
+      if (box[ip] >= 0) {
+        const size_t idx = (size_t)(ens ? (int)ens[ip] : 0) * (size_t)ngrid + (size_t)box[ip];
+        mean[idx] += q[ip];
+        cnt[idx]++;
+      }
+    for (size_t i = 0; i < total; i++)
+      if (cnt[i] > 0) mean[i] /= cnt[i];
+#pragma omp parallel for
+    for (int64_t ip = 0; ip < n; ip++)
+      if (box[ip] >= 0) {
+        double mix = 1.0;
+        if (ctl->mixing_trop < 1 || ctl->mixing_strat < 1) {
+          const double w = w_tropo(ctl, clim, atm->time[ip], atm->lat[ip], atm->p[ip]);
+          mix = w * ctl->mixing_trop + (1.0 - w) * ctl->mixing_strat;
+        }
+        const size_t idx = (size_t)(ens ? (int)ens[ip] : 0) * (size_t)ngrid + (size_t)box[ip];
+        q[ip] += (mean[idx] - q[ip]) * mix;
+      }
+  }
+  free(box); free(mean); free(cnt);
+}
+
+/* write_grid binning, 13840-13872, kernel weight 1 */
+void orc_grid_bin(const orc_atm_t *atm, int nq, int nx, int ny, int nz, double lon0, double lon1,
+                  double lat0, double lat1, double z0, double z1, double t0, double t1,
+                  int32_t *count, double *sum, double *sumsq) {
+  const size_t nb = (size_t)nx * ny * nz;
+  memset(count, 0, sizeof(int32_t) * nb);
+  memset(sum, 0, sizeof(double) * nb * (size_t)nq);
+  memset(sumsq, 0, sizeof(double) * nb * (size_t)nq);
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    const int b = box_of(atm->time[ip], atm->lon[ip], atm->lat[ip], atm->p[ip], t0, t1, lon0, lon1, lat0, lat1, z0, z1, nx, ny, nz);
+    if (b < 0) continue;
+    count[b]++;
+    for (int iq = 0; iq < nq; iq++) {
+      const double x = atm->q[(size_t)iq * atm->q_stride + ip];
+      sum[(size_t)iq * nb + b] += x;
+      sumsq[(size_t)iq * nb + b] += x * x;
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * mptrac_run_timestep restricted to the path, 7877-7945
+ * ------------------------------------------------------------------------------------------- */
+void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_met_t *met0,
+                      const orc_met_t *met1, orc_atm_t *atm, double t, uint64_t *ctr) {
+  orc_module_timesteps(ctl, met0, atm, t);
+  if (ctl->sort_dt > 0 && fmod(t, ctl->sort_dt) == 0) orc_module_sort(ctl, met0, atm);
+  orc_module_position(met0, met1, atm);
+  if (ctl->advect > 0) orc_module_advect(ctl, met0, met1, atm);
+  if (ctl->diffusion && (ctl->turb_dx_pbl > 0 || ctl->turb_dz_pbl > 0 || ctl->turb_dx_trop > 0 ||
+                         ctl->turb_dz_trop > 0 || ctl->turb_dx_strat > 0 || ctl->turb_dz_strat > 0))
+    orc_module_diff_turb(ctl, clim, met0, met1, atm, ctr);
+  if (ctl->diffusion && (ctl->turb_mesox > 0 || ctl->turb_mesoz > 0)) orc_module_diff_meso(ctl, met0, met1, atm, ctr);
+  if (ctl->qnt_rp >= 0 && ctl->qnt_rhop >= 0) orc_module_sedi(ctl, met0, met1, atm);
+  orc_module_position(met0, met1, atm);
+  if (ctl->mixing_trop >= 0 && ctl->mixing_strat >= 0 && (ctl->mixing_dt <= 0 || fmod(t, ctl->mixing_dt) == 0))
+    orc_module_mixing(ctl, clim, atm, t);
+}

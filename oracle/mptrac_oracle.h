@@ -1,0 +1,86 @@
+/*
+ * mptrac_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C, CPU restatement of the algorithm of MPTRAC's per-particle time-step path
+ * (slcs-jsc/mptrac, src/mptrac.c; line numbers in mptrac_oracle.c).  It exists only so that
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg can check the CUDA engine on a
+ * machine that has neither the reference tree nor its dependencies.  Nothing under mptrac_b200/
+ * includes, links or loads it.
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_reference.py runs this file against the unmodified
+ * reference built into oracle/_ref (module by module and through mptrac_run_timestep, on synthetic
+ * and ERA-Interim met) and against the reference's own goldens of tests/dt_test, tests/coord_test
+ * and tests/tools_test (sedi.tab); tests/golden/ holds vectors generated from the reference for
+ * machines without oracle/_ref.
+ */
+#ifndef MPTRAC_ORACLE_H
+#define MPTRAC_ORACLE_H
+
+#include <stdint.h>
+
+#define ORC_MIX_MAXQ 23
+
+/* same field order as mpb_ctl_t so one ctypes structure serves both (the oracle defines its own type
+ * on purpose: it must not depend on product headers) */
+typedef struct {
+  int32_t direction, met_coord_type, advect, advect_vert_coord, rng_type, diffusion, turb_pbl_scheme;
+  int32_t nq, qnt_rp, qnt_rhop, qnt_ens, nens;
+  int32_t mixing_nx, mixing_ny, mixing_nz;
+  int32_t n_mix_qnt;
+  int32_t mix_qnt[ORC_MIX_MAXQ];
+  int32_t _pad;
+  double t_start, t_stop, dt_mod, dt_met, met_utm_ref_lat, sort_dt;
+  double turb_dx_pbl, turb_dx_trop, turb_dx_strat, turb_dz_pbl, turb_dz_trop, turb_dz_strat;
+  double turb_mesox, turb_mesoz, turb_pbl_trans;
+  double mixing_dt, mixing_trop, mixing_strat;
+  double mixing_lon0, mixing_lon1, mixing_lat0, mixing_lat1, mixing_z0, mixing_z1;
+} orc_ctl_t;
+
+/* one met time level, dense: 3-D [nx][ny][np] (z fastest), 2-D [nx][ny] */
+typedef struct {
+  double time;
+  int32_t coord_type, nx, ny, np;
+  const double *lon, *lat, *p;
+  const float *u, *v, *w, *t, *ps, *pbl;
+} orc_met_t;
+
+typedef struct {
+  int32_t ntime, nlat;
+  const double *time, *lat, *tropo; /* [ntime][nlat] */
+} orc_clim_t;
+
+/* parcels + per-parcel cache (atm_t / cache_t) */
+typedef struct {
+  int64_t np;
+  double *time, *p, *lon, *lat;
+  double *q;        /* [nq][q_stride] */
+  int64_t q_stride;
+  double *dt;       /* [np]   cache->dt   */
+  float *uvwp;      /* [np][3] cache->uvwp */
+  double *rs;       /* [3 np + 1] cache->rs */
+} orc_atm_t;
+
+void orc_module_timesteps(const orc_ctl_t *ctl, const orc_met_t *met0, orc_atm_t *atm, double t);
+void orc_module_position(const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
+void orc_module_advect(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
+void orc_module_rng(double *rs, int64_t n, int method, uint64_t *ctr);
+void orc_module_diff_turb(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_met_t *met0,
+                          const orc_met_t *met1, orc_atm_t *atm, uint64_t *ctr);
+void orc_module_diff_meso(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1,
+                          orc_atm_t *atm, uint64_t *ctr);
+void orc_module_sedi(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
+void orc_module_sort(const orc_ctl_t *ctl, const orc_met_t *met0, orc_atm_t *atm);
+void orc_module_mixing(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm, double t);
+void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_met_t *met0,
+                      const orc_met_t *met1, orc_atm_t *atm, double t, uint64_t *ctr);
+
+double orc_sedi(double p, double T, double rp, double rhop);
+double orc_clim_tropo(const orc_clim_t *clim, double t, double lat);
+void orc_intpol_met_time_3d(const orc_met_t *met0, const orc_met_t *met1, const float *f0, const float *f1,
+                            double ts, double p, double lon, double lat, double *var);
+void orc_sort_keys(const orc_met_t *met0, const orc_atm_t *atm, int32_t *keys);
+void orc_grid_bin(const orc_atm_t *atm, int nq, int nx, int ny, int nz, double lon0, double lon1,
+                  double lat0, double lat1, double z0, double z1, double t0, double t1,
+                  int32_t *count, double *sum, double *sumsq);
+
+#endif

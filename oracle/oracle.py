@@ -1,0 +1,293 @@
+"""TEST INFRASTRUCTURE -- ctypes bindings of the CPU oracle (oracle/_build/libmptrac_oracle.so) and, where it
+was built (oracle/_ref), of the harness around the unmodified reference.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
+module.  Nothing in mptrac_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ORACLE_SO = HERE / "_build" / "libmptrac_oracle.so"
+HARNESS_SO = HERE / "_ref" / "lib" / "libref_harness.so"
+REF_BIN = HERE / "_ref" / "bin"
+MIX_MAXQ = 23
+
+_INT_FIELDS = ("direction", "met_coord_type", "advect", "advect_vert_coord", "rng_type", "diffusion",
+               "turb_pbl_scheme", "nq", "qnt_rp", "qnt_rhop", "qnt_ens", "nens",
+               "mixing_nx", "mixing_ny", "mixing_nz", "n_mix_qnt")
+_DBL_FIELDS = ("t_start", "t_stop", "dt_mod", "dt_met", "met_utm_ref_lat", "sort_dt",
+               "turb_dx_pbl", "turb_dx_trop", "turb_dx_strat", "turb_dz_pbl", "turb_dz_trop", "turb_dz_strat",
+               "turb_mesox", "turb_mesoz", "turb_pbl_trans", "mixing_dt", "mixing_trop", "mixing_strat",
+               "mixing_lon0", "mixing_lon1", "mixing_lat0", "mixing_lat1", "mixing_z0", "mixing_z1")
+
+
+class OrcCtl(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in _INT_FIELDS] + [("mix_qnt", C.c_int32 * MIX_MAXQ), ("_pad", C.c_int32)]
+                + [(n, C.c_double) for n in _DBL_FIELDS])
+
+
+class OrcMet(C.Structure):
+    _fields_ = [("time", C.c_double), ("coord_type", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("np", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("lon", "lat", "p", "u", "v", "w", "t", "ps", "pbl")]
+
+
+class OrcClim(C.Structure):
+    _fields_ = [("ntime", C.c_int32), ("nlat", C.c_int32), ("time", C.c_void_p), ("lat", C.c_void_p), ("tropo", C.c_void_p)]
+
+
+class OrcAtm(C.Structure):
+    _fields_ = [("np", C.c_int64), ("time", C.c_void_p), ("p", C.c_void_p), ("lon", C.c_void_p), ("lat", C.c_void_p),
+                ("q", C.c_void_p), ("q_stride", C.c_int64), ("dt", C.c_void_p), ("uvwp", C.c_void_p), ("rs", C.c_void_p)]
+
+
+def ctl_struct(ctl) -> OrcCtl:
+    """Build the C struct from any object with the ctl field names (e.g. mptrac_b200.Ctl) or a dict."""
+    get = (lambda k: ctl[k]) if isinstance(ctl, dict) else (lambda k: getattr(ctl, k))
+    s = OrcCtl()
+    for n in _INT_FIELDS:
+        if n != "n_mix_qnt":
+            setattr(s, n, int(get(n)))
+    for n in _DBL_FIELDS:
+        setattr(s, n, float(get(n)))
+    mq = list(get("mix_qnt"))
+    s.n_mix_qnt = len(mq)
+    for i, v in enumerate(mq):
+        s.mix_qnt[i] = int(v)
+    return s
+
+
+def met_struct(met):
+    """met: object with time, lon, lat, p, u, v, w, t, ps, pbl, coord_type (dense numpy arrays)."""
+    s = OrcMet()
+    s.time, s.coord_type = float(met.time), int(met.coord_type)
+    s.nx, s.ny, s.np = met.lon.size, met.lat.size, met.p.size
+    for n in ("lon", "lat", "p", "u", "v", "w", "t", "ps", "pbl"):
+        a = getattr(met, n)
+        setattr(s, n, a.ctypes.data if a is not None else None)
+    return s
+
+
+class Parcels:
+    """Host copy of atm_t + cache_t for np parcels."""
+
+    def __init__(self, time, p, lon, lat, q: Optional[np.ndarray] = None, uvwp=None, dt=None):
+        self.time = np.array(time, np.float64)
+        self.p = np.array(p, np.float64)
+        self.lon = np.array(lon, np.float64)
+        self.lat = np.array(lat, np.float64)
+        n = self.time.size
+        self.q = np.zeros((0, n)) if q is None else np.array(q, np.float64).reshape(-1, n)
+        self.uvwp = np.zeros((n, 3), np.float32) if uvwp is None else np.array(uvwp, np.float32)
+        self.dt = np.zeros(n) if dt is None else np.array(dt, np.float64)
+        self.rs = np.zeros(3 * n + 1)
+
+    @property
+    def np(self):
+        return self.time.size
+
+    def copy(self) -> "Parcels":
+        return Parcels(self.time, self.p, self.lon, self.lat, self.q, self.uvwp, self.dt)
+
+    def struct(self) -> OrcAtm:
+        s = OrcAtm()
+        s.np = self.time.size
+        for n in ("time", "p", "lon", "lat", "dt", "uvwp", "rs"):
+            setattr(s, n, getattr(self, n).ctypes.data)
+        s.q = self.q.ctypes.data if self.q.size else None
+        s.q_stride = self.q.shape[1] if self.q.size else 0
+        return s
+
+
+def clim_struct(clim):
+    """clim: (time[ntime], lat[nlat], tropo[ntime][nlat]) float64 arrays."""
+    t, la, tr = clim
+    s = OrcClim()
+    s.ntime, s.nlat = t.size, la.size
+    s.time, s.lat, s.tropo = t.ctypes.data, la.ctypes.data, tr.ctypes.data
+    return s
+
+
+def build_oracle():
+    subprocess.run(["make", "-C", str(HERE), "-s"], check=True)
+
+
+class Oracle:
+    """The CPU restatement."""
+
+    def __init__(self):
+        if not ORACLE_SO.exists():
+            build_oracle()
+        L = C.CDLL(str(ORACLE_SO))
+        P = C.POINTER
+        L.orc_sedi.restype = C.c_double
+        L.orc_sedi.argtypes = [C.c_double] * 4
+        L.orc_clim_tropo.restype = C.c_double
+        L.orc_clim_tropo.argtypes = [P(OrcClim), C.c_double, C.c_double]
+        L.orc_module_rng.argtypes = [C.c_void_p, C.c_int64, C.c_int, P(C.c_uint64)]
+        L.orc_run_timestep.argtypes = [P(OrcCtl), P(OrcClim), P(OrcMet), P(OrcMet), P(OrcAtm), C.c_double, P(C.c_uint64)]
+        L.orc_module_timesteps.argtypes = [P(OrcCtl), P(OrcMet), P(OrcAtm), C.c_double]
+        L.orc_module_position.argtypes = [P(OrcMet), P(OrcMet), P(OrcAtm)]
+        L.orc_module_advect.argtypes = [P(OrcCtl), P(OrcMet), P(OrcMet), P(OrcAtm)]
+        L.orc_module_diff_turb.argtypes = [P(OrcCtl), P(OrcClim), P(OrcMet), P(OrcMet), P(OrcAtm), P(C.c_uint64)]
+        L.orc_module_diff_meso.argtypes = [P(OrcCtl), P(OrcMet), P(OrcMet), P(OrcAtm), P(C.c_uint64)]
+        L.orc_module_sedi.argtypes = [P(OrcCtl), P(OrcMet), P(OrcMet), P(OrcAtm)]
+        L.orc_module_sort.argtypes = [P(OrcCtl), P(OrcMet), P(OrcAtm)]
+        L.orc_module_mixing.argtypes = [P(OrcCtl), P(OrcClim), P(OrcAtm), C.c_double]
+        L.orc_sort_keys.argtypes = [P(OrcMet), P(OrcAtm), C.c_void_p]
+        L.orc_intpol_met_time_3d.argtypes = [P(OrcMet), P(OrcMet), C.c_void_p, C.c_void_p] + [C.c_double] * 4 + [P(C.c_double)]
+        L.orc_grid_bin.argtypes = [P(OrcAtm), C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_double] * 8 + [C.c_void_p] * 3
+        for f in ("orc_module_rng", "orc_run_timestep", "orc_module_timesteps", "orc_module_position", "orc_module_advect",
+                  "orc_module_diff_turb", "orc_module_diff_meso", "orc_module_sedi", "orc_module_sort",
+                  "orc_module_mixing", "orc_sort_keys", "orc_intpol_met_time_3d", "orc_grid_bin"):
+            getattr(L, f).restype = None
+        self.L = L
+        self.ctr = 0
+
+    def sedi(self, p, T, rp, rhop):
+        return self.L.orc_sedi(p, T, rp, rhop)
+
+    def clim_tropo(self, clim, t, lat):
+        s = clim_struct(clim)
+        return self.L.orc_clim_tropo(C.byref(s), t, lat)
+
+    def module_rng(self, n, method):
+        rs = np.zeros(n + 1)
+        c = C.c_uint64(self.ctr)
+        self.L.orc_module_rng(rs.ctypes.data, n, method, C.byref(c))
+        self.ctr = c.value
+        return rs
+
+    def intpol_met_time_3d(self, met0, met1, field, ts, p, lon, lat):
+        m0, m1 = met_struct(met0), met_struct(met1)
+        out = C.c_double()
+        self.L.orc_intpol_met_time_3d(C.byref(m0), C.byref(m1), getattr(met0, field).ctypes.data,
+                                      getattr(met1, field).ctypes.data, ts, p, lon, lat, C.byref(out))
+        return out.value
+
+    def run(self, what, ctl, clim, met0, met1, atm: Parcels, t=0.0, nsteps=1):
+        """what: 'timestep' | 'timesteps' | 'position' | 'advect' | 'diff_turb' | 'diff_meso' | 'sedi' | 'sort' | 'mixing'."""
+        c = ctl_struct(ctl)
+        m0, m1 = met_struct(met0), met_struct(met1)
+        cl = clim_struct(clim) if clim is not None else OrcClim()
+        a = atm.struct()
+        ctr = C.c_uint64(self.ctr)
+        L = self.L
+        if what == "timestep":
+            for s in range(nsteps):
+                L.orc_run_timestep(C.byref(c), C.byref(cl), C.byref(m0), C.byref(m1), C.byref(a),
+                                   t + s * ctl.direction * ctl.dt_mod, C.byref(ctr))
+        elif what == "timesteps":
+            L.orc_module_timesteps(C.byref(c), C.byref(m0), C.byref(a), t)
+        elif what == "position":
+            L.orc_module_position(C.byref(m0), C.byref(m1), C.byref(a))
+        elif what == "advect":
+            L.orc_module_advect(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a))
+        elif what == "diff_turb":
+            L.orc_module_diff_turb(C.byref(c), C.byref(cl), C.byref(m0), C.byref(m1), C.byref(a), C.byref(ctr))
+        elif what == "diff_meso":
+            L.orc_module_diff_meso(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a), C.byref(ctr))
+        elif what == "sedi":
+            L.orc_module_sedi(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a))
+        elif what == "sort":
+            L.orc_module_sort(C.byref(c), C.byref(m0), C.byref(a))
+        elif what == "mixing":
+            L.orc_module_mixing(C.byref(c), C.byref(cl), C.byref(a), t)
+        else:
+            raise ValueError(what)
+        self.ctr = ctr.value
+        return atm
+
+    def sort_keys(self, met0, atm: Parcels):
+        keys = np.zeros(atm.np, np.int32)
+        m0 = met_struct(met0)
+        a = atm.struct()
+        self.L.orc_sort_keys(C.byref(m0), C.byref(a), keys.ctypes.data)
+        return keys
+
+    def grid_bin(self, atm: Parcels, nx, ny, nz, lon0, lon1, lat0, lat1, z0, z1, t0, t1):
+        nq = atm.q.shape[0]
+        nb = nx * ny * nz
+        cnt = np.zeros(nb, np.int32)
+        s = np.zeros((nq, nb))
+        sq = np.zeros((nq, nb))
+        a = atm.struct()
+        self.L.orc_grid_bin(C.byref(a), nq, nx, ny, nz, lon0, lon1, lat0, lat1, z0, z1, t0, t1,
+                            cnt.ctypes.data, s.ctypes.data, sq.ctypes.data)
+        return cnt, s, sq
+
+
+_WHAT = {"timestep": 0, "timesteps": 1, "position": 2, "advect": 3, "diff_turb": 4, "diff_meso": 5, "sedi": 6,
+         "sort": 7, "mixing": 8}
+
+
+def reference_available() -> bool:
+    return HARNESS_SO.exists()
+
+
+class Reference:
+    """The unmodified reference, driven in memory through oracle/_ref/lib/libref_harness.so."""
+
+    def __init__(self):
+        if not reference_available():
+            raise RuntimeError("oracle/_ref is not built (run oracle/build_ref.sh where /root/reference exists)")
+        L = C.CDLL(str(HARNESS_SO))
+        P = C.POINTER
+        L.ref_read_ctl.argtypes = [C.c_char_p, C.c_char_p, P(C.c_int)]
+        L.ref_clim_tropo.argtypes = [P(C.c_int), P(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_set_met.argtypes = [P(OrcMet), P(OrcMet)]
+        L.ref_run.argtypes = [P(OrcCtl), P(OrcAtm), C.c_double, C.c_int, C.c_int, P(C.c_uint64)]
+        L.ref_sedi.restype = C.c_double
+        L.ref_sedi.argtypes = [C.c_double] * 4
+        L.ref_module_rng.argtypes = [C.c_void_p, C.c_int64, C.c_int, P(C.c_uint64)]
+        L.ref_dims.argtypes = [P(C.c_int)] * 5
+        self.L = L
+        self.ctr = 0
+        self.qnt = {}
+
+    def dims(self):
+        v = [C.c_int() for _ in range(5)]
+        self.L.ref_dims(*[C.byref(x) for x in v])
+        return dict(zip(("EX", "EY", "EP", "NP", "NQ"), (x.value for x in v)))
+
+    def read_ctl(self, qnt_names=(), overrides=""):
+        out = (C.c_int * 5)()
+        nq = self.L.ref_read_ctl(",".join(qnt_names).encode(), overrides.encode(), out)
+        self.qnt = dict(zip(("rp", "rhop", "m", "vmr", "ens"), list(out)))
+        return nq
+
+    def clim_tropo(self):
+        nt, nl = C.c_int(), C.c_int()
+        t, la, tr = np.zeros(12), np.zeros(73), np.zeros(12 * 73)
+        self.L.ref_clim_tropo(C.byref(nt), C.byref(nl), t.ctypes.data, la.ctypes.data, tr.ctypes.data)
+        return t[:nt.value].copy(), la[:nl.value].copy(), tr[:nt.value * nl.value].reshape(nt.value, nl.value).copy()
+
+    def set_met(self, met0, met1):
+        m0, m1 = met_struct(met0), met_struct(met1)
+        self.L.ref_set_met(C.byref(m0), C.byref(m1))
+
+    def run(self, what, ctl, atm: Parcels, t=0.0, nsteps=1):
+        c = ctl_struct(ctl)
+        a = atm.struct()
+        ctr = C.c_uint64(self.ctr)
+        rc = self.L.ref_run(C.byref(c), C.byref(a), t, _WHAT[what], nsteps, C.byref(ctr))
+        if rc:
+            raise RuntimeError("ref_run failed")
+        self.ctr = ctr.value
+        return atm
+
+    def sedi(self, p, T, rp, rhop):
+        return self.L.ref_sedi(p, T, rp, rhop)
+
+    def module_rng(self, n, method):
+        rs = np.zeros(n + 1)
+        c = C.c_uint64(self.ctr)
+        self.L.ref_module_rng(rs.ctypes.data, n, method, C.byref(c))
+        self.ctr = c.value
+        return rs

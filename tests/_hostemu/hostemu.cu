@@ -1,0 +1,109 @@
+// TEST-ONLY host emulation of the device physics.  The development container has no GPU, so this file
+// runs the *same* __host__ __device__ source the kernels are built from (mptrac_b200/csrc/physics.cuh)
+// in a plain CPU loop, to debug the parcel arithmetic against the oracle before GPU time is spent.
+// It is never part of libmptrac_b200.so, never imported by the package, and proves nothing about the
+// GPU build: the parity tests proper are the `-m gpu` tests that call through the C ABI.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../mptrac_b200/csrc/physics.cuh"
+
+using namespace mpb;
+
+struct EmuMet {
+  double time;
+  int coord_type, nx, ny, np;
+  const double *lon, *lat, *p;
+  const float *u, *v, *w, *t, *ps, *pbl;
+};
+
+struct EmuCtl {
+  double t, t_start, t_stop, dt_met, utm_ref_lat;
+  double dx_pbl, dx_trop, dx_strat, dz_pbl, dz_trop, dz_strat, mesox, mesoz, pbl_trans;
+  uint64_t ctr_turb, ctr_meso;
+  int direction, pbl_scheme, advect, phys;
+  unsigned modules;
+};
+
+static std::vector<float4> pack4(const EmuMet &m) {
+  const size_t n = (size_t)m.nx * m.ny * m.np;
+  std::vector<float4> o(n);
+  for (size_t i = 0; i < n; i++) o[i] = make_float4(m.u[i], m.v[i], m.w[i], m.t ? m.t[i] : 0.f);
+  return o;
+}
+static std::vector<float2> pack2(const EmuMet &m) {
+  const size_t n = (size_t)m.nx * m.ny;
+  std::vector<float2> o(n);
+  for (size_t i = 0; i < n; i++) o[i] = make_float2(m.ps ? m.ps[i] : 0.f, m.pbl ? m.pbl[i] : 0.f);
+  return o;
+}
+
+template <int ADVECT>
+static void run(const MetView &g, const ClimView &cl, const CtlView &c, const EmuCtl &e, long long np, long long ig0,
+                double *time, double *lon, double *lat, double *p, double *dtarr, float *uvwp, const double *rp,
+                const double *rhop) {
+#pragma omp parallel for
+  for (long long ip = 0; ip < np; ip++) {
+    Parcel a = {time[ip], lon[ip], lat[ip], p[ip]};
+    double dt;
+    if (e.modules & MOD_TIMESTEPS) {
+      dt = parcel_dt(g, c, a);
+      if (e.modules & MOD_STORE_DT) dtarr[ip] = dt;
+    } else dt = dtarr[ip];
+    if (dt == 0) continue;
+    const uint64_t ig = (uint64_t)(ig0 + ip);
+    if (e.modules & MOD_POS_PRE) fix_position(g, a);
+    if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(g, dt, a);
+    if (e.phys & 1) diffuse_turbulent(g, cl, c, dt, ig, a);
+    if (e.phys & 2) diffuse_mesoscale(g, c, dt, ig, a, uvwp[3 * ip], uvwp[3 * ip + 1], uvwp[3 * ip + 2]);
+    if (e.phys & 4) sediment(g, dt, rp[ip], rhop[ip], a);
+    if (e.modules & MOD_POS_POST) fix_position(g, a);
+    time[ip] = a.time; lon[ip] = a.lon; lat[ip] = a.lat; p[ip] = a.p;
+  }
+}
+
+extern "C" int emu_step(const EmuMet *m0, const EmuMet *m1, const EmuCtl *e, int ntime, int nlat, const double *cl_time,
+                        const double *cl_lat, const double *cl_tropo, long long np, long long ig0, double *time,
+                        double *lon, double *lat, double *p, double *dt, float *uvwp, const double *rp,
+                        const double *rhop) {
+  std::vector<float4> f0 = pack4(*m0), f1 = pack4(*m1);
+  std::vector<float2> s0 = pack2(*m0), s1 = pack2(*m1);
+  MetView g;
+  g.f0 = f0.data(); g.f1 = f1.data(); g.s0 = s0.data(); g.s1 = s1.data();
+  g.lon = m0->lon; g.lat = m0->lat; g.p = m0->p;
+  g.t0 = m0->time; g.t1 = m1->time;
+  g.nx = m0->nx; g.ny = m0->ny; g.nz = m0->np; g.coord_type = m0->coord_type;
+  g.lon_first = m0->lon[0]; g.lon_last = m0->lon[g.nx - 1]; g.lon_d = m0->lon[1] - m0->lon[0];
+  g.lat_lo = g.lat_hi = m0->lat[0];
+  for (int i = 0; i < g.ny; i++) { g.lat_lo = fmin(g.lat_lo, m0->lat[i]); g.lat_hi = fmax(g.lat_hi, m0->lat[i]); }
+  g.lon_asc = m0->lon[0] < m0->lon[g.nx - 1];
+  { const int m = (g.ny - 1) >> 1; g.lat_asc = m0->lat[m] < m0->lat[m + 1]; }
+  { const int m = (g.nz - 1) >> 1; g.p_asc = m0->p[m] < m0->p[m + 1]; }
+  g.local = fabs(m0->lon[g.nx - 1] - m0->lon[0] - 360.0) >= 0.01;
+  ClimView cl = {cl_time, cl_lat, cl_tropo, ntime, nlat};
+  CtlView c;
+  c.t = e->t; c.t_start = e->t_start; c.t_stop = e->t_stop; c.dt_met = e->dt_met; c.utm_ref_lat = e->utm_ref_lat;
+  c.dx_pbl = e->dx_pbl; c.dx_trop = e->dx_trop; c.dx_strat = e->dx_strat;
+  c.dz_pbl = e->dz_pbl; c.dz_trop = e->dz_trop; c.dz_strat = e->dz_strat;
+  c.mesox = e->mesox; c.mesoz = e->mesoz; c.pbl_trans = e->pbl_trans;
+  c.ctr_turb = e->ctr_turb; c.ctr_meso = e->ctr_meso; c.direction = e->direction; c.pbl_scheme = e->pbl_scheme;
+  switch (e->advect) {
+    case 0: run<0>(g, cl, c, *e, np, ig0, time, lon, lat, p, dt, uvwp, rp, rhop); break;
+    case 1: run<1>(g, cl, c, *e, np, ig0, time, lon, lat, p, dt, uvwp, rp, rhop); break;
+    case 2: run<2>(g, cl, c, *e, np, ig0, time, lon, lat, p, dt, uvwp, rp, rhop); break;
+    case 4: run<4>(g, cl, c, *e, np, ig0, time, lon, lat, p, dt, uvwp, rp, rhop); break;
+    default: return 1;
+  }
+  return 0;
+}
+
+extern "C" void emu_sort_keys(const EmuMet *m0, long long np, const double *lon, const double *lat, const double *p, int *keys) {
+  MetView g;
+  std::memset(&g, 0, sizeof(g));
+  g.lon = m0->lon; g.lat = m0->lat; g.p = m0->p; g.nx = m0->nx; g.ny = m0->ny; g.nz = m0->np;
+  g.lon_first = m0->lon[0]; g.lon_d = m0->lon[1] - m0->lon[0];
+  { const int m = (g.ny - 1) >> 1; g.lat_asc = m0->lat[m] < m0->lat[m + 1]; }
+  { const int m = (g.nz - 1) >> 1; g.p_asc = m0->p[m] < m0->p[m + 1]; }
+  for (long long i = 0; i < np; i++) keys[i] = cell_key(g, lon[i], lat[i], p[i]);
+}

@@ -1,0 +1,431 @@
+"""GPU parity tests proper: the CUDA engine, called through the C ABI, against the CPU oracle on the same seeded
+inputs, against the committed golden fixtures generated from the unmodified reference, and -- at BASELINE.json's
+full sizes -- through size-independent properties.
+
+Tolerances (fp64 state, fp32 met; stated per test): the device build contracts a*b+c into FMAs and uses CUDA's
+libm (cos/log/exp/pow/sinf/cosf are not bit-identical to glibc's), so agreement is ~1e-13 relative per step instead
+of bit-exact; index / integer work (sort keys, box indices, counts, RNG integers) must be exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, abserr, clim_from_npz, met_from_npz, relerr
+
+pytestmark = pytest.mark.gpu
+
+# lon/lat in degrees (absolute), pressure relative
+TOL_POS_DEG = 1e-9
+TOL_P_REL = 1e-10
+
+REPORT = {}
+
+
+def _report(name, **kw):
+    REPORT[name] = {k: float(v) for k, v in kw.items()}
+    out = ROOT / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        (out / "parity_report.json").write_text(json.dumps(REPORT, indent=1, sort_keys=True))
+    except OSError:
+        pass
+
+
+def _engine(n, nq=0, strict=False):
+    from mptrac_b200 import Engine
+    return Engine(n, nq=nq, device=0, strict=strict)
+
+
+def _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat, q=None):
+    eng.set_ctl(ctl)
+    eng.set_clim_tropo(*clim)
+    eng.set_met(0, m0)
+    eng.set_met(1, m1)
+    eng.set_atm(tm, p, lon, lat, q)
+
+
+def _case(n=6000, grid=(48, 25, 24), lat_desc=False, seed=5, zmax=45.0):
+    from mptrac_b200 import synth
+    m0, m1 = synth.make_met_pair(*grid, t0=0.0, dt_met=21600.0, lat_descending=lat_desc)
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.05, zmax=zmax, seed=seed)
+    return m0, m1, tm, p, lon, lat, synth.make_clim_tropo()
+
+
+def _compare(tag, out, ref, tol_pos=TOL_POS_DEG, tol_p=TOL_P_REL):
+    e_lon, e_lat, e_p, e_t = abserr(out["lon"], ref.lon), abserr(out["lat"], ref.lat), relerr(out["p"], ref.p), abserr(out["time"], ref.time)
+    _report(tag, lon_abs=e_lon, lat_abs=e_lat, p_rel=e_p, time_abs=e_t)
+    assert e_t == 0.0, f"{tag}: time differs"
+    assert e_lon < tol_pos and e_lat < tol_pos, f"{tag}: lon {e_lon:.3e} lat {e_lat:.3e}"
+    assert e_p < tol_p, f"{tag}: p rel {e_p:.3e}"
+
+
+@pytest.mark.parametrize("advect", [1, 2, 4])
+@pytest.mark.parametrize("diffusion", [0, 1])
+@pytest.mark.parametrize("lat_desc", [False, True])
+@pytest.mark.parametrize("direction", [1, -1])
+def test_timestep_vs_oracle(oracle, advect, diffusion, lat_desc, direction):
+    from mptrac_b200 import Ctl
+    from oracle.oracle import Parcels
+    m0, m1, tm, p, lon, lat, clim = _case(lat_desc=lat_desc)
+    n = tm.size
+    t_start = 0.0 if direction == 1 else 21600.0
+    tm = np.full(n, t_start)
+    q = np.stack([np.full(n, 2.0), np.full(n, 1500.0)])
+    ctl = Ctl(nq=2, qnt_rp=0, qnt_rhop=1, advect=advect, diffusion=diffusion, direction=direction, t_start=t_start,
+              t_stop=t_start + direction * 86400.0, dt_mod=300.0, dt_met=21600.0, turb_dz_trop=0.5, turb_dz_pbl=1.0,
+              turb_dx_strat=20.0, turb_pbl_trans=0.3)
+    nsteps = 6
+    with _engine(n, 2) as eng:
+        _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat, q)
+        for s in range(nsteps):
+            eng.run_timestep(t_start + s * direction * 300.0)
+        out = eng.get_atm()
+        uv = eng.get_uvwp()
+        ctr = eng.rng_ctr
+    ref = Parcels(tm, p, lon, lat, q)
+    oracle.ctr = 0
+    oracle.run("timestep", ctl, clim, m0, m1, ref, t=t_start, nsteps=nsteps)
+    assert ctr == oracle.ctr
+    assert abserr(ref.lat, lat) > 1e-3, "nothing moved"
+    _compare(f"timestep[advect={advect},diff={diffusion},latdesc={int(lat_desc)},dir={direction}]", out, ref)
+    if diffusion:
+        assert relerr(uv + 1e-30, ref.uvwp + 1e-30) < 1e-4 or abserr(uv, ref.uvwp) < 1e-5
+
+
+def test_strict_build_is_tighter(oracle):
+    """-fmad=false flavour: remaining differences come from libm only."""
+    from mptrac_b200 import Ctl
+    from oracle.oracle import Parcels
+    m0, m1, tm, p, lon, lat, clim = _case()
+    n = tm.size
+    ctl = Ctl(advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0)
+    with _engine(n, 0, strict=True) as eng:
+        _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat)
+        for s in range(6):
+            eng.run_timestep(s * 300.0)
+        out = eng.get_atm()
+    ref = Parcels(tm, p, lon, lat)
+    oracle.run("timestep", ctl, clim, m0, m1, ref, t=0.0, nsteps=6)
+    _compare("strict_rk4", out, ref, tol_pos=1e-11, tol_p=1e-12)
+    _report("strict_rk4_bitexact_fraction", lon=np.mean(out["lon"] == ref.lon), lat=np.mean(out["lat"] == ref.lat), p=np.mean(out["p"] == ref.p))
+
+
+@pytest.mark.parametrize("module", ["position", "advect", "diff_turb", "diff_meso", "sedi"])
+def test_single_modules_vs_oracle(oracle, module):
+    """Each exported module_* entry point on its own (cache->dt supplied by module_timesteps)."""
+    from mptrac_b200 import Ctl
+    from oracle.oracle import Parcels
+    m0, m1, tm, p, lon, lat, clim = _case(seed=9)
+    n = tm.size
+    rng = np.random.default_rng(1)
+    # push some parcels out of range so that module_position has something to do
+    lon = lon + rng.choice([0.0, 360.0, -360.0], n)
+    lat = np.where(rng.uniform(size=n) < 0.05, lat + 100.0, lat)
+    p = np.where(rng.uniform(size=n) < 0.05, p * 1.5, p)
+    q = np.stack([rng.uniform(0.1, 10.0, n), rng.uniform(500.0, 2500.0, n)])
+    uvwp = rng.standard_normal((n, 3)).astype(np.float32)
+    ctl = Ctl(nq=2, qnt_rp=0, qnt_rhop=1, advect=4, diffusion=1, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0,
+              turb_dz_trop=0.5, turb_dz_pbl=1.0, turb_dx_strat=20.0, turb_pbl_trans=0.3)
+    with _engine(n, 2) as eng:
+        _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat, q)
+        eng.set_uvwp(uvwp)
+        eng.rng_ctr = 777
+        eng.module_timesteps(300.0)
+        dt = eng.get_dt()
+        getattr(eng, f"module_{module}")()
+        out = eng.get_atm()
+        uv = eng.get_uvwp()
+        ctr = eng.rng_ctr
+    ref = Parcels(tm, p, lon, lat, q, uvwp)
+    oracle.ctr = 777
+    oracle.run("timesteps", ctl, clim, m0, m1, ref, t=300.0)
+    assert np.array_equal(dt, ref.dt)
+    oracle.run(module, ctl, clim, m0, m1, ref, t=300.0)
+    assert ctr == oracle.ctr
+    _compare(f"module_{module}", out, ref)
+    assert abserr(uv, ref.uvwp) < 1e-5
+
+
+def test_rng_stream(oracle):
+    """Squares counters are integers: uniforms must be bit-exact; Box-Muller normals agree to float-trig accuracy."""
+    with _engine(10) as eng:
+        eng.rng_ctr = 12345
+        u = eng.module_rng(3001, 0)
+        g = eng.module_rng(3001, 1)
+        end = eng.rng_ctr
+    oracle.ctr = 12345
+    u0 = oracle.module_rng(3001, 0)
+    g0 = oracle.module_rng(3001, 1)
+    assert end == oracle.ctr
+    assert np.array_equal(u, u0)
+    assert abserr(g[:3001], g0[:3001]) < 5e-6
+    assert abs(np.mean(g[:3000])) < 0.1 and abs(np.std(g[:3000]) - 1) < 0.1
+
+
+def _golden(name):
+    f = GOLDEN / name
+    if not f.exists():
+        pytest.skip(f"{f} missing")
+    return np.load(f)
+
+
+def test_golden_dt_test():
+    """tests/dt_test of the reference (ERA-Interim, midpoint + turbulent + mesoscale diffusion, 7 outputs)."""
+    from mptrac_b200 import Ctl
+    z = _golden("dt_test.npz")
+    m0, m1, clim = met_from_npz(z, "m0"), met_from_npz(z, "m1"), clim_from_npz(z)
+    t0, n_total, k = float(z["t_start"]), int(z["np_total"]), z["time"].size
+    ctl = Ctl(nq=0, advect=2, diffusion=1, dt_mod=10.0, dt_met=86400.0, t_start=t0, t_stop=t0 + 60.0)
+    with _engine(k) as eng:
+        _setup(eng, ctl, clim, m0, m1, z["time"], z["p"], z["lon"], z["lat"])
+        eng.set_shard(0, n_total)   # the fixture holds the first k of n_total parcels: counters advance as for all
+        for s in range(7):
+            eng.run_timestep(t0 + 10.0 * s)
+            out = eng.get_atm()
+            rb, txt = z["ref_binary"][s], z["ref_shipped_text"][s]
+            e = dict(lon_abs=abserr(out["lon"], rb[2]), lat_abs=abserr(out["lat"], rb[3]), p_rel=relerr(out["p"], rb[1]))
+            _report(f"golden_dt_test_step{s}", **e)
+            assert e["lon_abs"] < 1e-9 and e["lat_abs"] < 1e-9 and e["p_rel"] < 1e-10 and np.array_equal(out["time"], rb[0])
+            # the reference's own shipped text goldens (%g: 6 significant digits)
+            zkm = 7.0 * np.log(1013.25 / out["p"])
+            assert relerr(zkm, txt[:, 1]) < 1e-5 and relerr(out["lon"], txt[:, 2]) < 1e-5 and relerr(out["lat"], txt[:, 3]) < 1e-5
+
+
+def test_golden_coord_test():
+    """tests/coord_test of the reference: Cartesian (UTM) met, three hourly levels (met swap), 13 outputs."""
+    from mptrac_b200 import Ctl
+    z = _golden("coord_test.npz")
+    mets = [met_from_npz(z, f"m{i}") for i in range(3)]
+    clim = clim_from_npz(z)
+    t0, n = float(z["t_start"]), z["time"].size
+    ctl = Ctl(nq=0, advect=2, diffusion=1, dt_mod=600.0, dt_met=3600.0, t_start=t0, t_stop=t0 + 7200.0, met_coord_type=1,
+              met_utm_ref_lat=48.1507476)
+    with _engine(n) as eng:
+        _setup(eng, ctl, clim, mets[0], mets[1], z["time"], z["p"], z["lon"], z["lat"])
+        for s in range(13):
+            t = t0 + 600.0 * s
+            if s == 7:   # first step with t > met1->time: the swap of mptrac_get_met, then one new level
+                eng.swap_met()
+                eng.set_met(1, mets[2])
+            eng.run_timestep(t)
+            out = eng.get_atm()
+            rb = z["ref_binary"][s]
+            e = dict(x_abs_m=abserr(out["lon"], rb[2]), y_abs_m=abserr(out["lat"], rb[3]), p_rel=relerr(out["p"], rb[1]))
+            _report(f"golden_coord_test_step{s}", **e)
+            assert e["x_abs_m"] < 1e-5 and e["y_abs_m"] < 1e-5 and e["p_rel"] < 1e-10
+            txt = z["ref_shipped_text"][s]
+            assert abserr(out["lon"], txt[:, 2]) < 0.02 and abserr(out["lat"], txt[:, 3]) < 0.02   # metres; text has 0.01 m resolution
+
+
+def test_golden_synth_full():
+    """RK4 + diff_turb + diff_meso + sedi + mixing on a north->south grid; reference binary results."""
+    from mptrac_b200 import Ctl, synth
+    z = _golden("synth_full.npz")
+    m0, m1 = synth.make_met_pair(24, 13, 20, t0=0.0, dt_met=21600.0, lat_descending=True)
+    clim = clim_from_npz(z)
+    n = z["time"].size
+    ctl = Ctl(nq=3, qnt_rp=0, qnt_rhop=1, advect=4, diffusion=1, t_start=0.0, t_stop=86400.0, dt_mod=600.0, dt_met=21600.0,
+              turb_dz_trop=0.5, turb_dz_pbl=1.0, turb_dx_strat=20.0, turb_pbl_trans=0.2, mixing_trop=0.3, mixing_strat=0.1,
+              mixing_dt=1200.0, mix_qnt=[2], mixing_nx=18, mixing_ny=9, mixing_nz=12)
+    with _engine(n, 3) as eng:
+        _setup(eng, ctl, clim, m0, m1, z["time"], z["p"], z["lon"], z["lat"], z["q"])
+        for s in range(8):
+            eng.run_timestep(600.0 * s)
+            out = eng.get_atm()
+            rb = z["ref_binary"][s]
+            e = dict(lon_abs=abserr(out["lon"], rb[2]), lat_abs=abserr(out["lat"], rb[3]), p_rel=relerr(out["p"], rb[1]),
+                     q_rel=relerr(out["q"][2], z["ref_q"][s][2]))
+            _report(f"golden_synth_full_step{s}", **e)
+            assert e["lon_abs"] < 1e-8 and e["lat_abs"] < 1e-8 and e["p_rel"] < 1e-9 and e["q_rel"] < 1e-9
+        assert eng.rng_ctr == int(z["ref_ctr"])
+
+
+def test_sort_matches_stable_oracle(oracle):
+    from mptrac_b200 import Ctl
+    from oracle.oracle import Parcels
+    m0, m1, tm, p, lon, lat, clim = _case(n=50000, seed=2)
+    n = tm.size
+    q = np.arange(n, dtype=np.float64)[None, :]          # original index rides along as a quantity
+    ctl = Ctl(nq=1, advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0)
+    with _engine(n, 1) as eng:
+        _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat, q)
+        eng.module_sort()
+        out = eng.get_atm()
+    ref = Parcels(tm, p, lon, lat, q)
+    keys_before = oracle.sort_keys(m0, ref)
+    oracle.run("sort", ctl, clim, m0, m1, ref)
+    # index work: bit-exact, including the order inside a cell (CUB radix sort is stable)
+    assert np.array_equal(out["q"][0], ref.q[0])
+    for k in ("lon", "lat", "p", "time"):
+        assert np.array_equal(out[k], getattr(ref, k))
+    keys_after = oracle.sort_keys(m0, Parcels(out["time"], out["p"], out["lon"], out["lat"]))
+    assert np.all(np.diff(keys_after) >= 0)
+    assert np.array_equal(np.sort(keys_before), keys_after)
+
+
+def test_sort_edge_cases(oracle):
+    """empty, single parcel, all parcels in one cell"""
+    from mptrac_b200 import Ctl
+    m0, m1, tm, p, lon, lat, clim = _case(n=100)
+    ctl = Ctl(nq=0, advect=2, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, sort_dt=300.0)
+    for n in (0, 1, 100):
+        with _engine(100) as eng:
+            same = n == 100
+            lo, la, pp = (np.full(n, 10.0), np.full(n, 20.0), np.full(n, 500.0)) if same else (lon[:n], lat[:n], p[:n])
+            _setup(eng, ctl, clim, m0, m1, tm[:n], pp, lo, la)
+            eng.run_timestep(0.0)
+            eng.run_timestep(300.0)
+            out = eng.get_atm()
+            assert out["lon"].size == n
+            if same:
+                assert np.all(out["lon"] == out["lon"][0]) and out["lon"][0] != 10.0
+
+
+def test_mixing_and_grid_vs_oracle(oracle):
+    from mptrac_b200 import Ctl
+    from oracle.oracle import Parcels
+    m0, m1, tm, p, lon, lat, clim = _case(n=40000, seed=4)
+    n = tm.size
+    rng = np.random.default_rng(0)
+    q = np.stack([rng.uniform(0, 1, n), rng.uniform(10, 20, n), rng.integers(0, 3, n).astype(float)])
+    ctl = Ctl(nq=3, advect=0, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, mixing_trop=0.4, mixing_strat=0.05,
+              mixing_dt=300.0, mix_qnt=[0, 1], mixing_nx=36, mixing_ny=18, mixing_nz=15, nens=3, qnt_ens=2)
+    with _engine(n, 3) as eng:
+        _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat, q)
+        eng.module_mixing(0.0)
+        out = eng.get_atm()
+        eng.grid_accumulate(36, 18, 4, -180, 180, -90, 90, 0, 40, -150.0, 150.0)
+        cnt, s, sq = eng.grid_fetch()
+    ref = Parcels(tm, p, lon, lat, q)
+    oracle.run("mixing", ctl, clim, m0, m1, ref, t=0.0)
+    assert abserr(ref.q[0], q[0]) > 1e-3
+    # sums run in a different order (atomics): ~1e-14 relative
+    e = dict(q0_rel=relerr(out["q"][0], ref.q[0]), q1_rel=relerr(out["q"][1], ref.q[1]))
+    _report("mixing", **e)
+    assert e["q0_rel"] < 1e-11 and e["q1_rel"] < 1e-11 and np.array_equal(out["q"][2], ref.q[2])
+    c0, s0, sq0 = oracle.grid_bin(Parcels(out["time"], out["p"], out["lon"], out["lat"], out["q"]), 36, 18, 4, -180, 180, -90, 90, 0, 40, -150.0, 150.0)
+    assert np.array_equal(cnt, c0) and cnt.sum() > 0.5 * n
+    assert relerr(s + 1e-300, s0 + 1e-300) < 1e-11 and relerr(sq + 1e-300, sq0 + 1e-300) < 1e-11
+
+
+def test_inactive_and_ragged_parcels(oracle):
+    """parcels that start later / are already past t_stop keep dt = 0 and must not be touched; np < np_max"""
+    from mptrac_b200 import Ctl
+    from oracle.oracle import Parcels
+    m0, m1, tm, p, lon, lat, clim = _case(n=3000)
+    n = tm.size
+    tm = np.where(np.arange(n) % 3 == 0, 900.0, 0.0)      # a third is released at t = 900 s
+    ctl = Ctl(advect=2, diffusion=1, t_start=0.0, t_stop=1200.0, dt_mod=300.0, dt_met=21600.0)
+    with _engine(5000) as eng:
+        _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat)
+        for s in range(6):                                  # runs past t_stop
+            eng.run_timestep(300.0 * s)
+        out = eng.get_atm()
+    ref = Parcels(tm, p, lon, lat)
+    oracle.ctr = 0
+    oracle.run("timestep", ctl, clim, m0, m1, ref, t=0.0, nsteps=6)
+    _compare("ragged", out, ref)
+    assert np.all(out["time"] <= 1200.0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# full-size (BASELINE configs[1]) properties
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c2():
+    from mptrac_b200 import synth
+    m0, m1 = synth.make_met_pair(360, 181, 60, t0=0.0, dt_met=21600.0)
+    tm, p, lon, lat = synth.make_parcels(1_000_000, t0=0.0, seed=123)
+    return m0, m1, tm, p, lon, lat, synth.make_clim_tropo()
+
+
+def test_fullsize_subsample_vs_oracle(oracle, c2):
+    """1 M parcels, 1 deg x 60 levels, RK4, 12 steps on the GPU; parcels are independent without diffusion, so a random
+    subset re-run through the oracle must land on the same positions."""
+    from mptrac_b200 import Ctl
+    from oracle.oracle import Parcels
+    m0, m1, tm, p, lon, lat, clim = c2
+    n = tm.size
+    ctl = Ctl(advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0)
+    with _engine(n) as eng:
+        _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat)
+        for s in range(13):
+            eng.run_timestep(300.0 * s)
+        out = eng.get_atm()
+    idx = np.random.default_rng(0).choice(n, 20000, replace=False)
+    ref = Parcels(tm[idx], p[idx], lon[idx], lat[idx])
+    oracle.run("timestep", ctl, clim, m0, m1, ref, t=0.0, nsteps=13)
+    _compare("fullsize_c2_subsample", {k: out[k][idx] for k in ("time", "lon", "lat", "p")}, ref)
+
+
+def test_fullsize_sharded_equals_single(c2):
+    """two contexts that each own half of the parcels (set_shard) reproduce the single-context run bit for bit,
+    diffusion included: random numbers are addressed by global parcel index"""
+    from mptrac_b200 import Ctl
+    m0, m1, tm, p, lon, lat, clim = c2
+    n = 400_000
+    ctl = Ctl(advect=2, diffusion=1, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0)
+    outs = []
+    for parts in ([(0, n)], [(0, n // 2), (n // 2, n)]):
+        res = {k: np.empty(n) for k in ("lon", "lat", "p")}
+        for a, b in parts:
+            with _engine(b - a) as eng:
+                _setup(eng, ctl, clim, m0, m1, tm[a:b], p[a:b], lon[a:b], lat[a:b])
+                eng.set_shard(a, n)
+                for s in range(4):
+                    eng.run_timestep(300.0 * s)
+                o = eng.get_atm()
+                for k in res:
+                    res[k][a:b] = o[k]
+        outs.append(res)
+    for k in ("lon", "lat", "p"):
+        assert np.array_equal(outs[0][k], outs[1][k])
+
+
+def test_fullsize_sort_is_a_permutation_and_keeps_results(oracle, c2):
+    """sorting by met cell (SORT_DT) must not change where (diffusion-free) parcels end up, only their order"""
+    from mptrac_b200 import Ctl
+    m0, m1, tm, p, lon, lat, clim = c2
+    n = tm.size
+    ident = np.arange(n, dtype=np.float64)[None, :]
+    res = []
+    for sort_dt in (-999.0, 600.0):
+        ctl = Ctl(nq=1, advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, sort_dt=sort_dt)
+        with _engine(n, 1) as eng:
+            _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat, ident)
+            for s in range(5):
+                eng.run_timestep(300.0 * s)
+            res.append(eng.get_atm())
+    a, b = res
+    order = b["q"][0].astype(np.int64)
+    assert np.array_equal(np.sort(order), np.arange(n))
+    for k in ("lon", "lat", "p", "time"):
+        assert np.array_equal(a[k][order], b[k])
+
+
+def test_fullsize_diffusion_moments(c2):
+    """statistical check at full size (north_star: moments when diffusion is on): the mean turbulent displacement over
+    1 M parcels is zero and its spread matches sqrt(2 K dt)"""
+    from mptrac_b200 import Ctl
+    m0, m1, tm, p, lon, lat, clim = c2
+    n = tm.size
+    lat0 = np.clip(lat, -60, 60)
+    ctl = Ctl(advect=0, diffusion=1, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, turb_mesox=0.0, turb_mesoz=0.0,
+              turb_dx_pbl=50.0, turb_dx_trop=50.0, turb_dx_strat=50.0, turb_dz_strat=0.0)
+    with _engine(n) as eng:
+        _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat0)
+        eng.run_timestep(0.0)
+        eng.run_timestep(300.0)
+        out = eng.get_atm()
+    dy_m = (out["lat"] - lat0) * np.pi / 180.0 * 6367.421e3
+    sigma = np.sqrt(2 * 50.0 * 300.0)
+    _report("diffusion_moments", mean_over_sigma=np.mean(dy_m) / sigma, std_over_sigma=np.std(dy_m) / sigma)
+    assert abs(np.mean(dy_m)) < 5 * sigma / np.sqrt(n)
+    assert abs(np.std(dy_m) / sigma - 1) < 5e-3
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
