@@ -119,6 +119,22 @@ uint64_t mpb_get_rng_ctr(mpb_ctx *ctx);
  *     modules on the path; all enabled modules run fused in ONE kernel per step. --- */
 int mpb_run_timestep(mpb_ctx *ctx, double t);
 
+/* A sub-sequence of the step, for callers that interleave modules of their own (the shim does this for
+ * reference modules that are not on the device path).  `mask` selects modules, which still run in the
+ * reference's order and only if the control parameters enable them; adjacent selected modules are fused into one
+ * kernel.  Without MPB_MOD_TIMESTEPS the per-parcel dt is read from device memory (cache_t::dt). */
+#define MPB_MOD_TIMESTEPS 0x001
+#define MPB_MOD_SORT      0x002
+#define MPB_MOD_POSITION0 0x004
+#define MPB_MOD_ADVECT    0x008
+#define MPB_MOD_DIFF_TURB 0x010
+#define MPB_MOD_DIFF_MESO 0x020
+#define MPB_MOD_SEDI      0x040
+#define MPB_MOD_POSITION1 0x080
+#define MPB_MOD_MIXING    0x100
+#define MPB_MOD_ALL       0x1ff
+int mpb_run_modules(mpb_ctx *ctx, double t, unsigned mask);
+
 /* --- single modules (same symbols the reference exports, src/mptrac.h:6140-7132); each is the
  *     same fused kernel restricted to one module and reads cache->dt from device memory. --- */
 int mpb_module_timesteps(mpb_ctx *ctx, double t);   /* src/mptrac.c:5999 */

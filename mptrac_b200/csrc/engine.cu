@@ -764,31 +764,53 @@ int mpb_set_rng_ctr(mpb_ctx *c, uint64_t ctr) {
 }
 uint64_t mpb_get_rng_ctr(mpb_ctx *c) { return c ? c->rng_ctr : 0; }
 
-int mpb_run_timestep(mpb_ctx *c, double t) {
-  API_BEGIN
-  use(c);
+static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
   const mpb_ctl_t &k = c->ctl;
   unsigned phys = 0;
-  if (turb_enabled(k)) phys |= PHYS_TURB;
-  if (meso_enabled(k)) phys |= PHYS_MESO;
-  if (sedi_enabled(k)) phys |= PHYS_SEDI;
-  unsigned modules = MOD_POS_PRE | MOD_POS_POST;
-  if (k.sort_dt > 0 && hits(t, k.sort_dt)) {
-    // the reference computes dt BEFORE it permutes the parcels and leaves cache->dt in slot order
-    // (src/mptrac.c:7877-7881): do the same with a dt-only launch, then sort, then read dt from memory
-    launch_step(c, t, 0, 0, MOD_TIMESTEPS | MOD_STORE_DT);
-    // a dt-only launch of parcels with dt != 0 rewrites lon/lat/p unchanged: harmless
+  if ((mask & MPB_MOD_DIFF_TURB) && turb_enabled(k)) phys |= PHYS_TURB;
+  if ((mask & MPB_MOD_DIFF_MESO) && meso_enabled(k)) phys |= PHYS_MESO;
+  if ((mask & MPB_MOD_SEDI) && sedi_enabled(k)) phys |= PHYS_SEDI;
+  const int advect = (mask & MPB_MOD_ADVECT) ? k.advect : 0;
+  unsigned modules = 0;
+  if (mask & MPB_MOD_POSITION0) modules |= MOD_POS_PRE;
+  if (mask & MPB_MOD_POSITION1) modules |= MOD_POS_POST;
+  const bool whole = (mask & 0xff) == 0xff;
+  const bool sort_now = (mask & MPB_MOD_SORT) && k.sort_dt > 0 && hits(t, k.sort_dt);
+  if (mask & MPB_MOD_TIMESTEPS) {
+    if (sort_now) {
+      // the reference computes dt BEFORE it permutes the parcels and leaves cache->dt in slot order
+      // (src/mptrac.c:7877-7881): a dt-only launch (active parcels are rewritten unchanged), then the sort,
+      // then the fused launch reads dt from memory
+      launch_step(c, t, 0, 0, MOD_TIMESTEPS | MOD_STORE_DT);
+      do_sort(c);
+    } else {
+      modules |= MOD_TIMESTEPS;
+      if (!whole) modules |= MOD_STORE_DT;   // later segments read cache->dt from memory
+    }
+  } else if (sort_now) {
     do_sort(c);
-  } else {
-    modules |= MOD_TIMESTEPS;
   }
-  launch_step(c, t, k.advect, phys, modules);
-  if (k.mixing_trop >= 0 && k.mixing_strat >= 0 && (k.mixing_dt <= 0 || hits(t, k.mixing_dt))) {  // :7943-7945
+  if (modules || advect || phys) launch_step(c, t, advect, phys, modules);
+  if ((mask & MPB_MOD_MIXING) && k.mixing_trop >= 0 && k.mixing_strat >= 0 &&
+      (k.mixing_dt <= 0 || hits(t, k.mixing_dt))) {  // src/mptrac.c:7943-7945
     mixing_begin(c, t);
     for (int i = 0; i < k.n_mix_qnt; i++)
       if (k.mix_qnt[i] >= 0) { mixing_accumulate(c, k.mix_qnt[i]); mixing_apply(c, k.mix_qnt[i]); }
   }
+}
+
+int mpb_run_timestep(mpb_ctx *c, double t) {
+  API_BEGIN
+  use(c);
+  run_modules(c, t, MPB_MOD_ALL);
+  API_END
+}
+
+int mpb_run_modules(mpb_ctx *c, double t, unsigned mask) {
+  API_BEGIN
+  use(c);
+  run_modules(c, t, mask);
   API_END
 }
 

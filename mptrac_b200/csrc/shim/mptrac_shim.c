@@ -1,0 +1,258 @@
+/*
+ * mptrac_shim.c -- the reference-facing side of the drop-in boundary.
+ *
+ * Built against the reference's OWN header (mptrac.h is found through -I<reference>/src at build time; it
+ * is never copied into this repository) and placed in front of the reference's libmptrac.so (link order or
+ * LD_PRELOAD).  It defines the symbols the unmodified `trac` driver and the library itself reach through the
+ * PLT -- mptrac_run_timestep, mptrac_update_device, mptrac_update_host, mptrac_free -- and forwards them to
+ * the C ABI of libmptrac_b200.so.  Host language = C, like the reference.
+ *
+ *   mptrac_update_device (src/mptrac.c:8005)  -> mpb_set_ctl / set_clim_tropo / set_met / set_atm / set_uvwp
+ *   mptrac_update_host   (src/mptrac.c:8061)  -> mpb_get_atm / get_uvwp / get_dt
+ *   mptrac_run_timestep  (src/mptrac.c:7851)  -> mpb_run_timestep, or -- when the control file enables modules that
+ *                                               are not on the device path -- mpb_run_modules segments with the
+ *                                               reference's own CPU modules called in between (hybrid mode)
+ *   mptrac_free          (src/mptrac.c:6377)  -> mpb_destroy, then the reference's own mptrac_free
+ *
+ * Errors follow the reference's convention: message + exit(EXIT_FAILURE) (ERRMSG, src/mptrac.h:2406-2410).
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+
+#include "mptrac.h"
+#include "mptrac_b200.h"
+
+static mpb_ctx *g_ctx;
+static const met_t *g_slot[2];    /* host met_t mirrored by device slot 0 / 1 */
+static int g_np = -1;             /* parcels on the device */
+static int g_dev_newer;           /* device parcels are newer than the host copy */
+static int g_verbose = -1;
+
+#define MPB(call)                                                        \
+  do {                                                                   \
+    if ((call) != 0) ERRMSG("mptrac_b200: %s", mpb_last_error());         \
+  } while (0)
+
+static int verbose(void) {
+  if (g_verbose < 0) g_verbose = getenv("MPTRAC_B200_VERBOSE") ? atoi(getenv("MPTRAC_B200_VERBOSE")) : 0;
+  return g_verbose;
+}
+
+static void ensure_ctx(const ctl_t *ctl, int np) {
+  if (g_ctx && np <= g_np) return;
+  if (g_ctx) MPB(mpb_destroy(g_ctx));
+  int dev = 0;
+  const char *e = getenv("MPTRAC_B200_DEVICE");
+  if (e) dev = atoi(e);
+  MPB(mpb_create(&g_ctx, dev, np, ctl->nq));
+  g_slot[0] = g_slot[1] = NULL;
+  g_np = np;
+  if (verbose()) printf("mptrac_b200: device context for %d parcels, %d quantities on GPU %d\n", np, ctl->nq, dev);
+}
+
+static void put_ctl(const ctl_t *c) {
+  mpb_ctl_t k;
+  memset(&k, 0, sizeof(k));
+  k.direction = c->direction; k.met_coord_type = c->met_coord_type; k.advect = c->advect;
+  k.advect_vert_coord = c->advect_vert_coord; k.rng_type = c->rng_type; k.diffusion = c->diffusion;
+  k.turb_pbl_scheme = c->turb_pbl_scheme; k.nq = c->nq; k.qnt_rp = c->qnt_rp; k.qnt_rhop = c->qnt_rhop;
+  k.qnt_ens = c->qnt_ens; k.nens = c->nens;
+  k.mixing_nx = c->mixing_nx; k.mixing_ny = c->mixing_ny; k.mixing_nz = c->mixing_nz;
+  const int mq[MPB_MIX_MAXQ] = {                      /* order of src/mptrac.c:5222-5230 */
+    c->qnt_m, c->qnt_vmr, c->qnt_Ch2o, c->qnt_Co3, c->qnt_Cco, c->qnt_Coh, c->qnt_Ch, c->qnt_Cho2,
+    c->qnt_Ch2o2, c->qnt_Co1d, c->qnt_Co3p, c->qnt_Cccl4, c->qnt_Cccl3f, c->qnt_Cccl2f2, c->qnt_Cn2o,
+    c->qnt_Csf6, c->qnt_aoa, c->qnt_Arn222, c->qnt_Apb210, c->qnt_Abe7, c->qnt_Acs137, c->qnt_Ai131, c->qnt_Axe133};
+  k.n_mix_qnt = MPB_MIX_MAXQ;
+  for (int i = 0; i < MPB_MIX_MAXQ; i++) k.mix_qnt[i] = mq[i];
+  k.t_start = c->t_start; k.t_stop = c->t_stop; k.dt_mod = c->dt_mod; k.dt_met = c->dt_met;
+  k.met_utm_ref_lat = c->met_utm_ref_lat; k.sort_dt = c->sort_dt;
+  k.turb_dx_pbl = c->turb_dx_pbl; k.turb_dx_trop = c->turb_dx_trop; k.turb_dx_strat = c->turb_dx_strat;
+  k.turb_dz_pbl = c->turb_dz_pbl; k.turb_dz_trop = c->turb_dz_trop; k.turb_dz_strat = c->turb_dz_strat;
+  k.turb_mesox = c->turb_mesox; k.turb_mesoz = c->turb_mesoz; k.turb_pbl_trans = c->turb_pbl_trans;
+  k.mixing_dt = c->mixing_dt; k.mixing_trop = c->mixing_trop; k.mixing_strat = c->mixing_strat;
+  k.mixing_lon0 = c->mixing_lon0; k.mixing_lon1 = c->mixing_lon1; k.mixing_lat0 = c->mixing_lat0;
+  k.mixing_lat1 = c->mixing_lat1; k.mixing_z0 = c->mixing_z0; k.mixing_z1 = c->mixing_z1;
+  MPB(mpb_set_ctl(g_ctx, &k));
+}
+
+static void put_met(met_t *m) {
+  int s = -1;
+  for (int i = 0; i < 2; i++) if (g_slot[i] == m) s = i;
+  if (s < 0) s = (g_slot[0] == NULL) ? 0 : (g_slot[1] == NULL ? 1 : 0);
+  mpb_met_view_t v;
+  v.time = m->time; v.coord_type = m->coord_type; v.nx = m->nx; v.ny = m->ny; v.np = m->np;
+  v.lon = m->lon; v.lat = m->lat; v.p = m->p;
+  v.u = &m->u[0][0][0]; v.v = &m->v[0][0][0]; v.w = &m->w[0][0][0]; v.t = &m->t[0][0][0];
+  v.ps = &m->ps[0][0]; v.pbl = &m->pbl[0][0];
+  v.sx = (int64_t) EY * EP; v.sy = EP; v.sx2 = EY;
+  MPB(mpb_set_met(g_ctx, s, &v));
+  g_slot[s] = m;
+  if (verbose()) printf("mptrac_b200: met level t=%.0f (%d x %d x %d) -> device slot %d\n", m->time, m->nx, m->ny, m->np, s);
+}
+
+static void put_atm(const atm_t *atm) {
+  MPB(mpb_set_atm(g_ctx, atm->np, atm->time, atm->p, atm->lon, atm->lat, &atm->q[0][0], NP));
+  g_dev_newer = 0;
+}
+
+static void get_atm(atm_t *atm) {
+  if (!g_ctx || !g_dev_newer) return;
+  MPB(mpb_get_atm(g_ctx, atm->time, atm->p, atm->lon, atm->lat, &atm->q[0][0], NP));
+  g_dev_newer = 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+
+void mptrac_update_device(const ctl_t *ctl, const cache_t *cache, const clim_t *clim, met_t **met0, met_t **met1,
+                          const atm_t *atm) {
+  SELECT_TIMER("UPDATE_DEVICE", "MEMORY");
+  static const ctl_t *last_ctl;
+  if (ctl) last_ctl = ctl;
+  if (atm) {
+    if (!last_ctl) ERRMSG("mptrac_b200: mptrac_update_device(atm) before the control parameters are known");
+    ensure_ctx(last_ctl, atm->np);
+  }
+  if (!g_ctx) return;              /* nothing to mirror yet (e.g. tools that never step) */
+  if (ctl) put_ctl(ctl);
+  else if (atm && last_ctl) put_ctl(last_ctl);
+  if (clim && clim->tropo_ntime > 0)
+    MPB(mpb_set_clim_tropo(g_ctx, clim->tropo_ntime, clim->tropo_nlat, clim->tropo_time, clim->tropo_lat, &clim->tropo[0][0]));
+  if (met0 && *met0) put_met(*met0);
+  if (met1 && *met1) put_met(*met1);
+  if (atm) put_atm(atm);
+  if (cache && g_np >= 0 && mpb_get_np(g_ctx) > 0) MPB(mpb_set_uvwp(g_ctx, &cache->uvwp[0][0]));
+}
+
+void mptrac_update_host(const ctl_t *ctl, const cache_t *cache, const clim_t *clim, met_t **met0, met_t **met1,
+                        const atm_t *atm) {
+  (void) ctl; (void) clim; (void) met0; (void) met1;   /* never modified on the device */
+  SELECT_TIMER("UPDATE_HOST", "MEMORY");
+  if (!g_ctx) return;
+  if (atm) get_atm((atm_t *) atm);
+  if (cache && mpb_get_np(g_ctx) > 0) {
+    MPB(mpb_get_uvwp(g_ctx, (float *) &cache->uvwp[0][0]));
+    MPB(mpb_get_dt(g_ctx, (double *) cache->dt));
+  }
+}
+
+void mptrac_free(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t *met0, met_t *met1, atm_t *atm, depo_t *depo, dd_t *dd) {
+  if (g_ctx) {
+    if (verbose()) printf("mptrac_b200: %lld kernel launches\n", (long long) mpb_launch_count(g_ctx));
+    MPB(mpb_destroy(g_ctx));
+    g_ctx = NULL; g_np = -1;
+  }
+  void (*real)(ctl_t *, cache_t *, clim_t *, met_t *, met_t *, atm_t *, depo_t *, dd_t *) = dlsym(RTLD_NEXT, "mptrac_free");
+  if (real) real(ctl, cache, clim, met0, met1, atm, depo, dd);
+}
+
+/* bring device slots in line with the (possibly swapped) host pointers, src/mptrac.c:6489-6491 */
+static void align_met(met_t *m0, met_t *m1) {
+  if (g_slot[0] == m1 && g_slot[1] == m0) {
+    MPB(mpb_swap_met(g_ctx));
+    const met_t *t = g_slot[0]; g_slot[0] = g_slot[1]; g_slot[1] = t;
+  }
+  if (g_slot[0] != m0) put_met(m0), align_met(m0, m1);
+  if (g_slot[1] != m1) put_met(m1);
+}
+
+/* run a reference CPU module with the host copy current; the device copy is refreshed afterwards */
+#define ON_HOST(stmt)                                                         \
+  do {                                                                        \
+    get_atm(atm);                                                             \
+    MPB(mpb_get_uvwp(g_ctx, &cache->uvwp[0][0]));                             \
+    MPB(mpb_get_dt(g_ctx, cache->dt));                                        \
+    stmt;                                                                     \
+    host_dirty = 1;                                                           \
+  } while (0)
+
+#define FLUSH_HOST()                                                          \
+  do {                                                                        \
+    if (host_dirty) { put_atm(atm); MPB(mpb_set_uvwp(g_ctx, &cache->uvwp[0][0])); host_dirty = 0; } \
+  } while (0)
+
+void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0, met_t **met1, atm_t *atm,
+                         depo_t *depo, double t, dd_t *dd) {
+  (void) dd;
+  if (!g_ctx) ERRMSG("mptrac_b200: mptrac_run_timestep before mptrac_init / mptrac_update_device");
+  if (ctl->advect_vert_coord != 0 || ctl->rng_type != 1)
+    ERRMSG("mptrac_b200: only ADVECT_VERT_COORD 0 and RNG_TYPE 1 run on the device");
+  SELECT_TIMER("MODULE_B200_STEP", "PHYSICS");
+  align_met(*met0, *met1);
+  int host_dirty = 0;
+
+  /* which reference modules does this control file enable that are NOT on the device path?
+     (conditions copied in meaning from the dispatcher, src/mptrac.c:7863-8000) */
+  const int init_cpu = (t == ctl->t_start) && ((ctl->isosurf >= 1 && ctl->isosurf <= 4) || 1 /* chem_init is unconditional */);
+  const int pbl_cpu = ctl->diffusion && ctl->turb_pbl_scheme == 1;
+  const int conv_cpu = (ctl->conv_mix_pbl || ctl->conv_cape >= 0) && (ctl->conv_dt <= 0 || fmod(t, ctl->conv_dt) == 0);
+  const int iso_cpu = ctl->isosurf >= 1 && ctl->isosurf <= 4;
+  const int meteo_cpu = ctl->met_dt_out > 0 && (ctl->met_dt_out < ctl->dt_mod || fmod(t, ctl->met_dt_out) == 0);
+  const int bound_cpu = (ctl->bound_lat0 < ctl->bound_lat1) && (ctl->bound_p0 > ctl->bound_p1);
+  const int decay_cpu = ctl->tdec_trop > 0 && ctl->tdec_strat > 0;
+  const int chemgrid_cpu = ctl->oh_chem_reaction != 0 || ctl->h2o2_chem_reaction != 0 || (ctl->kpp_chem && fmod(t, ctl->dt_kpp) == 0);
+  const int wet_cpu = (ctl->wet_depo_ic_a > 0 || ctl->wet_depo_ic_h[0] > 0) && (ctl->wet_depo_bc_a > 0 || ctl->wet_depo_bc_h[0] > 0);
+  const int tail_cpu = meteo_cpu || bound_cpu || ctl->qnt_loss_rate >= 0 || decay_cpu || chemgrid_cpu || ctl->oh_chem_reaction != 0 ||
+    ctl->h2o2_chem_reaction != 0 || ctl->tracer_chem || ctl->radio_decay || ctl->radio_depo || ctl->kpp_chem || wet_cpu || ctl->dry_depo_vdep > 0;
+
+  if (init_cpu) {
+    ON_HOST({
+      if (ctl->isosurf >= 1 && ctl->isosurf <= 4) module_isosurf_init(ctl, cache, *met0, *met1, atm);
+      module_chem_init(ctl, cache, clim, *met0, *met1, atm);
+    });
+    FLUSH_HOST();
+  }
+
+  if (!pbl_cpu && !conv_cpu && !iso_cpu && !tail_cpu) {
+    MPB(mpb_run_timestep(g_ctx, t));            /* the whole step is one fused launch (+ sort / mixing kernels) */
+  } else {
+    unsigned seg = MPB_MOD_TIMESTEPS | MPB_MOD_SORT | MPB_MOD_POSITION0 | MPB_MOD_ADVECT | MPB_MOD_DIFF_TURB;
+    if (pbl_cpu) {
+      MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0;
+      ON_HOST(module_diff_pbl(ctl, cache, *met0, *met1, atm));
+      FLUSH_HOST();
+    }
+    seg |= MPB_MOD_DIFF_MESO;
+    if (conv_cpu) {
+      MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0;
+      ON_HOST(module_convection(ctl, cache, *met0, *met1, atm));
+      FLUSH_HOST();
+    }
+    seg |= MPB_MOD_SEDI;
+    if (iso_cpu) {
+      MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0;
+      ON_HOST(module_isosurf(ctl, cache, *met0, *met1, atm));
+      FLUSH_HOST();
+    }
+    seg |= MPB_MOD_POSITION1;
+    MPB(mpb_run_modules(g_ctx, t, seg));
+    g_dev_newer = 1;
+    if (tail_cpu) {
+      /* everything after the final position check runs through the reference's own CPU code, in its order */
+      const int mix = ctl->mixing_trop >= 0 && ctl->mixing_strat >= 0 && (ctl->mixing_dt <= 0 || fmod(t, ctl->mixing_dt) == 0);
+      ON_HOST({
+        if (meteo_cpu) module_meteo(ctl, cache, clim, *met0, *met1, atm);
+        if (bound_cpu) module_bound_cond(ctl, cache, clim, *met0, *met1, atm);
+        if (ctl->qnt_loss_rate >= 0)
+          for (int ip = 0; ip < atm->np; ip++) if (cache->dt[ip] != 0) atm->q[ctl->qnt_loss_rate][ip] = 0;
+        if (decay_cpu) module_decay(ctl, cache, clim, atm);
+        if (mix) module_mixing(ctl, clim, atm, t);
+        if (chemgrid_cpu) module_chem_grid(ctl, *met0, *met1, atm, t);
+        if (ctl->oh_chem_reaction != 0) module_oh_chem(ctl, cache, clim, *met0, *met1, atm);
+        if (ctl->h2o2_chem_reaction != 0) module_h2o2_chem(ctl, cache, clim, *met0, *met1, atm);
+        if (ctl->tracer_chem) module_tracer_chem(ctl, cache, clim, *met0, *met1, atm);
+        if (ctl->radio_decay) module_radio_decay(ctl, cache, atm);
+        if (ctl->radio_depo) module_radio_depo(ctl, cache, *met0, *met1, atm, depo);
+        if (ctl->kpp_chem && fmod(t, ctl->dt_kpp) == 0) ERRMSG("mptrac_b200: KPP chemistry is not available");
+        if (wet_cpu) module_wet_depo(ctl, cache, *met0, *met1, atm);
+        if (ctl->dry_depo_vdep > 0) module_dry_depo(ctl, cache, *met0, *met1, atm);
+        if (bound_cpu) module_bound_cond(ctl, cache, clim, *met0, *met1, atm);
+      });
+      FLUSH_HOST();
+      g_dev_newer = 0;     /* host and device hold the same parcels now */
+    } else {
+      MPB(mpb_run_modules(g_ctx, t, MPB_MOD_MIXING));
+    }
+  }
+  if (!tail_cpu) g_dev_newer = 1;
+  if (!getenv("MPTRAC_B200_ASYNC")) MPB(mpb_sync(g_ctx));   /* keeps the reference's wall-clock timers honest */
+}

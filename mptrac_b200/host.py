@@ -201,6 +201,7 @@ def load_library(strict: bool = False) -> C.CDLL:
         "mpb_set_rng_ctr": (i32, [vp, u64]),
         "mpb_get_rng_ctr": (u64, [vp]),
         "mpb_run_timestep": (i32, [vp, dbl]),
+        "mpb_run_modules": (i32, [vp, dbl, C.c_uint]),
         "mpb_module_timesteps": (i32, [vp, dbl]),
         "mpb_module_position": (i32, [vp]),
         "mpb_module_advect": (i32, [vp]),
@@ -367,6 +368,9 @@ class Engine:
     # -- the step -------------------------------------------------------------------------------
     def run_timestep(self, t: float):
         self._ck(self._lib.mpb_run_timestep(self._h, float(t)))
+
+    def run_modules(self, t: float, mask: int):
+        self._ck(self._lib.mpb_run_modules(self._h, float(t), int(mask)))
 
     def module_timesteps(self, t: float):
         self._ck(self._lib.mpb_module_timesteps(self._h, float(t)))

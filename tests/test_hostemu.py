@@ -1,0 +1,99 @@
+"""The device physics source (mptrac_b200/csrc/physics.cuh), compiled for the HOST by tests/_hostemu, against the
+oracle.  This only exists because the development container has no GPU: it lets the per-parcel arithmetic of the
+kernels be debugged on the CPU.  It is test scaffolding -- not a product path, not a parity claim for the GPU build
+(those are the `-m gpu` tests)."""
+import ctypes as C
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+EMU_DIR = ROOT / "tests" / "_hostemu"
+
+
+class EmuCtl(C.Structure):
+    _fields_ = ([(n, C.c_double) for n in "t t_start t_stop dt_met utm_ref_lat dx_pbl dx_trop dx_strat dz_pbl dz_trop dz_strat mesox mesoz pbl_trans".split()]
+                + [("ctr_turb", C.c_uint64), ("ctr_meso", C.c_uint64)]
+                + [(n, C.c_int) for n in "direction pbl_scheme advect phys".split()] + [("modules", C.c_uint)])
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    so = EMU_DIR / "hostemu.so"
+    src = [EMU_DIR / "hostemu.cu", ROOT / "mptrac_b200" / "csrc" / "physics.cuh"]
+    if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in src):
+        subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off",
+                        "-shared", str(src[0]), "-o", str(so)], check=True)
+    return C.CDLL(str(so))
+
+
+def emu_timestep(emu, ctl, clim, m0, m1, a, t, ctr):
+    from oracle.oracle import met_struct
+    e = EmuCtl()
+    e.t, e.t_start, e.t_stop, e.dt_met, e.utm_ref_lat = t, ctl.t_start, ctl.t_stop, ctl.dt_met, ctl.met_utm_ref_lat
+    e.dx_pbl, e.dx_trop, e.dx_strat = ctl.turb_dx_pbl, ctl.turb_dx_trop, ctl.turb_dx_strat
+    e.dz_pbl, e.dz_trop, e.dz_strat = ctl.turb_dz_pbl, ctl.turb_dz_trop, ctl.turb_dz_strat
+    e.mesox, e.mesoz, e.pbl_trans = ctl.turb_mesox, ctl.turb_mesoz, ctl.turb_pbl_trans
+    e.direction, e.pbl_scheme, e.advect = ctl.direction, ctl.turb_pbl_scheme, ctl.advect
+    n, phys = a.np, 0
+    turb = ctl.diffusion and any(x > 0 for x in (ctl.turb_dx_pbl, ctl.turb_dz_pbl, ctl.turb_dx_trop, ctl.turb_dz_trop, ctl.turb_dx_strat, ctl.turb_dz_strat))
+    meso = ctl.diffusion and (ctl.turb_mesox > 0 or ctl.turb_mesoz > 0)
+    if turb:
+        phys |= 1; e.ctr_turb = ctr; ctr += 3 * n + 1
+    if meso:
+        phys |= 2; e.ctr_meso = ctr; ctr += 3 * n + 1
+    if ctl.qnt_rp >= 0 and ctl.qnt_rhop >= 0:
+        phys |= 4
+    e.phys, e.modules = phys, 1 | 2 | 64
+    s0, s1 = met_struct(m0), met_struct(m1)
+    rp = a.q[ctl.qnt_rp] if phys & 4 else a.time
+    rhop = a.q[ctl.qnt_rhop] if phys & 4 else a.time
+    vp = lambda x: C.c_void_p(x.ctypes.data)  # noqa: E731
+    rc = emu.emu_step(C.byref(s0), C.byref(s1), C.byref(e), clim[0].size, clim[1].size, vp(clim[0]), vp(clim[1]), vp(clim[2]),
+                      C.c_longlong(n), C.c_longlong(0), vp(a.time), vp(a.lon), vp(a.lat), vp(a.p), vp(a.dt), vp(a.uvwp), vp(rp), vp(rhop))
+    assert rc == 0
+    return ctr
+
+
+@pytest.mark.parametrize("advect", [1, 2, 4])
+@pytest.mark.parametrize("diffusion", [0, 1])
+@pytest.mark.parametrize("lat_desc", [False, True])
+@pytest.mark.parametrize("direction", [1, -1])
+def test_device_source_on_host_is_bit_exact(emu, oracle, advect, diffusion, lat_desc, direction):
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0, lat_descending=lat_desc)
+    n = 5000
+    _, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.05, zmax=45.0)
+    clim = synth.make_clim_tropo()
+    q = np.stack([np.full(n, 2.0), np.full(n, 1500.0)])
+    t_start = 0.0 if direction == 1 else 21600.0
+    ctl = Ctl(nq=2, qnt_rp=0, qnt_rhop=1, advect=advect, diffusion=diffusion, direction=direction, t_start=t_start,
+              t_stop=t_start + direction * 86400.0, dt_mod=300.0, dt_met=21600.0, turb_dz_trop=0.5, turb_dz_pbl=1.0,
+              turb_dx_strat=20.0, turb_pbl_trans=0.3)
+    tm = np.full(n, t_start)
+    a, b = Parcels(tm, p, lon, lat, q), Parcels(tm, p, lon, lat, q)
+    oracle.ctr = ctr = 0
+    for s in range(6):
+        ctr = emu_timestep(emu, ctl, clim, m0, m1, a, t_start + s * direction * 300.0, ctr)
+    oracle.run("timestep", ctl, clim, m0, m1, b, t=t_start, nsteps=6)
+    assert ctr == oracle.ctr
+    assert np.max(np.abs(b.lat - lat)) > 1e-3
+    for k in ("time", "lon", "lat", "p", "uvwp"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_device_sort_key_on_host(emu, oracle):
+    from mptrac_b200 import synth
+    from oracle.oracle import Parcels, met_struct
+    m0, _ = synth.make_met_pair(36, 19, 20, lat_descending=True)
+    tm, p, lon, lat = synth.make_parcels(20000, seed=3, zmin=0.0, zmax=70.0)
+    keys = np.zeros(tm.size, np.int32)
+    s0 = met_struct(m0)
+    emu.emu_sort_keys(C.byref(s0), C.c_longlong(tm.size), *[C.c_void_p(x.ctypes.data) for x in (lon, lat, p, keys)])
+    assert np.array_equal(keys, oracle.sort_keys(m0, Parcels(tm, p, lon, lat)))
