@@ -35,10 +35,10 @@ sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
     # name: (parcels per GPU, nlon, nlat, nlev, ctl overrides, algorithmic bytes per parcel-step excluding met, met fields)
-    "c2": dict(np=1_000_000, grid=(360, 181, 60), ctl=dict(advect=4, diffusion=0), state_bytes=64, met_fields=3,
-               desc="1M parcels, 1x1 deg x 60 levels (361x181x60), RK4 advection only"),
+    "c2": dict(np=1_000_000, grid=(360, 181, 60), ctl=dict(advect=4, diffusion=0, sort_dt=3600.0), state_bytes=64, met_fields=3,
+               desc="1M parcels, 1x1 deg x 60 levels (361x181x60), RK4 advection only, SORT_DT 3600 (cell sort every 12 steps, timed)"),
     "c3": dict(np=10_000_000, grid=(720, 361, 137), ctl=dict(advect=4, diffusion=1, turb_dx_pbl=0, turb_dx_trop=0,
-                                                              turb_dz_strat=0, qnt_rp=0, qnt_rhop=1, nq=2),
+                                                              turb_dz_strat=0, qnt_rp=0, qnt_rhop=1, nq=2, sort_dt=3600.0),
                state_bytes=104, met_fields=4,
                desc="10M parcels, 0.5x0.5 deg x 137 levels (721x361x137), RK4 + mesoscale diffusion + sedimentation"),
 }
@@ -130,8 +130,14 @@ def run_ours(args):
     ctl, m0, m1, (tm, p, lon, lat, q) = build_inputs(wl, rank, world)
     n = wl["np"]
 
+    # CPU arm first, in its own process, before this process touches CUDA (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_subprocess(args.workload, args.cpu_budget)
+
     eng = Engine(n, nq=ctl.nq, device=local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: the engine launches on it, the events time it
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     eng.set_ctl(ctl)
     eng.set_clim_tropo(*synth.make_clim_tropo())
@@ -256,8 +262,8 @@ def run_ours(args):
         "clocks": clk.summary(),
     }
     if rank == 0:
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_budget)
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
@@ -288,10 +294,24 @@ def cpu_baseline(workload, budget_s=20.0, steps=None):
         run = lambda t, k: orc.run("timestep", ctl, clim, m0, m1, atm, t=t, nsteps=k)   # noqa: E731
     run(0.0, 1)                 # dt = 0 step: touches everything once
     t0 = time.perf_counter(); run(DT_MOD, 1); one = time.perf_counter() - t0
-    k = steps or int(max(2, min(200, budget_s / max(one, 1e-3))))
+    k = steps or int(max(2, min(100, budget_s / max(one, 1e-3))))
     t0 = time.perf_counter(); run(2 * DT_MOD, k); el = time.perf_counter() - t0
     return {"value": n_sample * k / el, "unit": "particle-steps/s", "cores": cores, "kind": kind,
             "sample": f"{n_sample} parcels x {k} steps of the same workload ({el:.1f} s, OMP threads = {cores})"}
+
+
+def cpu_baseline_subprocess(workload, budget_s):
+    """Run the CPU arm in a fresh interpreter (no CUDA context, no torch thread pools next to the OpenMP team)."""
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", workload, "--cpu-budget", str(budget_s),
+           "--steps", "0", "--warmup", "1"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=max(180.0, 12 * budget_s))
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as exc:  # the CPU arm must never take the GPU number down with it
+        return {"error": repr(exc)}
 
 
 def run_reference(args):
@@ -303,8 +323,7 @@ def run_reference(args):
     if args.warmup > 0:
         cpu_baseline(args.workload, steps=1)
     # each "step" of this arm is a bounded sample: one model step over min(np, 1M) parcels on all host cores
-    per = max(1, min(args.steps, 10))
-    base = cpu_baseline(args.workload, steps=per)
+    base = cpu_baseline(args.workload, budget_s=args.cpu_budget, steps=(max(1, min(args.steps, 20)) if args.steps > 0 else None))
     v = base["value"]
     n_sample = min(wl["np"], 1_000_000)
     line = {"impl": "reference", "metric": "particle-steps/sec", "value": v, "unit": "particle-steps/s", "n_gpus": world,

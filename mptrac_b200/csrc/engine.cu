@@ -4,9 +4,10 @@
 // Data layout in HBM
 //   parcels   SoA fp64: time[np], p[np], lon[np], lat[np], q[nq][np_max]; dt[np]; uvwp float[np][3]
 //             (+ a second copy of the SoA used as the gather target of module_sort, then swapped)
-//   met       two time levels, each float4 node {u,v,w,T} [nx][ny][nz] (z fastest, 16 B/node: the two
-//             z-neighbours of a stencil column are one 32 B sector) and float2 {ps,pbl} [nx][ny];
-//             axes lon/lat/p fp64
+//   met       ONE array of 32-byte nodes {u0,v0,w0,T0,u1,v1,w1,T1} [nx][ny][nz] (z fastest) holding both bracketing
+//             time levels, so a stencil corner is one aligned 256-bit load (LDG.E.256) = one DRAM/L2 sector;
+//             float4 {ps0,pbl0,ps1,pbl1} [nx][ny]; axes lon/lat/p fp64 + per-interval reciprocals + a first-guess
+//             table for the pressure search
 //   clim      tropopause table fp64 [ntime][nlat] + its axes
 //
 // One fused kernel per model step does timesteps -> position -> advect -> diff_turb -> diff_meso ->
@@ -23,6 +24,7 @@
 #include <vector>
 
 #include "../../include/mptrac_b200.h"
+#include "met_tables.hpp"
 #include "physics.cuh"
 
 using namespace mpb;
@@ -137,15 +139,21 @@ static step_fn pick_step(int advect, unsigned phys) {
   }
 }
 
-// interleave four dense fields [n] into float4 nodes
+// write four dense fields [n] into time-level `slot` (0 / 1) of the interleaved nodes
 __global__ void pack_nodes_kernel(const float *u, const float *v, const float *w, const float *t,
-                                  float4 *out, size_t n) {
+                                  float4 *nodes, int slot, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = make_float4(u[i], v[i], w[i], t ? t[i] : 0.f);
+  if (i < n) nodes[2 * i + slot] = make_float4(u[i], v[i], w[i], t ? t[i] : 0.f);
 }
-__global__ void pack_surface_kernel(const float *ps, const float *pbl, float2 *out, size_t n) {
+__global__ void pack_surface_kernel(const float *ps, const float *pbl, float2 *surf, int slot, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = make_float2(ps ? ps[i] : 0.f, pbl ? pbl[i] : 0.f);
+  if (i < n) surf[2 * i + slot] = make_float2(ps ? ps[i] : 0.f, pbl ? pbl[i] : 0.f);
+}
+// exchange the two time levels in place (mptrac_get_met's pointer swap, src/mptrac.c:6489-6491)
+__global__ void swap_levels_kernel(float4 *nodes, size_t n, float2 *surf, size_t ncol) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float4 a = nodes[2 * i], b = nodes[2 * i + 1]; nodes[2 * i] = b; nodes[2 * i + 1] = a; }
+  if (i < ncol) { const float2 a = surf[2 * i], b = surf[2 * i + 1]; surf[2 * i] = b; surf[2 * i + 1] = a; }
 }
 
 __global__ void sort_keys_kernel(MetView met, const double *lon, const double *lat, const double *p,
@@ -252,8 +260,6 @@ __global__ void rng_fill_kernel(unsigned long long ctr0, double *rs, long long n
 // context
 // ------------------------------------------------------------------------------------------------
 struct MetLevel {
-  float4 *f = nullptr;
-  float2 *s = nullptr;
   double time = 0;
   bool valid = false;
 };
@@ -280,7 +286,11 @@ struct mpb_ctx {
 
   // met
   MetLevel lev[2];
-  double *ax_lon = nullptr, *ax_lat = nullptr, *ax_p = nullptr;
+  Node *nodes = nullptr;     // both levels interleaved
+  float4 *surf = nullptr;
+  double *ax_lon = nullptr, *ax_lat = nullptr, *ax_p = nullptr, *ax_rdlon = nullptr, *ax_rdlat = nullptr, *ax_rdp = nullptr;
+  unsigned short *p_lut = nullptr;
+  AxisTables tables;
   std::vector<double> h_lon, h_lat, h_p;
   int nx = 0, ny = 0, nz = 0, coord_type = 0;
   size_t node_cap = 0, col_cap = 0;
@@ -321,23 +331,13 @@ static void use(mpb_ctx *c) {
 
 static MetView met_view(const mpb_ctx *c) {
   REQUIRE(c->lev[0].valid && c->lev[1].valid, "both met levels must be set before stepping");
+  REQUIRE(c->lev[0].time != c->lev[1].time, "met0 and met1 carry the same time");
   MetView g;
-  g.f0 = c->lev[0].f; g.f1 = c->lev[1].f;
-  g.s0 = c->lev[0].s; g.s1 = c->lev[1].s;
+  g.f = c->nodes; g.s = c->surf;
   g.lon = c->ax_lon; g.lat = c->ax_lat; g.p = c->ax_p;
-  g.t0 = c->lev[0].time; g.t1 = c->lev[1].time;
-  g.nx = c->nx; g.ny = c->ny; g.nz = c->nz;
-  g.coord_type = c->coord_type;
-  g.lon_first = c->h_lon[0];
-  g.lon_last = c->h_lon[c->nx - 1];
-  g.lon_d = c->h_lon[1] - c->h_lon[0];
-  g.lat_lo = *std::min_element(c->h_lat.begin(), c->h_lat.end());
-  g.lat_hi = *std::max_element(c->h_lat.begin(), c->h_lat.end());
-  g.lon_asc = c->h_lon[0] < c->h_lon[c->nx - 1];
-  // direction test at the bisection midpoint, as the reference does (src/mptrac.c:3504)
-  { const int m = (c->ny - 1) >> 1; g.lat_asc = c->h_lat[m] < c->h_lat[m + 1]; }
-  { const int m = (c->nz - 1) >> 1; g.p_asc = c->h_p[m] < c->h_p[m + 1]; }
-  g.local = std::fabs(c->h_lon[c->nx - 1] - c->h_lon[0] - 360.0) >= 0.01;
+  g.rdlon = c->ax_rdlon; g.rdlat = c->ax_rdlat; g.rdp = c->ax_rdp; g.p_lut = c->p_lut;
+  fill_axis_scalars(g, c->h_lon.data(), c->nx, c->h_lat.data(), c->ny, c->h_p.data(), c->nz, c->coord_type,
+                    c->lev[0].time, c->lev[1].time, c->tables);
   return g;
 }
 
@@ -548,8 +548,8 @@ int mpb_destroy(mpb_ctx *c) {
   use(c);
   CK(cudaStreamSynchronize(c->stream));
   void *ptrs[] = {c->soa[0], c->soa[1], c->dt, c->uvwp, c->keys[0], c->keys[1], c->perm[0], c->perm[1],
-                  c->cub_tmp, c->lev[0].f, c->lev[0].s, c->lev[1].f, c->lev[1].s, c->ax_lon, c->ax_lat,
-                  c->ax_p, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_sum, c->mix_cnt,
+                  c->cub_tmp, c->nodes, c->surf, c->ax_lon, c->ax_lat, c->ax_p, c->ax_rdlon, c->ax_rdlat, c->ax_rdp,
+                  c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_sum, c->mix_cnt,
                   c->grid_sum, c->grid_sq, c->grid_cnt};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->stage_h) cudaFreeHost(c->stage_h);
@@ -608,17 +608,23 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
   REQUIRE(m && m->lon && m->lat && m->p && m->u && m->v && m->w, "met view lacks axes or wind fields");
   REQUIRE(m->nx >= 2 && m->ny >= 2 && m->np >= 2, "met grid needs at least 2 nodes per axis");
   const size_t nnode = (size_t)m->nx * m->ny * m->np, ncol = (size_t)m->nx * m->ny;
-  const bool regrid = (m->nx != c->nx || m->ny != c->ny || m->np != c->nz);
-  if (regrid) {
-    // a new grid shape invalidates the other level (src/mptrac.c:6545-6558 demands identical grids)
+  bool same_axes = (m->nx == c->nx && m->ny == c->ny && m->np == c->nz && m->coord_type == c->coord_type);
+  if (same_axes)
+    same_axes = std::equal(m->lon, m->lon + m->nx, c->h_lon.begin()) && std::equal(m->lat, m->lat + m->ny, c->h_lat.begin()) &&
+                std::equal(m->p, m->p + m->np, c->h_p.begin());
+  CK(cudaStreamSynchronize(c->stream));  // staging buffers are reused
+  if (!same_axes) {
+    // a new grid invalidates the other level too (src/mptrac.c:6545-6558 demands identical grids)
     c->lev[0].valid = c->lev[1].valid = false;
-    c->nx = m->nx; c->ny = m->ny; c->nz = m->np;
+    c->nx = m->nx; c->ny = m->ny; c->nz = m->np; c->coord_type = m->coord_type;
     if (nnode > c->node_cap) {
-      for (int i = 0; i < 2; i++) { if (c->lev[i].f) CK(cudaFree(c->lev[i].f)); CK(cudaMalloc(&c->lev[i].f, sizeof(float4) * nnode)); }
+      if (c->nodes) CK(cudaFree(c->nodes));
+      CK(cudaMalloc(&c->nodes, sizeof(Node) * nnode));
       c->node_cap = nnode;
     }
     if (ncol > c->col_cap) {
-      for (int i = 0; i < 2; i++) { if (c->lev[i].s) CK(cudaFree(c->lev[i].s)); CK(cudaMalloc(&c->lev[i].s, sizeof(float2) * ncol)); }
+      if (c->surf) CK(cudaFree(c->surf));
+      CK(cudaMalloc(&c->surf, sizeof(float4) * ncol));
       c->col_cap = ncol;
     }
     if (4 * nnode > c->stage_cap) {
@@ -628,19 +634,23 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
       CK(cudaMalloc(&c->stage_d, sizeof(float) * 4 * nnode));
       c->stage_cap = 4 * nnode;
     }
-    if (c->ax_lon) { CK(cudaFree(c->ax_lon)); CK(cudaFree(c->ax_lat)); CK(cudaFree(c->ax_p)); }
-    CK(cudaMalloc(&c->ax_lon, sizeof(double) * m->nx));
-    CK(cudaMalloc(&c->ax_lat, sizeof(double) * m->ny));
-    CK(cudaMalloc(&c->ax_p, sizeof(double) * m->np));
+    c->h_lon.assign(m->lon, m->lon + m->nx);
+    c->h_lat.assign(m->lat, m->lat + m->ny);
+    c->h_p.assign(m->p, m->p + m->np);
+    c->tables = build_axis_tables(m->lon, m->nx, m->lat, m->ny, m->p, m->np);
+    void **olds[] = {(void **)&c->ax_lon, (void **)&c->ax_lat, (void **)&c->ax_p, (void **)&c->ax_rdlon,
+                     (void **)&c->ax_rdlat, (void **)&c->ax_rdp, (void **)&c->p_lut};
+    for (void **o : olds) if (*o) { CK(cudaFree(*o)); *o = nullptr; }
+    auto up = [&](auto **dst, const auto &vec) {
+      using T = typename std::remove_reference<decltype(vec)>::type::value_type;
+      CK(cudaMalloc((void **)dst, sizeof(T) * std::max<size_t>(vec.size(), 1)));
+      CK(cudaMemcpyAsync(*dst, vec.data(), sizeof(T) * vec.size(), cudaMemcpyHostToDevice, c->stream));
+    };
+    up(&c->ax_lon, c->h_lon); up(&c->ax_lat, c->h_lat); up(&c->ax_p, c->h_p);
+    up(&c->ax_rdlon, c->tables.rdlon); up(&c->ax_rdlat, c->tables.rdlat); up(&c->ax_rdp, c->tables.rdp);
+    up(&c->p_lut, c->tables.p_lut);
+    CK(cudaStreamSynchronize(c->stream));
   }
-  CK(cudaStreamSynchronize(c->stream));  // staging buffers are reused
-  c->coord_type = m->coord_type;
-  c->h_lon.assign(m->lon, m->lon + m->nx);
-  c->h_lat.assign(m->lat, m->lat + m->ny);
-  c->h_p.assign(m->p, m->p + m->np);
-  CK(cudaMemcpyAsync(c->ax_lon, c->h_lon.data(), sizeof(double) * m->nx, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->ax_lat, c->h_lat.data(), sizeof(double) * m->ny, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->ax_p, c->h_p.data(), sizeof(double) * m->np, cudaMemcpyHostToDevice, c->stream));
 
   // compact the strided host fields into the pinned staging area (columns are contiguous runs of np floats)
   const float *src3[4] = {m->u, m->v, m->w, m->t};
@@ -655,7 +665,7 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
     CK(cudaMemcpyAsync(c->stage_d + (size_t)f * nnode, dst, sizeof(float) * nnode, cudaMemcpyHostToDevice, c->stream));
   }
   pack_nodes_kernel<<<nblocks((long long)nnode, 256), 256, 0, c->stream>>>(
-      c->stage_d, c->stage_d + nnode, c->stage_d + 2 * nnode, m->t ? c->stage_d + 3 * nnode : nullptr, c->lev[slot].f, nnode);
+      c->stage_d, c->stage_d + nnode, c->stage_d + 2 * nnode, m->t ? c->stage_d + 3 * nnode : nullptr, (float4 *)c->nodes, slot, nnode);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
 
@@ -669,7 +679,7 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
     CK(cudaMemcpyAsync(c->stage_d + (size_t)f * ncol, dst, sizeof(float) * ncol, cudaMemcpyHostToDevice, c->stream));
   }
   pack_surface_kernel<<<nblocks((long long)ncol, 256), 256, 0, c->stream>>>(
-      m->ps ? c->stage_d : nullptr, m->pbl ? c->stage_d + ncol : nullptr, c->lev[slot].s, ncol);
+      m->ps ? c->stage_d : nullptr, m->pbl ? c->stage_d + ncol : nullptr, (float2 *)c->surf, slot, ncol);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   c->launches += 2;
@@ -682,6 +692,12 @@ int mpb_swap_met(mpb_ctx *c) {
   API_BEGIN
   use(c);
   std::swap(c->lev[0], c->lev[1]);
+  const size_t nnode = (size_t)c->nx * c->ny * c->nz, ncol = (size_t)c->nx * c->ny;
+  if (nnode > 0 && c->nodes) {
+    swap_levels_kernel<<<nblocks((long long)nnode, 256), 256, 0, c->stream>>>((float4 *)c->nodes, nnode, (float2 *)c->surf, ncol);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
   API_END
 }
 
@@ -976,7 +992,7 @@ int64_t mpb_launch_count(mpb_ctx *c) { return c ? c->launches : -1; }
 int mpb_met_bytes(mpb_ctx *c, int64_t *bytes) {
   API_BEGIN
   REQUIRE(c && bytes, "null argument");
-  *bytes = 2ll * ((long long)c->nx * c->ny * c->nz * (long long)sizeof(float4) + (long long)c->nx * c->ny * (long long)sizeof(float2));
+  *bytes = (long long)c->nx * c->ny * c->nz * (long long)sizeof(Node) + (long long)c->nx * c->ny * (long long)sizeof(float4);
   API_END
 }
 

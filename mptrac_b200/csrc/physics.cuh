@@ -12,6 +12,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 #include <cuda_runtime.h>
 
 #define MPB_HD __host__ __device__ __forceinline__
@@ -48,13 +49,26 @@ enum : unsigned {
 // ----------------------------------------------------------------------------------------------
 // device views
 // ----------------------------------------------------------------------------------------------
+// One met node holds BOTH bracketing time levels: a 32-byte, 32-byte-aligned record that one 256-bit load
+// (LDG.E.256 on sm_100a) fetches as a single sector.
+struct alignas(32) Node {
+  float u0, v0, w0, t0;  // met0: u, v, w (omega), T
+  float u1, v1, w1, t1;  // met1
+};
+
 struct MetView {
-  const float4 *f0, *f1;  // [nx][ny][nz] nodes {u, v, w, T} of met0 / met1
-  const float2 *s0, *s1;  // [nx][ny] nodes {ps, pbl}
-  const double *lon, *lat, *p;  // axes
-  double t0, t1;          // met0->time, met1->time
-  double lon_first, lon_last, lon_d;   // lon[0], lon[nx-1], lon[1]-lon[0]
-  double lat_lo, lat_hi;  // min / max of the latitude axis
+  const Node *f;          // [nx][ny][nz], z fastest
+  const float4 *s;        // [nx][ny] {ps0, pbl0, ps1, pbl1}
+  const double *lon, *lat, *p;        // axes
+  const double *rdlon, *rdlat, *rdp;  // RN(1 / (x[i+1] - x[i])) per interval: divisions by grid constants
+                                      // become multiply + 2 FMA (Markstein) with the same rounding
+  const unsigned short *p_lut;        // first guess of the pressure interval from the high word of p
+  unsigned p_lut_base;                // high 32 bits of the smallest tabulated pressure
+  int p_lut_shift, p_lut_n;
+  double t0, t1, dt01, r_dt01;        // met0->time, met1->time, t1 - t0 and its reciprocal
+  double lon_first, lon_last, lon_d, r_lon_d;   // lon[0], lon[nx-1], lon[1]-lon[0] and its reciprocal
+  double lat_first, lat_scale;        // first guess of the latitude interval: (lat - lat_first) * lat_scale
+  double lat_lo, lat_hi;              // min / max of the latitude axis
   int nx, ny, nz;
   int coord_type;         // 0 lon/lat, 1 Cartesian
   int lon_asc, lat_asc, p_asc;
@@ -117,7 +131,24 @@ MPB_HD float f_mul(float a, float b) {
 #endif
 }
 
-// x - trunc(x / y) * y with the quotient truncated through int (src/mptrac.h:1121-1122)
+// x / d for a divisor d whose correctly rounded reciprocal rd = RN(1/d) is known: one multiply and two FMAs
+// (Markstein's correction step) instead of the ~30-instruction IEEE division sequence; the result is the
+// correctly rounded quotient for finite, normal operands, i.e. the same bits `x / d` gives on the CPU.
+MPB_HD double div_by(double x, double d, double rd) {
+  const double q = x * rd;
+  const double r = fma(-q, d, x);
+  return fma(r, rd, q);
+}
+
+constexpr double kR360 = 1.0 / 360.0;
+constexpr double kR1000 = 1.0 / 1000.0;
+constexpr double kRH0 = 1.0 / kH0;
+constexpr double kPiRE = kPi * kRE;
+constexpr double kRPiRE = 1.0 / (kPi * kRE);
+
+// x - trunc(x / 360) * 360 with the quotient truncated through int (FMOD, src/mptrac.h:1121-1122)
+MPB_HD double mod360(double x) { return x - (int)div_by(x, 360., kR360) * 360.; }
+// general form (cold paths)
 MPB_HD double mod_trunc(double x, double y) { return x - (int)(x / y) * y; }
 
 // y0 + (y1 - y0) / (x1 - x0) * (x - x0)  (src/mptrac.h:1351)
@@ -126,17 +157,17 @@ MPB_HD double lin(double x0, double y0, double x1, double y1, double x) {
 }
 
 // km -> hPa at pressure p (src/mptrac.h:941)
-MPB_HD double dz2dp(double dz, double p) { return -dz * p / kH0; }
+MPB_HD double dz2dp(double dz, double p) { return div_by(-dz * p, kH0, kRH0); }
 
 // metres east / north -> coordinate increment (src/mptrac.h:904-906, 922-923, 966, 989)
 MPB_HD double dx2coord(int coord_type, double dx, double lat) {
   if (coord_type != 0) return dx;
   if (lat < -89.999 || lat > 89.999) return 0.0;
-  return (dx / 1000.0) * 180. / (kPi * kRE * cos(lat * (kPi / 180.0)));
+  return div_by(dx, 1000.0, kR1000) * 180. / (kPiRE * cos(lat * (kPi / 180.0)));
 }
 MPB_HD double dy2coord(int coord_type, double dy) {
   if (coord_type != 0) return dy;
-  return (dy / 1000.0) * 180. / (kPi * kRE);
+  return div_by(div_by(dy, 1000.0, kR1000) * 180., kPiRE, kRPiRE);
 }
 
 // Interval search on a monotone axis; same result as the reference bisection (3495-3521):
@@ -157,8 +188,37 @@ MPB_HD int find_interval(const double *xx, int n, int ascending, double x) {
   return lo;
 }
 
+// Same result as find_interval, starting from a first guess i (any value): walk to the interval.  For a
+// monotone axis the answer of the reference bisection is unique, so the guess only affects the cost.
+MPB_HD int refine_interval(const double *xx, int n, int ascending, double x, int i) {
+  i = i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
+  if (ascending) {
+    while (i > 0 && ldg(xx + i) > x) i--;
+    while (i < n - 2 && ldg(xx + i + 1) <= x) i++;
+  } else {
+    while (i > 0 && ldg(xx + i) <= x) i--;
+    while (i < n - 2 && ldg(xx + i + 1) > x) i++;
+  }
+  return i;
+}
+
+MPB_HD unsigned hi_word(double x) {
+#ifdef __CUDA_ARCH__
+  return (unsigned)__double2hiint(x);
+#else
+  unsigned long long b;
+  memcpy(&b, &x, 8);
+  return (unsigned)(b >> 32);
+#endif
+}
+
 // Regular-axis index by division, clamped to [0, n-2] (3559-3574)
-MPB_HD int find_regular(double x0, double dx, int n, double x) {
+MPB_HD int find_regular(double x0, double dx, double rdx, int n, double x) {
+  const int i = (int)div_by(x - x0, dx, rdx);
+  return i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
+}
+// the same with a true division (cold paths: climatology axis)
+MPB_HD int find_regular_div(double x0, double dx, int n, double x) {
   const int i = (int)((x - x0) / dx);
   return i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
 }
@@ -166,7 +226,7 @@ MPB_HD int find_regular(double x0, double dx, int n, double x) {
 // horizontal range check before a lookup (2755-2803)
 MPB_HD void clamp_horizontal(const MetView &g, double lon, double lat, double &lon2, double &lat2) {
   if (g.coord_type == 0) {
-    lon2 = mod_trunc(lon, 360.);
+    lon2 = mod360(lon);
     if (lon2 < g.lon_first) lon2 += 360;
     else if (lon2 > g.lon_last) lon2 -= 360;
     lat2 = fmin(fmax(lat, g.lat_lo), g.lat_hi);
@@ -186,43 +246,68 @@ struct Stencil {
   double wx, wy, wz;  // weight of the LOWER index node along each axis (3015-3020)
 };
 
+MPB_HD int lat_interval(const MetView &g, double lat) {
+  return refine_interval(g.lat, g.ny, g.lat_asc, lat, (int)((lat - g.lat_first) * g.lat_scale));
+}
+
+MPB_HD int p_interval(const MetView &g, double p) {
+  const unsigned h = hi_word(p);
+  int k = h > g.p_lut_base ? (int)((h - g.p_lut_base) >> g.p_lut_shift) : 0;
+  k = k < g.p_lut_n ? k : g.p_lut_n - 1;
+  return refine_interval(g.p, g.nz, g.p_asc, p, (int)ldg(g.p_lut + k));
+}
+
+MPB_HD int lon_interval(const MetView &g, double lon) { return find_regular(g.lon_first, g.lon_d, g.r_lon_d, g.nx, lon); }
+
 MPB_HD void stencil_2d(const MetView &g, double lon, double lat, Stencil &s) {
   double lon2, lat2;
   clamp_horizontal(g, lon, lat, lon2, lat2);
-  s.ix = find_regular(g.lon_first, g.lon_d, g.nx, lon2);
-  s.iy = find_interval(g.lat, g.ny, g.lat_asc, lat2);
+  s.ix = lon_interval(g, lon2);
+  s.iy = lat_interval(g, lat2);
   const double x0 = ldg(g.lon + s.ix), x1 = ldg(g.lon + s.ix + 1);
   const double y0 = ldg(g.lat + s.iy), y1 = ldg(g.lat + s.iy + 1);
-  s.wx = (x1 - lon2) / (x1 - x0);
-  s.wy = (y1 - lat2) / (y1 - y0);
+  s.wx = div_by(x1 - lon2, x1 - x0, ldg(g.rdlon + s.ix));
+  s.wy = div_by(y1 - lat2, y1 - y0, ldg(g.rdlat + s.iy));
 }
 
 MPB_HD void stencil_3d(const MetView &g, double lon, double lat, double p, Stencil &s) {
   stencil_2d(g, lon, lat, s);
-  s.iz = find_interval(g.p, g.nz, g.p_asc, p);
+  s.iz = p_interval(g, p);
   const double p0 = ldg(g.p + s.iz), p1 = ldg(g.p + s.iz + 1);
-  s.wz = (p1 - p) / (p1 - p0);
+  s.wz = div_by(p1 - p, p1 - p0, ldg(g.rdp + s.iz));
 }
 
 // w * (lo - hi) + hi with the difference taken in fp32 first (3023-3038)
 MPB_HD double lerp_f32(double w, float lo, float hi) { return w * (double)f_sub(lo, hi) + (double)hi; }
 MPB_HD double lerp_f64(double w, double lo, double hi) { return w * (lo - hi) + hi; }
 
-struct Cube {  // the 8 corner nodes of one time level
-  float4 n000, n001, n010, n011, n100, n101, n110, n111;  // index order: x, y, z
+MPB_HD Node load_node(const Node *ptr) {
+#ifdef __CUDA_ARCH__
+  Node n;
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(n.u0), "=f"(n.v0), "=f"(n.w0), "=f"(n.t0), "=f"(n.u1), "=f"(n.v1), "=f"(n.w1), "=f"(n.t1)
+      : "l"(ptr));
+  return n;
+#else
+  return *ptr;
+#endif
+}
+
+struct Cube {  // the 8 corner nodes (both time levels each)
+  Node n000, n001, n010, n011, n100, n101, n110, n111;  // index order: x, y, z
 };
 
-MPB_HD void load_cube(const float4 *f, const MetView &g, const Stencil &s, Cube &c) {
+MPB_HD void load_cube(const MetView &g, const Stencil &s, Cube &c) {
   const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * (size_t)g.nz;
-  const float4 *b = f + ((size_t)s.ix * sx + (size_t)s.iy * sy + (size_t)s.iz);
-  c.n000 = ldg(b);
-  c.n001 = ldg(b + 1);
-  c.n010 = ldg(b + sy);
-  c.n011 = ldg(b + sy + 1);
-  c.n100 = ldg(b + sx);
-  c.n101 = ldg(b + sx + 1);
-  c.n110 = ldg(b + sx + sy);
-  c.n111 = ldg(b + sx + sy + 1);
+  const Node *b = g.f + ((size_t)s.ix * sx + (size_t)s.iy * sy + (size_t)s.iz);
+  c.n000 = load_node(b);
+  c.n001 = load_node(b + 1);
+  c.n010 = load_node(b + sy);
+  c.n011 = load_node(b + sy + 1);
+  c.n100 = load_node(b + sx);
+  c.n101 = load_node(b + sx + 1);
+  c.n110 = load_node(b + sx + sy);
+  c.n111 = load_node(b + sx + sy + 1);
 }
 
 #define MPB_TRILERP(member)                                              \
@@ -233,7 +318,7 @@ MPB_HD void load_cube(const float4 *f, const MetView &g, const Stencil &s, Cube 
                     lerp_f32(s.wz, c.n110.member, c.n111.member)))
 
 // time weight of met0 (3133)
-MPB_HD double time_weight(const MetView &g, double ts) { return (g.t1 - ts) / (g.t1 - g.t0); }
+MPB_HD double time_weight(const MetView &g, double ts) { return div_by(g.t1 - ts, g.dt01, g.r_dt01); }
 
 // u, v, w at (ts, p, lon, lat): intpol_met_time_3d x3 sharing one stencil (3112-3137, 3638-3643)
 MPB_HD void wind_at(const MetView &g, double ts, double lon, double lat, double p,
@@ -241,14 +326,11 @@ MPB_HD void wind_at(const MetView &g, double ts, double lon, double lat, double 
   Stencil s;
   stencil_3d(g, lon, lat, p, s);
   Cube c;
-  load_cube(g.f0, g, s, c);
-  const double u0 = MPB_TRILERP(x), v0 = MPB_TRILERP(y), w0 = MPB_TRILERP(z);
-  load_cube(g.f1, g, s, c);
-  const double u1 = MPB_TRILERP(x), v1 = MPB_TRILERP(y), w1 = MPB_TRILERP(z);
+  load_cube(g, s, c);
   const double wt = time_weight(g, ts);
-  u = lerp_f64(wt, u0, u1);
-  v = lerp_f64(wt, v0, v1);
-  w = lerp_f64(wt, w0, w1);
+  u = lerp_f64(wt, MPB_TRILERP(u0), MPB_TRILERP(u1));
+  v = lerp_f64(wt, MPB_TRILERP(v0), MPB_TRILERP(v1));
+  w = lerp_f64(wt, MPB_TRILERP(w0), MPB_TRILERP(w1));
 }
 
 // temperature at (ts, p, lon, lat)
@@ -256,11 +338,8 @@ MPB_HD double temperature_at(const MetView &g, double ts, double lon, double lat
   Stencil s;
   stencil_3d(g, lon, lat, p, s);
   Cube c;
-  load_cube(g.f0, g, s, c);
-  const double a0 = MPB_TRILERP(w);
-  load_cube(g.f1, g, s, c);
-  const double a1 = MPB_TRILERP(w);
-  return lerp_f64(time_weight(g, ts), a0, a1);
+  load_cube(g, s, c);
+  return lerp_f64(time_weight(g, ts), MPB_TRILERP(t0), MPB_TRILERP(t1));
 }
 
 // bilinear value of 4 corners with the nearest-neighbour rule for non-finite data (3084-3107)
@@ -284,12 +363,11 @@ MPB_HD void surface_at(const MetView &g, double ts, double lon, double lat, doub
   const size_t b = (size_t)s.ix * (size_t)g.ny + (size_t)s.iy;
   const size_t sx = (size_t)g.ny;
   const double wt = time_weight(g, ts);
-  float2 a00 = ldg(g.s0 + b), a01 = ldg(g.s0 + b + 1), a10 = ldg(g.s0 + b + sx), a11 = ldg(g.s0 + b + sx + 1);
+  const float4 a00 = ldg(g.s + b), a01 = ldg(g.s + b + 1), a10 = ldg(g.s + b + sx), a11 = ldg(g.s + b + sx + 1);
   const double ps0 = bilerp_guarded(s.wx, s.wy, a00.x, a01.x, a10.x, a11.x);
   const double pb0 = bilerp_guarded(s.wx, s.wy, a00.y, a01.y, a10.y, a11.y);
-  a00 = ldg(g.s1 + b); a01 = ldg(g.s1 + b + 1); a10 = ldg(g.s1 + b + sx); a11 = ldg(g.s1 + b + sx + 1);
-  const double ps1 = bilerp_guarded(s.wx, s.wy, a00.x, a01.x, a10.x, a11.x);
-  const double pb1 = bilerp_guarded(s.wx, s.wy, a00.y, a01.y, a10.y, a11.y);
+  const double ps1 = bilerp_guarded(s.wx, s.wy, a00.z, a01.z, a10.z, a11.z);
+  const double pb1 = bilerp_guarded(s.wx, s.wy, a00.w, a01.w, a10.w, a11.w);
   ps = time_blend_guarded(wt, ps0, ps1);
   pbl = time_blend_guarded(wt, pb0, pb1);
 }
@@ -315,8 +393,8 @@ MPB_HD double parcel_dt(const MetView &g, const CtlView &c, const Parcel &a) {
 // ----------------------------------------------------------------------------------------------
 MPB_HD void fix_position(const MetView &g, Parcel &a) {
   if (g.coord_type == 0) {
-    a.lon = mod_trunc(a.lon, 360.);
-    a.lat = mod_trunc(a.lat, 360.);
+    a.lon = mod360(a.lon);
+    a.lat = mod360(a.lat);
     while (a.lat < -90 || a.lat > 90) {
       if (a.lat > 90) { a.lat = 180 - a.lat; a.lon += 180; }
       if (a.lat < -90) { a.lat = -180 - a.lat; a.lon += 180; }
@@ -333,7 +411,8 @@ MPB_HD void fix_position(const MetView &g, Parcel &a) {
     a.p = ptop * ptop / a.p;
   } else if (a.p > 300.) {
     const size_t n11 = (size_t)g.ny + 1;
-    const double ps = time_blend_guarded(time_weight(g, a.time), (double)ldg(g.s0 + n11).x, (double)ldg(g.s1 + n11).x);
+    const float4 s11 = ldg(g.s + n11);
+    const double ps = time_blend_guarded(time_weight(g, a.time), (double)s11.x, (double)s11.z);
     if (a.p > ps) a.p = ps * ps / a.p;
   }
 }
@@ -412,7 +491,7 @@ MPB_HD double tropopause_pressure(const ClimView &cl, double t, double lat) {
   while (sec < 0) sec += kYear;
   const int it = find_interval(cl.time, cl.ntime, 1, sec);
   const double la0 = ldg(cl.lat), la1 = ldg(cl.lat + 1);
-  const int il = find_regular(la0, la1 - la0, cl.nlat, lat);
+  const int il = find_regular_div(la0, la1 - la0, cl.nlat, lat);
   const double y0 = ldg(cl.lat + il), y1 = ldg(cl.lat + il + 1);
   const double *row0 = cl.tropo + (size_t)it * cl.nlat + il;
   const double *row1 = row0 + cl.nlat;
@@ -511,40 +590,39 @@ struct Moments {
   }
 };
 
-MPB_HD void diffuse_mesoscale(const MetView &g, const CtlView &c, double dt, uint64_t ig,
+MPB_HD void diffuse_mesoscale(const MetView &g, const CtlView &k, double dt, uint64_t ig,
                               Parcel &a, float &up, float &vp, float &wp) {
   // raw index search at the parcel position: no wrap / clamp helper here (4283-4285)
   Stencil s;
-  s.ix = find_regular(g.lon_first, g.lon_d, g.nx, a.lon);
-  s.iy = find_interval(g.lat, g.ny, g.lat_asc, a.lat);
-  s.iz = find_interval(g.p, g.nz, g.p_asc, a.p);
+  s.ix = lon_interval(g, a.lon);
+  s.iy = lat_interval(g, a.lat);
+  s.iz = p_interval(g, a.p);
 
-  Cube c0, c1;
-  load_cube(g.f0, g, s, c0);
-  load_cube(g.f1, g, s, c1);
+  Cube c;
+  load_cube(g, s, c);
   Moments mu = {0.f, 0.f}, mv = {0.f, 0.f}, mw = {0.f, 0.f};
-#define MPB_ACC(node)                                              \
-  mu.add(c0.node.x); mv.add(c0.node.y); mw.add(c0.node.z);         \
-  mu.add(c1.node.x); mv.add(c1.node.y); mw.add(c1.node.z);
+#define MPB_ACC(node)                                        \
+  mu.add(c.node.u0); mv.add(c.node.v0); mw.add(c.node.w0);   \
+  mu.add(c.node.u1); mv.add(c.node.v1); mw.add(c.node.w1);
   MPB_ACC(n000) MPB_ACC(n001) MPB_ACC(n010) MPB_ACC(n011)
   MPB_ACC(n100) MPB_ACC(n101) MPB_ACC(n110) MPB_ACC(n111)
 #undef MPB_ACC
   const float usig = mu.sigma(), vsig = mv.sigma(), wsig = mw.sigma();
 
-  const double r = 1 - 2 * fabs(dt) / c.dt_met;
+  const double r = 1 - 2 * fabs(dt) / k.dt_met;
   const double r2 = sqrt(1 - r * r);
 
   double n0, n1, n2;
-  normals3(c.ctr_meso, ig, n0, n1, n2);
+  normals3(k.ctr_meso, ig, n0, n1, n2);
 
-  if (c.mesox > 0) {
-    up = (float)(r * up + r2 * n0 * c.mesox * usig);
+  if (k.mesox > 0) {
+    up = (float)(r * up + r2 * n0 * k.mesox * usig);
     a.lon += dx2coord(g.coord_type, up * dt, a.lat);
-    vp = (float)(r * vp + r2 * n1 * c.mesox * vsig);
+    vp = (float)(r * vp + r2 * n1 * k.mesox * vsig);
     a.lat += dy2coord(g.coord_type, vp * dt);
   }
-  if (c.mesoz > 0) {
-    wp = (float)(r * wp + r2 * n2 * c.mesoz * wsig);
+  if (k.mesoz > 0) {
+    wp = (float)(r * wp + r2 * n2 * k.mesoz * wsig);
     a.p += wp * dt;
   }
 }
@@ -573,10 +651,7 @@ MPB_HD void sediment(const MetView &g, double dt, double rp, double rhop, Parcel
 // cell key of module_sort (5909-5919): raw index searches, no wrap
 // ----------------------------------------------------------------------------------------------
 MPB_HD int cell_key(const MetView &g, double lon, double lat, double p) {
-  const int ix = find_regular(g.lon_first, g.lon_d, g.nx, lon);
-  const int iy = find_interval(g.lat, g.ny, g.lat_asc, lat);
-  const int iz = find_interval(g.p, g.nz, g.p_asc, p);
-  return (ix * g.ny + iy) * g.nz + iz;
+  return (lon_interval(g, lon) * g.ny + lat_interval(g, lat)) * g.nz + p_interval(g, p);
 }
 
 // altitude of a pressure (src/mptrac.h:2243)

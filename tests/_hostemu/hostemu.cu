@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../mptrac_b200/csrc/met_tables.hpp"
 #include "../../mptrac_b200/csrc/physics.cuh"
 
 using namespace mpb;
@@ -26,17 +27,40 @@ struct EmuCtl {
   unsigned modules;
 };
 
-static std::vector<float4> pack4(const EmuMet &m) {
-  const size_t n = (size_t)m.nx * m.ny * m.np;
-  std::vector<float4> o(n);
-  for (size_t i = 0; i < n; i++) o[i] = make_float4(m.u[i], m.v[i], m.w[i], m.t ? m.t[i] : 0.f);
+static std::vector<Node> pack_nodes(const EmuMet &m0, const EmuMet &m1) {
+  const size_t n = (size_t)m0.nx * m0.ny * m0.np;
+  std::vector<Node> o(n);
+  for (size_t i = 0; i < n; i++) {
+    o[i].u0 = m0.u[i]; o[i].v0 = m0.v[i]; o[i].w0 = m0.w[i]; o[i].t0 = m0.t ? m0.t[i] : 0.f;
+    o[i].u1 = m1.u[i]; o[i].v1 = m1.v[i]; o[i].w1 = m1.w[i]; o[i].t1 = m1.t ? m1.t[i] : 0.f;
+  }
   return o;
 }
-static std::vector<float2> pack2(const EmuMet &m) {
-  const size_t n = (size_t)m.nx * m.ny;
-  std::vector<float2> o(n);
-  for (size_t i = 0; i < n; i++) o[i] = make_float2(m.ps ? m.ps[i] : 0.f, m.pbl ? m.pbl[i] : 0.f);
+static std::vector<float4> pack_surf(const EmuMet &m0, const EmuMet &m1) {
+  const size_t n = (size_t)m0.nx * m0.ny;
+  std::vector<float4> o(n);
+  for (size_t i = 0; i < n; i++)
+    o[i] = make_float4(m0.ps ? m0.ps[i] : 0.f, m0.pbl ? m0.pbl[i] : 0.f, m1.ps ? m1.ps[i] : 0.f, m1.pbl ? m1.pbl[i] : 0.f);
   return o;
+}
+
+struct HostMet {
+  std::vector<Node> f;
+  std::vector<float4> s;
+  AxisTables t;
+  MetView g;
+};
+
+static void make_view(HostMet &h, const EmuMet *m0, const EmuMet *m1, bool with_fields) {
+  if (with_fields) { h.f = pack_nodes(*m0, *m1); h.s = pack_surf(*m0, *m1); }
+  h.t = build_axis_tables(m0->lon, m0->nx, m0->lat, m0->ny, m0->p, m0->np);
+  MetView &g = h.g;
+  std::memset(&g, 0, sizeof(g));
+  g.f = h.f.data(); g.s = h.s.data();
+  g.lon = m0->lon; g.lat = m0->lat; g.p = m0->p;
+  g.rdlon = h.t.rdlon.data(); g.rdlat = h.t.rdlat.data(); g.rdp = h.t.rdp.data(); g.p_lut = h.t.p_lut.data();
+  fill_axis_scalars(g, m0->lon, m0->nx, m0->lat, m0->ny, m0->p, m0->np, m0->coord_type, m0->time, m1 ? m1->time : m0->time + 1,
+                    h.t);
 }
 
 template <int ADVECT>
@@ -67,20 +91,9 @@ extern "C" int emu_step(const EmuMet *m0, const EmuMet *m1, const EmuCtl *e, int
                         const double *cl_lat, const double *cl_tropo, long long np, long long ig0, double *time,
                         double *lon, double *lat, double *p, double *dt, float *uvwp, const double *rp,
                         const double *rhop) {
-  std::vector<float4> f0 = pack4(*m0), f1 = pack4(*m1);
-  std::vector<float2> s0 = pack2(*m0), s1 = pack2(*m1);
-  MetView g;
-  g.f0 = f0.data(); g.f1 = f1.data(); g.s0 = s0.data(); g.s1 = s1.data();
-  g.lon = m0->lon; g.lat = m0->lat; g.p = m0->p;
-  g.t0 = m0->time; g.t1 = m1->time;
-  g.nx = m0->nx; g.ny = m0->ny; g.nz = m0->np; g.coord_type = m0->coord_type;
-  g.lon_first = m0->lon[0]; g.lon_last = m0->lon[g.nx - 1]; g.lon_d = m0->lon[1] - m0->lon[0];
-  g.lat_lo = g.lat_hi = m0->lat[0];
-  for (int i = 0; i < g.ny; i++) { g.lat_lo = fmin(g.lat_lo, m0->lat[i]); g.lat_hi = fmax(g.lat_hi, m0->lat[i]); }
-  g.lon_asc = m0->lon[0] < m0->lon[g.nx - 1];
-  { const int m = (g.ny - 1) >> 1; g.lat_asc = m0->lat[m] < m0->lat[m + 1]; }
-  { const int m = (g.nz - 1) >> 1; g.p_asc = m0->p[m] < m0->p[m + 1]; }
-  g.local = fabs(m0->lon[g.nx - 1] - m0->lon[0] - 360.0) >= 0.01;
+  HostMet h;
+  make_view(h, m0, m1, true);
+  const MetView &g = h.g;
   ClimView cl = {cl_time, cl_lat, cl_tropo, ntime, nlat};
   CtlView c;
   c.t = e->t; c.t_start = e->t_start; c.t_stop = e->t_stop; c.dt_met = e->dt_met; c.utm_ref_lat = e->utm_ref_lat;
@@ -99,11 +112,7 @@ extern "C" int emu_step(const EmuMet *m0, const EmuMet *m1, const EmuCtl *e, int
 }
 
 extern "C" void emu_sort_keys(const EmuMet *m0, long long np, const double *lon, const double *lat, const double *p, int *keys) {
-  MetView g;
-  std::memset(&g, 0, sizeof(g));
-  g.lon = m0->lon; g.lat = m0->lat; g.p = m0->p; g.nx = m0->nx; g.ny = m0->ny; g.nz = m0->np;
-  g.lon_first = m0->lon[0]; g.lon_d = m0->lon[1] - m0->lon[0];
-  { const int m = (g.ny - 1) >> 1; g.lat_asc = m0->lat[m] < m0->lat[m + 1]; }
-  { const int m = (g.nz - 1) >> 1; g.p_asc = m0->p[m] < m0->p[m + 1]; }
-  for (long long i = 0; i < np; i++) keys[i] = cell_key(g, lon[i], lat[i], p[i]);
+  HostMet h;
+  make_view(h, m0, nullptr, false);
+  for (long long i = 0; i < np; i++) keys[i] = cell_key(h.g, lon[i], lat[i], p[i]);
 }
