@@ -71,10 +71,17 @@ struct StepArgs {
 };
 
 constexpr unsigned PHYS_TURB = 1, PHYS_MESO = 2, PHYS_SEDI = 4;
-constexpr int kBlock = 128;
+// launch shape of the step kernel (compile-time so that variants can be swept: scripts/sweep_variants.sh)
+#ifndef MPB_BLOCK
+#define MPB_BLOCK 128
+#endif
+#ifndef MPB_MINBLOCKS
+#define MPB_MINBLOCKS 1
+#endif
+constexpr int kBlock = MPB_BLOCK;
 
 template <int ADVECT, unsigned PHYS>
-__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ StepArgs A) {
+__global__ void __launch_bounds__(kBlock, MPB_MINBLOCKS) step_kernel(const __grid_constant__ StepArgs A) {
   const long long ip = (long long)blockIdx.x * kBlock + threadIdx.x;
   if (ip >= A.np) return;
 
@@ -288,7 +295,8 @@ struct mpb_ctx {
   MetLevel lev[2];
   Node *nodes = nullptr;     // both levels interleaved
   float4 *surf = nullptr;
-  double *ax_lon = nullptr, *ax_lat = nullptr, *ax_p = nullptr, *ax_rdlon = nullptr, *ax_rdlat = nullptr, *ax_rdp = nullptr;
+  double *ax_lon = nullptr, *ax_lat = nullptr, *ax_p = nullptr;
+  AxisCell *ax_lonc = nullptr, *ax_latc = nullptr, *ax_pc = nullptr;
   unsigned short *p_lut = nullptr;
   AxisTables tables;
   std::vector<double> h_lon, h_lat, h_p;
@@ -335,7 +343,7 @@ static MetView met_view(const mpb_ctx *c) {
   MetView g;
   g.f = c->nodes; g.s = c->surf;
   g.lon = c->ax_lon; g.lat = c->ax_lat; g.p = c->ax_p;
-  g.rdlon = c->ax_rdlon; g.rdlat = c->ax_rdlat; g.rdp = c->ax_rdp; g.p_lut = c->p_lut;
+  g.lonc = c->ax_lonc; g.latc = c->ax_latc; g.pc = c->ax_pc; g.p_lut = c->p_lut;
   fill_axis_scalars(g, c->h_lon.data(), c->nx, c->h_lat.data(), c->ny, c->h_p.data(), c->nz, c->coord_type,
                     c->lev[0].time, c->lev[1].time, c->tables);
   return g;
@@ -548,7 +556,7 @@ int mpb_destroy(mpb_ctx *c) {
   use(c);
   CK(cudaStreamSynchronize(c->stream));
   void *ptrs[] = {c->soa[0], c->soa[1], c->dt, c->uvwp, c->keys[0], c->keys[1], c->perm[0], c->perm[1],
-                  c->cub_tmp, c->nodes, c->surf, c->ax_lon, c->ax_lat, c->ax_p, c->ax_rdlon, c->ax_rdlat, c->ax_rdp,
+                  c->cub_tmp, c->nodes, c->surf, c->ax_lon, c->ax_lat, c->ax_p, c->ax_lonc, c->ax_latc, c->ax_pc,
                   c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_sum, c->mix_cnt,
                   c->grid_sum, c->grid_sq, c->grid_cnt};
   for (void *p : ptrs) if (p) cudaFree(p);
@@ -638,8 +646,8 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
     c->h_lat.assign(m->lat, m->lat + m->ny);
     c->h_p.assign(m->p, m->p + m->np);
     c->tables = build_axis_tables(m->lon, m->nx, m->lat, m->ny, m->p, m->np);
-    void **olds[] = {(void **)&c->ax_lon, (void **)&c->ax_lat, (void **)&c->ax_p, (void **)&c->ax_rdlon,
-                     (void **)&c->ax_rdlat, (void **)&c->ax_rdp, (void **)&c->p_lut};
+    void **olds[] = {(void **)&c->ax_lon, (void **)&c->ax_lat, (void **)&c->ax_p, (void **)&c->ax_lonc,
+                     (void **)&c->ax_latc, (void **)&c->ax_pc, (void **)&c->p_lut};
     for (void **o : olds) if (*o) { CK(cudaFree(*o)); *o = nullptr; }
     auto up = [&](auto **dst, const auto &vec) {
       using T = typename std::remove_reference<decltype(vec)>::type::value_type;
@@ -647,7 +655,7 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
       CK(cudaMemcpyAsync(*dst, vec.data(), sizeof(T) * vec.size(), cudaMemcpyHostToDevice, c->stream));
     };
     up(&c->ax_lon, c->h_lon); up(&c->ax_lat, c->h_lat); up(&c->ax_p, c->h_p);
-    up(&c->ax_rdlon, c->tables.rdlon); up(&c->ax_rdlat, c->tables.rdlat); up(&c->ax_rdp, c->tables.rdp);
+    up(&c->ax_lonc, c->tables.lonc); up(&c->ax_latc, c->tables.latc); up(&c->ax_pc, c->tables.pc);
     up(&c->p_lut, c->tables.p_lut);
     CK(cudaStreamSynchronize(c->stream));
   }

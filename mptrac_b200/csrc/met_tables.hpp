@@ -13,7 +13,7 @@
 namespace mpb {
 
 struct AxisTables {
-  std::vector<double> rdlon, rdlat, rdp;
+  std::vector<AxisCell> lonc, latc, pc;   // one record per axis interval
   std::vector<unsigned short> p_lut;
   unsigned p_lut_base = 0;
   int p_lut_shift = 0;
@@ -38,10 +38,16 @@ inline int host_bisect(const double *xx, int n, double x) {  // the reference bi
 
 inline AxisTables build_axis_tables(const double *lon, int nx, const double *lat, int ny, const double *p, int nz) {
   AxisTables t;
-  t.rdlon.resize(nx - 1); t.rdlat.resize(ny - 1); t.rdp.resize(nz - 1);
-  for (int i = 0; i < nx - 1; i++) t.rdlon[i] = 1.0 / (lon[i + 1] - lon[i]);
-  for (int i = 0; i < ny - 1; i++) t.rdlat[i] = 1.0 / (lat[i + 1] - lat[i]);
-  for (int i = 0; i < nz - 1; i++) t.rdp[i] = 1.0 / (p[i + 1] - p[i]);
+  auto cells = [](const double *x, int n) {
+    std::vector<AxisCell> c((size_t)(n - 1));
+    for (int i = 0; i < n - 1; i++) {
+      c[i].lo = x[i]; c[i].hi = x[i + 1];
+      c[i].d = x[i + 1] - x[i];
+      c[i].rd = 1.0 / c[i].d;
+    }
+    return c;
+  };
+  t.lonc = cells(lon, nx); t.latc = cells(lat, ny); t.pc = cells(p, nz);
   // pressure first-guess table over the high word of the double (monotone in p for p > 0)
   double pmin = p[0], pmax = p[0];
   for (int i = 0; i < nz; i++) { pmin = std::min(pmin, p[i]); pmax = std::max(pmax, p[i]); }

@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 
 #define MPB_HD __host__ __device__ __forceinline__
+// rarely executed paths are kept out of line so that they cost neither registers nor instruction-cache lines on the hot path
+#define MPB_COLD __host__ __device__ __noinline__
 
 namespace mpb {
 
@@ -56,12 +58,18 @@ struct alignas(32) Node {
   float u1, v1, w1, t1;  // met1
 };
 
+// One interval of a grid axis: both end points, their difference and its correctly rounded reciprocal in one
+// 32-byte record, so that index verification and the interpolation weight need a single 256-bit load.
+struct alignas(32) AxisCell {
+  double lo, hi;  // x[i], x[i+1]
+  double d, rd;   // x[i+1] - x[i] and RN(1 / d): divisions by a grid constant become multiply + 2 FMA (Markstein)
+};
+
 struct MetView {
   const Node *f;          // [nx][ny][nz], z fastest
   const float4 *s;        // [nx][ny] {ps0, pbl0, ps1, pbl1}
-  const double *lon, *lat, *p;        // axes
-  const double *rdlon, *rdlat, *rdp;  // RN(1 / (x[i+1] - x[i])) per interval: divisions by grid constants
-                                      // become multiply + 2 FMA (Markstein) with the same rounding
+  const double *lon, *lat, *p;        // axes (slow paths, ptop)
+  const AxisCell *lonc, *latc, *pc;   // [n-1] intervals of each axis
   const unsigned short *p_lut;        // first guess of the pressure interval from the high word of p
   unsigned p_lut_base;                // high 32 bits of the smallest tabulated pressure
   int p_lut_shift, p_lut_n;
@@ -159,12 +167,31 @@ MPB_HD double lin(double x0, double y0, double x1, double y1, double x) {
 // km -> hPa at pressure p (src/mptrac.h:941)
 MPB_HD double dz2dp(double dz, double p) { return div_by(-dz * p, kH0, kRH0); }
 
-// metres east / north -> coordinate increment (src/mptrac.h:904-906, 922-923, 966, 989)
-MPB_HD double dx2coord(int coord_type, double dx, double lat) {
-  if (coord_type != 0) return dx;
-  if (lat < -89.999 || lat > 89.999) return 0.0;
-  return div_by(dx, 1000.0, kR1000) * 180. / (kPiRE * cos(lat * (kPi / 180.0)));
+// metres east / north -> coordinate increment (src/mptrac.h:904-906, 922-923, 966, 989).
+// DX2DEG(dx, lat) = dx * 180 / (pi * RE * cos(lat * pi / 180)), 0 within 0.001 deg of a pole.  The divisor only depends on
+// the latitude, and every Runge-Kutta stage of a step uses the same one (3659-3673): LonScale holds it together with
+// its correctly rounded reciprocal, so each further use costs a multiply and two FMAs instead of a cosine and a division
+// and still yields the correctly rounded quotient.
+struct LonScale {
+  double d, rd;
+  int mode;  // 0 = Cartesian (identity), 1 = polar cap (zero), 2 = divide by d
+};
+MPB_HD LonScale lon_scale(int coord_type, double lat) {
+  LonScale k;
+  k.d = 1.0; k.rd = 1.0;
+  if (coord_type != 0) { k.mode = 0; return k; }
+  if (lat < -89.999 || lat > 89.999) { k.mode = 1; return k; }
+  k.mode = 2;
+  k.d = kPiRE * cos(lat * (kPi / 180.0));
+  k.rd = 1.0 / k.d;
+  return k;
 }
+MPB_HD double dx2coord(const LonScale &k, double dx) {
+  if (k.mode == 0) return dx;
+  if (k.mode == 1) return 0.0;
+  return div_by(div_by(dx, 1000.0, kR1000) * 180., k.d, k.rd);
+}
+MPB_HD double dx2coord(int coord_type, double dx, double lat) { return dx2coord(lon_scale(coord_type, lat), dx); }
 MPB_HD double dy2coord(int coord_type, double dy) {
   if (coord_type != 0) return dy;
   return div_by(div_by(dy, 1000.0, kR1000) * 180., kPiRE, kRPiRE);
@@ -190,7 +217,7 @@ MPB_HD int find_interval(const double *xx, int n, int ascending, double x) {
 
 // Same result as find_interval, starting from a first guess i (any value): walk to the interval.  For a
 // monotone axis the answer of the reference bisection is unique, so the guess only affects the cost.
-MPB_HD int refine_interval(const double *xx, int n, int ascending, double x, int i) {
+static MPB_COLD int refine_interval(const double *xx, int n, int ascending, double x, int i) {
   i = i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
   if (ascending) {
     while (i > 0 && ldg(xx + i) > x) i--;
@@ -223,38 +250,88 @@ MPB_HD int find_regular_div(double x0, double dx, int n, double x) {
   return i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
 }
 
+// |x| < 360 from the high word alone (360.0 = 0x4076800000000000; its low word is zero)
+MPB_HD bool below_360(double x) { return (hi_word(x) & 0x7fffffffu) < 0x40768000u; }
+
+// FMOD(x, 360): for |x| < 360 the truncated quotient is 0 and x - 0 * 360 == x bit for bit, so the division is
+// only executed on the (rare) other side
+static MPB_COLD double mod360_cold(double x) { return mod360(x); }
+MPB_HD double wrap360(double x) { return below_360(x) ? x : mod360_cold(x); }
+
+MPB_HD double clamp_to(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }  // MIN(MAX(x, lo), hi)
+
 // horizontal range check before a lookup (2755-2803)
 MPB_HD void clamp_horizontal(const MetView &g, double lon, double lat, double &lon2, double &lat2) {
   if (g.coord_type == 0) {
-    lon2 = mod360(lon);
+    lon2 = wrap360(lon);
     if (lon2 < g.lon_first) lon2 += 360;
     else if (lon2 > g.lon_last) lon2 -= 360;
-    lat2 = fmin(fmax(lat, g.lat_lo), g.lat_hi);
+    lat2 = clamp_to(lat, g.lat_lo, g.lat_hi);
   } else {
     const double xlo = g.lon_asc ? g.lon_first : g.lon_last;
     const double xhi = g.lon_asc ? g.lon_last : g.lon_first;
-    lon2 = fmin(fmax(lon, xlo), xhi);
-    lat2 = fmin(fmax(lat, g.lat_lo), g.lat_hi);
+    lon2 = clamp_to(lon, xlo, xhi);
+    lat2 = clamp_to(lat, g.lat_lo, g.lat_hi);
   }
 }
 
 // ----------------------------------------------------------------------------------------------
 // met lookups
 // ----------------------------------------------------------------------------------------------
+MPB_HD AxisCell load_cell(const AxisCell *ptr) {
+#ifdef __CUDA_ARCH__
+  AxisCell c;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c.lo), "=d"(c.hi), "=d"(c.d), "=d"(c.rd) : "l"(ptr));
+  return c;
+#else
+  return *ptr;
+#endif
+}
+
 struct Stencil {
   int ix, iy, iz;
   double wx, wy, wz;  // weight of the LOWER index node along each axis (3015-3020)
 };
 
-MPB_HD int lat_interval(const MetView &g, double lat) {
-  return refine_interval(g.lat, g.ny, g.lat_asc, lat, (int)((lat - g.lat_first) * g.lat_scale));
+// Is [c.lo, c.hi] the interval i the reference bisection (3495-3521) returns for x?  The answer of that bisection on a
+// monotone axis is: ascending -- the largest i <= n-2 with xx[i] <= x (0 if none); descending -- the largest
+// i <= n-2 with xx[i] > x (0 if none).
+MPB_HD bool cell_holds(const AxisCell &c, int i, int n, int ascending, double x) {
+  const bool asc = ascending != 0, lo_gt = c.lo > x, hi_gt = c.hi > x;
+  const bool below_lo = (lo_gt == asc);    // ascending: lo > x, descending: lo <= x -- the answer lies at a smaller index
+  const bool above_hi = (hi_gt != asc);    // ascending: hi <= x, descending: hi > x -- ... at a larger index
+  return !(below_lo && i > 0) && !(above_hi && i < n - 2);
 }
 
-MPB_HD int p_interval(const MetView &g, double p) {
+// Interval + cell of an irregular axis from a first guess: one 256-bit load when the guess is right (it nearly always is),
+// the exact search otherwise.
+MPB_HD int locate_cell(const double *xx, const AxisCell *cells, int n, int ascending, double x, int guess, AxisCell &c) {
+  int i = guess < 0 ? 0 : (guess > n - 2 ? n - 2 : guess);
+  c = load_cell(cells + i);
+  if (!cell_holds(c, i, n, ascending, x)) {
+    i = refine_interval(xx, n, ascending, x, i);
+    c = load_cell(cells + i);
+  }
+  return i;
+}
+
+MPB_HD int lat_guess(const MetView &g, double lat) { return (int)((lat - g.lat_first) * g.lat_scale); }
+
+MPB_HD int p_guess(const MetView &g, double p) {
   const unsigned h = hi_word(p);
   int k = h > g.p_lut_base ? (int)((h - g.p_lut_base) >> g.p_lut_shift) : 0;
   k = k < g.p_lut_n ? k : g.p_lut_n - 1;
-  return refine_interval(g.p, g.nz, g.p_asc, p, (int)ldg(g.p_lut + k));
+  return (int)ldg(g.p_lut + k);
+}
+
+MPB_HD int lat_interval(const MetView &g, double lat) {
+  AxisCell c;
+  return locate_cell(g.lat, g.latc, g.ny, g.lat_asc, lat, lat_guess(g, lat), c);
+}
+
+MPB_HD int p_interval(const MetView &g, double p) {
+  AxisCell c;
+  return locate_cell(g.p, g.pc, g.nz, g.p_asc, p, p_guess(g, p), c);
 }
 
 MPB_HD int lon_interval(const MetView &g, double lon) { return find_regular(g.lon_first, g.lon_d, g.r_lon_d, g.nx, lon); }
@@ -263,18 +340,18 @@ MPB_HD void stencil_2d(const MetView &g, double lon, double lat, Stencil &s) {
   double lon2, lat2;
   clamp_horizontal(g, lon, lat, lon2, lat2);
   s.ix = lon_interval(g, lon2);
-  s.iy = lat_interval(g, lat2);
-  const double x0 = ldg(g.lon + s.ix), x1 = ldg(g.lon + s.ix + 1);
-  const double y0 = ldg(g.lat + s.iy), y1 = ldg(g.lat + s.iy + 1);
-  s.wx = div_by(x1 - lon2, x1 - x0, ldg(g.rdlon + s.ix));
-  s.wy = div_by(y1 - lat2, y1 - y0, ldg(g.rdlat + s.iy));
+  const AxisCell cx = load_cell(g.lonc + s.ix);
+  AxisCell cy;
+  s.iy = locate_cell(g.lat, g.latc, g.ny, g.lat_asc, lat2, lat_guess(g, lat2), cy);
+  s.wx = div_by(cx.hi - lon2, cx.d, cx.rd);
+  s.wy = div_by(cy.hi - lat2, cy.d, cy.rd);
 }
 
 MPB_HD void stencil_3d(const MetView &g, double lon, double lat, double p, Stencil &s) {
+  AxisCell cz;
+  s.iz = locate_cell(g.p, g.pc, g.nz, g.p_asc, p, p_guess(g, p), cz);
   stencil_2d(g, lon, lat, s);
-  s.iz = p_interval(g, p);
-  const double p0 = ldg(g.p + s.iz), p1 = ldg(g.p + s.iz + 1);
-  s.wz = div_by(p1 - p, p1 - p0, ldg(g.rdp + s.iz));
+  s.wz = div_by(cz.hi - p, cz.d, cz.rd);
 }
 
 // w * (lo - hi) + hi with the difference taken in fp32 first (3023-3038)
@@ -320,14 +397,13 @@ MPB_HD void load_cube(const MetView &g, const Stencil &s, Cube &c) {
 // time weight of met0 (3133)
 MPB_HD double time_weight(const MetView &g, double ts) { return div_by(g.t1 - ts, g.dt01, g.r_dt01); }
 
-// u, v, w at (ts, p, lon, lat): intpol_met_time_3d x3 sharing one stencil (3112-3137, 3638-3643)
-MPB_HD void wind_at(const MetView &g, double ts, double lon, double lat, double p,
+// u, v, w at (p, lon, lat) for the time weight wt: intpol_met_time_3d x3 sharing one stencil (3112-3137, 3638-3643)
+MPB_HD void wind_at(const MetView &g, double wt, double lon, double lat, double p,
                     double &u, double &v, double &w) {
   Stencil s;
   stencil_3d(g, lon, lat, p, s);
   Cube c;
   load_cube(g, s, c);
-  const double wt = time_weight(g, ts);
   u = lerp_f64(wt, MPB_TRILERP(u0), MPB_TRILERP(u1));
   v = lerp_f64(wt, MPB_TRILERP(v0), MPB_TRILERP(v1));
   w = lerp_f64(wt, MPB_TRILERP(w0), MPB_TRILERP(w1));
@@ -391,16 +467,23 @@ MPB_HD double parcel_dt(const MetView &g, const CtlView &c, const Parcel &a) {
 // gets is the time-blended surface pressure of grid node [1][1], not of the parcel's column.
 // That is what the reference's outputs contain, so it is reproduced here.
 // ----------------------------------------------------------------------------------------------
+static MPB_COLD void reflect_at_poles(double &lon, double &lat) {   // 5444-5468
+  lon = mod360(lon);
+  lat = mod360(lat);
+  while (lat < -90 || lat > 90) {
+    if (lat > 90) { lat = 180 - lat; lon += 180; }
+    if (lat < -90) { lat = -180 - lat; lon += 180; }
+  }
+  while (lon < -180) lon += 360;
+  while (lon >= 180) lon -= 360;
+}
+static MPB_COLD double reflect_p(double bound, double p) { return bound * bound / p; }
+
 MPB_HD void fix_position(const MetView &g, Parcel &a) {
   if (g.coord_type == 0) {
-    a.lon = mod360(a.lon);
-    a.lat = mod360(a.lat);
-    while (a.lat < -90 || a.lat > 90) {
-      if (a.lat > 90) { a.lat = 180 - a.lat; a.lon += 180; }
-      if (a.lat < -90) { a.lat = -180 - a.lat; a.lon += 180; }
-    }
-    while (a.lon < -180) a.lon += 360;
-    while (a.lon >= 180) a.lon -= 360;
+    // already canonical (|lon|, |lat| < 360 make both FMODs the identity): nothing to do
+    const bool canonical = below_360(a.lon) && a.lat >= -90 && a.lat <= 90 && a.lon >= -180 && a.lon < 180;
+    if (!canonical) reflect_at_poles(a.lon, a.lat);
   } else {
     double x, y;
     clamp_horizontal(g, a.lon, a.lat, x, y);
@@ -408,12 +491,12 @@ MPB_HD void fix_position(const MetView &g, Parcel &a) {
   }
   const double ptop = ldg(g.p + g.nz - 1);
   if (a.p < ptop) {
-    a.p = ptop * ptop / a.p;
+    a.p = reflect_p(ptop, a.p);
   } else if (a.p > 300.) {
     const size_t n11 = (size_t)g.ny + 1;
     const float4 s11 = ldg(g.s + n11);
     const double ps = time_blend_guarded(time_weight(g, a.time), (double)s11.x, (double)s11.z);
-    if (a.p > ps) a.p = ps * ps / a.p;
+    if (a.p > ps) a.p = reflect_p(ps, a.p);
   }
 }
 
@@ -425,6 +508,8 @@ MPB_HD void advect(const MetView &g, double dt, Parcel &a) {
   double um = 0, vm = 0, wm = 0;
   double u = 0, v = 0, w = 0;
   double lat_stage = a.lat;
+  const LonScale ks = lon_scale(g.coord_type, a.lat);   // the stages and (Euler, RK4) the final update share it
+  double wt = 0;
 #pragma unroll
   for (int i = 0; i < ORDER; i++) {
     double x, y, z, dts;
@@ -432,19 +517,20 @@ MPB_HD void advect(const MetView &g, double dt, Parcel &a) {
       dts = 0.0; x = a.lon; y = a.lat; z = a.p;
     } else {
       dts = (i == 3 ? 1.0 : 0.5) * dt;
-      x = a.lon + dx2coord(g.coord_type, dts * u, a.lat);
+      x = a.lon + dx2coord(ks, dts * u);
       y = a.lat + dy2coord(g.coord_type, dts * v);
       z = a.p + dts * w;
     }
     lat_stage = y;
-    wind_at(g, a.time + dts, x, y, z, u, v, w);
+    if (i != 2) wt = time_weight(g, a.time + dts);   // stages 1 and 2 are taken at the same time
+    wind_at(g, wt, x, y, z, u, v, w);
     double k = 1.0;
     if (ORDER == 2) k = (i == 0 ? 0.0 : 1.0);
     else if (ORDER == 4) k = (i == 0 || i == 3 ? 1.0 / 6.0 : 2.0 / 6.0);
     um += k * u; vm += k * v; wm += k * w;
   }
   a.time += dt;
-  a.lon += dx2coord(g.coord_type, dt * um, ORDER == 2 ? lat_stage : a.lat);
+  a.lon += (ORDER == 2) ? dx2coord(g.coord_type, dt * um, lat_stage) : dx2coord(ks, dt * um);
   a.lat += dy2coord(g.coord_type, dt * vm);
   a.p += dt * wm;
 }

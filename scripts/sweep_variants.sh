@@ -1,0 +1,24 @@
+#!/bin/bash
+# Build launch-shape variants of the step kernel (here, no GPU needed) or time them (on the GPU box).
+#   scripts/sweep_variants.sh build            -> mptrac_b200/_lib/variants/<name>/libmptrac_b200.so
+#   scripts/sweep_variants.sh run [workload]   -> gpurun_out/sweep_<workload>.jsonl (one bench line per variant)
+set -u
+cd "$(dirname "$0")/.."
+V=mptrac_b200/_lib/variants
+VARIANTS="${VARIANTS:-b128m1 b128m5 b128m6 b128m8 b256m2 b256m3 b256m4 b64m10 b64m12}"
+case "${1:-build}" in
+  build)
+    for v in $VARIANTS; do
+      b=${v#b}; b=${b%m*}; m=${v#*m}
+      mkdir -p $V/$v
+      nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fopenmp -shared \
+        -DMPB_BLOCK=$b -DMPB_MINBLOCKS=$m ${EXTRA:-} mptrac_b200/csrc/engine.cu -o $V/$v/libmptrac_b200.so &
+    done; wait; ls $V ;;
+  run)
+    WL=${2:-c2}; mkdir -p gpurun_out; : > gpurun_out/sweep_$WL.jsonl
+    for v in $VARIANTS; do
+      echo "== $v" >&2
+      MPTRAC_B200_LIBDIR=$PWD/$V/$v MPB_BENCH_NO_SUSTAIN=1 timeout 600 python bench.py --workload $WL --no-cpu --steps 36 --warmup 13 2>/dev/null \
+        | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(json.dumps({'variant':'$v','ms_per_step':d['ms_per_step'],'b2b_ms':d['back_to_back']['ms_per_step'],'value':d['value'],'frac':d['roofline']['frac']}))" | tee -a gpurun_out/sweep_$WL.jsonl
+    done ;;
+esac

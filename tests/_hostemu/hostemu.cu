@@ -58,7 +58,7 @@ static void make_view(HostMet &h, const EmuMet *m0, const EmuMet *m1, bool with_
   std::memset(&g, 0, sizeof(g));
   g.f = h.f.data(); g.s = h.s.data();
   g.lon = m0->lon; g.lat = m0->lat; g.p = m0->p;
-  g.rdlon = h.t.rdlon.data(); g.rdlat = h.t.rdlat.data(); g.rdp = h.t.rdp.data(); g.p_lut = h.t.p_lut.data();
+  g.lonc = h.t.lonc.data(); g.latc = h.t.latc.data(); g.pc = h.t.pc.data(); g.p_lut = h.t.p_lut.data();
   fill_axis_scalars(g, m0->lon, m0->nx, m0->lat, m0->ny, m0->p, m0->np, m0->coord_type, m0->time, m1 ? m1->time : m0->time + 1,
                     h.t);
 }

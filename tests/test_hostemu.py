@@ -25,7 +25,7 @@ def emu():
     if shutil.which("nvcc") is None:
         pytest.skip("nvcc not available")
     so = EMU_DIR / "hostemu.so"
-    src = [EMU_DIR / "hostemu.cu", ROOT / "mptrac_b200" / "csrc" / "physics.cuh"]
+    src = [EMU_DIR / "hostemu.cu", ROOT / "mptrac_b200" / "csrc" / "physics.cuh", ROOT / "mptrac_b200" / "csrc" / "met_tables.hpp"]
     if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in src):
         subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off",
                         "-shared", str(src[0]), "-o", str(so)], check=True)
