@@ -46,6 +46,37 @@ DT_MOD = 300.0
 DT_MET = 21600.0
 
 
+T0 = time.perf_counter()
+
+
+def _log(msg):
+    """Progress marker on stderr (a stalled run then shows where it stopped)."""
+    print(f"[bench {time.perf_counter() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def host_cores() -> int:
+    """Cores this process may actually use: the affinity mask, capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    for f in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = Path(f).read_text().split()
+            if f.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = float(txt[0])
+                per = float(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+                if q > 0:
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 def peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -130,11 +161,7 @@ def run_ours(args):
     ctl, m0, m1, (tm, p, lon, lat, q) = build_inputs(wl, rank, world)
     n = wl["np"]
 
-    # CPU arm first, in its own process, before this process touches CUDA (rank 0, N = 1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline_subprocess(args.workload, args.cpu_budget)
-
+    _log(f"inputs ready ({args.workload}, rank {rank}/{world})")
     eng = Engine(n, nq=ctl.nq, device=local)
     stream = torch.cuda.Stream()          # a real (non-default) stream: the engine launches on it, the events time it
     torch.cuda.set_stream(stream)
@@ -151,9 +178,6 @@ def run_ours(args):
     hn = {k: v.numpy() for k, v in host.items()}
     hqn = hq.numpy() if hq is not None else None
 
-    def upload():
-        eng.set_atm(hn["time"], hn["p"], hn["lon"], hn["lat"], hqn)
-
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     K, W = args.steps, args.warmup
 
@@ -162,63 +186,86 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    class Model:
+        """Model clock of the run.  Like the reference driver (mptrac_get_met, src/mptrac.c:6489-6499) it rolls the two
+        met levels forward when the clock reaches the later one -- swap + upload of a new level, alternating the two
+        synthetic fields -- so that every timed step interpolates INSIDE the met interval however long the run is."""
+        def __init__(self):
+            self.t, self.t1, self.rolls, self.lev = 0.0, DT_MET, 0, [m0, m1]
+
+        def next_t(self):
+            self.t += DT_MOD
+            if self.t > self.t1:
+                from dataclasses import replace
+                self.t1 += DT_MET
+                eng.swap_met()
+                eng.set_met(1, replace(self.lev[self.rolls % 2], time=self.t1))
+                self.rolls += 1
+            return self.t
+
+    model = Model()
+
     # ---------------- device-resident timing: per-step events, L2 flushed between steps ----------------
-    upload()
-    t_model = DT_MOD  # first step with dt != 0
-    for _ in range(W):
-        eng.run_timestep(t_model)
-        t_model += DT_MOD
+    _log("engine ready; device-resident timing")
+    eng.set_atm(hn["time"], hn["p"], hn["lon"], hn["lat"], hqn)
+    spinup = int(round(wl["ctl"].get("sort_dt", 0.0) / DT_MOD))    # reach the first cell sort: steady state of a long run
+    for _ in range(spinup + W):
+        eng.run_timestep(model.next_t())
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    launches0 = eng.launch_count
+    launches = 0
     barrier()
     with ClockSampler(local) as clk:
         wall0 = time.perf_counter()
         for k in range(K):
+            t_next = model.next_t()          # (a met roll, every 72 steps, happens here: outside the step's events)
             flush.zero_()
+            l0 = eng.launch_count
             ev[k][0].record(stream)
-            eng.run_timestep(t_model)
+            eng.run_timestep(t_next)
             ev[k][1].record(stream)
-            t_model += DT_MOD
+            launches += eng.launch_count - l0     # kernels of ours inside the timed events
         barrier()
         wall1 = time.perf_counter()
-        launches = eng.launch_count - launches0
         # the timed region lasts only milliseconds; keep the identical load running (untimed) for ~1 s so that the
         # 100 ms nvidia-smi sampler sees the clocks this kernel runs at
         t_end = time.perf_counter() + (0.0 if os.environ.get("MPB_BENCH_NO_SUSTAIN") else max(0.0, 1.0 - (wall1 - wall0)))
         while time.perf_counter() < t_end:
-            for _ in range(50):
-                eng.run_timestep(t_model)
-                t_model += DT_MOD
+            for _ in range(24):
+                eng.run_timestep(model.next_t())
             torch.cuda.synchronize()
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     total_ms = float(step_ms.sum())
 
     # ---------------- back-to-back (no flush), one bracket ----------------
+    _log("back-to-back timing")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rolls0 = model.rolls
     barrier()
     e0.record(stream)
     for k in range(K):
-        eng.run_timestep(t_model)
-        t_model += DT_MOD
+        eng.run_timestep(model.next_t())
     e1.record(stream)
     barrier()
     b2b_ms = e0.elapsed_time(e1)
+    b2b_rolls = model.rolls - rolls0
 
     # ---------------- end to end through the C ABI with host buffers ----------------
-    out = {"time": hn["time"], "p": hn["p"], "lon": hn["lon"], "lat": hn["lat"], "q": hqn}
+    # every step: parcels go host -> device, are stepped and come back (mpb_run_timestep_host pipelines the three
+    # chunk by chunk); the host arrays are what the caller reads after each step
+    _log("end-to-end timing")
+    eng.get_atm({"time": hn["time"], "p": hn["p"], "lon": hn["lon"], "lat": hn["lat"], "q": hqn})
     for _ in range(max(W, 3)):
-        upload(); eng.run_timestep(t_model); eng.get_atm(out); hn["time"][:] = t_model - DT_MOD
+        eng.run_timestep_host(model.next_t(), hn["time"], hn["p"], hn["lon"], hn["lat"], hqn)
     barrier()
     e0.record(stream)
     for k in range(K):
-        hn["time"][:] = t_model - DT_MOD   # parcels are "at" the previous model time so that dt = DT_MOD
-        upload()
-        eng.run_timestep(t_model)
-        eng.get_atm(out)                    # synchronous D2H of the result
+        eng.run_timestep_host(model.next_t(), hn["time"], hn["p"], hn["lon"], hn["lat"], hqn)
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
-    bytes_io = 32 * n + (8 * ctl.nq * n)
+    h2d_bytes = 32 * n + (16 * n if ctl.nq else 0)     # time, p, lon, lat (+ rp, rhop when sedimentation is on)
+    d2h_bytes = 32 * n
+    checksum = float(hn["lat"][:: max(1, n // 1024)].sum())   # the result is read on the host
 
     def allmax(x):
         if world == 1:
@@ -253,19 +300,24 @@ def run_ours(args):
         "config": {"workload": f"BASELINE configs[{1 if args.workload == 'c2' else 2}]: {wl['desc']}", "parcels_per_gpu": n,
                    "dt_mod_s": DT_MOD, "l2": "flushed between steps (256 MiB memset outside the per-step events)",
                    "parallelism": f"parcels sharded contiguously over {world} GPU(s), no data-path collective"},
-        "back_to_back": {"value": units / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / K, "note": "no L2 flush, one event bracket around K steps"},
-        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io,
-                "ms_per_step": e2e_ms / K},
+        "back_to_back": {"value": units / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / K, "met_rolls_inside": b2b_rolls,
+                         "note": "no L2 flush, one event bracket around K steps"},
+        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": e2e_ms / K, "api": "mpb_run_timestep_host (pinned host arrays in, same arrays out, every step)",
+                "host_checksum": checksum},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel": "step_kernel", "peak_source": peak_src},
         "clocks": clk.summary(),
     }
-    if rank == 0:
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
     eng.close()
+    if rank == 0:
+        # CPU arm last, in its own process with a hard deadline: it can never take the GPU numbers down with it
+        if world == 1 and not args.no_cpu:
+            _log("cpu_baseline leg")
+            line["cpu_baseline"] = cpu_baseline_subprocess(args.workload, args.cpu_budget)
+        print(json.dumps(line), flush=True)
+    _log("done")
     if world > 1:
         dist.destroy_process_group()
 
@@ -279,7 +331,7 @@ def cpu_baseline(workload, budget_s=20.0, steps=None):
     n_sample = min(wl["np"], 1_000_000)
     sl = slice(0, n_sample)
     atm = Parcels(tm[sl], p[sl], lon[sl], lat[sl], None if q is None else q[:, sl])
-    cores = os.cpu_count() or 1
+    cores = int(os.environ.get("OMP_NUM_THREADS", "0")) or host_cores()
     if reference_available():
         kind = "reference"
         ref = Reference()
@@ -301,15 +353,27 @@ def cpu_baseline(workload, budget_s=20.0, steps=None):
 
 
 def cpu_baseline_subprocess(workload, budget_s):
-    """Run the CPU arm in a fresh interpreter (no CUDA context, no torch thread pools next to the OpenMP team)."""
+    """Run the CPU arm in a fresh interpreter (no CUDA context, no torch thread pools next to the OpenMP team) with a
+    hard deadline; the whole process group is killed when it is exceeded."""
+    import signal
     cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", workload, "--cpu-budget", str(budget_s),
            "--steps", "0", "--warmup", "1"]
+    deadline = max(120.0, 8 * budget_s)
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=max(180.0, 12 * budget_s))
-        for ln in reversed(r.stdout.strip().splitlines()):
+        pr = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+        try:
+            out, err = pr.communicate(timeout=deadline)
+        except subprocess.TimeoutExpired:
+            os.killpg(pr.pid, signal.SIGKILL)
+            try:
+                out, err = pr.communicate(timeout=10)
+            except subprocess.TimeoutExpired:
+                out, err = "", "unresponsive after SIGKILL"
+            return {"error": f"cpu arm exceeded {deadline:.0f} s", "stderr": (err or "")[-300:]}
+        for ln in reversed(out.strip().splitlines()):
             if ln.startswith("{"):
                 return json.loads(ln)["cpu_baseline"]
-        return {"error": (r.stderr or r.stdout)[-300:]}
+        return {"error": (err or out)[-300:]}
     except Exception as exc:  # the CPU arm must never take the GPU number down with it
         return {"error": repr(exc)}
 
@@ -318,6 +382,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if "OMP_NUM_THREADS" not in os.environ:
+        # the OpenMP runtime reads this when the reference library is loaded (below); os.cpu_count() would count
+        # cores a container may not use
+        os.environ["OMP_NUM_THREADS"] = str(host_cores())
+    _log(f"reference arm on {os.environ['OMP_NUM_THREADS']} OpenMP threads")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl = WORKLOADS[args.workload]
     if args.warmup > 0:

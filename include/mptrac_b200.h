@@ -119,6 +119,16 @@ uint64_t mpb_get_rng_ctr(mpb_ctx *ctx);
  *     modules on the path; all enabled modules run fused in ONE kernel per step. --- */
 int mpb_run_timestep(mpb_ctx *ctx, double t);
 
+/* The same step for parcels that live in HOST memory (the driver's atm_t): stands in for the sequence
+ * mptrac_update_device(atm) -> mptrac_run_timestep -> mptrac_update_host(atm) (src/mptrac.c:8005, :7851, :8061) that a
+ * caller needs when it wants the parcels back after every step.  The arrays are cut into chunks that are uploaded,
+ * stepped and downloaded in a software pipeline over several streams, so the PCIe transfers of both directions and the
+ * kernels overlap; the result is identical to the three calls.  Pinned host memory makes the copies truly
+ * asynchronous; pageable memory works but serialises them.  Synchronous: the arrays are valid on return.
+ * Only the quantities the path reads (rp, rhop) are uploaded; no quantity is downloaded (the path does not modify any). */
+int mpb_run_timestep_host(mpb_ctx *ctx, double t, int64_t np, double *time, double *p, double *lon, double *lat,
+                          double *q, int64_t q_stride);
+
 /* A sub-sequence of the step, for callers that interleave modules of their own (the shim does this for
  * reference modules that are not on the device path).  `mask` selects modules, which still run in the
  * reference's order and only if the control parameters enable them; adjacent selected modules are fused into one

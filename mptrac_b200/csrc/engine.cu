@@ -76,9 +76,15 @@ constexpr unsigned PHYS_TURB = 1, PHYS_MESO = 2, PHYS_SEDI = 4;
 #define MPB_BLOCK 128
 #endif
 #ifndef MPB_MINBLOCKS
-#define MPB_MINBLOCKS 1
+#define MPB_MINBLOCKS 4
+#endif
+#ifndef MPB_CUBE_F64
+#define MPB_CUBE_F64 0
 #endif
 constexpr int kBlock = MPB_BLOCK;
+constexpr int kLanes = 4;                       // concurrent chunk pipelines of mpb_run_timestep_host
+constexpr long long kHostChunkMin = 16384;      // parcels per chunk: at least 128 KiB per array ...
+constexpr long long kHostChunkMax = 1 << 20;    // ... at most 8 MiB
 
 template <int ADVECT, unsigned PHYS>
 __global__ void __launch_bounds__(kBlock, MPB_MINBLOCKS) step_kernel(const __grid_constant__ StepArgs A) {
@@ -102,16 +108,26 @@ __global__ void __launch_bounds__(kBlock, MPB_MINBLOCKS) step_kernel(const __gri
 
   const unsigned long long ig = (unsigned long long)(A.ig0 + ip);
 
+  Cube cube;   // the met cell this parcel sits in, shared by every lookup of the step
+  cube_reset(cube);
   if (A.modules & MOD_POS_PRE) fix_position(A.met, a);
-  if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a);
+#if MPB_CUBE_F64
+  if (ADVECT > 0) {
+    WindCube wc;
+    cube_reset(wc);
+    advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, wc);
+  }
+#else
+  if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, cube);
+#endif
   if (PHYS & PHYS_TURB) diffuse_turbulent(A.met, A.clim, A.ctl, dt, ig, a);
   if (PHYS & PHYS_MESO) {
     float *s = A.uvwp + 3 * ip;
     float up = s[0], vp = s[1], wp = s[2];
-    diffuse_mesoscale(A.met, A.ctl, dt, ig, a, up, vp, wp);
+    diffuse_mesoscale(A.met, A.ctl, dt, ig, a, up, vp, wp, cube);
     s[0] = up; s[1] = vp; s[2] = wp;
   }
-  if (PHYS & PHYS_SEDI) sediment(A.met, dt, A.rp[ip], A.rhop[ip], a);
+  if (PHYS & PHYS_SEDI) sediment(A.met, dt, A.rp[ip], A.rhop[ip], a, cube);
   if (A.modules & MOD_POS_POST) fix_position(A.met, a);
 
   if (ADVECT > 0) A.time[ip] = a.time;
@@ -322,6 +338,11 @@ struct mpb_ctx {
   mpb_ctl_t ctl;
   bool have_ctl = false;
 
+  // host-resident stepping (mpb_run_timestep_host): streams that each carry whole chunks
+  cudaStream_t lane[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t lane_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t lane_go = nullptr;
+
   double *arr(int which) const { return soa[cur] + (size_t)which * np_max; }  // 0 time 1 p 2 lon 3 lat 4+ q
   double *time() const { return arr(0); }
   double *p() const { return arr(1); }
@@ -385,7 +406,8 @@ static unsigned long long rng_draw(mpb_ctx *c) {  // one module_rng(â€¦, 3*np, â
   return start;
 }
 
-static void launch_step(mpb_ctx *c, double t, int advect, unsigned phys, unsigned modules) {
+// kernel arguments of one (possibly restricted) step over all parcels; draws the module random-number counters
+static StepArgs step_args(mpb_ctx *c, double t, int advect, unsigned phys, unsigned modules) {
   REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
   StepArgs A;
   A.met = met_view(c);
@@ -407,11 +429,24 @@ static void launch_step(mpb_ctx *c, double t, int advect, unsigned phys, unsigne
   }
   A.np = c->np; A.ig0 = c->ig0; A.modules = modules;
   if (advect > 0) REQUIRE(c->ctl.advect_vert_coord == 0, "only ADVECT_VERT_COORD 0 runs on the device");
-  if (c->np == 0) return;
+  return A;
+}
+
+// launch the step kernel for parcels [off, off + cnt) on `stream`
+static void launch_range(mpb_ctx *c, StepArgs A, int advect, unsigned phys, long long off, long long cnt, cudaStream_t stream) {
+  if (cnt <= 0) return;
+  A.time += off; A.lon += off; A.lat += off; A.p += off; A.dt += off; A.uvwp += 3 * off;
+  if (A.rp) { A.rp += off; A.rhop += off; }
+  A.np = cnt; A.ig0 += off;
   step_fn fn = pick_step(advect, phys);
-  fn<<<nblocks(c->np, kBlock), kBlock, 0, c->stream>>>(A);
+  fn<<<nblocks(cnt, kBlock), kBlock, 0, stream>>>(A);
   CK(cudaGetLastError());
   c->launches++;
+}
+
+static void launch_step(mpb_ctx *c, double t, int advect, unsigned phys, unsigned modules) {
+  const StepArgs A = step_args(c, t, advect, phys, modules);
+  launch_range(c, A, advect, phys, 0, c->np, c->stream);
 }
 
 static void ensure_boxes(mpb_ctx *c) {
@@ -561,6 +596,11 @@ int mpb_destroy(mpb_ctx *c) {
                   c->grid_sum, c->grid_sq, c->grid_cnt};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->stage_h) cudaFreeHost(c->stage_h);
+  for (int i = 0; i < kLanes; i++) {
+    if (c->lane[i]) cudaStreamDestroy(c->lane[i]);
+    if (c->lane_done[i]) cudaEventDestroy(c->lane_done[i]);
+  }
+  if (c->lane_go) cudaEventDestroy(c->lane_go);
   cudaStreamDestroy(c->own_stream);
   delete c;
   API_END
@@ -828,6 +868,73 @@ int mpb_run_timestep(mpb_ctx *c, double t) {
   API_BEGIN
   use(c);
   run_modules(c, t, MPB_MOD_ALL);
+  API_END
+}
+
+// One model step for parcels that live in HOST memory: chunk k+1 uploads while chunk k computes and chunk k-1 downloads.
+// Each of kLanes streams carries whole chunks (H2D -> step kernel -> D2H in stream order); the copy engines of the two
+// directions and the SMs overlap across lanes.  The result equals mpb_set_atm + mpb_run_timestep + mpb_get_atm.
+int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double *p, double *lon, double *lat,
+                          double *q, int64_t q_stride) {
+  API_BEGIN
+  use(c);
+  REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
+  REQUIRE(np >= 0 && np <= c->np_max, "np exceeds the context capacity");
+  REQUIRE(np == 0 || (time && p && lon && lat), "null parcel array");
+  const mpb_ctl_t &k = c->ctl;
+  const bool sort_now = k.sort_dt > 0 && hits(t, k.sort_dt);
+  const bool mix_now = k.mixing_trop >= 0 && k.mixing_strat >= 0 && (k.mixing_dt <= 0 || hits(t, k.mixing_dt)) && k.n_mix_qnt > 0;
+  if (sort_now || mix_now || np < 4 * kHostChunkMin) {
+    // steps with a global phase (cell sort, box means) and tiny problems take the plain sequence
+    REQUIRE(mpb_set_atm(c, np, time, p, lon, lat, q, q_stride) == 0, g_err);
+    run_modules(c, t, MPB_MOD_ALL);
+    REQUIRE(mpb_get_atm(c, time, p, lon, lat, q, q_stride) == 0, g_err);
+    return 0;
+  }
+  c->np = np;
+  unsigned phys = 0;
+  if (turb_enabled(k)) phys |= PHYS_TURB;
+  if (meso_enabled(k)) phys |= PHYS_MESO;
+  if (sedi_enabled(k)) phys |= PHYS_SEDI;
+  REQUIRE(!(phys & PHYS_SEDI) || q != nullptr, "null quantity array");
+  const StepArgs A = step_args(c, t, k.advect, phys, MOD_TIMESTEPS | MOD_POS_PRE | MOD_POS_POST);
+  if (!c->lane[0]) {
+    for (int i = 0; i < kLanes; i++) {
+      CK(cudaStreamCreateWithFlags(&c->lane[i], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&c->lane_done[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&c->lane_go, cudaEventDisableTiming));
+  }
+  // everything already queued on the context's stream (met uploads, earlier steps) comes first
+  CK(cudaEventRecord(c->lane_go, c->stream));
+  for (int i = 0; i < kLanes; i++) CK(cudaStreamWaitEvent(c->lane[i], c->lane_go, 0));
+  long long chunk = (np + 2 * kLanes - 1) / (2 * kLanes);
+  chunk = std::max<long long>(kHostChunkMin, std::min<long long>(chunk, kHostChunkMax));
+  chunk = (chunk + kBlock - 1) / kBlock * kBlock;
+  int lane = 0;
+  for (long long off = 0; off < np; off += chunk, lane = (lane + 1) % kLanes) {
+    const long long cnt = std::min<long long>(chunk, np - off);
+    const size_t bytes = sizeof(double) * (size_t)cnt;
+    cudaStream_t st = c->lane[lane];
+    CK(cudaMemcpyAsync(c->time() + off, time + off, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->p() + off, p + off, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->lon() + off, lon + off, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->lat() + off, lat + off, bytes, cudaMemcpyHostToDevice, st));
+    if (phys & PHYS_SEDI) {   // the only quantities the path reads; none is modified
+      CK(cudaMemcpyAsync(c->q(k.qnt_rp) + off, q + (size_t)k.qnt_rp * q_stride + off, bytes, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(c->q(k.qnt_rhop) + off, q + (size_t)k.qnt_rhop * q_stride + off, bytes, cudaMemcpyHostToDevice, st));
+    }
+    launch_range(c, A, k.advect, phys, off, cnt, st);
+    CK(cudaMemcpyAsync(time + off, c->time() + off, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p + off, c->p() + off, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(lon + off, c->lon() + off, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(lat + off, c->lat() + off, bytes, cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < kLanes; i++) {
+    CK(cudaEventRecord(c->lane_done[i], c->lane[i]));
+    CK(cudaStreamWaitEvent(c->stream, c->lane_done[i], 0));   // later work on the context's stream sees the step
+  }
+  for (int i = 0; i < kLanes; i++) CK(cudaStreamSynchronize(c->lane[i]));   // the host arrays are valid on return
   API_END
 }
 

@@ -370,9 +370,16 @@ MPB_HD Node load_node(const Node *ptr) {
 #endif
 }
 
-struct Cube {  // the 8 corner nodes (both time levels each)
+// The 8 corner nodes (both time levels each) of one grid cell.  A Cube outlives a single lookup: the Runge-Kutta stages
+// of a step, the mesoscale statistics and the sedimentation lookup nearly always fall into the SAME cell (a stage moves
+// a parcel by a few km, a cell is ~100 km x 1 km), so the cube is fetched once per step and only re-fetched by the
+// threads whose cell changed.  That takes the scattered 32-byte gathers -- the kernel's first limiter, the L1 data pipe
+// -- from 4-6 per parcel-step to little more than one.
+struct Cube {
   Node n000, n001, n010, n011, n100, n101, n110, n111;  // index order: x, y, z
+  int ix, iy, iz;                                        // the cell held; ix < 0 = nothing yet
 };
+MPB_HD void cube_reset(Cube &c) { c.ix = -1; c.iy = -1; c.iz = -1; }
 
 MPB_HD void load_cube(const MetView &g, const Stencil &s, Cube &c) {
   const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * (size_t)g.nz;
@@ -385,6 +392,12 @@ MPB_HD void load_cube(const MetView &g, const Stencil &s, Cube &c) {
   c.n101 = load_node(b + sx + 1);
   c.n110 = load_node(b + sx + sy);
   c.n111 = load_node(b + sx + sy + 1);
+  c.ix = s.ix; c.iy = s.iy; c.iz = s.iz;
+}
+
+// make c hold the cell of s
+MPB_HD void fetch_cube(const MetView &g, const Stencil &s, Cube &c) {
+  if (c.ix != s.ix || c.iy != s.iy || c.iz != s.iz) load_cube(g, s, c);
 }
 
 #define MPB_TRILERP(member)                                              \
@@ -398,23 +411,65 @@ MPB_HD void load_cube(const MetView &g, const Stencil &s, Cube &c) {
 MPB_HD double time_weight(const MetView &g, double ts) { return div_by(g.t1 - ts, g.dt01, g.r_dt01); }
 
 // u, v, w at (p, lon, lat) for the time weight wt: intpol_met_time_3d x3 sharing one stencil (3112-3137, 3638-3643)
-MPB_HD void wind_at(const MetView &g, double wt, double lon, double lat, double p,
+MPB_HD void wind_at(const MetView &g, double wt, double lon, double lat, double p, Cube &c,
                     double &u, double &v, double &w) {
   Stencil s;
   stencil_3d(g, lon, lat, p, s);
-  Cube c;
-  load_cube(g, s, c);
+  fetch_cube(g, s, c);
   u = lerp_f64(wt, MPB_TRILERP(u0), MPB_TRILERP(u1));
   v = lerp_f64(wt, MPB_TRILERP(v0), MPB_TRILERP(v1));
   w = lerp_f64(wt, MPB_TRILERP(w0), MPB_TRILERP(w1));
 }
 
-// temperature at (ts, p, lon, lat)
-MPB_HD double temperature_at(const MetView &g, double ts, double lon, double lat, double p) {
+// Alternative cube for the wind lookups (build flag MPB_CUBE_F64): per (x, y) column and field the upper-level value
+// and the fp32 difference "lower - upper", both already promoted to fp64.  A lookup in an unchanged cell then needs no
+// F2F.F64.F32 conversions at all (they run at 16 lanes/clk/SM and are the kernel's second limiter), at the price of 96
+// live registers.
+struct WindCube {
+  double hi[4][6], df[4][6];   // [column (x0y0, x0y1, x1y0, x1y1)][u0, v0, w0, u1, v1, w1]
+  int ix, iy, iz;
+};
+MPB_HD void cube_reset(WindCube &c) { c.ix = -1; c.iy = -1; c.iz = -1; }
+
+MPB_HD void fetch_cube(const MetView &g, const Stencil &s, WindCube &c) {
+  if (c.ix == s.ix && c.iy == s.iy && c.iz == s.iz) return;
+  const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * (size_t)g.nz;
+  const Node *b = g.f + ((size_t)s.ix * sx + (size_t)s.iy * sy + (size_t)s.iz);
+  const size_t off[4] = {0, sy, sx, sx + sy};
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const Node lo = load_node(b + off[j]), hi = load_node(b + off[j] + 1);
+    c.hi[j][0] = (double)hi.u0; c.df[j][0] = (double)f_sub(lo.u0, hi.u0);
+    c.hi[j][1] = (double)hi.v0; c.df[j][1] = (double)f_sub(lo.v0, hi.v0);
+    c.hi[j][2] = (double)hi.w0; c.df[j][2] = (double)f_sub(lo.w0, hi.w0);
+    c.hi[j][3] = (double)hi.u1; c.df[j][3] = (double)f_sub(lo.u1, hi.u1);
+    c.hi[j][4] = (double)hi.v1; c.df[j][4] = (double)f_sub(lo.v1, hi.v1);
+    c.hi[j][5] = (double)hi.w1; c.df[j][5] = (double)f_sub(lo.w1, hi.w1);
+  }
+  c.ix = s.ix; c.iy = s.iy; c.iz = s.iz;
+}
+
+MPB_HD double trilerp(const Stencil &s, const WindCube &c, int k) {
+  return lerp_f64(s.wx,
+                  lerp_f64(s.wy, s.wz * c.df[0][k] + c.hi[0][k], s.wz * c.df[1][k] + c.hi[1][k]),
+                  lerp_f64(s.wy, s.wz * c.df[2][k] + c.hi[2][k], s.wz * c.df[3][k] + c.hi[3][k]));
+}
+
+MPB_HD void wind_at(const MetView &g, double wt, double lon, double lat, double p, WindCube &c,
+                    double &u, double &v, double &w) {
   Stencil s;
   stencil_3d(g, lon, lat, p, s);
-  Cube c;
-  load_cube(g, s, c);
+  fetch_cube(g, s, c);
+  u = lerp_f64(wt, trilerp(s, c, 0), trilerp(s, c, 3));
+  v = lerp_f64(wt, trilerp(s, c, 1), trilerp(s, c, 4));
+  w = lerp_f64(wt, trilerp(s, c, 2), trilerp(s, c, 5));
+}
+
+// temperature at (ts, p, lon, lat)
+MPB_HD double temperature_at(const MetView &g, double ts, double lon, double lat, double p, Cube &c) {
+  Stencil s;
+  stencil_3d(g, lon, lat, p, s);
+  fetch_cube(g, s, c);
   return lerp_f64(time_weight(g, ts), MPB_TRILERP(t0), MPB_TRILERP(t1));
 }
 
@@ -468,6 +523,10 @@ MPB_HD double parcel_dt(const MetView &g, const CtlView &c, const Parcel &a) {
 // That is what the reference's outputs contain, so it is reproduced here.
 // ----------------------------------------------------------------------------------------------
 static MPB_COLD void reflect_at_poles(double &lon, double &lat) {   // 5444-5468
+  // FMOD truncates its quotient through an int: beyond 2^31 * 360 (or for a non-finite value) it cannot bring a
+  // coordinate back into range and the loops below would never end -- the reference does not return in that case;
+  // a device kernel must, so such a parcel is left where it is (its lookups clamp to the grid edge).
+  if (!(fabs(lon) < 7.7e11) || !(fabs(lat) < 7.7e11)) return;
   lon = mod360(lon);
   lat = mod360(lat);
   while (lat < -90 || lat > 90) {
@@ -503,8 +562,8 @@ MPB_HD void fix_position(const MetView &g, Parcel &a) {
 // ----------------------------------------------------------------------------------------------
 // module_advect, pressure-level branch (3612-3677)
 // ----------------------------------------------------------------------------------------------
-template <int ORDER>
-MPB_HD void advect(const MetView &g, double dt, Parcel &a) {
+template <int ORDER, class CubeT>
+MPB_HD void advect(const MetView &g, double dt, Parcel &a, CubeT &c) {
   double um = 0, vm = 0, wm = 0;
   double u = 0, v = 0, w = 0;
   double lat_stage = a.lat;
@@ -523,7 +582,7 @@ MPB_HD void advect(const MetView &g, double dt, Parcel &a) {
     }
     lat_stage = y;
     if (i != 2) wt = time_weight(g, a.time + dts);   // stages 1 and 2 are taken at the same time
-    wind_at(g, wt, x, y, z, u, v, w);
+    wind_at(g, wt, x, y, z, c, u, v, w);
     double k = 1.0;
     if (ORDER == 2) k = (i == 0 ? 0.0 : 1.0);
     else if (ORDER == 4) k = (i == 0 || i == 3 ? 1.0 / 6.0 : 2.0 / 6.0);
@@ -574,6 +633,7 @@ MPB_HD void normals3(uint64_t ctr0, uint64_t ig, double &r0, double &r1, double 
 // ----------------------------------------------------------------------------------------------
 MPB_HD double tropopause_pressure(const ClimView &cl, double t, double lat) {
   double sec = mod_trunc(t, kYear);
+  if (!(fabs(sec) <= kYear)) sec = 0;   // non-finite or beyond the int quotient of FMOD: the loop below would never end
   while (sec < 0) sec += kYear;
   const int it = find_interval(cl.time, cl.ntime, 1, sec);
   const double la0 = ldg(cl.lat), la1 = ldg(cl.lat + 1);
@@ -677,15 +737,14 @@ struct Moments {
 };
 
 MPB_HD void diffuse_mesoscale(const MetView &g, const CtlView &k, double dt, uint64_t ig,
-                              Parcel &a, float &up, float &vp, float &wp) {
+                              Parcel &a, float &up, float &vp, float &wp, Cube &c) {
   // raw index search at the parcel position: no wrap / clamp helper here (4283-4285)
   Stencil s;
   s.ix = lon_interval(g, a.lon);
   s.iy = lat_interval(g, a.lat);
   s.iz = p_interval(g, a.p);
 
-  Cube c;
-  load_cube(g, s, c);
+  fetch_cube(g, s, c);
   Moments mu = {0.f, 0.f}, mv = {0.f, 0.f}, mw = {0.f, 0.f};
 #define MPB_ACC(node)                                        \
   mu.add(c.node.u0); mv.add(c.node.v0); mw.add(c.node.w0);   \
@@ -727,8 +786,8 @@ MPB_HD double settling_velocity(double p, double T, double rp, double rhop) {
   return 2. * (rp_m * rp_m) * (rhop - rho) * kG0 / (9. * eta) * G;
 }
 
-MPB_HD void sediment(const MetView &g, double dt, double rp, double rhop, Parcel &a) {
-  const double T = temperature_at(g, a.time, a.lon, a.lat, a.p);
+MPB_HD void sediment(const MetView &g, double dt, double rp, double rhop, Parcel &a, Cube &c) {
+  const double T = temperature_at(g, a.time, a.lon, a.lat, a.p, c);
   const double vs = settling_velocity(a.p, T, rp, rhop);
   a.p += dz2dp(vs * dt / 1000., a.p);
 }

@@ -201,6 +201,7 @@ def load_library(strict: bool = False) -> C.CDLL:
         "mpb_set_rng_ctr": (i32, [vp, u64]),
         "mpb_get_rng_ctr": (u64, [vp]),
         "mpb_run_timestep": (i32, [vp, dbl]),
+        "mpb_run_timestep_host": (i32, [vp, dbl, i64, vp, vp, vp, vp, vp, i64]),
         "mpb_run_modules": (i32, [vp, dbl, C.c_uint]),
         "mpb_module_timesteps": (i32, [vp, dbl]),
         "mpb_module_position": (i32, [vp]),
@@ -368,6 +369,22 @@ class Engine:
     # -- the step -------------------------------------------------------------------------------
     def run_timestep(self, t: float):
         self._ck(self._lib.mpb_run_timestep(self._h, float(t)))
+
+    def run_timestep_host(self, t: float, time, p, lon, lat, q: Optional[np.ndarray] = None):
+        """One step for parcels in HOST arrays (float64, contiguous, ideally pinned), updated in place: upload, step and
+        download are pipelined chunk by chunk (``mpb_run_timestep_host``)."""
+        arrs = (time, p, lon, lat)
+        n = arrs[0].size
+        for a in arrs:
+            if a.dtype != np.float64 or not a.flags.c_contiguous or a.size != n:
+                raise ValueError("parcel arrays must be contiguous float64 of one length")
+        stride = 0
+        if self.nq:
+            if q is None or q.dtype != np.float64 or q.ndim != 2 or q.shape[0] != self.nq or q.strides[1] != 8:
+                raise ValueError("q must be [nq][>=np] float64 with contiguous rows")
+            stride = q.strides[0] // 8
+        self._ck(self._lib.mpb_run_timestep_host(self._h, float(t), n, *[_ptr(a) for a in arrs],
+                                                 _ptr(q) if self.nq else None, stride))
 
     def run_modules(self, t: float, mask: int):
         self._ck(self._lib.mpb_run_modules(self._h, float(t), int(mask)))

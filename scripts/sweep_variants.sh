@@ -5,14 +5,15 @@
 set -u
 cd "$(dirname "$0")/.."
 V=mptrac_b200/_lib/variants
-VARIANTS="${VARIANTS:-b128m1 b128m5 b128m6 b128m8 b256m2 b256m3 b256m4 b64m10 b64m12}"
+# <flavour><block>m<min blocks per SM>; flavour f = fp32 cube kept across lookups, d = fp64 wind cube (MPB_CUBE_F64)
+VARIANTS="${VARIANTS:-f128m3 f128m4 f128m5 f256m2 f64m8 d128m2 d128m3 d128m4 d64m6 d64m8}"
 case "${1:-build}" in
   build)
     for v in $VARIANTS; do
-      b=${v#b}; b=${b%m*}; m=${v#*m}
+      fl=${v:0:1}; b=${v:1}; b=${b%m*}; m=${v#*m}; f64=0; [ "$fl" = d ] && f64=1
       mkdir -p $V/$v
       nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fopenmp -shared \
-        -DMPB_BLOCK=$b -DMPB_MINBLOCKS=$m ${EXTRA:-} mptrac_b200/csrc/engine.cu -o $V/$v/libmptrac_b200.so &
+        -DMPB_BLOCK=$b -DMPB_MINBLOCKS=$m -DMPB_CUBE_F64=$f64 ${EXTRA:-} mptrac_b200/csrc/engine.cu -o $V/$v/libmptrac_b200.so &
     done; wait; ls $V ;;
   run)
     WL=${2:-c2}; mkdir -p gpurun_out; : > gpurun_out/sweep_$WL.jsonl

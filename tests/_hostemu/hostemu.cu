@@ -77,11 +77,17 @@ static void run(const MetView &g, const ClimView &cl, const CtlView &c, const Em
     } else dt = dtarr[ip];
     if (dt == 0) continue;
     const uint64_t ig = (uint64_t)(ig0 + ip);
+    Cube cube;
+    cube_reset(cube);
     if (e.modules & MOD_POS_PRE) fix_position(g, a);
-    if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(g, dt, a);
+#if MPB_CUBE_F64
+    if (ADVECT > 0) { WindCube wc; cube_reset(wc); advect<(ADVECT > 0 ? ADVECT : 1)>(g, dt, a, wc); }
+#else
+    if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(g, dt, a, cube);
+#endif
     if (e.phys & 1) diffuse_turbulent(g, cl, c, dt, ig, a);
-    if (e.phys & 2) diffuse_mesoscale(g, c, dt, ig, a, uvwp[3 * ip], uvwp[3 * ip + 1], uvwp[3 * ip + 2]);
-    if (e.phys & 4) sediment(g, dt, rp[ip], rhop[ip], a);
+    if (e.phys & 2) diffuse_mesoscale(g, c, dt, ig, a, uvwp[3 * ip], uvwp[3 * ip + 1], uvwp[3 * ip + 2], cube);
+    if (e.phys & 4) sediment(g, dt, rp[ip], rhop[ip], a, cube);
     if (e.modules & MOD_POS_POST) fix_position(g, a);
     time[ip] = a.time; lon[ip] = a.lon; lat[ip] = a.lat; p[ip] = a.p;
   }

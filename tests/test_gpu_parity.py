@@ -338,7 +338,38 @@ def test_inactive_and_ragged_parcels(oracle):
     oracle.ctr = 0
     oracle.run("timestep", ctl, clim, m0, m1, ref, t=0.0, nsteps=6)
     _compare("ragged", out, ref, TOL_POS_DEG_DIFF, TOL_P_REL_DIFF)
-    assert np.all(out["time"] <= 1200.0)
+    # t_stop is inclusive (direction * (time - t_stop) <= 0, src/mptrac.c:6019-6024): a parcel AT t_stop still takes
+    # the step to t = 1500 s, then nothing moves any more
+    assert np.all(out["time"] == 1500.0)
+
+
+def test_host_resident_step_equals_three_calls():
+    """mpb_run_timestep_host (chunked upload / step / download pipeline) == set_atm + run_timestep + get_atm, bit for bit,
+    including steps that fall back because a cell sort is due, with diffusion (random numbers addressed per chunk) and
+    sedimentation (rp / rhop uploaded per chunk)."""
+    from mptrac_b200 import Ctl
+    m0, m1, tm, p, lon, lat, clim = _case(n=300_000, grid=(72, 37, 30))
+    n = tm.size
+    q = np.stack([np.full(n, 2.0), np.full(n, 1500.0)])
+    ctl = Ctl(nq=2, qnt_rp=0, qnt_rhop=1, advect=4, diffusion=1, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0,
+              turb_dz_trop=0.5, turb_dx_strat=20.0, sort_dt=900.0)
+    with _engine(n, 2) as a, _engine(n, 2) as b:
+        _setup(a, ctl, clim, m0, m1, tm, p, lon, lat, q)
+        _setup(b, ctl, clim, m0, m1, tm, p, lon, lat, q)
+        h = {k: v.copy() for k, v in zip(("time", "p", "lon", "lat"), (tm, p, lon, lat))}
+        hq = q.copy()
+        a.run_timestep(0.0)
+        b.run_timestep(0.0)
+        for s in range(1, 5):                        # t = 900 triggers the sort -> fallback path
+            a.run_timestep(300.0 * s)
+            b.run_timestep_host(300.0 * s, h["time"], h["p"], h["lon"], h["lat"], hq)
+        ref = a.get_atm()
+        assert a.rng_ctr == b.rng_ctr
+        uva, uvb = a.get_uvwp(), b.get_uvwp()
+    for k in ("time", "p", "lon", "lat"):
+        assert np.array_equal(ref[k], h[k]), k
+    assert np.array_equal(uva, uvb)
+    assert abserr(h["lat"], lat) > 1e-3
 
 
 # ------------------------------------------------------------------------------------------------------------------
