@@ -77,6 +77,10 @@ def host_cores() -> int:
     return max(1, n)
 
 
+def cpu_threads() -> int:
+    return int(os.environ.get("MPB_CPU_THREADS", "0")) or host_cores()
+
+
 def peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -331,7 +335,7 @@ def cpu_baseline(workload, budget_s=20.0, steps=None):
     n_sample = min(wl["np"], 1_000_000)
     sl = slice(0, n_sample)
     atm = Parcels(tm[sl], p[sl], lon[sl], lat[sl], None if q is None else q[:, sl])
-    cores = int(os.environ.get("OMP_NUM_THREADS", "0")) or host_cores()
+    cores = cpu_threads()
     if reference_available():
         kind = "reference"
         ref = Reference()
@@ -360,7 +364,8 @@ def cpu_baseline_subprocess(workload, budget_s):
            "--steps", "0", "--warmup", "1"]
     deadline = max(120.0, 8 * budget_s)
     try:
-        pr = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+        env = {k: v for k, v in os.environ.items() if k != "OMP_NUM_THREADS"}
+        pr = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True, env=env)
         try:
             out, err = pr.communicate(timeout=deadline)
         except subprocess.TimeoutExpired:
@@ -382,17 +387,26 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if "OMP_NUM_THREADS" not in os.environ:
-        # the OpenMP runtime reads this when the reference library is loaded (below); os.cpu_count() would count
-        # cores a container may not use
-        os.environ["OMP_NUM_THREADS"] = str(host_cores())
+    # the OpenMP runtime reads this when the reference library is loaded (below).  torchrun exports OMP_NUM_THREADS=1 to
+    # its workers, which is not what "all the host threads it can use" means: the count is ours (MPB_CPU_THREADS or
+    # every core this process may run on)
+    os.environ["OMP_NUM_THREADS"] = str(cpu_threads())
     _log(f"reference arm on {os.environ['OMP_NUM_THREADS']} OpenMP threads")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl = WORKLOADS[args.workload]
-    if args.warmup > 0:
-        cpu_baseline(args.workload, steps=1)
-    # each "step" of this arm is a bounded sample: one model step over min(np, 1M) parcels on all host cores
-    base = cpu_baseline(args.workload, budget_s=args.cpu_budget, steps=(max(1, min(args.steps, 20)) if args.steps > 0 else None))
+    # the reference logs through C stdio: keep file descriptor 1 clean for the one JSON line
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.warmup > 0:
+            cpu_baseline(args.workload, steps=1)
+        # each "step" of this arm is a bounded sample: one model step over min(np, 1M) parcels on all host cores
+        base = cpu_baseline(args.workload, budget_s=args.cpu_budget, steps=(max(1, min(args.steps, 20)) if args.steps > 0 else None))
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     v = base["value"]
     n_sample = min(wl["np"], 1_000_000)
     line = {"impl": "reference", "metric": "particle-steps/sec", "value": v, "unit": "particle-steps/s", "n_gpus": world,

@@ -86,8 +86,14 @@ constexpr int kLanes = 4;                       // concurrent chunk pipelines of
 constexpr long long kHostChunkMin = 16384;      // parcels per chunk: at least 128 KiB per array ...
 constexpr long long kHostChunkMax = 1 << 20;    // ... at most 8 MiB
 
+#ifdef MPB_NO_BOUNDS   // register budget given by -maxrregcount instead (variant sweeps)
+#define MPB_BOUNDS
+#else
+#define MPB_BOUNDS __launch_bounds__(kBlock, MPB_MINBLOCKS)
+#endif
+
 template <int ADVECT, unsigned PHYS>
-__global__ void __launch_bounds__(kBlock, MPB_MINBLOCKS) step_kernel(const __grid_constant__ StepArgs A) {
+__global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
   const long long ip = (long long)blockIdx.x * kBlock + threadIdx.x;
   if (ip >= A.np) return;
 
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(kBlock, MPB_MINBLOCKS) step_kernel(const __gri
 #else
   if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, cube);
 #endif
-  if (PHYS & PHYS_TURB) diffuse_turbulent(A.met, A.clim, A.ctl, dt, ig, a);
+  if (PHYS & PHYS_TURB) diffuse_turbulent(A.met, A.clim, A.ctl, dt, ig, a, cube.ax);
   if (PHYS & PHYS_MESO) {
     float *s = A.uvwp + 3 * ip;
     float up = s[0], vp = s[1], wp = s[2];

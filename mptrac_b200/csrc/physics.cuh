@@ -324,34 +324,56 @@ MPB_HD int p_guess(const MetView &g, double p) {
   return (int)ldg(g.p_lut + k);
 }
 
+MPB_HD int lon_interval(const MetView &g, double lon) { return find_regular(g.lon_first, g.lon_d, g.r_lon_d, g.nx, lon); }
+
+// The three axis intervals of the cell a parcel was last looked up in.  Successive lookups of one parcel (Runge-Kutta
+// stages, diffusion, sedimentation) nearly always stay inside them, so the interval search degenerates to two compares
+// against registers: no first-guess table, no interval record load, no dependent-load latency.
+struct CellAxes {
+  AxisCell x, y, z;
+  int ix, iy, iz;   // -1 = nothing yet
+};
+MPB_HD void axes_reset(CellAxes &a) { a.ix = -1; a.iy = -1; a.iz = -1; }
+
+MPB_HD int lon_cell(const MetView &g, double lon, CellAxes &a) {
+  const int ix = lon_interval(g, lon);
+  if (ix != a.ix) { a.x = load_cell(g.lonc + ix); a.ix = ix; }
+  return ix;
+}
+MPB_HD int lat_cell(const MetView &g, double lat, CellAxes &a) {
+  if (a.iy < 0 || !cell_holds(a.y, a.iy, g.ny, g.lat_asc, lat))
+    a.iy = locate_cell(g.lat, g.latc, g.ny, g.lat_asc, lat, lat_guess(g, lat), a.y);
+  return a.iy;
+}
+MPB_HD int p_cell(const MetView &g, double p, CellAxes &a) {
+  if (a.iz < 0 || !cell_holds(a.z, a.iz, g.nz, g.p_asc, p))
+    a.iz = locate_cell(g.p, g.pc, g.nz, g.p_asc, p, p_guess(g, p), a.z);
+  return a.iz;
+}
+
+// uncached searches (sort keys)
 MPB_HD int lat_interval(const MetView &g, double lat) {
   AxisCell c;
   return locate_cell(g.lat, g.latc, g.ny, g.lat_asc, lat, lat_guess(g, lat), c);
 }
-
 MPB_HD int p_interval(const MetView &g, double p) {
   AxisCell c;
   return locate_cell(g.p, g.pc, g.nz, g.p_asc, p, p_guess(g, p), c);
 }
 
-MPB_HD int lon_interval(const MetView &g, double lon) { return find_regular(g.lon_first, g.lon_d, g.r_lon_d, g.nx, lon); }
-
-MPB_HD void stencil_2d(const MetView &g, double lon, double lat, Stencil &s) {
+MPB_HD void stencil_2d(const MetView &g, double lon, double lat, CellAxes &a, Stencil &s) {
   double lon2, lat2;
   clamp_horizontal(g, lon, lat, lon2, lat2);
-  s.ix = lon_interval(g, lon2);
-  const AxisCell cx = load_cell(g.lonc + s.ix);
-  AxisCell cy;
-  s.iy = locate_cell(g.lat, g.latc, g.ny, g.lat_asc, lat2, lat_guess(g, lat2), cy);
-  s.wx = div_by(cx.hi - lon2, cx.d, cx.rd);
-  s.wy = div_by(cy.hi - lat2, cy.d, cy.rd);
+  s.ix = lon_cell(g, lon2, a);
+  s.iy = lat_cell(g, lat2, a);
+  s.wx = div_by(a.x.hi - lon2, a.x.hi - a.x.lo, a.x.rd);
+  s.wy = div_by(a.y.hi - lat2, a.y.hi - a.y.lo, a.y.rd);
 }
 
-MPB_HD void stencil_3d(const MetView &g, double lon, double lat, double p, Stencil &s) {
-  AxisCell cz;
-  s.iz = locate_cell(g.p, g.pc, g.nz, g.p_asc, p, p_guess(g, p), cz);
-  stencil_2d(g, lon, lat, s);
-  s.wz = div_by(cz.hi - p, cz.d, cz.rd);
+MPB_HD void stencil_3d(const MetView &g, double lon, double lat, double p, CellAxes &a, Stencil &s) {
+  s.iz = p_cell(g, p, a);
+  stencil_2d(g, lon, lat, a, s);
+  s.wz = div_by(a.z.hi - p, a.z.hi - a.z.lo, a.z.rd);
 }
 
 // w * (lo - hi) + hi with the difference taken in fp32 first (3023-3038)
@@ -378,8 +400,9 @@ MPB_HD Node load_node(const Node *ptr) {
 struct Cube {
   Node n000, n001, n010, n011, n100, n101, n110, n111;  // index order: x, y, z
   int ix, iy, iz;                                        // the cell held; ix < 0 = nothing yet
+  CellAxes ax;                                           // its axis intervals
 };
-MPB_HD void cube_reset(Cube &c) { c.ix = -1; c.iy = -1; c.iz = -1; }
+MPB_HD void cube_reset(Cube &c) { c.ix = -1; c.iy = -1; c.iz = -1; axes_reset(c.ax); }
 
 MPB_HD void load_cube(const MetView &g, const Stencil &s, Cube &c) {
   const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * (size_t)g.nz;
@@ -414,7 +437,7 @@ MPB_HD double time_weight(const MetView &g, double ts) { return div_by(g.t1 - ts
 MPB_HD void wind_at(const MetView &g, double wt, double lon, double lat, double p, Cube &c,
                     double &u, double &v, double &w) {
   Stencil s;
-  stencil_3d(g, lon, lat, p, s);
+  stencil_3d(g, lon, lat, p, c.ax, s);
   fetch_cube(g, s, c);
   u = lerp_f64(wt, MPB_TRILERP(u0), MPB_TRILERP(u1));
   v = lerp_f64(wt, MPB_TRILERP(v0), MPB_TRILERP(v1));
@@ -428,8 +451,9 @@ MPB_HD void wind_at(const MetView &g, double wt, double lon, double lat, double 
 struct WindCube {
   double hi[4][6], df[4][6];   // [column (x0y0, x0y1, x1y0, x1y1)][u0, v0, w0, u1, v1, w1]
   int ix, iy, iz;
+  CellAxes ax;
 };
-MPB_HD void cube_reset(WindCube &c) { c.ix = -1; c.iy = -1; c.iz = -1; }
+MPB_HD void cube_reset(WindCube &c) { c.ix = -1; c.iy = -1; c.iz = -1; axes_reset(c.ax); }
 
 MPB_HD void fetch_cube(const MetView &g, const Stencil &s, WindCube &c) {
   if (c.ix == s.ix && c.iy == s.iy && c.iz == s.iz) return;
@@ -458,7 +482,7 @@ MPB_HD double trilerp(const Stencil &s, const WindCube &c, int k) {
 MPB_HD void wind_at(const MetView &g, double wt, double lon, double lat, double p, WindCube &c,
                     double &u, double &v, double &w) {
   Stencil s;
-  stencil_3d(g, lon, lat, p, s);
+  stencil_3d(g, lon, lat, p, c.ax, s);
   fetch_cube(g, s, c);
   u = lerp_f64(wt, trilerp(s, c, 0), trilerp(s, c, 3));
   v = lerp_f64(wt, trilerp(s, c, 1), trilerp(s, c, 4));
@@ -468,7 +492,7 @@ MPB_HD void wind_at(const MetView &g, double wt, double lon, double lat, double 
 // temperature at (ts, p, lon, lat)
 MPB_HD double temperature_at(const MetView &g, double ts, double lon, double lat, double p, Cube &c) {
   Stencil s;
-  stencil_3d(g, lon, lat, p, s);
+  stencil_3d(g, lon, lat, p, c.ax, s);
   fetch_cube(g, s, c);
   return lerp_f64(time_weight(g, ts), MPB_TRILERP(t0), MPB_TRILERP(t1));
 }
@@ -488,9 +512,9 @@ MPB_HD double time_blend_guarded(double wt, double a0, double a1) {
 }
 
 // ps and pbl at the parcel position (INTPOL_2D(pbl,1); INTPOL_2D(ps,0), 4606-4617)
-MPB_HD void surface_at(const MetView &g, double ts, double lon, double lat, double &ps, double &pbl) {
+MPB_HD void surface_at(const MetView &g, double ts, double lon, double lat, CellAxes &ax, double &ps, double &pbl) {
   Stencil s;
-  stencil_2d(g, lon, lat, s);
+  stencil_2d(g, lon, lat, ax, s);
   const size_t b = (size_t)s.ix * (size_t)g.ny + (size_t)s.iy;
   const size_t sx = (size_t)g.ny;
   const double wt = time_weight(g, ts);
@@ -662,9 +686,9 @@ MPB_HD double weight_tropo(double pt, double p) { return ramp_weight(pt / 0.8668
 // module_diff_turb (4588-4734)
 // ----------------------------------------------------------------------------------------------
 MPB_HD void diffuse_turbulent(const MetView &g, const ClimView &cl, const CtlView &c, double dt,
-                              uint64_t ig, Parcel &a) {
+                              uint64_t ig, Parcel &a, CellAxes &ax) {
   double ps, pbl;
-  surface_at(g, a.time, a.lon, a.lat, ps, pbl);
+  surface_at(g, a.time, a.lon, a.lat, ax, ps, pbl);
   if (c.pbl_scheme > 0 && a.p >= pbl) return;
 
   const double ptop = ldg(g.p + g.nz - 1);
@@ -740,9 +764,9 @@ MPB_HD void diffuse_mesoscale(const MetView &g, const CtlView &k, double dt, uin
                               Parcel &a, float &up, float &vp, float &wp, Cube &c) {
   // raw index search at the parcel position: no wrap / clamp helper here (4283-4285)
   Stencil s;
-  s.ix = lon_interval(g, a.lon);
-  s.iy = lat_interval(g, a.lat);
-  s.iz = p_interval(g, a.p);
+  s.ix = lon_cell(g, a.lon, c.ax);
+  s.iy = lat_cell(g, a.lat, c.ax);
+  s.iz = p_cell(g, a.p, c.ax);
 
   fetch_cube(g, s, c);
   Moments mu = {0.f, 0.f}, mv = {0.f, 0.f}, mw = {0.f, 0.f};

@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 for w in $what; do
   case $w in
     tests)    timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log ;;
-    bench)    timeout 900 python bench.py --workload $WL > gpurun_out/bench_$WL.json 2> gpurun_out/bench_$WL.err; echo "bench rc=$?"; cat gpurun_out/bench_$WL.json ;;
+    bench)    timeout 420 python bench.py --workload $WL > gpurun_out/bench_$WL.json 2> gpurun_out/bench_$WL.err; echo "bench rc=$?"; cat gpurun_out/bench_$WL.json ;;
     benchref) timeout 900 python bench.py --impl reference --workload $WL --steps 5 --warmup 1 > gpurun_out/bench_ref_$WL.json 2> gpurun_out/bench_ref_$WL.err; cat gpurun_out/bench_ref_$WL.json ;;
     launches) MPB_BENCH_NO_SUSTAIN=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$WL.csv \
                 python bench.py --workload $WL --steps 24 --warmup 3 --no-cpu > gpurun_out/launches_$WL.log 2>&1; echo "launches rc=$?" ;;

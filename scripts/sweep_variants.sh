@@ -10,16 +10,18 @@ VARIANTS="${VARIANTS:-f128m3 f128m4 f128m5 f256m2 f64m8 d128m2 d128m3 d128m4 d64
 case "${1:-build}" in
   build)
     for v in $VARIANTS; do
-      fl=${v:0:1}; b=${v:1}; b=${b%m*}; m=${v#*m}; f64=0; [ "$fl" = d ] && f64=1
+      # <f|d><block>m<min blocks>  or  <f|d><block>r<register cap> (-maxrregcount, min blocks 1)
+      fl=${v:0:1}; f64=0; [ "$fl" = d ] && f64=1; rest=${v:1}; cap=""
+      if [[ "$rest" == *r* ]]; then b=${rest%r*}; m=1; cap="-maxrregcount=${rest#*r} -DMPB_NO_BOUNDS"; else b=${rest%m*}; m=${rest#*m}; fi
       mkdir -p $V/$v
       nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fopenmp -shared \
-        -DMPB_BLOCK=$b -DMPB_MINBLOCKS=$m -DMPB_CUBE_F64=$f64 ${EXTRA:-} mptrac_b200/csrc/engine.cu -o $V/$v/libmptrac_b200.so &
+        -DMPB_BLOCK=$b -DMPB_MINBLOCKS=$m -DMPB_CUBE_F64=$f64 $cap ${EXTRA:-} mptrac_b200/csrc/engine.cu -o $V/$v/libmptrac_b200.so &
     done; wait; ls $V ;;
   run)
     WL=${2:-c2}; mkdir -p gpurun_out; : > gpurun_out/sweep_$WL.jsonl
     for v in $VARIANTS; do
       echo "== $v" >&2
-      MPTRAC_B200_LIBDIR=$PWD/$V/$v MPB_BENCH_NO_SUSTAIN=1 timeout 600 python bench.py --workload $WL --no-cpu --steps 36 --warmup 13 2>/dev/null \
+      MPTRAC_B200_LIBDIR=$PWD/$V/$v MPB_BENCH_NO_SUSTAIN=1 timeout 300 python bench.py --workload $WL --no-cpu --steps 36 --warmup 3 2>/dev/null \
         | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(json.dumps({'variant':'$v','ms_per_step':d['ms_per_step'],'b2b_ms':d['back_to_back']['ms_per_step'],'value':d['value'],'frac':d['roofline']['frac']}))" | tee -a gpurun_out/sweep_$WL.jsonl
     done ;;
 esac

@@ -85,7 +85,7 @@ static void run(const MetView &g, const ClimView &cl, const CtlView &c, const Em
 #else
     if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(g, dt, a, cube);
 #endif
-    if (e.phys & 1) diffuse_turbulent(g, cl, c, dt, ig, a);
+    if (e.phys & 1) diffuse_turbulent(g, cl, c, dt, ig, a, cube.ax);
     if (e.phys & 2) diffuse_mesoscale(g, c, dt, ig, a, uvwp[3 * ip], uvwp[3 * ip + 1], uvwp[3 * ip + 2], cube);
     if (e.phys & 4) sediment(g, dt, rp[ip], rhop[ip], a, cube);
     if (e.modules & MOD_POS_POST) fix_position(g, a);

@@ -356,10 +356,10 @@ def test_host_resident_step_equals_three_calls():
     with _engine(n, 2) as a, _engine(n, 2) as b:
         _setup(a, ctl, clim, m0, m1, tm, p, lon, lat, q)
         _setup(b, ctl, clim, m0, m1, tm, p, lon, lat, q)
-        h = {k: v.copy() for k, v in zip(("time", "p", "lon", "lat"), (tm, p, lon, lat))}
-        hq = q.copy()
         a.run_timestep(0.0)
-        b.run_timestep(0.0)
+        b.run_timestep(0.0)                          # fmod(0, SORT_DT) == 0: the very first step already sorts
+        h = b.get_atm()                              # the host copy a driver would hold from here on
+        hq = h["q"]
         for s in range(1, 5):                        # t = 900 triggers the sort -> fallback path
             a.run_timestep(300.0 * s)
             b.run_timestep_host(300.0 * s, h["time"], h["p"], h["lon"], h["lat"], hq)
