@@ -21,6 +21,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mptrac_b200.h"
@@ -81,6 +82,12 @@ constexpr unsigned PHYS_TURB = 1, PHYS_MESO = 2, PHYS_SEDI = 4;
 #ifndef MPB_CUBE_F64
 #define MPB_CUBE_F64 0
 #endif
+#ifndef MPB_PERSIST      // 1: grid = SMs x resident blocks, threads loop over parcels; 0: one parcel per thread
+#define MPB_PERSIST 1
+#endif
+#ifndef MPB_PREFETCH     // hint the next parcel's met cell into L1 (persistent form only).  Measured on B200 (C2, sorted):
+#define MPB_PREFETCH 0   // 139 us with the hint vs 126 us without -- its index arithmetic costs more than the hits save
+#endif
 constexpr int kBlock = MPB_BLOCK;
 constexpr int kLanes = 4;                       // concurrent chunk pipelines of mpb_run_timestep_host
 constexpr long long kHostChunkMin = 16384;      // parcels per chunk: at least 128 KiB per array ...
@@ -92,17 +99,9 @@ constexpr long long kHostChunkMax = 1 << 20;    // ... at most 8 MiB
 #define MPB_BOUNDS __launch_bounds__(kBlock, MPB_MINBLOCKS)
 #endif
 
-template <int ADVECT, unsigned PHYS>
-__global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
-  const long long ip = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (ip >= A.np) return;
-
-  Parcel a;
-  a.time = A.time[ip];
-  a.lon = A.lon[ip];
-  a.lat = A.lat[ip];
-  a.p = A.p[ip];
-
+// One parcel, one model step: timesteps -> position -> advect -> diff_turb -> diff_meso -> sedi -> position, in registers.
+template <int ADVECT, unsigned PHYS, class Hook>
+__device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Parcel a, Hook between) {
   double dt;
   if (A.modules & MOD_TIMESTEPS) {
     dt = parcel_dt(A.met, A.ctl, a);
@@ -110,7 +109,7 @@ __global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
   } else {
     dt = A.dt[ip];
   }
-  if (dt == 0) return;  // PARTICLE_LOOP(check_dt = 1), src/mptrac.h:1754-1759
+  if (dt == 0) { between(); return; }  // PARTICLE_LOOP(check_dt = 1), src/mptrac.h:1754-1759
 
   const unsigned long long ig = (unsigned long long)(A.ig0 + ip);
 
@@ -121,11 +120,12 @@ __global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
   if (ADVECT > 0) {
     WindCube wc;
     cube_reset(wc);
-    advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, wc);
+    advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, wc, between);
   }
 #else
-  if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, cube);
+  if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, cube, between);
 #endif
+  if (ADVECT == 0) between();
   if (PHYS & PHYS_TURB) diffuse_turbulent(A.met, A.clim, A.ctl, dt, ig, a, cube.ax);
   if (PHYS & PHYS_MESO) {
     float *s = A.uvwp + 3 * ip;
@@ -140,6 +140,38 @@ __global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
   A.lon[ip] = a.lon;
   A.lat[ip] = a.lat;
   A.p[ip] = a.p;
+}
+
+__device__ __forceinline__ Parcel load_parcel(const StepArgs &A, long long ip) {
+  Parcel a;
+  a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
+  return a;
+}
+
+// Persistent form: the grid is sized to what the GPU holds at once (SMs x resident blocks) and every thread walks the
+// parcels ip, ip + stride, ...  While parcel k computes, the state of parcel k+1 is already in flight, the axis tables
+// stay hot in L1 for the whole launch and no block-launch gaps separate the parcels of a thread (the kernel holds ~100
+// registers of fp64 state per parcel, so only ~16 warps are resident per SM and every exposed latency counts).
+// MPB_PREFETCH additionally hints the met cell of parcel k+1 into L1 once the first lookup of k has been issued.
+template <int ADVECT, unsigned PHYS>
+__global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
+  const long long stride = (long long)gridDim.x * kBlock;
+  long long ip = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (ip >= A.np) return;
+  Parcel nxt = load_parcel(A, ip);
+  for (;;) {
+    const Parcel a = nxt;
+    const long long cur = ip;
+    ip += stride;
+    const bool more = ip < A.np;
+    if (more) nxt = load_parcel(A, ip);
+#if MPB_PREFETCH
+    step_parcel<ADVECT, PHYS>(A, cur, a, [&]() { if (more) prefetch_cube(A.met, nxt.lon, nxt.lat, nxt.p); });
+#else
+    step_parcel<ADVECT, PHYS>(A, cur, a, NoHook());
+#endif
+    if (!more) break;
+  }
 }
 
 typedef void (*step_fn)(const StepArgs);
@@ -344,6 +376,8 @@ struct mpb_ctx {
   mpb_ctl_t ctl;
   bool have_ctl = false;
 
+  std::vector<std::pair<step_fn, unsigned>> resident;   // blocks the device holds at once, per step kernel
+
   // host-resident stepping (mpb_run_timestep_host): streams that each carry whole chunks
   cudaStream_t lane[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t lane_done[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -438,6 +472,17 @@ static StepArgs step_args(mpb_ctx *c, double t, int advect, unsigned phys, unsig
   return A;
 }
 
+// blocks of `fn` the device holds at once (cached per kernel instantiation)
+static unsigned resident_blocks(mpb_ctx *c, step_fn fn) {
+  for (auto &e : c->resident) if (e.first == fn) return e.second;
+  int per_sm = 0, sms = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  const unsigned n = (unsigned)std::max(1, per_sm * sms);
+  c->resident.emplace_back(fn, n);
+  return n;
+}
+
 // launch the step kernel for parcels [off, off + cnt) on `stream`
 static void launch_range(mpb_ctx *c, StepArgs A, int advect, unsigned phys, long long off, long long cnt, cudaStream_t stream) {
   if (cnt <= 0) return;
@@ -445,7 +490,11 @@ static void launch_range(mpb_ctx *c, StepArgs A, int advect, unsigned phys, long
   if (A.rp) { A.rp += off; A.rhop += off; }
   A.np = cnt; A.ig0 += off;
   step_fn fn = pick_step(advect, phys);
-  fn<<<nblocks(cnt, kBlock), kBlock, 0, stream>>>(A);
+  unsigned grid = nblocks(cnt, kBlock);
+#if MPB_PERSIST
+  grid = std::min(grid, resident_blocks(c, fn));
+#endif
+  fn<<<grid, kBlock, 0, stream>>>(A);
   CK(cudaGetLastError());
   c->launches++;
 }

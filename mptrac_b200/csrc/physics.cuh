@@ -303,14 +303,21 @@ MPB_HD bool cell_holds(const AxisCell &c, int i, int n, int ascending, double x)
   return !(below_lo && i > 0) && !(above_hi && i < n - 2);
 }
 
-// Interval + cell of an irregular axis from a first guess: one 256-bit load when the guess is right (it nearly always is),
-// the exact search otherwise.
+// Interval + cell of an irregular axis from a first guess: one 256-bit load when the guess is right (it nearly always
+// is), one more when the answer is the neighbouring interval (a first-guess table bin that straddles a grid level), the
+// exact search otherwise.
 MPB_HD int locate_cell(const double *xx, const AxisCell *cells, int n, int ascending, double x, int guess, AxisCell &c) {
   int i = guess < 0 ? 0 : (guess > n - 2 ? n - 2 : guess);
   c = load_cell(cells + i);
   if (!cell_holds(c, i, n, ascending, x)) {
-    i = refine_interval(xx, n, ascending, x, i);
-    c = load_cell(cells + i);
+    const bool down = ((c.lo > x) == (ascending != 0));   // the answer lies at a smaller index
+    const int j = down ? (i > 0 ? i - 1 : 0) : (i < n - 2 ? i + 1 : n - 2);
+    c = load_cell(cells + j);
+    i = j;
+    if (!cell_holds(c, i, n, ascending, x)) {
+      i = refine_interval(xx, n, ascending, x, i);
+      c = load_cell(cells + i);
+    }
   }
   return i;
 }
@@ -416,6 +423,29 @@ MPB_HD void load_cube(const MetView &g, const Stencil &s, Cube &c) {
   c.n110 = load_node(b + sx + sy);
   c.n111 = load_node(b + sx + sy + 1);
   c.ix = s.ix; c.iy = s.iy; c.iz = s.iz;
+}
+
+// Hint the 8 corner nodes of the cell a parcel at (lon, lat, p) will look up into L1 (no registers, no waiting); the
+// indices are first guesses only -- a wrong guess costs nothing but the hint.
+MPB_HD void prefetch_cube(const MetView &g, double lon, double lat, double p) {
+#ifdef __CUDA_ARCH__
+  double lon2, lat2;
+  clamp_horizontal(g, lon, lat, lon2, lat2);
+  int ix = (int)((lon2 - g.lon_first) * g.r_lon_d), iy = lat_guess(g, lat2), iz = p_guess(g, p);
+  ix = ix < 0 ? 0 : (ix > g.nx - 2 ? g.nx - 2 : ix);
+  iy = iy < 0 ? 0 : (iy > g.ny - 2 ? g.ny - 2 : iy);
+  iz = iz < 0 ? 0 : (iz > g.nz - 2 ? g.nz - 2 : iz);
+  const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * (size_t)g.nz;
+  const Node *b = g.f + ((size_t)ix * sx + (size_t)iy * sy + (size_t)iz);
+  const Node *q[4] = {b, b + sy, b + sx, b + sx + sy};
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(q[j]));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(q[j] + 1));
+  }
+#else
+  (void)g; (void)lon; (void)lat; (void)p;
+#endif
 }
 
 // make c hold the cell of s
@@ -586,8 +616,12 @@ MPB_HD void fix_position(const MetView &g, Parcel &a) {
 // ----------------------------------------------------------------------------------------------
 // module_advect, pressure-level branch (3612-3677)
 // ----------------------------------------------------------------------------------------------
-template <int ORDER, class CubeT>
-MPB_HD void advect(const MetView &g, double dt, Parcel &a, CubeT &c) {
+struct NoHook { MPB_HD void operator()() const {} };
+
+// `between` runs once after the first stage's lookup has been issued: the step kernel uses it to prefetch the met cell
+// of the NEXT parcel of its thread while this parcel's stages compute.
+template <int ORDER, class CubeT, class Hook = NoHook>
+MPB_HD void advect(const MetView &g, double dt, Parcel &a, CubeT &c, Hook between = Hook()) {
   double um = 0, vm = 0, wm = 0;
   double u = 0, v = 0, w = 0;
   double lat_stage = a.lat;
@@ -607,6 +641,7 @@ MPB_HD void advect(const MetView &g, double dt, Parcel &a, CubeT &c) {
     lat_stage = y;
     if (i != 2) wt = time_weight(g, a.time + dts);   // stages 1 and 2 are taken at the same time
     wind_at(g, wt, x, y, z, c, u, v, w);
+    if (i == 0) between();
     double k = 1.0;
     if (ORDER == 2) k = (i == 0 ? 0.0 : 1.0);
     else if (ORDER == 4) k = (i == 0 || i == 3 ? 1.0 / 6.0 : 2.0 / 6.0);

@@ -13,9 +13,9 @@ case "${1:-build}" in
       # <f|d><block>m<min blocks>  or  <f|d><block>r<register cap> (-maxrregcount, min blocks 1)
       fl=${v:0:1}; f64=0; [ "$fl" = d ] && f64=1; rest=${v:1}; cap=""
       if [[ "$rest" == *r* ]]; then b=${rest%r*}; m=1; cap="-maxrregcount=${rest#*r} -DMPB_NO_BOUNDS"; else b=${rest%m*}; m=${rest#*m}; fi
-      mkdir -p $V/$v
+      mkdir -p $V/$v${TAG:-}
       nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fopenmp -shared \
-        -DMPB_BLOCK=$b -DMPB_MINBLOCKS=$m -DMPB_CUBE_F64=$f64 $cap ${EXTRA:-} mptrac_b200/csrc/engine.cu -o $V/$v/libmptrac_b200.so &
+        -DMPB_BLOCK=$b -DMPB_MINBLOCKS=$m -DMPB_CUBE_F64=$f64 $cap ${EXTRA:-} mptrac_b200/csrc/engine.cu -o $V/$v${TAG:-}/libmptrac_b200.so &
     done; wait; ls $V ;;
   run)
     WL=${2:-c2}; mkdir -p gpurun_out; : > gpurun_out/sweep_$WL.jsonl
