@@ -19,6 +19,10 @@ from typing import Optional, Sequence
 import numpy as np
 
 MIX_MAXQ = 23
+# module bits of mpb_run_modules (include/mptrac_b200.h MPB_MOD_*)
+MOD_TIMESTEPS, MOD_SORT, MOD_POSITION0, MOD_ADVECT, MOD_DIFF_TURB, MOD_DIFF_MESO, MOD_SEDI, MOD_POSITION1, MOD_MIXING = (
+    1 << i for i in range(9))
+MOD_ALL = 0x1ff
 _LIBDIR = Path(__file__).resolve().parent / "_lib"
 
 
