@@ -121,11 +121,12 @@ int mpb_run_timestep(mpb_ctx *ctx, double t);
 
 /* The same step for parcels that live in HOST memory (the driver's atm_t): stands in for the sequence
  * mptrac_update_device(atm) -> mptrac_run_timestep -> mptrac_update_host(atm) (src/mptrac.c:8005, :7851, :8061) that a
- * caller needs when it wants the parcels back after every step.  The arrays are cut into chunks that are uploaded,
- * stepped and downloaded in a software pipeline over several streams, so the PCIe transfers of both directions and the
- * kernels overlap; the result is identical to the three calls.  Pinned host memory makes the copies truly
- * asynchronous; pageable memory works but serialises them.  Synchronous: the arrays are valid on return.
- * Only the quantities the path reads (rp, rhop) are uploaded; no quantity is downloaded (the path does not modify any). */
+ * caller needs when it wants the parcels back after every step; the result is identical to the three calls.
+ * Pinned (page-locked) host arrays are read and written by the step kernel itself through their device mapping, so
+ * both PCIe directions run for the whole launch with no copy engine in between; pageable arrays are cut into chunks
+ * that are uploaded, stepped and downloaded in a software pipeline over several streams.  Steps with a global phase
+ * (cell sort, mixing) take the plain three-call sequence.  Synchronous: the arrays are valid on return.
+ * Only the quantities the path reads (rp, rhop) are transferred; none is written back (the path modifies none). */
 int mpb_run_timestep_host(mpb_ctx *ctx, double t, int64_t np, double *time, double *p, double *lon, double *lat,
                           double *q, int64_t q_stride);
 

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -66,6 +67,10 @@ struct StepArgs {
   double *time, *lon, *lat, *p, *dt;
   float *uvwp;
   const double *rp, *rhop;
+  // host-resident stepping without copy engines: parcels are read from and written back to mapped (pinned) host memory
+  // by the kernel itself; the device arrays above still receive the result.  Null = parcels live on the device.
+  const double *in_time, *in_lon, *in_lat, *in_p;
+  double *host_time, *host_lon, *host_lat, *host_p;
   long long np;
   long long ig0;  // global index of local parcel 0
   unsigned modules;
@@ -109,7 +114,11 @@ __device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Par
   } else {
     dt = A.dt[ip];
   }
-  if (dt == 0) { between(); return; }  // PARTICLE_LOOP(check_dt = 1), src/mptrac.h:1754-1759
+  if (dt == 0) {  // PARTICLE_LOOP(check_dt = 1), src/mptrac.h:1754-1759
+    between();
+    if (A.in_time) { A.time[ip] = a.time; A.lon[ip] = a.lon; A.lat[ip] = a.lat; A.p[ip] = a.p; }   // keep the device mirror
+    return;
+  }
 
   const unsigned long long ig = (unsigned long long)(A.ig0 + ip);
 
@@ -136,15 +145,22 @@ __device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Par
   if (PHYS & PHYS_SEDI) sediment(A.met, dt, A.rp[ip], A.rhop[ip], a, cube);
   if (A.modules & MOD_POS_POST) fix_position(A.met, a);
 
-  if (ADVECT > 0) A.time[ip] = a.time;
+  if (ADVECT > 0 || A.in_time) A.time[ip] = a.time;
   A.lon[ip] = a.lon;
   A.lat[ip] = a.lat;
   A.p[ip] = a.p;
+  if (A.host_time) {
+    if (ADVECT > 0) A.host_time[ip] = a.time;
+    A.host_lon[ip] = a.lon;
+    A.host_lat[ip] = a.lat;
+    A.host_p[ip] = a.p;
+  }
 }
 
 __device__ __forceinline__ Parcel load_parcel(const StepArgs &A, long long ip) {
   Parcel a;
-  a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
+  if (A.in_time) { a.time = A.in_time[ip]; a.lon = A.in_lon[ip]; a.lat = A.in_lat[ip]; a.p = A.in_p[ip]; }
+  else { a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip]; }
   return a;
 }
 
@@ -462,6 +478,8 @@ static StepArgs step_args(mpb_ctx *c, double t, int advect, unsigned phys, unsig
   A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p();
   A.dt = c->dt; A.uvwp = c->uvwp;
   A.rp = A.rhop = nullptr;
+  A.in_time = A.in_lon = A.in_lat = A.in_p = nullptr;
+  A.host_time = A.host_lon = A.host_lat = A.host_p = nullptr;
   if (phys & PHYS_SEDI) {
     REQUIRE(c->ctl.qnt_rp >= 0 && c->ctl.qnt_rp < c->nq && c->ctl.qnt_rhop >= 0 && c->ctl.qnt_rhop < c->nq,
             "sedimentation needs quantities rp and rhop");
@@ -487,6 +505,8 @@ static unsigned resident_blocks(mpb_ctx *c, step_fn fn) {
 static void launch_range(mpb_ctx *c, StepArgs A, int advect, unsigned phys, long long off, long long cnt, cudaStream_t stream) {
   if (cnt <= 0) return;
   A.time += off; A.lon += off; A.lat += off; A.p += off; A.dt += off; A.uvwp += 3 * off;
+  if (A.in_time) { A.in_time += off; A.in_lon += off; A.in_lat += off; A.in_p += off; }
+  if (A.host_time) { A.host_time += off; A.host_lon += off; A.host_lat += off; A.host_p += off; }
   if (A.rp) { A.rp += off; A.rhop += off; }
   A.np = cnt; A.ig0 += off;
   step_fn fn = pick_step(advect, phys);
@@ -952,7 +972,34 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
   if (meso_enabled(k)) phys |= PHYS_MESO;
   if (sedi_enabled(k)) phys |= PHYS_SEDI;
   REQUIRE(!(phys & PHYS_SEDI) || q != nullptr, "null quantity array");
-  const StepArgs A = step_args(c, t, k.advect, phys, MOD_TIMESTEPS | MOD_POS_PRE | MOD_POS_POST);
+  StepArgs A = step_args(c, t, k.advect, phys, MOD_TIMESTEPS | MOD_POS_PRE | MOD_POS_POST);
+
+  // Pinned host arrays are mapped into the device address space: the kernel then reads the parcels straight from host
+  // memory and writes them straight back -- both PCIe directions run concurrently for the whole launch, with no copy
+  // engine, no chunking and no staging (the persistent kernel keeps the next parcel's loads in flight a whole parcel
+  // ahead, which is what hides the link latency).  MPTRAC_B200_HOST_ZEROCOPY=0 selects the chunked copy pipeline.
+  static const bool allow_zc = !(std::getenv("MPTRAC_B200_HOST_ZEROCOPY") && std::atoi(std::getenv("MPTRAC_B200_HOST_ZEROCOPY")) == 0);
+  if (allow_zc) {
+    double *h[6] = {time, p, lon, lat, nullptr, nullptr};
+    int nh = 4;
+    if (phys & PHYS_SEDI) { h[4] = q + (size_t)k.qnt_rp * q_stride; h[5] = q + (size_t)k.qnt_rhop * q_stride; nh = 6; }
+    void *d[6];
+    bool mapped = true;
+    for (int i = 0; i < nh && mapped; i++) {
+      cudaPointerAttributes at;
+      mapped = cudaPointerGetAttributes(&at, h[i]) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
+      d[i] = mapped ? at.devicePointer : nullptr;
+    }
+    cudaGetLastError();
+    if (mapped) {
+      A.in_time = (const double *)d[0]; A.in_p = (const double *)d[1]; A.in_lon = (const double *)d[2]; A.in_lat = (const double *)d[3];
+      A.host_time = (double *)d[0]; A.host_p = (double *)d[1]; A.host_lon = (double *)d[2]; A.host_lat = (double *)d[3];
+      if (phys & PHYS_SEDI) { A.rp = (const double *)d[4]; A.rhop = (const double *)d[5]; }
+      launch_range(c, A, k.advect, phys, 0, np, c->stream);
+      CK(cudaStreamSynchronize(c->stream));   // the host arrays are valid on return
+      return 0;
+    }
+  }
   if (!c->lane[0]) {
     for (int i = 0; i < kLanes; i++) {
       CK(cudaStreamCreateWithFlags(&c->lane[i], cudaStreamNonBlocking));
@@ -965,8 +1012,21 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
   for (int i = 0; i < kLanes; i++) CK(cudaStreamWaitEvent(c->lane[i], c->lane_go, 0));
   long long chunk = (np + 2 * kLanes - 1) / (2 * kLanes);
   chunk = std::max<long long>(kHostChunkMin, std::min<long long>(chunk, kHostChunkMax));
+  if (const char *e = std::getenv("MPTRAC_B200_HOST_CHUNK")) chunk = std::max<long long>(kHostChunkMin, std::atoll(e));   // tuning aid
   chunk = (chunk + kBlock - 1) / kBlock * kBlock;
-  const bool strided = np > 0 && (p - time) >= np && (lon - p) == (p - time) && (lat - lon) == (p - time);
+  // MPTRAC_B200_TRACE=1: print the device timeline of this call's chunks (diagnostics; adds events, nothing else)
+  static const bool trace = std::getenv("MPTRAC_B200_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(e, st));
+    tev.push_back(e);
+  };
+  mark(c->stream);
+  static const bool allow_2d = !(std::getenv("MPTRAC_B200_HOST_2D") && std::atoi(std::getenv("MPTRAC_B200_HOST_2D")) == 0);
+  const bool strided = allow_2d && np > 0 && (p - time) >= np && (lon - p) == (p - time) && (lat - lon) == (p - time);
   const size_t spitch = strided ? sizeof(double) * (size_t)(p - time) : 0, dpitch = sizeof(double) * (size_t)c->np_max;
   int lane = 0;
   for (long long off = 0; off < np; off += chunk, lane = (lane + 1) % kLanes) {
@@ -987,7 +1047,9 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
       CK(cudaMemcpyAsync(c->q(k.qnt_rp) + off, q + (size_t)k.qnt_rp * q_stride + off, bytes, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(c->q(k.qnt_rhop) + off, q + (size_t)k.qnt_rhop * q_stride + off, bytes, cudaMemcpyHostToDevice, st));
     }
+    mark(st);
     launch_range(c, A, k.advect, phys, off, cnt, st);
+    mark(st);
     if (strided) {
       CK(cudaMemcpy2DAsync(time + off, spitch, c->time() + off, dpitch, bytes, 4, cudaMemcpyDeviceToHost, st));
     } else {
@@ -996,12 +1058,23 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
       CK(cudaMemcpyAsync(lon + off, c->lon() + off, bytes, cudaMemcpyDeviceToHost, st));
       CK(cudaMemcpyAsync(lat + off, c->lat() + off, bytes, cudaMemcpyDeviceToHost, st));
     }
+    mark(st);
   }
   for (int i = 0; i < kLanes; i++) {
     CK(cudaEventRecord(c->lane_done[i], c->lane[i]));
     CK(cudaStreamWaitEvent(c->stream, c->lane_done[i], 0));   // later work on the context's stream sees the step
   }
   for (int i = 0; i < kLanes; i++) CK(cudaStreamSynchronize(c->lane[i]));   // the host arrays are valid on return
+  if (trace && !tev.empty()) {
+    std::fprintf(stderr, "[mpb trace] host step, %lld parcels, chunk %lld%s:", (long long)np, chunk, strided ? ", 2-D copies" : "");
+    for (size_t i = 1; i < tev.size(); i++) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, tev[0], tev[i]));
+      std::fprintf(stderr, "%s%.0f", (i % 3 == 1) ? " | " : " ", ms * 1e3);
+    }
+    std::fprintf(stderr, "  (us since call: after H2D, after kernel, after D2H per chunk)\n");
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+  }
   API_END
 }
 

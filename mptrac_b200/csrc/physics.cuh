@@ -148,6 +148,25 @@ MPB_HD double div_by(double x, double d, double rd) {
   return fma(r, rd, q);
 }
 
+// Where a last-ulp difference is harmless -- interpolation weights, metre -> degree conversions, i.e. everything that
+// enters a position continuously -- the production device build multiplies by the reciprocal and skips the correction
+// (one fp64 op instead of a dependent chain of three; the RK stage is a latency-bound dependent chain).  The host build
+// (tests/_hostemu) and the strict device build (-DMPB_STRICT) keep the exact sequence; indices that decide a cell for
+// sorting or for the mesoscale statistics are always exact.  Measured deviation from the oracle: see DESIGN.md.
+#if defined(__CUDA_ARCH__) && !defined(MPB_STRICT)
+#define MPB_FAST_QUOT 1
+#else
+#define MPB_FAST_QUOT 0
+#endif
+MPB_HD double quot(double x, double d, double rd) {
+#if MPB_FAST_QUOT
+  (void)d;
+  return x * rd;
+#else
+  return div_by(x, d, rd);
+#endif
+}
+
 constexpr double kR360 = 1.0 / 360.0;
 constexpr double kR1000 = 1.0 / 1000.0;
 constexpr double kRH0 = 1.0 / kH0;
@@ -165,7 +184,7 @@ MPB_HD double lin(double x0, double y0, double x1, double y1, double x) {
 }
 
 // km -> hPa at pressure p (src/mptrac.h:941)
-MPB_HD double dz2dp(double dz, double p) { return div_by(-dz * p, kH0, kRH0); }
+MPB_HD double dz2dp(double dz, double p) { return quot(-dz * p, kH0, kRH0); }
 
 // metres east / north -> coordinate increment (src/mptrac.h:904-906, 922-923, 966, 989).
 // DX2DEG(dx, lat) = dx * 180 / (pi * RE * cos(lat * pi / 180)), 0 within 0.001 deg of a pole.  The divisor only depends on
@@ -176,6 +195,7 @@ struct LonScale {
   double d, rd;
   int mode;  // 0 = Cartesian (identity), 1 = polar cap (zero), 2 = divide by d
 };
+constexpr double kDegPerM = 180.0 / (1000.0 * kPi * kRE);   // fast path of DY2DEG(dy / 1000)
 MPB_HD LonScale lon_scale(int coord_type, double lat) {
   LonScale k;
   k.d = 1.0; k.rd = 1.0;
@@ -184,17 +204,28 @@ MPB_HD LonScale lon_scale(int coord_type, double lat) {
   k.mode = 2;
   k.d = kPiRE * cos(lat * (kPi / 180.0));
   k.rd = 1.0 / k.d;
+#if MPB_FAST_QUOT
+  k.rd *= 0.18;   // metres -> degrees in one multiply: dx / 1000 * 180 / d
+#endif
   return k;
 }
 MPB_HD double dx2coord(const LonScale &k, double dx) {
   if (k.mode == 0) return dx;
   if (k.mode == 1) return 0.0;
+#if MPB_FAST_QUOT
+  return dx * k.rd;
+#else
   return div_by(div_by(dx, 1000.0, kR1000) * 180., k.d, k.rd);
+#endif
 }
 MPB_HD double dx2coord(int coord_type, double dx, double lat) { return dx2coord(lon_scale(coord_type, lat), dx); }
 MPB_HD double dy2coord(int coord_type, double dy) {
   if (coord_type != 0) return dy;
+#if MPB_FAST_QUOT
+  return dy * kDegPerM;
+#else
   return div_by(div_by(dy, 1000.0, kR1000) * 180., kPiRE, kRPiRE);
+#endif
 }
 
 // Interval search on a monotone axis; same result as the reference bisection (3495-3521):
@@ -342,8 +373,17 @@ struct CellAxes {
 };
 MPB_HD void axes_reset(CellAxes &a) { a.ix = -1; a.iy = -1; a.iz = -1; }
 
-MPB_HD int lon_cell(const MetView &g, double lon, CellAxes &a) {
+// (`exact` = the index decides something discontinuous -- the mesoscale statistics; an interpolation lookup is continuous
+// across a cell face, so its index may come from the uncorrected quotient)
+MPB_HD int lon_cell(const MetView &g, double lon, CellAxes &a, bool exact = false) {
+#if MPB_FAST_QUOT
+  int ix;
+  if (exact) ix = lon_interval(g, lon);
+  else { ix = (int)((lon - g.lon_first) * g.r_lon_d); ix = ix < 0 ? 0 : (ix > g.nx - 2 ? g.nx - 2 : ix); }
+#else
+  (void)exact;
   const int ix = lon_interval(g, lon);
+#endif
   if (ix != a.ix) { a.x = load_cell(g.lonc + ix); a.ix = ix; }
   return ix;
 }
@@ -373,14 +413,14 @@ MPB_HD void stencil_2d(const MetView &g, double lon, double lat, CellAxes &a, St
   clamp_horizontal(g, lon, lat, lon2, lat2);
   s.ix = lon_cell(g, lon2, a);
   s.iy = lat_cell(g, lat2, a);
-  s.wx = div_by(a.x.hi - lon2, a.x.hi - a.x.lo, a.x.rd);
-  s.wy = div_by(a.y.hi - lat2, a.y.hi - a.y.lo, a.y.rd);
+  s.wx = quot(a.x.hi - lon2, a.x.hi - a.x.lo, a.x.rd);
+  s.wy = quot(a.y.hi - lat2, a.y.hi - a.y.lo, a.y.rd);
 }
 
 MPB_HD void stencil_3d(const MetView &g, double lon, double lat, double p, CellAxes &a, Stencil &s) {
   s.iz = p_cell(g, p, a);
   stencil_2d(g, lon, lat, a, s);
-  s.wz = div_by(a.z.hi - p, a.z.hi - a.z.lo, a.z.rd);
+  s.wz = quot(a.z.hi - p, a.z.hi - a.z.lo, a.z.rd);
 }
 
 // w * (lo - hi) + hi with the difference taken in fp32 first (3023-3038)
@@ -461,7 +501,7 @@ MPB_HD void fetch_cube(const MetView &g, const Stencil &s, Cube &c) {
                     lerp_f32(s.wz, c.n110.member, c.n111.member)))
 
 // time weight of met0 (3133)
-MPB_HD double time_weight(const MetView &g, double ts) { return div_by(g.t1 - ts, g.dt01, g.r_dt01); }
+MPB_HD double time_weight(const MetView &g, double ts) { return quot(g.t1 - ts, g.dt01, g.r_dt01); }
 
 // u, v, w at (p, lon, lat) for the time weight wt: intpol_met_time_3d x3 sharing one stencil (3112-3137, 3638-3643)
 MPB_HD void wind_at(const MetView &g, double wt, double lon, double lat, double p, Cube &c,
@@ -799,7 +839,7 @@ MPB_HD void diffuse_mesoscale(const MetView &g, const CtlView &k, double dt, uin
                               Parcel &a, float &up, float &vp, float &wp, Cube &c) {
   // raw index search at the parcel position: no wrap / clamp helper here (4283-4285)
   Stencil s;
-  s.ix = lon_cell(g, a.lon, c.ax);
+  s.ix = lon_cell(g, a.lon, c.ax, true);
   s.iy = lat_cell(g, a.lat, c.ax);
   s.iz = p_cell(g, a.p, c.ax);
 

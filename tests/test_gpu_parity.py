@@ -343,8 +343,8 @@ def test_inactive_and_ragged_parcels(oracle):
     assert np.all(out["time"] == 1500.0)
 
 
-@pytest.mark.parametrize("strided", [False, True], ids=["separate_arrays", "atm_t_layout"])
-def test_host_resident_step_equals_three_calls(strided):
+@pytest.mark.parametrize("layout", ["separate_arrays", "atm_t_layout", "pinned"])
+def test_host_resident_step_equals_three_calls(layout):
     """mpb_run_timestep_host (chunked upload / step / download pipeline) == set_atm + run_timestep + get_atm, bit for bit,
     including steps that fall back because a cell sort is due, with diffusion (random numbers addressed per chunk) and
     sedimentation (rp / rhop uploaded per chunk)."""
@@ -361,8 +361,12 @@ def test_host_resident_step_equals_three_calls(strided):
         b.run_timestep(0.0)                          # fmod(0, SORT_DT) == 0: the very first step already sorts
         h = b.get_atm()                              # the host copy a driver would hold from here on
         hq = h["q"]
-        if strided:                                  # time, p, lon, lat as consecutive rows of one block (atm_t): 2-D copies
+        if layout != "separate_arrays":              # time, p, lon, lat as consecutive rows of one block (atm_t): 2-D copies
             blk = np.stack([h[k] for k in ("time", "p", "lon", "lat")])
+            if layout == "pinned":                   # page-locked: the kernel reads / writes the host arrays itself
+                import torch
+                keep = (torch.from_numpy(blk).pin_memory(), torch.from_numpy(np.ascontiguousarray(hq)).pin_memory())
+                blk, hq = keep[0].numpy(), keep[1].numpy()
             h = {k: blk[i] for i, k in enumerate(("time", "p", "lon", "lat"))}
         for s in range(1, 5):                        # t = 900 triggers the sort -> fallback path
             a.run_timestep(300.0 * s)
