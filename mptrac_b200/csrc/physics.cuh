@@ -152,7 +152,7 @@ MPB_HD double div_by(double x, double d, double rd) {
 // enters a position continuously -- the production device build multiplies by the reciprocal and skips the correction
 // (one fp64 op instead of a dependent chain of three; the RK stage is a latency-bound dependent chain).  The host build
 // (tests/_hostemu) and the strict device build (-DMPB_STRICT) keep the exact sequence; indices that decide a cell for
-// sorting or for the mesoscale statistics are always exact.  Measured deviation from the oracle: see DESIGN.md.
+// sorting or for the mesoscale statistics are always exact.  Measured deviations: see DESIGN.md.
 #if defined(__CUDA_ARCH__) && !defined(MPB_STRICT)
 #define MPB_FAST_QUOT 1
 #else
