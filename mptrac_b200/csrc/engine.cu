@@ -90,6 +90,9 @@ constexpr unsigned PHYS_TURB = 1, PHYS_MESO = 2, PHYS_SEDI = 4;
 #ifndef MPB_PERSIST      // 1: grid = SMs x resident blocks, threads loop over parcels; 0: one parcel per thread
 #define MPB_PERSIST 1
 #endif
+#ifndef MPB_CONTIG       // persistent form: 1 = each block walks its own contiguous parcel range, 0 = grid-stride.
+#define MPB_CONTIG 0     // Measured on B200 (C2, sorted): 131 us contiguous vs 121 us grid-stride -- with the grid-stride walk all
+#endif                   // SMs sweep the same window of the sorted parcels together and share its nodes through L2
 #ifndef MPB_PREFETCH     // hint the next parcel's met cell into L1 (persistent form only).  Measured on B200 (C2, sorted):
 #define MPB_PREFETCH 0   // 139 us with the hint vs 126 us without -- its index arithmetic costs more than the hits save
 #endif
@@ -171,15 +174,24 @@ __device__ __forceinline__ Parcel load_parcel(const StepArgs &A, long long ip) {
 // MPB_PREFETCH additionally hints the met cell of parcel k+1 into L1 once the first lookup of k has been issued.
 template <int ADVECT, unsigned PHYS>
 __global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
+#if MPB_CONTIG
+  // every block owns one contiguous range of the (cell-sorted) parcels and walks it kBlock parcels at a time
+  const long long per_block = ((A.np + gridDim.x - 1) / gridDim.x + kBlock - 1) / kBlock * kBlock;
+  const long long stride = kBlock;
+  long long ip = (long long)blockIdx.x * per_block + threadIdx.x;
+  const long long end = min(A.np, ((long long)blockIdx.x + 1) * per_block);
+#else
   const long long stride = (long long)gridDim.x * kBlock;
   long long ip = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (ip >= A.np) return;
+  const long long end = A.np;
+#endif
+  if (ip >= end) return;
   Parcel nxt = load_parcel(A, ip);
   for (;;) {
     const Parcel a = nxt;
     const long long cur = ip;
     ip += stride;
-    const bool more = ip < A.np;
+    const bool more = ip < end;
     if (more) nxt = load_parcel(A, ip);
 #if MPB_PREFETCH
     step_parcel<ADVECT, PHYS>(A, cur, a, [&]() { if (more) prefetch_cube(A.met, nxt.lon, nxt.lat, nxt.p); });
