@@ -26,8 +26,16 @@
 extern "C" {
 #endif
 
-#define MPB_ABI_VERSION 1
+#define MPB_ABI_VERSION 2
 #define MPB_MIX_MAXQ 23  /* number of mixable quantities, src/mptrac.c:5222-5230 */
+
+/* Quantities module_meteo (src/mptrac.c:5062-5165) can set on the device: everything that derives from the met fields
+ * the path keeps resident (T, u, v, w on pressure levels; ps, pbl).  Slot order of mpb_ctl_t::qnt_meteo. */
+enum {
+  MPB_Q_PS, MPB_Q_PBL, MPB_Q_P, MPB_Q_T, MPB_Q_RHO, MPB_Q_U, MPB_Q_V, MPB_Q_W, MPB_Q_VH, MPB_Q_VZ, MPB_Q_THETA,
+  MPB_Q_PSAT, MPB_Q_PSICE, MPB_Q_ZETA_D, MPB_NMETEO
+};
+#define MPB_METEO_SLOTS 16
 
 typedef struct mpb_ctx mpb_ctx;
 
@@ -60,6 +68,8 @@ typedef struct mpb_ctl {
   double turb_pbl_trans;
   double mixing_dt, mixing_trop, mixing_strat;
   double mixing_lon0, mixing_lon1, mixing_lat0, mixing_lat1, mixing_z0, mixing_z1;
+  double met_dt_out;                        /* module_meteo every met_dt_out seconds (<= 0: never)  ctl->met_dt_out */
+  int32_t qnt_meteo[MPB_METEO_SLOTS];       /* quantity index per MPB_Q_* slot or -1               ctl->qnt_ps ... */
 } mpb_ctl_t;
 
 /* Host view of one met_t time level (src/mptrac.h:3844-4014).  3-D element (ix,iy,iz) lives at
@@ -143,7 +153,8 @@ int mpb_run_timestep_host(mpb_ctx *ctx, double t, int64_t np, double *time, doub
 #define MPB_MOD_SEDI      0x040
 #define MPB_MOD_POSITION1 0x080
 #define MPB_MOD_MIXING    0x100
-#define MPB_MOD_ALL       0x1ff
+#define MPB_MOD_METEO     0x200   /* between POSITION1 and MIXING, like the reference (src/mptrac.c:7927-7945) */
+#define MPB_MOD_ALL       0x3ff
 int mpb_run_modules(mpb_ctx *ctx, double t, unsigned mask);
 
 /* --- single modules (same symbols the reference exports, src/mptrac.h:6140-7132); each is the
@@ -155,6 +166,7 @@ int mpb_module_diff_turb(mpb_ctx *ctx);             /* src/mptrac.c:4588 */
 int mpb_module_diff_meso(mpb_ctx *ctx);             /* src/mptrac.c:4266 */
 int mpb_module_sedi(mpb_ctx *ctx);                  /* src/mptrac.c:5859 */
 int mpb_module_sort(mpb_ctx *ctx);                  /* src/mptrac.c:5887 */
+int mpb_module_meteo(mpb_ctx *ctx);                 /* src/mptrac.c:5062, the MPB_Q_* quantities; every parcel (check_dt = 0) */
 int mpb_module_mixing(mpb_ctx *ctx, double t);      /* src/mptrac.c:5169 (single device) */
 int mpb_module_rng(mpb_ctx *ctx, double *rs_host, int64_t n, int method); /* src/mptrac.c:5753; fills host array, advances counter */
 

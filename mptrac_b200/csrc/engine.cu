@@ -262,6 +262,41 @@ __global__ void gather_kernel(const double *__restrict__ src, double *__restrict
   for (int a = 0; a < narr; a++) dst[a * stride + ip] = src[a * stride + j];
 }
 
+// module_meteo for the quantities the resident fields give (src/mptrac.c:5062-5165): every parcel, dt or not
+struct MeteoArgs {
+  MetView met;
+  const double *time, *lon, *lat, *p;
+  double *q;            // [nq][q_stride]
+  long long q_stride, np;
+  int qnt[MPB_METEO_SLOTS];
+};
+
+__global__ void __launch_bounds__(128) meteo_kernel(const __grid_constant__ MeteoArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np) return;
+  Parcel a;
+  a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
+  Cube cube;
+  cube_reset(cube);
+  MeteoValues m;
+  meteo_at(A.met, a, cube, m);
+  auto set = [&](int slot, double v) { if (A.qnt[slot] >= 0) A.q[(long long)A.qnt[slot] * A.q_stride + ip] = v; };
+  set(MPB_Q_PS, m.ps);
+  set(MPB_Q_PBL, m.pbl);
+  set(MPB_Q_P, a.p);
+  set(MPB_Q_T, m.t);
+  set(MPB_Q_RHO, 100. * a.p / (kRA * m.t));                 // RHO, src/mptrac.h:1961
+  set(MPB_Q_U, m.u);
+  set(MPB_Q_V, m.v);
+  set(MPB_Q_W, m.w);
+  set(MPB_Q_VH, sqrt(m.u * m.u + m.v * m.v));
+  set(MPB_Q_VZ, -1e3 * kH0 / a.p * m.w);
+  if (A.qnt[MPB_Q_PSAT] >= 0) set(MPB_Q_PSAT, saturation_pressure(m.t));
+  if (A.qnt[MPB_Q_PSICE] >= 0) set(MPB_Q_PSICE, saturation_pressure_ice(m.t));
+  if (A.qnt[MPB_Q_THETA] >= 0) set(MPB_Q_THETA, potential_temperature(a.p, m.t));
+  if (A.qnt[MPB_Q_ZETA_D] >= 0) set(MPB_Q_ZETA_D, zeta_diagnosed(m.ps, a.p, m.t));
+}
+
 struct BoxArgs {
   double t0, t1, lon0, lon1, lat0, lat1, z0, z1;
   int nx, ny, nz;
@@ -630,6 +665,27 @@ static void mixing_apply(mpb_ctx *c, int iq) {
 
 static bool hits(double t, double every) { return std::fmod(t, every) == 0; }
 
+static bool meteo_wanted(const mpb_ctl_t &k) {
+  for (int i = 0; i < MPB_NMETEO; i++) if (k.qnt_meteo[i] >= 0) return true;
+  return false;
+}
+
+static void launch_meteo(mpb_ctx *c) {
+  REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
+  if (c->np == 0 || !meteo_wanted(c->ctl)) return;
+  MeteoArgs A;
+  A.met = met_view(c);
+  A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p();
+  A.q = c->nq ? c->q(0) : nullptr; A.q_stride = c->np_max; A.np = c->np;
+  for (int i = 0; i < MPB_METEO_SLOTS; i++) {
+    A.qnt[i] = i < MPB_NMETEO ? c->ctl.qnt_meteo[i] : -1;
+    REQUIRE(A.qnt[i] < c->nq, "meteo quantity index out of range");
+  }
+  meteo_kernel<<<nblocks(c->np, 128), 128, 0, c->stream>>>(A);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
@@ -715,6 +771,7 @@ int mpb_set_ctl(mpb_ctx *c, const mpb_ctl_t *ctl) {
   REQUIRE(ctl->nq == c->nq, "ctl.nq differs from the context's nq");
   REQUIRE(ctl->advect == 0 || ctl->advect == 1 || ctl->advect == 2 || ctl->advect == 4, "ADVECT must be 0, 1, 2 or 4");
   REQUIRE(ctl->n_mix_qnt >= 0 && ctl->n_mix_qnt <= MPB_MIX_MAXQ, "n_mix_qnt out of range");
+  for (int i = 0; i < MPB_NMETEO; i++) REQUIRE(ctl->qnt_meteo[i] < ctl->nq, "meteo quantity index out of range");
   c->ctl = *ctl;
   c->have_ctl = true;
   API_END
@@ -926,7 +983,7 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   unsigned modules = 0;
   if (mask & MPB_MOD_POSITION0) modules |= MOD_POS_PRE;
   if (mask & MPB_MOD_POSITION1) modules |= MOD_POS_POST;
-  const bool whole = (mask & 0xff) == 0xff;
+  const bool whole = (mask & 0xff) == 0xff;   // timesteps ... position1 in one launch: dt stays in registers
   const bool sort_now = (mask & MPB_MOD_SORT) && k.sort_dt > 0 && hits(t, k.sort_dt);
   if (mask & MPB_MOD_TIMESTEPS) {
     if (sort_now) {
@@ -943,6 +1000,8 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
     do_sort(c);
   }
   if (modules || advect || phys) launch_step(c, t, advect, phys, modules);
+  if ((mask & MPB_MOD_METEO) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out)))   // src/mptrac.c:7927-7929
+    launch_meteo(c);
   if ((mask & MPB_MOD_MIXING) && k.mixing_trop >= 0 && k.mixing_strat >= 0 &&
       (k.mixing_dt <= 0 || hits(t, k.mixing_dt))) {  // src/mptrac.c:7943-7945
     mixing_begin(c, t);
@@ -971,8 +1030,10 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
   const mpb_ctl_t &k = c->ctl;
   const bool sort_now = k.sort_dt > 0 && hits(t, k.sort_dt);
   const bool mix_now = k.mixing_trop >= 0 && k.mixing_strat >= 0 && (k.mixing_dt <= 0 || hits(t, k.mixing_dt)) && k.n_mix_qnt > 0;
-  if (sort_now || mix_now || np < 4 * kHostChunkMin) {
-    // steps with a global phase (cell sort, box means) and tiny problems take the plain sequence
+  const bool meteo_now = meteo_wanted(k) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out));
+  if (sort_now || mix_now || meteo_now || np < 4 * kHostChunkMin) {
+    // steps with a global phase (cell sort, box means), steps that write quantities (meteo) and tiny problems take the
+    // plain sequence
     REQUIRE(mpb_set_atm(c, np, time, p, lon, lat, q, q_stride) == 0, g_err);
     run_modules(c, t, MPB_MOD_ALL);
     REQUIRE(mpb_get_atm(c, time, p, lon, lat, q, q_stride) == 0, g_err);
@@ -1133,6 +1194,12 @@ int mpb_module_sedi(mpb_ctx *c) {
   API_BEGIN
   use(c);
   launch_step(c, 0.0, 0, PHYS_SEDI, 0);
+  API_END
+}
+int mpb_module_meteo(mpb_ctx *c) {
+  API_BEGIN
+  use(c);
+  launch_meteo(c);
   API_END
 }
 int mpb_module_sort(mpb_ctx *c) {

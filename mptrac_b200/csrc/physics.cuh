@@ -892,6 +892,39 @@ MPB_HD void sediment(const MetView &g, double dt, double rp, double rhop, Parcel
 }
 
 // ----------------------------------------------------------------------------------------------
+// module_meteo (5062-5165), the quantities that derive from the resident fields.  INTPOL_TIME_ALL (src/mptrac.h:1278)
+// computes ONE stencil (wrapped longitude, clamped latitude) and applies it to every 3-D and 2-D field.
+// ----------------------------------------------------------------------------------------------
+struct MeteoValues {
+  double ps, pbl, t, u, v, w;
+};
+
+MPB_HD void meteo_at(const MetView &g, const Parcel &a, Cube &c, MeteoValues &m) {
+  Stencil s;
+  stencil_3d(g, a.lon, a.lat, a.p, c.ax, s);
+  fetch_cube(g, s, c);
+  const double wt = time_weight(g, a.time);
+  m.t = lerp_f64(wt, MPB_TRILERP(t0), MPB_TRILERP(t1));
+  m.u = lerp_f64(wt, MPB_TRILERP(u0), MPB_TRILERP(u1));
+  m.v = lerp_f64(wt, MPB_TRILERP(v0), MPB_TRILERP(v1));
+  m.w = lerp_f64(wt, MPB_TRILERP(w0), MPB_TRILERP(w1));
+  const size_t b = (size_t)s.ix * (size_t)g.ny + (size_t)s.iy, sx = (size_t)g.ny;
+  const float4 a00 = ldg(g.s + b), a01 = ldg(g.s + b + 1), a10 = ldg(g.s + b + sx), a11 = ldg(g.s + b + sx + 1);
+  m.ps = time_blend_guarded(wt, bilerp_guarded(s.wx, s.wy, a00.x, a01.x, a10.x, a11.x),
+                            bilerp_guarded(s.wx, s.wy, a00.z, a01.z, a10.z, a11.z));
+  m.pbl = time_blend_guarded(wt, bilerp_guarded(s.wx, s.wy, a00.y, a01.y, a10.y, a11.y),
+                             bilerp_guarded(s.wx, s.wy, a00.w, a01.w, a10.w, a11.w));
+}
+
+constexpr double kT0 = 273.15, kKappa = 0.286;
+MPB_HD double potential_temperature(double p, double t) { return t * pow(1000. / p, kKappa); }   // THETA, src/mptrac.h:2124
+MPB_HD double saturation_pressure(double t) { return 6.112 * exp(17.62 * (t - kT0) / (243.12 + t - kT0)); }      // PSAT :1808
+MPB_HD double saturation_pressure_ice(double t) { return 6.112 * exp(22.46 * (t - kT0) / (272.62 + t - kT0)); }  // PSICE :1832
+MPB_HD double zeta_diagnosed(double ps, double p, double t) {                                                     // ZETA :2293
+  return (p / ps <= 0.3 ? 1. : sin(kPi / 2. * (1. - p / ps) / (1. - 0.3))) * potential_temperature(p, t);
+}
+
+// ----------------------------------------------------------------------------------------------
 // cell key of module_sort (5909-5919): raw index searches, no wrap
 // ----------------------------------------------------------------------------------------------
 MPB_HD int cell_key(const MetView &g, double lon, double lat, double p) {

@@ -9,7 +9,8 @@
  *
  *   mptrac_update_device (src/mptrac.c:8005)  -> mpb_set_ctl / set_clim_tropo / set_met / set_atm / set_uvwp
  *   mptrac_update_host   (src/mptrac.c:8061)  -> mpb_get_atm / get_uvwp / get_dt
- *   mptrac_run_timestep  (src/mptrac.c:7851)  -> mpb_run_timestep, or -- when the control file enables modules that
+ *   mptrac_run_timestep  (src/mptrac.c:7851)  -> mpb_run_timestep (module_meteo included when all its quantities derive
+ *                                               from T, u, v, w, ps, pbl), or -- when the control file enables modules that
  *                                               are not on the device path -- mpb_run_modules segments with the
  *                                               reference's own CPU modules called in between (hybrid mode)
  *   mptrac_free          (src/mptrac.c:6377)  -> mpb_destroy, then the reference's own mptrac_free
@@ -72,7 +73,30 @@ static void put_ctl(const ctl_t *c) {
   k.mixing_dt = c->mixing_dt; k.mixing_trop = c->mixing_trop; k.mixing_strat = c->mixing_strat;
   k.mixing_lon0 = c->mixing_lon0; k.mixing_lon1 = c->mixing_lon1; k.mixing_lat0 = c->mixing_lat0;
   k.mixing_lat1 = c->mixing_lat1; k.mixing_z0 = c->mixing_z0; k.mixing_z1 = c->mixing_z1;
+  k.met_dt_out = c->met_dt_out;
+  for (int i = 0; i < MPB_METEO_SLOTS; i++) k.qnt_meteo[i] = -1;
+  k.qnt_meteo[MPB_Q_PS] = c->qnt_ps; k.qnt_meteo[MPB_Q_PBL] = c->qnt_pbl; k.qnt_meteo[MPB_Q_P] = c->qnt_p;
+  k.qnt_meteo[MPB_Q_T] = c->qnt_t; k.qnt_meteo[MPB_Q_RHO] = c->qnt_rho; k.qnt_meteo[MPB_Q_U] = c->qnt_u;
+  k.qnt_meteo[MPB_Q_V] = c->qnt_v; k.qnt_meteo[MPB_Q_W] = c->qnt_w; k.qnt_meteo[MPB_Q_VH] = c->qnt_vh;
+  k.qnt_meteo[MPB_Q_VZ] = c->qnt_vz; k.qnt_meteo[MPB_Q_THETA] = c->qnt_theta; k.qnt_meteo[MPB_Q_PSAT] = c->qnt_psat;
+  k.qnt_meteo[MPB_Q_PSICE] = c->qnt_psice; k.qnt_meteo[MPB_Q_ZETA_D] = c->qnt_zeta_d;
   MPB(mpb_set_ctl(g_ctx, &k));
+}
+
+/* Does module_meteo (src/mptrac.c:5062-5165) set any quantity of this control file that the device cannot compute
+ * (anything that needs met fields beyond T, u, v, w, ps, pbl, or a climatology)?  Then it runs on the host. */
+static int meteo_needs_host(const ctl_t *c) {
+  static int force = -1;   /* MPTRAC_B200_HOST_METEO=1 keeps module_meteo on the reference's CPU code (hybrid mode) */
+  if (force < 0) force = getenv("MPTRAC_B200_HOST_METEO") ? atoi(getenv("MPTRAC_B200_HOST_METEO")) : 0;
+  if (force) return 1;
+  const int other[] = {
+    c->qnt_ts, c->qnt_zs, c->qnt_us, c->qnt_vs, c->qnt_ess, c->qnt_nss, c->qnt_shf, c->qnt_lsm, c->qnt_sst, c->qnt_pt,
+    c->qnt_tt, c->qnt_zt, c->qnt_h2ot, c->qnt_zg, c->qnt_h2o, c->qnt_o3, c->qnt_lwc, c->qnt_rwc, c->qnt_iwc, c->qnt_swc,
+    c->qnt_cc, c->qnt_pct, c->qnt_pcb, c->qnt_cl, c->qnt_plcl, c->qnt_plfc, c->qnt_pel, c->qnt_cape, c->qnt_cin, c->qnt_o3c,
+    c->qnt_hno3, c->qnt_oh, c->qnt_h2o2, c->qnt_ho2, c->qnt_o1d, c->qnt_pw, c->qnt_sh, c->qnt_rh, c->qnt_rhice,
+    c->qnt_tvirt, c->qnt_lapse, c->qnt_pv, c->qnt_tdew, c->qnt_tice, c->qnt_tnat, c->qnt_tsts};
+  for (size_t i = 0; i < sizeof(other) / sizeof(other[0]); i++) if (other[i] >= 0) return 1;
+  return 0;
 }
 
 static void put_met(met_t *m) {
@@ -186,7 +210,7 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
   const int pbl_cpu = ctl->diffusion && ctl->turb_pbl_scheme == 1;
   const int conv_cpu = (ctl->conv_mix_pbl || ctl->conv_cape >= 0) && (ctl->conv_dt <= 0 || fmod(t, ctl->conv_dt) == 0);
   const int iso_cpu = ctl->isosurf >= 1 && ctl->isosurf <= 4;
-  const int meteo_cpu = ctl->met_dt_out > 0 && (ctl->met_dt_out < ctl->dt_mod || fmod(t, ctl->met_dt_out) == 0);
+  const int meteo_cpu = ctl->met_dt_out > 0 && (ctl->met_dt_out < ctl->dt_mod || fmod(t, ctl->met_dt_out) == 0) && meteo_needs_host(ctl);
   const int bound_cpu = (ctl->bound_lat0 < ctl->bound_lat1) && (ctl->bound_p0 > ctl->bound_p1);
   const int decay_cpu = ctl->tdec_trop > 0 && ctl->tdec_strat > 0;
   const int chemgrid_cpu = ctl->oh_chem_reaction != 0 || ctl->h2o2_chem_reaction != 0 || (ctl->kpp_chem && fmod(t, ctl->dt_kpp) == 0);
@@ -224,6 +248,7 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
       FLUSH_HOST();
     }
     seg |= MPB_MOD_POSITION1;
+    if (!meteo_cpu) seg |= MPB_MOD_METEO;       /* every quantity module_meteo sets here is available on the device */
     MPB(mpb_run_modules(g_ctx, t, seg));
     g_dev_newer = 1;
     if (tail_cpu) {

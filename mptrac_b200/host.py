@@ -14,15 +14,18 @@ import ctypes as C
 import os
 from dataclasses import dataclass, field
 from pathlib import Path
-from typing import Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import numpy as np
 
 MIX_MAXQ = 23
+# quantities module_meteo can set on the device, in the slot order of mpb_ctl_t::qnt_meteo (MPB_Q_*)
+METEO_QNT = ("ps", "pbl", "p", "t", "rho", "u", "v", "w", "vh", "vz", "theta", "psat", "psice", "zeta_d")
+METEO_SLOTS = 16
 # module bits of mpb_run_modules (include/mptrac_b200.h MPB_MOD_*)
-MOD_TIMESTEPS, MOD_SORT, MOD_POSITION0, MOD_ADVECT, MOD_DIFF_TURB, MOD_DIFF_MESO, MOD_SEDI, MOD_POSITION1, MOD_MIXING = (
-    1 << i for i in range(9))
-MOD_ALL = 0x1ff
+(MOD_TIMESTEPS, MOD_SORT, MOD_POSITION0, MOD_ADVECT, MOD_DIFF_TURB, MOD_DIFF_MESO, MOD_SEDI, MOD_POSITION1, MOD_MIXING,
+ MOD_METEO) = (1 << i for i in range(10))
+MOD_ALL = 0x3ff
 _LIBDIR = Path(__file__).resolve().parent / "_lib"
 
 
@@ -42,7 +45,8 @@ class _CtlStruct(C.Structure):
             "turb_dx_pbl", "turb_dx_trop", "turb_dx_strat", "turb_dz_pbl", "turb_dz_trop", "turb_dz_strat",
             "turb_mesox", "turb_mesoz", "turb_pbl_trans",
             "mixing_dt", "mixing_trop", "mixing_strat",
-            "mixing_lon0", "mixing_lon1", "mixing_lat0", "mixing_lat1", "mixing_z0", "mixing_z1")]
+            "mixing_lon0", "mixing_lon1", "mixing_lat0", "mixing_lat1", "mixing_z0", "mixing_z1", "met_dt_out")]
+        + [("qnt_meteo", C.c_int32 * METEO_SLOTS)]
     )
 
 
@@ -105,13 +109,20 @@ class Ctl:
     mixing_lat1: float = 90.0
     mixing_z0: float = -5.0
     mixing_z1: float = 85.0
+    met_dt_out: float = 0.0                                   # module_meteo off (NB the reference's default is 0.1 = every step)
+    qnt_meteo: Dict[str, int] = field(default_factory=dict)   # quantity name (METEO_QNT) -> index, e.g. {"t": 0, "u": 1}
 
     def to_struct(self) -> _CtlStruct:
         s = _CtlStruct()
         for name, _ in _CtlStruct._fields_:
-            if name in ("mix_qnt", "_pad", "n_mix_qnt"):
+            if name in ("mix_qnt", "_pad", "n_mix_qnt", "qnt_meteo"):
                 continue
             setattr(s, name, getattr(self, name))
+        unknown = set(self.qnt_meteo) - set(METEO_QNT)
+        if unknown:
+            raise ValueError(f"module_meteo quantities not available on the device: {sorted(unknown)}")
+        for i in range(METEO_SLOTS):
+            s.qnt_meteo[i] = int(self.qnt_meteo.get(METEO_QNT[i], -1)) if i < len(METEO_QNT) else -1
         mq = list(self.mix_qnt)
         if len(mq) > MIX_MAXQ:
             raise ValueError("too many mixing quantities")
@@ -214,6 +225,7 @@ def load_library(strict: bool = False) -> C.CDLL:
         "mpb_module_diff_meso": (i32, [vp]),
         "mpb_module_sedi": (i32, [vp]),
         "mpb_module_sort": (i32, [vp]),
+        "mpb_module_meteo": (i32, [vp]),
         "mpb_module_mixing": (i32, [vp, dbl]),
         "mpb_module_rng": (i32, [vp, vp, i64, i32]),
         "mpb_mixing_begin": (i32, [vp, dbl]),
@@ -389,6 +401,9 @@ class Engine:
             stride = q.strides[0] // 8
         self._ck(self._lib.mpb_run_timestep_host(self._h, float(t), n, *[_ptr(a) for a in arrs],
                                                  _ptr(q) if self.nq else None, stride))
+
+    def module_meteo(self):
+        self._ck(self._lib.mpb_module_meteo(self._h))
 
     def run_modules(self, t: float, mask: int):
         self._ck(self._lib.mpb_run_modules(self._h, float(t), int(mask)))

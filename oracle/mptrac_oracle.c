@@ -588,6 +588,46 @@ void orc_grid_bin(const orc_atm_t *atm, int nq, int nx, int ny, int nz, double l
 /* ---------------------------------------------------------------------------------------------
  * mptrac_run_timestep restricted to the path, 7877-7945
  * ------------------------------------------------------------------------------------------- */
+/* ---------------------------------------------------------------------------------------------
+ * module_meteo, 5062-5165, restricted to the quantities that derive from T, u, v, w, ps, pbl.
+ * INTPOL_TIME_ALL (src/mptrac.h:1278-1316): the first 3-D lookup initialises indices and weights, every
+ * other field -- 3-D and 2-D -- reuses them; all parcels are visited (check_dt = 0).
+ * ------------------------------------------------------------------------------------------- */
+#define C_T0 273.15
+#define C_KAPPA 0.286
+static double theta_of(double p, double t) { return t * pow(1000. / p, C_KAPPA); }   /* THETA, mptrac.h:2124 */
+
+void orc_module_meteo(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm) {
+  const int32_t *qi = ctl->qnt_meteo;
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    const double tm = atm->time[ip], p = atm->p[ip], lon = atm->lon[ip], lat = atm->lat[ip];
+    cell_t c = CELL_ZERO;
+    const double t = time3(met0, met0->t, met1, met1->t, tm, p, lon, lat, &c, 1);
+    const double u = time3(met0, met0->u, met1, met1->u, tm, p, lon, lat, &c, 0);
+    const double v = time3(met0, met0->v, met1, met1->v, tm, p, lon, lat, &c, 0);
+    const double w = time3(met0, met0->w, met1, met1->w, tm, p, lon, lat, &c, 0);
+    const double ps = time2(met0, met0->ps, met1, met1->ps, tm, lon, lat, &c, 0);
+    const double pbl = time2(met0, met0->pbl, met1, met1->pbl, tm, lon, lat, &c, 0);
+#define SETQ(slot, val) do { if (qi[slot] >= 0) atm->q[(size_t)qi[slot] * (size_t)atm->q_stride + (size_t)ip] = (val); } while (0)
+    SETQ(0, ps);
+    SETQ(1, pbl);
+    SETQ(2, p);
+    SETQ(3, t);
+    SETQ(4, 100. * p / (C_RA * t));                       /* RHO, mptrac.h:1961 */
+    SETQ(5, u);
+    SETQ(6, v);
+    SETQ(7, w);
+    SETQ(8, sqrt(u * u + v * v));
+    SETQ(9, -1e3 * C_H0 / p * w);
+    SETQ(10, theta_of(p, t));
+    SETQ(11, 6.112 * exp(17.62 * (t - C_T0) / (243.12 + t - C_T0)));   /* PSAT, mptrac.h:1808 */
+    SETQ(12, 6.112 * exp(22.46 * (t - C_T0) / (272.62 + t - C_T0)));   /* PSICE, mptrac.h:1832 */
+    SETQ(13, (p / ps <= 0.3 ? 1. : sin(M_PI / 2. * (1. - p / ps) / (1. - 0.3))) * theta_of(p, t));   /* ZETA, mptrac.h:2293 */
+#undef SETQ
+  }
+}
+
 void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_met_t *met0,
                       const orc_met_t *met1, orc_atm_t *atm, double t, uint64_t *ctr) {
   orc_module_timesteps(ctl, met0, atm, t);
@@ -600,6 +640,11 @@ void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_me
   if (ctl->diffusion && (ctl->turb_mesox > 0 || ctl->turb_mesoz > 0)) orc_module_diff_meso(ctl, met0, met1, atm, ctr);
   if (ctl->qnt_rp >= 0 && ctl->qnt_rhop >= 0) orc_module_sedi(ctl, met0, met1, atm);
   orc_module_position(met0, met1, atm);
+  if (ctl->met_dt_out > 0 && (ctl->met_dt_out < ctl->dt_mod || fmod(t, ctl->met_dt_out) == 0)) {   /* 7927-7929 */
+    int any = 0;
+    for (int i = 0; i < ORC_METEO_SLOTS; i++) any |= ctl->qnt_meteo[i] >= 0;
+    if (any) orc_module_meteo(ctl, met0, met1, atm);
+  }
   if (ctl->mixing_trop >= 0 && ctl->mixing_strat >= 0 && (ctl->mixing_dt <= 0 || fmod(t, ctl->mixing_dt) == 0))
     orc_module_mixing(ctl, clim, atm, t);
 }

@@ -19,6 +19,8 @@
 #include <stdint.h>
 
 #define ORC_MIX_MAXQ 23
+#define ORC_METEO_SLOTS 16
+/* slots of orc_ctl_t::qnt_meteo: ps, pbl, p, t, rho, u, v, w, vh, vz, theta, psat, psice, zeta_d */
 
 /* same field order as mpb_ctl_t so one ctypes structure serves both (the oracle defines its own type
  * on purpose: it must not depend on product headers) */
@@ -34,6 +36,8 @@ typedef struct {
   double turb_mesox, turb_mesoz, turb_pbl_trans;
   double mixing_dt, mixing_trop, mixing_strat;
   double mixing_lon0, mixing_lon1, mixing_lat0, mixing_lat1, mixing_z0, mixing_z1;
+  double met_dt_out;
+  int32_t qnt_meteo[ORC_METEO_SLOTS];   /* quantity index or -1 */
 } orc_ctl_t;
 
 /* one met time level, dense: 3-D [nx][ny][np] (z fastest), 2-D [nx][ny] */
@@ -70,6 +74,7 @@ void orc_module_diff_meso(const orc_ctl_t *ctl, const orc_met_t *met0, const orc
                           orc_atm_t *atm, uint64_t *ctr);
 void orc_module_sedi(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
 void orc_module_sort(const orc_ctl_t *ctl, const orc_met_t *met0, orc_atm_t *atm);
+void orc_module_meteo(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
 void orc_module_mixing(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm, double t);
 void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_met_t *met0,
                       const orc_met_t *met1, orc_atm_t *atm, double t, uint64_t *ctr);

@@ -25,12 +25,14 @@ _INT_FIELDS = ("direction", "met_coord_type", "advect", "advect_vert_coord", "rn
 _DBL_FIELDS = ("t_start", "t_stop", "dt_mod", "dt_met", "met_utm_ref_lat", "sort_dt",
                "turb_dx_pbl", "turb_dx_trop", "turb_dx_strat", "turb_dz_pbl", "turb_dz_trop", "turb_dz_strat",
                "turb_mesox", "turb_mesoz", "turb_pbl_trans", "mixing_dt", "mixing_trop", "mixing_strat",
-               "mixing_lon0", "mixing_lon1", "mixing_lat0", "mixing_lat1", "mixing_z0", "mixing_z1")
+               "mixing_lon0", "mixing_lon1", "mixing_lat0", "mixing_lat1", "mixing_z0", "mixing_z1", "met_dt_out")
+METEO_QNT = ("ps", "pbl", "p", "t", "rho", "u", "v", "w", "vh", "vz", "theta", "psat", "psice", "zeta_d")
+METEO_SLOTS = 16
 
 
 class OrcCtl(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in _INT_FIELDS] + [("mix_qnt", C.c_int32 * MIX_MAXQ), ("_pad", C.c_int32)]
-                + [(n, C.c_double) for n in _DBL_FIELDS])
+                + [(n, C.c_double) for n in _DBL_FIELDS] + [("qnt_meteo", C.c_int32 * METEO_SLOTS)])
 
 
 class OrcMet(C.Structure):
@@ -60,6 +62,12 @@ def ctl_struct(ctl) -> OrcCtl:
     s.n_mix_qnt = len(mq)
     for i, v in enumerate(mq):
         s.mix_qnt[i] = int(v)
+    try:
+        qm = dict(get("qnt_meteo"))
+    except (KeyError, AttributeError):
+        qm = {}
+    for i in range(METEO_SLOTS):
+        s.qnt_meteo[i] = int(qm.get(METEO_QNT[i], -1)) if i < len(METEO_QNT) else -1
     return s
 
 
@@ -139,12 +147,13 @@ class Oracle:
         L.orc_module_diff_meso.argtypes = [P(OrcCtl), P(OrcMet), P(OrcMet), P(OrcAtm), P(C.c_uint64)]
         L.orc_module_sedi.argtypes = [P(OrcCtl), P(OrcMet), P(OrcMet), P(OrcAtm)]
         L.orc_module_sort.argtypes = [P(OrcCtl), P(OrcMet), P(OrcAtm)]
+        L.orc_module_meteo.argtypes = [P(OrcCtl), P(OrcMet), P(OrcMet), P(OrcAtm)]
         L.orc_module_mixing.argtypes = [P(OrcCtl), P(OrcClim), P(OrcAtm), C.c_double]
         L.orc_sort_keys.argtypes = [P(OrcMet), P(OrcAtm), C.c_void_p]
         L.orc_intpol_met_time_3d.argtypes = [P(OrcMet), P(OrcMet), C.c_void_p, C.c_void_p] + [C.c_double] * 4 + [P(C.c_double)]
         L.orc_grid_bin.argtypes = [P(OrcAtm), C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_double] * 8 + [C.c_void_p] * 3
         for f in ("orc_module_rng", "orc_run_timestep", "orc_module_timesteps", "orc_module_position", "orc_module_advect",
-                  "orc_module_diff_turb", "orc_module_diff_meso", "orc_module_sedi", "orc_module_sort",
+                  "orc_module_diff_turb", "orc_module_diff_meso", "orc_module_sedi", "orc_module_sort", "orc_module_meteo",
                   "orc_module_mixing", "orc_sort_keys", "orc_intpol_met_time_3d", "orc_grid_bin"):
             getattr(L, f).restype = None
         self.L = L
@@ -199,6 +208,8 @@ class Oracle:
             L.orc_module_sort(C.byref(c), C.byref(m0), C.byref(a))
         elif what == "mixing":
             L.orc_module_mixing(C.byref(c), C.byref(cl), C.byref(a), t)
+        elif what == "meteo":
+            L.orc_module_meteo(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a))
         else:
             raise ValueError(what)
         self.ctr = ctr.value
@@ -224,7 +235,7 @@ class Oracle:
 
 
 _WHAT = {"timestep": 0, "timesteps": 1, "position": 2, "advect": 3, "diff_turb": 4, "diff_meso": 5, "sedi": 6,
-         "sort": 7, "mixing": 8}
+         "sort": 7, "mixing": 8, "meteo": 9}
 
 
 def reference_available() -> bool:
@@ -257,9 +268,10 @@ class Reference:
         return dict(zip(("EX", "EY", "EP", "NP", "NQ"), (x.value for x in v)))
 
     def read_ctl(self, qnt_names=(), overrides=""):
-        out = (C.c_int * 5)()
+        out = (C.c_int * 19)()
         nq = self.L.ref_read_ctl(",".join(qnt_names).encode(), overrides.encode(), out)
-        self.qnt = dict(zip(("rp", "rhop", "m", "vmr", "ens"), list(out)))
+        self.qnt = dict(zip(("rp", "rhop", "m", "vmr", "ens"), list(out)[:5]))
+        self.qnt_meteo = {n: i for n, i in zip(METEO_QNT, list(out)[5:]) if i >= 0}   # name -> index the reference assigned
         return nq
 
     def clim_tropo(self):

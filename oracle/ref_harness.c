@@ -33,7 +33,8 @@ static void ensure_alloc(void) {
 }
 
 /* Reference defaults + quantity names (comma separated) + "KEY VALUE" overrides (space separated).
- * Returns the quantity index the reference assigned to `rp`, `rhop`, `m`, `vmr`, `ens` through out[5]. */
+ * Returns the quantity index the reference assigned to `rp`, `rhop`, `m`, `vmr`, `ens` and the 14 module_meteo
+ * quantities of the path through out[19]. */
 int ref_read_ctl(const char *qnt_names, const char *overrides, int *out) {
   ensure_alloc();
   static char buf[8192];
@@ -74,6 +75,11 @@ int ref_read_ctl(const char *qnt_names, const char *overrides, int *out) {
   if (out) {
     out[0] = h_ctl->qnt_rp; out[1] = h_ctl->qnt_rhop; out[2] = h_ctl->qnt_m; out[3] = h_ctl->qnt_vmr;
     out[4] = h_ctl->qnt_ens;
+    /* module_meteo quantities in the slot order of orc_ctl_t::qnt_meteo */
+    const int mq[14] = {h_ctl->qnt_ps, h_ctl->qnt_pbl, h_ctl->qnt_p, h_ctl->qnt_t, h_ctl->qnt_rho, h_ctl->qnt_u, h_ctl->qnt_v,
+                        h_ctl->qnt_w, h_ctl->qnt_vh, h_ctl->qnt_vz, h_ctl->qnt_theta, h_ctl->qnt_psat, h_ctl->qnt_psice,
+                        h_ctl->qnt_zeta_d};
+    for (int i = 0; i < 14; i++) out[5 + i] = mq[i];
   }
   return h_ctl->nq;
 }
@@ -131,7 +137,7 @@ static void apply_ctl(const orc_ctl_t *c) {
   h_ctl->mixing_dt = c->mixing_dt; h_ctl->mixing_trop = c->mixing_trop; h_ctl->mixing_strat = c->mixing_strat;
   h_ctl->mixing_lon0 = c->mixing_lon0; h_ctl->mixing_lon1 = c->mixing_lon1; h_ctl->mixing_lat0 = c->mixing_lat0;
   h_ctl->mixing_lat1 = c->mixing_lat1; h_ctl->mixing_z0 = c->mixing_z0; h_ctl->mixing_z1 = c->mixing_z1;
-  h_ctl->met_dt_out = 0;  /* module_meteo is not on the path */
+  h_ctl->met_dt_out = c->met_dt_out;
 }
 
 static void put_atm(const orc_atm_t *a) {
@@ -156,7 +162,7 @@ static void get_atm(orc_atm_t *a) {
 }
 
 /* what: 0 mptrac_run_timestep, 1 timesteps, 2 position, 3 advect, 4 diff_turb, 5 diff_meso, 6 sedi,
- *       7 sort, 8 mixing.  Met must have been set with ref_set_met, ctl with ref_read_ctl. */
+ *       7 sort, 8 mixing, 9 meteo.  Met must have been set with ref_set_met, ctl with ref_read_ctl. */
 int ref_run(const orc_ctl_t *ctl, orc_atm_t *atm, double t, int what, int nsteps, uint64_t *ctr) {
   ensure_alloc();
   apply_ctl(ctl);
@@ -176,6 +182,7 @@ int ref_run(const orc_ctl_t *ctl, orc_atm_t *atm, double t, int what, int nsteps
     case 6: module_sedi(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     case 7: module_sort(h_ctl, h_met0, h_atm); break;
     case 8: module_mixing(h_ctl, h_clim, h_atm, t); break;
+    case 9: module_meteo(h_ctl, h_cache, h_clim, h_met0, h_met1, h_atm); break;
     default: return 1;
   }
   *ctr = rng_ctr;

@@ -140,6 +140,7 @@ def gen_dt_test(ref):
     tabs = sorted(glob.glob(str(REF / "tests/dt_test/data.ref/atm_pl_*.tab")))
     assert len(tabs) == 7
     shipped = np.stack([read_tab(f)[:, :4] for f in tabs])
+    shipped_q = np.stack([read_tab(f)[:, 4:8] for f in tabs])     # the quantities t, u, v, w module_meteo wrote
     for s in range(7):
         check_ascii(Path(tabs[s]).name, full[s], shipped[s], n)
 
@@ -154,7 +155,8 @@ def gen_dt_test(ref):
     sub = Parcels(tm[:k], p[:k], lon[:k], lat[:k], np.zeros((4, k)))
     # random numbers are addressed by parcel index, so a prefix of the parcels sees the same numbers as long as
     # the counter advances as if all n were present: emulate that by stepping the counter by hand
-    res = []
+    res, res_q = [], []
+    cm = Ctl(**{**ctl.__dict__, "met_dt_out": 0.1, "qnt_meteo": ref.qnt_meteo})
     ref.ctr = 0
     for s in range(7):
         base = ref.ctr
@@ -171,13 +173,16 @@ def gen_dt_test(ref):
         ref.run("diff_meso", c, a)
         ref.ctr = base + 2 * (3 * n + 1)
         ref.run("position", c, a)
+        ref.run("meteo", cm, a)          # t, u, v, w at the new positions (module_meteo, every step: MET_DT_OUT 0.1)
         res.append(snapshots(a))
+        res_q.append(a.q.copy())
     res = np.stack(res)
     assert np.array_equal(res, full[:, :, :k]), "cropped / prefix run differs from the full reference run"
     tt, tl, tr = ref.clim_tropo()
     np.savez_compressed(OUT / "dt_test.npz", **met_arrays("m0", c0), **met_arrays("m1", c1),
                         time=tm[:k], p=p[:k], lon=lon[:k], lat=lat[:k], np_total=np.int64(n), t_start=t0,
                         ref_binary=res, ref_shipped_text=shipped[:, :k, :],
+                        ref_binary_q=np.stack(res_q), ref_shipped_q=shipped_q[:, :k, :],
                         tropo_time=tt, tropo_lat=tl, tropo=tr)
     print(f"  dt_test.npz: grid {c0.u.shape}, {k} of {n} parcels, 7 steps, bit-identical to the full run")
 
@@ -192,6 +197,7 @@ def gen_coord_test(ref):
     tabs = sorted(glob.glob(str(REF / "tests/coord_test/data.ref/atm_2025_05_01_*.tab")))
     assert len(tabs) == 13
     shipped = np.stack([read_tab(f)[:, :4] for f in tabs])
+    shipped_q = np.stack([read_tab(f)[:, 4:8] for f in tabs])     # the quantities t, u, v, w module_meteo wrote
     # the t0 snapshot is the initial state (written after the dt = 0 step); read it through the reference reader
     tm, p, lon, lat = ref_read_atm(ref, REF / "tests/coord_test/data.ref/atm_2025_05_01_00_00_00.tab")
     n = tm.size
@@ -258,7 +264,7 @@ def gen_synth(ref):
 
 if __name__ == "__main__":
     ref = Reference()
-    gen_sedi(ref)
-    gen_dt_test(ref)
-    gen_coord_test(ref)
-    gen_synth(ref)
+    only = set(sys.argv[1:])
+    for name, fn in (("sedi", gen_sedi), ("dt_test", gen_dt_test), ("coord_test", gen_coord_test), ("synth", gen_synth)):
+        if not only or name in only:
+            fn(ref)

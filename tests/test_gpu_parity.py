@@ -159,6 +159,33 @@ def test_single_modules_vs_oracle(oracle, module):
     assert abserr(uv, ref.uvwp) < 1e-5
 
 
+@pytest.mark.parametrize("lat_desc", [False, True])
+def test_module_meteo_vs_oracle(oracle, lat_desc):
+    """module_meteo on the device (all 14 quantities that derive from the resident fields) at scattered parcel times;
+    1e-13 relative: the device contracts FMAs and its pow / exp / sin differ from glibc's in the last bits"""
+    from mptrac_b200 import Ctl
+    from mptrac_b200.host import METEO_QNT
+    from oracle.oracle import Parcels
+    m0, m1, tm, p, lon, lat, clim = _case(lat_desc=lat_desc)
+    n = tm.size
+    tm = tm + np.random.default_rng(1).uniform(0, 20000, n)
+    qm = {name: i for i, name in enumerate(METEO_QNT)}
+    ctl = Ctl(nq=len(qm), advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, met_dt_out=0.1, qnt_meteo=qm)
+    q0 = np.zeros((len(qm), n))
+    with _engine(n, len(qm)) as eng:
+        _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat, q0)
+        eng.module_meteo()
+        out = eng.get_atm()
+    ref = Parcels(tm, p, lon, lat, q0)
+    oracle.run("meteo", ctl, clim, m0, m1, ref)
+    for name, i in qm.items():
+        signed = name in ("u", "v", "w", "vz")      # these pass through zero: error relative to the field's scale
+        e = abserr(out["q"][i], ref.q[i]) / np.max(np.abs(ref.q[i])) if signed else relerr(out["q"][i], ref.q[i])
+        _report(f"module_meteo[{name},latdesc={int(lat_desc)}]", rel=e)
+        assert e < 1e-12, name
+    assert np.array_equal(out["lon"], lon) and np.array_equal(out["p"], p)
+
+
 def test_rng_stream(oracle):
     """Squares counters are integers: uniforms must be bit-exact; Box-Muller normals agree to float-trig accuracy."""
     with _engine(10) as eng:
@@ -188,9 +215,12 @@ def test_golden_dt_test():
     z = _golden("dt_test.npz")
     m0, m1, clim = met_from_npz(z, "m0"), met_from_npz(z, "m1"), clim_from_npz(z)
     t0, n_total, k = float(z["t_start"]), int(z["np_total"]), z["time"].size
-    ctl = Ctl(nq=0, advect=2, diffusion=1, dt_mod=10.0, dt_met=86400.0, t_start=t0, t_stop=t0 + 60.0)
-    with _engine(k) as eng:
-        _setup(eng, ctl, clim, m0, m1, z["time"], z["p"], z["lon"], z["lat"])
+    # all 8 columns of the reference's goldens: positions, and the quantities t, u, v, w that module_meteo writes after
+    # every step (the test's control file leaves MET_DT_OUT at its default 0.1)
+    ctl = Ctl(nq=4, advect=2, diffusion=1, dt_mod=10.0, dt_met=86400.0, t_start=t0, t_stop=t0 + 60.0, met_dt_out=0.1,
+              qnt_meteo=dict(t=0, u=1, v=2, w=3))
+    with _engine(k, 4) as eng:
+        _setup(eng, ctl, clim, m0, m1, z["time"], z["p"], z["lon"], z["lat"], np.zeros((4, k)))
         eng.set_shard(0, n_total)   # the fixture holds the first k of n_total parcels: counters advance as for all
         for s in range(7):
             eng.run_timestep(t0 + 10.0 * s)
@@ -202,6 +232,12 @@ def test_golden_dt_test():
             # the reference's own shipped text goldens (%g: 6 significant digits)
             zkm = 7.0 * np.log(1013.25 / out["p"])
             assert relerr(zkm, txt[:, 1]) < 1e-5 and relerr(out["lon"], txt[:, 2]) < 1e-5 and relerr(out["lat"], txt[:, 3]) < 1e-5
+            rq = z["ref_binary_q"][s]
+            eq = float(np.max(np.abs(out["q"] - rq) / np.max(np.abs(rq), axis=1, keepdims=True)))
+            _report(f"golden_dt_test_step{s}_quantities", q_rel_to_scale=eq)
+            assert eq < 1e-7      # the positions they are evaluated at differ by ~1e-10 deg (diffusion: sinf / cosf)
+            tq = z["ref_shipped_q"][s]
+            assert np.all(np.abs(out["q"].T - tq) <= 1e-5 * np.maximum(np.abs(tq), 1e-3 * np.max(np.abs(tq), axis=0)))
 
 
 def test_golden_coord_test():

@@ -44,13 +44,18 @@ def test_dt_test_goldens(oracle):
     z = _golden("dt_test.npz")
     m0, m1, clim = met_from_npz(z, "m0"), met_from_npz(z, "m1"), clim_from_npz(z)
     t0, n_total = float(z["t_start"]), int(z["np_total"])
-    ctl = Ctl(nq=0, advect=2, diffusion=1, dt_mod=10.0, dt_met=86400.0, t_start=t0, t_stop=t0 + 60.0)
-    a = Parcels(z["time"], z["p"], z["lon"], z["lat"])
+    # quantities t, u, v, w: module_meteo after every step (the test's control file leaves MET_DT_OUT at 0.1)
+    ctl = Ctl(nq=4, advect=2, diffusion=1, dt_mod=10.0, dt_met=86400.0, t_start=t0, t_stop=t0 + 60.0, met_dt_out=0.1,
+              qnt_meteo=dict(t=0, u=1, v=2, w=3))
+    a = Parcels(z["time"], z["p"], z["lon"], z["lat"], np.zeros((4, z["time"].size)))
     oracle.ctr = 0
     for s in range(7):
         _prefix_steps(oracle, ctl, clim, m0, m1, a, t0 + 10.0 * s, n_total)
+        oracle.run("meteo", ctl, clim, m0, m1, a)
         rb, txt = z["ref_binary"][s], z["ref_shipped_text"][s]
         assert np.array_equal(np.stack([a.time, a.p, a.lon, a.lat]), rb), f"step {s}"
+        assert np.array_equal(a.q, z["ref_binary_q"][s]), f"step {s}: quantities"
+        assert relerr(a.q.T, z["ref_shipped_q"][s]) < 1e-5            # columns 5-8 of the shipped goldens
         zkm = 7.0 * np.log(1013.25 / a.p)
         assert abserr(a.time, txt[:, 0]) < 0.006
         assert relerr(zkm, txt[:, 1]) < 1e-5 and relerr(a.lon, txt[:, 2]) < 1e-5 and relerr(a.lat, txt[:, 3]) < 1e-5

@@ -119,3 +119,48 @@ def test_clim_tropo_table_is_what_the_goldens_hold(reference):
     t, la, tr = reference.clim_tropo()
     z = np.load(GOLDEN / "dt_test.npz")
     assert np.array_equal(tr, z["tropo"]) and np.array_equal(t, z["tropo_time"]) and np.array_equal(la, z["tropo_lat"])
+
+
+@pytest.mark.parametrize("lat_desc", [False, True])
+def test_module_meteo_bit_exact(oracle, reference, lat_desc):
+    """module_meteo restricted to the quantities of the path (src/mptrac.c:5062-5165), all 14 of them, parcels at
+    scattered times (check_dt = 0: every parcel is visited)"""
+    from mptrac_b200 import Ctl, synth
+    from mptrac_b200.host import METEO_QNT
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0, lat_descending=lat_desc)
+    n = 4000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.05, zmax=45.0, seed=5)
+    tm = tm + np.random.default_rng(1).uniform(0, 20000, n)
+    nq = reference.read_ctl(list(METEO_QNT), "")
+    assert nq == len(METEO_QNT) and set(reference.qnt_meteo) == set(METEO_QNT)
+    reference.set_met(m0, m1)
+    ctl = Ctl(nq=nq, advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, met_dt_out=0.1, qnt_meteo=reference.qnt_meteo)
+    a = Parcels(tm, p, lon, lat, np.zeros((nq, n)))
+    b = a.copy()
+    reference.run("meteo", ctl, a)
+    oracle.run("meteo", ctl, synth.make_clim_tropo(), m0, m1, b)
+    for name, k in reference.qnt_meteo.items():
+        assert np.array_equal(a.q[k], b.q[k]), name
+    assert np.all(a.q[reference.qnt_meteo["t"]] > 150)
+
+
+def test_run_timestep_with_meteo_bit_exact(oracle, reference):
+    """the dispatcher with MET_DT_OUT on: module_meteo after the final position check, before mixing (src/mptrac.c:7927)"""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    n = 3000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.05, zmax=45.0, seed=7)
+    nq = reference.read_ctl(["t", "u", "v", "w", "theta"], "")
+    reference.set_met(m0, m1)
+    ctl = Ctl(nq=nq, advect=2, diffusion=1, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, met_dt_out=0.1,
+              qnt_meteo=reference.qnt_meteo)
+    a = Parcels(tm, p, lon, lat, np.zeros((nq, n)))
+    b = a.copy()
+    reference.ctr = oracle.ctr = 0
+    reference.run("timestep", ctl, a, t=0.0, nsteps=4)
+    oracle.run("timestep", ctl, reference.clim_tropo(), m0, m1, b, t=0.0, nsteps=4)
+    for k in ("lon", "lat", "p"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.array_equal(a.q, b.q) and np.all(a.q[0] > 150)

@@ -24,7 +24,7 @@ def _need():
             pytest.skip(f"{f} not present (built only where /root/reference exists)")
 
 
-def _run_trac(tmp_path, ctl_text, atm_in, extra, preload=True):
+def _run_trac(tmp_path, ctl_text, atm_in, extra, preload=True, env_extra=None):
     d = tmp_path / "data"
     d.mkdir()
     (d / "trac.ctl").write_text(ctl_text)
@@ -33,6 +33,7 @@ def _run_trac(tmp_path, ctl_text, atm_in, extra, preload=True):
     env = dict(os.environ, OMP_NUM_THREADS="4", LANG="C", LC_ALL="C", MPTRAC_B200_VERBOSE="1")
     if preload:
         env["LD_PRELOAD"] = str(SHIM)
+    env.update(env_extra or {})
     r = subprocess.run([str(TRAC), str(tmp_path / "dirlist"), "trac.ctl", "atm_in.tab", *extra], env=env, cwd=tmp_path,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
@@ -57,21 +58,23 @@ T_STOP = 360547260
 """
 
 
-@pytest.mark.parametrize("mode", ["hybrid", "device_only"])
+@pytest.mark.parametrize("mode", ["as_shipped", "hybrid", "device_only"])
 def test_trac_dt_test_through_the_shim(tmp_path, mode):
-    """hybrid: the control file of tests/dt_test as shipped (module_meteo, which is not on the device path, runs through
-    the reference's CPU code between device steps) -> all 8 columns of the shipped goldens.
-    device_only: MET_DT_OUT 0 -> every step is one fused launch; columns 1-4."""
+    """as_shipped: the control file of tests/dt_test unchanged -- module_meteo (quantities t, u, v, w) runs on the
+    device after every step -> all 8 columns of the shipped goldens without any per-step host round trip.
+    hybrid: the same with module_meteo forced onto the reference's CPU code between device steps (the path every
+    module that is not on the device takes).  device_only: MET_DT_OUT 0 -> every step is one fused launch; columns 1-4."""
     _need()
     extra = ["ATM_BASENAME", "atm_pl"] + (["MET_DT_OUT", "0"] if mode == "device_only" else [])
-    d, out = _run_trac(tmp_path, DT_CTL.format(met=DATA), DATA / "dt_test.ref" / "atm_split.tab", extra)
+    d, out = _run_trac(tmp_path, DT_CTL.format(met=DATA), DATA / "dt_test.ref" / "atm_split.tab", extra,
+                       env_extra={"MPTRAC_B200_HOST_METEO": "1"} if mode == "hybrid" else None)
     assert "mptrac_b200:" in out and "kernel launches" in out, "the shim was not in the call path"
     gold = sorted((DATA / "dt_test.ref").glob("atm_pl_*.tab"))
     assert len(gold) == 7
     for g in gold:
         a, b = _tab(d / g.name), _tab(g)
         assert a.shape == b.shape
-        ncol = 8 if mode == "hybrid" else 4
+        ncol = 4 if mode == "device_only" else 8
         assert abserr(a[:, 0], b[:, 0]) < 0.006
         for c in range(1, ncol):
             # %g text: 6 significant digits; a last-digit flip is 1e-5 relative at worst
