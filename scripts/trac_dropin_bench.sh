@@ -1,0 +1,66 @@
+#!/bin/bash
+# The reference's UNMODIFIED `trac` driver at BASELINE C2 scale (~1 M parcels, 360x181x61 synthetic met from the
+# reference's own `wind` tool, RK4, 72 steps of 300 s), once as the reference runs it (OpenMP on the host cores) and once
+# with libmptrac_b200_shim.so pre-loaded; prints both timer summaries and the largest difference of the final parcel
+# positions.  Runs on the GPU box (needs oracle/_ref).   usage: scripts/trac_dropin_bench.sh [meteo]
+set -eu
+cd "$(dirname "$0")/.."
+R=$PWD/oracle/_ref/bin; SHIM=$PWD/mptrac_b200/_lib/libmptrac_b200_shim.so
+W=$(mktemp -d); mkdir -p $W/data gpurun_out
+QNT="NQ = 0"; MDO="MET_DT_OUT = 0"
+if [ "${1:-}" = meteo ]; then QNT=$'NQ = 4\nQNT_NAME[0] = t\nQNT_NAME[1] = u\nQNT_NAME[2] = v\nQNT_NAME[3] = w'; MDO=""; fi
+cat > $W/data/trac.ctl <<CTL
+$QNT
+METBASE = $W/data/wind
+DT_MET = 21600
+DT_MOD = 300
+T_STOP = 21600
+ADVECT = 4
+DIFFUSION = 0
+$MDO
+SORT_DT = 3600
+ATM_DT_OUT = 21600
+ATM_TYPE = 1
+ATM_TYPE_OUT = 1
+MET_CAPE = 0
+MET_PBL = 0
+CTL
+echo $W/data > $W/dirlist
+export LANG=C LC_ALL=C OMP_NUM_THREADS=$(nproc)
+for t in 0 21600; do
+  $R/wind $W/data/trac.ctl $W/data/wind WIND_T0 $t WIND_NX 360 WIND_NY 181 WIND_NZ 61 WIND_Z0 0 WIND_Z1 60 WIND_ALPHA 45 \
+     WIND_U0 38.59 WIND_U1 60 WIND_W0 0.01 WIND_TEMP0 280 WIND_TEMP1 220 > $W/wind_$t.log 2>&1
+done
+$R/atm_init $W/data/trac.ctl $W/data/atm_init.tab INIT_T0 0 INIT_T1 0 INIT_LON0 -180 INIT_LON1 179 INIT_DLON 1 \
+   INIT_LAT0 -89.5 INIT_LAT1 89.5 INIT_DLAT 1 INIT_Z0 2 INIT_Z1 30 INIT_DZ 2 > $W/init.log 2>&1
+grep -i "number of\|np =" $W/init.log | tail -2 || true
+run() {  # name, binary, preload
+  mkdir -p $W/$1; cp $W/data/trac.ctl $W/data/atm_init.tab $W/$1/; ln -sf $W/data/wind_*.nc $W/$1/ 2>/dev/null || true
+  sed -i "s|METBASE = .*|METBASE = $W/data/wind|" $W/$1/trac.ctl
+  echo $W/$1 > $W/dirlist_$1
+  local t0=$(date +%s.%N)
+  ( if [ -n "$3" ]; then export LD_PRELOAD=$3 MPTRAC_B200_VERBOSE=1; fi; $2 $W/dirlist_$1 trac.ctl atm_init.tab ATM_BASENAME atm > $W/$1.log 2>&1 ) || { echo "$1 FAILED"; tail -5 $W/$1.log; }
+  local t1=$(date +%s.%N)
+  echo "== $1: wall $(python -c "print(f'{$t1 - $t0:.2f}')") s"
+  grep -E "SIZE_NP|TIMER_GROUP_PHYSICS|TIMER_GROUP_INPUT|TIMER_GROUP_MEMORY|TIMER_MODULE_ADVECT|TIMER_MODULE_B200_STEP|TIMER_MODULE_METEO|TIMER_MODULE_SORT|TIMER_TOTAL|kernel launches" $W/$1.log || tail -5 $W/$1.log
+}
+run cpu $R/trac ""
+run gpu $R/trac_shared $SHIM
+python - <<PY
+import numpy as np, glob
+def rd(f):
+    a = np.fromfile(f, dtype=np.uint8)
+    # ATM_TYPE_OUT 1: int version, int np, then time, p, lon, lat (+ q) as doubles (src/mptrac.c:12872-12918)
+    hdr = np.frombuffer(a[:8].tobytes(), dtype=np.int32); n = int(hdr[1])
+    d = np.frombuffer(a[8:8 + 32 * n].tobytes(), dtype=np.float64).reshape(4, n)
+    return n, d
+fc = sorted(glob.glob("$W/cpu/atm_2*.tab"))[-1]; fg = sorted(glob.glob("$W/gpu/atm_2*.tab"))[-1]
+n, c = rd(fc); m, g = rd(fg)
+assert n == m
+# SORT_DT reorders parcels (the reference's sort is not stable: compare as sets, sorted by (lon, lat, p))
+kc, kg = np.lexsort(c[::-1]), np.lexsort(g[::-1])
+c, g = c[:, kc], g[:, kg]
+print(f"parcels {n}: max |dlon| {np.max(np.abs(c[2]-g[2])):.3e} deg, max |dlat| {np.max(np.abs(c[3]-g[3])):.3e} deg, max rel dp {np.max(np.abs(c[1]-g[1])/c[1]):.3e}")
+PY
+cp $W/cpu.log gpurun_out/trac_dropin_cpu.log; cp $W/gpu.log gpurun_out/trac_dropin_gpu.log
+rm -rf $W
