@@ -41,6 +41,9 @@ WORKLOADS = {
                                                               turb_dz_strat=0, qnt_rp=0, qnt_rhop=1, nq=2, sort_dt=3600.0),
                state_bytes=104, met_fields=4,
                desc="10M parcels, 0.5x0.5 deg x 137 levels (721x361x137), RK4 + mesoscale diffusion + sedimentation"),
+    # one GPU's share of BASELINE configs[3] (100 M parcels over 8 GPUs): dense -- 6 parcels per grid cell
+    "c4": dict(np=12_500_000, grid=(360, 181, 60), ctl=dict(advect=4, diffusion=1, sort_dt=3600.0), state_bytes=88, met_fields=3,
+               desc="12.5M parcels per GPU (100M / 8), 1x1 deg x 60 levels, RK4 + turbulent + mesoscale diffusion"),
 }
 DT_MOD = 300.0
 DT_MET = 21600.0
@@ -332,7 +335,7 @@ def run_ours(args):
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[{1 if args.workload == 'c2' else 2}]: {wl['desc']}", "parcels_per_gpu": n,
+        "config": {"workload": f"BASELINE configs[{dict(c2=1, c3=2, c4=3)[args.workload]}]: {wl['desc']}", "parcels_per_gpu": n,
                    "dt_mod_s": DT_MOD, "l2": "flushed between steps (256 MiB memset outside the per-step events)",
                    "parallelism": f"parcels sharded contiguously over {world} GPU(s), no data-path collective"},
         "back_to_back": {"value": units / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / K, "met_rolls_inside": b2b_rolls,
@@ -445,7 +448,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "particle-steps/sec", "value": v, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": n_sample / v * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[{1 if args.workload == 'c2' else 2}]: {wl['desc']}",
+            "config": {"workload": f"BASELINE configs[{dict(c2=1, c3=2, c4=3)[args.workload]}]: {wl['desc']}",
                        "note": "reference CPU arm: host cores only, rank 0 only"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

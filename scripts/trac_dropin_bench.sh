@@ -7,8 +7,9 @@ set -eu
 cd "$(dirname "$0")/.."
 R=$PWD/oracle/_ref/bin; SHIM=$PWD/mptrac_b200/_lib/libmptrac_b200_shim.so
 W=$(mktemp -d); mkdir -p $W/data gpurun_out
-QNT="NQ = 0"; MDO="MET_DT_OUT = 0"
-if [ "${1:-}" = meteo ]; then QNT=$'NQ = 4\nQNT_NAME[0] = t\nQNT_NAME[1] = u\nQNT_NAME[2] = v\nQNT_NAME[3] = w'; MDO=""; fi
+# (quantity idx = parcel index: SORT_DT reorders the parcels, the comparison matches them by index)
+QNT=$'NQ = 1\nQNT_NAME[0] = idx'; MDO="MET_DT_OUT = 0"; NQ=1
+if [ "${1:-}" = meteo ]; then QNT=$'NQ = 5\nQNT_NAME[0] = idx\nQNT_NAME[1] = t\nQNT_NAME[2] = u\nQNT_NAME[3] = v\nQNT_NAME[4] = w'; MDO=""; NQ=5; fi
 cat > $W/data/trac.ctl <<CTL
 $QNT
 METBASE = $W/data/wind
@@ -50,17 +51,16 @@ python - <<PY
 import numpy as np, glob
 def rd(f):
     a = np.fromfile(f, dtype=np.uint8)
-    # ATM_TYPE_OUT 1: int version, int np, then time, p, lon, lat (+ q) as doubles (src/mptrac.c:12872-12918)
+    # ATM_TYPE_OUT 1: int version, int np, then time, p, lon, lat, q[nq] as doubles (src/mptrac.c:12872-12918)
     hdr = np.frombuffer(a[:8].tobytes(), dtype=np.int32); n = int(hdr[1])
-    d = np.frombuffer(a[8:8 + 32 * n].tobytes(), dtype=np.float64).reshape(4, n)
-    return n, d
-fc = sorted(glob.glob("$W/cpu/atm_2*.tab"))[-1]; fg = sorted(glob.glob("$W/gpu/atm_2*.tab"))[-1]
+    d = np.frombuffer(a[8:8 + 8 * (4 + $NQ) * n].tobytes(), dtype=np.float64).reshape(4 + $NQ, n)
+    return n, d[:, np.argsort(d[4])]          # ordered by parcel index
+fc = sorted(glob.glob("$W/cpu/atm_2*.bin"))[-1]; fg = sorted(glob.glob("$W/gpu/atm_2*.bin"))[-1]
 n, c = rd(fc); m, g = rd(fg)
-assert n == m
-# SORT_DT reorders parcels (the reference's sort is not stable: compare as sets, sorted by (lon, lat, p))
-kc, kg = np.lexsort(c[::-1]), np.lexsort(g[::-1])
-c, g = c[:, kc], g[:, kg]
-print(f"parcels {n}: max |dlon| {np.max(np.abs(c[2]-g[2])):.3e} deg, max |dlat| {np.max(np.abs(c[3]-g[3])):.3e} deg, max rel dp {np.max(np.abs(c[1]-g[1])/c[1]):.3e}")
+assert n == m and np.array_equal(c[4], g[4])
+dlon = (c[2] - g[2] + 180.0) % 360.0 - 180.0
+print(f"parcels {n}: max |dlon| cos(lat) {np.max(np.abs(dlon) * np.cos(np.deg2rad(c[3]))):.3e} deg, max |dlat| {np.max(np.abs(c[3]-g[3])):.3e} deg, "
+      f"max rel dp {np.max(np.abs(c[1]-g[1])/c[1]):.3e}" + (f", quantities max rel-to-scale {np.max(np.abs(c[5:]-g[5:]) / np.max(np.abs(c[5:]), axis=1, keepdims=True)):.3e}" if $NQ > 1 else ""))
 PY
 cp $W/cpu.log gpurun_out/trac_dropin_cpu.log; cp $W/gpu.log gpurun_out/trac_dropin_gpu.log
 rm -rf $W
