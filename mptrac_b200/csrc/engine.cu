@@ -87,15 +87,12 @@ constexpr unsigned PHYS_TURB = 1, PHYS_MESO = 2, PHYS_SEDI = 4;
 #ifndef MPB_CUBE_F64
 #define MPB_CUBE_F64 0
 #endif
-#ifndef MPB_PERSIST      // 1: grid = SMs x resident blocks, threads loop over parcels; 0: one parcel per thread
-#define MPB_PERSIST 1
+#ifndef MPB_PERSIST      // 1: grid = SMs x resident blocks, threads loop over parcels; 0: one block per kBlock parcels
+#define MPB_PERSIST 1    // (measured: 126 us vs 135 us)
 #endif
 #ifndef MPB_CONTIG       // persistent form: 1 = each block walks its own contiguous parcel range, 0 = grid-stride.
 #define MPB_CONTIG 0     // Measured on B200 (C2, sorted): 131 us contiguous vs 121 us grid-stride -- with the grid-stride walk all
 #endif                   // SMs sweep the same window of the sorted parcels together and share its nodes through L2
-#ifndef MPB_PREFETCH     // hint the next parcel's met cell into L1 (persistent form only).  Measured on B200 (C2, sorted):
-#define MPB_PREFETCH 0   // 139 us with the hint vs 126 us without -- its index arithmetic costs more than the hits save
-#endif
 constexpr int kBlock = MPB_BLOCK;
 constexpr int kLanes = 4;                       // concurrent chunk pipelines of mpb_run_timestep_host
 constexpr long long kHostChunkMin = 16384;      // parcels per chunk: at least 128 KiB per array ...
@@ -108,8 +105,8 @@ constexpr long long kHostChunkMax = 1 << 20;    // ... at most 8 MiB
 #endif
 
 // One parcel, one model step: timesteps -> position -> advect -> diff_turb -> diff_meso -> sedi -> position, in registers.
-template <int ADVECT, unsigned PHYS, class Hook>
-__device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Parcel a, Hook between) {
+template <int ADVECT, unsigned PHYS>
+__device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Parcel a) {
   double dt;
   if (A.modules & MOD_TIMESTEPS) {
     dt = parcel_dt(A.met, A.ctl, a);
@@ -118,7 +115,6 @@ __device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Par
     dt = A.dt[ip];
   }
   if (dt == 0) {  // PARTICLE_LOOP(check_dt = 1), src/mptrac.h:1754-1759
-    between();
     if (A.in_time) { A.time[ip] = a.time; A.lon[ip] = a.lon; A.lat[ip] = a.lat; A.p[ip] = a.p; }   // keep the device mirror
     return;
   }
@@ -132,12 +128,11 @@ __device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Par
   if (ADVECT > 0) {
     WindCube wc;
     cube_reset(wc);
-    advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, wc, between);
+    advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, wc);
   }
 #else
-  if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, cube, between);
+  if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, cube);
 #endif
-  if (ADVECT == 0) between();
   if (PHYS & PHYS_TURB) diffuse_turbulent(A.met, A.clim, A.ctl, dt, ig, a, cube.ax);
   if (PHYS & PHYS_MESO) {
     float *s = A.uvwp + 3 * ip;
@@ -160,20 +155,30 @@ __device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Par
   }
 }
 
-__device__ __forceinline__ Parcel load_parcel(const StepArgs &A, long long ip) {
-  Parcel a;
-  if (A.in_time) { a.time = A.in_time[ip]; a.lon = A.in_lon[ip]; a.lat = A.in_lat[ip]; a.p = A.in_p[ip]; }
-  else { a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip]; }
-  return a;
+// Asynchronous copy of one parcel's state (time, lon, lat, p) into this thread's shared-memory slots: cp.async
+// (LDGSTS) needs no destination registers, so the load of the NEXT parcel can stay in flight for the whole step of the
+// current one -- with ~100 live fp64 registers per parcel a register prefetch is spilled at once, and the spill waits
+// for the load (r01e profile: 7 % of all stall samples).
+__device__ __forceinline__ void stage_parcel_async(const StepArgs &A, long long ip, double (*slot)[kBlock]) {
+  const double *src[4];
+  if (A.in_time) { src[0] = A.in_time; src[1] = A.in_lon; src[2] = A.in_lat; src[3] = A.in_p; }
+  else { src[0] = A.time; src[1] = A.lon; src[2] = A.lat; src[3] = A.p; }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(&slot[j][threadIdx.x]);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src[j] + ip) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // Persistent form: the grid is sized to what the GPU holds at once (SMs x resident blocks) and every thread walks the
-// parcels ip, ip + stride, ...  While parcel k computes, the state of parcel k+1 is already in flight, the axis tables
-// stay hot in L1 for the whole launch and no block-launch gaps separate the parcels of a thread (the kernel holds ~100
-// registers of fp64 state per parcel, so only ~16 warps are resident per SM and every exposed latency counts).
-// MPB_PREFETCH additionally hints the met cell of parcel k+1 into L1 once the first lookup of k has been issued.
+// parcels ip, ip + stride, ...  While parcel k computes, the state of parcel k+1 is already in flight (double-buffered
+// in shared memory), the axis tables stay hot in L1 for the whole launch and no block-launch gaps separate the parcels
+// of a thread (the kernel holds ~100 registers of fp64 state per parcel, so only ~16 warps are resident per SM and
+// every exposed latency counts).
 template <int ADVECT, unsigned PHYS>
 __global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
+  __shared__ double stage[2][4][kBlock];
 #if MPB_CONTIG
   // every block owns one contiguous range of the (cell-sorted) parcels and walks it kBlock parcels at a time
   const long long per_block = ((A.np + gridDim.x - 1) / gridDim.x + kBlock - 1) / kBlock * kBlock;
@@ -186,18 +191,19 @@ __global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
   const long long end = A.np;
 #endif
   if (ip >= end) return;
-  Parcel nxt = load_parcel(A, ip);
+  int buf = 0;
+  stage_parcel_async(A, ip, stage[0]);
   for (;;) {
-    const Parcel a = nxt;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // a thread only ever reads the slots it filled itself
+    Parcel a;
+    a.time = stage[buf][0][threadIdx.x]; a.lon = stage[buf][1][threadIdx.x];
+    a.lat = stage[buf][2][threadIdx.x]; a.p = stage[buf][3][threadIdx.x];
     const long long cur = ip;
     ip += stride;
     const bool more = ip < end;
-    if (more) nxt = load_parcel(A, ip);
-#if MPB_PREFETCH
-    step_parcel<ADVECT, PHYS>(A, cur, a, [&]() { if (more) prefetch_cube(A.met, nxt.lon, nxt.lat, nxt.p); });
-#else
-    step_parcel<ADVECT, PHYS>(A, cur, a, NoHook());
-#endif
+    buf ^= 1;
+    if (more) stage_parcel_async(A, ip, stage[buf]);
+    step_parcel<ADVECT, PHYS>(A, cur, a);
     if (!more) break;
   }
 }

@@ -465,29 +465,6 @@ MPB_HD void load_cube(const MetView &g, const Stencil &s, Cube &c) {
   c.ix = s.ix; c.iy = s.iy; c.iz = s.iz;
 }
 
-// Hint the 8 corner nodes of the cell a parcel at (lon, lat, p) will look up into L1 (no registers, no waiting); the
-// indices are first guesses only -- a wrong guess costs nothing but the hint.
-MPB_HD void prefetch_cube(const MetView &g, double lon, double lat, double p) {
-#ifdef __CUDA_ARCH__
-  double lon2, lat2;
-  clamp_horizontal(g, lon, lat, lon2, lat2);
-  int ix = (int)((lon2 - g.lon_first) * g.r_lon_d), iy = lat_guess(g, lat2), iz = p_guess(g, p);
-  ix = ix < 0 ? 0 : (ix > g.nx - 2 ? g.nx - 2 : ix);
-  iy = iy < 0 ? 0 : (iy > g.ny - 2 ? g.ny - 2 : iy);
-  iz = iz < 0 ? 0 : (iz > g.nz - 2 ? g.nz - 2 : iz);
-  const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * (size_t)g.nz;
-  const Node *b = g.f + ((size_t)ix * sx + (size_t)iy * sy + (size_t)iz);
-  const Node *q[4] = {b, b + sy, b + sx, b + sx + sy};
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(q[j]));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(q[j] + 1));
-  }
-#else
-  (void)g; (void)lon; (void)lat; (void)p;
-#endif
-}
-
 // make c hold the cell of s
 MPB_HD void fetch_cube(const MetView &g, const Stencil &s, Cube &c) {
   if (c.ix != s.ix || c.iy != s.iy || c.iz != s.iz) load_cube(g, s, c);
@@ -656,12 +633,8 @@ MPB_HD void fix_position(const MetView &g, Parcel &a) {
 // ----------------------------------------------------------------------------------------------
 // module_advect, pressure-level branch (3612-3677)
 // ----------------------------------------------------------------------------------------------
-struct NoHook { MPB_HD void operator()() const {} };
-
-// `between` runs once after the first stage's lookup has been issued: the step kernel uses it to prefetch the met cell
-// of the NEXT parcel of its thread while this parcel's stages compute.
-template <int ORDER, class CubeT, class Hook = NoHook>
-MPB_HD void advect(const MetView &g, double dt, Parcel &a, CubeT &c, Hook between = Hook()) {
+template <int ORDER, class CubeT>
+MPB_HD void advect(const MetView &g, double dt, Parcel &a, CubeT &c) {
   double um = 0, vm = 0, wm = 0;
   double u = 0, v = 0, w = 0;
   double lat_stage = a.lat;
@@ -681,7 +654,6 @@ MPB_HD void advect(const MetView &g, double dt, Parcel &a, CubeT &c, Hook betwee
     lat_stage = y;
     if (i != 2) wt = time_weight(g, a.time + dts);   // stages 1 and 2 are taken at the same time
     wind_at(g, wt, x, y, z, c, u, v, w);
-    if (i == 0) between();
     double k = 1.0;
     if (ORDER == 2) k = (i == 0 ? 0.0 : 1.0);
     else if (ORDER == 4) k = (i == 0 || i == 3 ? 1.0 / 6.0 : 2.0 / 6.0);
@@ -712,6 +684,14 @@ MPB_HD double squares_uniform(uint64_t ctr) {
 // The three normals rs[3*ig], rs[3*ig+1], rs[3*ig+2] of a module_rng(…, 3*np, 1) call whose
 // uniform stream started at counter ctr0.  Normal j is made from the uniform pair (j & ~1, +1):
 // even j takes the cosine, odd j the sine.
+MPB_HD void sin_cos_f(float x, float &s, float &c) {
+#ifdef __CUDA_ARCH__
+  sincosf(x, &s, &c);   // one argument reduction for both; same values as sinf(x), cosf(x)
+#else
+  s = sinf(x); c = cosf(x);
+#endif
+}
+
 MPB_HD void normals3(uint64_t ctr0, uint64_t ig, double &r0, double &r1, double &r2) {
   const uint64_t j0 = 3 * ig;
   const uint64_t pa = j0 & ~1ull;       // pair that holds j0
@@ -720,10 +700,13 @@ MPB_HD void normals3(uint64_t ctr0, uint64_t ig, double &r0, double &r1, double 
   const float fa = (float)(2.0 * kPi * squares_uniform(ctr0 + pa + 1));
   const double rb = sqrt(-2.0 * log(squares_uniform(ctr0 + pb)));
   const float fb = (float)(2.0 * kPi * squares_uniform(ctr0 + pb + 1));
+  float sa, ca, sb, cb;
+  sin_cos_f(fa, sa, ca);
+  sin_cos_f(fb, sb, cb);
   if ((j0 & 1ull) == 0) {
-    r0 = ra * cosf(fa); r1 = ra * sinf(fa); r2 = rb * cosf(fb);
+    r0 = ra * ca; r1 = ra * sa; r2 = rb * cb;
   } else {
-    r0 = ra * sinf(fa); r1 = rb * cosf(fb); r2 = rb * sinf(fb);
+    r0 = ra * sa; r1 = rb * cb; r2 = rb * sb;
   }
 }
 
