@@ -35,8 +35,8 @@ sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
     # name: (parcels per GPU, nlon, nlat, nlev, ctl overrides, algorithmic bytes per parcel-step excluding met, met fields)
-    "c2": dict(np=1_000_000, grid=(360, 181, 60), ctl=dict(advect=4, diffusion=0, sort_dt=3600.0), state_bytes=64, met_fields=3,
-               desc="1M parcels, 1x1 deg x 60 levels (361x181x60), RK4 advection only, SORT_DT 3600 (cell sort every 12 steps, timed)"),
+    "c2": dict(np=1_000_000, grid=(360, 181, 60), ctl=dict(advect=4, diffusion=0, sort_dt=7200.0), state_bytes=64, met_fields=3,
+               desc="1M parcels, 1x1 deg x 60 levels (361x181x60), RK4 advection only, SORT_DT 7200 (cell sort every 24 steps, timed)"),
     "c3": dict(np=10_000_000, grid=(720, 361, 137), ctl=dict(advect=4, diffusion=1, turb_dx_pbl=0, turb_dx_trop=0,
                                                               turb_dz_strat=0, qnt_rp=0, qnt_rhop=1, nq=2, sort_dt=3600.0),
                state_bytes=104, met_fields=4,
@@ -165,6 +165,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = WORKLOADS[args.workload]
+    if os.environ.get("MPB_BENCH_SORT_DT"):      # tuning aid: cell-sort cadence of the workload [s]
+        wl = dict(wl, ctl=dict(wl["ctl"], sort_dt=float(os.environ["MPB_BENCH_SORT_DT"])))
     ctl, m0, m1, (tm, p, lon, lat, q) = build_inputs(wl, rank, world)
     n = wl["np"]
 
