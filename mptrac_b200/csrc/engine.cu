@@ -121,7 +121,7 @@ __device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Par
 
   const unsigned long long ig = (unsigned long long)(A.ig0 + ip);
 
-  Cube cube;   // the met cell this parcel sits in, shared by every lookup of the step
+  CubeT<!(PHYS & PHYS_MESO)> cube;   // the met cell this parcel sits in, shared by every lookup of the step
   cube_reset(cube);
   if (A.modules & MOD_POS_PRE) fix_position(A.met, a);
 #if MPB_CUBE_F64
@@ -133,8 +133,8 @@ __device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Par
 #else
   if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, cube);
 #endif
-  if (PHYS & PHYS_TURB) diffuse_turbulent(A.met, A.clim, A.ctl, dt, ig, a, cube.ax);
-  if (PHYS & PHYS_MESO) {
+  if (PHYS & PHYS_TURB) diffuse_turbulent(A.met, A.clim, A.ctl, dt, ig, a);
+  if constexpr ((PHYS & PHYS_MESO) != 0) {
     float *s = A.uvwp + 3 * ip;
     float up = s[0], vp = s[1], wp = s[2];
     diffuse_mesoscale(A.met, A.ctl, dt, ig, a, up, vp, wp, cube);
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(128) meteo_kernel(const __grid_constant__ Mete
   if (ip >= A.np) return;
   Parcel a;
   a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
-  Cube cube;
+  CubeT<true> cube;
   cube_reset(cube);
   MeteoValues m;
   meteo_at(A.met, a, cube, m);

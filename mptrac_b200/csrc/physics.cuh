@@ -417,16 +417,8 @@ MPB_HD void stencil_2d(const MetView &g, double lon, double lat, CellAxes &a, St
   s.wy = quot(a.y.hi - lat2, a.y.hi - a.y.lo, a.y.rd);
 }
 
-MPB_HD void stencil_3d(const MetView &g, double lon, double lat, double p, CellAxes &a, Stencil &s) {
-  s.iz = p_cell(g, p, a);
-  stencil_2d(g, lon, lat, a, s);
-  s.wz = quot(a.z.hi - p, a.z.hi - a.z.lo, a.z.rd);
-}
-
-// w * (lo - hi) + hi with the difference taken in fp32 first (3023-3038)
 // (Measured alternative: promoting on the integer pipes -- IMAD.HI + shifts + LOP3, exact for normals and zero -- instead of
 // F2F.F64.F32, which runs on the 16-lane XU pipe: 158 us vs 117 us per step; the extra issue slots cost more than XU.)
-MPB_HD double lerp_f32(double w, float lo, float hi) { return w * (double)f_sub(lo, hi) + (double)hi; }
 MPB_HD double lerp_f64(double w, double lo, double hi) { return w * (lo - hi) + hi; }
 
 MPB_HD Node load_node(const Node *ptr) {
@@ -446,14 +438,26 @@ MPB_HD Node load_node(const Node *ptr) {
 // a parcel by a few km, a cell is ~100 km x 1 km), so the cube is fetched once per step and only re-fetched by the
 // threads whose cell changed.  That takes the scattered 32-byte gathers -- the kernel's first limiter, the L1 data pipe
 // -- from 4-6 per parcel-step to little more than one.
-struct Cube {
+// DIFF = true: the lower-level nodes are replaced, once per fetch, by the fp32 differences "lower - upper" every vertical
+// lerp starts with (3023-3038), which takes those subtractions off the per-stage path; the mesoscale statistics need the
+// raw corner values, so kernels that include them use DIFF = false.
+template <bool DIFF>
+struct CubeT {
   Node n000, n001, n010, n011, n100, n101, n110, n111;  // index order: x, y, z
   int ix, iy, iz;                                        // the cell held; ix < 0 = nothing yet
   CellAxes ax;                                           // its axis intervals
 };
-MPB_HD void cube_reset(Cube &c) { c.ix = -1; c.iy = -1; c.iz = -1; axes_reset(c.ax); }
+using Cube = CubeT<false>;
+template <bool DIFF>
+MPB_HD void cube_reset(CubeT<DIFF> &c) { c.ix = -1; c.iy = -1; c.iz = -1; axes_reset(c.ax); }
 
-MPB_HD void load_cube(const MetView &g, const Stencil &s, Cube &c) {
+MPB_HD void node_diff(Node &lo, const Node &hi) {
+  lo.u0 = f_sub(lo.u0, hi.u0); lo.v0 = f_sub(lo.v0, hi.v0); lo.w0 = f_sub(lo.w0, hi.w0); lo.t0 = f_sub(lo.t0, hi.t0);
+  lo.u1 = f_sub(lo.u1, hi.u1); lo.v1 = f_sub(lo.v1, hi.v1); lo.w1 = f_sub(lo.w1, hi.w1); lo.t1 = f_sub(lo.t1, hi.t1);
+}
+
+template <bool DIFF>
+MPB_HD void load_cube(const MetView &g, const Stencil &s, CubeT<DIFF> &c) {
   const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * (size_t)g.nz;
   const Node *b = g.f + ((size_t)s.ix * sx + (size_t)s.iy * sy + (size_t)s.iz);
   c.n000 = load_node(b);
@@ -464,30 +468,70 @@ MPB_HD void load_cube(const MetView &g, const Stencil &s, Cube &c) {
   c.n101 = load_node(b + sx + 1);
   c.n110 = load_node(b + sx + sy);
   c.n111 = load_node(b + sx + sy + 1);
+  if (DIFF) { node_diff(c.n000, c.n001); node_diff(c.n010, c.n011); node_diff(c.n100, c.n101); node_diff(c.n110, c.n111); }
   c.ix = s.ix; c.iy = s.iy; c.iz = s.iz;
 }
 
 // make c hold the cell of s
-MPB_HD void fetch_cube(const MetView &g, const Stencil &s, Cube &c) {
+template <bool DIFF>
+MPB_HD void fetch_cube(const MetView &g, const Stencil &s, CubeT<DIFF> &c) {
   if (c.ix != s.ix || c.iy != s.iy || c.iz != s.iz) load_cube(g, s, c);
 }
 
-#define MPB_TRILERP(member)                                              \
-  lerp_f64(s.wx,                                                         \
-           lerp_f64(s.wy, lerp_f32(s.wz, c.n000.member, c.n001.member),  \
-                    lerp_f32(s.wz, c.n010.member, c.n011.member)),       \
-           lerp_f64(s.wy, lerp_f32(s.wz, c.n100.member, c.n101.member),  \
-                    lerp_f32(s.wz, c.n110.member, c.n111.member)))
+// vertical lerp of one column: w * (lo - hi) + hi with the difference taken in fp32 first (3023-3038)
+template <bool DIFF>
+MPB_HD double lerp_col(double w, float lo_or_diff, float hi) {
+  return w * (double)(DIFF ? lo_or_diff : f_sub(lo_or_diff, hi)) + (double)hi;
+}
+
+#define MPB_TRILERP(member)                                                    \
+  lerp_f64(s.wx,                                                               \
+           lerp_f64(s.wy, lerp_col<DIFF>(s.wz, c.n000.member, c.n001.member),  \
+                    lerp_col<DIFF>(s.wz, c.n010.member, c.n011.member)),       \
+           lerp_f64(s.wy, lerp_col<DIFF>(s.wz, c.n100.member, c.n101.member),  \
+                    lerp_col<DIFF>(s.wz, c.n110.member, c.n111.member)))
+
+// Stencil of (lon, lat, p) with the cube made to hold its cell: indices + weights of intpol_met_space_3d's init part
+// (2997-3021).  INVARIANT: whenever c.ax names a cell, the cube holds that cell (every path that moves c.ax fetches).
+// Production device build: ONE combined test "still inside the cell the cube holds" decides between the register-only
+// fast path and the full search -- an RK stage moves a parcel by a few km, so ~85 % of all lookups take it.
+template <class CubeT>
+MPB_HD void locate(const MetView &g, double lon, double lat, double p, CubeT &c, Stencil &s) {
+  double lon2, lat2;
+  clamp_horizontal(g, lon, lat, lon2, lat2);
+  CellAxes &a = c.ax;
+#if MPB_FAST_QUOT
+  const bool inside = a.ix >= 0 && cell_holds(a.x, a.ix, g.nx, g.lon_asc, lon2) && cell_holds(a.y, a.iy, g.ny, g.lat_asc, lat2) &&
+                      cell_holds(a.z, a.iz, g.nz, g.p_asc, p);
+  if (!inside) {
+    lon_cell(g, lon2, a);
+    lat_cell(g, lat2, a);
+    p_cell(g, p, a);
+    s.ix = a.ix; s.iy = a.iy; s.iz = a.iz;
+    fetch_cube(g, s, c);
+  }
+#else
+  lon_cell(g, lon2, a);
+  lat_cell(g, lat2, a);
+  p_cell(g, p, a);
+  s.ix = a.ix; s.iy = a.iy; s.iz = a.iz;
+  fetch_cube(g, s, c);
+#endif
+  s.ix = a.ix; s.iy = a.iy; s.iz = a.iz;
+  s.wx = quot(a.x.hi - lon2, a.x.hi - a.x.lo, a.x.rd);
+  s.wy = quot(a.y.hi - lat2, a.y.hi - a.y.lo, a.y.rd);
+  s.wz = quot(a.z.hi - p, a.z.hi - a.z.lo, a.z.rd);
+}
 
 // time weight of met0 (3133)
 MPB_HD double time_weight(const MetView &g, double ts) { return quot(g.t1 - ts, g.dt01, g.r_dt01); }
 
 // u, v, w at (p, lon, lat) for the time weight wt: intpol_met_time_3d x3 sharing one stencil (3112-3137, 3638-3643)
-MPB_HD void wind_at(const MetView &g, double wt, double lon, double lat, double p, Cube &c,
+template <bool DIFF>
+MPB_HD void wind_at(const MetView &g, double wt, double lon, double lat, double p, CubeT<DIFF> &c,
                     double &u, double &v, double &w) {
   Stencil s;
-  stencil_3d(g, lon, lat, p, c.ax, s);
-  fetch_cube(g, s, c);
+  locate(g, lon, lat, p, c, s);
   u = lerp_f64(wt, MPB_TRILERP(u0), MPB_TRILERP(u1));
   v = lerp_f64(wt, MPB_TRILERP(v0), MPB_TRILERP(v1));
   w = lerp_f64(wt, MPB_TRILERP(w0), MPB_TRILERP(w1));
@@ -531,18 +575,17 @@ MPB_HD double trilerp(const Stencil &s, const WindCube &c, int k) {
 MPB_HD void wind_at(const MetView &g, double wt, double lon, double lat, double p, WindCube &c,
                     double &u, double &v, double &w) {
   Stencil s;
-  stencil_3d(g, lon, lat, p, c.ax, s);
-  fetch_cube(g, s, c);
+  locate(g, lon, lat, p, c, s);
   u = lerp_f64(wt, trilerp(s, c, 0), trilerp(s, c, 3));
   v = lerp_f64(wt, trilerp(s, c, 1), trilerp(s, c, 4));
   w = lerp_f64(wt, trilerp(s, c, 2), trilerp(s, c, 5));
 }
 
 // temperature at (ts, p, lon, lat)
-MPB_HD double temperature_at(const MetView &g, double ts, double lon, double lat, double p, Cube &c) {
+template <bool DIFF>
+MPB_HD double temperature_at(const MetView &g, double ts, double lon, double lat, double p, CubeT<DIFF> &c) {
   Stencil s;
-  stencil_3d(g, lon, lat, p, c.ax, s);
-  fetch_cube(g, s, c);
+  locate(g, lon, lat, p, c, s);
   return lerp_f64(time_weight(g, ts), MPB_TRILERP(t0), MPB_TRILERP(t1));
 }
 
@@ -746,8 +789,10 @@ MPB_HD double weight_tropo(double pt, double p) { return ramp_weight(pt / 0.8668
 // module_diff_turb (4588-4734)
 // ----------------------------------------------------------------------------------------------
 MPB_HD void diffuse_turbulent(const MetView &g, const ClimView &cl, const CtlView &c, double dt,
-                              uint64_t ig, Parcel &a, CellAxes &ax) {
+                              uint64_t ig, Parcel &a) {
   double ps, pbl;
+  CellAxes ax;            // a 2-D lookup of its own: the cube's axes must only move together with the cube (see locate)
+  axes_reset(ax);
   surface_at(g, a.time, a.lon, a.lat, ax, ps, pbl);
   if (c.pbl_scheme > 0 && a.p >= pbl) return;
 
@@ -870,7 +915,8 @@ MPB_HD double settling_velocity(double p, double T, double rp, double rhop) {
   return 2. * (rp_m * rp_m) * (rhop - rho) * kG0 / (9. * eta) * G;
 }
 
-MPB_HD void sediment(const MetView &g, double dt, double rp, double rhop, Parcel &a, Cube &c) {
+template <bool DIFF>
+MPB_HD void sediment(const MetView &g, double dt, double rp, double rhop, Parcel &a, CubeT<DIFF> &c) {
   const double T = temperature_at(g, a.time, a.lon, a.lat, a.p, c);
   const double vs = settling_velocity(a.p, T, rp, rhop);
   a.p += dz2dp(vs * dt / 1000., a.p);
@@ -884,10 +930,10 @@ struct MeteoValues {
   double ps, pbl, t, u, v, w;
 };
 
-MPB_HD void meteo_at(const MetView &g, const Parcel &a, Cube &c, MeteoValues &m) {
+template <bool DIFF>
+MPB_HD void meteo_at(const MetView &g, const Parcel &a, CubeT<DIFF> &c, MeteoValues &m) {
   Stencil s;
-  stencil_3d(g, a.lon, a.lat, a.p, c.ax, s);
-  fetch_cube(g, s, c);
+  locate(g, a.lon, a.lat, a.p, c, s);
   const double wt = time_weight(g, a.time);
   m.t = lerp_f64(wt, MPB_TRILERP(t0), MPB_TRILERP(t1));
   m.u = lerp_f64(wt, MPB_TRILERP(u0), MPB_TRILERP(u1));

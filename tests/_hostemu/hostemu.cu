@@ -63,7 +63,7 @@ static void make_view(HostMet &h, const EmuMet *m0, const EmuMet *m1, bool with_
                     h.t);
 }
 
-template <int ADVECT>
+template <int ADVECT, bool DIFF>
 static void run(const MetView &g, const ClimView &cl, const CtlView &c, const EmuCtl &e, long long np, long long ig0,
                 double *time, double *lon, double *lat, double *p, double *dtarr, float *uvwp, const double *rp,
                 const double *rhop) {
@@ -77,7 +77,7 @@ static void run(const MetView &g, const ClimView &cl, const CtlView &c, const Em
     } else dt = dtarr[ip];
     if (dt == 0) continue;
     const uint64_t ig = (uint64_t)(ig0 + ip);
-    Cube cube;
+    CubeT<DIFF> cube;     // like the kernels: difference cube unless the mesoscale module needs the raw corners
     cube_reset(cube);
     if (e.modules & MOD_POS_PRE) fix_position(g, a);
 #if MPB_CUBE_F64
@@ -85,12 +85,22 @@ static void run(const MetView &g, const ClimView &cl, const CtlView &c, const Em
 #else
     if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(g, dt, a, cube);
 #endif
-    if (e.phys & 1) diffuse_turbulent(g, cl, c, dt, ig, a, cube.ax);
-    if (e.phys & 2) diffuse_mesoscale(g, c, dt, ig, a, uvwp[3 * ip], uvwp[3 * ip + 1], uvwp[3 * ip + 2], cube);
+    if (e.phys & 1) diffuse_turbulent(g, cl, c, dt, ig, a);
+    if constexpr (!DIFF) {
+      if (e.phys & 2) diffuse_mesoscale(g, c, dt, ig, a, uvwp[3 * ip], uvwp[3 * ip + 1], uvwp[3 * ip + 2], cube);
+    }
     if (e.phys & 4) sediment(g, dt, rp[ip], rhop[ip], a, cube);
     if (e.modules & MOD_POS_POST) fix_position(g, a);
     time[ip] = a.time; lon[ip] = a.lon; lat[ip] = a.lat; p[ip] = a.p;
   }
+}
+
+template <int ADVECT>
+static void run(const MetView &g, const ClimView &cl, const CtlView &c, const EmuCtl &e, long long np, long long ig0,
+                double *time, double *lon, double *lat, double *p, double *dtarr, float *uvwp, const double *rp,
+                const double *rhop) {
+  if (e.phys & 2) run<ADVECT, false>(g, cl, c, e, np, ig0, time, lon, lat, p, dtarr, uvwp, rp, rhop);
+  else run<ADVECT, true>(g, cl, c, e, np, ig0, time, lon, lat, p, dtarr, uvwp, rp, rhop);
 }
 
 extern "C" int emu_step(const EmuMet *m0, const EmuMet *m1, const EmuCtl *e, int ntime, int nlat, const double *cl_time,
