@@ -40,7 +40,7 @@ def _run(cmd, **kw):
 def build_lib(force: bool = False, verbose_ptxas: bool = False) -> Path:
     """nvcc -> mptrac_b200/_lib/libmptrac_b200.so (+ the -fmad=false 'strict' flavour used by parity tests)."""
     LIBDIR.mkdir(exist_ok=True)
-    srcs = [CSRC / "engine.cu", CSRC / "physics.cuh", ROOT / "include" / "mptrac_b200.h"]
+    srcs = [CSRC / "engine.cu", CSRC / "physics.cuh", CSRC / "met_tables.hpp", ROOT / "include" / "mptrac_b200.h"]
     extra = ["-Xptxas", "-v"] if verbose_ptxas else []
     if force or _stale(LIB, srcs):
         _run(["nvcc", *NVCC_FLAGS, *extra, CSRC / "engine.cu", "-o", LIB])
