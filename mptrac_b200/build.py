@@ -45,7 +45,9 @@ def build_lib(force: bool = False, verbose_ptxas: bool = False) -> Path:
     if force or _stale(LIB, srcs):
         _run(["nvcc", *NVCC_FLAGS, *extra, CSRC / "engine.cu", "-o", LIB])
     if force or _stale(LIB_STRICT, srcs):
-        _run(["nvcc", *NVCC_FLAGS, "-fmad=false", "-DMPB_STRICT=1", CSRC / "engine.cu", "-o", LIB_STRICT])
+        # (the strict flavour also carries the TMA bulk-copy staging of the parcel stream, so that both staging paths
+        # run in the GPU test suite: csrc/engine.cu MPB_TMA_STAGE)
+        _run(["nvcc", *NVCC_FLAGS, "-fmad=false", "-DMPB_STRICT=1", "-DMPB_TMA_STAGE=1", CSRC / "engine.cu", "-o", LIB_STRICT])
     return LIB
 
 

@@ -87,12 +87,14 @@ constexpr unsigned PHYS_TURB = 1, PHYS_MESO = 2, PHYS_SEDI = 4;
 #ifndef MPB_CUBE_F64
 #define MPB_CUBE_F64 0
 #endif
+#ifndef MPB_TMA_STAGE    // 1: bulk copies (TMA, UBLKCP + mbarrier) stage the parcel stream of device-resident parcels;
+#define MPB_TMA_STAGE 0  // 0: per-lane cp.async (LDGSTS) only.  Measured on B200 (C2): 117.5 us per step with cp.async, 120-123 us
+#endif                   // with bulk copies (four copies serialised in one lane + mbarrier polling against four issued by all lanes at
+                         // once), and 120 us with both paths compiled in (the unrolled RK4 loop sits at the instruction-cache edge:
+                         // stall_no_instruction doubles).  The strict library is built with 1, so both paths are in the GPU test suite.
 #ifndef MPB_PERSIST      // 1: grid = SMs x resident blocks, threads loop over parcels; 0: one block per kBlock parcels
 #define MPB_PERSIST 1    // (measured: 126 us vs 135 us)
 #endif
-#ifndef MPB_CONTIG       // persistent form: 1 = each block walks its own contiguous parcel range, 0 = grid-stride.
-#define MPB_CONTIG 0     // Measured on B200 (C2, sorted): 131 us contiguous vs 121 us grid-stride -- with the grid-stride walk all
-#endif                   // SMs sweep the same window of the sorted parcels together and share its nodes through L2
 constexpr int kBlock = MPB_BLOCK;
 constexpr int kLanes = 4;                       // concurrent chunk pipelines of mpb_run_timestep_host
 constexpr long long kHostChunkMin = 16384;      // parcels per chunk: at least 128 KiB per array ...
@@ -155,56 +157,108 @@ __device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Par
   }
 }
 
-// Asynchronous copy of one parcel's state (time, lon, lat, p) into this thread's shared-memory slots: cp.async
-// (LDGSTS) needs no destination registers, so the load of the NEXT parcel can stay in flight for the whole step of the
-// current one -- with ~100 live fp64 registers per parcel a register prefetch is spilled at once, and the spill waits
-// for the load (r01e profile: 7 % of all stall samples).
-__device__ __forceinline__ void stage_parcel_async(const StepArgs &A, long long ip, double (*slot)[kBlock]) {
-  const double *src[4];
-  if (A.in_time) { src[0] = A.in_time; src[1] = A.in_lon; src[2] = A.in_lat; src[3] = A.in_p; }
-  else { src[0] = A.time; src[1] = A.lon; src[2] = A.lat; src[3] = A.p; }
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(&slot[j][threadIdx.x]);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src[j] + ip) : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
+// ------------------------------------------------------------------------------------------------
+// Staging of the parcel stream.  The four state arrays are contiguous SoA streams, and a warp consumes them 32 parcels
+// (256 bytes per array) at a time: exactly what the bulk-copy engine (TMA, cp.async.bulk -> UBLKCP) moves with ONE
+// instruction per array, into shared memory, with no destination registers and no per-lane address arithmetic.  That
+// matters here because the kernel holds ~100 live fp64 registers per parcel: a register prefetch of the next parcel is
+// spilled at once and the spill waits for the load (r01e profile: 7 % of all stall samples).  Every warp owns two
+// 4 x 256-byte slots and one mbarrier per slot; lane 0 arms the barrier with the byte count and issues the four copies
+// for chunk k+1 while the warp computes chunk k.  Warps never wait for each other.
+// The alternative path is per-lane cp.async (LDGSTS, 8 bytes per lane and array): it is what host-mapped sources
+// (zero-copy stepping of pinned host arrays) must use -- a bulk copy reads whole 256-byte tiles, which is only safe
+// inside the context's own padded allocations -- and, measured, also the faster one on this kernel (MPB_TMA_STAGE).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// Persistent form: the grid is sized to what the GPU holds at once (SMs x resident blocks) and every thread walks the
-// parcels ip, ip + stride, ...  While parcel k computes, the state of parcel k+1 is already in flight (double-buffered
-// in shared memory), the axis tables stay hot in L1 for the whole launch and no block-launch gaps separate the parcels
-// of a thread (the kernel holds ~100 registers of fp64 state per parcel, so only ~16 warps are resident per SM and
-// every exposed latency counts).
+constexpr int kWarps = kBlock / 32;
+constexpr unsigned kTileBytes = 32 * sizeof(double);   // one array's share of a warp's chunk
+
+// Persistent form: the grid is sized to what the GPU holds at once (SMs x resident blocks) and every warp walks the
+// chunks w0, w0 + stride, ... of 32 parcels.  While chunk k computes, the state of chunk k+1 is already in flight, the
+// axis tables stay hot in L1 for the whole launch and no block-launch gaps separate the chunks of a warp (only ~16
+// warps are resident per SM, so every exposed latency counts).
 template <int ADVECT, unsigned PHYS>
 __global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
-  __shared__ double stage[2][4][kBlock];
-#if MPB_CONTIG
-  // every block owns one contiguous range of the (cell-sorted) parcels and walks it kBlock parcels at a time
-  const long long per_block = ((A.np + gridDim.x - 1) / gridDim.x + kBlock - 1) / kBlock * kBlock;
-  const long long stride = kBlock;
-  long long ip = (long long)blockIdx.x * per_block + threadIdx.x;
-  const long long end = min(A.np, ((long long)blockIdx.x + 1) * per_block);
-#else
+  __shared__ alignas(128) double stage[2][4][kBlock];
+  __shared__ alignas(8) unsigned long long full[kWarps][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long stride = (long long)gridDim.x * kBlock;
-  long long ip = (long long)blockIdx.x * kBlock + threadIdx.x;
-  const long long end = A.np;
+  long long w0 = (long long)blockIdx.x * kBlock + warp * 32;   // first parcel of this warp's chunk
+  if (w0 >= A.np) return;                                        // (warp-uniform)
+#if MPB_TMA_STAGE
+  const bool tma = A.in_time == nullptr;   // device-resident parcels: bulk copies (warp-uniform: a launch parameter)
+#else
+  constexpr bool tma = false;
 #endif
-  if (ip >= end) return;
+
+  auto issue = [&](long long first, int b) {   // start the copies of chunk [first, first + 32) into slot b
+    if (tma) {
+      if (lane == 0) {
+        const unsigned bar = smem_u32(&full[warp][b]), dst = smem_u32(&stage[b][0][warp * 32]);
+        mbar_expect(bar, 4 * kTileBytes);
+        bulk_load(dst, A.time + first, kTileBytes, bar);
+        bulk_load(dst + kBlock * 8, A.lon + first, kTileBytes, bar);
+        bulk_load(dst + 2 * kBlock * 8, A.lat + first, kTileBytes, bar);
+        bulk_load(dst + 3 * kBlock * 8, A.p + first, kTileBytes, bar);
+      }
+    } else {
+      if (first + lane < A.np) {
+        const unsigned dst = smem_u32(&stage[b][0][threadIdx.x]);
+        const long long i = first + lane;
+        const bool host = A.in_time != nullptr;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"((host ? A.in_time : A.time) + i) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + kBlock * 8), "l"((host ? A.in_lon : A.lon) + i) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 2 * kBlock * 8), "l"((host ? A.in_lat : A.lat) + i) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 3 * kBlock * 8), "l"((host ? A.in_p : A.p) + i) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  };
+
+  if (tma) {
+    if (lane == 0) {
+      mbar_init(smem_u32(&full[warp][0]));
+      mbar_init(smem_u32(&full[warp][1]));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
   int buf = 0;
-  stage_parcel_async(A, ip, stage[0]);
+  unsigned phase = 0;   // bit b = parity the next completion of slot b's barrier will have
+  issue(w0, 0);
   for (;;) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");   // a thread only ever reads the slots it filled itself
+    if (tma) { mbar_wait(smem_u32(&full[warp][buf]), (phase >> buf) & 1u); phase ^= 1u << buf; }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");   // a lane only reads the slots it filled itself
+    const long long ip = w0 + lane;
     Parcel a;
     a.time = stage[buf][0][threadIdx.x]; a.lon = stage[buf][1][threadIdx.x];
     a.lat = stage[buf][2][threadIdx.x]; a.p = stage[buf][3][threadIdx.x];
-    const long long cur = ip;
-    ip += stride;
-    const bool more = ip < end;
+    w0 += stride;
+    const bool more = w0 < A.np;          // (warp-uniform)
     buf ^= 1;
-    if (more) stage_parcel_async(A, ip, stage[buf]);
-    step_parcel<ADVECT, PHYS>(A, cur, a);
+    __syncwarp();                         // every lane has read its slot of the buffer the next-but-one copy reuses
+    if (more) issue(w0, buf);
+    if (ip < A.np) step_parcel<ADVECT, PHYS>(A, ip, a);
     if (!more) break;
+    __syncwarp();                         // (reconverge before the next wait: measured 120 us with, 125 us without)
   }
 }
 
@@ -721,7 +775,9 @@ int mpb_create(mpb_ctx **out, int device, int64_t np_max, int nq) {
   REQUIRE(nq >= 0, "nq must be >= 0");
   CK(cudaSetDevice(device));
   mpb_ctx *c = new mpb_ctx();
-  c->device = device; c->np_max = std::max<long long>(np_max, 1); c->nq = nq;
+  // capacity in whole 32-parcel tiles: every array then starts 256-byte aligned and a warp's bulk copy of its (possibly
+  // partial) last tile stays inside the allocation
+  c->device = device; c->np_max = (std::max<long long>(np_max, 1) + 31) / 32 * 32; c->nq = nq;
   std::memset(&c->ctl, 0, sizeof(c->ctl));
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;

@@ -700,7 +700,7 @@ MPB_HD void advect(const MetView &g, double dt, Parcel &a, CubeT &c) {
   double lat_stage = a.lat;
   const LonScale ks = lon_scale(g.coord_type, a.lat);   // the stages and (Euler, RK4) the final update share it
   double wt = 0;
-#pragma unroll
+#pragma unroll   // (measured: a rolled stage loop -- 1600 instead of 2850 SASS instructions -- runs at the same speed)
   for (int i = 0; i < ORDER; i++) {
     double x, y, z, dts;
     if (i == 0) {

@@ -379,6 +379,32 @@ def test_inactive_and_ragged_parcels(oracle):
     assert np.all(out["time"] == 1500.0)
 
 
+def test_tma_staging_strict_library(oracle):
+    """the strict library stages the parcel stream with bulk copies (TMA: one cp.async.bulk per 256-byte tile, one
+    mbarrier per warp and slot) where the production library uses per-lane cp.async: ragged size (partial last tile),
+    cell sort, diffusion and sedimentation, against the oracle and against the production library"""
+    from mptrac_b200 import Ctl
+    from oracle.oracle import Parcels
+    m0, m1, tm, p, lon, lat, clim = _case(n=100_003, grid=(72, 37, 30))
+    n = tm.size
+    q = np.stack([np.full(n, 2.0), np.full(n, 1500.0)])
+    ctl = Ctl(nq=2, qnt_rp=0, qnt_rhop=1, advect=4, diffusion=1, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0,
+              turb_dz_trop=0.5, turb_dx_strat=20.0)
+    outs = []
+    for strict in (True, False):
+        with _engine(n, 2, strict=strict) as eng:
+            _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat, q)
+            for s in range(5):
+                eng.run_timestep(300.0 * s)
+            outs.append(eng.get_atm())
+    ref = Parcels(tm, p, lon, lat, q)
+    oracle.ctr = 0
+    oracle.run("timestep", ctl, clim, m0, m1, ref, t=0.0, nsteps=5)
+    _compare("tma_staging_strict", outs[0], ref, TOL_POS_DEG_DIFF, TOL_P_REL_DIFF)
+    assert abserr(outs[0]["lat"], outs[1]["lat"]) < TOL_POS_DEG_DIFF and relerr(outs[0]["p"], outs[1]["p"]) < TOL_P_REL_DIFF
+    assert abserr(outs[0]["lat"], lat) > 1e-3
+
+
 @pytest.mark.parametrize("layout", ["separate_arrays", "atm_t_layout", "pinned"])
 def test_host_resident_step_equals_three_calls(layout):
     """mpb_run_timestep_host (chunked upload / step / download pipeline) == set_atm + run_timestep + get_atm, bit for bit,
