@@ -39,33 +39,11 @@ def read_tab(path):
 
 
 def ref_read_met(ref, path, slot):
-    L = ref.L
-    L.ref_read_met.argtypes = [C.c_char_p, C.c_int]
-    if L.ref_read_met(str(path).encode(), slot) != 1:
-        raise RuntimeError(f"reference could not read {path}")
-    nx, ny, nz, ct = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-    tm = C.c_double()
-    L.ref_met_dims(slot, C.byref(nx), C.byref(ny), C.byref(nz), C.byref(ct), C.byref(tm))
-    nx, ny, nz = nx.value, ny.value, nz.value
-    lon, lat, p = np.zeros(nx), np.zeros(ny), np.zeros(nz)
-    f3 = [np.zeros((nx, ny, nz), np.float32) for _ in range(4)]
-    f2 = [np.zeros((nx, ny), np.float32) for _ in range(2)]
-    L.ref_get_met.argtypes = [C.c_int] + [C.c_void_p] * 9
-    L.ref_get_met(slot, *[a.ctypes.data for a in (lon, lat, p, *f3, *f2)])
-    return Met(time=tm.value, lon=lon, lat=lat, p=p, u=f3[0], v=f3[1], w=f3[2], t=f3[3], ps=f2[0], pbl=f2[1],
-               coord_type=ct.value)
+    return ref.read_met(path, slot, Met)
 
 
 def ref_read_atm(ref, path):
-    L = ref.L
-    L.ref_read_atm.argtypes = [C.c_char_p]
-    n = L.ref_read_atm(str(path).encode())
-    if n < 0:
-        raise RuntimeError(f"reference could not read {path}")
-    arrs = [np.zeros(n) for _ in range(4)]
-    L.ref_get_atm.argtypes = [C.c_void_p] * 4
-    L.ref_get_atm(*[a.ctypes.data for a in arrs])
-    return arrs  # time, p, lon, lat
+    return ref.read_atm(path)  # time, p, lon, lat
 
 
 def crop_met(m: Met, iy0, iy1, iz0, iz1) -> Met:

@@ -240,6 +240,43 @@ def test_golden_dt_test():
             assert np.all(np.abs(out["q"].T - tq) <= 1e-5 * np.maximum(np.abs(tq), 1e-3 * np.max(np.abs(tq), axis=0)))
 
 
+def test_c1_trac_test_parcels_midpoint_vs_reference(reference):
+    """BASELINE configs[0]: the 10 000 parcels of the reference's tests/trac_test (data.ref/atm_init.tab) on its
+    ERA-Interim test data, ADVECT 2 (midpoint), diffusion and every other module off, one day at DT_MOD 300 -- against
+    the UNMODIFIED reference run right here through oracle/_ref (met read + pre-processed by the reference itself).
+    north_star's bound is 1e-6 relative on lon / lat / p; measured ~1e-13."""
+    from mptrac_b200 import Ctl, Met
+    from oracle.oracle import Parcels
+    data = ROOT / "oracle" / "_ref" / "data"
+    files = [data / "ei_2011_06_05_00.nc", data / "ei_2011_06_06_00.nc", data / "trac_test.ref" / "atm_init.tab"]
+    if not all(f.exists() for f in files):
+        pytest.skip("reference test data not shipped (oracle/build_ref.sh)")
+    reference.read_ctl([], "")
+    m0, m1 = reference.read_met(files[0], 0, Met), reference.read_met(files[1], 1, Met)
+    tm, p, lon, lat = reference.read_atm(files[2])
+    n = tm.size
+    assert n == 10000 and m1.time - m0.time == 86400.0
+    t0 = m0.time
+    ctl = Ctl(advect=2, diffusion=0, t_start=t0, t_stop=t0 + 86400.0, dt_mod=300.0, dt_met=86400.0)
+    nsteps = 289          # t0, t0 + 300, ..., t0 + 86400 (the first call has dt = 0)
+    ref = Parcels(tm, p, lon, lat)
+    reference.ctr = 0
+    reference.run("timestep", ctl, ref, t=t0, nsteps=nsteps)
+    with _engine(n) as eng:
+        _setup(eng, ctl, reference.clim_tropo(), m0, m1, tm, p, lon, lat)
+        for s in range(nsteps):
+            eng.run_timestep(t0 + 300.0 * s)
+        out = eng.get_atm()
+    assert abserr(ref.lat, lat) > 1.0, "nothing moved"
+    # parcels that brushed a pole (DX2DEG switches the zonal displacement off within 0.001 deg of it, a discontinuity) are
+    # compared on the sphere like all others: the metric below weighs dlon with cos(lat)
+    _compare("c1_trac_test_midpoint_1day", out, ref, tol_pos=1e-6, tol_p=1e-6)
+    dlon = (out["lon"] - ref.lon + 180.0) % 360.0 - 180.0
+    med = float(np.median(np.hypot(dlon * np.cos(np.deg2rad(ref.lat)), out["lat"] - ref.lat)))
+    _report("c1_trac_test_midpoint_1day_median", pos_deg=med)
+    assert med < 1e-12
+
+
 def test_golden_coord_test():
     """tests/coord_test of the reference: Cartesian (UTM) met, three hourly levels (met swap), 13 outputs."""
     from mptrac_b200 import Ctl

@@ -3,7 +3,7 @@ container only -- skipped where oracle/_ref does not exist).  Everything must be
 import numpy as np
 import pytest
 
-from conftest import abserr
+from conftest import ROOT, abserr
 
 
 def _case(n, grid, lat_desc, seed=3):
@@ -164,3 +164,26 @@ def test_run_timestep_with_meteo_bit_exact(oracle, reference):
     for k in ("lon", "lat", "p"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
     assert np.array_equal(a.q, b.q) and np.all(a.q[0] > 150)
+
+
+def test_c1_trac_test_parcels_midpoint_bit_exact(oracle, reference):
+    """BASELINE configs[0]: the reference's tests/trac_test parcels on its ERA-Interim data, ADVECT 2, everything else
+    off, one day at DT_MOD 300: the restatement follows the reference bit for bit over all 289 steps"""
+    from mptrac_b200 import Ctl, Met
+    from oracle.oracle import Parcels
+    data = ROOT / "oracle" / "_ref" / "data"
+    files = [data / "ei_2011_06_05_00.nc", data / "ei_2011_06_06_00.nc", data / "trac_test.ref" / "atm_init.tab"]
+    if not all(f.exists() for f in files):
+        pytest.skip("reference test data not present")
+    reference.read_ctl([], "")
+    m0, m1 = reference.read_met(files[0], 0, Met), reference.read_met(files[1], 1, Met)
+    tm, p, lon, lat = reference.read_atm(files[2])
+    t0 = m0.time
+    ctl = Ctl(advect=2, diffusion=0, t_start=t0, t_stop=t0 + 86400.0, dt_mod=300.0, dt_met=86400.0)
+    a = Parcels(tm, p, lon, lat)
+    b = a.copy()
+    reference.run("timestep", ctl, a, t=t0, nsteps=289)
+    oracle.run("timestep", ctl, reference.clim_tropo(), m0, m1, b, t=t0, nsteps=289)
+    for k in ("time", "lon", "lat", "p"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.max(np.abs(a.lat - lat)) > 1.0
