@@ -179,6 +179,28 @@ static void align_met(met_t *m0, met_t *m1) {
   if (g_slot[1] != m1) put_met(m1);
 }
 
+/* The reference draws all random numbers from ONE counter (file-static rng_ctr, src/mptrac.c:35) in module order.  In
+ * hybrid mode some draws happen on the device (diff_turb, diff_meso) and some inside reference modules on the host
+ * (convection, diff_pbl), whose counter the shim cannot set -- but it can advance it: before a host module that draws,
+ * the host counter is brought up to the device's by drawing (and discarding) the difference; afterwards the device
+ * counter is set past the host module's draws.  The stream every module sees is then the reference's. */
+static unsigned long long g_host_rng;    /* what the reference's static counter is right now */
+
+static void host_rng_catch_up(const ctl_t *ctl, cache_t *cache) {
+  const unsigned long long want = mpb_get_rng_ctr(g_ctx);
+  while (g_host_rng < want) {
+    unsigned long long n = want - g_host_rng;              /* module_rng(n - 1) consumes n counters */
+    if (n > 3ull * NP + 1ull) n = 3ull * NP + 1ull;        /* capacity of cache->rs */
+    module_rng(ctl, cache->rs, (size_t) (n - 1), 0);
+    g_host_rng += n;
+  }
+}
+
+static void host_rng_drew(unsigned long long n) {
+  g_host_rng += n;
+  MPB(mpb_set_rng_ctr(g_ctx, g_host_rng));
+}
+
 /* run a reference CPU module with the host copy current; the device copy is refreshed afterwards */
 #define ON_HOST(stmt)                                                         \
   do {                                                                        \
@@ -231,19 +253,27 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
   } else {
     unsigned seg = MPB_MOD_TIMESTEPS | MPB_MOD_SORT | MPB_MOD_POSITION0 | MPB_MOD_ADVECT | MPB_MOD_DIFF_TURB;
     if (pbl_cpu) {
-      MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0;
-      ON_HOST(module_diff_pbl(ctl, cache, *met0, *met1, atm));
+      MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0; g_dev_newer = 1;
+      ON_HOST({
+        host_rng_catch_up(ctl, cache);
+        module_diff_pbl(ctl, cache, *met0, *met1, atm);
+        host_rng_drew(3ull * (unsigned long long) atm->np + 1ull);
+      });
       FLUSH_HOST();
     }
     seg |= MPB_MOD_DIFF_MESO;
     if (conv_cpu) {
-      MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0;
-      ON_HOST(module_convection(ctl, cache, *met0, *met1, atm));
+      MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0; g_dev_newer = 1;
+      ON_HOST({
+        host_rng_catch_up(ctl, cache);
+        module_convection(ctl, cache, *met0, *met1, atm);
+        host_rng_drew((unsigned long long) atm->np + 1ull);
+      });
       FLUSH_HOST();
     }
     seg |= MPB_MOD_SEDI;
     if (iso_cpu) {
-      MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0;
+      MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0; g_dev_newer = 1;
       ON_HOST(module_isosurf(ctl, cache, *met0, *met1, atm));
       FLUSH_HOST();
     }

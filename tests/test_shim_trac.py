@@ -108,3 +108,83 @@ T_STOP = 799380000
         a, b, g = _tab(f), _tab(dc / f.name), _tab(DATA / "coord_test.ref" / f.name)
         assert abserr(a[:, 2], b[:, 2]) < 0.011 and abserr(a[:, 3], b[:, 3]) < 0.011 and relerr(a[:, 1], b[:, 1]) < 2e-5
         assert abserr(a[:, 2], g[:, 2]) < 0.03 and abserr(a[:, 3], g[:, 3]) < 0.03
+
+
+TRAC_TEST_CTL = """NQ = 13
+QNT_NAME[0] = t
+QNT_NAME[1] = u
+QNT_NAME[2] = v
+QNT_NAME[3] = w
+QNT_NAME[4] = zg
+QNT_NAME[5] = pv
+QNT_NAME[6] = ps
+QNT_NAME[7] = pt
+QNT_NAME[8] = m
+QNT_NAME[9] = stat
+QNT_NAME[10] = ens
+QNT_NAME[11] = Cccl3f
+QNT_NAME[12] = Cx
+METBASE = {met}/ei
+MET_DT_OUT = 86400.0
+SPECIES = SO2
+BOUND_LAT0 = -90
+BOUND_LAT1 = 90
+BOUND_P0 = 1e10
+BOUND_P1 = -1e10
+BOUND_DPS = 100.0
+BOUND_MASS = 0.0
+CONV_CAPE = 0.0
+H2O2_CHEM_REACTION = 1
+TRACER_CHEM = 1
+CHEMGRID_NX = 72
+CHEMGRID_NY = 36
+CHEMGRID_NZ = 30
+DIFFUSION = 1
+TDEC_TROP = 259200.0
+TDEC_STRAT = 259200.0
+DRY_DEPO_VDEP = 0.15
+DRY_DEPO_DP = 300
+MIXING_TROP = 1e-3
+MIXING_STRAT = 1e-6
+DT_MET = 86400.0
+DT_MOD = 300.0
+T_STOP = 360806400
+"""
+
+
+@pytest.mark.timeout(900)
+def test_trac_trac_test_pl_through_the_shim(tmp_path):
+    """The reference's own end-to-end test, tests/trac_test (pressure-level run): 10 000 parcels, 3 days at 300 s, with
+    diffusion, convection, H2O2 + tracer chemistry, decay, dry deposition, mixing and boundary conditions all on -- the
+    modules of the path on the GPU, the other twelve through the reference's CPU code in between (hybrid mode, one random
+    number stream across both).  Compared with the goldens the reference ships (data.ref/atm_pl_*.tab, %g text)."""
+    _need()
+    gold = sorted((DATA / "trac_test.ref").glob("atm_pl_2011_*.tab"))
+    if len(gold) != 4 or not (DATA / "ei_2011_06_08_00.nc").exists() or not (DATA / "clim" / "cams_H2O2.nc").exists():
+        pytest.skip("trac_test data not shipped (oracle/build_ref.sh)")
+    # the chemistry modules read their climatologies from ../../data relative to the working directory, like the
+    # reference's own test does from tests/trac_test
+    (tmp_path / "data").symlink_to(DATA / "clim")
+    base = tmp_path / "tests" / "trac_test"
+    base.mkdir(parents=True)
+    d, out = _run_trac(base, TRAC_TEST_CTL.format(met=DATA), DATA / "trac_test.ref" / "atm_init.tab",
+                       ["ATM_BASENAME", "atm_pl", "STAT_BASENAME", "station_pl", "STAT_LON", "-22", "STAT_LAT", "-40"])
+    assert "kernel launches" in out
+    report = {}
+    for g in gold:
+        a, b = _tab(d / g.name), _tab(g)
+        assert a.shape == b.shape == (10000, 17)
+        assert abserr(a[:, 0], b[:, 0]) < 0.006
+        # position: z [km], lon, lat; a parcel "agrees" when all three match the 6-digit text to 1e-4 relative (+ small abs)
+        pos_ok = np.all(np.abs(a[:, 1:4] - b[:, 1:4]) <= 1e-4 * np.abs(b[:, 1:4]) + 1e-4, axis=1)
+        qnt_ok = np.all(np.abs(a[:, 4:] - b[:, 4:]) <= 1e-3 * np.abs(b[:, 4:]) + 1e-3 * np.max(np.abs(b[:, 4:]), axis=0), axis=1)
+        report[g.name] = (float(pos_ok.mean()), float((pos_ok & qnt_ok).mean()))
+    print("fraction of parcels agreeing with the shipped goldens (position, position + quantities):", report)
+    out_dir = ROOT / "gpurun_out"
+    out_dir.mkdir(exist_ok=True)
+    (out_dir / "trac_test_pl_shim.json").write_text(__import__("json").dumps(report, indent=1))
+    # convection, mixing and the boundary conditions are discontinuous in the parcel position (a parcel on the edge of a
+    # CAPE column or a mixing box switches sides with a last-digit difference), so after 864 steps a small fraction differs
+    assert report[gold[0].name][1] == 1.0                      # t0: initial state + module_meteo + boundary conditions
+    # measured on B200: positions 1.0 / 1.0 / 1.0 / 0.9999, positions + quantities 1.0 / 0.9998 / 0.9994 / 0.999
+    assert all(v[0] >= 0.999 and v[1] >= 0.99 for v in report.values()), report
