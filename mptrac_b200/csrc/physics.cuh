@@ -211,13 +211,39 @@ struct LonScale {
   int mode;  // 0 = Cartesian (identity), 1 = polar cap (zero), 2 = divide by d
 };
 constexpr double kDegPerM = 180.0 / (1000.0 * kPi * kRE);   // fast path of DY2DEG(dy / 1000)
+// cos(x) for |x| <= pi/2 (a latitude in radians): no argument reduction, no out-of-line slow path.  Polynomial kernels
+// of the classic fdlibm k_cos / k_sin scheme (Sun Microsystems' published minimax coefficients, < 1 ulp on
+// [-pi/4, pi/4]); beyond pi/4 the identity cos x = sin(pi/2 - |x|) with pi/2 split into two doubles.  Production device
+// build only: the host and the strict build call the library cosine.
+MPB_HD double cos_quarter(double x) {
+#if MPB_FAST_QUOT
+  const double ax = fabs(x);
+  if (ax <= 0.78539816339744830962) {
+    const double z = ax * ax;
+    const double r = z * (4.16666666666666019037e-02 + z * (-1.38888888888741095749e-03 + z * (2.48015872894767294178e-05 +
+                     z * (-2.75573143513906633035e-07 + z * (2.08757232129817482790e-09 + z * -1.13596475577881948265e-11)))));
+    const double hz = 0.5 * z, w = 1.0 - hz;
+    return w + (((1.0 - w) - hz) + z * r);
+  }
+  // y = pi/2 - |x| to twice the working precision, then sin(y + t) with the tail t folded into the kernel
+  const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+  const double y = pio2_hi - ax, t = ((pio2_hi - y) - ax) + pio2_lo;
+  const double z = y * y, v = z * y;
+  const double r = 8.33333333332248946124e-03 + z * (-1.98412698298579493134e-04 + z * (2.75573137070700676789e-06 +
+                   z * (-2.50507602534068634195e-08 + z * 1.58969099521155010221e-10)));
+  return y - ((z * (0.5 * t - v * r) - t) - v * -1.66666666666666324348e-01);
+#else
+  return cos(x);
+#endif
+}
+
 MPB_HD LonScale lon_scale(int coord_type, double lat) {
   LonScale k;
   k.d = 1.0; k.rd = 1.0;
   if (coord_type != 0) { k.mode = 0; return k; }
   if (lat < -89.999 || lat > 89.999) { k.mode = 1; return k; }
   k.mode = 2;
-  k.d = kPiRE * cos(lat * (kPi / 180.0));
+  k.d = kPiRE * cos_quarter(lat * (kPi / 180.0));   // |lat| <= 89.999 here
   k.rd = 1.0 / k.d;
 #if MPB_FAST_QUOT
   k.rd *= 0.18;   // metres -> degrees in one multiply: dx / 1000 * 180 / d
