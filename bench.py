@@ -347,7 +347,11 @@ def run_ours(args):
                 "host_checksum": checksum, "host_link": pc},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "algorithmic_bytes_per_launch": algo_bytes, "kernel": "step_kernel", "peak_source": peak_src},
+                     "algorithmic_bytes_per_launch": algo_bytes, "kernel": "step_kernel", "peak_source": peak_src,
+                     "note": "not HBM-bound: DRAM traffic is below the algorithmic bytes; the kernel is limited by latency at 16 "
+                             "resident warps/SM (about 100 live fp64 registers per parcel) and by the 192 f32->f64 conversions per "
+                             "RK4 step the reference's arithmetic needs (XU pipe 45 % busy: floor 47 us per 1M parcels, i.e. frac "
+                             "0.51 at best); ncu evidence under profiles/, analysis in DESIGN.md 3.1"},
         "clocks": clk.summary(),
     }
     eng.close()
