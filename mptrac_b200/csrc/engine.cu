@@ -2,16 +2,19 @@
 // MPTRAC time-step engine.  sm_100a only; no CPU fallback: every entry point needs a CUDA device.
 //
 // Data layout in HBM
-//   parcels   SoA fp64: time[np], p[np], lon[np], lat[np], q[nq][np_max]; dt[np]; uvwp float[np][3]
+//   parcels   SoA fp64: time | p | lon | lat | q[nq], each np_max long (np_max = capacity rounded up to whole 32-parcel
+//             tiles, so every array starts 256-byte aligned); dt[np]; uvwp float[np][3]
 //             (+ a second copy of the SoA used as the gather target of module_sort, then swapped)
 //   met       ONE array of 32-byte nodes {u0,v0,w0,T0,u1,v1,w1,T1} [nx][ny][nz] (z fastest) holding both bracketing
 //             time levels, so a stencil corner is one aligned 256-bit load (LDG.E.256) = one DRAM/L2 sector;
-//             float4 {ps0,pbl0,ps1,pbl1} [nx][ny]; axes lon/lat/p fp64 + per-interval reciprocals + a first-guess
-//             table for the pressure search
+//             float4 {ps0,pbl0,ps1,pbl1} [nx][ny]; per axis one array of 32-byte interval records
+//             {x[i], x[i+1], x[i+1]-x[i], 1/(x[i+1]-x[i])} + a first-guess table for the pressure search
 //   clim      tropopause table fp64 [ntime][nlat] + its axes
 //
-// One fused kernel per model step does timesteps -> position -> advect -> diff_turb -> diff_meso ->
-// sedi -> position for one parcel per thread (the order of mptrac_run_timestep, src/mptrac.c:7877-7919).
+// One fused, persistent kernel per model step does timesteps -> position -> advect -> diff_turb -> diff_meso ->
+// sedi -> position for one parcel per thread at a time (the order of mptrac_run_timestep, src/mptrac.c:7877-7919);
+// every warp walks the parcels 32 at a time with the next chunk's state staged asynchronously in shared memory.
+// module_meteo (meteo_kernel), the cell sort and the box reductions are separate launches.
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 
