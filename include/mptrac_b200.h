@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPB_ABI_VERSION 2
+#define MPB_ABI_VERSION 3
 #define MPB_MIX_MAXQ 23  /* number of mixable quantities, src/mptrac.c:5222-5230 */
 
 /* Quantities module_meteo (src/mptrac.c:5062-5165) can set on the device: everything that derives from the met fields
@@ -70,6 +70,8 @@ typedef struct mpb_ctl {
   double mixing_lon0, mixing_lon1, mixing_lat0, mixing_lat1, mixing_z0, mixing_z1;
   double met_dt_out;                        /* module_meteo every met_dt_out seconds (<= 0: never)  ctl->met_dt_out */
   int32_t qnt_meteo[MPB_METEO_SLOTS];       /* quantity index per MPB_Q_* slot or -1               ctl->qnt_ps ... */
+  int32_t qnt_zeta, qnt_eta;                /* the parcel's model-level coordinate (ADVECT_VERT_COORD 1 / 3) or -1:
+                                               ctl->qnt_zeta, ctl->qnt_eta (src/mptrac.c:3683-3687) */
 } mpb_ctl_t;
 
 /* Host view of one met_t time level (src/mptrac.h:3844-4014).  3-D element (ix,iy,iz) lives at
@@ -82,6 +84,12 @@ typedef struct mpb_met_view {
   const float *u, *v, *w, *t;
   const float *ps, *pbl;
   int64_t sx, sy, sx2;
+  /* fields on model levels (met_t::pl, ul, vl, wl, zetal, zeta_dotl, src/mptrac.h:3540-3556), element (ix,iy,k) at
+   * base[ix*sxl + iy*syl + k] with k < npl (the reference structs: sxl = EY*EP, syl = EP); npl = 0 and null pointers
+   * when the run does not advect on model levels */
+  int32_t npl, _pad;
+  const float *pl, *ul, *vl, *wl, *zetal, *zeta_dotl;
+  int64_t sxl, syl;
 } mpb_met_view_t;
 
 /* Parameters of the gridded-output binning (write_grid, src/mptrac.c:13752 ff.). */

@@ -360,6 +360,37 @@ __global__ void __launch_bounds__(128) meteo_kernel(const __grid_constant__ Mete
   if (A.qnt[MPB_Q_ZETA_D] >= 0) set(MPB_Q_ZETA_D, zeta_diagnosed(m.ps, a.p, m.t));
 }
 
+// module_advect on model levels (src/mptrac.c:3646-3657, 3680-3757) and module_advect_init (3762-3785): one parcel per
+// thread, dt from the cache (the fused kernel's timesteps segment ran before)
+struct LevelArgs {
+  MetView met;
+  double *time, *lon, *lat, *p;
+  const double *dt;
+  double *zq;           // the parcel's zeta / eta (null for ADVECT_VERT_COORD 2)
+  long long np;
+  int vert_coord;
+};
+
+template <int ORDER>
+__global__ void __launch_bounds__(128) advect_levels_kernel(const __grid_constant__ LevelArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np) return;
+  const double dt = A.dt[ip];
+  if (dt == 0) return;
+  Parcel a;
+  a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
+  double z = 0;
+  advect_on_levels<ORDER>(A.met, A.vert_coord, dt, a, A.zq ? &z : nullptr);
+  A.time[ip] = a.time; A.lon[ip] = a.lon; A.lat[ip] = a.lat; A.p[ip] = a.p;
+  if (A.zq) A.zq[ip] = z;
+}
+
+__global__ void __launch_bounds__(128) advect_init_kernel(const __grid_constant__ LevelArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np) return;
+  A.p[ip] = pressure_of_zeta(A.met, A.time[ip], A.zq[ip], A.lon[ip], A.lat[ip]);
+}
+
 struct BoxArgs {
   double t0, t1, lon0, lon1, lat0, lat1, z0, z1;
   int nx, ny, nz;
@@ -482,9 +513,15 @@ struct mpb_ctx {
   std::vector<double> h_lon, h_lat, h_p;
   int nx = 0, ny = 0, nz = 0, coord_type = 0;
   size_t node_cap = 0, col_cap = 0;
-  float *stage_h = nullptr;  // pinned, 4 dense fields
+  float *stage_h = nullptr;  // pinned, 4 dense fields (6 model-level fields)
   float *stage_d = nullptr;
   size_t stage_cap = 0;
+  // model levels (ADVECT_VERT_COORD 1 / 2 / 3): both time levels interleaved like the nodes
+  LevelNode *lev_p = nullptr, *lev_z = nullptr;   // {pl, ul, vl, wl}, {zetal, ul, vl, zeta_dotl}
+  float4 *lev_pz = nullptr;                        // {pl0, zetal0, pl1, zetal1}
+  int npl = 0;
+  size_t lev_cap = 0;
+  bool lev_valid[2] = {false, false};
 
   // clim
   double *cl_time = nullptr, *cl_lat = nullptr, *cl_tropo = nullptr;
@@ -533,6 +570,9 @@ static MetView met_view(const mpb_ctx *c) {
   g.lonc = c->ax_lonc; g.latc = c->ax_latc; g.pc = c->ax_pc; g.p_lut = c->p_lut;
   fill_axis_scalars(g, c->h_lon.data(), c->nx, c->h_lat.data(), c->ny, c->h_p.data(), c->nz, c->coord_type,
                     c->lev[0].time, c->lev[1].time, c->tables);
+  const bool levels = c->npl >= 2 && c->lev_valid[0] && c->lev_valid[1];
+  g.lp = levels ? c->lev_p : nullptr; g.lz = levels ? c->lev_z : nullptr; g.pz = levels ? c->lev_pz : nullptr;
+  g.npl = levels ? c->npl : 0;
   return g;
 }
 
@@ -596,7 +636,7 @@ static StepArgs step_args(mpb_ctx *c, double t, int advect, unsigned phys, unsig
     A.rp = c->q(c->ctl.qnt_rp); A.rhop = c->q(c->ctl.qnt_rhop);
   }
   A.np = c->np; A.ig0 = c->ig0; A.modules = modules;
-  if (advect > 0) REQUIRE(c->ctl.advect_vert_coord == 0, "only ADVECT_VERT_COORD 0 runs on the device");
+  if (advect > 0) REQUIRE(c->ctl.advect_vert_coord == 0, "the fused step advects on pressure levels only");
   return A;
 }
 
@@ -632,6 +672,44 @@ static void launch_range(mpb_ctx *c, StepArgs A, int advect, unsigned phys, long
 static void launch_step(mpb_ctx *c, double t, int advect, unsigned phys, unsigned modules) {
   const StepArgs A = step_args(c, t, advect, phys, modules);
   launch_range(c, A, advect, phys, 0, c->np, c->stream);
+}
+
+static LevelArgs level_args(mpb_ctx *c) {
+  const mpb_ctl_t &k = c->ctl;
+  LevelArgs A;
+  A.met = met_view(c);
+  REQUIRE(A.met.npl >= 2, "ADVECT_VERT_COORD 1, 2 and 3 need the model-level fields of both met levels (mpb_met_view_t::pl ...)");
+  A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p(); A.dt = c->dt;
+  A.np = c->np; A.vert_coord = k.advect_vert_coord;
+  A.zq = nullptr;
+  if (k.advect_vert_coord == 1 || k.advect_vert_coord == 3) {
+    const int iq = k.advect_vert_coord == 1 ? k.qnt_zeta : k.qnt_eta;
+    REQUIRE(iq >= 0 && iq < c->nq, "ADVECT_VERT_COORD 1 / 3 need the quantity zeta / eta");
+    A.zq = c->q(iq);
+  }
+  return A;
+}
+
+static void launch_advect_levels(mpb_ctx *c) {
+  if (c->np == 0) return;
+  const LevelArgs A = level_args(c);
+  const unsigned grid = nblocks(c->np, 128);
+  switch (c->ctl.advect) {
+    case 1: advect_levels_kernel<1><<<grid, 128, 0, c->stream>>>(A); break;
+    case 2: advect_levels_kernel<2><<<grid, 128, 0, c->stream>>>(A); break;
+    case 4: advect_levels_kernel<4><<<grid, 128, 0, c->stream>>>(A); break;
+    default: REQUIRE(false, "ADVECT must be 0, 1, 2 or 4");
+  }
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
+static void launch_advect_init(mpb_ctx *c) {   // src/mptrac.c:3762-3785: ADVECT_VERT_COORD 1 only
+  if (c->np == 0 || c->ctl.advect_vert_coord != 1) return;
+  const LevelArgs A = level_args(c);
+  advect_init_kernel<<<nblocks(c->np, 128), 128, 0, c->stream>>>(A);
+  CK(cudaGetLastError());
+  c->launches++;
 }
 
 static void ensure_boxes(mpb_ctx *c) {
@@ -801,7 +879,7 @@ int mpb_destroy(mpb_ctx *c) {
   void *ptrs[] = {c->soa[0], c->soa[1], c->dt, c->uvwp, c->keys[0], c->keys[1], c->perm[0], c->perm[1],
                   c->cub_tmp, c->nodes, c->surf, c->ax_lon, c->ax_lat, c->ax_p, c->ax_lonc, c->ax_latc, c->ax_pc,
                   c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_sum, c->mix_cnt,
-                  c->grid_sum, c->grid_sq, c->grid_cnt};
+                  c->grid_sum, c->grid_sq, c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->stage_h) cudaFreeHost(c->stage_h);
   for (int i = 0; i < kLanes; i++) {
@@ -873,6 +951,7 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
   if (!same_axes) {
     // a new grid invalidates the other level too (src/mptrac.c:6545-6558 demands identical grids)
     c->lev[0].valid = c->lev[1].valid = false;
+    c->lev_valid[0] = c->lev_valid[1] = false;
     c->nx = m->nx; c->ny = m->ny; c->nz = m->np; c->coord_type = m->coord_type;
     if (nnode > c->node_cap) {
       if (c->nodes) CK(cudaFree(c->nodes));
@@ -940,6 +1019,55 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   c->launches += 2;
+
+  // model levels: {pl, ul, vl, wl} and {zetal, ul, vl, zeta_dotl} records plus the {pl, zetal} pairs of the conversions
+  c->lev_valid[slot] = false;
+  if (m->npl >= 2 && m->pl && m->ul && m->vl) {
+    REQUIRE(m->wl || m->zeta_dotl, "model levels need wl or zeta_dotl");
+    const size_t nlev = ncol * (size_t)m->npl;
+    if (m->npl != c->npl || nlev > c->lev_cap) {
+      c->lev_valid[slot ^ 1] = false;
+      for (void *o : {(void *)c->lev_p, (void *)c->lev_z, (void *)c->lev_pz}) if (o) CK(cudaFree(o));
+      c->lev_p = c->lev_z = nullptr; c->lev_pz = nullptr;
+      CK(cudaMalloc(&c->lev_p, sizeof(LevelNode) * nlev));
+      CK(cudaMalloc(&c->lev_z, sizeof(LevelNode) * nlev));
+      CK(cudaMalloc(&c->lev_pz, sizeof(float4) * nlev));
+      CK(cudaMemsetAsync(c->lev_p, 0, sizeof(LevelNode) * nlev, c->stream));
+      CK(cudaMemsetAsync(c->lev_z, 0, sizeof(LevelNode) * nlev, c->stream));
+      CK(cudaMemsetAsync(c->lev_pz, 0, sizeof(float4) * nlev, c->stream));
+      c->lev_cap = nlev; c->npl = m->npl;
+    }
+    if (6 * nlev > c->stage_cap) {
+      CK(cudaFreeHost(c->stage_h)); CK(cudaFree(c->stage_d));
+      c->stage_h = nullptr; c->stage_d = nullptr;
+      CK(cudaMallocHost(&c->stage_h, sizeof(float) * 6 * nlev));
+      CK(cudaMalloc(&c->stage_d, sizeof(float) * 6 * nlev));
+      c->stage_cap = 6 * nlev;
+    }
+    const float *srcl[6] = {m->pl, m->ul, m->vl, m->wl, m->zetal, m->zeta_dotl};
+    const size_t lrow = sizeof(float) * (size_t)m->npl;
+    for (int f = 0; f < 6; f++) {
+      float *dst = c->stage_h + (size_t)f * nlev;
+      if (srcl[f]) {
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int ix = 0; ix < m->nx; ix++)
+          for (int iy = 0; iy < m->ny; iy++)
+            std::memcpy(dst + ((size_t)ix * m->ny + iy) * m->npl, srcl[f] + (size_t)ix * m->sxl + (size_t)iy * m->syl, lrow);
+      } else {
+        std::memset(dst, 0, sizeof(float) * nlev);
+      }
+      CK(cudaMemcpyAsync(c->stage_d + (size_t)f * nlev, dst, sizeof(float) * nlev, cudaMemcpyHostToDevice, c->stream));
+    }
+    float *d = c->stage_d;
+    const unsigned gl = nblocks((long long)nlev, 256);
+    pack_nodes_kernel<<<gl, 256, 0, c->stream>>>(d, d + nlev, d + 2 * nlev, d + 3 * nlev, (float4 *)c->lev_p, slot, nlev);
+    pack_nodes_kernel<<<gl, 256, 0, c->stream>>>(d + 4 * nlev, d + nlev, d + 2 * nlev, d + 5 * nlev, (float4 *)c->lev_z, slot, nlev);
+    pack_surface_kernel<<<gl, 256, 0, c->stream>>>(d, d + 4 * nlev, (float2 *)c->lev_pz, slot, nlev);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    c->launches += 3;
+    c->lev_valid[slot] = true;
+  }
   c->lev[slot].time = m->time;
   c->lev[slot].valid = true;
   API_END
@@ -954,6 +1082,15 @@ int mpb_swap_met(mpb_ctx *c) {
     swap_levels_kernel<<<nblocks((long long)nnode, 256), 256, 0, c->stream>>>((float4 *)c->nodes, nnode, (float2 *)c->surf, ncol);
     CK(cudaGetLastError());
     c->launches++;
+  }
+  std::swap(c->lev_valid[0], c->lev_valid[1]);
+  const size_t nlev = ncol * (size_t)c->npl;
+  if (nlev > 0 && c->lev_p) {
+    const unsigned gl = nblocks((long long)nlev, 256);
+    swap_levels_kernel<<<gl, 256, 0, c->stream>>>((float4 *)c->lev_p, nlev, (float2 *)c->lev_pz, nlev);
+    swap_levels_kernel<<<gl, 256, 0, c->stream>>>((float4 *)c->lev_z, nlev, nullptr, 0);
+    CK(cudaGetLastError());
+    c->launches += 2;
   }
   API_END
 }
@@ -1048,7 +1185,9 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   unsigned modules = 0;
   if (mask & MPB_MOD_POSITION0) modules |= MOD_POS_PRE;
   if (mask & MPB_MOD_POSITION1) modules |= MOD_POS_POST;
-  const bool whole = (mask & 0xff) == 0xff;   // timesteps ... position1 in one launch: dt stays in registers
+  const bool on_levels = advect > 0 && k.advect_vert_coord != 0;   // advection runs as its own launch between two segments
+  const bool whole = (mask & 0xff) == 0xff && !on_levels;   // timesteps ... position1 in one launch: dt stays in registers
+  if ((mask & MPB_MOD_TIMESTEPS) && t == k.t_start) launch_advect_init(c);   // src/mptrac.c:7863-7873
   const bool sort_now = (mask & MPB_MOD_SORT) && k.sort_dt > 0 && hits(t, k.sort_dt);
   if (mask & MPB_MOD_TIMESTEPS) {
     if (sort_now) {
@@ -1064,7 +1203,14 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   } else if (sort_now) {
     do_sort(c);
   }
-  if (modules || advect || phys) launch_step(c, t, advect, phys, modules);
+  if (on_levels) {
+    const unsigned pre = modules & (MOD_TIMESTEPS | MOD_STORE_DT | MOD_POS_PRE), post = modules & MOD_POS_POST;
+    if (pre) launch_step(c, t, 0, 0, pre);
+    launch_advect_levels(c);
+    if (post || phys) launch_step(c, t, 0, phys, post);
+  } else if (modules || advect || phys) {
+    launch_step(c, t, advect, phys, modules);
+  }
   if ((mask & MPB_MOD_METEO) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out)))   // src/mptrac.c:7927-7929
     launch_meteo(c);
   if ((mask & MPB_MOD_MIXING) && k.mixing_trop >= 0 && k.mixing_strat >= 0 &&
@@ -1096,7 +1242,7 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
   const bool sort_now = k.sort_dt > 0 && hits(t, k.sort_dt);
   const bool mix_now = k.mixing_trop >= 0 && k.mixing_strat >= 0 && (k.mixing_dt <= 0 || hits(t, k.mixing_dt)) && k.n_mix_qnt > 0;
   const bool meteo_now = meteo_wanted(k) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out));
-  if (sort_now || mix_now || meteo_now || np < 4 * kHostChunkMin) {
+  if (sort_now || mix_now || meteo_now || k.advect_vert_coord != 0 || np < 4 * kHostChunkMin) {
     // steps with a global phase (cell sort, box means), steps that write quantities (meteo) and tiny problems take the
     // plain sequence
     REQUIRE(mpb_set_atm(c, np, time, p, lon, lat, q, q_stride) == 0, g_err);

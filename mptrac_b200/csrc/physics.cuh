@@ -65,6 +65,11 @@ struct alignas(32) AxisCell {
   double d, rd;   // x[i+1] - x[i] and RN(1 / d): divisions by a grid constant become multiply + 2 FMA (Markstein)
 };
 
+struct alignas(32) LevelNode {
+  float h0, a0, b0, c0;   // time level 0: search coordinate, three fields
+  float h1, a1, b1, c1;   // time level 1
+};
+
 struct MetView {
   const Node *f;          // [nx][ny][nz], z fastest
   const float4 *s;        // [nx][ny] {ps0, pbl0, ps1, pbl1}
@@ -81,6 +86,12 @@ struct MetView {
   int coord_type;         // 0 lon/lat, 1 Cartesian
   int lon_asc, lat_asc, p_asc;
   int local;              // met domain is not global (5999-6012)
+  // model levels (ADVECT_VERT_COORD 1, 2, 3), null when the met data has none.  A LevelNode holds the search coordinate
+  // h and three fields of both time levels: lp {pl, ul, vl, wl} (omega on model levels), lz {zetal, ul, vl, zeta_dotl}
+  // (zeta / eta); pz {pl0, zetal0, pl1, zetal1} serves the two conversions pressure <-> zeta
+  const struct LevelNode *lp, *lz;
+  const float4 *pz;
+  int npl;
 };
 
 struct ClimView {
@@ -260,6 +271,13 @@ MPB_HD double dx2coord(const LonScale &k, double dx) {
 #endif
 }
 MPB_HD double dx2coord(int coord_type, double dx, double lat) { return dx2coord(lon_scale(coord_type, lat), dx); }
+// the same conversions in the reference's own operation order (model-level advection: not tuned)
+MPB_HD double dx2coord_exact(int coord_type, double dx, double lat) {
+  if (coord_type != 0) return dx;
+  if (lat < -89.999 || lat > 89.999) return 0.0;
+  return dx / 1000. * 180. / (kPi * kRE * cos(lat * (kPi / 180.0)));
+}
+MPB_HD double dy2coord_exact(int coord_type, double dy) { return coord_type != 0 ? dy : dy / 1000. * 180. / (kPi * kRE); }
 MPB_HD double dy2coord(int coord_type, double dy) {
   if (coord_type != 0) return dy;
 #if MPB_FAST_QUOT
@@ -749,6 +767,206 @@ MPB_HD void advect(const MetView &g, double dt, Parcel &a, CubeT &c) {
   a.lon += (ORDER == 2) ? dx2coord(g.coord_type, dt * um, lat_stage) : dx2coord(ks, dt * um);
   a.lat += dy2coord(g.coord_type, dt * vm);
   a.p += dt * wm;
+}
+
+// ----------------------------------------------------------------------------------------------
+// interpolation on model levels: intpol_met_4d_zeta (2808-2981), locate_vert (3578-3594), locate_irr_float
+// (3525-3555).  Differences from the pressure-level routines that are part of the contract: weights are those of the
+// UPPER-index node, time is interpolated first (fp32 subtraction, then fp64), and the level is searched on the
+// time- and horizontally interpolated coordinate, walking up from the lowest bracketing level of the 4 columns x 2 times.
+// The level accessors below say where a record keeps its search coordinate (h) and which fields are wanted.
+// ----------------------------------------------------------------------------------------------
+MPB_HD LevelNode load_level(const LevelNode *ptr) {
+#ifdef __CUDA_ARCH__
+  LevelNode n;
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(n.h0), "=f"(n.a0), "=f"(n.b0), "=f"(n.c0), "=f"(n.h1), "=f"(n.a1), "=f"(n.b1), "=f"(n.c1)
+      : "l"(ptr));
+  return n;
+#else
+  return *ptr;
+#endif
+}
+
+struct WindLevels {     // search on LevelNode::h, values a, b, c
+  const LevelNode *f;
+  MPB_HD void heights(size_t i, float &h0, float &h1) const { const LevelNode n = load_level(f + i); h0 = n.h0; h1 = n.h1; }
+  MPB_HD float height(size_t i, int t) const { return t ? ldg(&f[i].h1) : ldg(&f[i].h0); }
+};
+struct PressureOfZeta { // pz records searched on zeta (y, w), value pressure (x, z)
+  const float4 *f;
+  MPB_HD void heights(size_t i, float &h0, float &h1) const { const float4 n = ldg(f + i); h0 = n.y; h1 = n.w; }
+  MPB_HD float height(size_t i, int t) const { return t ? ldg(&f[i].w) : ldg(&f[i].y); }
+  MPB_HD void values(size_t i, float &a0, float &a1) const { const float4 n = ldg(f + i); a0 = n.x; a1 = n.z; }
+};
+struct ZetaOfPressure { // pz records searched on pressure (x, z), value zeta (y, w)
+  const float4 *f;
+  MPB_HD void heights(size_t i, float &h0, float &h1) const { const float4 n = ldg(f + i); h0 = n.x; h1 = n.z; }
+  MPB_HD float height(size_t i, int t) const { return t ? ldg(&f[i].z) : ldg(&f[i].x); }
+  MPB_HD void values(size_t i, float &a0, float &a1) const { const float4 n = ldg(f + i); a0 = n.y; a1 = n.w; }
+};
+
+struct LevelStencil {
+  size_t col[4];          // first record of the columns (ix,iy), (ix,iy+1), (ix+1,iy), (ix+1,iy+1)
+  int iz;
+  double wx, wy, wz, wt;  // weights of the upper-index node / of time level 1
+};
+
+// t * (v1 - v0) + v0 with the difference taken in fp32 (2870-2873)
+MPB_HD double time_lerp_f32(double wt, float v0, float v1) { return wt * (double)f_sub(v1, v0) + (double)v0; }
+MPB_HD double up_lerp(double w, double lo, double hi) { return w * (hi - lo) + lo; }
+
+// locate_irr_float on one time level of one column, starting from the guess ig (3525-3555)
+template <class L>
+MPB_HD int locate_level(const L &lv, size_t col, int n, int t, double x, int ig) {
+  const float g0 = lv.height(col + ig, t), g1 = lv.height(col + ig + 1, t);
+  if ((g0 <= x && x < g1) || (g0 >= x && x > g1)) return ig;
+  int lo = 0, hi = n - 1, i = (hi + lo) >> 1;
+  if (lv.height(col + i, t) < lv.height(col + i + 1, t)) {
+    while (hi > lo + 1) { i = (hi + lo) >> 1; if (lv.height(col + i, t) > x) hi = i; else lo = i; }
+  } else {
+    while (hi > lo + 1) { i = (hi + lo) >> 1; if (lv.height(col + i, t) <= x) hi = i; else lo = i; }
+  }
+  return lo;
+}
+
+// search coordinate at level k: time first, then latitude, then longitude (2866-2889)
+template <class L>
+MPB_HD double level_height(const L &lv, const LevelStencil &s, int k) {
+  float a0, a1, b0, b1, c0, c1, d0, d1;
+  lv.heights(s.col[0] + k, a0, a1); lv.heights(s.col[1] + k, b0, b1);
+  lv.heights(s.col[2] + k, c0, c1); lv.heights(s.col[3] + k, d0, d1);
+  const double h00 = time_lerp_f32(s.wt, a0, a1), h01 = time_lerp_f32(s.wt, b0, b1);
+  const double h10 = time_lerp_f32(s.wt, c0, c1), h11 = time_lerp_f32(s.wt, d0, d1);
+  return up_lerp(s.wx, up_lerp(s.wy, h00, h01), up_lerp(s.wy, h10, h11));
+}
+
+template <class L>
+MPB_HD void locate_on_levels(const MetView &g, const L &lv, double ts, double height, double lon, double lat, LevelStencil &s) {
+  double lon2, lat2;
+  clamp_horizontal(g, lon, lat, lon2, lat2);
+  const int ix = lon_interval(g, lon2);
+  AxisCell cy;
+  const int iy = locate_cell(g.lat, g.latc, g.ny, g.lat_asc, lat2, lat_guess(g, lat2), cy);
+  const size_t npl = (size_t)g.npl, sx = (size_t)g.ny * npl;
+  s.col[0] = (size_t)ix * sx + (size_t)iy * npl;
+  s.col[1] = s.col[0] + npl;
+  s.col[2] = s.col[0] + sx;
+  s.col[3] = s.col[2] + npl;
+  // locate_vert: columns in the order (ix,iy), (ix+1,iy), (ix,iy+1), (ix+1,iy+1), each from the previous answer
+  int kmin = 0, kmax = 0;
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    int k = locate_level(lv, s.col[0], g.npl, t, height, 0);
+    int lo = k, hi = k;
+    k = locate_level(lv, s.col[2], g.npl, t, height, k); lo = k < lo ? k : lo; hi = k > hi ? k : hi;
+    k = locate_level(lv, s.col[1], g.npl, t, height, k); lo = k < lo ? k : lo; hi = k > hi ? k : hi;
+    k = locate_level(lv, s.col[3], g.npl, t, height, k); lo = k < lo ? k : lo; hi = k > hi ? k : hi;
+    if (t == 0) { kmin = lo; kmax = hi; } else { kmin = lo < kmin ? lo : kmin; kmax = hi > kmax ? hi : kmax; }
+  }
+  s.iz = kmin;
+  s.wt = (ts - g.t0) / (g.t1 - g.t0);
+  const AxisCell cx = load_cell(g.lonc + ix);
+  s.wx = (lon2 - cx.lo) / (cx.hi - cx.lo);
+  s.wy = (lat2 - cy.lo) / (cy.hi - cy.lo);
+  double bot = level_height(lv, s, s.iz), top = level_height(lv, s, s.iz + 1);
+  const float f0 = lv.height(0, 0), f1 = lv.height(1, 0);          // heights0[0][0][0] vs [0][0][1], 2914-2921
+  const bool desc = f0 > f1, asc = f0 < f1;
+  while ((desc && ((bot <= height) || (top > height)) && (bot >= height) && (s.iz < kmax)) ||
+         (asc && ((bot >= height) || (top < height)) && (bot <= height) && (s.iz < kmax))) {
+    s.iz++;
+    bot = top;
+    top = level_height(lv, s, s.iz + 1);
+  }
+  s.wz = (height - bot) / (top - bot);
+}
+
+// one field at the 8 corners: time, then longitude, then latitude, then level (2941-2980)
+MPB_HD double combine_levels(const LevelStencil &s, const double v[2][2][2] /* [x][y][k] */) {
+  const double b00 = up_lerp(s.wx, v[0][0][0], v[1][0][0]), b10 = up_lerp(s.wx, v[0][1][0], v[1][1][0]);
+  const double b01 = up_lerp(s.wx, v[0][0][1], v[1][0][1]), b11 = up_lerp(s.wx, v[0][1][1], v[1][1][1]);
+  return up_lerp(s.wz, up_lerp(s.wy, b00, b10), up_lerp(s.wy, b01, b11));
+}
+
+// u, v and the vertical velocity on model levels: three intpol_met_4d_zeta calls sharing one stencil (3646-3657, 3714-3722)
+MPB_HD void wind_on_levels(const MetView &g, const LevelNode *f, double ts, double height, double lon, double lat,
+                           double &u, double &v, double &w) {
+  const WindLevels lv = {f};
+  LevelStencil s;
+  locate_on_levels(g, lv, ts, height, lon, lat, s);
+  double a[2][2][2], b[2][2][2], c[2][2][2];
+  const int cx[4] = {0, 0, 1, 1}, cy[4] = {0, 1, 0, 1};
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const LevelNode n = load_level(f + s.col[j] + s.iz + k);
+      a[cx[j]][cy[j]][k] = time_lerp_f32(s.wt, n.a0, n.a1);
+      b[cx[j]][cy[j]][k] = time_lerp_f32(s.wt, n.b0, n.b1);
+      c[cx[j]][cy[j]][k] = time_lerp_f32(s.wt, n.c0, n.c1);
+    }
+  u = combine_levels(s, a); v = combine_levels(s, b); w = combine_levels(s, c);
+}
+
+// the conversions pressure <-> zeta (3690-3695, 3750-3755, 3779-3782)
+template <class L>
+MPB_HD double convert_on_levels(const MetView &g, const L &lv, double ts, double height, double lon, double lat) {
+  LevelStencil s;
+  locate_on_levels(g, lv, ts, height, lon, lat, s);
+  double a[2][2][2];
+  const int cx[4] = {0, 0, 1, 1}, cy[4] = {0, 1, 0, 1};
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      float a0, a1;
+      lv.values(s.col[j] + s.iz + k, a0, a1);
+      a[cx[j]][cy[j]][k] = time_lerp_f32(s.wt, a0, a1);
+    }
+  return combine_levels(s, a);
+}
+MPB_HD double zeta_of_pressure(const MetView &g, double ts, double p, double lon, double lat) {
+  return convert_on_levels(g, ZetaOfPressure{g.pz}, ts, p, lon, lat);
+}
+MPB_HD double pressure_of_zeta(const MetView &g, double ts, double zeta, double lon, double lat) {
+  return convert_on_levels(g, PressureOfZeta{g.pz}, ts, zeta, lon, lat);
+}
+
+// module_advect with a model-level vertical coordinate: VERT_COORD 2 (omega on model levels, the parcel's vertical
+// coordinate is its pressure) and 1 / 3 (zeta / eta, kept in the quantity `zq`)
+template <int ORDER>
+MPB_HD void advect_on_levels(const MetView &g, int vert_coord, double dt, Parcel &a, double *zq) {
+  const LevelNode *f = vert_coord == 2 ? g.lp : g.lz;
+  if (zq) *zq = zeta_of_pressure(g, a.time, a.p, a.lon, a.lat);
+  const double z0 = zq ? *zq : a.p;
+  double um = 0, vm = 0, wm = 0, u = 0, v = 0, w = 0, lat_stage = a.lat;
+#pragma unroll
+  for (int i = 0; i < ORDER; i++) {
+    double x, y, z, dts;
+    if (i == 0) {
+      dts = 0.0; x = a.lon; y = a.lat; z = z0;
+    } else {
+      dts = (i == 3 ? 1.0 : 0.5) * dt;
+      x = a.lon + dx2coord_exact(g.coord_type, dts * u, a.lat);
+      y = a.lat + dy2coord_exact(g.coord_type, dts * v);
+      z = z0 + dts * w;
+    }
+    lat_stage = y;
+    wind_on_levels(g, f, a.time + dts, z, x, y, u, v, w);
+    double k = 1.0;
+    if (ORDER == 2) k = (i == 0 ? 0.0 : 1.0);
+    else if (ORDER == 4) k = (i == 0 || i == 3 ? 1.0 / 6.0 : 2.0 / 6.0);
+    um += k * u; vm += k * v; wm += k * w;
+  }
+  a.time += dt;
+  a.lon += dx2coord_exact(g.coord_type, dt * um, ORDER == 2 ? lat_stage : a.lat);
+  a.lat += dy2coord_exact(g.coord_type, dt * vm);
+  if (zq) {
+    *zq = z0 + dt * wm;
+    a.p = pressure_of_zeta(g, a.time, *zq, a.lon, a.lat);
+  } else {
+    a.p = z0 + dt * wm;
+  }
 }
 
 // ----------------------------------------------------------------------------------------------

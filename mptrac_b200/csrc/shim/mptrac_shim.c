@@ -51,6 +51,8 @@ static void ensure_ctx(const ctl_t *ctl, int np) {
   if (verbose()) printf("mptrac_b200: device context for %d parcels, %d quantities on GPU %d\n", np, ctl->nq, dev);
 }
 
+static int g_levels;   /* the control file advects on model levels: the met uploads carry pl, ul, vl, wl, zetal, zeta_dotl */
+
 static void put_ctl(const ctl_t *c) {
   mpb_ctl_t k;
   memset(&k, 0, sizeof(k));
@@ -80,6 +82,8 @@ static void put_ctl(const ctl_t *c) {
   k.qnt_meteo[MPB_Q_V] = c->qnt_v; k.qnt_meteo[MPB_Q_W] = c->qnt_w; k.qnt_meteo[MPB_Q_VH] = c->qnt_vh;
   k.qnt_meteo[MPB_Q_VZ] = c->qnt_vz; k.qnt_meteo[MPB_Q_THETA] = c->qnt_theta; k.qnt_meteo[MPB_Q_PSAT] = c->qnt_psat;
   k.qnt_meteo[MPB_Q_PSICE] = c->qnt_psice; k.qnt_meteo[MPB_Q_ZETA_D] = c->qnt_zeta_d;
+  k.qnt_zeta = c->qnt_zeta; k.qnt_eta = c->qnt_eta;
+  g_levels = c->advect_vert_coord != 0;
   MPB(mpb_set_ctl(g_ctx, &k));
 }
 
@@ -109,6 +113,13 @@ static void put_met(met_t *m) {
   v.u = &m->u[0][0][0]; v.v = &m->v[0][0][0]; v.w = &m->w[0][0][0]; v.t = &m->t[0][0][0];
   v.ps = &m->ps[0][0]; v.pbl = &m->pbl[0][0];
   v.sx = (int64_t) EY * EP; v.sy = EP; v.sx2 = EY;
+  v.npl = 0; v._pad = 0; v.pl = v.ul = v.vl = v.wl = v.zetal = v.zeta_dotl = NULL;
+  v.sxl = (int64_t) EY * EP; v.syl = EP;
+  if (g_levels) {
+    v.npl = m->npl;
+    v.pl = &m->pl[0][0][0]; v.ul = &m->ul[0][0][0]; v.vl = &m->vl[0][0][0]; v.wl = &m->wl[0][0][0];
+    v.zetal = &m->zetal[0][0][0]; v.zeta_dotl = &m->zeta_dotl[0][0][0];
+  }
   MPB(mpb_set_met(g_ctx, s, &v));
   g_slot[s] = m;
   if (verbose()) printf("mptrac_b200: met level t=%.0f (%d x %d x %d) -> device slot %d\n", m->time, m->nx, m->ny, m->np, s);
@@ -220,8 +231,8 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
                          depo_t *depo, double t, dd_t *dd) {
   (void) dd;
   if (!g_ctx) ERRMSG("mptrac_b200: mptrac_run_timestep before mptrac_init / mptrac_update_device");
-  if (ctl->advect_vert_coord != 0 || ctl->rng_type != 1)
-    ERRMSG("mptrac_b200: only ADVECT_VERT_COORD 0 and RNG_TYPE 1 run on the device");
+  if (ctl->rng_type != 1)
+    ERRMSG("mptrac_b200: only RNG_TYPE 1 runs on the device");
   SELECT_TIMER("MODULE_B200_STEP", "PHYSICS");
   align_met(*met0, *met1);
   int host_dirty = 0;

@@ -46,7 +46,7 @@ class _CtlStruct(C.Structure):
             "turb_mesox", "turb_mesoz", "turb_pbl_trans",
             "mixing_dt", "mixing_trop", "mixing_strat",
             "mixing_lon0", "mixing_lon1", "mixing_lat0", "mixing_lat1", "mixing_z0", "mixing_z1", "met_dt_out")]
-        + [("qnt_meteo", C.c_int32 * METEO_SLOTS)]
+        + [("qnt_meteo", C.c_int32 * METEO_SLOTS), ("qnt_zeta", C.c_int32), ("qnt_eta", C.c_int32)]
     )
 
 
@@ -58,6 +58,10 @@ class _MetViewStruct(C.Structure):
         ("u", C.c_void_p), ("v", C.c_void_p), ("w", C.c_void_p), ("t", C.c_void_p),
         ("ps", C.c_void_p), ("pbl", C.c_void_p),
         ("sx", C.c_int64), ("sy", C.c_int64), ("sx2", C.c_int64),
+        ("npl", C.c_int32), ("_pad", C.c_int32),
+        ("pl", C.c_void_p), ("ul", C.c_void_p), ("vl", C.c_void_p), ("wl", C.c_void_p),
+        ("zetal", C.c_void_p), ("zeta_dotl", C.c_void_p),
+        ("sxl", C.c_int64), ("syl", C.c_int64),
     ]
 
 
@@ -110,6 +114,8 @@ class Ctl:
     mixing_z0: float = -5.0
     mixing_z1: float = 85.0
     met_dt_out: float = 0.0                                   # module_meteo off (NB the reference's default is 0.1 = every step)
+    qnt_zeta: int = -1                                        # quantity holding zeta (ADVECT_VERT_COORD 1)
+    qnt_eta: int = -1                                         # quantity holding eta (ADVECT_VERT_COORD 3)
     qnt_meteo: Dict[str, int] = field(default_factory=dict)   # quantity name (METEO_QNT) -> index, e.g. {"t": 0, "u": 1}
 
     def to_struct(self) -> _CtlStruct:
@@ -146,6 +152,13 @@ class Met:
     ps: Optional[np.ndarray] = None
     pbl: Optional[np.ndarray] = None
     coord_type: int = 0
+    # model-level fields [nx][ny][npl] (ADVECT_VERT_COORD 1, 2, 3): pressure, winds, omega, zeta (or eta) and its tendency
+    pl: Optional[np.ndarray] = None
+    ul: Optional[np.ndarray] = None
+    vl: Optional[np.ndarray] = None
+    wl: Optional[np.ndarray] = None
+    zetal: Optional[np.ndarray] = None
+    zeta_dotl: Optional[np.ndarray] = None
 
     def __post_init__(self):
         self.lon = np.ascontiguousarray(self.lon, dtype=np.float64)
@@ -166,6 +179,15 @@ class Met:
                 if a.shape != shp3[:2]:
                     raise ValueError(f"met field {n} has shape {a.shape}, expected {shp3[:2]}")
                 setattr(self, n, a)
+        npl = None
+        for n in ("pl", "ul", "vl", "wl", "zetal", "zeta_dotl"):
+            a = getattr(self, n)
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                npl = a.shape[2] if npl is None else npl
+                if a.ndim != 3 or a.shape != (shp3[0], shp3[1], npl):
+                    raise ValueError(f"model-level field {n} has shape {a.shape}, expected {(shp3[0], shp3[1], npl)}")
+                setattr(self, n, a)
 
     def view(self) -> _MetViewStruct:
         nx, ny, nz = self.lon.size, self.lat.size, self.p.size
@@ -176,6 +198,12 @@ class Met:
             a = getattr(self, n)
             setattr(s, n, a.ctypes.data if a is not None else None)
         s.sx, s.sy, s.sx2 = ny * nz, nz, ny
+        npl = 0
+        for n in ("pl", "ul", "vl", "wl", "zetal", "zeta_dotl"):
+            a = getattr(self, n)
+            setattr(s, n, a.ctypes.data if a is not None else None)
+            npl = a.shape[2] if a is not None else npl
+        s.npl, s.sxl, s.syl = npl, ny * npl, npl
         return s
 
 

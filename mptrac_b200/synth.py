@@ -81,3 +81,34 @@ def make_clim_tropo():
     season = np.cos(2 * np.pi * (time[:, None] / (365.25 * 86400.0)))
     tropo = 300.0 - 200.0 * np.exp(-(lat[None, :] / 35.0) ** 2) + 15.0 * season * np.sin(np.deg2rad(lat))[None, :]
     return time, lat, np.ascontiguousarray(tropo)
+
+
+def add_model_levels(met: Met, npl=None, seed=7) -> Met:
+    """Model-level fields for ADVECT_VERT_COORD 1 / 2 / 3 on the grid of ``met``: level pressures that undulate with the
+    surface (hybrid-coordinate like, decreasing with the level index), winds and omega sampled from the pressure-level
+    fields plus small-scale structure, a zeta coordinate that increases with height and its tendency."""
+    nx, ny, nz = met.u.shape
+    npl = npl or nz
+    rng = np.random.default_rng(seed)
+    lam = np.deg2rad(met.lon)[:, None, None]
+    phi = np.deg2rad(met.lat)[None, :, None]
+    k = np.arange(npl)[None, None, :]
+    zlev = 60.0 * (k + 0.3) / npl                                   # km
+    bump = 1.0 + 0.04 * np.sin(2 * lam + 0.3 * met.time / 21600.0) * np.cos(phi) * np.exp(-zlev / 8.0)
+    pl = (P0 * np.exp(-zlev / H0) * bump).astype(np.float32)
+    jet = np.exp(-((zlev - 11.0) / 6.0) ** 2)
+    ul = ((10.0 + 35.0 * jet) * np.cos(phi) * (1.0 + 0.3 * np.sin(3 * lam)) + 5.0 * np.sin(2 * phi)).astype(np.float32)
+    vl = (8.0 * np.cos(phi) * np.sin(2 * lam) * (0.3 + jet)).astype(np.float32)
+    wl = (0.02 * np.sin(lam) * np.cos(2 * phi) * np.sin(np.pi * zlev / 60.0) * (pl / P0 + 0.05)).astype(np.float32)
+    ul = ul + 0.5 * rng.standard_normal(ul.shape, dtype=np.float32)
+    vl = vl + 0.5 * rng.standard_normal(vl.shape, dtype=np.float32)
+    zetal = (250.0 + 30.0 * zlev * (1.0 + 0.02 * np.cos(lam) * np.cos(phi))).astype(np.float32)      # K, increasing upward
+    zeta_dotl = (2e-4 * np.cos(2 * lam) * np.cos(phi) * np.sin(np.pi * zlev / 60.0)
+                 * np.ones_like(zetal)).astype(np.float32)                                           # K / s
+    out = []
+    for a in (pl, ul, vl, wl, zetal, zeta_dotl):
+        a = np.ascontiguousarray(np.broadcast_to(a, (nx, ny, npl))).copy()
+        a[-1] = a[0]                     # periodic wrap column
+        out.append(a)
+    from dataclasses import replace
+    return replace(met, pl=out[0], ul=out[1], vl=out[2], wl=out[3], zetal=out[4], zeta_dotl=out[5])

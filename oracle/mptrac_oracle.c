@@ -245,7 +245,160 @@ void orc_module_position(const orc_met_t *met0, const orc_met_t *met1, orc_atm_t
 /* ---------------------------------------------------------------------------------------------
  * module_advect, pressure-level branch, 3612-3677
  * ------------------------------------------------------------------------------------------- */
+/* ---------------------------------------------------------------------------------------------
+ * interpolation on model levels: intpol_met_4d_zeta 2808-2981, locate_vert 3578-3594,
+ * locate_irr_float 3525-3555.  NB the weight convention differs from the pressure-level routines
+ * (weight of the UPPER-index node), and time is interpolated FIRST.
+ * ------------------------------------------------------------------------------------------- */
+static size_t atl(const orc_met_t *m, int ix, int iy, int k) {
+  return ((size_t)ix * (size_t)m->ny + (size_t)iy) * (size_t)m->npl + (size_t)k;
+}
+
+static int bisect_float(const float *xx, int n, double x, int ig) {
+  int lo = 0, hi = n - 1, i = (hi + lo) >> 1;
+  if ((xx[ig] <= x && x < xx[ig + 1]) || (xx[ig] >= x && x > xx[ig + 1])) return ig;
+  if (xx[i] < xx[i + 1]) {
+    while (hi > lo + 1) { i = (hi + lo) >> 1; if (xx[i] > x) hi = i; else lo = i; }
+  } else {
+    while (hi > lo + 1) { i = (hi + lo) >> 1; if (xx[i] <= x) hi = i; else lo = i; }
+  }
+  return lo;
+}
+
+typedef struct {
+  int ix, iy, iz;            /* ci[0], ci[1], ci[2] */
+  double wx, wy, wz, wt;     /* cw[0], cw[1], cw[2], cw[3] */
+} zcell_t;
+
+/* time-then-bilinear value of a model-level field at level k of the column quartet (the "height_bot/top" blocks) */
+static double level_value(const orc_met_t *m, const float *f0, const float *f1, const zcell_t *c, int k) {
+  const double v00 = c->wt * (f1[atl(m, c->ix, c->iy, k)] - f0[atl(m, c->ix, c->iy, k)]) + f0[atl(m, c->ix, c->iy, k)];
+  const double v01 = c->wt * (f1[atl(m, c->ix, c->iy + 1, k)] - f0[atl(m, c->ix, c->iy + 1, k)]) + f0[atl(m, c->ix, c->iy + 1, k)];
+  const double v10 = c->wt * (f1[atl(m, c->ix + 1, c->iy, k)] - f0[atl(m, c->ix + 1, c->iy, k)]) + f0[atl(m, c->ix + 1, c->iy, k)];
+  const double v11 = c->wt * (f1[atl(m, c->ix + 1, c->iy + 1, k)] - f0[atl(m, c->ix + 1, c->iy + 1, k)]) + f0[atl(m, c->ix + 1, c->iy + 1, k)];
+  const double a0 = c->wy * (v01 - v00) + v00;
+  const double a1 = c->wy * (v11 - v10) + v10;
+  return c->wx * (a1 - a0) + a0;
+}
+
+/* the init part: 2825-2938 */
+static void zeta_locate(const orc_met_t *m0, const float *h0, const orc_met_t *m1, const float *h1, double ts, double height,
+                        double lon, double lat, zcell_t *c) {
+  double lon2, lat2;
+  horizontal_check(m0, lon, lat, &lon2, &lat2);
+  c->ix = regular_index(m0->lon, m0->nx, lon2);
+  c->iy = bisect(m0->lat, m0->ny, lat2);
+  int ind[2][4];
+  const float *hh[2] = {h0, h1};
+  const int npl[2] = {m0->npl, m1->npl};
+  for (int t = 0; t < 2; t++) {   /* locate_vert: each column starts from the previous column's answer */
+    ind[t][0] = bisect_float(hh[t] + atl(m0, c->ix, c->iy, 0), npl[t], height, 0);
+    ind[t][1] = bisect_float(hh[t] + atl(m0, c->ix + 1, c->iy, 0), npl[t], height, ind[t][0]);
+    ind[t][2] = bisect_float(hh[t] + atl(m0, c->ix, c->iy + 1, 0), npl[t], height, ind[t][1]);
+    ind[t][3] = bisect_float(hh[t] + atl(m0, c->ix + 1, c->iy + 1, 0), npl[t], height, ind[t][2]);
+  }
+  c->iz = ind[0][0];
+  int k_max = ind[0][0];
+  for (int t = 0; t < 2; t++)
+    for (int j = 0; j < 4; j++) {
+      if (c->iz > ind[t][j]) c->iz = ind[t][j];
+      if (k_max < ind[t][j]) k_max = ind[t][j];
+    }
+  c->wt = (ts - m0->time) / (m1->time - m0->time);
+  c->wx = (lon2 - m0->lon[c->ix]) / (m0->lon[c->ix + 1] - m0->lon[c->ix]);
+  c->wy = (lat2 - m0->lat[c->iy]) / (m0->lat[c->iy + 1] - m0->lat[c->iy]);
+  double bot = level_value(m0, h0, h1, c, c->iz), top = level_value(m0, h0, h1, c, c->iz + 1);
+  const int descending = h0[0] > h0[1], ascending = h0[0] < h0[1];   /* heights0[0][0][0] vs [0][0][1], 2914-2921 */
+  while ((descending && ((bot <= height) || (top > height)) && (bot >= height) && (c->iz < k_max)) ||
+         (ascending && ((bot >= height) || (top < height)) && (bot <= height) && (c->iz < k_max))) {
+    c->iz++;
+    bot = top;
+    top = level_value(m0, h0, h1, c, c->iz + 1);
+  }
+  c->wz = (height - bot) / (top - bot);
+}
+
+/* the value part: 2941-2980 (time first, then lon, lat, level) */
+static double zeta_value(const orc_met_t *m, const float *a0, const float *a1, const zcell_t *c) {
+#define TV(dx, dy, dk) (c->wt * (a1[atl(m, c->ix + dx, c->iy + dy, c->iz + dk)] - a0[atl(m, c->ix + dx, c->iy + dy, c->iz + dk)]) \
+                        + a0[atl(m, c->ix + dx, c->iy + dy, c->iz + dk)])
+  const double v000 = TV(0, 0, 0), v100 = TV(1, 0, 0), v010 = TV(0, 1, 0), v110 = TV(1, 1, 0);
+  const double v001 = TV(0, 0, 1), v101 = TV(1, 0, 1), v011 = TV(0, 1, 1), v111 = TV(1, 1, 1);
+#undef TV
+  const double b00 = c->wx * (v100 - v000) + v000, b10 = c->wx * (v110 - v010) + v010;
+  const double b01 = c->wx * (v101 - v001) + v001, b11 = c->wx * (v111 - v011) + v011;
+  const double e0 = c->wy * (b10 - b00) + b00, e1 = c->wy * (b11 - b01) + b01;
+  return c->wz * (e1 - e0) + e0;
+}
+
+void orc_intpol_met_4d_zeta(const orc_met_t *met0, const float *h0, const float *a0, const orc_met_t *met1, const float *h1,
+                            const float *a1, double ts, double height, double lon, double lat, double *var) {
+  zcell_t c;
+  zeta_locate(met0, h0, met1, h1, ts, height, lon, lat, &c);
+  *var = zeta_value(met0, a0, a1, &c);
+}
+
+/* module_advect_init, 3762-3785: pressure consistent with zeta (ADVECT_VERT_COORD 1 only, every parcel) */
+void orc_module_advect_init(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm) {
+  if (ctl->advect_vert_coord != 1) return;
+  double *zeta = atm->q + (size_t)ctl->qnt_zeta * (size_t)atm->q_stride;
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++)
+    orc_intpol_met_4d_zeta(met0, met0->zetal, met0->pl, met1, met1->zetal, met1->pl, atm->time[ip], zeta[ip], atm->lon[ip],
+                           atm->lat[ip], &atm->p[ip]);
+}
+
+/* module_advect with the vertical velocity of a model-level coordinate: branch A with ADVECT_VERT_COORD 2 (3646-3657: omega on
+ * model levels, heights = pl) and branch B (3680-3757: zeta / eta, the parcel's coordinate lives in a quantity) */
+static void advect_model_levels(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm) {
+  const int n = ctl->advect, ct = met0->coord_type, vc = ctl->advect_vert_coord;
+  const float *h0 = vc == 2 ? met0->pl : met0->zetal, *h1 = vc == 2 ? met1->pl : met1->zetal;
+  const float *w0 = vc == 2 ? met0->wl : met0->zeta_dotl, *w1 = vc == 2 ? met1->wl : met1->zeta_dotl;
+  double *zq = vc == 2 ? NULL : atm->q + (size_t)(vc == 1 ? ctl->qnt_zeta : ctl->qnt_eta) * (size_t)atm->q_stride;
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    const double dt = atm->dt[ip];
+    if (dt == 0) continue;
+    const double lon0 = atm->lon[ip], lat0 = atm->lat[ip], t0 = atm->time[ip];
+    if (zq)   /* pressure -> zeta / eta, 3690-3695 */
+      orc_intpol_met_4d_zeta(met0, met0->pl, met0->zetal, met1, met1->pl, met1->zetal, t0, atm->p[ip], lon0, lat0, &zq[ip]);
+    const double z0 = zq ? zq[ip] : atm->p[ip];
+    double u[4], v[4], w[4], um = 0, vm = 0, wm = 0, pos[3] = {0, 0, 0};
+    for (int i = 0; i < n; i++) {
+      double dts = 0.0;
+      if (i == 0) {
+        pos[0] = lon0; pos[1] = lat0; pos[2] = z0;
+      } else {
+        dts = (i == 3 ? 1.0 : 0.5) * dt;
+        pos[0] = lon0 + east_m_to_coord(ct, dts * u[i - 1], lat0);
+        pos[1] = lat0 + north_m_to_coord(ct, dts * v[i - 1]);
+        pos[2] = z0 + dts * w[i - 1];
+      }
+      zcell_t c;
+      zeta_locate(met0, h0, met1, h1, t0 + dts, pos[2], pos[0], pos[1], &c);
+      u[i] = zeta_value(met0, met0->ul, met1->ul, &c);
+      v[i] = zeta_value(met0, met0->vl, met1->vl, &c);
+      w[i] = zeta_value(met0, w0, w1, &c);
+      double k = 1.0;
+      if (n == 2) k = (i == 0 ? 0.0 : 1.0);
+      else if (n == 4) k = (i == 0 || i == 3 ? 1.0 / 6.0 : 2.0 / 6.0);
+      um += k * u[i]; vm += k * v[i]; wm += k * w[i];
+    }
+    atm->time[ip] = t0 + dt;
+    atm->lon[ip] = lon0 + east_m_to_coord(ct, dt * um, n == 2 ? pos[1] : lat0);
+    atm->lat[ip] = lat0 + north_m_to_coord(ct, dt * vm);
+    if (zq) {   /* 3746-3755 */
+      zq[ip] = z0 + dt * wm;
+      orc_intpol_met_4d_zeta(met0, met0->zetal, met0->pl, met1, met1->zetal, met1->pl, atm->time[ip], zq[ip], atm->lon[ip],
+                             atm->lat[ip], &atm->p[ip]);
+    } else {
+      atm->p[ip] = z0 + dt * wm;
+    }
+  }
+}
+
 void orc_module_advect(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm) {
+  if (ctl->advect_vert_coord != 0) { advect_model_levels(ctl, met0, met1, atm); return; }
   const int n = ctl->advect, ct = met0->coord_type;
 #pragma omp parallel for
   for (int64_t ip = 0; ip < atm->np; ip++) {
@@ -630,6 +783,7 @@ void orc_module_meteo(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met
 
 void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_met_t *met0,
                       const orc_met_t *met1, orc_atm_t *atm, double t, uint64_t *ctr) {
+  if (t == ctl->t_start) orc_module_advect_init(ctl, met0, met1, atm);   /* 7863-7873 */
   orc_module_timesteps(ctl, met0, atm, t);
   if (ctl->sort_dt > 0 && fmod(t, ctl->sort_dt) == 0) orc_module_sort(ctl, met0, atm);
   orc_module_position(met0, met1, atm);

@@ -38,6 +38,7 @@ typedef struct {
   double mixing_lon0, mixing_lon1, mixing_lat0, mixing_lat1, mixing_z0, mixing_z1;
   double met_dt_out;
   int32_t qnt_meteo[ORC_METEO_SLOTS];   /* quantity index or -1 */
+  int32_t qnt_zeta, qnt_eta;            /* vertical coordinate quantity of ADVECT_VERT_COORD 1 / 3, or -1 */
 } orc_ctl_t;
 
 /* one met time level, dense: 3-D [nx][ny][np] (z fastest), 2-D [nx][ny] */
@@ -46,6 +47,9 @@ typedef struct {
   int32_t coord_type, nx, ny, np;
   const double *lon, *lat, *p;
   const float *u, *v, *w, *t, *ps, *pbl;
+  /* model-level fields (ADVECT_VERT_COORD 1, 2, 3), dense [nx][ny][npl]; NULL when absent */
+  int32_t npl;
+  const float *pl, *ul, *vl, *wl, *zetal, *zeta_dotl;
 } orc_met_t;
 
 typedef struct {
@@ -67,6 +71,9 @@ typedef struct {
 void orc_module_timesteps(const orc_ctl_t *ctl, const orc_met_t *met0, orc_atm_t *atm, double t);
 void orc_module_position(const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
 void orc_module_advect(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
+void orc_module_advect_init(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
+void orc_intpol_met_4d_zeta(const orc_met_t *met0, const float *h0, const float *a0, const orc_met_t *met1, const float *h1,
+                            const float *a1, double ts, double height, double lon, double lat, double *var);
 void orc_module_rng(double *rs, int64_t n, int method, uint64_t *ctr);
 void orc_module_diff_turb(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_met_t *met0,
                           const orc_met_t *met1, orc_atm_t *atm, uint64_t *ctr);

@@ -32,12 +32,17 @@ METEO_SLOTS = 16
 
 class OrcCtl(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in _INT_FIELDS] + [("mix_qnt", C.c_int32 * MIX_MAXQ), ("_pad", C.c_int32)]
-                + [(n, C.c_double) for n in _DBL_FIELDS] + [("qnt_meteo", C.c_int32 * METEO_SLOTS)])
+                + [(n, C.c_double) for n in _DBL_FIELDS] + [("qnt_meteo", C.c_int32 * METEO_SLOTS)]
+                + [("qnt_zeta", C.c_int32), ("qnt_eta", C.c_int32)])
+
+
+_LEVEL_FIELDS = ("pl", "ul", "vl", "wl", "zetal", "zeta_dotl")   # model-level fields, [nx][ny][npl]
 
 
 class OrcMet(C.Structure):
     _fields_ = [("time", C.c_double), ("coord_type", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("np", C.c_int32)] + [
-        (n, C.c_void_p) for n in ("lon", "lat", "p", "u", "v", "w", "t", "ps", "pbl")]
+        (n, C.c_void_p) for n in ("lon", "lat", "p", "u", "v", "w", "t", "ps", "pbl")] + [("npl", C.c_int32)] + [
+        (n, C.c_void_p) for n in _LEVEL_FIELDS]
 
 
 class OrcClim(C.Structure):
@@ -68,6 +73,11 @@ def ctl_struct(ctl) -> OrcCtl:
         qm = {}
     for i in range(METEO_SLOTS):
         s.qnt_meteo[i] = int(qm.get(METEO_QNT[i], -1)) if i < len(METEO_QNT) else -1
+    for n in ("qnt_zeta", "qnt_eta"):
+        try:
+            setattr(s, n, int(get(n)))
+        except (KeyError, AttributeError):
+            setattr(s, n, -1)
     return s
 
 
@@ -79,6 +89,12 @@ def met_struct(met):
     for n in ("lon", "lat", "p", "u", "v", "w", "t", "ps", "pbl"):
         a = getattr(met, n)
         setattr(s, n, a.ctypes.data if a is not None else None)
+    s.npl = 0
+    for n in _LEVEL_FIELDS:
+        a = getattr(met, n, None)
+        setattr(s, n, a.ctypes.data if a is not None else None)
+        if a is not None:
+            s.npl = a.shape[2]
     return s
 
 
@@ -148,6 +164,8 @@ class Oracle:
         L.orc_module_sedi.argtypes = [P(OrcCtl), P(OrcMet), P(OrcMet), P(OrcAtm)]
         L.orc_module_sort.argtypes = [P(OrcCtl), P(OrcMet), P(OrcAtm)]
         L.orc_module_meteo.argtypes = [P(OrcCtl), P(OrcMet), P(OrcMet), P(OrcAtm)]
+        L.orc_module_advect_init.argtypes = [P(OrcCtl), P(OrcMet), P(OrcMet), P(OrcAtm)]
+        L.orc_module_advect_init.restype = None
         L.orc_module_mixing.argtypes = [P(OrcCtl), P(OrcClim), P(OrcAtm), C.c_double]
         L.orc_sort_keys.argtypes = [P(OrcMet), P(OrcAtm), C.c_void_p]
         L.orc_intpol_met_time_3d.argtypes = [P(OrcMet), P(OrcMet), C.c_void_p, C.c_void_p] + [C.c_double] * 4 + [P(C.c_double)]
@@ -210,6 +228,8 @@ class Oracle:
             L.orc_module_mixing(C.byref(c), C.byref(cl), C.byref(a), t)
         elif what == "meteo":
             L.orc_module_meteo(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a))
+        elif what == "advect_init":
+            L.orc_module_advect_init(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a))
         else:
             raise ValueError(what)
         self.ctr = ctr.value
@@ -235,7 +255,7 @@ class Oracle:
 
 
 _WHAT = {"timestep": 0, "timesteps": 1, "position": 2, "advect": 3, "diff_turb": 4, "diff_meso": 5, "sedi": 6,
-         "sort": 7, "mixing": 8, "meteo": 9}
+         "sort": 7, "mixing": 8, "meteo": 9, "advect_init": 10}
 
 
 def reference_available() -> bool:
@@ -268,10 +288,11 @@ class Reference:
         return dict(zip(("EX", "EY", "EP", "NP", "NQ"), (x.value for x in v)))
 
     def read_ctl(self, qnt_names=(), overrides=""):
-        out = (C.c_int * 19)()
+        out = (C.c_int * 21)()
         nq = self.L.ref_read_ctl(",".join(qnt_names).encode(), overrides.encode(), out)
         self.qnt = dict(zip(("rp", "rhop", "m", "vmr", "ens"), list(out)[:5]))
-        self.qnt_meteo = {n: i for n, i in zip(METEO_QNT, list(out)[5:]) if i >= 0}   # name -> index the reference assigned
+        self.qnt["zeta"], self.qnt["eta"] = out[19], out[20]
+        self.qnt_meteo = {n: i for n, i in zip(METEO_QNT, list(out)[5:19]) if i >= 0}   # name -> index the reference assigned
         return nq
 
     def clim_tropo(self):

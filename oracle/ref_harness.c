@@ -34,7 +34,7 @@ static void ensure_alloc(void) {
 
 /* Reference defaults + quantity names (comma separated) + "KEY VALUE" overrides (space separated).
  * Returns the quantity index the reference assigned to `rp`, `rhop`, `m`, `vmr`, `ens` and the 14 module_meteo
- * quantities of the path through out[19]. */
+ * quantities of the path and `zeta`, `eta` through out[21]. */
 int ref_read_ctl(const char *qnt_names, const char *overrides, int *out) {
   ensure_alloc();
   static char buf[8192];
@@ -80,6 +80,7 @@ int ref_read_ctl(const char *qnt_names, const char *overrides, int *out) {
                         h_ctl->qnt_w, h_ctl->qnt_vh, h_ctl->qnt_vz, h_ctl->qnt_theta, h_ctl->qnt_psat, h_ctl->qnt_psice,
                         h_ctl->qnt_zeta_d};
     for (int i = 0; i < 14; i++) out[5 + i] = mq[i];
+    out[19] = h_ctl->qnt_zeta; out[20] = h_ctl->qnt_eta;
   }
   return h_ctl->nq;
 }
@@ -114,6 +115,19 @@ static void fill_met(met_t *dst, const orc_met_t *src) {
       dst->ps[ix][iy] = src->ps ? src->ps[(size_t)ix * src->ny + iy] : 0.f;
       dst->pbl[ix][iy] = src->pbl ? src->pbl[(size_t)ix * src->ny + iy] : 0.f;
     }
+  if (src->pl) {   /* model-level fields (ADVECT_VERT_COORD 1, 2, 3) */
+    if (src->npl > EP) ERRMSG("model levels exceed the reference build's EP");
+    dst->npl = src->npl;
+    const float *in[6] = {src->pl, src->ul, src->vl, src->wl, src->zetal, src->zeta_dotl};
+    float (*out[6])[EY][EP] = {dst->pl, dst->ul, dst->vl, dst->wl, dst->zetal, dst->zeta_dotl};
+#pragma omp parallel for collapse(2)
+    for (int ix = 0; ix < src->nx; ix++)
+      for (int iy = 0; iy < src->ny; iy++) {
+        const size_t o = ((size_t)ix * src->ny + iy) * src->npl;
+        for (int f = 0; f < 6; f++)
+          if (in[f]) memcpy(out[f][ix][iy], in[f] + o, sizeof(float) * (size_t)src->npl);
+      }
+  }
 }
 
 int ref_set_met(const orc_met_t *m0, const orc_met_t *m1) {
@@ -162,7 +176,7 @@ static void get_atm(orc_atm_t *a) {
 }
 
 /* what: 0 mptrac_run_timestep, 1 timesteps, 2 position, 3 advect, 4 diff_turb, 5 diff_meso, 6 sedi,
- *       7 sort, 8 mixing, 9 meteo.  Met must have been set with ref_set_met, ctl with ref_read_ctl. */
+ *       7 sort, 8 mixing, 9 meteo, 10 advect_init.  Met must have been set with ref_set_met, ctl with ref_read_ctl. */
 int ref_run(const orc_ctl_t *ctl, orc_atm_t *atm, double t, int what, int nsteps, uint64_t *ctr) {
   ensure_alloc();
   apply_ctl(ctl);
@@ -183,6 +197,7 @@ int ref_run(const orc_ctl_t *ctl, orc_atm_t *atm, double t, int what, int nsteps
     case 7: module_sort(h_ctl, h_met0, h_atm); break;
     case 8: module_mixing(h_ctl, h_clim, h_atm, t); break;
     case 9: module_meteo(h_ctl, h_cache, h_clim, h_met0, h_met1, h_atm); break;
+    case 10: module_advect_init(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     default: return 1;
   }
   *ctr = rng_ctr;

@@ -17,6 +17,8 @@ struct EmuMet {
   int coord_type, nx, ny, np;
   const double *lon, *lat, *p;
   const float *u, *v, *w, *t, *ps, *pbl;
+  int npl;
+  const float *pl, *ul, *vl, *wl, *zetal, *zeta_dotl;
 };
 
 struct EmuCtl {
@@ -131,4 +133,53 @@ extern "C" void emu_sort_keys(const EmuMet *m0, long long np, const double *lon,
   HostMet h;
   make_view(h, m0, nullptr, false);
   for (long long i = 0; i < np; i++) keys[i] = cell_key(h.g, lon[i], lat[i], p[i]);
+}
+
+// model levels: the packing of mpb_set_met restated for the host
+struct HostLevels {
+  std::vector<LevelNode> lp, lz;
+  std::vector<float4> pz;
+};
+static void pack_levels(HostLevels &L, MetView &g, const EmuMet &m0, const EmuMet &m1) {
+  const size_t n = (size_t)m0.nx * m0.ny * m0.npl;
+  L.lp.resize(n); L.lz.resize(n); L.pz.resize(n);
+  auto at = [](const float *f, size_t i) { return f ? f[i] : 0.f; };
+  for (size_t i = 0; i < n; i++) {
+    L.lp[i] = {m0.pl[i], m0.ul[i], m0.vl[i], at(m0.wl, i), m1.pl[i], m1.ul[i], m1.vl[i], at(m1.wl, i)};
+    L.lz[i] = {at(m0.zetal, i), m0.ul[i], m0.vl[i], at(m0.zeta_dotl, i), at(m1.zetal, i), m1.ul[i], m1.vl[i], at(m1.zeta_dotl, i)};
+    L.pz[i] = make_float4(m0.pl[i], at(m0.zetal, i), m1.pl[i], at(m1.zetal, i));
+  }
+  g.lp = L.lp.data(); g.lz = L.lz.data(); g.pz = L.pz.data(); g.npl = m0.npl;
+}
+
+extern "C" int emu_advect_levels(const EmuMet *m0, const EmuMet *m1, int vert_coord, int order, long long np, double *time,
+                                 double *lon, double *lat, double *p, const double *dt, double *zq) {
+  HostMet h;
+  HostLevels L;
+  make_view(h, m0, m1, false);
+  pack_levels(L, h.g, *m0, *m1);
+  const MetView &g = h.g;
+#pragma omp parallel for
+  for (long long ip = 0; ip < np; ip++) {
+    if (dt[ip] == 0) continue;
+    Parcel a = {time[ip], lon[ip], lat[ip], p[ip]};
+    double z = 0;
+    double *zp = zq ? &z : nullptr;
+    if (order == 1) advect_on_levels<1>(g, vert_coord, dt[ip], a, zp);
+    else if (order == 2) advect_on_levels<2>(g, vert_coord, dt[ip], a, zp);
+    else advect_on_levels<4>(g, vert_coord, dt[ip], a, zp);
+    time[ip] = a.time; lon[ip] = a.lon; lat[ip] = a.lat; p[ip] = a.p;
+    if (zq) zq[ip] = z;
+  }
+  return 0;
+}
+
+extern "C" int emu_advect_init(const EmuMet *m0, const EmuMet *m1, long long np, const double *time, const double *lon,
+                               const double *lat, double *p, const double *zq) {
+  HostMet h;
+  HostLevels L;
+  make_view(h, m0, m1, false);
+  pack_levels(L, h.g, *m0, *m1);
+  for (long long ip = 0; ip < np; ip++) p[ip] = pressure_of_zeta(h.g, time[ip], zq[ip], lon[ip], lat[ip]);
+  return 0;
 }

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 35
     for s in syms:
         assert hasattr(lib, s), f"{s} is declared in include/mptrac_b200.h but not exported"
-    assert lib.mpb_abi_version() == 2
+    assert lib.mpb_abi_version() == 3
 
 
 def test_strict_flavour_exports_the_same_abi():
@@ -40,10 +40,10 @@ def test_python_mirror_binds_every_symbol():
 def test_ctl_struct_layout_matches_header():
     # 16 int32 + 23 int32 + pad = 40 int32 = 160 bytes, then 25 doubles, then 16 int32 (ABI version 2)
     from mptrac_b200.host import _CtlStruct, _GridStruct, _MetViewStruct
-    assert C.sizeof(_CtlStruct) == 160 + 25 * 8 + 16 * 4
+    assert C.sizeof(_CtlStruct) == 160 + 25 * 8 + 16 * 4 + 2 * 4
     assert _CtlStruct.t_start.offset == 160
     assert _CtlStruct.met_dt_out.offset == 160 + 24 * 8
-    assert C.sizeof(_MetViewStruct) == 8 + 16 + 9 * 8 + 3 * 8
+    assert C.sizeof(_MetViewStruct) == 8 + 16 + 9 * 8 + 3 * 8 + 8 + 6 * 8 + 2 * 8
     assert C.sizeof(_GridStruct) == 16 + 8 * 8
 
 

@@ -186,6 +186,55 @@ def test_module_meteo_vs_oracle(oracle, lat_desc):
     assert np.array_equal(out["lon"], lon) and np.array_equal(out["p"], p)
 
 
+@pytest.mark.parametrize("vert_coord", [1, 2, 3])
+@pytest.mark.parametrize("advect", [1, 2, 4])
+@pytest.mark.parametrize("diffusion", [0, 1])
+def test_model_level_advection_vs_oracle(oracle, vert_coord, advect, diffusion):
+    """ADVECT_VERT_COORD 1 / 2 / 3 (zeta, omega on model levels, eta): module_advect_init at t_start, the model-level
+    advection launch between the timesteps/position segment and the diffusion/sedimentation/position segment, the zeta /
+    eta quantity written back; met levels uploaded in swapped order and exchanged with mpb_swap_met."""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    m0, m1, tm, p, lon, lat, clim = _case(n=6000, grid=(48, 25, 24))
+    m0, m1 = synth.add_model_levels(m0, npl=30), synth.add_model_levels(m1, npl=30)
+    n = tm.size
+    rng = np.random.default_rng(2)
+    q = np.stack([rng.uniform(0.1, 10, n), rng.uniform(500, 2500, n), rng.uniform(300.0, 1500.0, n)])
+    ctl = Ctl(nq=3, qnt_rp=0, qnt_rhop=1, advect=advect, advect_vert_coord=vert_coord, diffusion=diffusion, t_start=0.0,
+              t_stop=1e6, dt_mod=300.0, dt_met=21600.0, turb_dz_trop=0.5, turb_dx_strat=20.0, turb_mesox=0.16, turb_mesoz=0.16,
+              qnt_zeta=2 if vert_coord == 1 else -1, qnt_eta=2 if vert_coord == 3 else -1, sort_dt=600.0)
+    with _engine(n, 3) as eng:
+        eng.set_ctl(ctl)
+        eng.set_clim_tropo(*clim)
+        eng.set_met(0, m1)
+        eng.set_met(1, m0)
+        eng.swap_met()
+        eng.set_atm(tm, p, lon, lat, q)
+        for s in range(5):
+            eng.run_timestep(300.0 * s)
+        out = eng.get_atm()
+    ref = Parcels(tm, p, lon, lat, q)
+    oracle.ctr = 0
+    oracle.run("timestep", ctl, clim, m0, m1, ref, t=0.0, nsteps=5)
+    assert abserr(ref.lat, lat) > 1e-3
+    # the cell sort permutes both sides alike (stable, same keys): compare in place
+    tol = (TOL_POS_DEG_DIFF, TOL_P_REL_DIFF) if diffusion else (TOL_POS_DEG, TOL_P_REL)
+    _compare(f"levels_vc{vert_coord}_adv{advect}_diff{diffusion}", out, ref, *tol)
+    if vert_coord != 2:
+        assert relerr(out["q"][2], ref.q[2]) < tol[1]
+    assert np.array_equal(out["q"][:2], ref.q[:2])
+
+
+def test_model_level_advection_needs_the_fields():
+    from mptrac_b200 import Ctl
+    m0, m1, tm, p, lon, lat, clim = _case(n=100)
+    ctl = Ctl(advect=4, advect_vert_coord=2, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0)
+    with _engine(100) as eng:
+        _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat)
+        with pytest.raises(RuntimeError, match="model-level"):
+            eng.run_timestep(300.0)
+
+
 def test_rng_stream(oracle):
     """Squares counters are integers: uniforms must be bit-exact; Box-Muller normals agree to float-trig accuracy."""
     with _engine(10) as eng:

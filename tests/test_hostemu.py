@@ -98,3 +98,37 @@ def test_device_sort_key_on_host(emu, oracle):
     s0 = met_struct(m0)
     emu.emu_sort_keys(C.byref(s0), C.c_longlong(tm.size), *[C.c_void_p(x.ctypes.data) for x in (lon, lat, p, keys)])
     assert np.array_equal(keys, oracle.sort_keys(m0, Parcels(tm, p, lon, lat)))
+
+
+@pytest.mark.parametrize("vert_coord", [1, 2, 3])
+@pytest.mark.parametrize("advect", [1, 2, 4])
+def test_model_level_advection_on_host_is_bit_exact(emu, oracle, vert_coord, advect):
+    """advect_on_levels / pressure_of_zeta of the device source against the oracle's model-level module_advect and
+    module_advect_init."""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels, met_struct
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    m0, m1 = synth.add_model_levels(m0, npl=30), synth.add_model_levels(m1, npl=30)
+    n = 4000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=1.0, zmax=45.0, seed=5)
+    clim = synth.make_clim_tropo()
+    q = np.random.default_rng(2).uniform(300.0, 1500.0, (1, n))
+    ctl = Ctl(nq=1, advect=advect, advect_vert_coord=vert_coord, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0,
+              qnt_zeta=0 if vert_coord == 1 else -1, qnt_eta=0 if vert_coord == 3 else -1)
+    a = Parcels(tm, p, lon, lat, q)
+    oracle.run("timesteps", ctl, clim, m0, m1, a, t=300.0)
+    b = a.copy()
+    s0, s1 = met_struct(m0), met_struct(m1)
+    vp = lambda x: C.c_void_p(x.ctypes.data)  # noqa: E731
+    if vert_coord == 1:
+        oracle.run("advect_init", ctl, clim, m0, m1, b, t=0.0)
+        assert emu.emu_advect_init(C.byref(s0), C.byref(s1), C.c_longlong(n), vp(a.time), vp(a.lon), vp(a.lat), vp(a.p), vp(a.q[0])) == 0
+        assert np.array_equal(a.p, b.p) and np.max(np.abs(a.p - p)) > 1.0
+    for _ in range(3):
+        oracle.run("advect", ctl, clim, m0, m1, b, t=0.0)
+        zq = vp(a.q[0]) if vert_coord != 2 else None
+        assert emu.emu_advect_levels(C.byref(s0), C.byref(s1), vert_coord, advect, C.c_longlong(n), vp(a.time), vp(a.lon),
+                                     vp(a.lat), vp(a.p), vp(a.dt), zq) == 0
+    assert np.max(np.abs(b.lat - lat)) > 1e-3
+    for k in ("time", "lon", "lat", "p", "q"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k

@@ -187,3 +187,37 @@ def test_c1_trac_test_parcels_midpoint_bit_exact(oracle, reference):
     for k in ("time", "lon", "lat", "p"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
     assert np.max(np.abs(a.lat - lat)) > 1.0
+
+
+@pytest.mark.parametrize("vert_coord", [1, 2, 3])
+@pytest.mark.parametrize("advect", [1, 2, 4])
+def test_model_level_advection_bit_exact(oracle, reference, vert_coord, advect):
+    """ADVECT_VERT_COORD 1 / 2 / 3: intpol_met_4d_zeta, module_advect's model-level branches and module_advect_init
+    (src/mptrac.c:2808-2981, 3646-3657, 3680-3785), with diffusion and sedimentation running after them."""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    m0, m1 = synth.add_model_levels(m0, npl=30), synth.add_model_levels(m1, npl=30)
+    n = 4000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=1.0, zmax=45.0, seed=5)
+    names = ["rp", "rhop"] + (["zeta"] if vert_coord == 1 else ["eta"] if vert_coord == 3 else [])
+    nq = reference.read_ctl(names, "")
+    reference.set_met(m0, m1)
+    clim = reference.clim_tropo()
+    rng = np.random.default_rng(2)
+    q = np.zeros((nq, n))
+    q[0], q[1] = rng.uniform(0.1, 10, n), rng.uniform(500, 2500, n)
+    if vert_coord == 1:
+        q[reference.qnt["zeta"]] = rng.uniform(300.0, 1500.0, n)   # module_advect_init derives the pressure from it
+    ctl = Ctl(nq=nq, qnt_rp=0, qnt_rhop=1, advect=advect, advect_vert_coord=vert_coord, diffusion=1, t_start=0.0, t_stop=1e6,
+              dt_mod=300.0, dt_met=21600.0, turb_dz_trop=0.5, turb_dx_strat=20.0, turb_mesox=0.16, turb_mesoz=0.16,
+              qnt_zeta=reference.qnt["zeta"], qnt_eta=reference.qnt["eta"])
+    a = Parcels(tm, p, lon, lat, q)
+    b = a.copy()
+    reference.ctr = oracle.ctr = 0
+    reference.run("timestep", ctl, a, t=0.0, nsteps=5)
+    oracle.run("timestep", ctl, clim, m0, m1, b, t=0.0, nsteps=5)
+    assert abserr(a.lat, lat) > 1e-3
+    if vert_coord == 1:
+        assert abserr(a.p, p) > 1.0
+    assert _same(a, b)
