@@ -153,22 +153,28 @@ T_STOP = 360806400
 
 
 @pytest.mark.timeout(900)
-def test_trac_trac_test_pl_through_the_shim(tmp_path):
-    """The reference's own end-to-end test, tests/trac_test (pressure-level run): 10 000 parcels, 3 days at 300 s, with
-    diffusion, convection, H2O2 + tracer chemistry, decay, dry deposition, mixing and boundary conditions all on -- the
-    modules of the path on the GPU, the other twelve through the reference's CPU code in between (hybrid mode, one random
-    number stream across both).  Compared with the goldens the reference ships (data.ref/atm_pl_*.tab, %g text)."""
+@pytest.mark.parametrize("levels", ["pl", "ml"])
+def test_trac_trac_test_through_the_shim(tmp_path, levels):
+    """The reference's own end-to-end test, tests/trac_test: 10 000 parcels, 3 days at 300 s, with diffusion, convection,
+    H2O2 + tracer chemistry, decay, dry deposition, mixing and boundary conditions all on -- the modules of the path on
+    the GPU, the other twelve through the reference's CPU code in between (hybrid mode, one random number stream across
+    both).  `pl` is the pressure-level run, `ml` the run on ERA5 model levels (MET_VERT_COORD 1, ADVECT_VERT_COORD 2:
+    omega on model levels, tests/trac_test/run.sh:98-108).  Compared with the goldens the reference ships
+    (data.ref/atm_pl_*.tab, atm_ml_*.tab: %g text)."""
     _need()
-    gold = sorted((DATA / "trac_test.ref").glob("atm_pl_2011_*.tab"))
-    if len(gold) != 4 or not (DATA / "ei_2011_06_08_00.nc").exists() or not (DATA / "clim" / "cams_H2O2.nc").exists():
+    gold = sorted((DATA / "trac_test.ref").glob(f"atm_{levels}_2011_*.tab"))
+    met = "ei" if levels == "pl" else "era5ml"
+    if len(gold) != 4 or not (DATA / f"{met}_2011_06_08_00.nc").exists() or not (DATA / "clim" / "cams_H2O2.nc").exists():
         pytest.skip("trac_test data not shipped (oracle/build_ref.sh)")
     # the chemistry modules read their climatologies from ../../data relative to the working directory, like the
     # reference's own test does from tests/trac_test
     (tmp_path / "data").symlink_to(DATA / "clim")
     base = tmp_path / "tests" / "trac_test"
     base.mkdir(parents=True)
-    d, out = _run_trac(base, TRAC_TEST_CTL.format(met=DATA), DATA / "trac_test.ref" / "atm_init.tab",
-                       ["ATM_BASENAME", "atm_pl", "STAT_BASENAME", "station_pl", "STAT_LON", "-22", "STAT_LAT", "-40"])
+    extra = ["ATM_BASENAME", f"atm_{levels}", "STAT_BASENAME", f"station_{levels}", "STAT_LON", "-22", "STAT_LAT", "-40"]
+    if levels == "ml":
+        extra += ["METBASE", f"{DATA}/era5ml", "MET_PRESS_LEVEL_DEF", "6", "MET_VERT_COORD", "1", "ADVECT_VERT_COORD", "2"]
+    d, out = _run_trac(base, TRAC_TEST_CTL.format(met=DATA), DATA / "trac_test.ref" / "atm_init.tab", extra)
     assert "kernel launches" in out
     report = {}
     for g in gold:
@@ -182,7 +188,7 @@ def test_trac_trac_test_pl_through_the_shim(tmp_path):
     print("fraction of parcels agreeing with the shipped goldens (position, position + quantities):", report)
     out_dir = ROOT / "gpurun_out"
     out_dir.mkdir(exist_ok=True)
-    (out_dir / "trac_test_pl_shim.json").write_text(__import__("json").dumps(report, indent=1))
+    (out_dir / f"trac_test_{levels}_shim.json").write_text(__import__("json").dumps(report, indent=1))
     # convection, mixing and the boundary conditions are discontinuous in the parcel position (a parcel on the edge of a
     # CAPE column or a mixing box switches sides with a last-digit difference), so after 864 steps a small fraction differs
     assert report[gold[0].name][1] == 1.0                      # t0: initial state + module_meteo + boundary conditions
