@@ -1258,16 +1258,25 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
   REQUIRE(!(phys & PHYS_SEDI) || q != nullptr, "null quantity array");
   StepArgs A = step_args(c, t, k.advect, phys, MOD_TIMESTEPS | MOD_POS_PRE | MOD_POS_POST);
 
-  // Pinned host arrays are mapped into the device address space: the kernel then reads the parcels straight from host
-  // memory and writes them straight back -- both PCIe directions run concurrently for the whole launch, with no copy
-  // engine, no chunking and no staging (the persistent kernel keeps the next parcel's loads in flight a whole parcel
-  // ahead, which is what hides the link latency).  MPTRAC_B200_HOST_ZEROCOPY=0 selects the chunked copy pipeline.
-  static const bool allow_zc = !(std::getenv("MPTRAC_B200_HOST_ZEROCOPY") && std::atoi(std::getenv("MPTRAC_B200_HOST_ZEROCOPY")) == 0);
-  if (allow_zc) {
+  // MPTRAC_B200_HOST_MODE picks how the parcels cross the host link (read per call):
+  //   zerocopy (default)  kernel reads and writes the mapped host arrays, no copy engine
+  //   dma_in              copy engine uploads chunk by chunk, the kernel writes its results straight to the host arrays
+  //   dma_out             the kernel reads the host arrays, the copy engine downloads chunk by chunk
+  //   copy                copy engine both ways (also what unmapped = pageable host arrays get)
+  // MPTRAC_B200_HOST_ZEROCOPY=0 is the older spelling of "copy".
+  enum { HM_ZEROCOPY, HM_DMA_IN, HM_DMA_OUT, HM_COPY } mode = HM_ZEROCOPY;
+  if (const char *e = std::getenv("MPTRAC_B200_HOST_MODE")) {
+    if (!std::strcmp(e, "dma_in")) mode = HM_DMA_IN;
+    else if (!std::strcmp(e, "dma_out")) mode = HM_DMA_OUT;
+    else if (!std::strcmp(e, "copy")) mode = HM_COPY;
+    else REQUIRE(!std::strcmp(e, "zerocopy"), "MPTRAC_B200_HOST_MODE must be zerocopy, dma_in, dma_out or copy");
+  }
+  if (std::getenv("MPTRAC_B200_HOST_ZEROCOPY") && std::atoi(std::getenv("MPTRAC_B200_HOST_ZEROCOPY")) == 0) mode = HM_COPY;
+  void *d[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (mode != HM_COPY) {
     double *h[6] = {time, p, lon, lat, nullptr, nullptr};
     int nh = 4;
     if (phys & PHYS_SEDI) { h[4] = q + (size_t)k.qnt_rp * q_stride; h[5] = q + (size_t)k.qnt_rhop * q_stride; nh = 6; }
-    void *d[6];
     bool mapped = true;
     for (int i = 0; i < nh && mapped; i++) {
       cudaPointerAttributes at;
@@ -1275,15 +1284,26 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
       d[i] = mapped ? at.devicePointer : nullptr;
     }
     cudaGetLastError();
-    if (mapped) {
-      A.in_time = (const double *)d[0]; A.in_p = (const double *)d[1]; A.in_lon = (const double *)d[2]; A.in_lat = (const double *)d[3];
-      A.host_time = (double *)d[0]; A.host_p = (double *)d[1]; A.host_lon = (double *)d[2]; A.host_lat = (double *)d[3];
-      if (phys & PHYS_SEDI) { A.rp = (const double *)d[4]; A.rhop = (const double *)d[5]; }
-      launch_range(c, A, k.advect, phys, 0, np, c->stream);
-      CK(cudaStreamSynchronize(c->stream));   // the host arrays are valid on return
-      return 0;
-    }
+    if (!mapped) mode = HM_COPY;
   }
+  // Pinned host arrays are mapped into the device address space: the kernel then reads the parcels straight from host
+  // memory and writes them straight back -- both PCIe directions run concurrently for the whole launch, with no copy
+  // engine, no chunking and no staging (the persistent kernel keeps the next parcel's loads in flight a whole parcel
+  // ahead, which is what hides the link latency).
+  if (mode == HM_ZEROCOPY) {
+    A.in_time = (const double *)d[0]; A.in_p = (const double *)d[1]; A.in_lon = (const double *)d[2]; A.in_lat = (const double *)d[3];
+    A.host_time = (double *)d[0]; A.host_p = (double *)d[1]; A.host_lon = (double *)d[2]; A.host_lat = (double *)d[3];
+    if (phys & PHYS_SEDI) { A.rp = (const double *)d[4]; A.rhop = (const double *)d[5]; }
+    launch_range(c, A, k.advect, phys, 0, np, c->stream);
+    CK(cudaStreamSynchronize(c->stream));   // the host arrays are valid on return
+    return 0;
+  }
+  const bool dma_in = mode != HM_DMA_OUT, dma_out = mode != HM_DMA_IN;
+  if (!dma_in) {
+    A.in_time = (const double *)d[0]; A.in_p = (const double *)d[1]; A.in_lon = (const double *)d[2]; A.in_lat = (const double *)d[3];
+    if (phys & PHYS_SEDI) { A.rp = (const double *)d[4]; A.rhop = (const double *)d[5]; }
+  }
+  if (!dma_out) { A.host_time = (double *)d[0]; A.host_p = (double *)d[1]; A.host_lon = (double *)d[2]; A.host_lat = (double *)d[3]; }
   if (!c->lane[0]) {
     for (int i = 0; i < kLanes; i++) {
       CK(cudaStreamCreateWithFlags(&c->lane[i], cudaStreamNonBlocking));
@@ -1317,7 +1337,9 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
     const long long cnt = std::min<long long>(chunk, np - off);
     const size_t bytes = sizeof(double) * (size_t)cnt;
     cudaStream_t st = c->lane[lane];
-    if (strided) {
+    if (!dma_in) {
+      // the kernel reads this chunk from the mapped host arrays
+    } else if (strided) {
       // time, p, lon, lat sit at one constant stride in the caller's memory (they are consecutive members of atm_t):
       // one 2-D copy per direction and chunk instead of four
       CK(cudaMemcpy2DAsync(c->time() + off, dpitch, time + off, spitch, bytes, 4, cudaMemcpyHostToDevice, st));
@@ -1327,14 +1349,16 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
       CK(cudaMemcpyAsync(c->lon() + off, lon + off, bytes, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(c->lat() + off, lat + off, bytes, cudaMemcpyHostToDevice, st));
     }
-    if (phys & PHYS_SEDI) {   // the only quantities the path reads; none is modified
+    if (dma_in && (phys & PHYS_SEDI)) {   // the only quantities the path reads; none is modified
       CK(cudaMemcpyAsync(c->q(k.qnt_rp) + off, q + (size_t)k.qnt_rp * q_stride + off, bytes, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(c->q(k.qnt_rhop) + off, q + (size_t)k.qnt_rhop * q_stride + off, bytes, cudaMemcpyHostToDevice, st));
     }
     mark(st);
     launch_range(c, A, k.advect, phys, off, cnt, st);
     mark(st);
-    if (strided) {
+    if (!dma_out) {
+      // the kernel has written this chunk to the mapped host arrays
+    } else if (strided) {
       CK(cudaMemcpy2DAsync(time + off, spitch, c->time() + off, dpitch, bytes, 4, cudaMemcpyDeviceToHost, st));
     } else {
       CK(cudaMemcpyAsync(time + off, c->time() + off, bytes, cudaMemcpyDeviceToHost, st));

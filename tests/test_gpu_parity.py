@@ -491,12 +491,15 @@ def test_tma_staging_strict_library(oracle):
     assert abserr(outs[0]["lat"], lat) > 1e-3
 
 
-@pytest.mark.parametrize("layout", ["separate_arrays", "atm_t_layout", "pinned"])
-def test_host_resident_step_equals_three_calls(layout):
+@pytest.mark.parametrize("layout", ["separate_arrays", "atm_t_layout", "pinned", "pinned:dma_in", "pinned:dma_out", "pinned:copy"])
+def test_host_resident_step_equals_three_calls(layout, monkeypatch):
     """mpb_run_timestep_host (chunked upload / step / download pipeline) == set_atm + run_timestep + get_atm, bit for bit,
     including steps that fall back because a cell sort is due, with diffusion (random numbers addressed per chunk) and
     sedimentation (rp / rhop uploaded per chunk)."""
     from mptrac_b200 import Ctl
+    if ":" in layout:   # how pinned arrays cross the host link (MPTRAC_B200_HOST_MODE); the default is zerocopy
+        layout, mode = layout.split(":")
+        monkeypatch.setenv("MPTRAC_B200_HOST_MODE", mode)
     m0, m1, tm, p, lon, lat, clim = _case(n=300_000, grid=(72, 37, 30))
     n = tm.size
     q = np.stack([np.full(n, 2.0), np.full(n, 1500.0)])
