@@ -44,9 +44,23 @@ WORKLOADS = {
     # one GPU's share of BASELINE configs[3] (100 M parcels over 8 GPUs): dense -- 6 parcels per grid cell
     "c4": dict(np=12_500_000, grid=(360, 181, 60), ctl=dict(advect=4, diffusion=1, sort_dt=3600.0), state_bytes=88, met_fields=3,
                desc="12.5M parcels per GPU (100M / 8), 1x1 deg x 60 levels, RK4 + turbulent + mesoscale diffusion"),
+    # configs[1] on model levels: omega on 60 model levels, the reference's trac_test "ml" setting.
+    # Three launches per step (timesteps + position | model-level advection | position); per parcel-step the advection
+    # reads time, lon, lat, p, dt and writes time, lon, lat, p (72 B), the two segments around it 64 B + 8 B and 64 B
+    "c2ml": dict(np=1_000_000, grid=(360, 181, 60), levels=60, ctl=dict(advect=4, advect_vert_coord=2, diffusion=0, sort_dt=7200.0),
+                 state_bytes=208, met_fields=4, kernel="advect_levels_kernel (+ 2 step_kernel segments)", label="configs[1] on model levels",
+                 roofline_note="bytes and time of the whole step (3 launches; advect_levels_kernel is 91 % of it).  Not HBM-bound: the "
+                               "model-level lookup is four dependent load rounds per Runge-Kutta stage (column searches on both time "
+                               "levels, then the 8 records) at 16 resident warps/SM, ~890 instructions per stage; ncu r01h under "
+                               "profiles/, DESIGN.md 7",
+                 desc="1M parcels, 1x1 deg x 60 model levels, RK4 advection with omega on model levels (ADVECT_VERT_COORD 2)"),
 }
 DT_MOD = 300.0
 DT_MET = 21600.0
+
+
+def workload_label(name):
+    return WORKLOADS[name].get("label") or f"configs[{dict(c2=1, c3=2, c4=3)[name]}]"
 
 
 T0 = time.perf_counter()
@@ -139,6 +153,8 @@ def build_inputs(wl, rank, world):
     from mptrac_b200 import Ctl, synth
     nlon, nlat, nlev = wl["grid"]
     m0, m1 = synth.make_met_pair(nlon, nlat, nlev, t0=0.0, dt_met=DT_MET)
+    if wl.get("levels"):
+        m0, m1 = synth.add_model_levels(m0, npl=wl["levels"]), synth.add_model_levels(m1, npl=wl["levels"])
     n = wl["np"]
     tm, p, lon, lat = synth.make_parcels(n, t0=0.0, seed=123 + rank)
     kw = dict(nq=0, t_start=0.0, t_stop=1e9, dt_mod=DT_MOD, dt_met=DT_MET)
@@ -337,7 +353,7 @@ def run_ours(args):
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[{dict(c2=1, c3=2, c4=3)[args.workload]}]: {wl['desc']}", "parcels_per_gpu": n,
+        "config": {"workload": f"BASELINE {workload_label(args.workload)}: {wl['desc']}", "parcels_per_gpu": n,
                    "dt_mod_s": DT_MOD, "l2": "flushed between steps (256 MiB memset outside the per-step events)",
                    "parallelism": f"parcels sharded contiguously over {world} GPU(s), no data-path collective"},
         "back_to_back": {"value": units / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / K, "met_rolls_inside": b2b_rolls,
@@ -347,11 +363,12 @@ def run_ours(args):
                 "host_checksum": checksum, "host_link": pc},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "algorithmic_bytes_per_launch": algo_bytes, "kernel": "step_kernel", "peak_source": peak_src,
-                     "note": "not HBM-bound: DRAM traffic is below the algorithmic bytes; the kernel is limited by latency at 16 "
-                             "resident warps/SM (about 100 live fp64 registers per parcel) and by the 192 f32->f64 conversions per "
-                             "RK4 step the reference's arithmetic needs (XU pipe 45 % busy: floor 47 us per 1M parcels, i.e. frac "
-                             "0.51 at best); ncu evidence under profiles/, analysis in DESIGN.md 3.1"},
+                     "algorithmic_bytes_per_launch": algo_bytes, "kernel": wl.get("kernel", "step_kernel"), "peak_source": peak_src,
+                     "note": wl.get("roofline_note") or (
+                         "not HBM-bound: DRAM traffic is below the algorithmic bytes; the kernel is limited by latency at 16 "
+                         "resident warps/SM (about 100 live fp64 registers per parcel) and by the 192 f32->f64 conversions per "
+                         "RK4 step the reference's arithmetic needs (XU pipe 45 % busy: floor 47 us per 1M parcels, i.e. frac "
+                         "0.51 at best); ncu evidence under profiles/, analysis in DESIGN.md 3.1")},
         "clocks": clk.summary(),
     }
     eng.close()
@@ -454,7 +471,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "particle-steps/sec", "value": v, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": n_sample / v * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[{dict(c2=1, c3=2, c4=3)[args.workload]}]: {wl['desc']}",
+            "config": {"workload": f"BASELINE {workload_label(args.workload)}: {wl['desc']}",
                        "note": "reference CPU arm: host cores only, rank 0 only"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

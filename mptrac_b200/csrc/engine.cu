@@ -103,6 +103,9 @@ constexpr int kLanes = 4;                       // concurrent chunk pipelines of
 constexpr long long kHostChunkMin = 16384;      // parcels per chunk: at least 128 KiB per array ...
 constexpr long long kHostChunkMax = 1 << 20;    // ... at most 8 MiB
 
+#ifndef MPB_LEVEL_MINBLOCKS
+#define MPB_LEVEL_MINBLOCKS 4   // resident blocks per SM the model-level advection kernel is compiled for
+#endif
 #ifdef MPB_NO_BOUNDS   // register budget given by -maxrregcount instead (variant sweeps)
 #define MPB_BOUNDS
 #else
@@ -367,12 +370,14 @@ struct LevelArgs {
   double *time, *lon, *lat, *p;
   const double *dt;
   double *zq;           // the parcel's zeta / eta (null for ADVECT_VERT_COORD 2)
+  unsigned short *hint; // per array slot: level + 1 found by the previous step's first lookup (0 = none); a search hint
+                        // that is verified before use, so stale values (after a cell sort) only cost the bisection
   long long np;
   int vert_coord;
 };
 
 template <int ORDER>
-__global__ void __launch_bounds__(128) advect_levels_kernel(const __grid_constant__ LevelArgs A) {
+__global__ void __launch_bounds__(128, MPB_LEVEL_MINBLOCKS) advect_levels_kernel(const __grid_constant__ LevelArgs A) {
   const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (ip >= A.np) return;
   const double dt = A.dt[ip];
@@ -380,9 +385,11 @@ __global__ void __launch_bounds__(128) advect_levels_kernel(const __grid_constan
   Parcel a;
   a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
   double z = 0;
-  advect_on_levels<ORDER>(A.met, A.vert_coord, dt, a, A.zq ? &z : nullptr);
+  int hint = (int)A.hint[ip] - 1;
+  advect_on_levels<ORDER>(A.met, A.vert_coord, dt, a, A.zq ? &z : nullptr, A.zq ? nullptr : &hint);
   A.time[ip] = a.time; A.lon[ip] = a.lon; A.lat[ip] = a.lat; A.p[ip] = a.p;
   if (A.zq) A.zq[ip] = z;
+  else A.hint[ip] = (unsigned short)(hint + 1);
 }
 
 __global__ void __launch_bounds__(128) advect_init_kernel(const __grid_constant__ LevelArgs A) {
@@ -522,6 +529,7 @@ struct mpb_ctx {
   int npl = 0;
   size_t lev_cap = 0;
   bool lev_valid[2] = {false, false};
+  unsigned short *lev_hint = nullptr;              // LevelArgs::hint
 
   // clim
   double *cl_time = nullptr, *cl_lat = nullptr, *cl_tropo = nullptr;
@@ -681,6 +689,11 @@ static LevelArgs level_args(mpb_ctx *c) {
   REQUIRE(A.met.npl >= 2, "ADVECT_VERT_COORD 1, 2 and 3 need the model-level fields of both met levels (mpb_met_view_t::pl ...)");
   A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p(); A.dt = c->dt;
   A.np = c->np; A.vert_coord = k.advect_vert_coord;
+  if (!c->lev_hint) {
+    CK(cudaMalloc(&c->lev_hint, sizeof(unsigned short) * (size_t)c->np_max));
+    CK(cudaMemsetAsync(c->lev_hint, 0, sizeof(unsigned short) * (size_t)c->np_max, c->stream));
+  }
+  A.hint = c->lev_hint;
   A.zq = nullptr;
   if (k.advect_vert_coord == 1 || k.advect_vert_coord == 3) {
     const int iq = k.advect_vert_coord == 1 ? k.qnt_zeta : k.qnt_eta;
@@ -879,7 +892,7 @@ int mpb_destroy(mpb_ctx *c) {
   void *ptrs[] = {c->soa[0], c->soa[1], c->dt, c->uvwp, c->keys[0], c->keys[1], c->perm[0], c->perm[1],
                   c->cub_tmp, c->nodes, c->surf, c->ax_lon, c->ax_lat, c->ax_p, c->ax_lonc, c->ax_latc, c->ax_pc,
                   c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_sum, c->mix_cnt,
-                  c->grid_sum, c->grid_sq, c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz};
+                  c->grid_sum, c->grid_sq, c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz, c->lev_hint};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->stage_h) cudaFreeHost(c->stage_h);
   for (int i = 0; i < kLanes; i++) {
