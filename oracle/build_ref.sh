@@ -73,15 +73,19 @@ if [ "$what" = ref ] || [ "$what" = all ]; then
 fi
 # test data of the reference's own tests that exercise this path (data files, not sources): they let the GPU box
 # run the unmodified `trac` end to end through the shim.  oracle/_ref is git-ignored.
-if [ ! -f "$OUT/data/.stamp5" ]; then
+if [ ! -f "$OUT/data/.stamp6" ]; then
   mkdir -p "$OUT/data/dt_test.ref" "$OUT/data/coord_test.ref" "$OUT/data/trac_test.ref"
   cp "$REF"/tests/trac_test/data.ref/atm_init.tab "$REF"/tests/trac_test/data.ref/atm_pl_2011_*.tab "$REF"/tests/trac_test/data.ref/atm_ml_2011_*.tab "$OUT/data/trac_test.ref/"
   cp "$REF"/tests/data/era5ml_2011_06_0[5678]_00.nc "$OUT/data/"   # model-level met data of trac_test's atm_ml run
+  # tests/interoper_test part 2: diabatic (zeta) transport on CLaMS-convention ERA-Interim data, ADVECT_VERT_COORD 1
+  mkdir -p "$OUT/data/interoper_test.ref"
+  cp "$REF"/tests/data/erai_vlr_1607010[06].nc "$OUT/data/"
+  cp "$REF"/tests/interoper_test/data.ref/init/pos_glo_16070100.nc "$REF"/tests/interoper_test/data.ref/atm_2016_07_01_0[06]_00_00.tab "$OUT/data/interoper_test.ref/"
   cp "$REF"/tests/data/ei_2011_06_07_00.nc "$REF"/tests/data/ei_2011_06_08_00.nc "$OUT/data/"
   mkdir -p "$OUT/data/clim" && cp "$REF"/data/*.nc "$REF"/data/*.tab "$OUT/data/clim/"   # climatologies the chemistry modules read
   cp "$REF"/tests/data/ei_2011_06_05_00.nc "$REF"/tests/data/ei_2011_06_06_00.nc "$REF"/tests/data/era5_utm32_2025_05_01_0[012].nc "$OUT/data/"
   cp "$REF"/tests/dt_test/data.ref/atm_split.tab "$REF"/tests/dt_test/data.ref/atm_pl_*.tab "$OUT/data/dt_test.ref/"
   cp "$REF"/tests/coord_test/data.ref/atm_2025_05_01_*.tab "$OUT/data/coord_test.ref/"
-  touch "$OUT/data/.stamp5"
+  touch "$OUT/data/.stamp6"
 fi
 echo "oracle/_ref ready: $(ls "$OUT/bin" | tr '\n' ' ')"

@@ -24,17 +24,17 @@ def _need():
             pytest.skip(f"{f} not present (built only where /root/reference exists)")
 
 
-def _run_trac(tmp_path, ctl_text, atm_in, extra, preload=True, env_extra=None):
+def _run_trac(tmp_path, ctl_text, atm_in, extra, preload=True, env_extra=None, atm_name="atm_in.tab"):
     d = tmp_path / "data"
     d.mkdir()
     (d / "trac.ctl").write_text(ctl_text)
-    (d / "atm_in.tab").write_bytes(atm_in.read_bytes())
+    (d / atm_name).write_bytes(atm_in.read_bytes())
     (tmp_path / "dirlist").write_text(str(d) + "\n")
     env = dict(os.environ, OMP_NUM_THREADS="4", LANG="C", LC_ALL="C", MPTRAC_B200_VERBOSE="1")
     if preload:
         env["LD_PRELOAD"] = str(SHIM)
     env.update(env_extra or {})
-    r = subprocess.run([str(TRAC), str(tmp_path / "dirlist"), "trac.ctl", "atm_in.tab", *extra], env=env, cwd=tmp_path,
+    r = subprocess.run([str(TRAC), str(tmp_path / "dirlist"), "trac.ctl", atm_name, *extra], env=env, cwd=tmp_path,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     return d, r.stdout
@@ -194,3 +194,63 @@ def test_trac_trac_test_through_the_shim(tmp_path, levels):
     assert report[gold[0].name][1] == 1.0                      # t0: initial state + module_meteo + boundary conditions
     # measured on B200: positions 1.0 / 1.0 / 1.0 / 0.9999, positions + quantities 1.0 / 0.9998 / 0.9994 / 0.999
     assert all(v[0] >= 0.999 and v[1] >= 0.99 for v in report.values()), report
+
+
+INTEROPER_CTL = """MET_CONVENTION = 1
+MET_PRESS_LEVEL_DEF = 5
+ATM_TYPE = 3
+ATM_TYPE_OUT = 0
+ADVECT = 2
+MET_CLAMS = 1
+ADVECT_VERT_COORD = 1
+MET_VERT_COORD = 1
+NQ = 7
+QNT_NAME[0] = theta
+QNT_NAME[1] = pv
+QNT_NAME[2] = m
+QNT_NAME[3] = zeta
+QNT_NAME[4] = zeta_d
+QNT_NAME[5] = ps
+QNT_NAME[6] = p
+METBASE = {met}/erai_vlr
+DIRECTION = 1
+MET_TROPO = 3
+TDEC_TROP = 259200
+TDEC_STRAT = 259200
+DT_MOD = 180
+DT_MET = 21600
+T_START = 520646400
+T_STOP = 520668000
+CHUNKSZHINT = 163840000
+ATM_DT_OUT = 21600
+"""
+
+
+@pytest.mark.timeout(900)
+def test_trac_interoper_test_zeta_through_the_shim(tmp_path):
+    """The reference's tests/interoper_test, part 2 (run.sh:22-66): diabatic transport in the zeta coordinate
+    (ADVECT_VERT_COORD 1: module_advect_init + module_advect's zeta branch) on CLaMS-convention ERA-Interim data, parcels
+    read from a CLaMS netCDF position file, 6 hours at 180 s with the midpoint scheme; module_meteo (pv needs the host) and
+    module_decay run through the reference's CPU code between the device segments.  Compared with the shipped goldens."""
+    _need()
+    ref = DATA / "interoper_test.ref"
+    gold = sorted(ref.glob("atm_2016_07_01_*.tab"))
+    if len(gold) != 2 or not (DATA / "erai_vlr_16070106.nc").exists():
+        pytest.skip("interoper_test data not shipped (oracle/build_ref.sh)")
+    (tmp_path / "data").symlink_to(DATA / "clim")
+    base = tmp_path / "tests" / "interoper_test"
+    base.mkdir(parents=True)
+    d, out = _run_trac(base, INTEROPER_CTL.format(met=DATA), ref / "pos_glo_16070100.nc", ["ATM_BASENAME", "atm", "GRID_BASENAME", "grid"],
+                       atm_name="pos_glo_16070100.nc")
+    assert "kernel launches" in out
+    report = {}
+    for g in gold:
+        a, b = _tab(d / g.name), _tab(g)
+        assert a.shape == b.shape
+        ok = np.all(np.abs(a - b) <= 1e-4 * np.abs(b) + 1e-4 * np.max(np.abs(b), axis=0), axis=1)
+        report[g.name] = float(ok.mean())
+    print("fraction of parcels agreeing with the shipped goldens in every column:", report)
+    out_dir = ROOT / "gpurun_out"
+    out_dir.mkdir(exist_ok=True)
+    (out_dir / "interoper_test_shim.json").write_text(__import__("json").dumps(report, indent=1))
+    assert all(v >= 0.999 for v in report.values()), report
