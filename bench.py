@@ -44,6 +44,21 @@ WORKLOADS = {
     # one GPU's share of BASELINE configs[3] (100 M parcels over 8 GPUs): dense -- 6 parcels per grid cell
     "c4": dict(np=12_500_000, grid=(360, 181, 60), ctl=dict(advect=4, diffusion=1, sort_dt=3600.0), state_bytes=88, met_fields=3,
                desc="12.5M parcels per GPU (100M / 8), 1x1 deg x 60 levels, RK4 + turbulent + mesoscale diffusion"),
+    # BASELINE configs[3] as stated: the c4 share plus the gridded output EVERY step (write_grid's binning on the device,
+    # src/mptrac.c:13840-13872, reference default grid 360 x 180 x 1): local partial boxes -> one NCCL sum-reduction to
+    # rank 0 -> rank 0 reads count / sum / sum of squares on the host
+    "c4g": dict(np=12_500_000, grid=(360, 181, 60), ctl=dict(advect=4, diffusion=1, sort_dt=3600.0, nq=1), state_bytes=104, met_fields=3,
+                q_init=1.0, out_grid=dict(nx=360, ny=180, nz=1, lon0=-180.0, lon1=180.0, lat0=-90.0, lat1=90.0, z0=-5.0, z1=85.0),
+                label="configs[3]", kernel="step_kernel (+ grid binning, NCCL reduce)",
+                desc="12.5M parcels per GPU (100M / 8), 1x1 deg x 60 levels, RK4 + turbulent + mesoscale diffusion, gridded output "
+                     "(360x180x1 boxes) reduced over the ranks every step"),
+    # BASELINE configs[4]: 10 M parcels over 8 GPUs, inter-parcel mixing and the cell sort EVERY step (MIXING_DT = SORT_DT =
+    # DT_MOD); reference default mixing grid 360 x 180 x 90 = 5.8 M boxes: accumulate -> NCCL all-reduce of 70 MB -> relax
+    "c5": dict(np=1_250_000, grid=(360, 181, 60), ctl=dict(advect=4, diffusion=0, sort_dt=300.0, nq=1, mixing_trop=1e-3, mixing_strat=1e-6,
+                                                             mixing_dt=300.0, mix_qnt=[0]), state_bytes=112, met_fields=3,
+               q_init="uniform", mixing=True, label="configs[4]", kernel="step_kernel (+ sort, mixing kernels, NCCL all-reduce)",
+               desc="1.25M parcels per GPU (10M / 8), 1x1 deg x 60 levels, RK4, cell sort and inter-parcel mixing (360x180x90 boxes, "
+                    "all-reduced over the ranks) every step"),
     # configs[1] on model levels: omega on 60 model levels, the reference's trac_test "ml" setting.
     # Three launches per step (timesteps + position | model-level advection | position); per parcel-step the advection
     # reads time, lon, lat, p, dt and writes time, lon, lat, p (72 B), the two segments around it 64 B + 8 B and 64 B
@@ -161,7 +176,9 @@ def build_inputs(wl, rank, world):
     kw.update(wl["ctl"])
     ctl = Ctl(**kw)
     q = None
-    if ctl.nq:
+    if ctl.nq and wl.get("q_init") is not None:
+        q = np.full((ctl.nq, n), 1.0) if wl["q_init"] != "uniform" else np.random.default_rng(7 + rank).uniform(0.0, 1.0, (ctl.nq, n))
+    elif ctl.nq:
         q = np.zeros((ctl.nq, n))
         q[0], q[1] = 1.0, 1500.0   # rp = 1 micron, rhop = 1500 kg/m3
     return ctl, m0, m1, (tm, p, lon, lat, q)
@@ -231,12 +248,43 @@ def run_ours(args):
 
     model = Model()
 
+    # one model step.  Workloads with an exchange: the box arrays are summed over the ranks by NCCL on the
+    # stream the engine launches on -- mixing between its accumulate and apply kernels, gridded output after the step
+    dev = torch.device("cuda", local)
+    if wl.get("mixing"):
+        from mptrac_b200 import dist as mdist
+        from mptrac_b200.host import MOD_ALL, MOD_MIXING
+
+        def step(t):
+            eng.run_modules(t, MOD_ALL & ~MOD_MIXING)
+            mdist.mixing_step(eng, t, dev)
+    elif wl.get("out_grid"):
+        from mptrac_b200 import dist as mdist
+        grid_seen = []
+
+        def step(t):
+            eng.run_timestep(t)
+            g = mdist.grid_output(eng, dict(wl["out_grid"], t0=t - 0.5 * DT_MOD, t1=t + 0.5 * DT_MOD), dev)
+            if g is not None:
+                grid_seen[:] = [int(g[0].sum())]      # rank 0 holds the reduced boxes on the host
+    else:
+        step = eng.run_timestep
+    exchange = bool(wl.get("mixing") or wl.get("out_grid"))
+
+    def host_step(t):
+        if exchange:   # host buffers in, step with its exchange, host buffers out
+            eng.set_atm(hn["time"], hn["p"], hn["lon"], hn["lat"], hqn)
+            step(t)
+            eng.get_atm({"time": hn["time"], "p": hn["p"], "lon": hn["lon"], "lat": hn["lat"], "q": hqn})
+        else:
+            eng.run_timestep_host(t, hn["time"], hn["p"], hn["lon"], hn["lat"], hqn)
+
     # ---------------- device-resident timing: per-step events, L2 flushed between steps ----------------
     _log("engine ready; device-resident timing")
     eng.set_atm(hn["time"], hn["p"], hn["lon"], hn["lat"], hqn)
     spinup = int(round(wl["ctl"].get("sort_dt", 0.0) / DT_MOD))    # reach the first cell sort: steady state of a long run
     for _ in range(spinup + W):
-        eng.run_timestep(model.next_t())
+        step(model.next_t())
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     launches = 0
     barrier()
@@ -247,7 +295,7 @@ def run_ours(args):
             flush.zero_()
             l0 = eng.launch_count
             ev[k][0].record(stream)
-            eng.run_timestep(t_next)
+            step(t_next)
             ev[k][1].record(stream)
             launches += eng.launch_count - l0     # kernels of ours inside the timed events
         barrier()
@@ -257,7 +305,7 @@ def run_ours(args):
         t_end = time.perf_counter() + (0.0 if os.environ.get("MPB_BENCH_NO_SUSTAIN") else max(0.0, 1.0 - (wall1 - wall0)))
         while time.perf_counter() < t_end:
             for _ in range(24):
-                eng.run_timestep(model.next_t())
+                step(model.next_t())
             torch.cuda.synchronize()
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     total_ms = float(step_ms.sum())
@@ -269,7 +317,7 @@ def run_ours(args):
     barrier()
     e0.record(stream)
     for k in range(K):
-        eng.run_timestep(model.next_t())
+        step(model.next_t())
     e1.record(stream)
     barrier()
     b2b_ms = e0.elapsed_time(e1)
@@ -281,11 +329,11 @@ def run_ours(args):
     _log("end-to-end timing")
     eng.get_atm({"time": hn["time"], "p": hn["p"], "lon": hn["lon"], "lat": hn["lat"], "q": hqn})
     for _ in range(max(W, 3)):
-        eng.run_timestep_host(model.next_t(), hn["time"], hn["p"], hn["lon"], hn["lat"], hqn)
+        host_step(model.next_t())
     barrier()
     e0.record(stream)
     for k in range(K):
-        eng.run_timestep_host(model.next_t(), hn["time"], hn["p"], hn["lon"], hn["lat"], hqn)
+        host_step(model.next_t())
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -321,6 +369,11 @@ def run_ours(args):
         pc = {"error": repr(exc)}
     h2d_bytes = 32 * n + (16 * n if ctl.nq else 0)     # time, p, lon, lat (+ rp, rhop when sedimentation is on)
     d2h_bytes = 32 * n
+    if exchange:                                       # set_atm / get_atm move every quantity both ways
+        h2d_bytes = d2h_bytes = (32 + 8 * ctl.nq) * n
+        if wl.get("out_grid") and rank == 0:
+            g = wl["out_grid"]
+            d2h_bytes += g["nx"] * g["ny"] * g["nz"] * (4 + 16 * max(ctl.nq, 1))   # count, sum, sum of squares on rank 0
     checksum = float(hn["lat"][:: max(1, n // 1024)].sum())   # the result is read on the host
 
     def allmax(x):
@@ -355,11 +408,14 @@ def run_ours(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"BASELINE {workload_label(args.workload)}: {wl['desc']}", "parcels_per_gpu": n,
                    "dt_mod_s": DT_MOD, "l2": "flushed between steps (256 MiB memset outside the per-step events)",
-                   "parallelism": f"parcels sharded contiguously over {world} GPU(s), no data-path collective"},
+                   "parallelism": f"parcels sharded contiguously over {world} GPU(s), " + (
+                       "one NCCL all-reduce of the mixing boxes per step" if wl.get("mixing") else
+                       "one NCCL reduce of the output-grid boxes per step" if wl.get("out_grid") else "no data-path collective")},
         "back_to_back": {"value": units / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / K, "met_rolls_inside": b2b_rolls,
                          "note": "no L2 flush, one event bracket around K steps"},
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": e2e_ms / K, "api": "mpb_run_timestep_host (pinned host arrays in, same arrays out, every step)",
+                "ms_per_step": e2e_ms / K, "api": ("mpb_set_atm + step with its exchange + mpb_get_atm (pinned host arrays, every step)" if exchange else
+                        "mpb_run_timestep_host (pinned host arrays in, same arrays out, every step)"),
                 "host_checksum": checksum, "host_link": pc},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -396,7 +452,7 @@ def cpu_baseline(workload, budget_s=20.0, steps=None):
     if reference_available():
         kind = "reference"
         ref = Reference()
-        names = ["rp", "rhop"] if ctl.nq else []
+        names = (["rp", "rhop"] if ctl.qnt_rp >= 0 else ["m"])[:ctl.nq]
         ref.read_ctl(names, "")
         ref.set_met(m0, m1)
         run = lambda t, k: ref.run("timestep", ctl, atm, t=t, nsteps=k)   # noqa: E731

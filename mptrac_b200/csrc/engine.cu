@@ -447,17 +447,39 @@ __global__ void mix_apply_kernel(ClimView clim, const int *box, double *q, const
 }
 
 // src/mptrac.c:13862-13872 with kernel weight 1 (no GRID_KERNEL file)
+// Gridded output: count, sum and sum of squares per box (src/mptrac.c:13840-13872).  Parcels arrive cell-sorted, so the
+// lanes of a warp mostly fall into one or two boxes: each run of equal box indices is summed inside the warp (segmented
+// scan over shuffles) and only the last lane of a run touches memory -- ~200 parcels per box would otherwise serialise
+// on the same three addresses in L2.  Runs need not be maximal (an unsorted stream just issues more atomics).
 __global__ void grid_accumulate_kernel(const int *box, const double *q, long long q_stride, int nq,
                                        long long nbox, int *cnt, double *sum, double *sq, long long np) {
-  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ip >= np) return;
-  const int b = box[ip];
-  if (b < 0) return;
-  atomicAdd(cnt + b, 1);
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (the grid covers whole warps: no early return)
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int b = ip < np ? box[ip] : -1;
+  const int prev = __shfl_up_sync(full, b, 1);
+  const unsigned heads = __ballot_sync(full, lane == 0 || prev != b);
+  const int start = 31 - __clz(heads & (full >> (31 - lane)));             // first lane of this lane's run
+  const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+  int n = 1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int tn = __shfl_up_sync(full, n, d);
+    if (lane - d >= start) n += tn;
+  }
+  if (tail && b >= 0) atomicAdd(cnt + b, n);
   for (int iq = 0; iq < nq; iq++) {
-    const double x = q[iq * q_stride + ip];
-    atomicAdd(sum + iq * nbox + b, x);
-    atomicAdd(sq + iq * nbox + b, x * x);
+    const double x = b >= 0 ? q[iq * q_stride + ip] : 0.0;
+    double s1 = x, s2 = x * x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double t1 = __shfl_up_sync(full, s1, d), t2 = __shfl_up_sync(full, s2, d);
+      if (lane - d >= start) { s1 += t1; s2 += t2; }
+    }
+    if (tail && b >= 0) {
+      atomicAdd(sum + iq * nbox + b, s1);
+      atomicAdd(sq + iq * nbox + b, s2);
+    }
   }
 }
 
