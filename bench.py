@@ -195,6 +195,11 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # libraries write to file descriptor 1 behind Python's back (NCCL prints its version line there): keep the real
+    # stdout for the one JSON line and send everything else to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = WORKLOADS[args.workload]
@@ -433,7 +438,8 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             _log("cpu_baseline leg")
             line["cpu_baseline"] = cpu_baseline_subprocess(args.workload, args.cpu_budget)
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     _log("done")
     if world > 1:
         dist.destroy_process_group()
