@@ -26,16 +26,32 @@
 extern "C" {
 #endif
 
-#define MPB_ABI_VERSION 3
+#define MPB_ABI_VERSION 4
 #define MPB_MIX_MAXQ 23  /* number of mixable quantities, src/mptrac.c:5222-5230 */
 
-/* Quantities module_meteo (src/mptrac.c:5062-5165) can set on the device: everything that derives from the met fields
- * the path keeps resident (T, u, v, w on pressure levels; ps, pbl).  Slot order of mpb_ctl_t::qnt_meteo. */
+/* Quantities module_meteo (src/mptrac.c:5062-5165) can set on the device, slot order of mpb_ctl_t::qnt_meteo:
+ *   PS .. ZETA_D  from the met fields the path keeps resident (T, u, v, w on pressure levels; ps, pbl);
+ *   TS .. O3C     the further 2-D fields of INTPOL_TIME_ALL (src/mptrac.h:1278-1316), slot = MPB_Q_TS + MPB_F2_*;
+ *   ZG .. CC      its further 3-D fields, slot = MPB_Q_ZG + MPB_F3_*;
+ *   PW .. TICE    derived from T and H2O (PW, SH, RH, RHICE, TVIRT, lapse_rate, TDEW, TICE).
+ * A further-field quantity needs that field in both met levels (mpb_met_view_t::x2 / x3).  Quantities that read a
+ * climatology (hno3, oh, h2o2, ho2, o1d, tnat, tsts) are not on the device. */
 enum {
   MPB_Q_PS, MPB_Q_PBL, MPB_Q_P, MPB_Q_T, MPB_Q_RHO, MPB_Q_U, MPB_Q_V, MPB_Q_W, MPB_Q_VH, MPB_Q_VZ, MPB_Q_THETA,
-  MPB_Q_PSAT, MPB_Q_PSICE, MPB_Q_ZETA_D, MPB_NMETEO
+  MPB_Q_PSAT, MPB_Q_PSICE, MPB_Q_ZETA_D,
+  MPB_Q_TS, MPB_Q_ZS, MPB_Q_US, MPB_Q_VS, MPB_Q_ESS, MPB_Q_NSS, MPB_Q_SHF, MPB_Q_LSM, MPB_Q_SST, MPB_Q_PT, MPB_Q_TT, MPB_Q_ZT,
+  MPB_Q_H2OT, MPB_Q_PCT, MPB_Q_PCB, MPB_Q_CL, MPB_Q_PLCL, MPB_Q_PLFC, MPB_Q_PEL, MPB_Q_CAPE, MPB_Q_CIN, MPB_Q_O3C,
+  MPB_Q_ZG, MPB_Q_PV, MPB_Q_H2O, MPB_Q_O3, MPB_Q_LWC, MPB_Q_RWC, MPB_Q_IWC, MPB_Q_SWC, MPB_Q_CC,
+  MPB_Q_PW, MPB_Q_SH, MPB_Q_RH, MPB_Q_RHICE, MPB_Q_TVIRT, MPB_Q_LAPSE, MPB_Q_TDEW, MPB_Q_TICE, MPB_NMETEO
 };
-#define MPB_METEO_SLOTS 16
+#define MPB_METEO_SLOTS 64
+/* further met fields: met_t::ts ... o3c ([EX][EY]) and met_t::z ... cc ([EX][EY][EP]), src/mptrac.h:3886-3995 */
+enum {
+  MPB_F2_TS, MPB_F2_ZS, MPB_F2_US, MPB_F2_VS, MPB_F2_ESS, MPB_F2_NSS, MPB_F2_SHF, MPB_F2_LSM, MPB_F2_SST, MPB_F2_PT, MPB_F2_TT,
+  MPB_F2_ZT, MPB_F2_H2OT, MPB_F2_PCT, MPB_F2_PCB, MPB_F2_CL, MPB_F2_PLCL, MPB_F2_PLFC, MPB_F2_PEL, MPB_F2_CAPE, MPB_F2_CIN,
+  MPB_F2_O3C, MPB_NX2
+};
+enum { MPB_F3_Z, MPB_F3_PV, MPB_F3_H2O, MPB_F3_O3, MPB_F3_LWC, MPB_F3_RWC, MPB_F3_IWC, MPB_F3_SWC, MPB_F3_CC, MPB_NX3 };
 
 typedef struct mpb_ctx mpb_ctx;
 
@@ -90,6 +106,9 @@ typedef struct mpb_met_view {
   int32_t npl, _pad;
   const float *pl, *ul, *vl, *wl, *zetal, *zeta_dotl;
   int64_t sxl, syl;
+  /* further fields for module_meteo, MPB_F2_* (strides like ps) and MPB_F3_* (strides like u); NULL = not given */
+  const float *x2[MPB_NX2];
+  const float *x3[MPB_NX3];
 } mpb_met_view_t;
 
 /* Parameters of the gridded-output binning (write_grid, src/mptrac.c:13752 ff.). */

@@ -363,6 +363,61 @@ __global__ void __launch_bounds__(128) meteo_kernel(const __grid_constant__ Mete
   if (A.qnt[MPB_Q_ZETA_D] >= 0) set(MPB_Q_ZETA_D, zeta_diagnosed(m.ps, a.p, m.t));
 }
 
+// module_meteo, the quantities that need further met fields (INTPOL_TIME_ALL's other 9 3-D and 22 2-D fields) and the
+// ones derived from temperature and water vapour: same stencil and time weight as meteo_kernel, fields that were not
+// asked for are not touched
+struct MeteoFieldArgs {
+  MetView met;
+  const double *time, *lon, *lat, *p;
+  double *q;
+  long long q_stride, np;
+  const float2 *x2[MPB_NX2], *x3[MPB_NX3];   // null = not wanted
+  int qnt[MPB_METEO_SLOTS];
+  int moist;                                 // any of PW .. TICE wanted
+};
+
+__global__ void __launch_bounds__(128) meteo_fields_kernel(const __grid_constant__ MeteoFieldArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np) return;
+  Parcel a;
+  a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
+  CubeT<true> cube;
+  cube_reset(cube);
+  Stencil s;
+  locate(A.met, a.lon, a.lat, a.p, cube, s);
+  const double wt = time_weight(A.met, a.time);
+  auto set = [&](int slot, double v) { A.q[(long long)A.qnt[slot] * A.q_stride + ip] = v; };
+#pragma unroll 1
+  for (int f = 0; f < MPB_NX2; f++)
+    if (A.x2[f] && A.qnt[MPB_Q_TS + f] >= 0) set(MPB_Q_TS + f, field2_at(A.met, A.x2[f], s, wt));
+#pragma unroll 1
+  for (int f = 0; f < MPB_NX3; f++)
+    if (A.x3[f] && A.qnt[MPB_Q_ZG + f] >= 0) set(MPB_Q_ZG + f, field3_at(A.met, A.x3[f], s, wt));
+  if (A.moist) {
+    const double t = lerp_f64(wt, MPB_TRILERP_OF(cube, s, t0), MPB_TRILERP_OF(cube, s, t1));
+    MoistValues w;
+    moist_at(a.p, t, field3_at(A.met, A.x3[MPB_F3_H2O], s, wt), w);
+    if (A.qnt[MPB_Q_PW] >= 0) set(MPB_Q_PW, w.pw);
+    if (A.qnt[MPB_Q_SH] >= 0) set(MPB_Q_SH, w.sh);
+    if (A.qnt[MPB_Q_RH] >= 0) set(MPB_Q_RH, w.rh);
+    if (A.qnt[MPB_Q_RHICE] >= 0) set(MPB_Q_RHICE, w.rhice);
+    if (A.qnt[MPB_Q_TVIRT] >= 0) set(MPB_Q_TVIRT, w.tvirt);
+    if (A.qnt[MPB_Q_LAPSE] >= 0) set(MPB_Q_LAPSE, w.lapse);
+    if (A.qnt[MPB_Q_TDEW] >= 0) set(MPB_Q_TDEW, w.tdew);
+    if (A.qnt[MPB_Q_TICE] >= 0) set(MPB_Q_TICE, w.tice);
+  }
+}
+
+// dst[2 i + slot] = src[i]: one time level of a further field into its interleaved array
+__global__ void pack_scalar_kernel(const float *src, float *dst, int slot, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[2 * i + slot] = src[i];
+}
+__global__ void swap_pairs_kernel(float2 *a, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float2 v = a[i]; a[i] = make_float2(v.y, v.x); }
+}
+
 // module_advect on model levels (src/mptrac.c:3646-3657, 3680-3757) and module_advect_init (3762-3785): one parcel per
 // thread, dt from the cache (the fused kernel's timesteps segment ran before)
 struct LevelArgs {
@@ -552,6 +607,9 @@ struct mpb_ctx {
   size_t lev_cap = 0;
   bool lev_valid[2] = {false, false};
   unsigned short *lev_hint = nullptr;              // LevelArgs::hint
+  // further fields for module_meteo (mpb_met_view_t::x2 / x3): per field one array, both time levels of a node adjacent
+  float2 *x2[MPB_NX2] = {}, *x3[MPB_NX3] = {};
+  bool x2_valid[2][MPB_NX2] = {}, x3_valid[2][MPB_NX3] = {};
 
   // clim
   double *cl_time = nullptr, *cl_lat = nullptr, *cl_tropo = nullptr;
@@ -845,10 +903,44 @@ static bool meteo_wanted(const mpb_ctl_t &k) {
   for (int i = 0; i < MPB_NMETEO; i++) if (k.qnt_meteo[i] >= 0) return true;
   return false;
 }
+static bool meteo_wanted(const mpb_ctl_t &k, int first, int last) {
+  for (int i = first; i <= last; i++) if (k.qnt_meteo[i] >= 0) return true;
+  return false;
+}
+
+static void launch_meteo_fields(mpb_ctx *c) {
+  const mpb_ctl_t &k = c->ctl;
+  MeteoFieldArgs A;
+  A.met = met_view(c);
+  A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p();
+  A.q = c->nq ? c->q(0) : nullptr; A.q_stride = c->np_max; A.np = c->np;
+  for (int i = 0; i < MPB_METEO_SLOTS; i++) {
+    A.qnt[i] = i < MPB_NMETEO ? k.qnt_meteo[i] : -1;
+    REQUIRE(A.qnt[i] < c->nq, "meteo quantity index out of range");
+  }
+  A.moist = meteo_wanted(k, MPB_Q_PW, MPB_Q_TICE) ? 1 : 0;
+  for (int f = 0; f < MPB_NX2; f++) {
+    const bool want = k.qnt_meteo[MPB_Q_TS + f] >= 0;
+    REQUIRE(!want || (c->x2[f] && c->x2_valid[0][f] && c->x2_valid[1][f]),
+            "a module_meteo quantity needs a 2-D met field that was not given for both levels (mpb_met_view_t::x2)");
+    A.x2[f] = want ? c->x2[f] : nullptr;
+  }
+  for (int f = 0; f < MPB_NX3; f++) {
+    const bool want = k.qnt_meteo[MPB_Q_ZG + f] >= 0 || (f == MPB_F3_H2O && A.moist);
+    REQUIRE(!want || (c->x3[f] && c->x3_valid[0][f] && c->x3_valid[1][f]),
+            "a module_meteo quantity needs a 3-D met field that was not given for both levels (mpb_met_view_t::x3)");
+    A.x3[f] = want ? c->x3[f] : nullptr;
+  }
+  meteo_fields_kernel<<<nblocks(c->np, 128), 128, 0, c->stream>>>(A);
+  CK(cudaGetLastError());
+  c->launches++;
+}
 
 static void launch_meteo(mpb_ctx *c) {
   REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
   if (c->np == 0 || !meteo_wanted(c->ctl)) return;
+  if (meteo_wanted(c->ctl, MPB_Q_TS, MPB_NMETEO - 1)) launch_meteo_fields(c);
+  if (!meteo_wanted(c->ctl, MPB_Q_PS, MPB_Q_ZETA_D)) return;
   MeteoArgs A;
   A.met = met_view(c);
   A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p();
@@ -916,6 +1008,8 @@ int mpb_destroy(mpb_ctx *c) {
                   c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_sum, c->mix_cnt,
                   c->grid_sum, c->grid_sq, c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz, c->lev_hint};
   for (void *p : ptrs) if (p) cudaFree(p);
+  for (float2 *p : c->x2) if (p) cudaFree(p);
+  for (float2 *p : c->x3) if (p) cudaFree(p);
   if (c->stage_h) cudaFreeHost(c->stage_h);
   for (int i = 0; i < kLanes; i++) {
     if (c->lane[i]) cudaStreamDestroy(c->lane[i]);
@@ -987,6 +1081,8 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
     // a new grid invalidates the other level too (src/mptrac.c:6545-6558 demands identical grids)
     c->lev[0].valid = c->lev[1].valid = false;
     c->lev_valid[0] = c->lev_valid[1] = false;
+    for (int f = 0; f < MPB_NX2; f++) { if (c->x2[f]) CK(cudaFree(c->x2[f])); c->x2[f] = nullptr; c->x2_valid[0][f] = c->x2_valid[1][f] = false; }
+    for (int f = 0; f < MPB_NX3; f++) { if (c->x3[f]) CK(cudaFree(c->x3[f])); c->x3[f] = nullptr; c->x3_valid[0][f] = c->x3_valid[1][f] = false; }
     c->nx = m->nx; c->ny = m->ny; c->nz = m->np; c->coord_type = m->coord_type;
     if (nnode > c->node_cap) {
       if (c->nodes) CK(cudaFree(c->nodes));
@@ -1103,6 +1199,36 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
     c->launches += 3;
     c->lev_valid[slot] = true;
   }
+  // further fields for module_meteo: one interleaved array per field, filled level by level
+  auto put_field = [&](const float *src, float2 **dst, size_t n, bool three_d) {
+    if (!*dst) {
+      CK(cudaMalloc(dst, sizeof(float2) * n));
+      CK(cudaMemsetAsync(*dst, 0, sizeof(float2) * n, c->stream));
+    }
+    float *h = c->stage_h;
+    if (three_d) {
+#pragma omp parallel for collapse(2) schedule(static)
+      for (int ix = 0; ix < m->nx; ix++)
+        for (int iy = 0; iy < m->ny; iy++)
+          std::memcpy(h + ((size_t)ix * m->ny + iy) * m->np, src + (size_t)ix * m->sx + (size_t)iy * m->sy, sizeof(float) * (size_t)m->np);
+    } else {
+      for (int ix = 0; ix < m->nx; ix++)
+        std::memcpy(h + (size_t)ix * m->ny, src + (size_t)ix * m->sx2, sizeof(float) * (size_t)m->ny);
+    }
+    CK(cudaMemcpyAsync(c->stage_d, h, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    pack_scalar_kernel<<<nblocks((long long)n, 256), 256, 0, c->stream>>>(c->stage_d, (float *)*dst, slot, n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));   // the staging area is reused by the next field
+    c->launches++;
+  };
+  for (int f = 0; f < MPB_NX2; f++) {
+    c->x2_valid[slot][f] = false;
+    if (m->x2[f]) { put_field(m->x2[f], &c->x2[f], ncol, false); c->x2_valid[slot][f] = true; }
+  }
+  for (int f = 0; f < MPB_NX3; f++) {
+    c->x3_valid[slot][f] = false;
+    if (m->x3[f]) { put_field(m->x3[f], &c->x3[f], nnode, true); c->x3_valid[slot][f] = true; }
+  }
   c->lev[slot].time = m->time;
   c->lev[slot].valid = true;
   API_END
@@ -1118,6 +1244,15 @@ int mpb_swap_met(mpb_ctx *c) {
     CK(cudaGetLastError());
     c->launches++;
   }
+  for (int f = 0; f < MPB_NX2; f++) {
+    std::swap(c->x2_valid[0][f], c->x2_valid[1][f]);
+    if (c->x2[f]) { swap_pairs_kernel<<<nblocks((long long)ncol, 256), 256, 0, c->stream>>>(c->x2[f], ncol); c->launches++; }
+  }
+  for (int f = 0; f < MPB_NX3; f++) {
+    std::swap(c->x3_valid[0][f], c->x3_valid[1][f]);
+    if (c->x3[f]) { swap_pairs_kernel<<<nblocks((long long)nnode, 256), 256, 0, c->stream>>>(c->x3[f], nnode); c->launches++; }
+  }
+  CK(cudaGetLastError());
   std::swap(c->lev_valid[0], c->lev_valid[1]);
   const size_t nlev = ncol * (size_t)c->npl;
   if (nlev > 0 && c->lev_p) {

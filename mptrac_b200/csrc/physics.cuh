@@ -550,6 +550,14 @@ MPB_HD double lerp_col(double w, float lo_or_diff, float hi) {
            lerp_f64(s.wy, lerp_col<DIFF>(s.wz, c.n100.member, c.n101.member),  \
                     lerp_col<DIFF>(s.wz, c.n110.member, c.n111.member)))
 
+// the same on a named cube and stencil (DIFF cube: CubeT<true>)
+#define MPB_TRILERP_OF(c, s, member)                                                  \
+  lerp_f64((s).wx,                                                                    \
+           lerp_f64((s).wy, lerp_col<true>((s).wz, (c).n000.member, (c).n001.member), \
+                    lerp_col<true>((s).wz, (c).n010.member, (c).n011.member)),        \
+           lerp_f64((s).wy, lerp_col<true>((s).wz, (c).n100.member, (c).n101.member), \
+                    lerp_col<true>((s).wz, (c).n110.member, (c).n111.member)))
+
 // Stencil of (lon, lat, p) with the cube made to hold its cell: indices + weights of intpol_met_space_3d's init part
 // (2997-3021).  INVARIANT: whenever c.ax names a cell, the cube holds that cell (every path that moves c.ax fetches).
 // Production device build: ONE combined test "still inside the cell the cube holds" decides between the register-only
@@ -1281,7 +1289,47 @@ MPB_HD void meteo_at(const MetView &g, const Parcel &a, CubeT<DIFF> &c, MeteoVal
                              bilerp_guarded(s.wx, s.wy, a00.w, a01.w, a10.w, a11.w));
 }
 
+// One further field of INTPOL_TIME_ALL (src/mptrac.h:1278-1316) at a stencil that is already located; the two time
+// levels of a node sit next to each other (.x = met0, .y = met1).  3-D: intpol_met_space_3d per level (3023-3043), plain
+// time blend (3133-3136); 2-D: intpol_met_space_2d with its nearest-neighbour rule for non-finite data and the guarded
+// time blend (3084-3107, 3163-3169).
+MPB_HD double field3_at(const MetView &g, const float2 *f, const Stencil &s, double wt) {
+  const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * (size_t)g.nz;
+  const float2 *b = f + ((size_t)s.ix * sx + (size_t)s.iy * sy + (size_t)s.iz);
+  const float2 n000 = ldg(b), n001 = ldg(b + 1), n010 = ldg(b + sy), n011 = ldg(b + sy + 1);
+  const float2 n100 = ldg(b + sx), n101 = ldg(b + sx + 1), n110 = ldg(b + sx + sy), n111 = ldg(b + sx + sy + 1);
+  const double v0 = lerp_f64(s.wx, lerp_f64(s.wy, lerp_col<false>(s.wz, n000.x, n001.x), lerp_col<false>(s.wz, n010.x, n011.x)),
+                             lerp_f64(s.wy, lerp_col<false>(s.wz, n100.x, n101.x), lerp_col<false>(s.wz, n110.x, n111.x)));
+  const double v1 = lerp_f64(s.wx, lerp_f64(s.wy, lerp_col<false>(s.wz, n000.y, n001.y), lerp_col<false>(s.wz, n010.y, n011.y)),
+                             lerp_f64(s.wy, lerp_col<false>(s.wz, n100.y, n101.y), lerp_col<false>(s.wz, n110.y, n111.y)));
+  return lerp_f64(wt, v0, v1);
+}
+MPB_HD double field2_at(const MetView &g, const float2 *f, const Stencil &s, double wt) {
+  const size_t b = (size_t)s.ix * (size_t)g.ny + (size_t)s.iy, sx = (size_t)g.ny;
+  const float2 a00 = ldg(f + b), a01 = ldg(f + b + 1), a10 = ldg(f + b + sx), a11 = ldg(f + b + sx + 1);
+  return time_blend_guarded(wt, bilerp_guarded(s.wx, s.wy, a00.x, a01.x, a10.x, a11.x),
+                            bilerp_guarded(s.wx, s.wy, a00.y, a01.y, a10.y, a11.y));
+}
+
 constexpr double kT0 = 273.15, kKappa = 0.286;
+constexpr double kEps = 18.01528 / 28.9644, kLV = 2501000., kCpd = 1003.5;   // EPS = MH2O / MA, LV, CPD (src/mptrac.h:260, 275, 255)
+// the quantities module_meteo derives from temperature and water vapour (5136-5152)
+struct MoistValues {
+  double pw, sh, rh, rhice, tvirt, lapse, tdew, tice;
+};
+MPB_HD void moist_at(double p, double t, double h2o, MoistValues &m) {
+  const double hh = h2o > 0.1e-6 ? h2o : 0.1e-6;                      // MAX((h2o), 0.1e-6)
+  m.pw = p * hh / (1. + (1. - kEps) * hh);                             // PW, src/mptrac.h:1859
+  m.sh = kEps * hh;                                                    // SH :2024
+  m.rh = m.pw / (6.112 * exp(17.62 * (t - kT0) / (243.12 + t - kT0))) * 100.;    // RH :1906
+  m.rhice = m.pw / (6.112 * exp(22.46 * (t - kT0) / (272.62 + t - kT0))) * 100.; // RHICE :1936
+  m.tvirt = t * (1. + (1. - kEps) * hh);                               // TVIRT :2199
+  const double a = kRA * (t * t), r = m.sh / (1. - m.sh);              // lapse_rate, src/mptrac.c:3324-3338
+  m.lapse = 1e3 * kG0 * (a + kLV * r * t) / (kCpd * a + (kLV * kLV) * r * kEps);
+  m.tdew = kT0 + 243.12 * log(m.pw / 6.112) / (17.62 - log(m.pw / 6.112));       // TDEW :2075
+  m.tice = kT0 + 272.62 * log(m.pw / 6.112) / (22.46 - log(m.pw / 6.112));       // TICE :2100
+}
+
 MPB_HD double potential_temperature(double p, double t) { return t * pow(1000. / p, kKappa); }   // THETA, src/mptrac.h:2124
 MPB_HD double saturation_pressure(double t) { return 6.112 * exp(17.62 * (t - kT0) / (243.12 + t - kT0)); }      // PSAT :1808
 MPB_HD double saturation_pressure_ice(double t) { return 6.112 * exp(22.46 * (t - kT0) / (272.62 + t - kT0)); }  // PSICE :1832

@@ -51,6 +51,16 @@ static void ensure_ctx(const ctl_t *ctl, int np) {
   if (verbose()) printf("mptrac_b200: device context for %d parcels, %d quantities on GPU %d\n", np, ctl->nq, dev);
 }
 
+/* MPTRAC_B200_DEVICE_METEO_FIELDS=1: module_meteo quantities that read further met fields (zg, pv, h2o, o3, cloud and
+ * surface fields, rh ...) are computed on the device too; the fields they need are uploaded with each met level.  Off by
+ * default in this version: the device code is pinned on the host (tests/test_hostemu.py), its GPU parity run is pending. */
+static int device_meteo_fields(void) {
+  static int on = -1;
+  if (on < 0) on = getenv("MPTRAC_B200_DEVICE_METEO_FIELDS") ? atoi(getenv("MPTRAC_B200_DEVICE_METEO_FIELDS")) : 0;
+  return on;
+}
+static int g_fields, g_need2[MPB_NX2], g_need3[MPB_NX3];
+
 static int g_levels;   /* the control file advects on model levels: the met uploads carry pl, ul, vl, wl, zetal, zeta_dotl */
 
 static void put_ctl(const ctl_t *c) {
@@ -84,6 +94,18 @@ static void put_ctl(const ctl_t *c) {
   k.qnt_meteo[MPB_Q_PSICE] = c->qnt_psice; k.qnt_meteo[MPB_Q_ZETA_D] = c->qnt_zeta_d;
   k.qnt_zeta = c->qnt_zeta; k.qnt_eta = c->qnt_eta;
   g_levels = c->advect_vert_coord != 0;
+  g_fields = device_meteo_fields();
+  memset(g_need2, 0, sizeof(g_need2)); memset(g_need3, 0, sizeof(g_need3));
+  if (g_fields) {
+    const int q2[MPB_NX2] = {c->qnt_ts, c->qnt_zs, c->qnt_us, c->qnt_vs, c->qnt_ess, c->qnt_nss, c->qnt_shf, c->qnt_lsm, c->qnt_sst,
+                             c->qnt_pt, c->qnt_tt, c->qnt_zt, c->qnt_h2ot, c->qnt_pct, c->qnt_pcb, c->qnt_cl, c->qnt_plcl, c->qnt_plfc,
+                             c->qnt_pel, c->qnt_cape, c->qnt_cin, c->qnt_o3c};
+    const int q3[MPB_NX3] = {c->qnt_zg, c->qnt_pv, c->qnt_h2o, c->qnt_o3, c->qnt_lwc, c->qnt_rwc, c->qnt_iwc, c->qnt_swc, c->qnt_cc};
+    const int qm[8] = {c->qnt_pw, c->qnt_sh, c->qnt_rh, c->qnt_rhice, c->qnt_tvirt, c->qnt_lapse, c->qnt_tdew, c->qnt_tice};
+    for (int f = 0; f < MPB_NX2; f++) { k.qnt_meteo[MPB_Q_TS + f] = q2[f]; g_need2[f] = q2[f] >= 0; }
+    for (int f = 0; f < MPB_NX3; f++) { k.qnt_meteo[MPB_Q_ZG + f] = q3[f]; g_need3[f] = q3[f] >= 0; }
+    for (int i = 0; i < 8; i++) { k.qnt_meteo[MPB_Q_PW + i] = qm[i]; if (qm[i] >= 0) g_need3[MPB_F3_H2O] = 1; }
+  }
   MPB(mpb_set_ctl(g_ctx, &k));
 }
 
@@ -93,6 +115,11 @@ static int meteo_needs_host(const ctl_t *c) {
   static int force = -1;   /* MPTRAC_B200_HOST_METEO=1 keeps module_meteo on the reference's CPU code (hybrid mode) */
   if (force < 0) force = getenv("MPTRAC_B200_HOST_METEO") ? atoi(getenv("MPTRAC_B200_HOST_METEO")) : 0;
   if (force) return 1;
+  if (device_meteo_fields()) {
+    const int clim_q[] = {c->qnt_hno3, c->qnt_oh, c->qnt_h2o2, c->qnt_ho2, c->qnt_o1d, c->qnt_tnat, c->qnt_tsts};
+    for (size_t i = 0; i < sizeof(clim_q) / sizeof(clim_q[0]); i++) if (clim_q[i] >= 0) return 1;
+    return 0;
+  }
   const int other[] = {
     c->qnt_ts, c->qnt_zs, c->qnt_us, c->qnt_vs, c->qnt_ess, c->qnt_nss, c->qnt_shf, c->qnt_lsm, c->qnt_sst, c->qnt_pt,
     c->qnt_tt, c->qnt_zt, c->qnt_h2ot, c->qnt_zg, c->qnt_h2o, c->qnt_o3, c->qnt_lwc, c->qnt_rwc, c->qnt_iwc, c->qnt_swc,
@@ -108,6 +135,7 @@ static void put_met(met_t *m) {
   for (int i = 0; i < 2; i++) if (g_slot[i] == m) s = i;
   if (s < 0) s = (g_slot[0] == NULL) ? 0 : (g_slot[1] == NULL ? 1 : 0);
   mpb_met_view_t v;
+  memset(&v, 0, sizeof(v));
   v.time = m->time; v.coord_type = m->coord_type; v.nx = m->nx; v.ny = m->ny; v.np = m->np;
   v.lon = m->lon; v.lat = m->lat; v.p = m->p;
   v.u = &m->u[0][0][0]; v.v = &m->v[0][0][0]; v.w = &m->w[0][0][0]; v.t = &m->t[0][0][0];
@@ -119,6 +147,16 @@ static void put_met(met_t *m) {
     v.npl = m->npl;
     v.pl = &m->pl[0][0][0]; v.ul = &m->ul[0][0][0]; v.vl = &m->vl[0][0][0]; v.wl = &m->wl[0][0][0];
     v.zetal = &m->zetal[0][0][0]; v.zeta_dotl = &m->zeta_dotl[0][0][0];
+  }
+  if (g_fields) {   /* the further fields the control file's module_meteo quantities read (device_meteo_fields()) */
+    const float *f2[MPB_NX2] = {&m->ts[0][0], &m->zs[0][0], &m->us[0][0], &m->vs[0][0], &m->ess[0][0], &m->nss[0][0], &m->shf[0][0],
+                                &m->lsm[0][0], &m->sst[0][0], &m->pt[0][0], &m->tt[0][0], &m->zt[0][0], &m->h2ot[0][0], &m->pct[0][0],
+                                &m->pcb[0][0], &m->cl[0][0], &m->plcl[0][0], &m->plfc[0][0], &m->pel[0][0], &m->cape[0][0],
+                                &m->cin[0][0], &m->o3c[0][0]};
+    const float *f3[MPB_NX3] = {&m->z[0][0][0], &m->pv[0][0][0], &m->h2o[0][0][0], &m->o3[0][0][0], &m->lwc[0][0][0],
+                                &m->rwc[0][0][0], &m->iwc[0][0][0], &m->swc[0][0][0], &m->cc[0][0][0]};
+    for (int f = 0; f < MPB_NX2; f++) if (g_need2[f]) v.x2[f] = f2[f];
+    for (int f = 0; f < MPB_NX3; f++) if (g_need3[f]) v.x3[f] = f3[f];
   }
   MPB(mpb_set_met(g_ctx, s, &v));
   g_slot[s] = m;

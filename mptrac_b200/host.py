@@ -20,8 +20,15 @@ import numpy as np
 
 MIX_MAXQ = 23
 # quantities module_meteo can set on the device, in the slot order of mpb_ctl_t::qnt_meteo (MPB_Q_*)
-METEO_QNT = ("ps", "pbl", "p", "t", "rho", "u", "v", "w", "vh", "vz", "theta", "psat", "psice", "zeta_d")
-METEO_SLOTS = 16
+METEO_QNT = ("ps", "pbl", "p", "t", "rho", "u", "v", "w", "vh", "vz", "theta", "psat", "psice", "zeta_d",
+             "ts", "zs", "us", "vs", "ess", "nss", "shf", "lsm", "sst", "pt", "tt", "zt", "h2ot", "pct", "pcb", "cl", "plcl", "plfc",
+             "pel", "cape", "cin", "o3c",
+             "zg", "pv", "h2o", "o3", "lwc", "rwc", "iwc", "swc", "cc",
+             "pw", "sh", "rh", "rhice", "tvirt", "lapse", "tdew", "tice")
+METEO_SLOTS = 64
+# further met fields module_meteo interpolates (mpb_met_view_t::x2 / x3, MPB_F2_* / MPB_F3_*): Met.extra[name]
+MET_X2 = ("ts", "zs", "us", "vs", "ess", "nss", "shf", "lsm", "sst", "pt", "tt", "zt", "h2ot", "pct", "pcb", "cl", "plcl", "plfc", "pel", "cape", "cin", "o3c")   # [nx][ny]
+MET_X3 = ("z", "pv", "h2o", "o3", "lwc", "rwc", "iwc", "swc", "cc")   # [nx][ny][np]; "z" is the geopotential height that quantity zg reports
 # module bits of mpb_run_modules (include/mptrac_b200.h MPB_MOD_*)
 (MOD_TIMESTEPS, MOD_SORT, MOD_POSITION0, MOD_ADVECT, MOD_DIFF_TURB, MOD_DIFF_MESO, MOD_SEDI, MOD_POSITION1, MOD_MIXING,
  MOD_METEO) = (1 << i for i in range(10))
@@ -62,6 +69,7 @@ class _MetViewStruct(C.Structure):
         ("pl", C.c_void_p), ("ul", C.c_void_p), ("vl", C.c_void_p), ("wl", C.c_void_p),
         ("zetal", C.c_void_p), ("zeta_dotl", C.c_void_p),
         ("sxl", C.c_int64), ("syl", C.c_int64),
+        ("x2", C.c_void_p * len(MET_X2)), ("x3", C.c_void_p * len(MET_X3)),
     ]
 
 
@@ -159,6 +167,8 @@ class Met:
     wl: Optional[np.ndarray] = None
     zetal: Optional[np.ndarray] = None
     zeta_dotl: Optional[np.ndarray] = None
+    # further fields for module_meteo, by name (MET_X2: [nx][ny], MET_X3: [nx][ny][np])
+    extra: Dict[str, np.ndarray] = field(default_factory=dict)
 
     def __post_init__(self):
         self.lon = np.ascontiguousarray(self.lon, dtype=np.float64)
@@ -188,6 +198,14 @@ class Met:
                 if a.ndim != 3 or a.shape != (shp3[0], shp3[1], npl):
                     raise ValueError(f"model-level field {n} has shape {a.shape}, expected {(shp3[0], shp3[1], npl)}")
                 setattr(self, n, a)
+        for n in list(self.extra):
+            if n not in MET_X2 and n not in MET_X3:
+                raise ValueError(f"unknown met field {n!r} (known: {MET_X2 + MET_X3})")
+            want = shp3 if n in MET_X3 else shp3[:2]
+            a = np.ascontiguousarray(self.extra[n], dtype=np.float32)
+            if a.shape != want:
+                raise ValueError(f"met field {n} has shape {a.shape}, expected {want}")
+            self.extra[n] = a
 
     def view(self) -> _MetViewStruct:
         nx, ny, nz = self.lon.size, self.lat.size, self.p.size
@@ -204,6 +222,10 @@ class Met:
             setattr(s, n, a.ctypes.data if a is not None else None)
             npl = a.shape[2] if a is not None else npl
         s.npl, s.sxl, s.syl = npl, ny * npl, npl
+        for i, n in enumerate(MET_X2):
+            s.x2[i] = self.extra[n].ctypes.data if n in self.extra else None
+        for i, n in enumerate(MET_X3):
+            s.x3[i] = self.extra[n].ctypes.data if n in self.extra else None
         return s
 
 

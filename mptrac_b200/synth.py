@@ -112,3 +112,57 @@ def add_model_levels(met: Met, npl=None, seed=7) -> Met:
         out.append(a)
     from dataclasses import replace
     return replace(met, pl=out[0], ul=out[1], vl=out[2], wl=out[3], zetal=out[4], zeta_dotl=out[5])
+
+
+def add_meteo_fields(met: Met, seed=11, with_gaps=True) -> Met:
+    """The further fields module_meteo interpolates (``Met.extra``): smooth synthetic geopotential height, potential
+    vorticity, water vapour, ozone, cloud water contents and cover on the 3-D grid; surface, tropopause, cloud and
+    convective 2-D fields.  ``with_gaps`` puts NaNs into a few 2-D fields the way the reference's diagnostics do (no
+    cloud, no free-convection level), which exercises the nearest-neighbour rule of the 2-D interpolation."""
+    from dataclasses import replace
+    from .host import MET_X2, MET_X3
+    nx, ny, nz = met.u.shape
+    rng = np.random.default_rng(seed + int(met.time) % 977)
+    lam = np.deg2rad(met.lon)[:, None, None]
+    phi = np.deg2rad(met.lat)[None, :, None]
+    z = (H0 * np.log(P0 / met.p))[None, None, :]
+    wave = np.sin(2 * lam + 0.2 * met.time / 21600.0) * np.cos(phi)
+    extra = {
+        "z": z * (1.0 + 0.01 * wave) + 0.0 * lam,
+        "pv": 0.3 * np.sign(np.sin(phi)) * np.exp(z / 7.0) * (1.0 + 0.2 * wave) * (np.abs(np.sin(phi)) + 0.05),
+        "h2o": 0.02 * np.exp(-z / 2.2) * (1.0 + 0.5 * wave) + 3e-6,
+        "o3": 8e-6 * np.exp(-((z - 32.0) / 9.0) ** 2) * (1.0 + 0.1 * wave) + 2e-8,
+        "lwc": 2e-5 * np.exp(-((z - 2.0) / 1.5) ** 2) * np.maximum(wave, 0.0),
+        "rwc": 1e-5 * np.exp(-((z - 1.5) / 1.0) ** 2) * np.maximum(wave, 0.0),
+        "iwc": 1e-5 * np.exp(-((z - 9.0) / 2.0) ** 2) * np.maximum(-wave, 0.0),
+        "swc": 5e-6 * np.exp(-((z - 6.0) / 2.0) ** 2) * np.maximum(-wave, 0.0),
+        "cc": np.clip(0.5 * np.exp(-((z - 4.0) / 3.0) ** 2) * (1.0 + wave), 0.0, 1.0),
+    }
+    lam2, phi2 = lam[:, :, 0], phi[:, :, 0]
+    w2 = np.sin(3 * lam2 + 0.1 * met.time / 21600.0) * np.cos(phi2)
+    two = {
+        "ts": 288.0 - 40.0 * np.sin(phi2) ** 2 + 3.0 * w2, "zs": 0.5 * (1.0 + w2) * np.cos(phi2) ** 2,
+        "us": 5.0 * np.cos(phi2) + 2.0 * w2, "vs": 2.0 * w2, "ess": 0.1 * w2, "nss": -0.05 * w2, "shf": 50.0 * (1.0 + w2),
+        "lsm": (w2 > 0.2).astype(np.float64), "sst": 290.0 - 25.0 * np.sin(phi2) ** 2 + w2,
+        "pt": 100.0 + 200.0 * np.sin(phi2) ** 2 + 10.0 * w2, "tt": 200.0 + 15.0 * np.sin(phi2) ** 2 + w2,
+        "zt": 17.0 - 9.0 * np.sin(phi2) ** 2 + 0.3 * w2, "h2ot": 4e-6 * (1.0 + 0.2 * w2),
+        "pct": 300.0 + 100.0 * w2, "pcb": 850.0 + 50.0 * w2, "cl": 0.2 * (1.0 + w2),
+        "plcl": 900.0 + 30.0 * w2, "plfc": 800.0 + 50.0 * w2, "pel": 250.0 + 60.0 * w2,
+        "cape": 500.0 * np.maximum(w2, 0.0), "cin": 50.0 * np.maximum(-w2, 0.0), "o3c": 300.0 + 60.0 * np.sin(phi2) ** 2 + 10.0 * w2,
+    }
+    for k in two:
+        two[k] = two[k] + 0.0 * lam2
+    if with_gaps:
+        for k in ("pct", "pcb", "plfc", "pel"):
+            a = np.array(np.broadcast_to(two[k], (nx, ny)), dtype=np.float64)
+            a[rng.uniform(size=a.shape) < 0.15] = np.nan
+            two[k] = a
+    extra.update(two)
+    out = {}
+    for k, a in extra.items():
+        shape = (nx, ny, nz) if k in MET_X3 else (nx, ny)
+        a = np.array(np.broadcast_to(a, shape), dtype=np.float32)
+        a[-1] = a[0]                     # periodic wrap column
+        out[k] = a
+    assert set(out) == set(MET_X2) | set(MET_X3)
+    return replace(met, extra=out)

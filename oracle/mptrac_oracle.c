@@ -747,6 +747,10 @@ void orc_grid_bin(const orc_atm_t *atm, int nq, int nx, int ny, int nz, double l
  * other field -- 3-D and 2-D -- reuses them; all parcels are visited (check_dt = 0).
  * ------------------------------------------------------------------------------------------- */
 #define C_T0 273.15
+#define C_MH2O 18.01528              /* mptrac.h:295 */
+#define C_EPS (C_MH2O / C_MA)        /* mptrac.h:260 */
+#define C_LV 2501000.                /* mptrac.h:275 */
+#define C_CPD 1003.5                 /* mptrac.h:255 */
 #define C_KAPPA 0.286
 static double theta_of(double p, double t) { return t * pow(1000. / p, C_KAPPA); }   /* THETA, mptrac.h:2124 */
 
@@ -777,6 +781,32 @@ void orc_module_meteo(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met
     SETQ(11, 6.112 * exp(17.62 * (t - C_T0) / (243.12 + t - C_T0)));   /* PSAT, mptrac.h:1808 */
     SETQ(12, 6.112 * exp(22.46 * (t - C_T0) / (272.62 + t - C_T0)));   /* PSICE, mptrac.h:1832 */
     SETQ(13, (p / ps <= 0.3 ? 1. : sin(M_PI / 2. * (1. - p / ps) / (1. - 0.3))) * theta_of(p, t));   /* ZETA, mptrac.h:2293 */
+    /* the other fields of INTPOL_TIME_ALL, same stencil */
+    for (int f = 0; f < ORC_NX2; f++)
+      if (qi[14 + f] >= 0 && met0->x2[f] && met1->x2[f])
+        SETQ(14 + f, time2(met0, met0->x2[f], met1, met1->x2[f], tm, lon, lat, &c, 0));
+    for (int f = 0; f < ORC_NX3; f++)
+      if (qi[36 + f] >= 0 && met0->x3[f] && met1->x3[f])
+        SETQ(36 + f, time3(met0, met0->x3[f], met1, met1->x3[f], tm, p, lon, lat, &c, 0));
+    int moist = 0;
+    for (int k = 45; k <= 52; k++) moist |= qi[k] >= 0;
+    if (moist && met0->x3[2] && met1->x3[2]) {
+      const double h2o = time3(met0, met0->x3[2], met1, met1->x3[2], tm, p, lon, lat, &c, 0);
+      const double hh = h2o > 0.1e-6 ? h2o : 0.1e-6;                       /* MAX((h2o), 0.1e-6) */
+      const double pw = p * hh / (1. + (1. - C_EPS) * hh);                 /* PW, mptrac.h:1859 */
+      const double sh = C_EPS * hh;                                        /* SH, mptrac.h:2024 */
+      SETQ(45, pw);
+      SETQ(46, sh);
+      SETQ(47, pw / (6.112 * exp(17.62 * (t - C_T0) / (243.12 + t - C_T0))) * 100.);   /* RH, mptrac.h:1906 */
+      SETQ(48, pw / (6.112 * exp(22.46 * (t - C_T0) / (272.62 + t - C_T0))) * 100.);   /* RHICE, mptrac.h:1936 */
+      SETQ(49, t * (1. + (1. - C_EPS) * hh));                              /* TVIRT, mptrac.h:2199 */
+      {                                                                    /* lapse_rate, src/mptrac.c:3324-3338 */
+        const double a = C_RA * (t * t), r = sh / (1. - sh);
+        SETQ(50, 1e3 * C_G0 * (a + C_LV * r * t) / (C_CPD * a + (C_LV * C_LV) * r * C_EPS));
+      }
+      SETQ(51, C_T0 + 243.12 * log(pw / 6.112) / (17.62 - log(pw / 6.112)));   /* TDEW, mptrac.h:2075 */
+      SETQ(52, C_T0 + 272.62 * log(pw / 6.112) / (22.46 - log(pw / 6.112)));   /* TICE, mptrac.h:2100 */
+    }
 #undef SETQ
   }
 }

@@ -19,8 +19,15 @@
 #include <stdint.h>
 
 #define ORC_MIX_MAXQ 23
-#define ORC_METEO_SLOTS 16
-/* slots of orc_ctl_t::qnt_meteo: ps, pbl, p, t, rho, u, v, w, vh, vz, theta, psat, psice, zeta_d */
+#define ORC_METEO_SLOTS 64
+#define ORC_NX2 22
+#define ORC_NX3 9
+/* slots of orc_ctl_t::qnt_meteo:
+ *    0-13  ps, pbl, p, t, rho, u, v, w, vh, vz, theta, psat, psice, zeta_d
+ *   14-35  the 2-D fields of orc_met_t::x2 in their order: ts, zs, us, vs, ess, nss, shf, lsm, sst, pt, tt, zt, h2ot, pct,
+ *          pcb, cl, plcl, plfc, pel, cape, cin, o3c
+ *   36-44  the 3-D fields of orc_met_t::x3 in their order: zg (met_t::z), pv, h2o, o3, lwc, rwc, iwc, swc, cc
+ *   45-52  pw, sh, rh, rhice, tvirt, lapse, tdew, tice */
 
 /* same field order as mpb_ctl_t so one ctypes structure serves both (the oracle defines its own type
  * on purpose: it must not depend on product headers) */
@@ -50,6 +57,9 @@ typedef struct {
   /* model-level fields (ADVECT_VERT_COORD 1, 2, 3), dense [nx][ny][npl]; NULL when absent */
   int32_t npl;
   const float *pl, *ul, *vl, *wl, *zetal, *zeta_dotl;
+  /* further fields module_meteo interpolates (INTPOL_TIME_ALL, src/mptrac.h:1278-1316); NULL when absent */
+  const float *x2[ORC_NX2];   /* [nx][ny] */
+  const float *x3[ORC_NX3];   /* [nx][ny][np] */
 } orc_met_t;
 
 typedef struct {

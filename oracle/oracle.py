@@ -26,8 +26,16 @@ _DBL_FIELDS = ("t_start", "t_stop", "dt_mod", "dt_met", "met_utm_ref_lat", "sort
                "turb_dx_pbl", "turb_dx_trop", "turb_dx_strat", "turb_dz_pbl", "turb_dz_trop", "turb_dz_strat",
                "turb_mesox", "turb_mesoz", "turb_pbl_trans", "mixing_dt", "mixing_trop", "mixing_strat",
                "mixing_lon0", "mixing_lon1", "mixing_lat0", "mixing_lat1", "mixing_z0", "mixing_z1", "met_dt_out")
-METEO_QNT = ("ps", "pbl", "p", "t", "rho", "u", "v", "w", "vh", "vz", "theta", "psat", "psice", "zeta_d")
-METEO_SLOTS = 16
+# slots of orc_ctl_t::qnt_meteo (mptrac_oracle.h): 14 from the path's own fields, the 22 2-D and 9 3-D further fields of
+# INTPOL_TIME_ALL, 8 derived from t and h2o
+METEO_QNT = ("ps", "pbl", "p", "t", "rho", "u", "v", "w", "vh", "vz", "theta", "psat", "psice", "zeta_d",
+             "ts", "zs", "us", "vs", "ess", "nss", "shf", "lsm", "sst", "pt", "tt", "zt", "h2ot", "pct", "pcb", "cl", "plcl", "plfc",
+             "pel", "cape", "cin", "o3c",
+             "zg", "pv", "h2o", "o3", "lwc", "rwc", "iwc", "swc", "cc",
+             "pw", "sh", "rh", "rhice", "tvirt", "lapse", "tdew", "tice")
+METEO_SLOTS = 64
+MET_X2 = ("ts", "zs", "us", "vs", "ess", "nss", "shf", "lsm", "sst", "pt", "tt", "zt", "h2ot", "pct", "pcb", "cl", "plcl", "plfc", "pel", "cape", "cin", "o3c")   # orc_met_t::x2, [nx][ny]
+MET_X3 = ("z", "pv", "h2o", "o3", "lwc", "rwc", "iwc", "swc", "cc")   # orc_met_t::x3, [nx][ny][np]
 
 
 class OrcCtl(C.Structure):
@@ -42,7 +50,7 @@ _LEVEL_FIELDS = ("pl", "ul", "vl", "wl", "zetal", "zeta_dotl")   # model-level f
 class OrcMet(C.Structure):
     _fields_ = [("time", C.c_double), ("coord_type", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("np", C.c_int32)] + [
         (n, C.c_void_p) for n in ("lon", "lat", "p", "u", "v", "w", "t", "ps", "pbl")] + [("npl", C.c_int32)] + [
-        (n, C.c_void_p) for n in _LEVEL_FIELDS]
+        (n, C.c_void_p) for n in _LEVEL_FIELDS] + [("x2", C.c_void_p * len(MET_X2)), ("x3", C.c_void_p * len(MET_X3))]
 
 
 class OrcClim(C.Structure):
@@ -95,6 +103,11 @@ def met_struct(met):
         setattr(s, n, a.ctypes.data if a is not None else None)
         if a is not None:
             s.npl = a.shape[2]
+    extra = getattr(met, "extra", None) or {}
+    for i, n in enumerate(MET_X2):
+        s.x2[i] = extra[n].ctypes.data if n in extra else None
+    for i, n in enumerate(MET_X3):
+        s.x3[i] = extra[n].ctypes.data if n in extra else None
     return s
 
 
@@ -288,11 +301,11 @@ class Reference:
         return dict(zip(("EX", "EY", "EP", "NP", "NQ"), (x.value for x in v)))
 
     def read_ctl(self, qnt_names=(), overrides=""):
-        out = (C.c_int * 21)()
+        out = (C.c_int * 72)()
         nq = self.L.ref_read_ctl(",".join(qnt_names).encode(), overrides.encode(), out)
         self.qnt = dict(zip(("rp", "rhop", "m", "vmr", "ens"), list(out)[:5]))
-        self.qnt["zeta"], self.qnt["eta"] = out[19], out[20]
-        self.qnt_meteo = {n: i for n, i in zip(METEO_QNT, list(out)[5:19]) if i >= 0}   # name -> index the reference assigned
+        self.qnt["zeta"], self.qnt["eta"] = out[70], out[71]
+        self.qnt_meteo = {n: i for n, i in zip(METEO_QNT, list(out)[5:5 + len(METEO_QNT)]) if i >= 0}   # name -> index the reference assigned
         return nq
 
     def clim_tropo(self):

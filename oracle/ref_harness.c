@@ -34,7 +34,7 @@ static void ensure_alloc(void) {
 
 /* Reference defaults + quantity names (comma separated) + "KEY VALUE" overrides (space separated).
  * Returns the quantity index the reference assigned to `rp`, `rhop`, `m`, `vmr`, `ens` and the 14 module_meteo
- * quantities of the path and `zeta`, `eta` through out[21]. */
+ * quantities (slot order of orc_ctl_t::qnt_meteo, out[5..68]) and `zeta`, `eta` (out[70], out[71]); out holds 72 ints. */
 int ref_read_ctl(const char *qnt_names, const char *overrides, int *out) {
   ensure_alloc();
   static char buf[8192];
@@ -76,11 +76,19 @@ int ref_read_ctl(const char *qnt_names, const char *overrides, int *out) {
     out[0] = h_ctl->qnt_rp; out[1] = h_ctl->qnt_rhop; out[2] = h_ctl->qnt_m; out[3] = h_ctl->qnt_vmr;
     out[4] = h_ctl->qnt_ens;
     /* module_meteo quantities in the slot order of orc_ctl_t::qnt_meteo */
-    const int mq[14] = {h_ctl->qnt_ps, h_ctl->qnt_pbl, h_ctl->qnt_p, h_ctl->qnt_t, h_ctl->qnt_rho, h_ctl->qnt_u, h_ctl->qnt_v,
+    const int mq[53] = {h_ctl->qnt_ps, h_ctl->qnt_pbl, h_ctl->qnt_p, h_ctl->qnt_t, h_ctl->qnt_rho, h_ctl->qnt_u, h_ctl->qnt_v,
                         h_ctl->qnt_w, h_ctl->qnt_vh, h_ctl->qnt_vz, h_ctl->qnt_theta, h_ctl->qnt_psat, h_ctl->qnt_psice,
-                        h_ctl->qnt_zeta_d};
-    for (int i = 0; i < 14; i++) out[5 + i] = mq[i];
-    out[19] = h_ctl->qnt_zeta; out[20] = h_ctl->qnt_eta;
+                        h_ctl->qnt_zeta_d,
+                        h_ctl->qnt_ts, h_ctl->qnt_zs, h_ctl->qnt_us, h_ctl->qnt_vs, h_ctl->qnt_ess, h_ctl->qnt_nss, h_ctl->qnt_shf,
+                        h_ctl->qnt_lsm, h_ctl->qnt_sst, h_ctl->qnt_pt, h_ctl->qnt_tt, h_ctl->qnt_zt, h_ctl->qnt_h2ot, h_ctl->qnt_pct,
+                        h_ctl->qnt_pcb, h_ctl->qnt_cl, h_ctl->qnt_plcl, h_ctl->qnt_plfc, h_ctl->qnt_pel, h_ctl->qnt_cape,
+                        h_ctl->qnt_cin, h_ctl->qnt_o3c,
+                        h_ctl->qnt_zg, h_ctl->qnt_pv, h_ctl->qnt_h2o, h_ctl->qnt_o3, h_ctl->qnt_lwc, h_ctl->qnt_rwc, h_ctl->qnt_iwc,
+                        h_ctl->qnt_swc, h_ctl->qnt_cc,
+                        h_ctl->qnt_pw, h_ctl->qnt_sh, h_ctl->qnt_rh, h_ctl->qnt_rhice, h_ctl->qnt_tvirt, h_ctl->qnt_lapse,
+                        h_ctl->qnt_tdew, h_ctl->qnt_tice};
+    for (int i = 0; i < 64; i++) out[5 + i] = i < 53 ? mq[i] : -1;
+    out[70] = h_ctl->qnt_zeta; out[71] = h_ctl->qnt_eta;
   }
   return h_ctl->nq;
 }
@@ -115,6 +123,22 @@ static void fill_met(met_t *dst, const orc_met_t *src) {
       dst->ps[ix][iy] = src->ps ? src->ps[(size_t)ix * src->ny + iy] : 0.f;
       dst->pbl[ix][iy] = src->pbl ? src->pbl[(size_t)ix * src->ny + iy] : 0.f;
     }
+  {   /* the further fields module_meteo interpolates (zero where the caller has none, like a file that lacks them) */
+    float (*o2[ORC_NX2])[EY] = {dst->ts, dst->zs, dst->us, dst->vs, dst->ess, dst->nss, dst->shf, dst->lsm, dst->sst, dst->pt, dst->tt,
+                                dst->zt, dst->h2ot, dst->pct, dst->pcb, dst->cl, dst->plcl, dst->plfc, dst->pel, dst->cape, dst->cin,
+                                dst->o3c};
+    float (*o3[ORC_NX3])[EY][EP] = {dst->z, dst->pv, dst->h2o, dst->o3, dst->lwc, dst->rwc, dst->iwc, dst->swc, dst->cc};
+#pragma omp parallel for collapse(2)
+    for (int ix = 0; ix < src->nx; ix++)
+      for (int iy = 0; iy < src->ny; iy++) {
+        const size_t o = ((size_t)ix * src->ny + iy) * src->np;
+        for (int f = 0; f < ORC_NX2; f++) o2[f][ix][iy] = src->x2[f] ? src->x2[f][(size_t)ix * src->ny + iy] : 0.f;
+        for (int f = 0; f < ORC_NX3; f++) {
+          if (src->x3[f]) memcpy(o3[f][ix][iy], src->x3[f] + o, sizeof(float) * (size_t)src->np);
+          else memset(o3[f][ix][iy], 0, sizeof(float) * (size_t)src->np);
+        }
+      }
+  }
   if (src->pl) {   /* model-level fields (ADVECT_VERT_COORD 1, 2, 3) */
     if (src->npl > EP) ERRMSG("model levels exceed the reference build's EP");
     dst->npl = src->npl;

@@ -19,6 +19,7 @@ struct EmuMet {
   const float *u, *v, *w, *t, *ps, *pbl;
   int npl;
   const float *pl, *ul, *vl, *wl, *zetal, *zeta_dotl;
+  const float *x2[22], *x3[9];
 };
 
 struct EmuCtl {
@@ -181,5 +182,45 @@ extern "C" int emu_advect_init(const EmuMet *m0, const EmuMet *m1, long long np,
   make_view(h, m0, m1, false);
   pack_levels(L, h.g, *m0, *m1);
   for (long long ip = 0; ip < np; ip++) p[ip] = pressure_of_zeta(h.g, time[ip], zq[ip], lon[ip], lat[ip]);
+  return 0;
+}
+
+// module_meteo: the 14 quantities of the resident fields (meteo_kernel's arithmetic) and the further fields / moist
+// quantities (meteo_fields_kernel's), slot order of mpb_ctl_t::qnt_meteo
+extern "C" int emu_meteo(const EmuMet *m0, const EmuMet *m1, long long np, const double *time, const double *lon,
+                         const double *lat, const double *p, double *q, long long q_stride, const int *qnt) {
+  HostMet h;
+  make_view(h, m0, m1, true);
+  const MetView &g = h.g;
+  const size_t nnode = (size_t)m0->nx * m0->ny * m0->np, ncol = (size_t)m0->nx * m0->ny;
+  std::vector<float2> x2[22], x3[9];
+  for (int f = 0; f < 22; f++)
+    if (m0->x2[f] && m1->x2[f]) { x2[f].resize(ncol); for (size_t i = 0; i < ncol; i++) x2[f][i] = make_float2(m0->x2[f][i], m1->x2[f][i]); }
+  for (int f = 0; f < 9; f++)
+    if (m0->x3[f] && m1->x3[f]) { x3[f].resize(nnode); for (size_t i = 0; i < nnode; i++) x3[f][i] = make_float2(m0->x3[f][i], m1->x3[f][i]); }
+#pragma omp parallel for
+  for (long long ip = 0; ip < np; ip++) {
+    auto set = [&](int slot, double v) { if (qnt[slot] >= 0) q[(long long)qnt[slot] * q_stride + ip] = v; };
+    Parcel a = {time[ip], lon[ip], lat[ip], p[ip]};
+    CubeT<true> cube;
+    cube_reset(cube);
+    MeteoValues m;
+    meteo_at(g, a, cube, m);
+    set(0, m.ps); set(1, m.pbl); set(2, a.p); set(3, m.t); set(4, 100. * a.p / (kRA * m.t)); set(5, m.u); set(6, m.v); set(7, m.w);
+    set(8, sqrt(m.u * m.u + m.v * m.v)); set(9, -1e3 * kH0 / a.p * m.w); set(10, potential_temperature(a.p, m.t));
+    set(11, saturation_pressure(m.t)); set(12, saturation_pressure_ice(m.t)); set(13, zeta_diagnosed(m.ps, a.p, m.t));
+    Stencil s;
+    locate(g, a.lon, a.lat, a.p, cube, s);
+    const double wt = time_weight(g, a.time);
+    for (int f = 0; f < 22; f++) if (qnt[14 + f] >= 0 && !x2[f].empty()) set(14 + f, field2_at(g, x2[f].data(), s, wt));
+    for (int f = 0; f < 9; f++) if (qnt[36 + f] >= 0 && !x3[f].empty()) set(36 + f, field3_at(g, x3[f].data(), s, wt));
+    bool moist = false;
+    for (int k = 45; k <= 52; k++) moist |= qnt[k] >= 0;
+    if (moist && !x3[2].empty()) {
+      MoistValues w;
+      moist_at(a.p, m.t, field3_at(g, x3[2].data(), s, wt), w);
+      set(45, w.pw); set(46, w.sh); set(47, w.rh); set(48, w.rhice); set(49, w.tvirt); set(50, w.lapse); set(51, w.tdew); set(52, w.tice);
+    }
+  }
   return 0;
 }

@@ -2,6 +2,7 @@
 declares, and refuses loudly to work without a CUDA device (no CPU fallback)."""
 import ctypes as C
 import re
+from pathlib import Path
 
 import pytest
 
@@ -21,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 35
     for s in syms:
         assert hasattr(lib, s), f"{s} is declared in include/mptrac_b200.h but not exported"
-    assert lib.mpb_abi_version() == 3
+    assert lib.mpb_abi_version() == 4
 
 
 def test_strict_flavour_exports_the_same_abi():
@@ -37,14 +38,39 @@ def test_python_mirror_binds_every_symbol():
     assert set(lib._mpb_symbols) == set(header_symbols())
 
 
-def test_ctl_struct_layout_matches_header():
-    # 16 int32 + 23 int32 + pad = 40 int32 = 160 bytes, then 25 doubles, then 16 int32 (ABI version 2)
+def _c_layout(struct, members):
+    """sizeof and offsetof of every member, from a C program compiled against include/mptrac_b200.h"""
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    body = "".join(f'  printf("{m} %zu\\n", offsetof({struct}, {m}));\n' for m in members)
+    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "mptrac_b200.h"\nint main(void) {\n'
+           f'  printf("sizeof %zu\\n", sizeof({struct}));\n{body}  return 0;\n}}\n')
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "l.c").write_text(src)
+        subprocess.run(["gcc", "-I", str(ROOT / "include"), str(Path(d) / "l.c"), "-o", str(Path(d) / "l")], check=True)
+        out = subprocess.run([str(Path(d) / "l")], check=True, capture_output=True, text=True).stdout
+    return {k: int(v) for k, v in (ln.split() for ln in out.strip().splitlines())}
+
+
+@pytest.mark.parametrize("which", ["ctl", "met_view", "grid"])
+def test_struct_layouts_match_the_header(which):
+    """every member of the ctypes mirrors (mptrac_b200/host.py) sits where the C compiler puts it (ABI version 4); the
+    oracle's own control structure shares the layout of mpb_ctl_t by construction, which is checked too"""
     from mptrac_b200.host import _CtlStruct, _GridStruct, _MetViewStruct
-    assert C.sizeof(_CtlStruct) == 160 + 25 * 8 + 16 * 4 + 2 * 4
-    assert _CtlStruct.t_start.offset == 160
-    assert _CtlStruct.met_dt_out.offset == 160 + 24 * 8
-    assert C.sizeof(_MetViewStruct) == 8 + 16 + 9 * 8 + 3 * 8 + 8 + 6 * 8 + 2 * 8
-    assert C.sizeof(_GridStruct) == 16 + 8 * 8
+    from oracle.oracle import OrcCtl
+    cls, cname = {"ctl": (_CtlStruct, "mpb_ctl_t"), "met_view": (_MetViewStruct, "mpb_met_view_t"), "grid": (_GridStruct, "mpb_grid_t")}[which]
+    members = [n for n, _ in cls._fields_]
+    lay = _c_layout(cname, members)
+    assert lay.pop("sizeof") == C.sizeof(cls)
+    for m in members:
+        assert lay[m] == getattr(cls, m).offset, m
+    if which == "ctl":
+        assert C.sizeof(OrcCtl) == C.sizeof(_CtlStruct)
+        for n, _ in OrcCtl._fields_:
+            assert getattr(OrcCtl, n).offset == getattr(_CtlStruct, n).offset, n
 
 
 @pytest.mark.skipif(has_gpu(), reason="only meaningful on a machine without a GPU")

@@ -169,7 +169,7 @@ def test_module_meteo_vs_oracle(oracle, lat_desc):
     m0, m1, tm, p, lon, lat, clim = _case(lat_desc=lat_desc)
     n = tm.size
     tm = tm + np.random.default_rng(1).uniform(0, 20000, n)
-    qm = {name: i for i, name in enumerate(METEO_QNT)}
+    qm = {name: i for i, name in enumerate(METEO_QNT[:14])}    # ps ... zeta_d: the quantities of the resident fields
     ctl = Ctl(nq=len(qm), advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, met_dt_out=0.1, qnt_meteo=qm)
     q0 = np.zeros((len(qm), n))
     with _engine(n, len(qm)) as eng:

@@ -132,3 +132,29 @@ def test_model_level_advection_on_host_is_bit_exact(emu, oracle, vert_coord, adv
     assert np.max(np.abs(b.lat - lat)) > 1e-3
     for k in ("time", "lon", "lat", "p", "q"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+@pytest.mark.parametrize("lat_desc", [False, True])
+def test_module_meteo_all_fields_on_host_is_bit_exact(emu, oracle, lat_desc):
+    """meteo_at, field2_at, field3_at and moist_at of the device source against the oracle's module_meteo: all 53
+    quantities, 2-D fields with NaN gaps."""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import METEO_QNT, Parcels, met_struct
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0, lat_descending=lat_desc)
+    m0, m1 = synth.add_meteo_fields(m0), synth.add_meteo_fields(m1)
+    n = 5000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.05, zmax=45.0, seed=4)
+    tm = tm + np.random.default_rng(3).uniform(0.0, 21600.0, n)
+    qm = {name: i for i, name in enumerate(METEO_QNT)}
+    ctl = Ctl(nq=len(qm), t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, met_dt_out=300.0, qnt_meteo=qm)
+    a = Parcels(tm, p, lon, lat, np.zeros((len(qm), n)))
+    b = a.copy()
+    oracle.run("meteo", ctl, synth.make_clim_tropo(), m0, m1, b, t=300.0)
+    s0, s1 = met_struct(m0), met_struct(m1)
+    qnt = (C.c_int * 64)(*([qm[nm] for nm in METEO_QNT] + [-1] * (64 - len(METEO_QNT))))
+    vp = lambda x: C.c_void_p(x.ctypes.data)  # noqa: E731
+    assert emu.emu_meteo(C.byref(s0), C.byref(s1), C.c_longlong(n), vp(a.time), vp(a.lon), vp(a.lat), vp(a.p), vp(a.q),
+                         C.c_longlong(n), qnt) == 0
+    for name, i in qm.items():
+        assert np.array_equal(a.q[i], b.q[i], equal_nan=True), name
+        assert np.any(b.q[i] != 0), name

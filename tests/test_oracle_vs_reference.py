@@ -132,8 +132,9 @@ def test_module_meteo_bit_exact(oracle, reference, lat_desc):
     n = 4000
     tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.05, zmax=45.0, seed=5)
     tm = tm + np.random.default_rng(1).uniform(0, 20000, n)
-    nq = reference.read_ctl(list(METEO_QNT), "")
-    assert nq == len(METEO_QNT) and set(reference.qnt_meteo) == set(METEO_QNT)
+    names = list(METEO_QNT[:14])
+    nq = reference.read_ctl(names, "")
+    assert nq == len(names) and set(reference.qnt_meteo) == set(names)
     reference.set_met(m0, m1)
     ctl = Ctl(nq=nq, advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, met_dt_out=0.1, qnt_meteo=reference.qnt_meteo)
     a = Parcels(tm, p, lon, lat, np.zeros((nq, n)))
@@ -221,3 +222,34 @@ def test_model_level_advection_bit_exact(oracle, reference, vert_coord, advect):
     if vert_coord == 1:
         assert abserr(a.p, p) > 1.0
     assert _same(a, b)
+
+
+@pytest.mark.parametrize("lat_desc", [False, True])
+def test_module_meteo_all_fields_bit_exact(oracle, reference, lat_desc):
+    """module_meteo with every quantity the met fields give (INTPOL_TIME_ALL: 13 3-D and 24 2-D fields, src/mptrac.h:1278)
+    plus the ones derived from t and h2o -- 53 quantities; 2-D fields with NaN gaps (nearest-neighbour rule, 3084-3107)."""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import METEO_QNT, Parcels
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0, lat_descending=lat_desc)
+    m0, m1 = synth.add_meteo_fields(m0), synth.add_meteo_fields(m1)
+    n = 5000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.05, zmax=45.0, seed=4)
+    tm = tm + np.random.default_rng(3).uniform(0.0, 21600.0, n)
+    assert len(METEO_QNT) == 53
+    clim = reference.clim_tropo()
+    seen = set()
+    for k in range(0, len(METEO_QNT), 13):      # the reference build holds NQ = 15 quantities at most
+        names = list(METEO_QNT[k:k + 13])
+        nq = reference.read_ctl(names)
+        assert nq == len(names) == len(reference.qnt_meteo)
+        reference.set_met(m0, m1)
+        ctl = Ctl(nq=nq, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, met_dt_out=300.0, qnt_meteo=reference.qnt_meteo)
+        a = Parcels(tm, p, lon, lat, np.zeros((nq, n)))
+        b = a.copy()
+        reference.run("meteo", ctl, a, t=300.0)
+        oracle.run("meteo", ctl, clim, m0, m1, b, t=300.0)
+        for name, i in reference.qnt_meteo.items():
+            assert np.array_equal(a.q[i], b.q[i], equal_nan=True), name
+            assert np.any(a.q[i] != 0), name
+            seen.add(name)
+    assert seen == set(METEO_QNT)
