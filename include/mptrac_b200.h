@@ -88,6 +88,13 @@ typedef struct mpb_ctl {
   int32_t qnt_meteo[MPB_METEO_SLOTS];       /* quantity index per MPB_Q_* slot or -1               ctl->qnt_ps ... */
   int32_t qnt_zeta, qnt_eta;                /* the parcel's model-level coordinate (ADVECT_VERT_COORD 1 / 3) or -1:
                                                ctl->qnt_zeta, ctl->qnt_eta (src/mptrac.c:3683-3687) */
+  /* module_convection (src/mptrac.c:4102-4171; needs the met fields MPB_F2_CAPE, _CIN, _PEL when conv_cape >= 0) and
+   * module_decay (4227-4263) with the reset of the total loss rate before it (7931-7936) */
+  double conv_cape, conv_cin, conv_pbl_trans, conv_dt;   /* ctl->conv_*: off with conv_cape < 0 and conv_mix_pbl 0 */
+  double tdec_trop, tdec_strat;                          /* ctl->tdec_*: decay runs when both are > 0 */
+  int32_t conv_mix_pbl;
+  int32_t qnt_m, qnt_vmr, qnt_mloss_decay, qnt_loss_rate;   /* quantity indices or -1 */
+  int32_t _pad2;
 } mpb_ctl_t;
 
 /* Host view of one met_t time level (src/mptrac.h:3844-4014).  3-D element (ix,iy,iz) lives at
@@ -181,7 +188,9 @@ int mpb_run_timestep_host(mpb_ctx *ctx, double t, int64_t np, double *time, doub
 #define MPB_MOD_POSITION1 0x080
 #define MPB_MOD_MIXING    0x100
 #define MPB_MOD_METEO     0x200   /* between POSITION1 and MIXING, like the reference (src/mptrac.c:7927-7945) */
-#define MPB_MOD_ALL       0x3ff
+#define MPB_MOD_CONVECTION 0x400  /* between DIFF_MESO and SEDI (src/mptrac.c:7905-7908) */
+#define MPB_MOD_DECAY     0x800   /* reset of the total loss rate + module_decay, between METEO and MIXING (7931-7940) */
+#define MPB_MOD_ALL       0xfff
 int mpb_run_modules(mpb_ctx *ctx, double t, unsigned mask);
 
 /* --- single modules (same symbols the reference exports, src/mptrac.h:6140-7132); each is the

@@ -418,6 +418,56 @@ __global__ void swap_pairs_kernel(float2 *a, size_t n) {
   if (i < n) { const float2 v = a[i]; a[i] = make_float2(v.y, v.x); }
 }
 
+// module_convection (src/mptrac.c:4102-4171): parcels with dt != 0; the uniform random number of parcel ip is number
+// ig0 + ip of the module's module_rng call (method 0), addressed by global index like the normals of the diffusion modules
+struct ConvArgs {
+  MetView met;
+  ConvView conv;
+  const double *time, *lon, *lat, *dt;
+  double *p;
+  unsigned long long ctr;
+  long long ig0, np;
+};
+__global__ void __launch_bounds__(128) convection_kernel(const __grid_constant__ ConvArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np || A.dt[ip] == 0) return;
+  Parcel a;
+  a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
+  convect(A.met, A.conv, squares_uniform(A.ctr + (unsigned long long)(A.ig0 + ip)), a);
+  A.p[ip] = a.p;
+}
+
+// the reset of the total loss rate (src/mptrac.c:7931-7936) and module_decay (4227-4263): parcels with dt != 0
+struct DecayArgs {
+  ClimView clim;
+  const double *time, *lat, *p, *dt;
+  double *m, *vmr, *mloss, *loss_rate;   // quantity rows or null
+  double tdec_trop, tdec_strat, utm_ref_lat;
+  long long np;
+  int coord_type, decay;                 // decay = 0: only the reset
+};
+__global__ void __launch_bounds__(128) decay_kernel(const __grid_constant__ DecayArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np) return;
+  const double dt = A.dt[ip];
+  if (dt == 0) return;
+  double rate = 0;
+  if (A.decay) {
+    Parcel a;
+    a.time = A.time[ip]; a.lon = 0; a.lat = A.lat[ip]; a.p = A.p[ip];
+    double tdec;
+    const double aux = decay_factor(A.clim, A.coord_type, A.utm_ref_lat, A.tdec_trop, A.tdec_strat, a, dt, tdec);
+    if (A.m) {
+      const double m = A.m[ip];
+      if (A.mloss) A.mloss[ip] += m * (1 - aux);
+      A.m[ip] = m * aux;
+      rate = 1. / tdec;
+    }
+    if (A.vmr) A.vmr[ip] *= aux;
+  }
+  if (A.loss_rate) A.loss_rate[ip] = 0 + rate;
+}
+
 // module_advect on model levels (src/mptrac.c:3646-3657, 3680-3757) and module_advect_init (3762-3785): one parcel per
 // thread, dt from the cache (the fused kernel's timesteps segment ran before)
 struct LevelArgs {
@@ -908,6 +958,57 @@ static bool meteo_wanted(const mpb_ctl_t &k, int first, int last) {
   return false;
 }
 
+static bool convection_enabled(const mpb_ctl_t &k) { return k.conv_mix_pbl || k.conv_cape >= 0; }   // src/mptrac.c:7905
+static bool decay_enabled(const mpb_ctl_t &k) { return k.tdec_trop > 0 && k.tdec_strat > 0; }        // :7938
+
+static void launch_convection(mpb_ctx *c) {
+  const mpb_ctl_t &k = c->ctl;
+  REQUIRE(k.rng_type == 1, "only RNG_TYPE 1 (Squares) runs on the device");
+  // one module_rng(np, uniform) call: np + 1 counters, whether or not any parcel is active
+  const unsigned long long ctr = c->rng_ctr;
+  c->rng_ctr += (unsigned long long)(c->global_np >= 0 ? c->global_np : c->np) + 1ull;
+  if (c->np == 0) return;
+  ConvArgs A;
+  A.met = met_view(c);
+  A.conv.cape = k.conv_cape; A.conv.cin = k.conv_cin; A.conv.pbl_trans = k.conv_pbl_trans; A.conv.mix_pbl = k.conv_mix_pbl;
+  A.conv.fcape = A.conv.fcin = A.conv.fpel = nullptr;
+  if (k.conv_cape >= 0) {
+    for (int f : {MPB_F2_CAPE, MPB_F2_CIN, MPB_F2_PEL})
+      REQUIRE(c->x2[f] && c->x2_valid[0][f] && c->x2_valid[1][f],
+              "module_convection with CONV_CAPE >= 0 needs the met fields cape, cin and pel of both levels (mpb_met_view_t::x2)");
+    A.conv.fcape = c->x2[MPB_F2_CAPE]; A.conv.fcin = c->x2[MPB_F2_CIN]; A.conv.fpel = c->x2[MPB_F2_PEL];
+  }
+  A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p(); A.dt = c->dt;
+  A.ctr = ctr; A.ig0 = c->ig0; A.np = c->np;
+  convection_kernel<<<nblocks(c->np, 128), 128, 0, c->stream>>>(A);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
+static void launch_decay(mpb_ctx *c) {
+  const mpb_ctl_t &k = c->ctl;
+  const bool decay = decay_enabled(k);
+  if (c->np == 0 || (!decay && k.qnt_loss_rate < 0)) return;
+  auto row = [&](int iq) -> double * {
+    if (iq < 0) return nullptr;
+    REQUIRE(iq < c->nq, "decay quantity index out of range");
+    return c->q(iq);
+  };
+  if (decay) {
+    REQUIRE(k.qnt_m >= 0 || k.qnt_vmr >= 0, "module_decay needs quantity mass or volume mixing ratio");   // src/mptrac.c:4237
+    REQUIRE(c->cl_tropo != nullptr, "module_decay needs the tropopause climatology (mpb_set_clim_tropo)");
+  }
+  DecayArgs A;
+  A.clim = clim_view(c);
+  A.time = c->time(); A.lat = c->lat(); A.p = c->p(); A.dt = c->dt;
+  A.m = row(k.qnt_m); A.vmr = row(k.qnt_vmr); A.mloss = row(k.qnt_mloss_decay); A.loss_rate = row(k.qnt_loss_rate);
+  A.tdec_trop = k.tdec_trop; A.tdec_strat = k.tdec_strat; A.utm_ref_lat = k.met_utm_ref_lat;
+  A.np = c->np; A.coord_type = k.met_coord_type; A.decay = decay ? 1 : 0;
+  decay_kernel<<<nblocks(c->np, 128), 128, 0, c->stream>>>(A);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
 static void launch_meteo_fields(mpb_ctx *c) {
   const mpb_ctl_t &k = c->ctl;
   MeteoFieldArgs A;
@@ -1356,7 +1457,10 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   if (mask & MPB_MOD_POSITION0) modules |= MOD_POS_PRE;
   if (mask & MPB_MOD_POSITION1) modules |= MOD_POS_POST;
   const bool on_levels = advect > 0 && k.advect_vert_coord != 0;   // advection runs as its own launch between two segments
-  const bool whole = (mask & 0xff) == 0xff && !on_levels;   // timesteps ... position1 in one launch: dt stays in registers
+  const bool conv_now = (mask & MPB_MOD_CONVECTION) && convection_enabled(k) && (k.conv_dt <= 0 || hits(t, k.conv_dt));
+  const bool decay_now = (mask & MPB_MOD_DECAY) && (decay_enabled(k) || k.qnt_loss_rate >= 0);
+  // timesteps ... position1 in one launch: dt stays in registers (modules that run as their own launch read it from memory)
+  const bool whole = (mask & 0xff) == 0xff && !on_levels && !conv_now && !decay_now;
   if ((mask & MPB_MOD_TIMESTEPS) && t == k.t_start) launch_advect_init(c);   // src/mptrac.c:7863-7873
   const bool sort_now = (mask & MPB_MOD_SORT) && k.sort_dt > 0 && hits(t, k.sort_dt);
   if (mask & MPB_MOD_TIMESTEPS) {
@@ -1373,16 +1477,29 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   } else if (sort_now) {
     do_sort(c);
   }
-  if (on_levels) {
-    const unsigned pre = modules & (MOD_TIMESTEPS | MOD_STORE_DT | MOD_POS_PRE), post = modules & MOD_POS_POST;
+  const unsigned pre = modules & (MOD_TIMESTEPS | MOD_STORE_DT | MOD_POS_PRE), post = modules & MOD_POS_POST;
+  if (on_levels && !conv_now) {
     if (pre) launch_step(c, t, 0, 0, pre);
     launch_advect_levels(c);
     if (post || phys) launch_step(c, t, 0, phys, post);
+  } else if (conv_now) {
+    // module_convection sits between diff_meso and sedi (src/mptrac.c:7897-7912): the fused step splits around it
+    const unsigned before = phys & (PHYS_TURB | PHYS_MESO), after = phys & PHYS_SEDI;
+    if (on_levels) {
+      if (pre) launch_step(c, t, 0, 0, pre);
+      launch_advect_levels(c);
+      if (before) launch_step(c, t, 0, before, 0);
+    } else if (pre || advect || before) {
+      launch_step(c, t, advect, before, pre);
+    }
+    launch_convection(c);
+    if (post || after) launch_step(c, t, 0, after, post);
   } else if (modules || advect || phys) {
     launch_step(c, t, advect, phys, modules);
   }
   if ((mask & MPB_MOD_METEO) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out)))   // src/mptrac.c:7927-7929
     launch_meteo(c);
+  if (decay_now) launch_decay(c);   // src/mptrac.c:7931-7940
   if ((mask & MPB_MOD_MIXING) && k.mixing_trop >= 0 && k.mixing_strat >= 0 &&
       (k.mixing_dt <= 0 || hits(t, k.mixing_dt))) {  // src/mptrac.c:7943-7945
     mixing_begin(c, t);
@@ -1412,7 +1529,8 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
   const bool sort_now = k.sort_dt > 0 && hits(t, k.sort_dt);
   const bool mix_now = k.mixing_trop >= 0 && k.mixing_strat >= 0 && (k.mixing_dt <= 0 || hits(t, k.mixing_dt)) && k.n_mix_qnt > 0;
   const bool meteo_now = meteo_wanted(k) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out));
-  if (sort_now || mix_now || meteo_now || k.advect_vert_coord != 0 || np < 4 * kHostChunkMin) {
+  if (sort_now || mix_now || meteo_now || k.advect_vert_coord != 0 || convection_enabled(k) || decay_enabled(k) || k.qnt_loss_rate >= 0 ||
+      np < 4 * kHostChunkMin) {
     // steps with a global phase (cell sort, box means), steps that write quantities (meteo) and tiny problems take the
     // plain sequence
     REQUIRE(mpb_set_atm(c, np, time, p, lon, lat, q, q_stride) == 0, g_err);

@@ -1338,6 +1338,51 @@ MPB_HD double zeta_diagnosed(double ps, double p, double t) {                   
 }
 
 // ----------------------------------------------------------------------------------------------
+// module_convection (4102-4171): the mixing range reaches from the surface to the PBL top (CONV_MIX_PBL) and / or to
+// the equilibrium level where CAPE (and CIN) pass their thresholds; the parcel's new pressure is uniformly distributed
+// in density over that range, `r` being the parcel's uniform random number
+// ----------------------------------------------------------------------------------------------
+struct ConvView {
+  double cape, cin, pbl_trans;          // ctl->conv_cape, conv_cin, conv_pbl_trans
+  int mix_pbl;                          // ctl->conv_mix_pbl
+  const float2 *fcape, *fcin, *fpel;    // the 2-D fields (both time levels), needed when cape >= 0
+};
+MPB_HD void convect(const MetView &g, const ConvView &k, double r, Parcel &a) {
+  CellAxes ax;
+  axes_reset(ax);
+  double ps, pbl;
+  surface_at(g, a.time, a.lon, a.lat, ax, ps, pbl);
+  const double pbot = ps;
+  double ptop = ps;
+  if (k.mix_pbl) ptop = pbl - k.pbl_trans * (ps - pbl);
+  if (k.cape >= 0) {
+    Stencil s;
+    stencil_2d(g, a.lon, a.lat, ax, s);
+    const double wt = time_weight(g, a.time);
+    const double cape = field2_at(g, k.fcape, s, wt), cin = field2_at(g, k.fcin, s, wt), pel = field2_at(g, k.fpel, s, wt);
+    if (isfinite(cape) && cape >= k.cape && (k.cin <= 0 || (isfinite(cin) && cin >= k.cin))) ptop = ptop < pel ? ptop : pel;   // GSL_MIN
+  }
+  if (ptop != pbot && a.p >= ptop) {
+    CubeT<true> c;
+    cube_reset(c);
+    const double tbot = temperature_at(g, a.time, a.lon, a.lat, pbot, c);
+    const double ttop = temperature_at(g, a.time, a.lon, a.lat, ptop, c);
+    const double rhobot = pbot / tbot, rhotop = ptop / ttop;
+    const double rho = rhobot + (rhotop - rhobot) * r;
+    a.p = lin(rhobot, pbot, rhotop, ptop, rho);
+  }
+}
+
+// module_decay (4227-4263): the e-folding time blends the tropospheric and the stratospheric one with tropo_weight
+// (12748-12770); returns exp(-dt / tdec)
+MPB_HD double decay_factor(const ClimView &cl, int coord_type, double utm_ref_lat, double tdec_trop, double tdec_strat,
+                           const Parcel &a, double dt, double &tdec) {
+  const double w = weight_tropo(tropopause_pressure(cl, a.time, coord_type == 0 ? a.lat : utm_ref_lat), a.p);
+  tdec = w * tdec_trop + (1 - w) * tdec_strat;
+  return exp(-dt / tdec);
+}
+
+// ----------------------------------------------------------------------------------------------
 // cell key of module_sort (5909-5919): raw index searches, no wrap
 // ----------------------------------------------------------------------------------------------
 MPB_HD int cell_key(const MetView &g, double lon, double lat, double p) {

@@ -93,6 +93,11 @@ static void put_ctl(const ctl_t *c) {
   k.qnt_meteo[MPB_Q_VZ] = c->qnt_vz; k.qnt_meteo[MPB_Q_THETA] = c->qnt_theta; k.qnt_meteo[MPB_Q_PSAT] = c->qnt_psat;
   k.qnt_meteo[MPB_Q_PSICE] = c->qnt_psice; k.qnt_meteo[MPB_Q_ZETA_D] = c->qnt_zeta_d;
   k.qnt_zeta = c->qnt_zeta; k.qnt_eta = c->qnt_eta;
+  /* module_convection and module_decay stay on the reference's CPU code in this version (their kernels are pinned on the
+     host, the GPU run is pending): switched off on the device side whatever the control file says */
+  k.conv_cape = k.conv_cin = k.conv_dt = -999; k.conv_pbl_trans = 0; k.conv_mix_pbl = 0;
+  k.tdec_trop = k.tdec_strat = 0;
+  k.qnt_m = k.qnt_vmr = k.qnt_mloss_decay = k.qnt_loss_rate = -1;
   g_levels = c->advect_vert_coord != 0;
   g_fields = device_meteo_fields();
   memset(g_need2, 0, sizeof(g_need2)); memset(g_need3, 0, sizeof(g_need3));

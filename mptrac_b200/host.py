@@ -31,8 +31,8 @@ MET_X2 = ("ts", "zs", "us", "vs", "ess", "nss", "shf", "lsm", "sst", "pt", "tt",
 MET_X3 = ("z", "pv", "h2o", "o3", "lwc", "rwc", "iwc", "swc", "cc")   # [nx][ny][np]; "z" is the geopotential height that quantity zg reports
 # module bits of mpb_run_modules (include/mptrac_b200.h MPB_MOD_*)
 (MOD_TIMESTEPS, MOD_SORT, MOD_POSITION0, MOD_ADVECT, MOD_DIFF_TURB, MOD_DIFF_MESO, MOD_SEDI, MOD_POSITION1, MOD_MIXING,
- MOD_METEO) = (1 << i for i in range(10))
-MOD_ALL = 0x3ff
+ MOD_METEO, MOD_CONVECTION, MOD_DECAY) = (1 << i for i in range(12))
+MOD_ALL = 0xfff
 _LIBDIR = Path(__file__).resolve().parent / "_lib"
 
 
@@ -54,6 +54,8 @@ class _CtlStruct(C.Structure):
             "mixing_dt", "mixing_trop", "mixing_strat",
             "mixing_lon0", "mixing_lon1", "mixing_lat0", "mixing_lat1", "mixing_z0", "mixing_z1", "met_dt_out")]
         + [("qnt_meteo", C.c_int32 * METEO_SLOTS), ("qnt_zeta", C.c_int32), ("qnt_eta", C.c_int32)]
+        + [(n, C.c_double) for n in ("conv_cape", "conv_cin", "conv_pbl_trans", "conv_dt", "tdec_trop", "tdec_strat")]
+        + [(n, C.c_int32) for n in ("conv_mix_pbl", "qnt_m", "qnt_vmr", "qnt_mloss_decay", "qnt_loss_rate", "_pad2")]
     )
 
 
@@ -124,12 +126,23 @@ class Ctl:
     met_dt_out: float = 0.0                                   # module_meteo off (NB the reference's default is 0.1 = every step)
     qnt_zeta: int = -1                                        # quantity holding zeta (ADVECT_VERT_COORD 1)
     qnt_eta: int = -1                                         # quantity holding eta (ADVECT_VERT_COORD 3)
+    conv_cape: float = -999.0          # module_convection: CAPE threshold [J/kg], < 0 = off
+    conv_cin: float = -999.0
+    conv_pbl_trans: float = 0.0
+    conv_dt: float = -999.0
+    conv_mix_pbl: int = 0
+    tdec_trop: float = 0.0             # module_decay: e-folding times [s], both > 0 = on
+    tdec_strat: float = 0.0
+    qnt_m: int = -1
+    qnt_vmr: int = -1
+    qnt_mloss_decay: int = -1
+    qnt_loss_rate: int = -1
     qnt_meteo: Dict[str, int] = field(default_factory=dict)   # quantity name (METEO_QNT) -> index, e.g. {"t": 0, "u": 1}
 
     def to_struct(self) -> _CtlStruct:
         s = _CtlStruct()
         for name, _ in _CtlStruct._fields_:
-            if name in ("mix_qnt", "_pad", "n_mix_qnt", "qnt_meteo"):
+            if name in ("mix_qnt", "_pad", "_pad2", "n_mix_qnt", "qnt_meteo"):
                 continue
             setattr(s, name, getattr(self, name))
         unknown = set(self.qnt_meteo) - set(METEO_QNT)

@@ -811,6 +811,63 @@ void orc_module_meteo(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met
   }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * module_convection, 4102-4171: one uniform random number per parcel (module_rng method 0), the mixing range from the
+ * surface to the PBL top and / or the equilibrium level where CAPE (and CIN) pass their thresholds, the new pressure
+ * uniformly distributed in density between the two
+ * ------------------------------------------------------------------------------------------- */
+void orc_module_convection(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm, uint64_t *ctr) {
+  orc_module_rng(atm->rs, atm->np, 0, ctr);
+  const float *cape0 = met0->x2[19], *cape1 = met1->x2[19], *cin0 = met0->x2[20], *cin1 = met1->x2[20];
+  const float *pel0 = met0->x2[18], *pel1 = met1->x2[18];
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    if (atm->dt[ip] == 0) continue;
+    const double tm = atm->time[ip], lon = atm->lon[ip], lat = atm->lat[ip];
+    cell_t c = CELL_ZERO;
+    const double ps = time2(met0, met0->ps, met1, met1->ps, tm, lon, lat, &c, 1);
+    const double pbot = ps;
+    double ptop = ps;
+    if (ctl->conv_mix_pbl) {
+      const double pbl = time2(met0, met0->pbl, met1, met1->pbl, tm, lon, lat, &c, 0);
+      ptop = pbl - ctl->conv_pbl_trans * (ps - pbl);
+    }
+    if (ctl->conv_cape >= 0) {
+      const double cape = time2(met0, cape0, met1, cape1, tm, lon, lat, &c, 0);
+      const double cin = time2(met0, cin0, met1, cin1, tm, lon, lat, &c, 0);
+      const double pel = time2(met0, pel0, met1, pel1, tm, lon, lat, &c, 0);
+      if (isfinite(cape) && cape >= ctl->conv_cape && (ctl->conv_cin <= 0 || (isfinite(cin) && cin >= ctl->conv_cin)))
+        ptop = ptop < pel ? ptop : pel;   /* GSL_MIN */
+    }
+    if (ptop != pbot && atm->p[ip] >= ptop) {
+      const double tbot = time3(met0, met0->t, met1, met1->t, tm, pbot, lon, lat, &c, 1);
+      const double ttop = time3(met0, met0->t, met1, met1->t, tm, ptop, lon, lat, &c, 1);
+      const double rhobot = pbot / tbot, rhotop = ptop / ttop;
+      const double rho = rhobot + (rhotop - rhobot) * atm->rs[ip];
+      atm->p[ip] = linear(rhobot, pbot, rhotop, ptop, rho);
+    }
+  }
+}
+
+/* module_decay, 4227-4263 (and the reset of the total loss rate that precedes it, 7931-7936) */
+void orc_module_decay(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm) {
+  const size_t st = (size_t)atm->q_stride;
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    if (atm->dt[ip] == 0) continue;
+    const double w = w_tropo(ctl, clim, atm->time[ip], atm->lat[ip], atm->p[ip]);
+    const double tdec = w * ctl->tdec_trop + (1 - w) * ctl->tdec_strat;
+    const double aux = exp(-atm->dt[ip] / tdec);
+    if (ctl->qnt_m >= 0) {
+      double *m = atm->q + (size_t)ctl->qnt_m * st + ip;
+      if (ctl->qnt_mloss_decay >= 0) atm->q[(size_t)ctl->qnt_mloss_decay * st + ip] += *m * (1 - aux);
+      *m *= aux;
+      if (ctl->qnt_loss_rate >= 0) atm->q[(size_t)ctl->qnt_loss_rate * st + ip] += 1. / tdec;
+    }
+    if (ctl->qnt_vmr >= 0) atm->q[(size_t)ctl->qnt_vmr * st + ip] *= aux;
+  }
+}
+
 void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_met_t *met0,
                       const orc_met_t *met1, orc_atm_t *atm, double t, uint64_t *ctr) {
   if (t == ctl->t_start) orc_module_advect_init(ctl, met0, met1, atm);   /* 7863-7873 */
@@ -822,6 +879,8 @@ void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_me
                          ctl->turb_dz_trop > 0 || ctl->turb_dx_strat > 0 || ctl->turb_dz_strat > 0))
     orc_module_diff_turb(ctl, clim, met0, met1, atm, ctr);
   if (ctl->diffusion && (ctl->turb_mesox > 0 || ctl->turb_mesoz > 0)) orc_module_diff_meso(ctl, met0, met1, atm, ctr);
+  if ((ctl->conv_mix_pbl || ctl->conv_cape >= 0) && (ctl->conv_dt <= 0 || fmod(t, ctl->conv_dt) == 0))   /* 7905-7908 */
+    orc_module_convection(ctl, met0, met1, atm, ctr);
   if (ctl->qnt_rp >= 0 && ctl->qnt_rhop >= 0) orc_module_sedi(ctl, met0, met1, atm);
   orc_module_position(met0, met1, atm);
   if (ctl->met_dt_out > 0 && (ctl->met_dt_out < ctl->dt_mod || fmod(t, ctl->met_dt_out) == 0)) {   /* 7927-7929 */
@@ -829,6 +888,10 @@ void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_me
     for (int i = 0; i < ORC_METEO_SLOTS; i++) any |= ctl->qnt_meteo[i] >= 0;
     if (any) orc_module_meteo(ctl, met0, met1, atm);
   }
+  if (ctl->qnt_loss_rate >= 0)   /* 7931-7936 */
+    for (int64_t ip = 0; ip < atm->np; ip++)
+      if (atm->dt[ip] != 0) atm->q[(size_t)ctl->qnt_loss_rate * (size_t)atm->q_stride + ip] = 0;
+  if (ctl->tdec_trop > 0 && ctl->tdec_strat > 0) orc_module_decay(ctl, clim, atm);   /* 7938-7940 */
   if (ctl->mixing_trop >= 0 && ctl->mixing_strat >= 0 && (ctl->mixing_dt <= 0 || fmod(t, ctl->mixing_dt) == 0))
     orc_module_mixing(ctl, clim, atm, t);
 }

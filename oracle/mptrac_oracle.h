@@ -46,6 +46,12 @@ typedef struct {
   double met_dt_out;
   int32_t qnt_meteo[ORC_METEO_SLOTS];   /* quantity index or -1 */
   int32_t qnt_zeta, qnt_eta;            /* vertical coordinate quantity of ADVECT_VERT_COORD 1 / 3, or -1 */
+  /* module_convection (src/mptrac.c:4102-4171) and module_decay (4227-4263) */
+  double conv_cape, conv_cin, conv_pbl_trans, conv_dt;
+  double tdec_trop, tdec_strat;
+  int32_t conv_mix_pbl;
+  int32_t qnt_m, qnt_vmr, qnt_mloss_decay, qnt_loss_rate;
+  int32_t _pad2;
 } orc_ctl_t;
 
 /* one met time level, dense: 3-D [nx][ny][np] (z fastest), 2-D [nx][ny] */
@@ -92,6 +98,8 @@ void orc_module_diff_meso(const orc_ctl_t *ctl, const orc_met_t *met0, const orc
 void orc_module_sedi(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
 void orc_module_sort(const orc_ctl_t *ctl, const orc_met_t *met0, orc_atm_t *atm);
 void orc_module_meteo(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
+void orc_module_convection(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm, uint64_t *ctr);
+void orc_module_decay(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm);
 void orc_module_mixing(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm, double t);
 void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_met_t *met0,
                       const orc_met_t *met1, orc_atm_t *atm, double t, uint64_t *ctr);

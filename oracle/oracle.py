@@ -26,6 +26,11 @@ _DBL_FIELDS = ("t_start", "t_stop", "dt_mod", "dt_met", "met_utm_ref_lat", "sort
                "turb_dx_pbl", "turb_dx_trop", "turb_dx_strat", "turb_dz_pbl", "turb_dz_trop", "turb_dz_strat",
                "turb_mesox", "turb_mesoz", "turb_pbl_trans", "mixing_dt", "mixing_trop", "mixing_strat",
                "mixing_lon0", "mixing_lon1", "mixing_lat0", "mixing_lat1", "mixing_z0", "mixing_z1", "met_dt_out")
+# module_convection / module_decay block at the end of orc_ctl_t, with the reference's defaults
+_TAIL_DBL = ("conv_cape", "conv_cin", "conv_pbl_trans", "conv_dt", "tdec_trop", "tdec_strat")
+_TAIL_INT = ("conv_mix_pbl", "qnt_m", "qnt_vmr", "qnt_mloss_decay", "qnt_loss_rate")
+_TAIL_DEFAULT = dict(conv_cape=-999.0, conv_cin=-999.0, conv_pbl_trans=0.0, conv_dt=-999.0, tdec_trop=0.0, tdec_strat=0.0,
+                     conv_mix_pbl=0, qnt_m=-1, qnt_vmr=-1, qnt_mloss_decay=-1, qnt_loss_rate=-1)
 # slots of orc_ctl_t::qnt_meteo (mptrac_oracle.h): 14 from the path's own fields, the 22 2-D and 9 3-D further fields of
 # INTPOL_TIME_ALL, 8 derived from t and h2o
 METEO_QNT = ("ps", "pbl", "p", "t", "rho", "u", "v", "w", "vh", "vz", "theta", "psat", "psice", "zeta_d",
@@ -41,7 +46,8 @@ MET_X3 = ("z", "pv", "h2o", "o3", "lwc", "rwc", "iwc", "swc", "cc")   # orc_met_
 class OrcCtl(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in _INT_FIELDS] + [("mix_qnt", C.c_int32 * MIX_MAXQ), ("_pad", C.c_int32)]
                 + [(n, C.c_double) for n in _DBL_FIELDS] + [("qnt_meteo", C.c_int32 * METEO_SLOTS)]
-                + [("qnt_zeta", C.c_int32), ("qnt_eta", C.c_int32)])
+                + [("qnt_zeta", C.c_int32), ("qnt_eta", C.c_int32)]
+                + [(n, C.c_double) for n in _TAIL_DBL] + [(n, C.c_int32) for n in _TAIL_INT] + [("_pad2", C.c_int32)])
 
 
 _LEVEL_FIELDS = ("pl", "ul", "vl", "wl", "zetal", "zeta_dotl")   # model-level fields, [nx][ny][npl]
@@ -86,6 +92,12 @@ def ctl_struct(ctl) -> OrcCtl:
             setattr(s, n, int(get(n)))
         except (KeyError, AttributeError):
             setattr(s, n, -1)
+    for n in _TAIL_DBL + _TAIL_INT:
+        try:
+            v = get(n)
+        except (KeyError, AttributeError):
+            v = _TAIL_DEFAULT[n]
+        setattr(s, n, float(v) if n in _TAIL_DBL else int(v))
     return s
 
 
@@ -243,6 +255,10 @@ class Oracle:
             L.orc_module_meteo(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a))
         elif what == "advect_init":
             L.orc_module_advect_init(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a))
+        elif what == "convection":
+            L.orc_module_convection(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a), C.byref(ctr))
+        elif what == "decay":
+            L.orc_module_decay(C.byref(c), C.byref(cl), C.byref(a))
         else:
             raise ValueError(what)
         self.ctr = ctr.value
@@ -268,7 +284,7 @@ class Oracle:
 
 
 _WHAT = {"timestep": 0, "timesteps": 1, "position": 2, "advect": 3, "diff_turb": 4, "diff_meso": 5, "sedi": 6,
-         "sort": 7, "mixing": 8, "meteo": 9, "advect_init": 10}
+         "sort": 7, "mixing": 8, "meteo": 9, "advect_init": 10, "convection": 11, "decay": 12}
 
 
 def reference_available() -> bool:
@@ -301,10 +317,10 @@ class Reference:
         return dict(zip(("EX", "EY", "EP", "NP", "NQ"), (x.value for x in v)))
 
     def read_ctl(self, qnt_names=(), overrides=""):
-        out = (C.c_int * 72)()
+        out = (C.c_int * 74)()
         nq = self.L.ref_read_ctl(",".join(qnt_names).encode(), overrides.encode(), out)
         self.qnt = dict(zip(("rp", "rhop", "m", "vmr", "ens"), list(out)[:5]))
-        self.qnt["zeta"], self.qnt["eta"] = out[70], out[71]
+        self.qnt["zeta"], self.qnt["eta"], self.qnt["mloss_decay"], self.qnt["loss_rate"] = out[70], out[71], out[72], out[73]
         self.qnt_meteo = {n: i for n, i in zip(METEO_QNT, list(out)[5:5 + len(METEO_QNT)]) if i >= 0}   # name -> index the reference assigned
         return nq
 

@@ -34,7 +34,7 @@ static void ensure_alloc(void) {
 
 /* Reference defaults + quantity names (comma separated) + "KEY VALUE" overrides (space separated).
  * Returns the quantity index the reference assigned to `rp`, `rhop`, `m`, `vmr`, `ens` and the 14 module_meteo
- * quantities (slot order of orc_ctl_t::qnt_meteo, out[5..68]) and `zeta`, `eta` (out[70], out[71]); out holds 72 ints. */
+ * quantities (slot order of orc_ctl_t::qnt_meteo, out[5..68]) and `zeta`, `eta`, `mloss_decay`, `loss_rate` (out[70..73]); out holds 74 ints. */
 int ref_read_ctl(const char *qnt_names, const char *overrides, int *out) {
   ensure_alloc();
   static char buf[8192];
@@ -89,6 +89,7 @@ int ref_read_ctl(const char *qnt_names, const char *overrides, int *out) {
                         h_ctl->qnt_tdew, h_ctl->qnt_tice};
     for (int i = 0; i < 64; i++) out[5 + i] = i < 53 ? mq[i] : -1;
     out[70] = h_ctl->qnt_zeta; out[71] = h_ctl->qnt_eta;
+    out[72] = h_ctl->qnt_mloss_decay; out[73] = h_ctl->qnt_loss_rate;
   }
   return h_ctl->nq;
 }
@@ -176,6 +177,9 @@ static void apply_ctl(const orc_ctl_t *c) {
   h_ctl->mixing_lon0 = c->mixing_lon0; h_ctl->mixing_lon1 = c->mixing_lon1; h_ctl->mixing_lat0 = c->mixing_lat0;
   h_ctl->mixing_lat1 = c->mixing_lat1; h_ctl->mixing_z0 = c->mixing_z0; h_ctl->mixing_z1 = c->mixing_z1;
   h_ctl->met_dt_out = c->met_dt_out;
+  h_ctl->conv_cape = c->conv_cape; h_ctl->conv_cin = c->conv_cin; h_ctl->conv_pbl_trans = c->conv_pbl_trans;
+  h_ctl->conv_dt = c->conv_dt; h_ctl->conv_mix_pbl = c->conv_mix_pbl;
+  h_ctl->tdec_trop = c->tdec_trop; h_ctl->tdec_strat = c->tdec_strat;
 }
 
 static void put_atm(const orc_atm_t *a) {
@@ -222,6 +226,8 @@ int ref_run(const orc_ctl_t *ctl, orc_atm_t *atm, double t, int what, int nsteps
     case 8: module_mixing(h_ctl, h_clim, h_atm, t); break;
     case 9: module_meteo(h_ctl, h_cache, h_clim, h_met0, h_met1, h_atm); break;
     case 10: module_advect_init(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
+    case 11: module_convection(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
+    case 12: module_decay(h_ctl, h_cache, h_clim, h_atm); break;
     default: return 1;
   }
   *ctr = rng_ctr;

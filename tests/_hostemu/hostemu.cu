@@ -224,3 +224,39 @@ extern "C" int emu_meteo(const EmuMet *m0, const EmuMet *m1, long long np, const
   }
   return 0;
 }
+
+// module_convection: r[ip] are the uniform random numbers of the module's module_rng call
+extern "C" int emu_convection(const EmuMet *m0, const EmuMet *m1, double conv_cape, double conv_cin, double conv_pbl_trans,
+                              int conv_mix_pbl, long long np, const double *time, const double *lon, const double *lat,
+                              double *p, const double *dt, const double *r) {
+  HostMet h;
+  make_view(h, m0, m1, true);
+  const size_t ncol = (size_t)m0->nx * m0->ny;
+  std::vector<float2> f[3];
+  const int idx[3] = {19, 20, 18};   // cape, cin, pel
+  for (int k = 0; k < 3; k++)
+    if (m0->x2[idx[k]] && m1->x2[idx[k]]) {
+      f[k].resize(ncol);
+      for (size_t i = 0; i < ncol; i++) f[k][i] = make_float2(m0->x2[idx[k]][i], m1->x2[idx[k]][i]);
+    }
+  ConvView k = {conv_cape, conv_cin, conv_pbl_trans, conv_mix_pbl, f[0].data(), f[1].data(), f[2].data()};
+#pragma omp parallel for
+  for (long long ip = 0; ip < np; ip++) {
+    if (dt[ip] == 0) continue;
+    Parcel a = {time[ip], lon[ip], lat[ip], p[ip]};
+    convect(h.g, k, r[ip], a);
+    p[ip] = a.p;
+  }
+  return 0;
+}
+
+extern "C" int emu_decay(int coord_type, double utm_ref_lat, double tdec_trop, double tdec_strat, int ntime, int nlat,
+                         const double *cl_time, const double *cl_lat, const double *cl_tropo, long long np, const double *time,
+                         const double *lat, const double *p, const double *dt, double *aux, double *tdec) {
+  ClimView cl = {cl_time, cl_lat, cl_tropo, ntime, nlat};
+  for (long long ip = 0; ip < np; ip++) {
+    Parcel a = {time[ip], 0.0, lat[ip], p[ip]};
+    aux[ip] = decay_factor(cl, coord_type, utm_ref_lat, tdec_trop, tdec_strat, a, dt[ip], tdec[ip]);
+  }
+  return 0;
+}

@@ -67,3 +67,70 @@ def test_trac_trac_test_pl_with_device_meteo_fields(tmp_path, monkeypatch):
     import test_shim_trac as T
     monkeypatch.setenv("MPTRAC_B200_DEVICE_METEO_FIELDS", "1")
     T.test_trac_trac_test_through_the_shim(tmp_path, "pl")
+
+
+@pytest.mark.parametrize("mix_pbl,cape,cin", [(1, -999.0, -999.0), (0, 100.0, -999.0), (1, 50.0, 10.0)])
+@pytest.mark.parametrize("vert_coord", [0, 2])
+def test_convection_in_the_step_vs_oracle(oracle, mix_pbl, cape, cin, vert_coord):
+    """module_convection between diff_meso and sedi (the fused step splits around it; with model-level advection five
+    launches), its uniform random numbers taken from the shared counter stream"""
+    from mptrac_b200 import Ctl, Engine, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    m0, m1 = synth.add_meteo_fields(m0), synth.add_meteo_fields(m1)
+    if vert_coord:
+        m0, m1 = synth.add_model_levels(m0, npl=30), synth.add_model_levels(m1, npl=30)
+    n = 6000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.0, zmax=14.0, seed=6)
+    q = np.stack([np.full(n, 2.0), np.full(n, 1500.0)])
+    ctl = Ctl(nq=2, qnt_rp=0, qnt_rhop=1, advect=2, advect_vert_coord=vert_coord, diffusion=1, t_start=0.0, t_stop=1e6, dt_mod=300.0,
+              dt_met=21600.0, turb_dz_trop=0.5, turb_mesox=0.16, turb_mesoz=0.16, conv_mix_pbl=mix_pbl, conv_cape=cape, conv_cin=cin,
+              conv_pbl_trans=0.2 if mix_pbl else 0.0)
+    clim = synth.make_clim_tropo()
+    with Engine(n, nq=2, device=0) as eng:
+        eng.set_ctl(ctl)
+        eng.set_clim_tropo(*clim)
+        eng.set_met(0, m0)
+        eng.set_met(1, m1)
+        eng.set_atm(tm, p, lon, lat, q)
+        for s in range(5):
+            eng.run_timestep(300.0 * s)
+        out = eng.get_atm()
+        ctr = eng.rng_ctr
+    ref = Parcels(tm, p, lon, lat, q)
+    oracle.ctr = 0
+    oracle.run("timestep", ctl, clim, m0, m1, ref, t=0.0, nsteps=5)
+    assert ctr == oracle.ctr
+    # diffusion on: normals differ by ~1e-7 relative between CUDA's and glibc's sinf / cosf (see test_gpu_parity.py)
+    assert abserr(out["lat"], ref.lat) < 1e-7 and abserr(out["time"], ref.time) == 0
+    # a parcel on the edge of the mixing range may fall on the other side: allow a handful of them
+    bad = np.abs(out["p"] - ref.p) > 1e-6 * ref.p
+    assert bad.mean() < 2e-3, bad.mean()
+    assert np.mean(ref.p != p) > 0.02
+
+
+def test_decay_in_the_step_vs_oracle(oracle):
+    from mptrac_b200 import Ctl, Engine, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(36, 19, 20, t0=0.0, dt_met=21600.0)
+    n = 4000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.1, zmax=40.0, seed=9)
+    q = np.random.default_rng(4).uniform(0.5, 2.0, (4, n))
+    ctl = Ctl(nq=4, advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, tdec_trop=86400.0, tdec_strat=10 * 86400.0,
+              qnt_m=0, qnt_vmr=1, qnt_mloss_decay=2, qnt_loss_rate=3)
+    clim = synth.make_clim_tropo()
+    with Engine(n, nq=4, device=0) as eng:
+        eng.set_ctl(ctl)
+        eng.set_clim_tropo(*clim)
+        eng.set_met(0, m0)
+        eng.set_met(1, m1)
+        eng.set_atm(tm, p, lon, lat, q)
+        for s in range(4):
+            eng.run_timestep(300.0 * s)
+        out = eng.get_atm()
+    ref = Parcels(tm, p, lon, lat, q)
+    oracle.run("timestep", ctl, clim, m0, m1, ref, t=0.0, nsteps=4)
+    assert abserr(out["lat"], ref.lat) < 1e-11
+    for i in range(4):
+        assert relerr(out["q"][i], ref.q[i]) < 1e-12, i
+    assert np.all(ref.q[0] < q[0]) and np.all(ref.q[3] > 0)

@@ -158,3 +158,48 @@ def test_module_meteo_all_fields_on_host_is_bit_exact(emu, oracle, lat_desc):
     for name, i in qm.items():
         assert np.array_equal(a.q[i], b.q[i], equal_nan=True), name
         assert np.any(b.q[i] != 0), name
+
+
+@pytest.mark.parametrize("mix_pbl,cape,cin", [(1, -999.0, -999.0), (0, 100.0, -999.0), (1, 50.0, 10.0)])
+def test_module_convection_on_host_is_bit_exact(emu, oracle, mix_pbl, cape, cin):
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels, met_struct
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    m0, m1 = synth.add_meteo_fields(m0), synth.add_meteo_fields(m1)
+    n = 5000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.0, zmax=14.0, seed=6)
+    ctl = Ctl(advect=2, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, conv_mix_pbl=mix_pbl, conv_cape=cape, conv_cin=cin,
+              conv_pbl_trans=0.2 if mix_pbl else 0.0)
+    clim = synth.make_clim_tropo()
+    a = Parcels(tm, p, lon, lat)
+    oracle.run("timesteps", ctl, clim, m0, m1, a, t=300.0)
+    b = a.copy()
+    oracle.ctr = 17
+    oracle.run("convection", ctl, clim, m0, m1, b, t=300.0)
+    r = b.rs[:n].copy()        # the uniform random numbers the module drew (cache->rs)
+    s0, s1 = met_struct(m0), met_struct(m1)
+    vp = lambda x: C.c_void_p(x.ctypes.data)  # noqa: E731
+    assert emu.emu_convection(C.byref(s0), C.byref(s1), C.c_double(cape), C.c_double(cin), C.c_double(ctl.conv_pbl_trans),
+                              mix_pbl, C.c_longlong(n), vp(a.time), vp(a.lon), vp(a.lat), vp(a.p), vp(a.dt), vp(r)) == 0
+    assert np.array_equal(a.p, b.p)
+    assert 0.02 < np.mean(b.p != p) < 0.98
+
+
+def test_module_decay_on_host_is_bit_exact(emu, oracle):
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(36, 19, 20, t0=0.0, dt_met=21600.0)
+    n = 4000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.1, zmax=40.0, seed=9)
+    clim = synth.make_clim_tropo()
+    q = np.ones((1, n))
+    ctl = Ctl(nq=1, advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, tdec_trop=86400.0, tdec_strat=10 * 86400.0, qnt_m=0)
+    a = Parcels(tm, p, lon, lat, q)
+    oracle.run("timesteps", ctl, clim, m0, m1, a, t=300.0)
+    b = a.copy()
+    oracle.run("decay", ctl, clim, m0, m1, b, t=300.0)
+    aux, tdec = np.zeros(n), np.zeros(n)
+    vp = lambda x: C.c_void_p(x.ctypes.data)  # noqa: E731
+    assert emu.emu_decay(0, C.c_double(0.0), C.c_double(86400.0), C.c_double(864000.0), clim[0].size, clim[1].size, vp(clim[0]),
+                         vp(clim[1]), vp(clim[2]), C.c_longlong(n), vp(a.time), vp(a.lat), vp(a.p), vp(a.dt), vp(aux), vp(tdec)) == 0
+    assert np.array_equal(a.q[0] * aux, b.q[0]) and np.all(aux < 1) and np.ptp(tdec) > 0

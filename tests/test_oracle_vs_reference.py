@@ -253,3 +253,69 @@ def test_module_meteo_all_fields_bit_exact(oracle, reference, lat_desc):
             assert np.any(a.q[i] != 0), name
             seen.add(name)
     assert seen == set(METEO_QNT)
+
+
+@pytest.mark.parametrize("mix_pbl,cape,cin", [(1, -999.0, -999.0), (0, 100.0, -999.0), (1, 50.0, 10.0)])
+def test_module_convection_bit_exact(oracle, reference, mix_pbl, cape, cin):
+    """module_convection (src/mptrac.c:4102-4171): PBL mixing, CAPE / CIN thresholds with the equilibrium level, NaN gaps in
+    the equilibrium-level field; alone and inside the dispatcher (between diff_meso and sedi, its own random numbers)"""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    m0, m1 = synth.add_meteo_fields(m0), synth.add_meteo_fields(m1)
+    n = 5000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.0, zmax=14.0, seed=6)
+    nq = reference.read_ctl(["rp", "rhop"])
+    reference.set_met(m0, m1)
+    clim = reference.clim_tropo()
+    q = np.stack([np.full(n, 2.0), np.full(n, 1500.0)])
+    ctl = Ctl(nq=nq, qnt_rp=0, qnt_rhop=1, advect=2, diffusion=1, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0,
+              turb_dz_trop=0.5, turb_mesox=0.16, turb_mesoz=0.16, conv_mix_pbl=mix_pbl, conv_cape=cape, conv_cin=cin,
+              conv_pbl_trans=0.2 if mix_pbl else 0.0)
+    a = Parcels(tm, p, lon, lat, q)
+    reference.ctr = oracle.ctr = 3
+    reference.run("timesteps", ctl, a, t=300.0)
+    b = a.copy()
+    reference.run("convection", ctl, a, t=300.0)
+    oracle.run("convection", ctl, clim, m0, m1, b, t=300.0)
+    assert reference.ctr == oracle.ctr == 3 + n + 1
+    assert _same(a, b)
+    moved = np.mean(a.p != p)
+    assert 0.02 < moved < 0.98, moved
+    a = Parcels(tm, p, lon, lat, q)
+    b = a.copy()
+    reference.ctr = oracle.ctr = 0
+    reference.run("timestep", ctl, a, t=0.0, nsteps=5)
+    oracle.run("timestep", ctl, clim, m0, m1, b, t=0.0, nsteps=5)
+    assert reference.ctr == oracle.ctr
+    assert _same(a, b)
+
+
+def test_module_decay_bit_exact(oracle, reference):
+    """module_decay with mass, volume mixing ratio, the decay-loss and total-loss-rate quantities (src/mptrac.c:4227-4263,
+    7931-7940); alone and inside the dispatcher"""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(36, 19, 20, t0=0.0, dt_met=21600.0)
+    n = 4000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.1, zmax=40.0, seed=9)
+    nq = reference.read_ctl(["m", "vmr", "mloss_decay", "loss_rate"])
+    qi = reference.qnt
+    reference.set_met(m0, m1)
+    clim = reference.clim_tropo()
+    rng = np.random.default_rng(4)
+    q = rng.uniform(0.5, 2.0, (nq, n))
+    ctl = Ctl(nq=nq, advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, tdec_trop=86400.0, tdec_strat=10 * 86400.0,
+              qnt_m=qi["m"], qnt_vmr=qi["vmr"], qnt_mloss_decay=qi["mloss_decay"], qnt_loss_rate=qi["loss_rate"])
+    a = Parcels(tm, p, lon, lat, q)
+    reference.run("timesteps", ctl, a, t=300.0)
+    b = a.copy()
+    reference.run("decay", ctl, a, t=300.0)
+    oracle.run("decay", ctl, clim, m0, m1, b, t=300.0)
+    assert _same(a, b) and np.all(a.q[qi["m"]] < q[qi["m"]])
+    a = Parcels(tm, p, lon, lat, q)
+    b = a.copy()
+    reference.run("timestep", ctl, a, t=0.0, nsteps=4)
+    oracle.run("timestep", ctl, clim, m0, m1, b, t=0.0, nsteps=4)
+    assert _same(a, b)
+    assert np.allclose(a.q[qi["loss_rate"]], 1.0 / 86400.0, rtol=0.9) and np.all(a.q[qi["loss_rate"]] > 0)
