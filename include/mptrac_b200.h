@@ -26,6 +26,8 @@
 extern "C" {
 #endif
 
+/* ABI history (mpb_abi_version()): 2 module_meteo quantities of the resident fields; 3 model-level fields and the zeta / eta
+ * quantities (ADVECT_VERT_COORD 1, 2, 3); 4 further met fields (x2 / x3), 64 meteo slots, module_convection and module_decay */
 #define MPB_ABI_VERSION 4
 #define MPB_MIX_MAXQ 23  /* number of mixable quantities, src/mptrac.c:5222-5230 */
 
