@@ -96,7 +96,8 @@ typedef struct mpb_ctl {
   double tdec_trop, tdec_strat;                          /* ctl->tdec_*: decay runs when both are > 0 */
   int32_t conv_mix_pbl;
   int32_t qnt_m, qnt_vmr, qnt_mloss_decay, qnt_loss_rate;   /* quantity indices or -1 */
-  int32_t _pad2;
+  int32_t isosurf;            /* ctl->isosurf: module_isosurf (src/mptrac.c:4956-5004), 0 = off, 1 pressure, 2 density,
+                                 3 potential temperature, 4 balloon time series (mpb_set_balloon) */
 } mpb_ctl_t;
 
 /* Host view of one met_t time level (src/mptrac.h:3844-4014).  3-D element (ix,iy,iz) lives at
@@ -151,6 +152,11 @@ int mpb_set_uvwp(mpb_ctx *ctx, const float *uvwp /* [np][3], cache_t::uvwp */);
 int mpb_get_atm(mpb_ctx *ctx, double *time, double *p, double *lon, double *lat,
                 double *q, int64_t q_stride);
 int mpb_get_uvwp(mpb_ctx *ctx, float *uvwp);
+/* module_isosurf (src/mptrac.c:4886-5004): cache_t::iso_var [np] stays attached to the array slot (module_sort does not move
+ * it, src/mptrac.c:5944-5949); the balloon series is what module_isosurf_init reads from ctl->balloon for ISOSURF 4 */
+int mpb_set_iso_var(mpb_ctx *ctx, const double *iso_var);
+int mpb_get_iso_var(mpb_ctx *ctx, double *iso_var);
+int mpb_set_balloon(mpb_ctx *ctx, int n, const double *ts, const double *ps);
 int mpb_get_dt(mpb_ctx *ctx, double *dt /* cache_t::dt */);
 int64_t mpb_get_np(mpb_ctx *ctx);
 
@@ -192,7 +198,8 @@ int mpb_run_timestep_host(mpb_ctx *ctx, double t, int64_t np, double *time, doub
 #define MPB_MOD_METEO     0x200   /* between POSITION1 and MIXING, like the reference (src/mptrac.c:7927-7945) */
 #define MPB_MOD_CONVECTION 0x400  /* between DIFF_MESO and SEDI (src/mptrac.c:7905-7908) */
 #define MPB_MOD_DECAY     0x800   /* reset of the total loss rate + module_decay, between METEO and MIXING (7931-7940) */
-#define MPB_MOD_ALL       0xfff
+#define MPB_MOD_ISOSURF   0x1000  /* between SEDI and POSITION1 (src/mptrac.c:7914-7916); its init runs at t_start */
+#define MPB_MOD_ALL       0x1fff
 int mpb_run_modules(mpb_ctx *ctx, double t, unsigned mask);
 
 /* --- single modules (same symbols the reference exports, src/mptrac.h:6140-7132); each is the

@@ -437,6 +437,24 @@ __global__ void __launch_bounds__(128) convection_kernel(const __grid_constant__
   A.p[ip] = a.p;
 }
 
+// module_isosurf_init (init = 1) and module_isosurf (src/mptrac.c:4886-5004): every parcel, dt or not
+struct IsoArgs {
+  MetView met;
+  const double *time, *lon, *lat;
+  double *p, *iso_var;
+  const double *ts, *ps;
+  long long np;
+  int mode, n, init;
+};
+__global__ void __launch_bounds__(128) isosurf_kernel(const __grid_constant__ IsoArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np) return;
+  Parcel a;
+  a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
+  if (A.init) A.iso_var[ip] = isosurf_variable(A.met, A.mode, a);
+  else A.p[ip] = isosurf_pressure(A.met, A.mode, A.mode == 4 ? 0.0 : A.iso_var[ip], a, A.ts, A.ps, A.n);
+}
+
 // the reset of the total loss rate (src/mptrac.c:7931-7936) and module_decay (4227-4263): parcels with dt != 0
 struct DecayArgs {
   ClimView clim;
@@ -657,6 +675,9 @@ struct mpb_ctx {
   size_t lev_cap = 0;
   bool lev_valid[2] = {false, false};
   unsigned short *lev_hint = nullptr;              // LevelArgs::hint
+  // module_isosurf: cache_t::iso_var (attached to the array slot, like uvwp) and the balloon series of ISOSURF 4
+  double *iso_var = nullptr, *iso_ts = nullptr, *iso_ps = nullptr;
+  int iso_n = 0;
   // further fields for module_meteo (mpb_met_view_t::x2 / x3): per field one array, both time levels of a node adjacent
   float2 *x2[MPB_NX2] = {}, *x3[MPB_NX3] = {};
   bool x2_valid[2][MPB_NX2] = {}, x3_valid[2][MPB_NX3] = {};
@@ -985,6 +1006,26 @@ static void launch_convection(mpb_ctx *c) {
   c->launches++;
 }
 
+static bool isosurf_enabled(const mpb_ctl_t &k) { return k.isosurf >= 1 && k.isosurf <= 4; }   // src/mptrac.c:7866, 7914
+
+static void launch_isosurf(mpb_ctx *c, bool init) {
+  const mpb_ctl_t &k = c->ctl;
+  if (c->np == 0 || (init && k.isosurf == 4)) return;   // (the balloon series arrives through mpb_set_balloon)
+  if (!c->iso_var) {
+    CK(cudaMalloc(&c->iso_var, sizeof(double) * (size_t)std::max<long long>(c->np_max, 1)));
+    CK(cudaMemsetAsync(c->iso_var, 0, sizeof(double) * (size_t)std::max<long long>(c->np_max, 1), c->stream));
+  }
+  if (k.isosurf == 4) REQUIRE(c->iso_n >= 1, "ISOSURF 4 needs the balloon pressure series (mpb_set_balloon)");
+  IsoArgs A;
+  A.met = met_view(c);
+  A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p(); A.iso_var = c->iso_var;
+  A.ts = c->iso_ts; A.ps = c->iso_ps; A.n = c->iso_n;
+  A.np = c->np; A.mode = k.isosurf; A.init = init ? 1 : 0;
+  isosurf_kernel<<<nblocks(c->np, 128), 128, 0, c->stream>>>(A);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
 static void launch_decay(mpb_ctx *c) {
   const mpb_ctl_t &k = c->ctl;
   const bool decay = decay_enabled(k);
@@ -1107,7 +1148,7 @@ int mpb_destroy(mpb_ctx *c) {
   void *ptrs[] = {c->soa[0], c->soa[1], c->dt, c->uvwp, c->keys[0], c->keys[1], c->perm[0], c->perm[1],
                   c->cub_tmp, c->nodes, c->surf, c->ax_lon, c->ax_lat, c->ax_p, c->ax_lonc, c->ax_latc, c->ax_pc,
                   c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_sum, c->mix_cnt,
-                  c->grid_sum, c->grid_sq, c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz, c->lev_hint};
+                  c->grid_sum, c->grid_sq, c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz, c->lev_hint, c->iso_var, c->iso_ts, c->iso_ps};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (float2 *p : c->x2) if (p) cudaFree(p);
   for (float2 *p : c->x3) if (p) cudaFree(p);
@@ -1394,6 +1435,39 @@ int mpb_set_uvwp(mpb_ctx *c, const float *uvwp) {
   API_END
 }
 
+int mpb_set_iso_var(mpb_ctx *c, const double *iso_var) {
+  API_BEGIN
+  use(c);
+  REQUIRE(iso_var != nullptr, "null iso_var");
+  if (!c->iso_var) CK(cudaMalloc(&c->iso_var, sizeof(double) * (size_t)std::max<long long>(c->np_max, 1)));
+  if (c->np > 0) CK(cudaMemcpyAsync(c->iso_var, iso_var, sizeof(double) * (size_t)c->np, cudaMemcpyHostToDevice, c->stream));
+  API_END
+}
+
+int mpb_get_iso_var(mpb_ctx *c, double *iso_var) {
+  API_BEGIN
+  use(c);
+  REQUIRE(iso_var != nullptr && c->iso_var != nullptr, "no iso_var on the device");
+  if (c->np > 0) CK(cudaMemcpyAsync(iso_var, c->iso_var, sizeof(double) * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  API_END
+}
+
+int mpb_set_balloon(mpb_ctx *c, int n, const double *ts, const double *ps) {
+  API_BEGIN
+  use(c);
+  REQUIRE(n >= 1 && ts && ps, "bad balloon series");
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->iso_ts) { CK(cudaFree(c->iso_ts)); CK(cudaFree(c->iso_ps)); c->iso_ts = c->iso_ps = nullptr; }
+  CK(cudaMalloc(&c->iso_ts, sizeof(double) * (size_t)n));
+  CK(cudaMalloc(&c->iso_ps, sizeof(double) * (size_t)n));
+  CK(cudaMemcpyAsync(c->iso_ts, ts, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->iso_ps, ps, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->iso_n = n;
+  API_END
+}
+
 int mpb_get_atm(mpb_ctx *c, double *time, double *p, double *lon, double *lat, double *q, int64_t q_stride) {
   API_BEGIN
   use(c);
@@ -1460,8 +1534,12 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   const bool conv_now = (mask & MPB_MOD_CONVECTION) && convection_enabled(k) && (k.conv_dt <= 0 || hits(t, k.conv_dt));
   const bool decay_now = (mask & MPB_MOD_DECAY) && (decay_enabled(k) || k.qnt_loss_rate >= 0);
   // timesteps ... position1 in one launch: dt stays in registers (modules that run as their own launch read it from memory)
-  const bool whole = (mask & 0xff) == 0xff && !on_levels && !conv_now && !decay_now;
-  if ((mask & MPB_MOD_TIMESTEPS) && t == k.t_start) launch_advect_init(c);   // src/mptrac.c:7863-7873
+  const bool iso_now = (mask & MPB_MOD_ISOSURF) && isosurf_enabled(k);
+  const bool whole = (mask & 0xff) == 0xff && !on_levels && !conv_now && !decay_now && !iso_now;
+  if ((mask & MPB_MOD_TIMESTEPS) && t == k.t_start) {   // src/mptrac.c:7863-7873
+    if (iso_now) launch_isosurf(c, true);
+    launch_advect_init(c);
+  }
   const bool sort_now = (mask & MPB_MOD_SORT) && k.sort_dt > 0 && hits(t, k.sort_dt);
   if (mask & MPB_MOD_TIMESTEPS) {
     if (sort_now) {
@@ -1477,7 +1555,9 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   } else if (sort_now) {
     do_sort(c);
   }
-  const unsigned pre = modules & (MOD_TIMESTEPS | MOD_STORE_DT | MOD_POS_PRE), post = modules & MOD_POS_POST;
+  // module_isosurf sits between sedi and the final position check (src/mptrac.c:7910-7919): that check then runs alone
+  const unsigned pre = modules & (MOD_TIMESTEPS | MOD_STORE_DT | MOD_POS_PRE), post = iso_now ? 0u : (modules & MOD_POS_POST);
+  if (iso_now) modules &= ~MOD_POS_POST;
   if (on_levels && !conv_now) {
     if (pre) launch_step(c, t, 0, 0, pre);
     launch_advect_levels(c);
@@ -1496,6 +1576,10 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
     if (post || after) launch_step(c, t, 0, after, post);
   } else if (modules || advect || phys) {
     launch_step(c, t, advect, phys, modules);
+  }
+  if (iso_now) {
+    launch_isosurf(c, false);
+    if (mask & MPB_MOD_POSITION1) launch_step(c, t, 0, 0, MOD_POS_POST);
   }
   if ((mask & MPB_MOD_METEO) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out)))   // src/mptrac.c:7927-7929
     launch_meteo(c);
@@ -1529,7 +1613,7 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
   const bool sort_now = k.sort_dt > 0 && hits(t, k.sort_dt);
   const bool mix_now = k.mixing_trop >= 0 && k.mixing_strat >= 0 && (k.mixing_dt <= 0 || hits(t, k.mixing_dt)) && k.n_mix_qnt > 0;
   const bool meteo_now = meteo_wanted(k) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out));
-  if (sort_now || mix_now || meteo_now || k.advect_vert_coord != 0 || convection_enabled(k) || decay_enabled(k) || k.qnt_loss_rate >= 0 ||
+  if (sort_now || mix_now || meteo_now || k.advect_vert_coord != 0 || convection_enabled(k) || decay_enabled(k) || k.qnt_loss_rate >= 0 || isosurf_enabled(k) ||
       np < 4 * kHostChunkMin) {
     // steps with a global phase (cell sort, box means), steps that write quantities (meteo) and tiny problems take the
     // plain sequence

@@ -1373,6 +1373,30 @@ MPB_HD void convect(const MetView &g, const ConvView &k, double r, Parcel &a) {
   }
 }
 
+// module_isosurf_init / module_isosurf (4886-5004): the conserved variable of a parcel (pressure, density p / T,
+// potential temperature) and the pressure that restores it; mode 4 follows a balloon's pressure time series
+MPB_HD double isosurf_variable(const MetView &g, int mode, const Parcel &a) {
+  if (mode == 1) return a.p;
+  CubeT<true> c;
+  cube_reset(c);
+  const double t = temperature_at(g, a.time, a.lon, a.lat, a.p, c);
+  return mode == 2 ? a.p / t : potential_temperature(a.p, t);
+}
+MPB_HD double isosurf_pressure(const MetView &g, int mode, double var, const Parcel &a, const double *ts, const double *ps, int n) {
+  if (mode == 1) return var;
+  if (mode == 2 || mode == 3) {
+    CubeT<true> c;
+    cube_reset(c);
+    const double t = temperature_at(g, a.time, a.lon, a.lat, a.p, c);
+    return mode == 2 ? var * t : 1000. * pow(var / t, -1. / kKappa);
+  }
+  if (a.time <= ts[0]) return ps[0];
+  if (a.time >= ts[n - 1]) return ps[n - 1];
+  const int mid = (n - 1) >> 1;
+  const int i = find_interval(ts, n, ts[mid] < ts[mid + 1], a.time);   // locate_irr (3495-3521)
+  return ps[i] + (ps[i + 1] - ps[i]) / (ts[i + 1] - ts[i]) * (a.time - ts[i]);   // LIN, src/mptrac.h:1351
+}
+
 // module_decay (4227-4263): the e-folding time blends the tropospheric and the stratospheric one with tropo_weight
 // (12748-12770); returns exp(-dt / tdec)
 MPB_HD double decay_factor(const ClimView &cl, int coord_type, double utm_ref_lat, double tdec_trop, double tdec_strat,

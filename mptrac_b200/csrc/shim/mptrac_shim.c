@@ -98,6 +98,7 @@ static void put_ctl(const ctl_t *c) {
   k.conv_cape = k.conv_cin = k.conv_dt = -999; k.conv_pbl_trans = 0; k.conv_mix_pbl = 0;
   k.tdec_trop = k.tdec_strat = 0;
   k.qnt_m = k.qnt_vmr = k.qnt_mloss_decay = k.qnt_loss_rate = -1;
+  k.isosurf = 0;    /* module_isosurf likewise (iso_cpu below) */
   g_levels = c->advect_vert_coord != 0;
   g_fields = device_meteo_fields();
   memset(g_need2, 0, sizeof(g_need2)); memset(g_need3, 0, sizeof(g_need3));

@@ -31,8 +31,8 @@ MET_X2 = ("ts", "zs", "us", "vs", "ess", "nss", "shf", "lsm", "sst", "pt", "tt",
 MET_X3 = ("z", "pv", "h2o", "o3", "lwc", "rwc", "iwc", "swc", "cc")   # [nx][ny][np]; "z" is the geopotential height that quantity zg reports
 # module bits of mpb_run_modules (include/mptrac_b200.h MPB_MOD_*)
 (MOD_TIMESTEPS, MOD_SORT, MOD_POSITION0, MOD_ADVECT, MOD_DIFF_TURB, MOD_DIFF_MESO, MOD_SEDI, MOD_POSITION1, MOD_MIXING,
- MOD_METEO, MOD_CONVECTION, MOD_DECAY) = (1 << i for i in range(12))
-MOD_ALL = 0xfff
+ MOD_METEO, MOD_CONVECTION, MOD_DECAY, MOD_ISOSURF) = (1 << i for i in range(13))
+MOD_ALL = 0x1fff
 _LIBDIR = Path(__file__).resolve().parent / "_lib"
 
 
@@ -55,7 +55,7 @@ class _CtlStruct(C.Structure):
             "mixing_lon0", "mixing_lon1", "mixing_lat0", "mixing_lat1", "mixing_z0", "mixing_z1", "met_dt_out")]
         + [("qnt_meteo", C.c_int32 * METEO_SLOTS), ("qnt_zeta", C.c_int32), ("qnt_eta", C.c_int32)]
         + [(n, C.c_double) for n in ("conv_cape", "conv_cin", "conv_pbl_trans", "conv_dt", "tdec_trop", "tdec_strat")]
-        + [(n, C.c_int32) for n in ("conv_mix_pbl", "qnt_m", "qnt_vmr", "qnt_mloss_decay", "qnt_loss_rate", "_pad2")]
+        + [(n, C.c_int32) for n in ("conv_mix_pbl", "qnt_m", "qnt_vmr", "qnt_mloss_decay", "qnt_loss_rate", "isosurf")]
     )
 
 
@@ -137,12 +137,13 @@ class Ctl:
     qnt_vmr: int = -1
     qnt_mloss_decay: int = -1
     qnt_loss_rate: int = -1
+    isosurf: int = 0                   # module_isosurf: 1 pressure, 2 density, 3 potential temperature, 4 balloon series
     qnt_meteo: Dict[str, int] = field(default_factory=dict)   # quantity name (METEO_QNT) -> index, e.g. {"t": 0, "u": 1}
 
     def to_struct(self) -> _CtlStruct:
         s = _CtlStruct()
         for name, _ in _CtlStruct._fields_:
-            if name in ("mix_qnt", "_pad", "_pad2", "n_mix_qnt", "qnt_meteo"):
+            if name in ("mix_qnt", "_pad", "n_mix_qnt", "qnt_meteo"):
                 continue
             setattr(s, name, getattr(self, name))
         unknown = set(self.qnt_meteo) - set(METEO_QNT)
@@ -273,6 +274,9 @@ def load_library(strict: bool = False) -> C.CDLL:
         "mpb_set_uvwp": (i32, [vp, vp]),
         "mpb_get_atm": (i32, [vp, vp, vp, vp, vp, vp, i64]),
         "mpb_get_uvwp": (i32, [vp, vp]),
+        "mpb_set_iso_var": (i32, [vp, vp]),
+        "mpb_get_iso_var": (i32, [vp, vp]),
+        "mpb_set_balloon": (i32, [vp, i32, vp, vp]),
         "mpb_get_dt": (i32, [vp, vp]),
         "mpb_get_np": (i64, [vp]),
         "mpb_set_shard": (i32, [vp, i64, i64]),
@@ -425,6 +429,21 @@ class Engine:
         a = np.empty((self.np, 3), np.float32)
         self._ck(self._lib.mpb_get_uvwp(self._h, _ptr(a)))
         return a
+
+    def set_iso_var(self, iso_var):
+        a = np.ascontiguousarray(iso_var, np.float64)
+        self._ck(self._lib.mpb_set_iso_var(self._h, _ptr(a)))
+
+    def get_iso_var(self) -> np.ndarray:
+        a = np.empty(self.np, np.float64)
+        self._ck(self._lib.mpb_get_iso_var(self._h, _ptr(a)))
+        return a
+
+    def set_balloon(self, ts, ps):
+        ts, ps = np.ascontiguousarray(ts, np.float64), np.ascontiguousarray(ps, np.float64)
+        if ts.size != ps.size or ts.size < 1:
+            raise ValueError("balloon series: ts and ps must have the same length >= 1")
+        self._ck(self._lib.mpb_set_balloon(self._h, int(ts.size), _ptr(ts), _ptr(ps)))
 
     def get_dt(self) -> np.ndarray:
         a = np.empty(self.np, np.float64)

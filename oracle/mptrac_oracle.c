@@ -849,6 +849,40 @@ void orc_module_convection(const orc_ctl_t *ctl, const orc_met_t *met0, const or
   }
 }
 
+/* module_isosurf_init 4886-4952 (modes 1-3; mode 4 reads the balloon file into cache->iso_ts / iso_ps, which the caller
+ * provides here) and module_isosurf 4956-5004: every parcel, dt or not */
+void orc_module_isosurf_init(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm) {
+  if (ctl->isosurf < 1 || ctl->isosurf > 3) return;
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    if (ctl->isosurf == 1) { atm->iso_var[ip] = atm->p[ip]; continue; }
+    cell_t c = CELL_ZERO;
+    const double t = time3(met0, met0->t, met1, met1->t, atm->time[ip], atm->p[ip], atm->lon[ip], atm->lat[ip], &c, 1);
+    atm->iso_var[ip] = ctl->isosurf == 2 ? atm->p[ip] / t : theta_of(atm->p[ip], t);
+  }
+}
+
+void orc_module_isosurf(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm) {
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    if (ctl->isosurf == 1) {
+      atm->p[ip] = atm->iso_var[ip];
+    } else if (ctl->isosurf == 2 || ctl->isosurf == 3) {
+      cell_t c = CELL_ZERO;
+      const double t = time3(met0, met0->t, met1, met1->t, atm->time[ip], atm->p[ip], atm->lon[ip], atm->lat[ip], &c, 1);
+      atm->p[ip] = ctl->isosurf == 2 ? atm->iso_var[ip] * t : 1000. * pow(atm->iso_var[ip] / t, -1. / C_KAPPA);
+    } else if (ctl->isosurf == 4) {
+      const double tm = atm->time[ip];
+      if (tm <= atm->iso_ts[0]) atm->p[ip] = atm->iso_ps[0];
+      else if (tm >= atm->iso_ts[atm->iso_n - 1]) atm->p[ip] = atm->iso_ps[atm->iso_n - 1];
+      else {
+        const int i = bisect(atm->iso_ts, atm->iso_n, tm);
+        atm->p[ip] = linear(atm->iso_ts[i], atm->iso_ps[i], atm->iso_ts[i + 1], atm->iso_ps[i + 1], tm);
+      }
+    }
+  }
+}
+
 /* module_decay, 4227-4263 (and the reset of the total loss rate that precedes it, 7931-7936) */
 void orc_module_decay(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm) {
   const size_t st = (size_t)atm->q_stride;
@@ -870,7 +904,10 @@ void orc_module_decay(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *a
 
 void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_met_t *met0,
                       const orc_met_t *met1, orc_atm_t *atm, double t, uint64_t *ctr) {
-  if (t == ctl->t_start) orc_module_advect_init(ctl, met0, met1, atm);   /* 7863-7873 */
+  if (t == ctl->t_start) {   /* 7863-7873 */
+    if (ctl->isosurf >= 1 && ctl->isosurf <= 4) orc_module_isosurf_init(ctl, met0, met1, atm);
+    orc_module_advect_init(ctl, met0, met1, atm);
+  }
   orc_module_timesteps(ctl, met0, atm, t);
   if (ctl->sort_dt > 0 && fmod(t, ctl->sort_dt) == 0) orc_module_sort(ctl, met0, atm);
   orc_module_position(met0, met1, atm);
@@ -882,6 +919,7 @@ void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_me
   if ((ctl->conv_mix_pbl || ctl->conv_cape >= 0) && (ctl->conv_dt <= 0 || fmod(t, ctl->conv_dt) == 0))   /* 7905-7908 */
     orc_module_convection(ctl, met0, met1, atm, ctr);
   if (ctl->qnt_rp >= 0 && ctl->qnt_rhop >= 0) orc_module_sedi(ctl, met0, met1, atm);
+  if (ctl->isosurf >= 1 && ctl->isosurf <= 4) orc_module_isosurf(ctl, met0, met1, atm);   /* 7914-7916 */
   orc_module_position(met0, met1, atm);
   if (ctl->met_dt_out > 0 && (ctl->met_dt_out < ctl->dt_mod || fmod(t, ctl->met_dt_out) == 0)) {   /* 7927-7929 */
     int any = 0;

@@ -51,7 +51,7 @@ typedef struct {
   double tdec_trop, tdec_strat;
   int32_t conv_mix_pbl;
   int32_t qnt_m, qnt_vmr, qnt_mloss_decay, qnt_loss_rate;
-  int32_t _pad2;
+  int32_t isosurf;                      /* ctl->isosurf: 0 off, 1 pressure, 2 density, 3 potential temperature, 4 balloon */
 } orc_ctl_t;
 
 /* one met time level, dense: 3-D [nx][ny][np] (z fastest), 2-D [nx][ny] */
@@ -82,6 +82,9 @@ typedef struct {
   double *dt;       /* [np]   cache->dt   */
   float *uvwp;      /* [np][3] cache->uvwp */
   double *rs;       /* [3 np + 1] cache->rs */
+  double *iso_var;  /* [np] cache->iso_var (module_isosurf), attached to the array slot like uvwp; may be NULL */
+  int32_t iso_n, _pad;              /* balloon time series of ISOSURF 4: cache->iso_n, iso_ts, iso_ps */
+  const double *iso_ts, *iso_ps;
 } orc_atm_t;
 
 void orc_module_timesteps(const orc_ctl_t *ctl, const orc_met_t *met0, orc_atm_t *atm, double t);
@@ -100,6 +103,8 @@ void orc_module_sort(const orc_ctl_t *ctl, const orc_met_t *met0, orc_atm_t *atm
 void orc_module_meteo(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
 void orc_module_convection(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm, uint64_t *ctr);
 void orc_module_decay(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm);
+void orc_module_isosurf_init(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
+void orc_module_isosurf(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
 void orc_module_mixing(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm, double t);
 void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_met_t *met0,
                       const orc_met_t *met1, orc_atm_t *atm, double t, uint64_t *ctr);

@@ -28,9 +28,9 @@ _DBL_FIELDS = ("t_start", "t_stop", "dt_mod", "dt_met", "met_utm_ref_lat", "sort
                "mixing_lon0", "mixing_lon1", "mixing_lat0", "mixing_lat1", "mixing_z0", "mixing_z1", "met_dt_out")
 # module_convection / module_decay block at the end of orc_ctl_t, with the reference's defaults
 _TAIL_DBL = ("conv_cape", "conv_cin", "conv_pbl_trans", "conv_dt", "tdec_trop", "tdec_strat")
-_TAIL_INT = ("conv_mix_pbl", "qnt_m", "qnt_vmr", "qnt_mloss_decay", "qnt_loss_rate")
+_TAIL_INT = ("conv_mix_pbl", "qnt_m", "qnt_vmr", "qnt_mloss_decay", "qnt_loss_rate", "isosurf")
 _TAIL_DEFAULT = dict(conv_cape=-999.0, conv_cin=-999.0, conv_pbl_trans=0.0, conv_dt=-999.0, tdec_trop=0.0, tdec_strat=0.0,
-                     conv_mix_pbl=0, qnt_m=-1, qnt_vmr=-1, qnt_mloss_decay=-1, qnt_loss_rate=-1)
+                     conv_mix_pbl=0, qnt_m=-1, qnt_vmr=-1, qnt_mloss_decay=-1, qnt_loss_rate=-1, isosurf=0)
 # slots of orc_ctl_t::qnt_meteo (mptrac_oracle.h): 14 from the path's own fields, the 22 2-D and 9 3-D further fields of
 # INTPOL_TIME_ALL, 8 derived from t and h2o
 METEO_QNT = ("ps", "pbl", "p", "t", "rho", "u", "v", "w", "vh", "vz", "theta", "psat", "psice", "zeta_d",
@@ -47,7 +47,7 @@ class OrcCtl(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in _INT_FIELDS] + [("mix_qnt", C.c_int32 * MIX_MAXQ), ("_pad", C.c_int32)]
                 + [(n, C.c_double) for n in _DBL_FIELDS] + [("qnt_meteo", C.c_int32 * METEO_SLOTS)]
                 + [("qnt_zeta", C.c_int32), ("qnt_eta", C.c_int32)]
-                + [(n, C.c_double) for n in _TAIL_DBL] + [(n, C.c_int32) for n in _TAIL_INT] + [("_pad2", C.c_int32)])
+                + [(n, C.c_double) for n in _TAIL_DBL] + [(n, C.c_int32) for n in _TAIL_INT])
 
 
 _LEVEL_FIELDS = ("pl", "ul", "vl", "wl", "zetal", "zeta_dotl")   # model-level fields, [nx][ny][npl]
@@ -65,7 +65,8 @@ class OrcClim(C.Structure):
 
 class OrcAtm(C.Structure):
     _fields_ = [("np", C.c_int64), ("time", C.c_void_p), ("p", C.c_void_p), ("lon", C.c_void_p), ("lat", C.c_void_p),
-                ("q", C.c_void_p), ("q_stride", C.c_int64), ("dt", C.c_void_p), ("uvwp", C.c_void_p), ("rs", C.c_void_p)]
+                ("q", C.c_void_p), ("q_stride", C.c_int64), ("dt", C.c_void_p), ("uvwp", C.c_void_p), ("rs", C.c_void_p),
+                ("iso_var", C.c_void_p), ("iso_n", C.c_int32), ("_pad", C.c_int32), ("iso_ts", C.c_void_p), ("iso_ps", C.c_void_p)]
 
 
 def ctl_struct(ctl) -> OrcCtl:
@@ -136,19 +137,27 @@ class Parcels:
         self.uvwp = np.zeros((n, 3), np.float32) if uvwp is None else np.array(uvwp, np.float32)
         self.dt = np.zeros(n) if dt is None else np.array(dt, np.float64)
         self.rs = np.zeros(3 * n + 1)
+        self.iso_var = np.zeros(n)      # cache->iso_var (module_isosurf)
+        self.balloon = None             # (ts, ps) of ISOSURF 4
 
     @property
     def np(self):
         return self.time.size
 
     def copy(self) -> "Parcels":
-        return Parcels(self.time, self.p, self.lon, self.lat, self.q, self.uvwp, self.dt)
+        c = Parcels(self.time, self.p, self.lon, self.lat, self.q, self.uvwp, self.dt)
+        c.iso_var[:] = self.iso_var
+        c.balloon = self.balloon
+        return c
 
     def struct(self) -> OrcAtm:
         s = OrcAtm()
         s.np = self.time.size
-        for n in ("time", "p", "lon", "lat", "dt", "uvwp", "rs"):
+        for n in ("time", "p", "lon", "lat", "dt", "uvwp", "rs", "iso_var"):
             setattr(s, n, getattr(self, n).ctypes.data)
+        if self.balloon is not None:
+            self._bal = [np.ascontiguousarray(x, np.float64) for x in self.balloon]
+            s.iso_n, s.iso_ts, s.iso_ps = self._bal[0].size, self._bal[0].ctypes.data, self._bal[1].ctypes.data
         s.q = self.q.ctypes.data if self.q.size else None
         s.q_stride = self.q.shape[1] if self.q.size else 0
         return s
@@ -259,6 +268,10 @@ class Oracle:
             L.orc_module_convection(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a), C.byref(ctr))
         elif what == "decay":
             L.orc_module_decay(C.byref(c), C.byref(cl), C.byref(a))
+        elif what == "isosurf_init":
+            L.orc_module_isosurf_init(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a))
+        elif what == "isosurf":
+            L.orc_module_isosurf(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a))
         else:
             raise ValueError(what)
         self.ctr = ctr.value
@@ -284,7 +297,7 @@ class Oracle:
 
 
 _WHAT = {"timestep": 0, "timesteps": 1, "position": 2, "advect": 3, "diff_turb": 4, "diff_meso": 5, "sedi": 6,
-         "sort": 7, "mixing": 8, "meteo": 9, "advect_init": 10, "convection": 11, "decay": 12}
+         "sort": 7, "mixing": 8, "meteo": 9, "advect_init": 10, "convection": 11, "decay": 12, "isosurf_init": 13, "isosurf": 14}
 
 
 def reference_available() -> bool:

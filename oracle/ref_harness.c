@@ -180,6 +180,7 @@ static void apply_ctl(const orc_ctl_t *c) {
   h_ctl->conv_cape = c->conv_cape; h_ctl->conv_cin = c->conv_cin; h_ctl->conv_pbl_trans = c->conv_pbl_trans;
   h_ctl->conv_dt = c->conv_dt; h_ctl->conv_mix_pbl = c->conv_mix_pbl;
   h_ctl->tdec_trop = c->tdec_trop; h_ctl->tdec_strat = c->tdec_strat;
+  h_ctl->isosurf = c->isosurf;
 }
 
 static void put_atm(const orc_atm_t *a) {
@@ -191,6 +192,7 @@ static void put_atm(const orc_atm_t *a) {
   for (int iq = 0; iq < h_ctl->nq; iq++) memcpy(h_atm->q[iq], a->q + (size_t)iq * a->q_stride, 8 * n);
   if (a->dt) memcpy(h_cache->dt, a->dt, 8 * n);
   if (a->uvwp) memcpy(h_cache->uvwp, a->uvwp, 12 * n);
+  if (a->iso_var) memcpy(h_cache->iso_var, a->iso_var, 8 * n);
 }
 
 static void get_atm(orc_atm_t *a) {
@@ -201,6 +203,7 @@ static void get_atm(orc_atm_t *a) {
   if (a->dt) memcpy(a->dt, h_cache->dt, 8 * n);
   if (a->uvwp) memcpy(a->uvwp, h_cache->uvwp, 12 * n);
   if (a->rs) memcpy(a->rs, h_cache->rs, 8 * (3 * n + 1));
+  if (a->iso_var) memcpy(a->iso_var, h_cache->iso_var, 8 * n);
 }
 
 /* what: 0 mptrac_run_timestep, 1 timesteps, 2 position, 3 advect, 4 diff_turb, 5 diff_meso, 6 sedi,
@@ -210,6 +213,9 @@ int ref_run(const orc_ctl_t *ctl, orc_atm_t *atm, double t, int what, int nsteps
   apply_ctl(ctl);
   if (h_clim->tropo_ntime == 0) clim_tropo_init(h_clim);
   put_atm(atm);
+  /* ISOSURF 4: module_isosurf_init appends the balloon file (ctl->balloon, set through ref_read_ctl's overrides) to the
+     cache's time series without resetting its length */
+  if (what == 0 || what == 13) h_cache->iso_n = 0;
   rng_ctr = *ctr;
   switch (what) {
     case 0:
@@ -228,6 +234,8 @@ int ref_run(const orc_ctl_t *ctl, orc_atm_t *atm, double t, int what, int nsteps
     case 10: module_advect_init(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     case 11: module_convection(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     case 12: module_decay(h_ctl, h_cache, h_clim, h_atm); break;
+    case 13: module_isosurf_init(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
+    case 14: module_isosurf(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     default: return 1;
   }
   *ctr = rng_ctr;

@@ -260,3 +260,16 @@ extern "C" int emu_decay(int coord_type, double utm_ref_lat, double tdec_trop, d
   }
   return 0;
 }
+
+extern "C" int emu_isosurf(const EmuMet *m0, const EmuMet *m1, int mode, int init, long long np, const double *time, const double *lon,
+                           const double *lat, double *p, double *iso_var, const double *ts, const double *ps, int n) {
+  HostMet h;
+  make_view(h, m0, m1, true);
+#pragma omp parallel for
+  for (long long ip = 0; ip < np; ip++) {
+    Parcel a = {time[ip], lon[ip], lat[ip], p[ip]};
+    if (init) iso_var[ip] = isosurf_variable(h.g, mode, a);
+    else p[ip] = isosurf_pressure(h.g, mode, iso_var[ip], a, ts, ps, n);
+  }
+  return 0;
+}

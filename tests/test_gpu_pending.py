@@ -134,3 +134,36 @@ def test_decay_in_the_step_vs_oracle(oracle):
     for i in range(4):
         assert relerr(out["q"][i], ref.q[i]) < 1e-12, i
     assert np.all(ref.q[0] < q[0]) and np.all(ref.q[3] > 0)
+
+
+@pytest.mark.parametrize("isosurf", [1, 2, 3, 4])
+def test_isosurf_in_the_step_vs_oracle(oracle, isosurf):
+    """module_isosurf_init at t_start and module_isosurf between sedi and the final position check (which then runs as
+    its own launch); ISOSURF 4 with a balloon series uploaded through mpb_set_balloon"""
+    from mptrac_b200 import Ctl, Engine, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    n = 3000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=1.0, zmax=30.0, seed=12)
+    clim = synth.make_clim_tropo()
+    ctl = Ctl(advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, isosurf=isosurf, sort_dt=600.0)
+    balloon = (np.array([0.0, 400.0, 900.0, 1300.0]), np.array([500.0, 420.0, 380.0, 300.0]))
+    with Engine(n, nq=0, device=0) as eng:
+        eng.set_ctl(ctl)
+        eng.set_clim_tropo(*clim)
+        eng.set_met(0, m0)
+        eng.set_met(1, m1)
+        if isosurf == 4:
+            eng.set_balloon(*balloon)
+        eng.set_atm(tm, p, lon, lat)
+        for s in range(6):
+            eng.run_timestep(300.0 * s)
+        out = eng.get_atm()
+        iso = eng.get_iso_var()
+    ref = Parcels(tm, p, lon, lat)
+    ref.balloon = balloon
+    oracle.run("timestep", ctl, clim, m0, m1, ref, t=0.0, nsteps=6)
+    assert abserr(out["lat"], ref.lat) < 1e-11 and abserr(out["time"], ref.time) == 0
+    assert relerr(out["p"], ref.p) < 1e-12
+    if isosurf != 4:
+        assert relerr(iso, ref.iso_var) < 1e-13

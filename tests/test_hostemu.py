@@ -203,3 +203,35 @@ def test_module_decay_on_host_is_bit_exact(emu, oracle):
     assert emu.emu_decay(0, C.c_double(0.0), C.c_double(86400.0), C.c_double(864000.0), clim[0].size, clim[1].size, vp(clim[0]),
                          vp(clim[1]), vp(clim[2]), C.c_longlong(n), vp(a.time), vp(a.lat), vp(a.p), vp(a.dt), vp(aux), vp(tdec)) == 0
     assert np.array_equal(a.q[0] * aux, b.q[0]) and np.all(aux < 1) and np.ptp(tdec) > 0
+
+
+@pytest.mark.parametrize("isosurf", [1, 2, 3, 4])
+def test_module_isosurf_on_host_is_bit_exact(emu, oracle, isosurf):
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels, met_struct
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    n = 3000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=1.0, zmax=30.0, seed=12)
+    clim = synth.make_clim_tropo()
+    ctl = Ctl(advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, isosurf=isosurf)
+    ts, ps = np.array([0.0, 400.0, 900.0, 1300.0]), np.array([500.0, 420.0, 380.0, 300.0])
+    a = Parcels(tm, p, lon, lat)
+    a.balloon = (ts, ps)
+    b = a.copy()
+    s0, s1 = met_struct(m0), met_struct(m1)
+    vp = lambda x: C.c_void_p(x.ctypes.data)  # noqa: E731
+    args = lambda init: (C.byref(s0), C.byref(s1), isosurf, init, C.c_longlong(n), vp(a.time), vp(a.lon), vp(a.lat), vp(a.p),  # noqa: E731
+                         vp(a.iso_var), vp(ts), vp(ps), 4)
+    if isosurf != 4:
+        oracle.run("isosurf_init", ctl, clim, m0, m1, b)
+        assert emu.emu_isosurf(*args(1)) == 0
+        assert np.array_equal(a.iso_var, b.iso_var) and np.any(a.iso_var != 0)
+    for x in (a, b):                       # move the parcels: the restored pressure then differs from the present one
+        x.time[:] = np.linspace(-100.0, 1500.0, n)
+        x.lon[:] = (x.lon + 3.0 + 180.0) % 360.0 - 180.0
+        x.p[:] = x.p * 1.02
+    oracle.run("isosurf", ctl, clim, m0, m1, b)
+    assert emu.emu_isosurf(*args(0)) == 0
+    assert np.array_equal(a.p, b.p)
+    if isosurf != 1:
+        assert np.max(np.abs(a.p - p * 1.02)) > 1e-6

@@ -319,3 +319,36 @@ def test_module_decay_bit_exact(oracle, reference):
     oracle.run("timestep", ctl, clim, m0, m1, b, t=0.0, nsteps=4)
     assert _same(a, b)
     assert np.allclose(a.q[qi["loss_rate"]], 1.0 / 86400.0, rtol=0.9) and np.all(a.q[qi["loss_rate"]] > 0)
+
+
+@pytest.mark.parametrize("isosurf", [1, 2, 3, 4])
+def test_module_isosurf_bit_exact(oracle, reference, isosurf, tmp_path):
+    """module_isosurf_init + module_isosurf (src/mptrac.c:4886-5004): parcels kept on pressure / density / potential
+    temperature surfaces or on a balloon's pressure time series, inside the dispatcher (between sedi and the final
+    position check, every parcel every step)"""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    n = 3000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=1.0, zmax=30.0, seed=12)
+    balloon = (np.array([0.0, 400.0, 900.0, 1300.0]), np.array([500.0, 420.0, 380.0, 300.0]))
+    bfile = tmp_path / "balloon.tab"
+    bfile.write_text("# t p\n" + "".join(f"{t:.1f} {q:.1f}\n" for t, q in zip(*balloon)))
+    nq = reference.read_ctl([], f"BALLOON {bfile}" if isosurf == 4 else "")
+    reference.set_met(m0, m1)
+    clim = reference.clim_tropo()
+    ctl = Ctl(nq=nq, advect=4, diffusion=1, turb_dz_trop=0.5, turb_mesox=0.16, turb_mesoz=0.16, t_start=0.0, t_stop=1e6, dt_mod=300.0,
+              dt_met=21600.0, isosurf=isosurf)
+    a = Parcels(tm, p, lon, lat)
+    if isosurf == 4:
+        a.balloon = balloon
+    b = a.copy()
+    reference.ctr = oracle.ctr = 0
+    reference.run("timestep", ctl, a, t=0.0, nsteps=6)
+    oracle.run("timestep", ctl, clim, m0, m1, b, t=0.0, nsteps=6)
+    assert _same(a, b) and np.array_equal(a.iso_var, b.iso_var)
+    assert abserr(a.lat, lat) > 1e-3
+    if isosurf == 1:
+        assert np.array_equal(a.p, p)
+    if isosurf == 4:
+        assert np.all(a.p == 300.0)
