@@ -199,7 +199,8 @@ int mpb_run_timestep_host(mpb_ctx *ctx, double t, int64_t np, double *time, doub
 #define MPB_MOD_CONVECTION 0x400  /* between DIFF_MESO and SEDI (src/mptrac.c:7905-7908) */
 #define MPB_MOD_DECAY     0x800   /* reset of the total loss rate + module_decay, between METEO and MIXING (7931-7940) */
 #define MPB_MOD_ISOSURF   0x1000  /* between SEDI and POSITION1 (src/mptrac.c:7914-7916); its init runs at t_start */
-#define MPB_MOD_ALL       0x1fff
+#define MPB_MOD_DIFF_PBL  0x2000  /* TURB_PBL_SCHEME 1, between DIFF_TURB and DIFF_MESO (src/mptrac.c:7897-7899) */
+#define MPB_MOD_ALL       0x3fff
 int mpb_run_modules(mpb_ctx *ctx, double t, unsigned mask);
 
 /* --- single modules (same symbols the reference exports, src/mptrac.h:6140-7132); each is the

@@ -418,6 +418,30 @@ __global__ void swap_pairs_kernel(float2 *a, size_t n) {
   if (i < n) { const float2 v = a[i]; a[i] = make_float2(v.y, v.x); }
 }
 
+// module_diff_pbl (src/mptrac.c:4343-4584): parcels with dt != 0, three normals per parcel from the shared counter stream
+struct PblArgs {
+  MetView met;
+  PblFields f;
+  double *time, *lon, *lat, *p;
+  const double *dt;
+  float *uvwp;
+  unsigned long long ctr;
+  long long ig0, np;
+};
+__global__ void __launch_bounds__(128) diff_pbl_kernel(const __grid_constant__ PblArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np) return;
+  const double dt = A.dt[ip];
+  if (dt == 0) return;
+  Parcel a;
+  a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
+  float *s = A.uvwp + 3 * ip;
+  float up = s[0], vp = s[1], wp = s[2];
+  diffuse_pbl(A.met, A.f, A.ctr, dt, (unsigned long long)(A.ig0 + ip), a, up, vp, wp);
+  s[0] = up; s[1] = vp; s[2] = wp;
+  A.lon[ip] = a.lon; A.lat[ip] = a.lat; A.p[ip] = a.p;
+}
+
 // module_convection (src/mptrac.c:4102-4171): parcels with dt != 0; the uniform random number of parcel ip is number
 // ig0 + ip of the module's module_rng call (method 0), addressed by global index like the normals of the diffusion modules
 struct ConvArgs {
@@ -982,6 +1006,25 @@ static bool meteo_wanted(const mpb_ctl_t &k, int first, int last) {
 static bool convection_enabled(const mpb_ctl_t &k) { return k.conv_mix_pbl || k.conv_cape >= 0; }   // src/mptrac.c:7905
 static bool decay_enabled(const mpb_ctl_t &k) { return k.tdec_trop > 0 && k.tdec_strat > 0; }        // :7938
 
+static void launch_diff_pbl(mpb_ctx *c) {
+  REQUIRE(c->ctl.rng_type == 1, "only RNG_TYPE 1 (Squares) runs on the device");
+  const unsigned long long ctr = rng_draw(c);   // module_rng(3 np, normal)
+  if (c->np == 0) return;
+  PblArgs A;
+  A.met = met_view(c);
+  for (int f : {MPB_F2_ESS, MPB_F2_NSS, MPB_F2_SHF})
+    REQUIRE(c->x2[f] && c->x2_valid[0][f] && c->x2_valid[1][f],
+            "module_diff_pbl needs the met fields ess, nss and shf of both levels (mpb_met_view_t::x2)");
+  REQUIRE(c->x3[MPB_F3_H2O] && c->x3_valid[0][MPB_F3_H2O] && c->x3_valid[1][MPB_F3_H2O],
+          "module_diff_pbl needs the met field h2o of both levels (mpb_met_view_t::x3)");
+  A.f.ess = c->x2[MPB_F2_ESS]; A.f.nss = c->x2[MPB_F2_NSS]; A.f.shf = c->x2[MPB_F2_SHF]; A.f.h2o = c->x3[MPB_F3_H2O];
+  A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p(); A.dt = c->dt; A.uvwp = c->uvwp;
+  A.ctr = ctr; A.ig0 = c->ig0; A.np = c->np;
+  diff_pbl_kernel<<<nblocks(c->np, 128), 128, 0, c->stream>>>(A);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
 static void launch_convection(mpb_ctx *c) {
   const mpb_ctl_t &k = c->ctl;
   REQUIRE(k.rng_type == 1, "only RNG_TYPE 1 (Squares) runs on the device");
@@ -1535,7 +1578,8 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   const bool decay_now = (mask & MPB_MOD_DECAY) && (decay_enabled(k) || k.qnt_loss_rate >= 0);
   // timesteps ... position1 in one launch: dt stays in registers (modules that run as their own launch read it from memory)
   const bool iso_now = (mask & MPB_MOD_ISOSURF) && isosurf_enabled(k);
-  const bool whole = (mask & 0xff) == 0xff && !on_levels && !conv_now && !decay_now && !iso_now;
+  const bool pbl_now = (mask & MPB_MOD_DIFF_PBL) && k.diffusion && k.turb_pbl_scheme == 1;   // src/mptrac.c:7897-7899
+  const bool whole = (mask & 0xff) == 0xff && !on_levels && !pbl_now && !conv_now && !decay_now && !iso_now;
   if ((mask & MPB_MOD_TIMESTEPS) && t == k.t_start) {   // src/mptrac.c:7863-7873
     if (iso_now) launch_isosurf(c, true);
     launch_advect_init(c);
@@ -1555,32 +1599,25 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   } else if (sort_now) {
     do_sort(c);
   }
-  // module_isosurf sits between sedi and the final position check (src/mptrac.c:7910-7919): that check then runs alone
-  const unsigned pre = modules & (MOD_TIMESTEPS | MOD_STORE_DT | MOD_POS_PRE), post = iso_now ? 0u : (modules & MOD_POS_POST);
-  if (iso_now) modules &= ~MOD_POS_POST;
-  if (on_levels && !conv_now) {
-    if (pre) launch_step(c, t, 0, 0, pre);
-    launch_advect_levels(c);
-    if (post || phys) launch_step(c, t, 0, phys, post);
-  } else if (conv_now) {
-    // module_convection sits between diff_meso and sedi (src/mptrac.c:7897-7912): the fused step splits around it
-    const unsigned before = phys & (PHYS_TURB | PHYS_MESO), after = phys & PHYS_SEDI;
-    if (on_levels) {
-      if (pre) launch_step(c, t, 0, 0, pre);
-      launch_advect_levels(c);
-      if (before) launch_step(c, t, 0, before, 0);
-    } else if (pre || advect || before) {
-      launch_step(c, t, advect, before, pre);
-    }
-    launch_convection(c);
-    if (post || after) launch_step(c, t, 0, after, post);
-  } else if (modules || advect || phys) {
-    launch_step(c, t, advect, phys, modules);
-  }
-  if (iso_now) {
-    launch_isosurf(c, false);
-    if (mask & MPB_MOD_POSITION1) launch_step(c, t, 0, 0, MOD_POS_POST);
-  }
+  // The per-parcel modules in the reference's order (src/mptrac.c:7876-7919).  Everything the fused kernel covers
+  // accumulates in one segment; a module that runs as its own launch -- model-level advection, diff_pbl, convection,
+  // isosurf -- flushes the segment before it, so a plain configuration is ONE launch and each such module adds two.
+  int seg_advect = 0;
+  unsigned seg_phys = 0, seg_modules = modules & (MOD_TIMESTEPS | MOD_STORE_DT | MOD_POS_PRE);
+  auto flush = [&]() {
+    if (seg_advect || seg_phys || seg_modules) launch_step(c, t, seg_advect, seg_phys, seg_modules);
+    seg_advect = 0; seg_phys = 0; seg_modules = 0;
+  };
+  if (on_levels) { flush(); launch_advect_levels(c); }
+  else seg_advect = advect;
+  seg_phys |= phys & PHYS_TURB;
+  if (pbl_now) { flush(); launch_diff_pbl(c); }
+  seg_phys |= phys & PHYS_MESO;
+  if (conv_now) { flush(); launch_convection(c); }
+  seg_phys |= phys & PHYS_SEDI;
+  if (iso_now) { flush(); launch_isosurf(c, false); }
+  seg_modules |= modules & MOD_POS_POST;
+  flush();
   if ((mask & MPB_MOD_METEO) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out)))   // src/mptrac.c:7927-7929
     launch_meteo(c);
   if (decay_now) launch_decay(c);   // src/mptrac.c:7931-7940
@@ -1614,6 +1651,7 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
   const bool mix_now = k.mixing_trop >= 0 && k.mixing_strat >= 0 && (k.mixing_dt <= 0 || hits(t, k.mixing_dt)) && k.n_mix_qnt > 0;
   const bool meteo_now = meteo_wanted(k) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out));
   if (sort_now || mix_now || meteo_now || k.advect_vert_coord != 0 || convection_enabled(k) || decay_enabled(k) || k.qnt_loss_rate >= 0 || isosurf_enabled(k) ||
+      (k.diffusion && k.turb_pbl_scheme == 1) ||
       np < 4 * kHostChunkMin) {
     // steps with a global phase (cell sort, box means), steps that write quantities (meteo) and tiny problems take the
     // plain sequence

@@ -209,6 +209,9 @@ MPB_HD double lin(double x0, double y0, double x1, double y1, double x) {
   return y0 + fdiv(y1 - y0, x1 - x0) * (x - x0);
 }
 
+// log-pressure altitude [km], Z(p) (src/mptrac.h:2243)
+MPB_HD double altitude(double p) { return kH0 * log(kP0 / p); }
+
 // km -> hPa at pressure p (src/mptrac.h:941)
 MPB_HD double dz2dp(double dz, double p) { return quot(-dz * p, kH0, kRH0); }
 
@@ -1338,6 +1341,142 @@ MPB_HD double zeta_diagnosed(double ps, double p, double t) {                   
 }
 
 // ----------------------------------------------------------------------------------------------
+// module_diff_pbl (4343-4584, TURB_PBL_SCHEME 1): Hanna / FLEXPART closure inside the boundary layer.  Velocity standard
+// deviations, their vertical derivative and the Lagrangian time scales follow from the friction velocity (surface
+// stresses ess, nss), the surface heat flux shf through the Monin-Obukhov length, and the height within the PBL; then
+// a Langevin update of the three velocity perturbations, the horizontal displacement, and the vertical one in
+// geometric height with reflection at the ground and the PBL top.  Parcels above the PBL are left to diff_turb.
+// ----------------------------------------------------------------------------------------------
+struct PblFields {
+  const float2 *ess, *nss, *shf;   // 2-D (MPB_F2_ESS, _NSS, _SHF), both time levels
+  const float2 *h2o;               // 3-D (MPB_F3_H2O)
+};
+MPB_HD double max_of(double a, double b) { return a > b ? a : b; }    // MAX, src/mptrac.h:1378
+MPB_HD double clamp_of(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }   // CLAMP :756
+
+MPB_HD void diffuse_pbl(const MetView &g, const PblFields &f, uint64_t ctr, double dt, uint64_t ig, Parcel &a,
+                        float &up, float &vp, float &wp) {
+  double dsigw_dz = 0.0, sig_u = 0.0, sig_v = 0.0, sig_w = 0.0, tau_u = 0.0, tau_v = 0.0, tau_w = 0.0;
+  CellAxes ax;
+  axes_reset(ax);
+  double ps, pbl;
+  surface_at(g, a.time, a.lon, a.lat, ax, ps, pbl);
+  if (a.p < pbl) return;
+  if (!(ps > 0.0 && pbl > 0.0 && ps > pbl)) return;
+  const double p = a.p < ps ? a.p : ps;
+  const double zs = altitude(ps);
+  const double z_raw = 1e3 * (altitude(p) - zs);
+  const double zi = 1e3 * (altitude(pbl) - zs);
+  if (!(zi > 1.0)) return;
+  const double z = clamp_of(z_raw, 0.0, zi);
+  const double zeta = clamp_of(z / zi, 1e-6, 1.0 - 1e-6);
+  const double z_m = max_of(z, 1.0);
+  Stencil s2;
+  stencil_2d(g, a.lon, a.lat, ax, s2);
+  const double wt = time_weight(g, a.time);
+  const double ess = field2_at(g, f.ess, s2, wt), nss = field2_at(g, f.nss, s2, wt);
+  CubeT<true> cube;
+  cube_reset(cube);
+  Stencil s;
+  locate(g, a.lon, a.lat, p, cube, s);
+  const double t = lerp_f64(wt, MPB_TRILERP_OF(cube, s, t0), MPB_TRILERP_OF(cube, s, t1));
+  const double h2o = field3_at(g, f.h2o, s, wt);
+  const double hh = max_of(h2o, 0.1e-6);
+  const double tv = t * (1. + (1. - kEps) * hh);                                    // TVIRT
+  const double thetav = potential_temperature(p, t) * (1. + (1. - kEps) * max_of(hh, 0.1e-6));   // THETAVIRT :2153
+  const double rho = 100. * p / (kRA * tv);                                         // RHO
+  const double tau = sqrt(ess * ess + nss * nss);
+  if (!(rho > 0.0)) return;
+  const double ustar = sqrt(max_of(tau / rho, 0.0));
+  const double ust = max_of(1e-4, ustar);
+  const double shf = field2_at(g, f.shf, s2, wt);
+  double ol = 1e12;
+  if (fabs(shf) > 1e-6) ol = thetav * rho * kCpd * (ust * ust) * ust / (0.40 * kG0 * shf);   // KARMAN = 0.40
+  if (zi / fabs(ol) < 1.0) {            // neutral
+    const double corr = z_m / ust;
+    const double sigw0 = 1.3 * ust * exp(-2e-4 * corr);
+    sig_u = max_of(2.0 * ust * exp(-3e-4 * corr), 1e-5);
+    sig_v = max_of(sigw0, 1e-5);
+    sig_w = max_of(sigw0, 1e-5);
+    dsigw_dz = -2e-4 * sigw0 / ust;
+    tau_u = 0.5 * z_m / sig_w / (1.0 + 1.5e-3 * corr);
+    tau_v = tau_u;
+    tau_w = tau_u;
+  } else if (ol < 0.0) {                // unstable
+    const double wstar_arg = -kG0 / thetav * shf / (rho * kCpd) * zi;
+    const double wstar = pow(max_of(wstar_arg, 0.0), 1.0 / 3.0);
+    double dsigw2_dz = 0.0;
+    sig_u = max_of(ust * pow(max_of(12.0 - 0.5 * zi / ol, 0.0), 1.0 / 3.0), 1e-6);
+    sig_v = sig_u;
+    if (zeta < 0.03) {
+      const double arg = max_of(3.0 * zeta - ol / zi, 1e-12);
+      sig_w = 0.96 * wstar * pow(arg, 1.0 / 3.0);
+      dsigw2_dz = 1.8432 * (wstar * wstar) / zi * pow(arg, -1.0 / 3.0);
+    } else if (zeta < 0.4) {
+      const double arg = max_of(3.0 * zeta - ol / zi, 1e-12);
+      const double s1 = 0.96 * pow(arg, 1.0 / 3.0);
+      const double sb = 0.763 * pow(zeta, 0.175);
+      if (s1 < sb) {
+        sig_w = wstar * s1;
+        dsigw2_dz = 1.8432 * (wstar * wstar) / zi * pow(arg, -1.0 / 3.0);
+      } else {
+        sig_w = wstar * sb;
+        dsigw2_dz = 0.203759 * (wstar * wstar) / zi * pow(zeta, -0.65);
+      }
+    } else if (zeta < 0.96) {
+      sig_w = 0.722 * wstar * pow(1.0 - zeta, 0.207);
+      dsigw2_dz = -0.215812 * (wstar * wstar) / zi * pow(1.0 - zeta, -0.586);
+    } else {
+      sig_w = 0.37 * wstar;
+      dsigw2_dz = 0.0;
+    }
+    sig_w = max_of(sig_w, 1e-6);
+    dsigw_dz = sig_w > 1e-12 ? 0.5 * dsigw2_dz / sig_w : 0.0;
+    tau_u = 0.15 * zi / max_of(sig_u, 1e-12);
+    tau_v = tau_u;
+    if (z_m < fabs(ol)) {
+      const double denom = 0.55 - 0.38 * fabs(z_m / ol);
+      tau_w = 0.1 * z_m / (sig_w * max_of(denom, 0.05));
+    } else if (zeta < 0.1)
+      tau_w = 0.59 * z_m / sig_w;
+    else
+      tau_w = 0.15 * zi / sig_w * (1.0 - exp(-5.0 * zeta));
+  } else {                              // stable
+    sig_u = max_of(2.0 * ust * (1.0 - zeta), 1e-6);
+    sig_v = max_of(1.3 * ust * (1.0 - zeta), 1e-6);
+    sig_w = max_of(1.3 * ust * (1.0 - zeta), 1e-6);
+    dsigw_dz = -1.3 * ust / zi;
+    tau_u = 0.15 * zi / sig_u * sqrt(zeta);
+    tau_v = 0.467 * tau_u;
+    tau_w = 0.1 * zi / sig_w * pow(zeta, 0.8);
+  }
+  tau_u = max_of(tau_u, 10.0);
+  tau_v = max_of(tau_v, 10.0);
+  tau_w = max_of(tau_w, 30.0);
+  if (!(sig_u > 0.0 && sig_v > 0.0 && sig_w > 0.0 && tau_u > 0.0 && tau_v > 0.0 && tau_w > 0.0)) return;
+
+  double n0, n1, n2;
+  normals3(ctr, ig, n0, n1, n2);
+  const double dt_abs = fabs(dt);
+  const double ru = exp(-dt_abs / tau_u), ru2 = sqrt(max_of(0.0, 1.0 - ru * ru));
+  const double rv = exp(-dt_abs / tau_v), rv2 = sqrt(max_of(0.0, 1.0 - rv * rv));
+  up = (float)(up * ru + sig_u * ru2 * n0);
+  vp = (float)(vp * rv + sig_v * rv2 * n1);
+  const double rw = exp(-dt_abs / tau_w), rw2 = sqrt(max_of(0.0, 1.0 - rw * rw));
+  const double rhoaux = -1.0 / (1e3 * kH0);
+  wp = (float)(wp * rw + sig_w * rw2 * n2 + tau_w * (1.0 - rw) * (2.0 * sig_w * dsigw_dz + rhoaux * (sig_w * sig_w)));
+  a.lon += dx2coord(g.coord_type, up * dt, a.lat);
+  a.lat += dy2coord(g.coord_type, vp * dt);
+  double znew = z + wp * dt;
+  while (znew < 0.0 || znew > zi) {
+    if (znew < 0.0) { znew = -znew; wp = -wp; }
+    if (znew > zi) { znew = 2.0 * zi - znew; wp = -wp; }
+  }
+  a.p = kP0 * exp(-(zs + znew / 1000.0) / kH0);    // P(z), src/mptrac.h:1784
+  a.p = clamp_of(a.p, pbl, ps);
+}
+
+// ----------------------------------------------------------------------------------------------
 // module_convection (4102-4171): the mixing range reaches from the surface to the PBL top (CONV_MIX_PBL) and / or to
 // the equilibrium level where CAPE (and CIN) pass their thresholds; the parcel's new pressure is uniformly distributed
 // in density over that range, `r` being the parcel's uniform random number
@@ -1414,7 +1553,6 @@ MPB_HD int cell_key(const MetView &g, double lon, double lat, double p) {
 }
 
 // altitude of a pressure (src/mptrac.h:2243)
-MPB_HD double altitude(double p) { return kH0 * log(kP0 / p); }
 
 // box index of module_mixing / write_grid (5201-5218, 13844-13860); -1 = outside
 MPB_HD int box_index(double time, double lon, double lat, double p, double t0, double t1,

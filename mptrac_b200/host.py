@@ -31,8 +31,8 @@ MET_X2 = ("ts", "zs", "us", "vs", "ess", "nss", "shf", "lsm", "sst", "pt", "tt",
 MET_X3 = ("z", "pv", "h2o", "o3", "lwc", "rwc", "iwc", "swc", "cc")   # [nx][ny][np]; "z" is the geopotential height that quantity zg reports
 # module bits of mpb_run_modules (include/mptrac_b200.h MPB_MOD_*)
 (MOD_TIMESTEPS, MOD_SORT, MOD_POSITION0, MOD_ADVECT, MOD_DIFF_TURB, MOD_DIFF_MESO, MOD_SEDI, MOD_POSITION1, MOD_MIXING,
- MOD_METEO, MOD_CONVECTION, MOD_DECAY, MOD_ISOSURF) = (1 << i for i in range(13))
-MOD_ALL = 0x1fff
+ MOD_METEO, MOD_CONVECTION, MOD_DECAY, MOD_ISOSURF, MOD_DIFF_PBL) = (1 << i for i in range(14))
+MOD_ALL = 0x3fff
 _LIBDIR = Path(__file__).resolve().parent / "_lib"
 
 

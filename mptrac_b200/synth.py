@@ -142,7 +142,7 @@ def add_meteo_fields(met: Met, seed=11, with_gaps=True) -> Met:
     w2 = np.sin(3 * lam2 + 0.1 * met.time / 21600.0) * np.cos(phi2)
     two = {
         "ts": 288.0 - 40.0 * np.sin(phi2) ** 2 + 3.0 * w2, "zs": 0.5 * (1.0 + w2) * np.cos(phi2) ** 2,
-        "us": 5.0 * np.cos(phi2) + 2.0 * w2, "vs": 2.0 * w2, "ess": 0.1 * w2, "nss": -0.05 * w2, "shf": 50.0 * (1.0 + w2),
+        "us": 5.0 * np.cos(phi2) + 2.0 * w2, "vs": 2.0 * w2, "ess": 0.1 * w2, "nss": -0.05 * w2, "shf": 120.0 * w2 - 10.0,
         "lsm": (w2 > 0.2).astype(np.float64), "sst": 290.0 - 25.0 * np.sin(phi2) ** 2 + w2,
         "pt": 100.0 + 200.0 * np.sin(phi2) ** 2 + 10.0 * w2, "tt": 200.0 + 15.0 * np.sin(phi2) ** 2 + w2,
         "zt": 17.0 - 9.0 * np.sin(phi2) ** 2 + 0.3 * w2, "h2ot": 4e-6 * (1.0 + 0.2 * w2),

@@ -13,6 +13,7 @@
 #include "mptrac_oracle.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -812,11 +813,150 @@ void orc_module_meteo(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * module_diff_pbl, 4343-4584 (TURB_PBL_SCHEME 1): Hanna / FLEXPART turbulence closure inside the boundary layer -- neutral,
+ * unstable and stable regimes from the Monin-Obukhov length --, Langevin update of the three velocity perturbations,
+ * horizontal displacement, vertical displacement in geometric height with reflection at the ground and the PBL top
+ * ------------------------------------------------------------------------------------------- */
+#define O_MAX(a, b) (((a) > (b)) ? (a) : (b))
+#define O_MIN(a, b) (((a) < (b)) ? (a) : (b))
+#define O_CLAMP(v, lo, hi) (((v) < (lo)) ? (lo) : (((v) > (hi)) ? (hi) : (v)))
+#define O_SQR(x) ((x) * (x))
+#define O_Z(p) (C_H0 * log(C_P0 / (p)))
+void orc_module_diff_pbl(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm, uint64_t *ctr) {
+  (void)ctl;
+  if (!met0->x2[4] || !met0->x2[5] || !met0->x2[6] || !met0->x3[2] || !met1->x2[4] || !met1->x2[5] || !met1->x2[6] || !met1->x3[2]) {
+    fprintf(stderr, "orc_module_diff_pbl: the met levels lack ess, nss, shf or h2o\n");
+    abort();
+  }
+  orc_module_rng(atm->rs, 3 * atm->np, 1, ctr);
+  const int ct = met0->coord_type;
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    if (atm->dt[ip] == 0) continue;
+    const double tm = atm->time[ip], lon = atm->lon[ip], lat = atm->lat[ip];
+    double dsigw_dz = 0.0, sig_u = 0.0, sig_v = 0.0, sig_w = 0.0, tau_u = 0.0, tau_v = 0.0, tau_w = 0.0;
+    cell_t c = CELL_ZERO;
+    const double pbl = time2(met0, met0->pbl, met1, met1->pbl, tm, lon, lat, &c, 1);
+    if (atm->p[ip] < pbl) continue;
+    const double ps = time2(met0, met0->ps, met1, met1->ps, tm, lon, lat, &c, 0);
+    if (!(ps > 0.0 && pbl > 0.0 && ps > pbl)) continue;
+    const double p = O_MIN(atm->p[ip], ps);
+    const double zs = O_Z(ps);
+    const double z_raw = 1e3 * (O_Z(p) - zs);
+    const double zi = 1e3 * (O_Z(pbl) - zs);
+    if (!(zi > 1.0)) continue;
+    const double z = O_CLAMP(z_raw, 0.0, zi);
+    const double zeta = O_CLAMP(z / zi, 1e-6, 1.0 - 1e-6);
+    const double z_m = O_MAX(z, 1.0);
+    const double ess = time2(met0, met0->x2[4], met1, met1->x2[4], tm, lon, lat, &c, 0);
+    const double nss = time2(met0, met0->x2[5], met1, met1->x2[5], tm, lon, lat, &c, 0);
+    const double t = time3(met0, met0->t, met1, met1->t, tm, p, lon, lat, &c, 1);
+    const double h2o = time3(met0, met0->x3[2], met1, met1->x3[2], tm, p, lon, lat, &c, 0);
+    const double hh = O_MAX(h2o, 0.1e-6);
+    const double tv = t * (1. + (1. - C_EPS) * hh);
+    const double thetav = theta_of(p, t) * (1. + (1. - C_EPS) * O_MAX(hh, 0.1e-6));
+    const double rho = 100. * p / (C_RA * tv);
+    const double tau = sqrt(O_SQR(ess) + O_SQR(nss));
+    if (!(rho > 0.0)) continue;
+    const double ustar = sqrt(O_MAX(tau / rho, 0.0));
+    const double ust = O_MAX(1e-4, ustar);
+    const double shf = time2(met0, met0->x2[6], met1, met1->x2[6], tm, lon, lat, &c, 1);
+    double ol = 1e12;
+    if (fabs(shf) > 1e-6) ol = thetav * rho * C_CPD * O_SQR(ust) * ust / (0.40 * C_G0 * shf);
+    if (zi / fabs(ol) < 1.0) {
+      const double corr = z_m / ust;
+      const double sigw0 = 1.3 * ust * exp(-2e-4 * corr);
+      sig_u = O_MAX(2.0 * ust * exp(-3e-4 * corr), 1e-5);
+      sig_v = O_MAX(sigw0, 1e-5);
+      sig_w = O_MAX(sigw0, 1e-5);
+      dsigw_dz = -2e-4 * sigw0 / ust;
+      tau_u = 0.5 * z_m / sig_w / (1.0 + 1.5e-3 * corr);
+      tau_v = tau_u;
+      tau_w = tau_u;
+    } else if (ol < 0.0) {
+      const double wstar_arg = -C_G0 / thetav * shf / (rho * C_CPD) * zi;
+      const double wstar = pow(O_MAX(wstar_arg, 0.0), 1.0 / 3.0);
+      double dsigw2_dz = 0.0;
+      sig_u = O_MAX(ust * pow(O_MAX(12.0 - 0.5 * zi / ol, 0.0), 1.0 / 3.0), 1e-6);
+      sig_v = sig_u;
+      if (zeta < 0.03) {
+        const double arg = O_MAX(3.0 * zeta - ol / zi, 1e-12);
+        sig_w = 0.96 * wstar * pow(arg, 1.0 / 3.0);
+        dsigw2_dz = 1.8432 * O_SQR(wstar) / zi * pow(arg, -1.0 / 3.0);
+      } else if (zeta < 0.4) {
+        const double arg = O_MAX(3.0 * zeta - ol / zi, 1e-12);
+        const double s1 = 0.96 * pow(arg, 1.0 / 3.0);
+        const double s2 = 0.763 * pow(zeta, 0.175);
+        if (s1 < s2) {
+          sig_w = wstar * s1;
+          dsigw2_dz = 1.8432 * O_SQR(wstar) / zi * pow(arg, -1.0 / 3.0);
+        } else {
+          sig_w = wstar * s2;
+          dsigw2_dz = 0.203759 * O_SQR(wstar) / zi * pow(zeta, -0.65);
+        }
+      } else if (zeta < 0.96) {
+        sig_w = 0.722 * wstar * pow(1.0 - zeta, 0.207);
+        dsigw2_dz = -0.215812 * O_SQR(wstar) / zi * pow(1.0 - zeta, -0.586);
+      } else {
+        sig_w = 0.37 * wstar;
+        dsigw2_dz = 0.0;
+      }
+      sig_w = O_MAX(sig_w, 1e-6);
+      dsigw_dz = sig_w > 1e-12 ? 0.5 * dsigw2_dz / sig_w : 0.0;
+      tau_u = 0.15 * zi / O_MAX(sig_u, 1e-12);
+      tau_v = tau_u;
+      if (z_m < fabs(ol)) {
+        const double denom = 0.55 - 0.38 * fabs(z_m / ol);
+        tau_w = 0.1 * z_m / (sig_w * O_MAX(denom, 0.05));
+      } else if (zeta < 0.1)
+        tau_w = 0.59 * z_m / sig_w;
+      else
+        tau_w = 0.15 * zi / sig_w * (1.0 - exp(-5.0 * zeta));
+    } else {
+      sig_u = O_MAX(2.0 * ust * (1.0 - zeta), 1e-6);
+      sig_v = O_MAX(1.3 * ust * (1.0 - zeta), 1e-6);
+      sig_w = O_MAX(1.3 * ust * (1.0 - zeta), 1e-6);
+      dsigw_dz = -1.3 * ust / zi;
+      tau_u = 0.15 * zi / sig_u * sqrt(zeta);
+      tau_v = 0.467 * tau_u;
+      tau_w = 0.1 * zi / sig_w * pow(zeta, 0.8);
+    }
+    tau_u = O_MAX(tau_u, 10.0);
+    tau_v = O_MAX(tau_v, 10.0);
+    tau_w = O_MAX(tau_w, 30.0);
+    if (!(sig_u > 0.0 && sig_v > 0.0 && sig_w > 0.0 && tau_u > 0.0 && tau_v > 0.0 && tau_w > 0.0)) continue;
+    const double dt = atm->dt[ip], dt_abs = fabs(dt);
+    const double ru = exp(-dt_abs / tau_u), ru2 = sqrt(O_MAX(0.0, 1.0 - O_SQR(ru)));
+    const double rv = exp(-dt_abs / tau_v), rv2 = sqrt(O_MAX(0.0, 1.0 - O_SQR(rv)));
+    float *up = atm->uvwp + 3 * ip;
+    up[0] = (float)(up[0] * ru + sig_u * ru2 * atm->rs[3 * ip]);
+    up[1] = (float)(up[1] * rv + sig_v * rv2 * atm->rs[3 * ip + 1]);
+    const double rw = exp(-dt_abs / tau_w), rw2 = sqrt(O_MAX(0.0, 1.0 - O_SQR(rw)));
+    const double rhoaux = -1.0 / (1e3 * C_H0);
+    up[2] = (float)(up[2] * rw + sig_w * rw2 * atm->rs[3 * ip + 2]
+                    + tau_w * (1.0 - rw) * (2.0 * sig_w * dsigw_dz + rhoaux * O_SQR(sig_w)));
+    atm->lon[ip] += east_m_to_coord(ct, up[0] * dt, atm->lat[ip]);
+    atm->lat[ip] += north_m_to_coord(ct, up[1] * dt);
+    double znew = z + up[2] * dt;
+    while (znew < 0.0 || znew > zi) {
+      if (znew < 0.0) { znew = -znew; up[2] = -up[2]; }
+      if (znew > zi) { znew = 2.0 * zi - znew; up[2] = -up[2]; }
+    }
+    atm->p[ip] = C_P0 * exp(-(zs + znew / 1000.0) / C_H0);
+    atm->p[ip] = O_CLAMP(atm->p[ip], pbl, ps);
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
  * module_convection, 4102-4171: one uniform random number per parcel (module_rng method 0), the mixing range from the
  * surface to the PBL top and / or the equilibrium level where CAPE (and CIN) pass their thresholds, the new pressure
  * uniformly distributed in density between the two
  * ------------------------------------------------------------------------------------------- */
 void orc_module_convection(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm, uint64_t *ctr) {
+  if (ctl->conv_cape >= 0 && (!met0->x2[18] || !met0->x2[19] || !met0->x2[20] || !met1->x2[18] || !met1->x2[19] || !met1->x2[20])) {
+    fprintf(stderr, "orc_module_convection: the met levels lack cape, cin or pel\n");
+    abort();
+  }
   orc_module_rng(atm->rs, atm->np, 0, ctr);
   const float *cape0 = met0->x2[19], *cape1 = met1->x2[19], *cin0 = met0->x2[20], *cin1 = met1->x2[20];
   const float *pel0 = met0->x2[18], *pel1 = met1->x2[18];
@@ -915,6 +1055,7 @@ void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_me
   if (ctl->diffusion && (ctl->turb_dx_pbl > 0 || ctl->turb_dz_pbl > 0 || ctl->turb_dx_trop > 0 ||
                          ctl->turb_dz_trop > 0 || ctl->turb_dx_strat > 0 || ctl->turb_dz_strat > 0))
     orc_module_diff_turb(ctl, clim, met0, met1, atm, ctr);
+  if (ctl->diffusion && ctl->turb_pbl_scheme == 1) orc_module_diff_pbl(ctl, met0, met1, atm, ctr);   /* 7897-7899 */
   if (ctl->diffusion && (ctl->turb_mesox > 0 || ctl->turb_mesoz > 0)) orc_module_diff_meso(ctl, met0, met1, atm, ctr);
   if ((ctl->conv_mix_pbl || ctl->conv_cape >= 0) && (ctl->conv_dt <= 0 || fmod(t, ctl->conv_dt) == 0))   /* 7905-7908 */
     orc_module_convection(ctl, met0, met1, atm, ctr);

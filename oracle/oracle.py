@@ -268,6 +268,8 @@ class Oracle:
             L.orc_module_convection(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a), C.byref(ctr))
         elif what == "decay":
             L.orc_module_decay(C.byref(c), C.byref(cl), C.byref(a))
+        elif what == "diff_pbl":
+            L.orc_module_diff_pbl(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a), C.byref(ctr))
         elif what == "isosurf_init":
             L.orc_module_isosurf_init(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a))
         elif what == "isosurf":
@@ -297,7 +299,7 @@ class Oracle:
 
 
 _WHAT = {"timestep": 0, "timesteps": 1, "position": 2, "advect": 3, "diff_turb": 4, "diff_meso": 5, "sedi": 6,
-         "sort": 7, "mixing": 8, "meteo": 9, "advect_init": 10, "convection": 11, "decay": 12, "isosurf_init": 13, "isosurf": 14}
+         "sort": 7, "mixing": 8, "meteo": 9, "advect_init": 10, "convection": 11, "decay": 12, "isosurf_init": 13, "isosurf": 14, "diff_pbl": 15}
 
 
 def reference_available() -> bool:

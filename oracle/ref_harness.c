@@ -234,6 +234,7 @@ int ref_run(const orc_ctl_t *ctl, orc_atm_t *atm, double t, int what, int nsteps
     case 10: module_advect_init(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     case 11: module_convection(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     case 12: module_decay(h_ctl, h_cache, h_clim, h_atm); break;
+    case 15: module_diff_pbl(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     case 13: module_isosurf_init(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     case 14: module_isosurf(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     default: return 1;

@@ -273,3 +273,25 @@ extern "C" int emu_isosurf(const EmuMet *m0, const EmuMet *m1, int mode, int ini
   }
   return 0;
 }
+
+extern "C" int emu_diff_pbl(const EmuMet *m0, const EmuMet *m1, unsigned long long ctr, long long np, double *time, double *lon,
+                            double *lat, double *p, const double *dt, float *uvwp) {
+  HostMet h;
+  make_view(h, m0, m1, true);
+  const size_t nnode = (size_t)m0->nx * m0->ny * m0->np, ncol = (size_t)m0->nx * m0->ny;
+  std::vector<float2> e(ncol), n(ncol), sh(ncol), w(nnode);
+  for (size_t i = 0; i < ncol; i++) {
+    e[i] = make_float2(m0->x2[4][i], m1->x2[4][i]); n[i] = make_float2(m0->x2[5][i], m1->x2[5][i]);
+    sh[i] = make_float2(m0->x2[6][i], m1->x2[6][i]);
+  }
+  for (size_t i = 0; i < nnode; i++) w[i] = make_float2(m0->x3[2][i], m1->x3[2][i]);
+  const PblFields f = {e.data(), n.data(), sh.data(), w.data()};
+#pragma omp parallel for
+  for (long long ip = 0; ip < np; ip++) {
+    if (dt[ip] == 0) continue;
+    Parcel a = {time[ip], lon[ip], lat[ip], p[ip]};
+    diffuse_pbl(h.g, f, ctr, dt[ip], (uint64_t)ip, a, uvwp[3 * ip], uvwp[3 * ip + 1], uvwp[3 * ip + 2]);
+    lon[ip] = a.lon; lat[ip] = a.lat; p[ip] = a.p;
+  }
+  return 0;
+}

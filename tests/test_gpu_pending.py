@@ -167,3 +167,37 @@ def test_isosurf_in_the_step_vs_oracle(oracle, isosurf):
     assert relerr(out["p"], ref.p) < 1e-12
     if isosurf != 4:
         assert relerr(iso, ref.iso_var) < 1e-13
+
+
+def test_diff_pbl_in_the_step_vs_oracle(oracle):
+    """module_diff_pbl (TURB_PBL_SCHEME 1) between diff_turb and diff_meso: the fused step splits around it; its normals
+    come from the shared counter stream between those of the two other diffusion modules"""
+    from mptrac_b200 import Ctl, Engine, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    m0, m1 = synth.add_meteo_fields(m0, with_gaps=False), synth.add_meteo_fields(m1, with_gaps=False)
+    n = 6000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.0, zmax=4.0, seed=21)
+    clim = synth.make_clim_tropo()
+    ctl = Ctl(advect=2, diffusion=1, turb_pbl_scheme=1, turb_dz_trop=0.5, turb_dx_pbl=30.0, turb_dz_pbl=1.0, turb_mesox=0.16,
+              turb_mesoz=0.16, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0)
+    with Engine(n, nq=0, device=0) as eng:
+        eng.set_ctl(ctl)
+        eng.set_clim_tropo(*clim)
+        eng.set_met(0, m0)
+        eng.set_met(1, m1)
+        eng.set_atm(tm, p, lon, lat)
+        for s in range(4):
+            eng.run_timestep(300.0 * s)
+        out = eng.get_atm()
+        ctr = eng.rng_ctr
+        uv = eng.get_uvwp()
+    ref = Parcels(tm, p, lon, lat)
+    oracle.ctr = 0
+    oracle.run("timestep", ctl, clim, m0, m1, ref, t=0.0, nsteps=4)
+    assert ctr == oracle.ctr
+    assert abserr(out["lat"], ref.lat) < 1e-7 and abserr(out["time"], ref.time) == 0
+    # the closure switches regime and the reflection switches side at thresholds: a few parcels may fall on the other side
+    bad = np.abs(out["p"] - ref.p) > 1e-6 * ref.p
+    assert bad.mean() < 2e-3, bad.mean()
+    assert np.mean(np.abs(uv - ref.uvwp) > 1e-4 * (1 + np.abs(ref.uvwp))) < 2e-3

@@ -235,3 +235,27 @@ def test_module_isosurf_on_host_is_bit_exact(emu, oracle, isosurf):
     assert np.array_equal(a.p, b.p)
     if isosurf != 1:
         assert np.max(np.abs(a.p - p * 1.02)) > 1e-6
+
+
+def test_module_diff_pbl_on_host_is_bit_exact(emu, oracle):
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels, met_struct
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    m0, m1 = synth.add_meteo_fields(m0, with_gaps=False), synth.add_meteo_fields(m1, with_gaps=False)
+    n = 6000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.0, zmax=4.0, seed=21)
+    clim = synth.make_clim_tropo()
+    ctl = Ctl(advect=2, diffusion=1, turb_pbl_scheme=1, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0)
+    uvwp = np.random.default_rng(2).standard_normal((n, 3)).astype(np.float32)
+    a = Parcels(tm, p, lon, lat, None, uvwp)
+    oracle.run("timesteps", ctl, clim, m0, m1, a, t=300.0)
+    b = a.copy()
+    oracle.ctr = 23
+    oracle.run("diff_pbl", ctl, clim, m0, m1, b, t=300.0)
+    s0, s1 = met_struct(m0), met_struct(m1)
+    vp = lambda x: C.c_void_p(x.ctypes.data)  # noqa: E731
+    assert emu.emu_diff_pbl(C.byref(s0), C.byref(s1), C.c_ulonglong(23), C.c_longlong(n), vp(a.time), vp(a.lon), vp(a.lat), vp(a.p),
+                            vp(a.dt), vp(a.uvwp)) == 0
+    for k in ("lon", "lat", "p", "uvwp"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert 0.1 < np.mean(b.p != p) < 0.95

@@ -352,3 +352,37 @@ def test_module_isosurf_bit_exact(oracle, reference, isosurf, tmp_path):
         assert np.array_equal(a.p, p)
     if isosurf == 4:
         assert np.all(a.p == 300.0)
+
+
+def test_module_diff_pbl_bit_exact(oracle, reference):
+    """module_diff_pbl (src/mptrac.c:4343-4584, TURB_PBL_SCHEME 1): neutral, unstable and stable closures, reflection at the
+    ground and the PBL top; alone and inside the dispatcher (between diff_turb, which then skips the PBL, and diff_meso)"""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    m0, m1 = synth.add_meteo_fields(m0, with_gaps=False), synth.add_meteo_fields(m1, with_gaps=False)
+    n = 6000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.0, zmax=4.0, seed=21)
+    nq = reference.read_ctl([])
+    reference.set_met(m0, m1)
+    clim = reference.clim_tropo()
+    ctl = Ctl(nq=nq, advect=2, diffusion=1, turb_pbl_scheme=1, turb_dz_trop=0.5, turb_dx_pbl=30.0, turb_dz_pbl=1.0, turb_mesox=0.16,
+              turb_mesoz=0.16, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0)
+    rng = np.random.default_rng(2)
+    uvwp = rng.standard_normal((n, 3)).astype(np.float32)
+    a = Parcels(tm, p, lon, lat, None, uvwp)
+    reference.ctr = oracle.ctr = 11
+    reference.run("timesteps", ctl, a, t=300.0)
+    b = a.copy()
+    reference.run("diff_pbl", ctl, a, t=300.0)
+    oracle.run("diff_pbl", ctl, clim, m0, m1, b, t=300.0)
+    assert reference.ctr == oracle.ctr == 11 + 3 * n + 1
+    assert _same(a, b)
+    inside = a.p != p
+    assert 0.1 < inside.mean() < 0.95, inside.mean()
+    a = Parcels(tm, p, lon, lat, None, uvwp)
+    b = a.copy()
+    reference.ctr = oracle.ctr = 0
+    reference.run("timestep", ctl, a, t=0.0, nsteps=6)
+    oracle.run("timestep", ctl, clim, m0, m1, b, t=0.0, nsteps=6)
+    assert reference.ctr == oracle.ctr and _same(a, b)
