@@ -27,7 +27,8 @@ extern "C" {
 #endif
 
 /* ABI history (mpb_abi_version()): 2 module_meteo quantities of the resident fields; 3 model-level fields and the zeta / eta
- * quantities (ADVECT_VERT_COORD 1, 2, 3); 4 further met fields (x2 / x3), 64 meteo slots, module_convection and module_decay */
+ * quantities (ADVECT_VERT_COORD 1, 2, 3); 4 further met fields (x2 / x3), 64 meteo slots, module_convection, module_decay,
+ * module_isosurf, module_diff_pbl, module_bound_cond (their control fields at the end of mpb_ctl_t, MPB_MOD_* bits) */
 #define MPB_ABI_VERSION 4
 #define MPB_MIX_MAXQ 23  /* number of mixable quantities, src/mptrac.c:5222-5230 */
 
@@ -98,6 +99,12 @@ typedef struct mpb_ctl {
   int32_t qnt_m, qnt_vmr, qnt_mloss_decay, qnt_loss_rate;   /* quantity indices or -1 */
   int32_t isosurf;            /* ctl->isosurf: module_isosurf (src/mptrac.c:4956-5004), 0 = off, 1 pressure, 2 density,
                                  3 potential temperature, 4 balloon time series (mpb_set_balloon) */
+  /* module_bound_cond (src/mptrac.c:3789-3881): on when bound_lat0 < bound_lat1 and bound_p0 > bound_p1 (7926, 7997) */
+  double bound_mass, bound_mass_trend, bound_vmr, bound_vmr_trend;   /* ctl->bound_* */
+  double bound_lat0, bound_lat1, bound_p0, bound_p1, bound_dps, bound_dzs, bound_zetas;
+  int32_t bound_pbl, qnt_aoa;
+  int32_t qnt_cts[5];         /* ctl->qnt_Cccl4, qnt_Cccl3f, qnt_Cccl2f2, qnt_Cn2o, qnt_Csf6 */
+  int32_t cts_on;             /* bit i: ctl->clim_*_timeseries of species i is not "-" (series through mpb_set_clim_ts) */
 } mpb_ctl_t;
 
 /* Host view of one met_t time level (src/mptrac.h:3844-4014).  3-D element (ix,iy,iz) lives at
@@ -157,6 +164,8 @@ int mpb_get_uvwp(mpb_ctx *ctx, float *uvwp);
 int mpb_set_iso_var(mpb_ctx *ctx, const double *iso_var);
 int mpb_get_iso_var(mpb_ctx *ctx, double *iso_var);
 int mpb_set_balloon(mpb_ctx *ctx, int n, const double *ts, const double *ps);
+/* trace-gas time series of module_bound_cond, clim_t::ccl4, ccl3f, ccl2f2, n2o, sf6 (species 0 .. 4; src/mptrac.h:3821-3833) */
+int mpb_set_clim_ts(mpb_ctx *ctx, int species, int n, const double *time, const double *vmr);
 int mpb_get_dt(mpb_ctx *ctx, double *dt /* cache_t::dt */);
 int64_t mpb_get_np(mpb_ctx *ctx);
 
@@ -200,7 +209,9 @@ int mpb_run_timestep_host(mpb_ctx *ctx, double t, int64_t np, double *time, doub
 #define MPB_MOD_DECAY     0x800   /* reset of the total loss rate + module_decay, between METEO and MIXING (7931-7940) */
 #define MPB_MOD_ISOSURF   0x1000  /* between SEDI and POSITION1 (src/mptrac.c:7914-7916); its init runs at t_start */
 #define MPB_MOD_DIFF_PBL  0x2000  /* TURB_PBL_SCHEME 1, between DIFF_TURB and DIFF_MESO (src/mptrac.c:7897-7899) */
-#define MPB_MOD_ALL       0x3fff
+#define MPB_MOD_BOUND0    0x4000  /* module_bound_cond after METEO (src/mptrac.c:7926-7929) ... */
+#define MPB_MOD_BOUND1    0x8000  /* ... and again at the end of the step (7997-8000) */
+#define MPB_MOD_ALL       0xffff
 int mpb_run_modules(mpb_ctx *ctx, double t, unsigned mask);
 
 /* --- single modules (same symbols the reference exports, src/mptrac.h:6140-7132); each is the

@@ -461,6 +461,31 @@ __global__ void __launch_bounds__(128) convection_kernel(const __grid_constant__
   A.p[ip] = a.p;
 }
 
+// module_bound_cond (src/mptrac.c:3789-3881): parcels with dt != 0
+struct BoundArgs {
+  MetView met;
+  BoundView k;
+  const double *time, *lon, *lat, *p, *dt;
+  double *m, *vmr, *aoa, *cts[5];          // quantity rows or null
+  const double *cts_time[5], *cts_vmr[5];
+  int cts_n[5];
+  double mass, mass_trend, vmr0, vmr_trend;
+  long long np;
+};
+__global__ void __launch_bounds__(128) bound_cond_kernel(const __grid_constant__ BoundArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np || A.dt[ip] == 0) return;
+  Parcel a;
+  a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
+  if (!bound_applies(A.met, A.k, a)) return;
+  if (A.m && A.mass >= 0) A.m[ip] = A.mass + A.mass_trend * a.time;
+  if (A.vmr && A.vmr0 >= 0) A.vmr[ip] = A.vmr0 + A.vmr_trend * a.time;
+#pragma unroll
+  for (int k = 0; k < 5; k++)
+    if (A.cts[k]) A.cts[k][ip] = series_at(A.cts_time[k], A.cts_vmr[k], A.cts_n[k], a.time);
+  if (A.aoa) A.aoa[ip] = a.time;
+}
+
 // module_isosurf_init (init = 1) and module_isosurf (src/mptrac.c:4886-5004): every parcel, dt or not
 struct IsoArgs {
   MetView met;
@@ -699,6 +724,9 @@ struct mpb_ctx {
   size_t lev_cap = 0;
   bool lev_valid[2] = {false, false};
   unsigned short *lev_hint = nullptr;              // LevelArgs::hint
+  // module_bound_cond: the five trace-gas time series of clim_t (ccl4, ccl3f, ccl2f2, n2o, sf6)
+  double *cts_time[5] = {}, *cts_vmr[5] = {};
+  int cts_n[5] = {};
   // module_isosurf: cache_t::iso_var (attached to the array slot, like uvwp) and the balloon series of ISOSURF 4
   double *iso_var = nullptr, *iso_ts = nullptr, *iso_ps = nullptr;
   int iso_n = 0;
@@ -1069,6 +1097,39 @@ static void launch_isosurf(mpb_ctx *c, bool init) {
   c->launches++;
 }
 
+static bool bound_enabled(const mpb_ctl_t &k) { return k.bound_lat0 < k.bound_lat1 && k.bound_p0 > k.bound_p1; }   // src/mptrac.c:7926
+
+static void launch_bound_cond(mpb_ctx *c) {
+  const mpb_ctl_t &k = c->ctl;
+  if (c->np == 0) return;
+  // (the reference tests qnt_Cccl4 for truth, not for >= 0: src/mptrac.c:3802)
+  if (k.qnt_m < 0 && k.qnt_vmr < 0 && k.qnt_cts[0] && k.qnt_cts[1] < 0 && k.qnt_cts[2] < 0 && k.qnt_cts[3] < 0 && k.qnt_cts[4] < 0 &&
+      k.qnt_aoa < 0)
+    return;
+  auto row = [&](int iq) -> double * {
+    if (iq < 0) return nullptr;
+    REQUIRE(iq < c->nq, "boundary-condition quantity index out of range");
+    return c->q(iq);
+  };
+  BoundArgs A;
+  A.met = met_view(c);
+  A.k.lat0 = k.bound_lat0; A.k.lat1 = k.bound_lat1; A.k.p0 = k.bound_p0; A.k.p1 = k.bound_p1;
+  A.k.dps = k.bound_dps; A.k.dzs = k.bound_dzs; A.k.zetas = k.bound_zetas; A.k.pbl = k.bound_pbl;
+  A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p(); A.dt = c->dt;
+  A.m = row(k.qnt_m); A.vmr = row(k.qnt_vmr); A.aoa = row(k.qnt_aoa);
+  for (int i = 0; i < 5; i++) {
+    const bool on = k.qnt_cts[i] >= 0 && ((k.cts_on >> i) & 1);
+    REQUIRE(!on || c->cts_n[i] >= 1, "module_bound_cond needs the time series of a trace gas (mpb_set_clim_ts)");
+    A.cts[i] = on ? row(k.qnt_cts[i]) : nullptr;
+    A.cts_time[i] = c->cts_time[i]; A.cts_vmr[i] = c->cts_vmr[i]; A.cts_n[i] = c->cts_n[i];
+  }
+  A.mass = k.bound_mass; A.mass_trend = k.bound_mass_trend; A.vmr0 = k.bound_vmr; A.vmr_trend = k.bound_vmr_trend;
+  A.np = c->np;
+  bound_cond_kernel<<<nblocks(c->np, 128), 128, 0, c->stream>>>(A);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
 static void launch_decay(mpb_ctx *c) {
   const mpb_ctl_t &k = c->ctl;
   const bool decay = decay_enabled(k);
@@ -1193,6 +1254,8 @@ int mpb_destroy(mpb_ctx *c) {
                   c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_sum, c->mix_cnt,
                   c->grid_sum, c->grid_sq, c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz, c->lev_hint, c->iso_var, c->iso_ts, c->iso_ps};
   for (void *p : ptrs) if (p) cudaFree(p);
+  for (double *p : c->cts_time) if (p) cudaFree(p);
+  for (double *p : c->cts_vmr) if (p) cudaFree(p);
   for (float2 *p : c->x2) if (p) cudaFree(p);
   for (float2 *p : c->x3) if (p) cudaFree(p);
   if (c->stage_h) cudaFreeHost(c->stage_h);
@@ -1496,6 +1559,21 @@ int mpb_get_iso_var(mpb_ctx *c, double *iso_var) {
   API_END
 }
 
+int mpb_set_clim_ts(mpb_ctx *c, int species, int n, const double *time, const double *vmr) {
+  API_BEGIN
+  use(c);
+  REQUIRE(species >= 0 && species < 5 && n >= 1 && time && vmr, "bad time series");
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->cts_time[species]) { CK(cudaFree(c->cts_time[species])); CK(cudaFree(c->cts_vmr[species])); c->cts_time[species] = c->cts_vmr[species] = nullptr; }
+  CK(cudaMalloc(&c->cts_time[species], sizeof(double) * (size_t)n));
+  CK(cudaMalloc(&c->cts_vmr[species], sizeof(double) * (size_t)n));
+  CK(cudaMemcpyAsync(c->cts_time[species], time, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->cts_vmr[species], vmr, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->cts_n[species] = n;
+  API_END
+}
+
 int mpb_set_balloon(mpb_ctx *c, int n, const double *ts, const double *ps) {
   API_BEGIN
   use(c);
@@ -1579,7 +1657,8 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   // timesteps ... position1 in one launch: dt stays in registers (modules that run as their own launch read it from memory)
   const bool iso_now = (mask & MPB_MOD_ISOSURF) && isosurf_enabled(k);
   const bool pbl_now = (mask & MPB_MOD_DIFF_PBL) && k.diffusion && k.turb_pbl_scheme == 1;   // src/mptrac.c:7897-7899
-  const bool whole = (mask & 0xff) == 0xff && !on_levels && !pbl_now && !conv_now && !decay_now && !iso_now;
+  const bool bound0 = (mask & MPB_MOD_BOUND0) && bound_enabled(k), bound1 = (mask & MPB_MOD_BOUND1) && bound_enabled(k);
+  const bool whole = (mask & 0xff) == 0xff && !on_levels && !pbl_now && !conv_now && !decay_now && !iso_now && !bound0 && !bound1;
   if ((mask & MPB_MOD_TIMESTEPS) && t == k.t_start) {   // src/mptrac.c:7863-7873
     if (iso_now) launch_isosurf(c, true);
     launch_advect_init(c);
@@ -1620,6 +1699,7 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   flush();
   if ((mask & MPB_MOD_METEO) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out)))   // src/mptrac.c:7927-7929
     launch_meteo(c);
+  if (bound0) launch_bound_cond(c);   // src/mptrac.c:7926-7929
   if (decay_now) launch_decay(c);   // src/mptrac.c:7931-7940
   if ((mask & MPB_MOD_MIXING) && k.mixing_trop >= 0 && k.mixing_strat >= 0 &&
       (k.mixing_dt <= 0 || hits(t, k.mixing_dt))) {  // src/mptrac.c:7943-7945
@@ -1627,6 +1707,7 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
     for (int i = 0; i < k.n_mix_qnt; i++)
       if (k.mix_qnt[i] >= 0) { mixing_accumulate(c, k.mix_qnt[i]); mixing_apply(c, k.mix_qnt[i]); }
   }
+  if (bound1) launch_bound_cond(c);   // src/mptrac.c:7997-8000
 }
 
 int mpb_run_timestep(mpb_ctx *c, double t) {
@@ -1651,7 +1732,7 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
   const bool mix_now = k.mixing_trop >= 0 && k.mixing_strat >= 0 && (k.mixing_dt <= 0 || hits(t, k.mixing_dt)) && k.n_mix_qnt > 0;
   const bool meteo_now = meteo_wanted(k) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out));
   if (sort_now || mix_now || meteo_now || k.advect_vert_coord != 0 || convection_enabled(k) || decay_enabled(k) || k.qnt_loss_rate >= 0 || isosurf_enabled(k) ||
-      (k.diffusion && k.turb_pbl_scheme == 1) ||
+      (k.diffusion && k.turb_pbl_scheme == 1) || bound_enabled(k) ||
       np < 4 * kHostChunkMin) {
     // steps with a global phase (cell sort, box means), steps that write quantities (meteo) and tiny problems take the
     // plain sequence

@@ -1536,6 +1536,40 @@ MPB_HD double isosurf_pressure(const MetView &g, int mode, double var, const Par
   return ps[i] + (ps[i + 1] - ps[i]) / (ts[i + 1] - ts[i]) * (a.time - ts[i]);   // LIN, src/mptrac.h:1351
 }
 
+// module_bound_cond (3789-3881): is the parcel inside the latitude / pressure window and -- where asked -- inside the
+// surface layer (pressure depth, height, zeta, PBL)?  The quantities are then reset by the caller.
+struct BoundView {
+  double lat0, lat1, p0, p1, dps, dzs, zetas;   // ctl->bound_*
+  int pbl;
+};
+MPB_HD bool bound_applies(const MetView &g, const BoundView &k, const Parcel &a) {
+  if (a.lat < k.lat0 || a.lat > k.lat1 || a.p > k.p0 || a.p < k.p1) return false;
+  if (k.dps > 0 || k.dzs > 0 || k.zetas > 0 || k.pbl) {
+    CellAxes ax;
+    axes_reset(ax);
+    double ps, pbl;
+    surface_at(g, a.time, a.lon, a.lat, ax, ps, pbl);
+    if (k.dps > 0 && a.p < ps - k.dps) return false;
+    if (k.dzs > 0 && altitude(a.p) > altitude(ps) + k.dzs) return false;
+    if (k.zetas > 0) {
+      CubeT<true> c;
+      cube_reset(c);
+      const double t = temperature_at(g, a.time, a.lon, a.lat, a.p, c);
+      if (zeta_diagnosed(ps, a.p, t) > k.zetas) return false;
+    }
+    if (k.pbl && a.p < pbl) return false;
+  }
+  return true;
+}
+// clim_ts (396-410)
+MPB_HD double series_at(const double *tm, const double *v, int n, double t) {
+  if (t <= tm[0]) return v[0];
+  if (t >= tm[n - 1]) return v[n - 1];
+  const int mid = (n - 1) >> 1;
+  const int i = find_interval(tm, n, tm[mid] < tm[mid + 1], t);
+  return v[i] + (v[i + 1] - v[i]) / (tm[i + 1] - tm[i]) * (t - tm[i]);   // LIN
+}
+
 // module_decay (4227-4263): the e-folding time blends the tropospheric and the stratospheric one with tropo_weight
 // (12748-12770); returns exp(-dt / tdec)
 MPB_HD double decay_factor(const ClimView &cl, int coord_type, double utm_ref_lat, double tdec_trop, double tdec_strat,

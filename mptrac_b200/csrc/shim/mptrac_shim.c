@@ -99,6 +99,10 @@ static void put_ctl(const ctl_t *c) {
   k.tdec_trop = k.tdec_strat = 0;
   k.qnt_m = k.qnt_vmr = k.qnt_mloss_decay = k.qnt_loss_rate = -1;
   k.isosurf = 0;    /* module_isosurf likewise (iso_cpu below) */
+  k.bound_lat0 = k.bound_lat1 = k.bound_p0 = k.bound_p1 = -999;   /* module_bound_cond likewise (bound_cpu below) */
+  k.bound_mass = k.bound_vmr = k.bound_dps = k.bound_dzs = k.bound_zetas = -999;
+  k.qnt_aoa = -1; k.cts_on = 0;
+  for (int i = 0; i < 5; i++) k.qnt_cts[i] = -1;
   g_levels = c->advect_vert_coord != 0;
   g_fields = device_meteo_fields();
   memset(g_need2, 0, sizeof(g_need2)); memset(g_need3, 0, sizeof(g_need3));

@@ -31,8 +31,8 @@ MET_X2 = ("ts", "zs", "us", "vs", "ess", "nss", "shf", "lsm", "sst", "pt", "tt",
 MET_X3 = ("z", "pv", "h2o", "o3", "lwc", "rwc", "iwc", "swc", "cc")   # [nx][ny][np]; "z" is the geopotential height that quantity zg reports
 # module bits of mpb_run_modules (include/mptrac_b200.h MPB_MOD_*)
 (MOD_TIMESTEPS, MOD_SORT, MOD_POSITION0, MOD_ADVECT, MOD_DIFF_TURB, MOD_DIFF_MESO, MOD_SEDI, MOD_POSITION1, MOD_MIXING,
- MOD_METEO, MOD_CONVECTION, MOD_DECAY, MOD_ISOSURF, MOD_DIFF_PBL) = (1 << i for i in range(14))
-MOD_ALL = 0x3fff
+ MOD_METEO, MOD_CONVECTION, MOD_DECAY, MOD_ISOSURF, MOD_DIFF_PBL, MOD_BOUND0, MOD_BOUND1) = (1 << i for i in range(16))
+MOD_ALL = 0xffff
 _LIBDIR = Path(__file__).resolve().parent / "_lib"
 
 
@@ -56,6 +56,9 @@ class _CtlStruct(C.Structure):
         + [("qnt_meteo", C.c_int32 * METEO_SLOTS), ("qnt_zeta", C.c_int32), ("qnt_eta", C.c_int32)]
         + [(n, C.c_double) for n in ("conv_cape", "conv_cin", "conv_pbl_trans", "conv_dt", "tdec_trop", "tdec_strat")]
         + [(n, C.c_int32) for n in ("conv_mix_pbl", "qnt_m", "qnt_vmr", "qnt_mloss_decay", "qnt_loss_rate", "isosurf")]
+        + [(n, C.c_double) for n in ("bound_mass", "bound_mass_trend", "bound_vmr", "bound_vmr_trend", "bound_lat0", "bound_lat1",
+                                     "bound_p0", "bound_p1", "bound_dps", "bound_dzs", "bound_zetas")]
+        + [("bound_pbl", C.c_int32), ("qnt_aoa", C.c_int32), ("qnt_cts", C.c_int32 * 5), ("cts_on", C.c_int32)]
     )
 
 
@@ -138,12 +141,27 @@ class Ctl:
     qnt_mloss_decay: int = -1
     qnt_loss_rate: int = -1
     isosurf: int = 0                   # module_isosurf: 1 pressure, 2 density, 3 potential temperature, 4 balloon series
+    bound_mass: float = -999.0         # module_bound_cond: on when bound_lat0 < bound_lat1 and bound_p0 > bound_p1
+    bound_mass_trend: float = 0.0
+    bound_vmr: float = -999.0
+    bound_vmr_trend: float = 0.0
+    bound_lat0: float = -999.0
+    bound_lat1: float = -999.0
+    bound_p0: float = -999.0
+    bound_p1: float = -999.0
+    bound_dps: float = -999.0
+    bound_dzs: float = -999.0
+    bound_zetas: float = -999.0
+    bound_pbl: int = 0
+    qnt_aoa: int = -1
+    qnt_cts: Sequence[int] = (-1, -1, -1, -1, -1)   # Cccl4, Cccl3f, Cccl2f2, Cn2o, Csf6
+    cts_on: int = 0                    # bit i: species i has a time series (Engine.set_clim_ts)
     qnt_meteo: Dict[str, int] = field(default_factory=dict)   # quantity name (METEO_QNT) -> index, e.g. {"t": 0, "u": 1}
 
     def to_struct(self) -> _CtlStruct:
         s = _CtlStruct()
         for name, _ in _CtlStruct._fields_:
-            if name in ("mix_qnt", "_pad", "n_mix_qnt", "qnt_meteo"):
+            if name in ("mix_qnt", "_pad", "n_mix_qnt", "qnt_meteo", "qnt_cts"):
                 continue
             setattr(s, name, getattr(self, name))
         unknown = set(self.qnt_meteo) - set(METEO_QNT)
@@ -151,6 +169,8 @@ class Ctl:
             raise ValueError(f"module_meteo quantities not available on the device: {sorted(unknown)}")
         for i in range(METEO_SLOTS):
             s.qnt_meteo[i] = int(self.qnt_meteo.get(METEO_QNT[i], -1)) if i < len(METEO_QNT) else -1
+        for i in range(5):
+            s.qnt_cts[i] = int(self.qnt_cts[i])
         mq = list(self.mix_qnt)
         if len(mq) > MIX_MAXQ:
             raise ValueError("too many mixing quantities")
@@ -277,6 +297,7 @@ def load_library(strict: bool = False) -> C.CDLL:
         "mpb_set_iso_var": (i32, [vp, vp]),
         "mpb_get_iso_var": (i32, [vp, vp]),
         "mpb_set_balloon": (i32, [vp, i32, vp, vp]),
+        "mpb_set_clim_ts": (i32, [vp, i32, i32, vp, vp]),
         "mpb_get_dt": (i32, [vp, vp]),
         "mpb_get_np": (i64, [vp]),
         "mpb_set_shard": (i32, [vp, i64, i64]),
@@ -444,6 +465,13 @@ class Engine:
         if ts.size != ps.size or ts.size < 1:
             raise ValueError("balloon series: ts and ps must have the same length >= 1")
         self._ck(self._lib.mpb_set_balloon(self._h, int(ts.size), _ptr(ts), _ptr(ps)))
+
+    def set_clim_ts(self, species: int, time, vmr):
+        """trace-gas time series of module_bound_cond; species 0 .. 4 = Cccl4, Cccl3f, Cccl2f2, Cn2o, Csf6"""
+        time, vmr = np.ascontiguousarray(time, np.float64), np.ascontiguousarray(vmr, np.float64)
+        if time.size != vmr.size or time.size < 1:
+            raise ValueError("time series: time and vmr must have the same length >= 1")
+        self._ck(self._lib.mpb_set_clim_ts(self._h, int(species), int(time.size), _ptr(time), _ptr(vmr)))
 
     def get_dt(self) -> np.ndarray:
         a = np.empty(self.np, np.float64)

@@ -1023,6 +1023,53 @@ void orc_module_isosurf(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_m
   }
 }
 
+/* module_bound_cond, 3789-3881 (clim_ts 396-410): parcels with dt != 0 inside the latitude / pressure window and, where asked,
+ * inside the surface layer get their mass, volume mixing ratio, trace-gas and age-of-air quantities reset */
+static const orc_cts_t *g_cts;
+void orc_set_cts(const orc_cts_t *cts) { g_cts = cts; }
+
+static double series_at(const orc_cts_t *cts, int k, double t) {
+  const double *tm = cts->time[k], *v = cts->vmr[k];
+  const int n = cts->n[k];
+  if (t <= tm[0]) return v[0];
+  if (t >= tm[n - 1]) return v[n - 1];
+  const int i = bisect(tm, n, t);
+  return linear(tm[i], v[i], tm[i + 1], v[i + 1], t);
+}
+
+void orc_module_bound_cond(const orc_ctl_t *ctl, const orc_cts_t *cts, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm) {
+  /* (the reference tests qnt_Cccl4 for truth, not for >= 0: src/mptrac.c:3802) */
+  if (ctl->qnt_m < 0 && ctl->qnt_vmr < 0 && ctl->qnt_cts[0] && ctl->qnt_cts[1] < 0 && ctl->qnt_cts[2] < 0 && ctl->qnt_cts[3] < 0 &&
+      ctl->qnt_cts[4] < 0 && ctl->qnt_aoa < 0)
+    return;
+  const size_t st = (size_t)atm->q_stride;
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    if (atm->dt[ip] == 0) continue;
+    const double tm = atm->time[ip], lon = atm->lon[ip], lat = atm->lat[ip], p = atm->p[ip];
+    if (lat < ctl->bound_lat0 || lat > ctl->bound_lat1 || p > ctl->bound_p0 || p < ctl->bound_p1) continue;
+    if (ctl->bound_dps > 0 || ctl->bound_dzs > 0 || ctl->bound_zetas > 0 || ctl->bound_pbl) {
+      cell_t c = CELL_ZERO;
+      const double ps = time2(met0, met0->ps, met1, met1->ps, tm, lon, lat, &c, 1);
+      if (ctl->bound_dps > 0 && p < ps - ctl->bound_dps) continue;
+      if (ctl->bound_dzs > 0 && C_H0 * log(C_P0 / p) > C_H0 * log(C_P0 / ps) + ctl->bound_dzs) continue;
+      if (ctl->bound_zetas > 0) {
+        const double t = time3(met0, met0->t, met1, met1->t, tm, p, lon, lat, &c, 1);
+        if ((p / ps <= 0.3 ? 1. : sin(M_PI / 2. * (1. - p / ps) / (1. - 0.3))) * theta_of(p, t) > ctl->bound_zetas) continue;
+      }
+      if (ctl->bound_pbl) {
+        const double pbl = time2(met0, met0->pbl, met1, met1->pbl, tm, lon, lat, &c, 0);
+        if (p < pbl) continue;
+      }
+    }
+    if (ctl->qnt_m >= 0 && ctl->bound_mass >= 0) atm->q[(size_t)ctl->qnt_m * st + ip] = ctl->bound_mass + ctl->bound_mass_trend * tm;
+    if (ctl->qnt_vmr >= 0 && ctl->bound_vmr >= 0) atm->q[(size_t)ctl->qnt_vmr * st + ip] = ctl->bound_vmr + ctl->bound_vmr_trend * tm;
+    for (int k = 0; k < ORC_NCTS; k++)
+      if (ctl->qnt_cts[k] >= 0 && (ctl->cts_on >> k & 1)) atm->q[(size_t)ctl->qnt_cts[k] * st + ip] = series_at(cts, k, tm);
+    if (ctl->qnt_aoa >= 0) atm->q[(size_t)ctl->qnt_aoa * st + ip] = tm;
+  }
+}
+
 /* module_decay, 4227-4263 (and the reset of the total loss rate that precedes it, 7931-7936) */
 void orc_module_decay(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm) {
   const size_t st = (size_t)atm->q_stride;
@@ -1067,10 +1114,13 @@ void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_me
     for (int i = 0; i < ORC_METEO_SLOTS; i++) any |= ctl->qnt_meteo[i] >= 0;
     if (any) orc_module_meteo(ctl, met0, met1, atm);
   }
+  const int bound = ctl->bound_lat0 < ctl->bound_lat1 && ctl->bound_p0 > ctl->bound_p1;
+  if (bound) orc_module_bound_cond(ctl, g_cts, met0, met1, atm);   /* 7926-7929 */
   if (ctl->qnt_loss_rate >= 0)   /* 7931-7936 */
     for (int64_t ip = 0; ip < atm->np; ip++)
       if (atm->dt[ip] != 0) atm->q[(size_t)ctl->qnt_loss_rate * (size_t)atm->q_stride + ip] = 0;
   if (ctl->tdec_trop > 0 && ctl->tdec_strat > 0) orc_module_decay(ctl, clim, atm);   /* 7938-7940 */
   if (ctl->mixing_trop >= 0 && ctl->mixing_strat >= 0 && (ctl->mixing_dt <= 0 || fmod(t, ctl->mixing_dt) == 0))
     orc_module_mixing(ctl, clim, atm, t);
+  if (bound) orc_module_bound_cond(ctl, g_cts, met0, met1, atm);    /* 7997-8000 */
 }

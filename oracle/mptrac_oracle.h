@@ -52,7 +52,19 @@ typedef struct {
   int32_t conv_mix_pbl;
   int32_t qnt_m, qnt_vmr, qnt_mloss_decay, qnt_loss_rate;
   int32_t isosurf;                      /* ctl->isosurf: 0 off, 1 pressure, 2 density, 3 potential temperature, 4 balloon */
+  /* module_bound_cond (src/mptrac.c:3789-3881) */
+  double bound_mass, bound_mass_trend, bound_vmr, bound_vmr_trend;
+  double bound_lat0, bound_lat1, bound_p0, bound_p1, bound_dps, bound_dzs, bound_zetas;
+  int32_t bound_pbl, qnt_aoa;
+  int32_t qnt_cts[5];                   /* qnt_Cccl4, qnt_Cccl3f, qnt_Cccl2f2, qnt_Cn2o, qnt_Csf6 */
+  int32_t cts_on;                       /* bit i: the control file names a time series for species i (not "-") */
 } orc_ctl_t;
+
+#define ORC_NCTS 5
+typedef struct {                        /* clim_ts_t of the five species above (src/mptrac.h:3733-3744) */
+  int32_t n[ORC_NCTS], _pad;
+  const double *time[ORC_NCTS], *vmr[ORC_NCTS];
+} orc_cts_t;
 
 /* one met time level, dense: 3-D [nx][ny][np] (z fastest), 2-D [nx][ny] */
 typedef struct {
@@ -104,6 +116,8 @@ void orc_module_meteo(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met
 void orc_module_diff_pbl(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm, uint64_t *ctr);
 void orc_module_convection(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm, uint64_t *ctr);
 void orc_module_decay(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm);
+void orc_module_bound_cond(const orc_ctl_t *ctl, const orc_cts_t *cts, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
+void orc_set_cts(const orc_cts_t *cts);   /* the series orc_run_timestep's boundary conditions use (NULL = none) */
 void orc_module_isosurf_init(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
 void orc_module_isosurf(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
 void orc_module_mixing(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm, double t);

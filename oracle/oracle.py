@@ -31,6 +31,29 @@ _TAIL_DBL = ("conv_cape", "conv_cin", "conv_pbl_trans", "conv_dt", "tdec_trop", 
 _TAIL_INT = ("conv_mix_pbl", "qnt_m", "qnt_vmr", "qnt_mloss_decay", "qnt_loss_rate", "isosurf")
 _TAIL_DEFAULT = dict(conv_cape=-999.0, conv_cin=-999.0, conv_pbl_trans=0.0, conv_dt=-999.0, tdec_trop=0.0, tdec_strat=0.0,
                      conv_mix_pbl=0, qnt_m=-1, qnt_vmr=-1, qnt_mloss_decay=-1, qnt_loss_rate=-1, isosurf=0)
+# module_bound_cond block
+_BOUND_DBL = ("bound_mass", "bound_mass_trend", "bound_vmr", "bound_vmr_trend", "bound_lat0", "bound_lat1", "bound_p0", "bound_p1",
+              "bound_dps", "bound_dzs", "bound_zetas")
+_BOUND_DEFAULT = dict(bound_mass=-999.0, bound_mass_trend=0.0, bound_vmr=-999.0, bound_vmr_trend=0.0, bound_lat0=-999.0, bound_lat1=-999.0,
+                      bound_p0=-999.0, bound_p1=-999.0, bound_dps=-999.0, bound_dzs=-999.0, bound_zetas=-999.0)
+CTS_SPECIES = ("Cccl4", "Cccl3f", "Cccl2f2", "Cn2o", "Csf6")
+
+
+class OrcCts(C.Structure):
+    _fields_ = [("n", C.c_int32 * 5), ("_pad", C.c_int32), ("time", C.c_void_p * 5), ("vmr", C.c_void_p * 5)]
+
+
+def cts_struct(series):
+    """series: dict species -> (time, vmr); returns (OrcCts, keep-alive list)"""
+    s, keep = OrcCts(), []
+    for k, name in enumerate(CTS_SPECIES):
+        if series and name in series:
+            t, v = (np.ascontiguousarray(x, np.float64) for x in series[name])
+            keep += [t, v]
+            s.n[k], s.time[k], s.vmr[k] = t.size, t.ctypes.data, v.ctypes.data
+    return s, keep
+
+
 # slots of orc_ctl_t::qnt_meteo (mptrac_oracle.h): 14 from the path's own fields, the 22 2-D and 9 3-D further fields of
 # INTPOL_TIME_ALL, 8 derived from t and h2o
 METEO_QNT = ("ps", "pbl", "p", "t", "rho", "u", "v", "w", "vh", "vz", "theta", "psat", "psice", "zeta_d",
@@ -47,7 +70,9 @@ class OrcCtl(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in _INT_FIELDS] + [("mix_qnt", C.c_int32 * MIX_MAXQ), ("_pad", C.c_int32)]
                 + [(n, C.c_double) for n in _DBL_FIELDS] + [("qnt_meteo", C.c_int32 * METEO_SLOTS)]
                 + [("qnt_zeta", C.c_int32), ("qnt_eta", C.c_int32)]
-                + [(n, C.c_double) for n in _TAIL_DBL] + [(n, C.c_int32) for n in _TAIL_INT])
+                + [(n, C.c_double) for n in _TAIL_DBL] + [(n, C.c_int32) for n in _TAIL_INT]
+                + [(n, C.c_double) for n in _BOUND_DBL] + [("bound_pbl", C.c_int32), ("qnt_aoa", C.c_int32),
+                                                          ("qnt_cts", C.c_int32 * 5), ("cts_on", C.c_int32)])
 
 
 _LEVEL_FIELDS = ("pl", "ul", "vl", "wl", "zetal", "zeta_dotl")   # model-level fields, [nx][ny][npl]
@@ -99,6 +124,22 @@ def ctl_struct(ctl) -> OrcCtl:
         except (KeyError, AttributeError):
             v = _TAIL_DEFAULT[n]
         setattr(s, n, float(v) if n in _TAIL_DBL else int(v))
+    for n in _BOUND_DBL:
+        try:
+            setattr(s, n, float(get(n)))
+        except (KeyError, AttributeError):
+            setattr(s, n, _BOUND_DEFAULT[n])
+    for n, d in (("bound_pbl", 0), ("qnt_aoa", -1), ("cts_on", 0)):
+        try:
+            setattr(s, n, int(get(n)))
+        except (KeyError, AttributeError):
+            setattr(s, n, d)
+    try:
+        qc = list(get("qnt_cts"))
+    except (KeyError, AttributeError):
+        qc = [-1] * 5
+    for k in range(5):
+        s.qnt_cts[k] = int(qc[k])
     return s
 
 
@@ -189,6 +230,8 @@ class Oracle:
         L.orc_clim_tropo.restype = C.c_double
         L.orc_clim_tropo.argtypes = [P(OrcClim), C.c_double, C.c_double]
         L.orc_module_rng.argtypes = [C.c_void_p, C.c_int64, C.c_int, P(C.c_uint64)]
+        self._cts = cts_struct(None)
+        L.orc_set_cts(C.byref(self._cts[0]))
         L.orc_run_timestep.argtypes = [P(OrcCtl), P(OrcClim), P(OrcMet), P(OrcMet), P(OrcAtm), C.c_double, P(C.c_uint64)]
         L.orc_module_timesteps.argtypes = [P(OrcCtl), P(OrcMet), P(OrcAtm), C.c_double]
         L.orc_module_position.argtypes = [P(OrcMet), P(OrcMet), P(OrcAtm)]
@@ -232,6 +275,11 @@ class Oracle:
                                       getattr(met1, field).ctypes.data, ts, p, lon, lat, C.byref(out))
         return out.value
 
+    def set_cts(self, series):
+        """trace-gas time series of module_bound_cond: dict species (CTS_SPECIES) -> (time, vmr)"""
+        self._cts = cts_struct(series)
+        self.L.orc_set_cts(C.byref(self._cts[0]))
+
     def run(self, what, ctl, clim, met0, met1, atm: Parcels, t=0.0, nsteps=1):
         """what: 'timestep' | 'timesteps' | 'position' | 'advect' | 'diff_turb' | 'diff_meso' | 'sedi' | 'sort' | 'mixing'."""
         c = ctl_struct(ctl)
@@ -268,6 +316,8 @@ class Oracle:
             L.orc_module_convection(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a), C.byref(ctr))
         elif what == "decay":
             L.orc_module_decay(C.byref(c), C.byref(cl), C.byref(a))
+        elif what == "bound_cond":
+            L.orc_module_bound_cond(C.byref(c), C.byref(self._cts[0]), C.byref(m0), C.byref(m1), C.byref(a))
         elif what == "diff_pbl":
             L.orc_module_diff_pbl(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a), C.byref(ctr))
         elif what == "isosurf_init":
@@ -299,7 +349,7 @@ class Oracle:
 
 
 _WHAT = {"timestep": 0, "timesteps": 1, "position": 2, "advect": 3, "diff_turb": 4, "diff_meso": 5, "sedi": 6,
-         "sort": 7, "mixing": 8, "meteo": 9, "advect_init": 10, "convection": 11, "decay": 12, "isosurf_init": 13, "isosurf": 14, "diff_pbl": 15}
+         "sort": 7, "mixing": 8, "meteo": 9, "advect_init": 10, "convection": 11, "decay": 12, "isosurf_init": 13, "isosurf": 14, "diff_pbl": 15, "bound_cond": 16}
 
 
 def reference_available() -> bool:
@@ -332,12 +382,18 @@ class Reference:
         return dict(zip(("EX", "EY", "EP", "NP", "NQ"), (x.value for x in v)))
 
     def read_ctl(self, qnt_names=(), overrides=""):
-        out = (C.c_int * 74)()
+        out = (C.c_int * 80)()
         nq = self.L.ref_read_ctl(",".join(qnt_names).encode(), overrides.encode(), out)
         self.qnt = dict(zip(("rp", "rhop", "m", "vmr", "ens"), list(out)[:5]))
         self.qnt["zeta"], self.qnt["eta"], self.qnt["mloss_decay"], self.qnt["loss_rate"] = out[70], out[71], out[72], out[73]
+        self.qnt["aoa"] = out[74]
+        self.qnt["cts"] = [out[75 + k] for k in range(5)]
         self.qnt_meteo = {n: i for n, i in zip(METEO_QNT, list(out)[5:5 + len(METEO_QNT)]) if i >= 0}   # name -> index the reference assigned
         return nq
+
+    def set_cts(self, series):
+        s, keep = cts_struct(series)
+        self.L.ref_set_cts(C.byref(s))
 
     def clim_tropo(self):
         nt, nl = C.c_int(), C.c_int()

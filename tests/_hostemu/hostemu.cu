@@ -295,3 +295,16 @@ extern "C" int emu_diff_pbl(const EmuMet *m0, const EmuMet *m1, unsigned long lo
   }
   return 0;
 }
+
+extern "C" int emu_bound_applies(const EmuMet *m0, const EmuMet *m1, const double *k7, int pbl, long long np, const double *time,
+                                 const double *lon, const double *lat, const double *p, int *hit) {
+  HostMet h;
+  make_view(h, m0, m1, true);
+  const BoundView k = {k7[0], k7[1], k7[2], k7[3], k7[4], k7[5], k7[6], pbl};
+  for (long long ip = 0; ip < np; ip++) {
+    Parcel a = {time[ip], lon[ip], lat[ip], p[ip]};
+    hit[ip] = bound_applies(h.g, k, a) ? 1 : 0;
+  }
+  return 0;
+}
+extern "C" double emu_series_at(const double *tm, const double *v, int n, double t) { return series_at(tm, v, n, t); }

@@ -201,3 +201,41 @@ def test_diff_pbl_in_the_step_vs_oracle(oracle):
     bad = np.abs(out["p"] - ref.p) > 1e-6 * ref.p
     assert bad.mean() < 2e-3, bad.mean()
     assert np.mean(np.abs(uv - ref.uvwp) > 1e-4 * (1 + np.abs(ref.uvwp))) < 2e-3
+
+
+@pytest.mark.parametrize("layer", ["none", "dps", "dzs_pbl", "zetas"])
+def test_bound_cond_in_the_step_vs_oracle(oracle, layer):
+    """module_bound_cond after module_meteo and again at the end of the step, with mass, volume mixing ratio, two trace-gas
+    time series (mpb_set_clim_ts) and age of air"""
+    from mptrac_b200 import Ctl, Engine, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(36, 19, 20, t0=0.0, dt_met=21600.0)
+    n = 4000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.0, zmax=12.0, seed=31)
+    clim = synth.make_clim_tropo()
+    series = {"Cccl3f": (np.array([-1e4, 500.0, 2000.0, 1e5]), np.array([2e-10, 2.2e-10, 2.1e-10, 1.9e-10])),
+              "Csf6": (np.array([0.0, 1000.0]), np.array([1e-11, 1.2e-11]))}
+    oracle.set_cts(series)
+    kw = dict(none={}, dps=dict(bound_dps=150.0), dzs_pbl=dict(bound_dzs=1.5, bound_pbl=1), zetas=dict(bound_zetas=320.0))[layer]
+    ctl = Ctl(nq=5, advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, qnt_m=0, qnt_vmr=1, qnt_aoa=2,
+              qnt_cts=(-1, 3, -1, -1, 4), cts_on=0b10010, bound_mass=3.0, bound_mass_trend=1e-3, bound_vmr=1e-9, bound_lat0=-60.0,
+              bound_lat1=70.0, bound_p0=1e10, bound_p1=300.0, **kw)
+    q = np.random.default_rng(1).uniform(0.5, 2.0, (5, n))
+    with Engine(n, nq=5, device=0) as eng:
+        eng.set_ctl(ctl)
+        eng.set_clim_tropo(*clim)
+        eng.set_met(0, m0)
+        eng.set_met(1, m1)
+        eng.set_clim_ts(1, *series["Cccl3f"])
+        eng.set_clim_ts(4, *series["Csf6"])
+        eng.set_atm(tm, p, lon, lat, q)
+        for s in range(4):
+            eng.run_timestep(300.0 * s)
+        out = eng.get_atm()
+    ref = Parcels(tm, p, lon, lat, q)
+    oracle.run("timestep", ctl, clim, m0, m1, ref, t=0.0, nsteps=4)
+    assert abserr(out["lat"], ref.lat) < 1e-11
+    # a parcel on the edge of the window or of the surface layer may fall on the other side
+    bad = np.any(np.abs(out["q"] - ref.q) > 1e-12 * np.abs(ref.q), axis=0)
+    assert bad.mean() < 2e-3, bad.mean()
+    assert 0.05 < np.mean(ref.q[2] == ref.time) < 0.95

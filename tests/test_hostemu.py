@@ -259,3 +259,33 @@ def test_module_diff_pbl_on_host_is_bit_exact(emu, oracle):
     for k in ("lon", "lat", "p", "uvwp"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
     assert 0.1 < np.mean(b.p != p) < 0.95
+
+
+@pytest.mark.parametrize("layer", ["none", "dps", "dzs_pbl", "zetas"])
+def test_module_bound_cond_on_host_is_bit_exact(emu, oracle, layer):
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels, met_struct
+    m0, m1 = synth.make_met_pair(36, 19, 20, t0=0.0, dt_met=21600.0)
+    n = 4000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.0, zmax=12.0, seed=31)
+    clim = synth.make_clim_tropo()
+    series = {"Cccl3f": (np.array([-1e4, 500.0, 2000.0, 1e5]), np.array([2e-10, 2.2e-10, 2.1e-10, 1.9e-10]))}
+    oracle.set_cts(series)
+    kw = dict(none={}, dps=dict(bound_dps=150.0), dzs_pbl=dict(bound_dzs=1.5, bound_pbl=1), zetas=dict(bound_zetas=320.0))[layer]
+    ctl = Ctl(nq=2, advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, qnt_aoa=0, qnt_cts=(-1, 1, -1, -1, -1), cts_on=2,
+              bound_lat0=-60.0, bound_lat1=70.0, bound_p0=1e10, bound_p1=300.0, **kw)
+    a = Parcels(tm + np.linspace(0.0, 3000.0, n), p, lon, lat, np.full((2, n), -1.0))
+    a.dt[:] = 300.0
+    oracle.run("bound_cond", ctl, clim, m0, m1, a, t=300.0)
+    s0, s1 = met_struct(m0), met_struct(m1)
+    k7 = np.array([ctl.bound_lat0, ctl.bound_lat1, ctl.bound_p0, ctl.bound_p1, ctl.bound_dps, ctl.bound_dzs, ctl.bound_zetas])
+    hit = np.zeros(n, np.int32)
+    vp = lambda x: C.c_void_p(x.ctypes.data)  # noqa: E731
+    assert emu.emu_bound_applies(C.byref(s0), C.byref(s1), vp(k7), ctl.bound_pbl, C.c_longlong(n), vp(a.time), vp(a.lon), vp(a.lat),
+                                 vp(a.p), vp(hit)) == 0
+    assert np.array_equal(hit == 1, a.q[0] == a.time) and 0.05 < hit.mean() < 0.95
+    emu.emu_series_at.restype = C.c_double
+    emu.emu_series_at.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+    ts, v = series["Cccl3f"]
+    got = np.array([emu.emu_series_at(ts.ctypes.data, v.ctypes.data, ts.size, float(t)) for t in a.time[hit == 1]])
+    assert np.array_equal(got, a.q[1][hit == 1])

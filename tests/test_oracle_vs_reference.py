@@ -386,3 +386,40 @@ def test_module_diff_pbl_bit_exact(oracle, reference):
     reference.run("timestep", ctl, a, t=0.0, nsteps=6)
     oracle.run("timestep", ctl, clim, m0, m1, b, t=0.0, nsteps=6)
     assert reference.ctr == oracle.ctr and _same(a, b)
+
+
+@pytest.mark.parametrize("layer", ["none", "dps", "dzs_pbl", "zetas"])
+def test_module_bound_cond_bit_exact(oracle, reference, layer):
+    """module_bound_cond (src/mptrac.c:3789-3881) with mass, volume mixing ratio, two trace-gas time series and age of air,
+    the latitude / pressure window and the four surface-layer tests; alone and inside the dispatcher (twice per step)"""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(36, 19, 20, t0=0.0, dt_met=21600.0)
+    n = 4000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.0, zmax=12.0, seed=31)
+    nq = reference.read_ctl(["m", "vmr", "aoa", "Cccl3f", "Csf6"])
+    qi = reference.qnt
+    reference.set_met(m0, m1)
+    clim = reference.clim_tropo()
+    series = {"Cccl3f": (np.array([-1e4, 500.0, 2000.0, 1e5]), np.array([2e-10, 2.2e-10, 2.1e-10, 1.9e-10])),
+              "Csf6": (np.array([0.0, 1000.0]), np.array([1e-11, 1.2e-11]))}
+    reference.set_cts(series)
+    oracle.set_cts(series)
+    kw = dict(none={}, dps=dict(bound_dps=150.0), dzs_pbl=dict(bound_dzs=1.5, bound_pbl=1), zetas=dict(bound_zetas=320.0))[layer]
+    ctl = Ctl(nq=nq, advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, qnt_m=qi["m"], qnt_vmr=qi["vmr"],
+              qnt_aoa=qi["aoa"], qnt_cts=qi["cts"], cts_on=0b10010, bound_mass=3.0, bound_mass_trend=1e-3, bound_vmr=1e-9,
+              bound_lat0=-60.0, bound_lat1=70.0, bound_p0=1e10, bound_p1=300.0, **kw)
+    q = np.random.default_rng(1).uniform(0.5, 2.0, (nq, n))
+    a = Parcels(tm, p, lon, lat, q)
+    reference.run("timesteps", ctl, a, t=300.0)
+    b = a.copy()
+    reference.run("bound_cond", ctl, a, t=300.0)
+    oracle.run("bound_cond", ctl, clim, m0, m1, b, t=300.0)
+    assert _same(a, b)
+    hit = a.q[qi["aoa"]] == a.time
+    assert 0.05 < hit.mean() < 0.95, hit.mean()
+    a = Parcels(tm, p, lon, lat, q)
+    b = a.copy()
+    reference.run("timestep", ctl, a, t=0.0, nsteps=4)
+    oracle.run("timestep", ctl, clim, m0, m1, b, t=0.0, nsteps=4)
+    assert _same(a, b)
