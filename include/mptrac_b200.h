@@ -213,6 +213,10 @@ int mpb_run_timestep_host(mpb_ctx *ctx, double t, int64_t np, double *time, doub
 #define MPB_MOD_BOUND1    0x8000  /* ... and again at the end of the step (7997-8000) */
 #define MPB_MOD_ALL       0xffff
 int mpb_run_modules(mpb_ctx *ctx, double t, unsigned mask);
+/* The launches mpb_run_modules(ctx, t, mask) would make for this control structure, as text ("step(advect=4,phys=0x0,mod=0x43)
+ * meteo ..."): pure host logic, needs neither a context nor a device.  mod bits: 0x01 timesteps, 0x02 position (initial),
+ * 0x40 position (final), 0x80 dt written to cache_t::dt; phys bits: 1 diff_turb, 2 diff_meso, 4 sedi. */
+int mpb_plan_modules(const mpb_ctl_t *ctl, double t, unsigned mask, char *buf, int len);
 
 /* --- single modules (same symbols the reference exports, src/mptrac.h:6140-7132); each is the
  *     same fused kernel restricted to one module and reads cache->dt from device memory. --- */

@@ -1640,9 +1640,17 @@ int mpb_set_rng_ctr(mpb_ctx *c, uint64_t ctr) {
 }
 uint64_t mpb_get_rng_ctr(mpb_ctx *c) { return c ? c->rng_ctr : 0; }
 
-static void run_modules(mpb_ctx *c, double t, unsigned mask) {
-  REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
-  const mpb_ctl_t &k = c->ctl;
+// The launches of one mpb_run_modules call, in order.  Planning is pure host logic on the control structure (no device
+// state), so that the dispatch can be checked without a GPU (mpb_plan_modules, tests/test_dispatch_plan.py).
+struct Op {
+  enum Kind { STEP, SORT, ISOSURF_INIT, ADVECT_INIT, ADVECT_LEVELS, DIFF_PBL, CONVECTION, ISOSURF, METEO, BOUND_COND, DECAY, MIXING } kind;
+  int advect;
+  unsigned phys, modules;
+};
+
+static std::vector<Op> plan_modules(const mpb_ctl_t &k, double t, unsigned mask) {
+  std::vector<Op> ops;
+  auto op = [&](Op::Kind kind) { ops.push_back(Op{kind, 0, 0u, 0u}); };
   unsigned phys = 0;
   if ((mask & MPB_MOD_DIFF_TURB) && turb_enabled(k)) phys |= PHYS_TURB;
   if ((mask & MPB_MOD_DIFF_MESO) && meso_enabled(k)) phys |= PHYS_MESO;
@@ -1652,16 +1660,16 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
   if (mask & MPB_MOD_POSITION0) modules |= MOD_POS_PRE;
   if (mask & MPB_MOD_POSITION1) modules |= MOD_POS_POST;
   const bool on_levels = advect > 0 && k.advect_vert_coord != 0;   // advection runs as its own launch between two segments
+  const bool pbl_now = (mask & MPB_MOD_DIFF_PBL) && k.diffusion && k.turb_pbl_scheme == 1;   // src/mptrac.c:7897-7899
   const bool conv_now = (mask & MPB_MOD_CONVECTION) && convection_enabled(k) && (k.conv_dt <= 0 || hits(t, k.conv_dt));
+  const bool iso_now = (mask & MPB_MOD_ISOSURF) && isosurf_enabled(k);
+  const bool bound0 = (mask & MPB_MOD_BOUND0) && bound_enabled(k), bound1 = (mask & MPB_MOD_BOUND1) && bound_enabled(k);
   const bool decay_now = (mask & MPB_MOD_DECAY) && (decay_enabled(k) || k.qnt_loss_rate >= 0);
   // timesteps ... position1 in one launch: dt stays in registers (modules that run as their own launch read it from memory)
-  const bool iso_now = (mask & MPB_MOD_ISOSURF) && isosurf_enabled(k);
-  const bool pbl_now = (mask & MPB_MOD_DIFF_PBL) && k.diffusion && k.turb_pbl_scheme == 1;   // src/mptrac.c:7897-7899
-  const bool bound0 = (mask & MPB_MOD_BOUND0) && bound_enabled(k), bound1 = (mask & MPB_MOD_BOUND1) && bound_enabled(k);
   const bool whole = (mask & 0xff) == 0xff && !on_levels && !pbl_now && !conv_now && !decay_now && !iso_now && !bound0 && !bound1;
   if ((mask & MPB_MOD_TIMESTEPS) && t == k.t_start) {   // src/mptrac.c:7863-7873
-    if (iso_now) launch_isosurf(c, true);
-    launch_advect_init(c);
+    if (iso_now && k.isosurf != 4) op(Op::ISOSURF_INIT);   // (the balloon series of ISOSURF 4 arrives through mpb_set_balloon)
+    if (k.advect_vert_coord == 1) op(Op::ADVECT_INIT);
   }
   const bool sort_now = (mask & MPB_MOD_SORT) && k.sort_dt > 0 && hits(t, k.sort_dt);
   if (mask & MPB_MOD_TIMESTEPS) {
@@ -1669,45 +1677,88 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
       // the reference computes dt BEFORE it permutes the parcels and leaves cache->dt in slot order
       // (src/mptrac.c:7877-7881): a dt-only launch (active parcels are rewritten unchanged), then the sort,
       // then the fused launch reads dt from memory
-      launch_step(c, t, 0, 0, MOD_TIMESTEPS | MOD_STORE_DT);
-      do_sort(c);
+      ops.push_back(Op{Op::STEP, 0, 0u, MOD_TIMESTEPS | MOD_STORE_DT});
+      op(Op::SORT);
     } else {
       modules |= MOD_TIMESTEPS;
       if (!whole) modules |= MOD_STORE_DT;   // later segments read cache->dt from memory
     }
   } else if (sort_now) {
-    do_sort(c);
+    op(Op::SORT);
   }
   // The per-parcel modules in the reference's order (src/mptrac.c:7876-7919).  Everything the fused kernel covers
   // accumulates in one segment; a module that runs as its own launch -- model-level advection, diff_pbl, convection,
   // isosurf -- flushes the segment before it, so a plain configuration is ONE launch and each such module adds two.
-  int seg_advect = 0;
-  unsigned seg_phys = 0, seg_modules = modules & (MOD_TIMESTEPS | MOD_STORE_DT | MOD_POS_PRE);
+  Op seg{Op::STEP, 0, 0u, modules & (MOD_TIMESTEPS | MOD_STORE_DT | MOD_POS_PRE)};
   auto flush = [&]() {
-    if (seg_advect || seg_phys || seg_modules) launch_step(c, t, seg_advect, seg_phys, seg_modules);
-    seg_advect = 0; seg_phys = 0; seg_modules = 0;
+    if (seg.advect || seg.phys || seg.modules) ops.push_back(seg);
+    seg = Op{Op::STEP, 0, 0u, 0u};
   };
-  if (on_levels) { flush(); launch_advect_levels(c); }
-  else seg_advect = advect;
-  seg_phys |= phys & PHYS_TURB;
-  if (pbl_now) { flush(); launch_diff_pbl(c); }
-  seg_phys |= phys & PHYS_MESO;
-  if (conv_now) { flush(); launch_convection(c); }
-  seg_phys |= phys & PHYS_SEDI;
-  if (iso_now) { flush(); launch_isosurf(c, false); }
-  seg_modules |= modules & MOD_POS_POST;
+  if (on_levels) { flush(); op(Op::ADVECT_LEVELS); }
+  else seg.advect = advect;
+  seg.phys |= phys & PHYS_TURB;
+  if (pbl_now) { flush(); op(Op::DIFF_PBL); }
+  seg.phys |= phys & PHYS_MESO;
+  if (conv_now) { flush(); op(Op::CONVECTION); }
+  seg.phys |= phys & PHYS_SEDI;
+  if (iso_now) { flush(); op(Op::ISOSURF); }
+  seg.modules |= modules & MOD_POS_POST;
   flush();
-  if ((mask & MPB_MOD_METEO) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out)))   // src/mptrac.c:7927-7929
-    launch_meteo(c);
-  if (bound0) launch_bound_cond(c);   // src/mptrac.c:7926-7929
-  if (decay_now) launch_decay(c);   // src/mptrac.c:7931-7940
-  if ((mask & MPB_MOD_MIXING) && k.mixing_trop >= 0 && k.mixing_strat >= 0 &&
-      (k.mixing_dt <= 0 || hits(t, k.mixing_dt))) {  // src/mptrac.c:7943-7945
-    mixing_begin(c, t);
-    for (int i = 0; i < k.n_mix_qnt; i++)
-      if (k.mix_qnt[i] >= 0) { mixing_accumulate(c, k.mix_qnt[i]); mixing_apply(c, k.mix_qnt[i]); }
+  if ((mask & MPB_MOD_METEO) && meteo_wanted(k) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out)))   // :7921-7924
+    op(Op::METEO);
+  if (bound0) op(Op::BOUND_COND);     // :7926-7929
+  if (decay_now) op(Op::DECAY);       // :7931-7940
+  if ((mask & MPB_MOD_MIXING) && k.mixing_trop >= 0 && k.mixing_strat >= 0 && (k.mixing_dt <= 0 || hits(t, k.mixing_dt)))   // :7943-7945
+    op(Op::MIXING);
+  if (bound1) op(Op::BOUND_COND);     // :7997-8000
+  return ops;
+}
+
+static void run_modules(mpb_ctx *c, double t, unsigned mask) {
+  REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
+  const mpb_ctl_t &k = c->ctl;
+  for (const Op &o : plan_modules(k, t, mask)) {
+    switch (o.kind) {
+      case Op::STEP: launch_step(c, t, o.advect, o.phys, o.modules); break;
+      case Op::SORT: do_sort(c); break;
+      case Op::ISOSURF_INIT: launch_isosurf(c, true); break;
+      case Op::ADVECT_INIT: launch_advect_init(c); break;
+      case Op::ADVECT_LEVELS: launch_advect_levels(c); break;
+      case Op::DIFF_PBL: launch_diff_pbl(c); break;
+      case Op::CONVECTION: launch_convection(c); break;
+      case Op::ISOSURF: launch_isosurf(c, false); break;
+      case Op::METEO: launch_meteo(c); break;
+      case Op::BOUND_COND: launch_bound_cond(c); break;
+      case Op::DECAY: launch_decay(c); break;
+      case Op::MIXING:
+        mixing_begin(c, t);
+        for (int i = 0; i < k.n_mix_qnt; i++)
+          if (k.mix_qnt[i] >= 0) { mixing_accumulate(c, k.mix_qnt[i]); mixing_apply(c, k.mix_qnt[i]); }
+        break;
+    }
   }
-  if (bound1) launch_bound_cond(c);   // src/mptrac.c:7997-8000
+}
+
+// The plan of mpb_run_modules(ctx, t, mask) for a control structure, as text: one launch per token, e.g.
+// "step(advect=4,phys=0x0,mod=0x43) meteo".  Needs neither a context nor a device.
+int mpb_plan_modules(const mpb_ctl_t *ctl, double t, unsigned mask, char *buf, int len) {
+  API_BEGIN
+  REQUIRE(ctl && buf && len > 0, "bad arguments");
+  static const char *names[] = {"step", "sort", "isosurf_init", "advect_init", "advect_levels", "diff_pbl", "convection", "isosurf",
+                                "meteo", "bound_cond", "decay", "mixing"};
+  std::string out;
+  for (const Op &o : plan_modules(*ctl, t, mask)) {
+    if (!out.empty()) out += ' ';
+    out += names[o.kind];
+    if (o.kind == Op::STEP) {
+      char tmp[64];
+      std::snprintf(tmp, sizeof(tmp), "(advect=%d,phys=0x%x,mod=0x%x)", o.advect, o.phys, o.modules);
+      out += tmp;
+    }
+  }
+  REQUIRE((int)out.size() < len, "plan buffer too small");
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  API_END
 }
 
 int mpb_run_timestep(mpb_ctx *c, double t) {

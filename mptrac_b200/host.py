@@ -263,6 +263,16 @@ class Met:
         return s
 
 
+def plan_modules(ctl: "Ctl", t: float, mask: int = MOD_ALL) -> str:
+    """The launches ``Engine.run_modules(t, mask)`` would make for ``ctl`` (``mpb_plan_modules``: no device needed)."""
+    lib = load_library()
+    buf = C.create_string_buffer(4096)
+    s = ctl.to_struct()
+    if lib.mpb_plan_modules(C.byref(s), float(t), int(mask), buf, len(buf)) != 0:
+        raise MpbError(lib.mpb_last_error().decode())
+    return buf.value.decode()
+
+
 _lib_cache = {}
 
 
@@ -298,6 +308,7 @@ def load_library(strict: bool = False) -> C.CDLL:
         "mpb_get_iso_var": (i32, [vp, vp]),
         "mpb_set_balloon": (i32, [vp, i32, vp, vp]),
         "mpb_set_clim_ts": (i32, [vp, i32, i32, vp, vp]),
+        "mpb_plan_modules": (i32, [vp, dbl, C.c_uint, C.c_char_p, i32]),
         "mpb_get_dt": (i32, [vp, vp]),
         "mpb_get_np": (i64, [vp]),
         "mpb_set_shard": (i32, [vp, i64, i64]),
