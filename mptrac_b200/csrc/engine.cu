@@ -1668,7 +1668,8 @@ static std::vector<Op> plan_modules(const mpb_ctl_t &k, double t, unsigned mask)
   // timesteps ... position1 in one launch: dt stays in registers (modules that run as their own launch read it from memory)
   const bool whole = (mask & 0xff) == 0xff && !on_levels && !pbl_now && !conv_now && !decay_now && !iso_now && !bound0 && !bound1;
   if ((mask & MPB_MOD_TIMESTEPS) && t == k.t_start) {   // src/mptrac.c:7863-7873
-    if (iso_now && k.isosurf != 4) op(Op::ISOSURF_INIT);   // (the balloon series of ISOSURF 4 arrives through mpb_set_balloon)
+    // (whichever segment carries MPB_MOD_ISOSURF later; the balloon series of ISOSURF 4 arrives through mpb_set_balloon)
+    if (isosurf_enabled(k) && k.isosurf != 4) op(Op::ISOSURF_INIT);
     if (k.advect_vert_coord == 1) op(Op::ADVECT_INIT);
   }
   const bool sort_now = (mask & MPB_MOD_SORT) && k.sort_dt > 0 && hits(t, k.sort_dt);

@@ -60,6 +60,24 @@ static int device_meteo_fields(void) {
   return on;
 }
 static int g_fields, g_need2[MPB_NX2], g_need3[MPB_NX3];
+static int meteo_needs_host(const ctl_t *c);
+
+/* MPTRAC_B200_DEVICE_MODULES=1: module_diff_pbl, module_convection, module_isosurf and -- when nothing else keeps the tail
+ * of the step on the host -- module_bound_cond and module_decay run on the device at their places in the dispatcher
+ * instead of the reference's CPU code.  Off by default for the same reason as MPTRAC_B200_DEVICE_METEO_FIELDS. */
+static int device_modules(void) {
+  static int on = -1;
+  if (on < 0) on = getenv("MPTRAC_B200_DEVICE_MODULES") ? atoi(getenv("MPTRAC_B200_DEVICE_MODULES")) : 0;
+  return on;
+}
+
+/* modules after the final position check that only exist on the host (chemistry, deposition): with any of them on,
+ * everything from module_meteo's successor to the end of the step runs through the reference's code, in its order */
+static int tail_needs_host(const ctl_t *c) {
+  const int wet = (c->wet_depo_ic_a > 0 || c->wet_depo_ic_h[0] > 0) && (c->wet_depo_bc_a > 0 || c->wet_depo_bc_h[0] > 0);
+  return c->oh_chem_reaction != 0 || c->h2o2_chem_reaction != 0 || c->kpp_chem || c->tracer_chem || c->radio_decay || c->radio_depo ||
+    wet || c->dry_depo_vdep > 0;
+}
 
 static int g_levels;   /* the control file advects on model levels: the met uploads carry pl, ul, vl, wl, zetal, zeta_dotl */
 
@@ -104,16 +122,35 @@ static void put_ctl(const ctl_t *c) {
   k.qnt_aoa = -1; k.cts_on = 0;
   for (int i = 0; i < 5; i++) k.qnt_cts[i] = -1;
   g_levels = c->advect_vert_coord != 0;
-  g_fields = device_meteo_fields();
+  g_fields = device_meteo_fields() || device_modules();
   memset(g_need2, 0, sizeof(g_need2)); memset(g_need3, 0, sizeof(g_need3));
-  if (g_fields) {
+  if (device_modules()) {
+    k.conv_cape = c->conv_cape; k.conv_cin = c->conv_cin; k.conv_dt = c->conv_dt; k.conv_pbl_trans = c->conv_pbl_trans;
+    k.conv_mix_pbl = c->conv_mix_pbl;
+    k.isosurf = c->isosurf;
+    if (c->conv_cape >= 0) g_need2[MPB_F2_CAPE] = g_need2[MPB_F2_CIN] = g_need2[MPB_F2_PEL] = 1;
+    if (c->diffusion && c->turb_pbl_scheme == 1) g_need2[MPB_F2_ESS] = g_need2[MPB_F2_NSS] = g_need2[MPB_F2_SHF] = g_need3[MPB_F3_H2O] = 1;
+    if (!tail_needs_host(c) && !meteo_needs_host(c)) {
+      k.tdec_trop = c->tdec_trop; k.tdec_strat = c->tdec_strat;
+      k.qnt_m = c->qnt_m; k.qnt_vmr = c->qnt_vmr; k.qnt_mloss_decay = c->qnt_mloss_decay; k.qnt_loss_rate = c->qnt_loss_rate;
+      k.bound_mass = c->bound_mass; k.bound_mass_trend = c->bound_mass_trend; k.bound_vmr = c->bound_vmr;
+      k.bound_vmr_trend = c->bound_vmr_trend; k.bound_lat0 = c->bound_lat0; k.bound_lat1 = c->bound_lat1; k.bound_p0 = c->bound_p0;
+      k.bound_p1 = c->bound_p1; k.bound_dps = c->bound_dps; k.bound_dzs = c->bound_dzs; k.bound_zetas = c->bound_zetas;
+      k.bound_pbl = c->bound_pbl; k.qnt_aoa = c->qnt_aoa;
+      const int qc[5] = {c->qnt_Cccl4, c->qnt_Cccl3f, c->qnt_Cccl2f2, c->qnt_Cn2o, c->qnt_Csf6};
+      const char *nm[5] = {c->clim_ccl4_timeseries, c->clim_ccl3f_timeseries, c->clim_ccl2f2_timeseries, c->clim_n2o_timeseries,
+                           c->clim_sf6_timeseries};
+      for (int i = 0; i < 5; i++) { k.qnt_cts[i] = qc[i]; if (nm[i][0] != '-') k.cts_on |= 1 << i; }
+    }
+  }
+  if (device_meteo_fields()) {
     const int q2[MPB_NX2] = {c->qnt_ts, c->qnt_zs, c->qnt_us, c->qnt_vs, c->qnt_ess, c->qnt_nss, c->qnt_shf, c->qnt_lsm, c->qnt_sst,
                              c->qnt_pt, c->qnt_tt, c->qnt_zt, c->qnt_h2ot, c->qnt_pct, c->qnt_pcb, c->qnt_cl, c->qnt_plcl, c->qnt_plfc,
                              c->qnt_pel, c->qnt_cape, c->qnt_cin, c->qnt_o3c};
     const int q3[MPB_NX3] = {c->qnt_zg, c->qnt_pv, c->qnt_h2o, c->qnt_o3, c->qnt_lwc, c->qnt_rwc, c->qnt_iwc, c->qnt_swc, c->qnt_cc};
     const int qm[8] = {c->qnt_pw, c->qnt_sh, c->qnt_rh, c->qnt_rhice, c->qnt_tvirt, c->qnt_lapse, c->qnt_tdew, c->qnt_tice};
-    for (int f = 0; f < MPB_NX2; f++) { k.qnt_meteo[MPB_Q_TS + f] = q2[f]; g_need2[f] = q2[f] >= 0; }
-    for (int f = 0; f < MPB_NX3; f++) { k.qnt_meteo[MPB_Q_ZG + f] = q3[f]; g_need3[f] = q3[f] >= 0; }
+    for (int f = 0; f < MPB_NX2; f++) { k.qnt_meteo[MPB_Q_TS + f] = q2[f]; g_need2[f] |= q2[f] >= 0; }
+    for (int f = 0; f < MPB_NX3; f++) { k.qnt_meteo[MPB_Q_ZG + f] = q3[f]; g_need3[f] |= q3[f] >= 0; }
     for (int i = 0; i < 8; i++) { k.qnt_meteo[MPB_Q_PW + i] = qm[i]; if (qm[i] >= 0) g_need3[MPB_F3_H2O] = 1; }
   }
   MPB(mpb_set_ctl(g_ctx, &k));
@@ -200,6 +237,11 @@ void mptrac_update_device(const ctl_t *ctl, const cache_t *cache, const clim_t *
   else if (atm && last_ctl) put_ctl(last_ctl);
   if (clim && clim->tropo_ntime > 0)
     MPB(mpb_set_clim_tropo(g_ctx, clim->tropo_ntime, clim->tropo_nlat, clim->tropo_time, clim->tropo_lat, &clim->tropo[0][0]));
+  if (clim && device_modules()) {
+    const clim_ts_t *ts[5] = {&clim->ccl4, &clim->ccl3f, &clim->ccl2f2, &clim->n2o, &clim->sf6};
+    for (int i = 0; i < 5; i++)
+      if (ts[i]->ntime > 0) MPB(mpb_set_clim_ts(g_ctx, i, ts[i]->ntime, ts[i]->time, ts[i]->vmr));
+  }
   if (met0 && *met0) put_met(*met0);
   if (met1 && *met1) put_met(*met1);
   if (atm) put_atm(atm);
@@ -288,29 +330,35 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
   /* which reference modules does this control file enable that are NOT on the device path?
      (conditions copied in meaning from the dispatcher, src/mptrac.c:7863-8000) */
   const int init_cpu = (t == ctl->t_start) && ((ctl->isosurf >= 1 && ctl->isosurf <= 4) || 1 /* chem_init is unconditional */);
-  const int pbl_cpu = ctl->diffusion && ctl->turb_pbl_scheme == 1;
-  const int conv_cpu = (ctl->conv_mix_pbl || ctl->conv_cape >= 0) && (ctl->conv_dt <= 0 || fmod(t, ctl->conv_dt) == 0);
-  const int iso_cpu = ctl->isosurf >= 1 && ctl->isosurf <= 4;
+  const int dm = device_modules();                                          /* route the rank-4 modules to the device */
+  const int dm_tail = dm && !tail_needs_host(ctl) && !meteo_needs_host(ctl);   /* ... bound_cond and decay among them (put_ctl) */
+  const int pbl_cpu = !dm && ctl->diffusion && ctl->turb_pbl_scheme == 1;
+  const int conv_cpu = !dm && (ctl->conv_mix_pbl || ctl->conv_cape >= 0) && (ctl->conv_dt <= 0 || fmod(t, ctl->conv_dt) == 0);
+  const int iso_cpu = !dm && ctl->isosurf >= 1 && ctl->isosurf <= 4;
   const int meteo_cpu = ctl->met_dt_out > 0 && (ctl->met_dt_out < ctl->dt_mod || fmod(t, ctl->met_dt_out) == 0) && meteo_needs_host(ctl);
-  const int bound_cpu = (ctl->bound_lat0 < ctl->bound_lat1) && (ctl->bound_p0 > ctl->bound_p1);
-  const int decay_cpu = ctl->tdec_trop > 0 && ctl->tdec_strat > 0;
+  const int bound_cpu = !dm_tail && (ctl->bound_lat0 < ctl->bound_lat1) && (ctl->bound_p0 > ctl->bound_p1);
+  const int decay_cpu = !dm_tail && ctl->tdec_trop > 0 && ctl->tdec_strat > 0;
+  const int loss_cpu = !dm_tail && ctl->qnt_loss_rate >= 0;
   const int chemgrid_cpu = ctl->oh_chem_reaction != 0 || ctl->h2o2_chem_reaction != 0 || (ctl->kpp_chem && fmod(t, ctl->dt_kpp) == 0);
   const int wet_cpu = (ctl->wet_depo_ic_a > 0 || ctl->wet_depo_ic_h[0] > 0) && (ctl->wet_depo_bc_a > 0 || ctl->wet_depo_bc_h[0] > 0);
-  const int tail_cpu = meteo_cpu || bound_cpu || ctl->qnt_loss_rate >= 0 || decay_cpu || chemgrid_cpu || ctl->oh_chem_reaction != 0 ||
+  const int tail_cpu = meteo_cpu || bound_cpu || loss_cpu || decay_cpu || chemgrid_cpu || ctl->oh_chem_reaction != 0 ||
     ctl->h2o2_chem_reaction != 0 || ctl->tracer_chem || ctl->radio_decay || ctl->radio_depo || ctl->kpp_chem || wet_cpu || ctl->dry_depo_vdep > 0;
 
   if (init_cpu) {
     ON_HOST({
-      if (ctl->isosurf >= 1 && ctl->isosurf <= 4) module_isosurf_init(ctl, cache, *met0, *met1, atm);
+      /* (routed: the device computes iso_var itself; ISOSURF 4 still reads the balloon file here) */
+      if (ctl->isosurf >= 1 && ctl->isosurf <= 4 && (!dm || ctl->isosurf == 4)) module_isosurf_init(ctl, cache, *met0, *met1, atm);
       module_chem_init(ctl, cache, clim, *met0, *met1, atm);
     });
     FLUSH_HOST();
+    if (dm && ctl->isosurf == 4) MPB(mpb_set_balloon(g_ctx, cache->iso_n, cache->iso_ts, cache->iso_ps));
   }
 
   if (!pbl_cpu && !conv_cpu && !iso_cpu && !tail_cpu) {
     MPB(mpb_run_timestep(g_ctx, t));            /* the whole step is one fused launch (+ sort / mixing kernels) */
   } else {
     unsigned seg = MPB_MOD_TIMESTEPS | MPB_MOD_SORT | MPB_MOD_POSITION0 | MPB_MOD_ADVECT | MPB_MOD_DIFF_TURB;
+    if (dm) seg |= MPB_MOD_DIFF_PBL;
     if (pbl_cpu) {
       MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0; g_dev_newer = 1;
       ON_HOST({
@@ -321,6 +369,7 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
       FLUSH_HOST();
     }
     seg |= MPB_MOD_DIFF_MESO;
+    if (dm) seg |= MPB_MOD_CONVECTION;
     if (conv_cpu) {
       MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0; g_dev_newer = 1;
       ON_HOST({
@@ -331,6 +380,7 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
       FLUSH_HOST();
     }
     seg |= MPB_MOD_SEDI;
+    if (dm) seg |= MPB_MOD_ISOSURF;
     if (iso_cpu) {
       MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0; g_dev_newer = 1;
       ON_HOST(module_isosurf(ctl, cache, *met0, *met1, atm));
@@ -338,6 +388,7 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
     }
     seg |= MPB_MOD_POSITION1;
     if (!meteo_cpu) seg |= MPB_MOD_METEO;       /* every quantity module_meteo sets here is available on the device */
+    if (dm_tail) seg |= MPB_MOD_BOUND0 | MPB_MOD_DECAY;
     MPB(mpb_run_modules(g_ctx, t, seg));
     g_dev_newer = 1;
     if (tail_cpu) {
@@ -364,7 +415,7 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
       FLUSH_HOST();
       g_dev_newer = 0;     /* host and device hold the same parcels now */
     } else {
-      MPB(mpb_run_modules(g_ctx, t, MPB_MOD_MIXING));
+      MPB(mpb_run_modules(g_ctx, t, MPB_MOD_MIXING | (dm_tail ? MPB_MOD_BOUND1 : 0u)));
     }
   }
   if (!tail_cpu) g_dev_newer = 1;

@@ -61,6 +61,28 @@ def test_module_meteo_field_quantity_without_its_field_fails_loudly():
 
 
 @pytest.mark.timeout(900)
+@pytest.mark.parametrize("levels", ["pl", "ml"])
+def test_trac_trac_test_with_routed_modules(tmp_path, monkeypatch, levels):
+    """tests/trac_test through the shim with MPTRAC_B200_DEVICE_MODULES=1 and MPTRAC_B200_DEVICE_METEO_FIELDS=1: its
+    module_convection (CONV_CAPE 0: cape, cin, pel uploaded with each met level) and its zg / pv / pt run on the device;
+    chemistry and deposition keep the tail of the step -- boundary conditions and decay with it -- on the host"""
+    import test_shim_trac as T
+    monkeypatch.setenv("MPTRAC_B200_DEVICE_MODULES", "1")
+    monkeypatch.setenv("MPTRAC_B200_DEVICE_METEO_FIELDS", "1")
+    T.test_trac_trac_test_through_the_shim(tmp_path, levels)
+
+
+@pytest.mark.timeout(900)
+def test_trac_interoper_test_with_routed_modules(tmp_path, monkeypatch):
+    """tests/interoper_test (zeta coordinate) with MPTRAC_B200_DEVICE_MODULES=1: module_decay is the only tail module of
+    that control file besides module_meteo, whose pv keeps it on the host unless the fields go to the device too"""
+    import test_shim_trac as T
+    monkeypatch.setenv("MPTRAC_B200_DEVICE_MODULES", "1")
+    monkeypatch.setenv("MPTRAC_B200_DEVICE_METEO_FIELDS", "1")
+    T.test_trac_interoper_test_zeta_through_the_shim(tmp_path)
+
+
+@pytest.mark.timeout(900)
 def test_trac_trac_test_pl_with_device_meteo_fields(tmp_path, monkeypatch):
     """tests/trac_test (pressure-level run) through the shim with MPTRAC_B200_DEVICE_METEO_FIELDS=1: zg, pv and pt of its
     control file come from the device's module_meteo instead of the reference's CPU code"""
