@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Benchmark of the MPTRAC time-step path on B200 (contract: see the task statement / DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c4g|c5|c2ml]
+
+Workloads: c2 (default) = BASELINE configs[1]; c3 = configs[2]; c4 = one GPU's share of configs[3], c4g the same with
+the gridded output reduced over the ranks every step; c5 = one GPU's share of configs[4] (cell sort + mixing all-reduce
+every step); c2ml = configs[1] on model levels (ADVECT_VERT_COORD 2).  N > 1 runs under torchrun, one rank per GPU.
 
 One "step" = one model time step (mptrac_run_timestep restricted to the path) over every parcel of the
 workload.  Default workload = BASELINE.json configs[1] ("c2"): 1 M parcels, 1 deg x 1 deg x 60-level synthetic
