@@ -28,7 +28,7 @@ extern "C" {
 
 /* ABI history (mpb_abi_version()): 2 module_meteo quantities of the resident fields; 3 model-level fields and the zeta / eta
  * quantities (ADVECT_VERT_COORD 1, 2, 3); 4 further met fields (x2 / x3), 64 meteo slots, module_convection, module_decay,
- * module_isosurf, module_diff_pbl, module_bound_cond (their control fields at the end of mpb_ctl_t, MPB_MOD_* bits) */
+ * module_isosurf, module_diff_pbl, module_bound_cond, module_chem_grid (their control fields at the end of mpb_ctl_t, MPB_MOD_* bits) */
 #define MPB_ABI_VERSION 4
 #define MPB_MIX_MAXQ 23  /* number of mixable quantities, src/mptrac.c:5222-5230 */
 
@@ -105,6 +105,11 @@ typedef struct mpb_ctl {
   int32_t bound_pbl, qnt_aoa;
   int32_t qnt_cts[5];         /* ctl->qnt_Cccl4, qnt_Cccl3f, qnt_Cccl2f2, qnt_Cn2o, qnt_Csf6 */
   int32_t cts_on;             /* bit i: ctl->clim_*_timeseries of species i is not "-" (series through mpb_set_clim_ts) */
+  /* module_chem_grid (src/mptrac.c:3885-4054): volume mixing ratio of the parcel's chemistry-grid box into quantity Cx */
+  double chemgrid_lon0, chemgrid_lon1, chemgrid_lat0, chemgrid_lat1, chemgrid_z0, chemgrid_z1, molmass;   /* ctl->chemgrid_*, molmass */
+  int32_t chemgrid_nx, chemgrid_ny, chemgrid_nz, qnt_Cx;
+  int32_t chemgrid;           /* run it (the reference does for its OH / H2O2 / KPP chemistry, src/mptrac.c:7947-7950) */
+  int32_t _pad3;
 } mpb_ctl_t;
 
 /* Host view of one met_t time level (src/mptrac.h:3844-4014).  3-D element (ix,iy,iz) lives at
@@ -211,7 +216,8 @@ int mpb_run_timestep_host(mpb_ctx *ctx, double t, int64_t np, double *time, doub
 #define MPB_MOD_DIFF_PBL  0x2000  /* TURB_PBL_SCHEME 1, between DIFF_TURB and DIFF_MESO (src/mptrac.c:7897-7899) */
 #define MPB_MOD_BOUND0    0x4000  /* module_bound_cond after METEO (src/mptrac.c:7926-7929) ... */
 #define MPB_MOD_BOUND1    0x8000  /* ... and again at the end of the step (7997-8000) */
-#define MPB_MOD_ALL       0xffff
+#define MPB_MOD_CHEMGRID  0x10000 /* module_chem_grid, after MIXING (src/mptrac.c:7947-7950) */
+#define MPB_MOD_ALL       0x1ffff
 int mpb_run_modules(mpb_ctx *ctx, double t, unsigned mask);
 /* The launches mpb_run_modules(ctx, t, mask) would make for this control structure, as text ("step(advect=4,phys=0x0,mod=0x43)
  * meteo ..."): pure host logic, needs neither a context nor a device.  mod bits: 0x01 timesteps, 0x02 position (initial),

@@ -461,6 +461,30 @@ __global__ void __launch_bounds__(128) convection_kernel(const __grid_constant__
   A.p[ip] = a.p;
 }
 
+// module_chem_grid (src/mptrac.c:3885-4054): box per parcel + mass per box, then the box's volume mixing ratio per parcel
+struct ChemArgs {
+  MetView met;
+  ChemGrid k;
+  const double *time, *lon, *lat, *p, *m, *ens;
+  double *cx, *mass;
+  int *box;
+  long long np;
+  int ngrid;
+};
+__global__ void chem_mass_kernel(const __grid_constant__ ChemArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np) return;
+  const int b = chem_box(A.k, A.time[ip], A.lon[ip], A.lat[ip], A.p[ip]);
+  A.box[ip] = b;
+  if (b >= 0) atomicAdd(A.mass + b + (A.ens ? (int)A.ens[ip] * A.ngrid : 0), A.m[ip]);
+}
+__global__ void __launch_bounds__(128) chem_apply_kernel(const __grid_constant__ ChemArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np) return;
+  const int b = A.box[ip];
+  if (b >= 0) A.cx[ip] = chem_vmr(A.met, A.k, b, A.mass[b + (A.ens ? (int)A.ens[ip] * A.ngrid : 0)]);
+}
+
 // module_bound_cond (src/mptrac.c:3789-3881): parcels with dt != 0
 struct BoundArgs {
   MetView met;
@@ -724,6 +748,9 @@ struct mpb_ctx {
   size_t lev_cap = 0;
   bool lev_valid[2] = {false, false};
   unsigned short *lev_hint = nullptr;              // LevelArgs::hint
+  // module_chem_grid: mass per box (and ensemble member)
+  double *chem_mass = nullptr;
+  long long chem_cap = 0;
   // module_bound_cond: the five trace-gas time series of clim_t (ccl4, ccl3f, ccl2f2, n2o, sf6)
   double *cts_time[5] = {}, *cts_vmr[5] = {};
   int cts_n[5] = {};
@@ -1097,6 +1124,39 @@ static void launch_isosurf(mpb_ctx *c, bool init) {
   c->launches++;
 }
 
+static void launch_chem_grid(mpb_ctx *c, double t) {
+  const mpb_ctl_t &k = c->ctl;
+  if (c->np == 0 || k.qnt_m < 0 || k.qnt_Cx < 0) return;   // src/mptrac.c:3896-3897
+  REQUIRE(k.met_coord_type == 0, "module_chem_grid supports the lat/lon grid only");
+  REQUIRE(k.molmass > 0, "module_chem_grid: molar mass is not defined");
+  REQUIRE(k.qnt_m < c->nq && k.qnt_Cx < c->nq && (k.nens <= 0 || (k.qnt_ens >= 0 && k.qnt_ens < c->nq)), "chemistry-grid quantity index out of range");
+  REQUIRE(k.chemgrid_nx > 0 && k.chemgrid_ny > 0 && k.chemgrid_nz > 0, "bad chemistry grid");
+  const long long ngrid = (long long)k.chemgrid_nx * k.chemgrid_ny * k.chemgrid_nz, total = ngrid * (k.nens > 0 ? k.nens : 1);
+  REQUIRE(total < (1ll << 31), "chemistry grid too large");
+  ensure_boxes(c);
+  if (total > c->chem_cap) {
+    if (c->chem_mass) CK(cudaFree(c->chem_mass));
+    CK(cudaMalloc(&c->chem_mass, sizeof(double) * (size_t)total));
+    c->chem_cap = total;
+  }
+  CK(cudaMemsetAsync(c->chem_mass, 0, sizeof(double) * (size_t)total, c->stream));
+  ChemArgs A;
+  A.met = met_view(c);
+  A.k.lon0 = k.chemgrid_lon0; A.k.lon1 = k.chemgrid_lon1; A.k.lat0 = k.chemgrid_lat0; A.k.lat1 = k.chemgrid_lat1;
+  A.k.z0 = k.chemgrid_z0; A.k.z1 = k.chemgrid_z1;
+  A.k.dlon = (k.chemgrid_lon1 - k.chemgrid_lon0) / k.chemgrid_nx; A.k.dlat = (k.chemgrid_lat1 - k.chemgrid_lat0) / k.chemgrid_ny;
+  A.k.dz = (k.chemgrid_z1 - k.chemgrid_z0) / k.chemgrid_nz;
+  A.k.t0 = t - 0.5 * k.dt_mod; A.k.t1 = t + 0.5 * k.dt_mod; A.k.tt = t; A.k.molmass = k.molmass;
+  A.k.nx = k.chemgrid_nx; A.k.ny = k.chemgrid_ny; A.k.nz = k.chemgrid_nz;
+  A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p();
+  A.m = c->q(k.qnt_m); A.cx = c->q(k.qnt_Cx); A.ens = k.nens > 0 ? c->q(k.qnt_ens) : nullptr;
+  A.mass = c->chem_mass; A.box = c->box; A.np = c->np; A.ngrid = (int)ngrid;
+  chem_mass_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(A);
+  chem_apply_kernel<<<nblocks(c->np, 128), 128, 0, c->stream>>>(A);
+  CK(cudaGetLastError());
+  c->launches += 2;
+}
+
 static bool bound_enabled(const mpb_ctl_t &k) { return k.bound_lat0 < k.bound_lat1 && k.bound_p0 > k.bound_p1; }   // src/mptrac.c:7926
 
 static void launch_bound_cond(mpb_ctx *c) {
@@ -1252,7 +1312,7 @@ int mpb_destroy(mpb_ctx *c) {
   void *ptrs[] = {c->soa[0], c->soa[1], c->dt, c->uvwp, c->keys[0], c->keys[1], c->perm[0], c->perm[1],
                   c->cub_tmp, c->nodes, c->surf, c->ax_lon, c->ax_lat, c->ax_p, c->ax_lonc, c->ax_latc, c->ax_pc,
                   c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_sum, c->mix_cnt,
-                  c->grid_sum, c->grid_sq, c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz, c->lev_hint, c->iso_var, c->iso_ts, c->iso_ps};
+                  c->grid_sum, c->grid_sq, c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz, c->lev_hint, c->iso_var, c->iso_ts, c->iso_ps, c->chem_mass};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (double *p : c->cts_time) if (p) cudaFree(p);
   for (double *p : c->cts_vmr) if (p) cudaFree(p);
@@ -1643,7 +1703,8 @@ uint64_t mpb_get_rng_ctr(mpb_ctx *c) { return c ? c->rng_ctr : 0; }
 // The launches of one mpb_run_modules call, in order.  Planning is pure host logic on the control structure (no device
 // state), so that the dispatch can be checked without a GPU (mpb_plan_modules, tests/test_dispatch_plan.py).
 struct Op {
-  enum Kind { STEP, SORT, ISOSURF_INIT, ADVECT_INIT, ADVECT_LEVELS, DIFF_PBL, CONVECTION, ISOSURF, METEO, BOUND_COND, DECAY, MIXING } kind;
+  enum Kind { STEP, SORT, ISOSURF_INIT, ADVECT_INIT, ADVECT_LEVELS, DIFF_PBL, CONVECTION, ISOSURF, METEO, BOUND_COND, DECAY, MIXING,
+              CHEM_GRID } kind;
   int advect;
   unsigned phys, modules;
 };
@@ -1711,6 +1772,7 @@ static std::vector<Op> plan_modules(const mpb_ctl_t &k, double t, unsigned mask)
   if (decay_now) op(Op::DECAY);       // :7931-7940
   if ((mask & MPB_MOD_MIXING) && k.mixing_trop >= 0 && k.mixing_strat >= 0 && (k.mixing_dt <= 0 || hits(t, k.mixing_dt)))   // :7943-7945
     op(Op::MIXING);
+  if ((mask & MPB_MOD_CHEMGRID) && k.chemgrid) op(Op::CHEM_GRID);   // :7947-7950
   if (bound1) op(Op::BOUND_COND);     // :7997-8000
   return ops;
 }
@@ -1731,6 +1793,7 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
       case Op::METEO: launch_meteo(c); break;
       case Op::BOUND_COND: launch_bound_cond(c); break;
       case Op::DECAY: launch_decay(c); break;
+      case Op::CHEM_GRID: launch_chem_grid(c, t); break;
       case Op::MIXING:
         mixing_begin(c, t);
         for (int i = 0; i < k.n_mix_qnt; i++)
@@ -1746,7 +1809,7 @@ int mpb_plan_modules(const mpb_ctl_t *ctl, double t, unsigned mask, char *buf, i
   API_BEGIN
   REQUIRE(ctl && buf && len > 0, "bad arguments");
   static const char *names[] = {"step", "sort", "isosurf_init", "advect_init", "advect_levels", "diff_pbl", "convection", "isosurf",
-                                "meteo", "bound_cond", "decay", "mixing"};
+                                "meteo", "bound_cond", "decay", "mixing", "chem_grid"};
   std::string out;
   for (const Op &o : plan_modules(*ctl, t, mask)) {
     if (!out.empty()) out += ' ';
@@ -1784,7 +1847,7 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
   const bool mix_now = k.mixing_trop >= 0 && k.mixing_strat >= 0 && (k.mixing_dt <= 0 || hits(t, k.mixing_dt)) && k.n_mix_qnt > 0;
   const bool meteo_now = meteo_wanted(k) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out));
   if (sort_now || mix_now || meteo_now || k.advect_vert_coord != 0 || convection_enabled(k) || decay_enabled(k) || k.qnt_loss_rate >= 0 || isosurf_enabled(k) ||
-      (k.diffusion && k.turb_pbl_scheme == 1) || bound_enabled(k) ||
+      (k.diffusion && k.turb_pbl_scheme == 1) || bound_enabled(k) || k.chemgrid ||
       np < 4 * kHostChunkMin) {
     // steps with a global phase (cell sort, box means), steps that write quantities (meteo) and tiny problems take the
     // plain sequence

@@ -1570,6 +1570,31 @@ MPB_HD double series_at(const double *tm, const double *v, int n, double t) {
   return v[i] + (v[i + 1] - v[i]) / (tm[i + 1] - tm[i]) * (t - tm[i]);   // LIN
 }
 
+// module_chem_grid (3885-4054): box of the chemistry grid a parcel is in (or -1), and the volume mixing ratio of a box from
+// its mass at the temperature of its centre
+struct ChemGrid {
+  double lon0, lon1, lat0, lat1, z0, z1, dlon, dlat, dz, t0, t1, tt, molmass;
+  int nx, ny, nz;
+};
+MPB_HD int chem_box(const ChemGrid &k, double time, double lon, double lat, double p) {
+  const double zpart = altitude(p);
+  if (time < k.t0 || time > k.t1 || lon < k.lon0 || lon >= k.lon1 || lat < k.lat0 || lat >= k.lat1 || zpart < k.z0 || zpart >= k.z1)
+    return -1;
+  const int ix = (int)((lon - k.lon0) / k.dlon), iy = (int)((lat - k.lat0) / k.dlat), iz = (int)((zpart - k.z0) / k.dz);
+  if (ix >= k.nx || iy >= k.ny || iz >= k.nz) return -1;
+  return (ix * k.ny + iy) * k.nz + iz;   // ARRAY_3D, src/mptrac.h:709
+}
+MPB_HD double chem_vmr(const MetView &g, const ChemGrid &k, int box, double mass) {
+  const int iz = box % k.nz, iy = (box / k.nz) % k.ny, ix = box / (k.nz * k.ny);
+  const double z = k.z0 + k.dz * (iz + 0.5), press = kP0 * exp(-z / kH0);
+  const double lon = k.lon0 + k.dlon * (ix + 0.5), lat = k.lat0 + k.dlat * (iy + 0.5);
+  const double area = k.dlat * k.dlon * ((kRE * kPi / 180.) * (kRE * kPi / 180.)) * cos(lat * (kPi / 180.0));
+  CubeT<true> c;
+  cube_reset(c);
+  const double temp = temperature_at(g, k.tt, lon, lat, press, c);
+  return kMA / k.molmass * mass / ((100. * press / (kRA * temp)) * area * k.dz * 1e9);
+}
+
 // module_decay (4227-4263): the e-folding time blends the tropospheric and the stratospheric one with tropo_weight
 // (12748-12770); returns exp(-dt / tdec)
 MPB_HD double decay_factor(const ClimView &cl, int coord_type, double utm_ref_lat, double tdec_trop, double tdec_strat,

@@ -121,6 +121,7 @@ static void put_ctl(const ctl_t *c) {
   k.bound_mass = k.bound_vmr = k.bound_dps = k.bound_dzs = k.bound_zetas = -999;
   k.qnt_aoa = -1; k.cts_on = 0;
   for (int i = 0; i < 5; i++) k.qnt_cts[i] = -1;
+  k.chemgrid = 0; k.qnt_Cx = -1;   /* module_chem_grid feeds the chemistry modules, which are host-only: stays on the host */
   g_levels = c->advect_vert_coord != 0;
   g_fields = device_meteo_fields() || device_modules();
   memset(g_need2, 0, sizeof(g_need2)); memset(g_need3, 0, sizeof(g_need3));

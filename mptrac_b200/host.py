@@ -31,8 +31,8 @@ MET_X2 = ("ts", "zs", "us", "vs", "ess", "nss", "shf", "lsm", "sst", "pt", "tt",
 MET_X3 = ("z", "pv", "h2o", "o3", "lwc", "rwc", "iwc", "swc", "cc")   # [nx][ny][np]; "z" is the geopotential height that quantity zg reports
 # module bits of mpb_run_modules (include/mptrac_b200.h MPB_MOD_*)
 (MOD_TIMESTEPS, MOD_SORT, MOD_POSITION0, MOD_ADVECT, MOD_DIFF_TURB, MOD_DIFF_MESO, MOD_SEDI, MOD_POSITION1, MOD_MIXING,
- MOD_METEO, MOD_CONVECTION, MOD_DECAY, MOD_ISOSURF, MOD_DIFF_PBL, MOD_BOUND0, MOD_BOUND1) = (1 << i for i in range(16))
-MOD_ALL = 0xffff
+ MOD_METEO, MOD_CONVECTION, MOD_DECAY, MOD_ISOSURF, MOD_DIFF_PBL, MOD_BOUND0, MOD_BOUND1, MOD_CHEMGRID) = (1 << i for i in range(17))
+MOD_ALL = 0x1ffff
 _LIBDIR = Path(__file__).resolve().parent / "_lib"
 
 
@@ -59,6 +59,9 @@ class _CtlStruct(C.Structure):
         + [(n, C.c_double) for n in ("bound_mass", "bound_mass_trend", "bound_vmr", "bound_vmr_trend", "bound_lat0", "bound_lat1",
                                      "bound_p0", "bound_p1", "bound_dps", "bound_dzs", "bound_zetas")]
         + [("bound_pbl", C.c_int32), ("qnt_aoa", C.c_int32), ("qnt_cts", C.c_int32 * 5), ("cts_on", C.c_int32)]
+        + [(n, C.c_double) for n in ("chemgrid_lon0", "chemgrid_lon1", "chemgrid_lat0", "chemgrid_lat1", "chemgrid_z0", "chemgrid_z1",
+                                     "molmass")]
+        + [(n, C.c_int32) for n in ("chemgrid_nx", "chemgrid_ny", "chemgrid_nz", "qnt_Cx", "chemgrid", "_pad3")]
     )
 
 
@@ -156,12 +159,24 @@ class Ctl:
     qnt_aoa: int = -1
     qnt_cts: Sequence[int] = (-1, -1, -1, -1, -1)   # Cccl4, Cccl3f, Cccl2f2, Cn2o, Csf6
     cts_on: int = 0                    # bit i: species i has a time series (Engine.set_clim_ts)
+    chemgrid_lon0: float = -180.0      # module_chem_grid: on with chemgrid = 1 (the reference runs it for its chemistry modules)
+    chemgrid_lon1: float = 180.0
+    chemgrid_lat0: float = -90.0
+    chemgrid_lat1: float = 90.0
+    chemgrid_z0: float = -5.0
+    chemgrid_z1: float = 85.0
+    molmass: float = -999.0
+    chemgrid_nx: int = 360
+    chemgrid_ny: int = 180
+    chemgrid_nz: int = 90
+    qnt_Cx: int = -1
+    chemgrid: int = 0
     qnt_meteo: Dict[str, int] = field(default_factory=dict)   # quantity name (METEO_QNT) -> index, e.g. {"t": 0, "u": 1}
 
     def to_struct(self) -> _CtlStruct:
         s = _CtlStruct()
         for name, _ in _CtlStruct._fields_:
-            if name in ("mix_qnt", "_pad", "n_mix_qnt", "qnt_meteo", "qnt_cts"):
+            if name in ("mix_qnt", "_pad", "_pad3", "n_mix_qnt", "qnt_meteo", "qnt_cts"):
                 continue
             setattr(s, name, getattr(self, name))
         unknown = set(self.qnt_meteo) - set(METEO_QNT)

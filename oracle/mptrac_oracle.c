@@ -1070,6 +1070,49 @@ void orc_module_bound_cond(const orc_ctl_t *ctl, const orc_cts_t *cts, const orc
   }
 }
 
+/* module_chem_grid, 3885-4054: mass per box of a regular lon / lat / log-pressure-height grid (summed in parcel order, like the
+ * reference's serial loop) -> volume mixing ratio of the box at the temperature of its centre -> quantity Cx of its parcels */
+void orc_module_chem_grid(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm, double tt) {
+  if (ctl->qnt_m < 0 || ctl->qnt_Cx < 0) return;
+  const int nx = ctl->chemgrid_nx, ny = ctl->chemgrid_ny, nz = ctl->chemgrid_nz, ngrid = nx * ny * nz;
+  const int nens = ctl->nens > 0 ? ctl->nens : 1;
+  const size_t st = (size_t)atm->q_stride;
+  const double dz = (ctl->chemgrid_z1 - ctl->chemgrid_z0) / nz, dlon = (ctl->chemgrid_lon1 - ctl->chemgrid_lon0) / nx;
+  const double dlat = (ctl->chemgrid_lat1 - ctl->chemgrid_lat0) / ny;
+  const double t0 = tt - 0.5 * ctl->dt_mod, t1 = tt + 0.5 * ctl->dt_mod;
+  double *mass = calloc((size_t)ngrid * (size_t)nens, sizeof(double));
+  int *idx = malloc(sizeof(int) * (size_t)(atm->np > 0 ? atm->np : 1));
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    const double zpart = C_H0 * log(C_P0 / atm->p[ip]);
+    idx[ip] = -1;
+    if (atm->time[ip] < t0 || atm->time[ip] > t1 || atm->lon[ip] < ctl->chemgrid_lon0 || atm->lon[ip] >= ctl->chemgrid_lon1 ||
+        atm->lat[ip] < ctl->chemgrid_lat0 || atm->lat[ip] >= ctl->chemgrid_lat1 || zpart < ctl->chemgrid_z0 || zpart >= ctl->chemgrid_z1)
+      continue;
+    const int ix = (int)((atm->lon[ip] - ctl->chemgrid_lon0) / dlon), iy = (int)((atm->lat[ip] - ctl->chemgrid_lat0) / dlat);
+    const int iz = (int)((zpart - ctl->chemgrid_z0) / dz);
+    if (ix >= nx || iy >= ny || iz >= nz) continue;
+    idx[ip] = (ix * ny + iy) * nz + iz;
+    int mi = idx[ip];
+    if (ctl->nens > 0) mi += (int)atm->q[(size_t)ctl->qnt_ens * st + ip] * ngrid;
+    mass[mi] += atm->q[(size_t)ctl->qnt_m * st + ip];
+  }
+#pragma omp parallel for
+  for (int64_t ip = 0; ip < atm->np; ip++) {
+    if (idx[ip] < 0) continue;
+    const int iz = idx[ip] % nz, iy = (idx[ip] / nz) % ny, ix = idx[ip] / (nz * ny);
+    const double z = ctl->chemgrid_z0 + dz * (iz + 0.5), press = C_P0 * exp(-z / C_H0);
+    const double lon = ctl->chemgrid_lon0 + dlon * (ix + 0.5), lat = ctl->chemgrid_lat0 + dlat * (iy + 0.5);
+    const double area = dlat * dlon * ((C_RE * M_PI / 180.) * (C_RE * M_PI / 180.)) * cos(lat * (M_PI / 180.0));
+    cell_t c = CELL_ZERO;
+    const double temp = time3(met0, met0->t, met1, met1->t, tt, press, lon, lat, &c, 1);
+    int mi = idx[ip];
+    if (ctl->nens > 0) mi += (int)atm->q[(size_t)ctl->qnt_ens * st + ip] * ngrid;
+    atm->q[(size_t)ctl->qnt_Cx * st + ip] = C_MA / ctl->molmass * mass[mi] / ((100. * press / (C_RA * temp)) * area * dz * 1e9);
+  }
+  free(mass);
+  free(idx);
+}
+
 /* module_decay, 4227-4263 (and the reset of the total loss rate that precedes it, 7931-7936) */
 void orc_module_decay(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm) {
   const size_t st = (size_t)atm->q_stride;
@@ -1122,5 +1165,6 @@ void orc_run_timestep(const orc_ctl_t *ctl, const orc_clim_t *clim, const orc_me
   if (ctl->tdec_trop > 0 && ctl->tdec_strat > 0) orc_module_decay(ctl, clim, atm);   /* 7938-7940 */
   if (ctl->mixing_trop >= 0 && ctl->mixing_strat >= 0 && (ctl->mixing_dt <= 0 || fmod(t, ctl->mixing_dt) == 0))
     orc_module_mixing(ctl, clim, atm, t);
+  if (ctl->chemgrid) orc_module_chem_grid(ctl, met0, met1, atm, t);   /* 7947-7950 */
   if (bound) orc_module_bound_cond(ctl, g_cts, met0, met1, atm);    /* 7997-8000 */
 }

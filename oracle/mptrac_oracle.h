@@ -58,6 +58,11 @@ typedef struct {
   int32_t bound_pbl, qnt_aoa;
   int32_t qnt_cts[5];                   /* qnt_Cccl4, qnt_Cccl3f, qnt_Cccl2f2, qnt_Cn2o, qnt_Csf6 */
   int32_t cts_on;                       /* bit i: the control file names a time series for species i (not "-") */
+  /* module_chem_grid (src/mptrac.c:3885-4054) */
+  double chemgrid_lon0, chemgrid_lon1, chemgrid_lat0, chemgrid_lat1, chemgrid_z0, chemgrid_z1, molmass;
+  int32_t chemgrid_nx, chemgrid_ny, chemgrid_nz, qnt_Cx;
+  int32_t chemgrid;                     /* the dispatcher's condition (oh / h2o2 / kpp chemistry on), 7947-7950 */
+  int32_t _pad3;
 } orc_ctl_t;
 
 #define ORC_NCTS 5
@@ -117,6 +122,7 @@ void orc_module_diff_pbl(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_
 void orc_module_convection(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm, uint64_t *ctr);
 void orc_module_decay(const orc_ctl_t *ctl, const orc_clim_t *clim, orc_atm_t *atm);
 void orc_module_bound_cond(const orc_ctl_t *ctl, const orc_cts_t *cts, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
+void orc_module_chem_grid(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm, double t);
 void orc_set_cts(const orc_cts_t *cts);   /* the series orc_run_timestep's boundary conditions use (NULL = none) */
 void orc_module_isosurf_init(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);
 void orc_module_isosurf(const orc_ctl_t *ctl, const orc_met_t *met0, const orc_met_t *met1, orc_atm_t *atm);

@@ -36,6 +36,10 @@ _BOUND_DBL = ("bound_mass", "bound_mass_trend", "bound_vmr", "bound_vmr_trend", 
               "bound_dps", "bound_dzs", "bound_zetas")
 _BOUND_DEFAULT = dict(bound_mass=-999.0, bound_mass_trend=0.0, bound_vmr=-999.0, bound_vmr_trend=0.0, bound_lat0=-999.0, bound_lat1=-999.0,
                       bound_p0=-999.0, bound_p1=-999.0, bound_dps=-999.0, bound_dzs=-999.0, bound_zetas=-999.0)
+_CHEM_DBL = ("chemgrid_lon0", "chemgrid_lon1", "chemgrid_lat0", "chemgrid_lat1", "chemgrid_z0", "chemgrid_z1", "molmass")
+_CHEM_INT = ("chemgrid_nx", "chemgrid_ny", "chemgrid_nz", "qnt_Cx", "chemgrid")
+_CHEM_DEFAULT = dict(chemgrid_lon0=-180.0, chemgrid_lon1=180.0, chemgrid_lat0=-90.0, chemgrid_lat1=90.0, chemgrid_z0=-5.0, chemgrid_z1=85.0,
+                     molmass=-999.0, chemgrid_nx=360, chemgrid_ny=180, chemgrid_nz=90, qnt_Cx=-1, chemgrid=0)
 CTS_SPECIES = ("Cccl4", "Cccl3f", "Cccl2f2", "Cn2o", "Csf6")
 
 
@@ -72,7 +76,8 @@ class OrcCtl(C.Structure):
                 + [("qnt_zeta", C.c_int32), ("qnt_eta", C.c_int32)]
                 + [(n, C.c_double) for n in _TAIL_DBL] + [(n, C.c_int32) for n in _TAIL_INT]
                 + [(n, C.c_double) for n in _BOUND_DBL] + [("bound_pbl", C.c_int32), ("qnt_aoa", C.c_int32),
-                                                          ("qnt_cts", C.c_int32 * 5), ("cts_on", C.c_int32)])
+                                                          ("qnt_cts", C.c_int32 * 5), ("cts_on", C.c_int32)]
+                + [(n, C.c_double) for n in _CHEM_DBL] + [(n, C.c_int32) for n in _CHEM_INT] + [("_pad3", C.c_int32)])
 
 
 _LEVEL_FIELDS = ("pl", "ul", "vl", "wl", "zetal", "zeta_dotl")   # model-level fields, [nx][ny][npl]
@@ -140,6 +145,12 @@ def ctl_struct(ctl) -> OrcCtl:
         qc = [-1] * 5
     for k in range(5):
         s.qnt_cts[k] = int(qc[k])
+    for n in _CHEM_DBL + _CHEM_INT:
+        try:
+            v = get(n)
+        except (KeyError, AttributeError):
+            v = _CHEM_DEFAULT[n]
+        setattr(s, n, float(v) if n in _CHEM_DBL else int(v))
     return s
 
 
@@ -316,6 +327,8 @@ class Oracle:
             L.orc_module_convection(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a), C.byref(ctr))
         elif what == "decay":
             L.orc_module_decay(C.byref(c), C.byref(cl), C.byref(a))
+        elif what == "chem_grid":
+            L.orc_module_chem_grid(C.byref(c), C.byref(m0), C.byref(m1), C.byref(a), C.c_double(t))
         elif what == "bound_cond":
             L.orc_module_bound_cond(C.byref(c), C.byref(self._cts[0]), C.byref(m0), C.byref(m1), C.byref(a))
         elif what == "diff_pbl":
@@ -349,7 +362,7 @@ class Oracle:
 
 
 _WHAT = {"timestep": 0, "timesteps": 1, "position": 2, "advect": 3, "diff_turb": 4, "diff_meso": 5, "sedi": 6,
-         "sort": 7, "mixing": 8, "meteo": 9, "advect_init": 10, "convection": 11, "decay": 12, "isosurf_init": 13, "isosurf": 14, "diff_pbl": 15, "bound_cond": 16}
+         "sort": 7, "mixing": 8, "meteo": 9, "advect_init": 10, "convection": 11, "decay": 12, "isosurf_init": 13, "isosurf": 14, "diff_pbl": 15, "bound_cond": 16, "chem_grid": 17}
 
 
 def reference_available() -> bool:
@@ -382,11 +395,11 @@ class Reference:
         return dict(zip(("EX", "EY", "EP", "NP", "NQ"), (x.value for x in v)))
 
     def read_ctl(self, qnt_names=(), overrides=""):
-        out = (C.c_int * 80)()
+        out = (C.c_int * 81)()
         nq = self.L.ref_read_ctl(",".join(qnt_names).encode(), overrides.encode(), out)
         self.qnt = dict(zip(("rp", "rhop", "m", "vmr", "ens"), list(out)[:5]))
         self.qnt["zeta"], self.qnt["eta"], self.qnt["mloss_decay"], self.qnt["loss_rate"] = out[70], out[71], out[72], out[73]
-        self.qnt["aoa"] = out[74]
+        self.qnt["aoa"], self.qnt["Cx"] = out[74], out[80]
         self.qnt["cts"] = [out[75 + k] for k in range(5)]
         self.qnt_meteo = {n: i for n, i in zip(METEO_QNT, list(out)[5:5 + len(METEO_QNT)]) if i >= 0}   # name -> index the reference assigned
         return nq

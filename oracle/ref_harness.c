@@ -34,7 +34,7 @@ static void ensure_alloc(void) {
 
 /* Reference defaults + quantity names (comma separated) + "KEY VALUE" overrides (space separated).
  * Returns the quantity index the reference assigned to `rp`, `rhop`, `m`, `vmr`, `ens` and the 14 module_meteo
- * quantities (slot order of orc_ctl_t::qnt_meteo, out[5..68]) and `zeta`, `eta`, `mloss_decay`, `loss_rate`, `aoa`, `Cccl4`, `Cccl3f`, `Cccl2f2`, `Cn2o`, `Csf6` (out[70..79]); out holds 80 ints. */
+ * quantities (slot order of orc_ctl_t::qnt_meteo, out[5..68]) and `zeta`, `eta`, `mloss_decay`, `loss_rate`, `aoa`, `Cccl4`, `Cccl3f`, `Cccl2f2`, `Cn2o`, `Csf6`, `Cx` (out[70..80]); out holds 81 ints. */
 int ref_read_ctl(const char *qnt_names, const char *overrides, int *out) {
   ensure_alloc();
   static char buf[8192];
@@ -91,7 +91,7 @@ int ref_read_ctl(const char *qnt_names, const char *overrides, int *out) {
     out[70] = h_ctl->qnt_zeta; out[71] = h_ctl->qnt_eta;
     out[72] = h_ctl->qnt_mloss_decay; out[73] = h_ctl->qnt_loss_rate;
     out[74] = h_ctl->qnt_aoa; out[75] = h_ctl->qnt_Cccl4; out[76] = h_ctl->qnt_Cccl3f; out[77] = h_ctl->qnt_Cccl2f2;
-    out[78] = h_ctl->qnt_Cn2o; out[79] = h_ctl->qnt_Csf6;
+    out[78] = h_ctl->qnt_Cn2o; out[79] = h_ctl->qnt_Csf6; out[80] = h_ctl->qnt_Cx;
   }
   return h_ctl->nq;
 }
@@ -187,6 +187,10 @@ static void apply_ctl(const orc_ctl_t *c) {
   h_ctl->bound_vmr_trend = c->bound_vmr_trend; h_ctl->bound_lat0 = c->bound_lat0; h_ctl->bound_lat1 = c->bound_lat1;
   h_ctl->bound_p0 = c->bound_p0; h_ctl->bound_p1 = c->bound_p1; h_ctl->bound_dps = c->bound_dps; h_ctl->bound_dzs = c->bound_dzs;
   h_ctl->bound_zetas = c->bound_zetas; h_ctl->bound_pbl = c->bound_pbl;
+  h_ctl->chemgrid_lon0 = c->chemgrid_lon0; h_ctl->chemgrid_lon1 = c->chemgrid_lon1; h_ctl->chemgrid_lat0 = c->chemgrid_lat0;
+  h_ctl->chemgrid_lat1 = c->chemgrid_lat1; h_ctl->chemgrid_z0 = c->chemgrid_z0; h_ctl->chemgrid_z1 = c->chemgrid_z1;
+  h_ctl->chemgrid_nx = c->chemgrid_nx; h_ctl->chemgrid_ny = c->chemgrid_ny; h_ctl->chemgrid_nz = c->chemgrid_nz;
+  h_ctl->molmass = c->molmass;
   char *names[5] = {h_ctl->clim_ccl4_timeseries, h_ctl->clim_ccl3f_timeseries, h_ctl->clim_ccl2f2_timeseries,
                     h_ctl->clim_n2o_timeseries, h_ctl->clim_sf6_timeseries};
   for (int k = 0; k < 5; k++) strcpy(names[k], (c->cts_on >> k & 1) ? "given" : "-");
@@ -255,6 +259,7 @@ int ref_run(const orc_ctl_t *ctl, orc_atm_t *atm, double t, int what, int nsteps
     case 10: module_advect_init(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     case 11: module_convection(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     case 12: module_decay(h_ctl, h_cache, h_clim, h_atm); break;
+    case 17: module_chem_grid(h_ctl, h_met0, h_met1, h_atm, t); break;
     case 16: module_bound_cond(h_ctl, h_cache, h_clim, h_met0, h_met1, h_atm); break;
     case 15: module_diff_pbl(h_ctl, h_cache, h_met0, h_met1, h_atm); break;
     case 13: module_isosurf_init(h_ctl, h_cache, h_met0, h_met1, h_atm); break;

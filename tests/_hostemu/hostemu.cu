@@ -308,3 +308,23 @@ extern "C" int emu_bound_applies(const EmuMet *m0, const EmuMet *m1, const doubl
   return 0;
 }
 extern "C" double emu_series_at(const double *tm, const double *v, int n, double t) { return series_at(tm, v, n, t); }
+
+// module_chem_grid with the box masses summed in parcel order (the device sums them with atomics)
+extern "C" int emu_chem_grid(const EmuMet *m0, const EmuMet *m1, const double *k13, int nx, int ny, int nz, int nens, long long np,
+                             const double *time, const double *lon, const double *lat, const double *p, const double *m,
+                             const double *ens, double *cx) {
+  HostMet h;
+  make_view(h, m0, m1, true);
+  ChemGrid k = {k13[0], k13[1], k13[2], k13[3], k13[4], k13[5], k13[6], k13[7], k13[8], k13[9], k13[10], k13[11], k13[12], nx, ny, nz};
+  const int ngrid = nx * ny * nz;
+  std::vector<double> mass((size_t)ngrid * (nens > 0 ? nens : 1), 0.0);
+  std::vector<int> box((size_t)np);
+  for (long long ip = 0; ip < np; ip++) {
+    box[ip] = chem_box(k, time[ip], lon[ip], lat[ip], p[ip]);
+    if (box[ip] >= 0) mass[box[ip] + (nens > 0 ? (int)ens[ip] * ngrid : 0)] += m[ip];
+  }
+#pragma omp parallel for
+  for (long long ip = 0; ip < np; ip++)
+    if (box[ip] >= 0) cx[ip] = chem_vmr(h.g, k, box[ip], mass[box[ip] + (nens > 0 ? (int)ens[ip] * ngrid : 0)]);
+  return 0;
+}

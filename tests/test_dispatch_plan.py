@@ -85,3 +85,9 @@ def test_isosurf_init_only_for_the_modes_that_compute_it(isosurf):
     want = [step(4, 0, TS | STORE | PRE), "isosurf", step(0, 0, POST)]
     assert plan_modules(c, 300.0) == " ".join(want)
     assert plan_modules(c, 0.0) == " ".join((["isosurf_init"] if isosurf != 4 else []) + want)
+
+
+def test_chem_grid_follows_mixing():
+    c = Ctl(advect=4, nq=2, qnt_m=0, qnt_Cx=1, molmass=64.0, chemgrid=1, mixing_trop=1e-3, mixing_strat=1e-6, mixing_dt=300.0, mix_qnt=[0],
+            bound_lat0=-90.0, bound_lat1=90.0, bound_p0=1e10, bound_p1=-1e10, **BASE)
+    assert plan_modules(c, 300.0) == " ".join([step(4, 0, TS | STORE | PRE | POST), "bound_cond", "mixing", "chem_grid", "bound_cond"])

@@ -289,3 +289,29 @@ def test_module_bound_cond_on_host_is_bit_exact(emu, oracle, layer):
     ts, v = series["Cccl3f"]
     got = np.array([emu.emu_series_at(ts.ctypes.data, v.ctypes.data, ts.size, float(t)) for t in a.time[hit == 1]])
     assert np.array_equal(got, a.q[1][hit == 1])
+
+
+@pytest.mark.parametrize("nens", [0, 3])
+def test_module_chem_grid_on_host_is_bit_exact(emu, oracle, nens):
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels, met_struct
+    m0, m1 = synth.make_met_pair(36, 19, 20, t0=0.0, dt_met=21600.0)
+    n = 20000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.0, zmax=30.0, seed=41)
+    tm = tm + np.random.default_rng(2).choice([0.0, 0.0, 0.0, 400.0], n)
+    rng = np.random.default_rng(3)
+    q = np.zeros((3, n))
+    q[0], q[2] = rng.uniform(0.5, 2.0, n), rng.integers(0, 3, n)
+    ctl = Ctl(nq=3, advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, qnt_m=0, qnt_Cx=1, qnt_ens=2, nens=nens, molmass=64.07,
+              chemgrid_nx=36, chemgrid_ny=18, chemgrid_nz=15, chemgrid_z0=0.0, chemgrid_z1=30.0, chemgrid=1)
+    b = Parcels(tm, p, lon, lat, q)
+    oracle.run("chem_grid", ctl, synth.make_clim_tropo(), m0, m1, b, t=0.0)
+    dlon, dlat, dz = 360.0 / 36, 180.0 / 18, 30.0 / 15
+    k13 = np.array([-180.0, 180.0, -90.0, 90.0, 0.0, 30.0, dlon, dlat, dz, -150.0, 150.0, 0.0, 64.07])
+    cx = np.zeros(n)
+    s0, s1 = met_struct(m0), met_struct(m1)
+    vp = lambda x: C.c_void_p(x.ctypes.data)  # noqa: E731
+    m, ens = np.ascontiguousarray(q[0]), np.ascontiguousarray(q[2])
+    assert emu.emu_chem_grid(C.byref(s0), C.byref(s1), vp(k13), 36, 18, 15, nens, C.c_longlong(n), vp(tm), vp(lon), vp(lat), vp(p),
+                             vp(m), vp(ens), vp(cx)) == 0
+    assert np.array_equal(cx, b.q[1]) and 0.5 < np.mean(cx > 0) < 0.9

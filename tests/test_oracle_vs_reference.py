@@ -423,3 +423,31 @@ def test_module_bound_cond_bit_exact(oracle, reference, layer):
     reference.run("timestep", ctl, a, t=0.0, nsteps=4)
     oracle.run("timestep", ctl, clim, m0, m1, b, t=0.0, nsteps=4)
     assert _same(a, b)
+
+
+@pytest.mark.parametrize("nens", [0, 3])
+def test_module_chem_grid_bit_exact(oracle, reference, nens):
+    """module_chem_grid (src/mptrac.c:3885-4054): box masses summed in parcel order, volume mixing ratio at the temperature of
+    the box centre, with and without ensembles"""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    m0, m1 = synth.make_met_pair(36, 19, 20, t0=0.0, dt_met=21600.0)
+    n = 20000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.0, zmax=30.0, seed=41)
+    tm = tm + np.random.default_rng(2).choice([0.0, 0.0, 0.0, 400.0], n)     # some parcels outside the time window
+    nq = reference.read_ctl(["m", "Cx", "ens"], "MOLMASS 64.07")
+    qi = reference.qnt
+    reference.set_met(m0, m1)
+    clim = reference.clim_tropo()
+    rng = np.random.default_rng(3)
+    q = np.zeros((nq, n))
+    q[qi["m"]] = rng.uniform(0.5, 2.0, n)
+    q[qi["ens"]] = rng.integers(0, 3, n)
+    ctl = Ctl(nq=nq, advect=4, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, qnt_m=qi["m"], qnt_Cx=qi["Cx"], qnt_ens=qi["ens"],
+              nens=nens, molmass=64.07, chemgrid_nx=36, chemgrid_ny=18, chemgrid_nz=15, chemgrid_z0=0.0, chemgrid_z1=30.0, chemgrid=1)
+    a = Parcels(tm, p, lon, lat, q)
+    b = a.copy()
+    reference.run("chem_grid", ctl, a, t=0.0)
+    oracle.run("chem_grid", ctl, clim, m0, m1, b, t=0.0)
+    assert _same(a, b)
+    assert 0.5 < np.mean(a.q[qi["Cx"]] > 0) < 0.9
