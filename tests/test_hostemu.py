@@ -315,3 +315,35 @@ def test_module_chem_grid_on_host_is_bit_exact(emu, oracle, nens):
     assert emu.emu_chem_grid(C.byref(s0), C.byref(s1), vp(k13), 36, 18, 15, nens, C.c_longlong(n), vp(tm), vp(lon), vp(lat), vp(p),
                              vp(m), vp(ens), vp(cx)) == 0
     assert np.array_equal(cx, b.q[1]) and 0.5 < np.mean(cx > 0) < 0.9
+
+
+def test_model_level_advection_fuzz_on_host(emu, oracle):
+    """many small cases (level counts, grids, latitude order, coordinates, integrators) with parcels exactly on level
+    pressures and beyond both ends of the columns: the verified-hint level search must give the bisection's answer"""
+    import itertools
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels, met_struct
+    vp = lambda x: C.c_void_p(x.ctypes.data)  # noqa: E731
+    clim = synth.make_clim_tropo()
+    for seed, npl, vc, adv, desc in itertools.product(range(2), (8, 61), (1, 2, 3), (2, 4), (False, True)):
+        m0, m1 = synth.make_met_pair(24, 13, 10, t0=0.0, dt_met=21600.0, lat_descending=desc)
+        m0, m1 = synth.add_model_levels(m0, npl=npl, seed=seed), synth.add_model_levels(m1, npl=npl, seed=seed + 100)
+        n = 800
+        tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.0, zmax=62.0, seed=seed)
+        p[:50] = m0.pl[3, 4, np.random.default_rng(seed).integers(0, npl, 50)]
+        p[50:60], p[60:70] = 1200.0, 0.05
+        q = np.random.default_rng(seed).uniform(200.0, 2200.0, (1, n))
+        ctl = Ctl(nq=1, advect=adv, advect_vert_coord=vc, t_start=0.0, t_stop=1e6, dt_mod=600.0, dt_met=21600.0,
+                  qnt_zeta=0 if vc == 1 else -1, qnt_eta=0 if vc == 3 else -1)
+        a = Parcels(tm, p, lon, lat, q)
+        oracle.run("timesteps", ctl, clim, m0, m1, a, t=600.0)
+        b = a.copy()
+        s0, s1 = met_struct(m0), met_struct(m1)
+        for _ in range(4):
+            oracle.run("advect", ctl, clim, m0, m1, b, t=0.0)
+            zq = vp(a.q[0]) if vc != 2 else None
+            assert emu.emu_advect_levels(C.byref(s0), C.byref(s1), vc, adv, C.c_longlong(n), vp(a.time), vp(a.lon), vp(a.lat), vp(a.p),
+                                         vp(a.dt), zq) == 0
+            a.time[:] = b.time[:] = 0.0       # stay inside the met interval
+        for k in ("lon", "lat", "p", "q"):
+            assert np.array_equal(getattr(a, k), getattr(b, k), equal_nan=True), (seed, npl, vc, adv, desc, k)
