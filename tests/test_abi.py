@@ -85,3 +85,21 @@ def test_product_does_not_import_oracle():
         if f.suffix in (".py", ".cu", ".cuh", ".c", ".h") and f.is_file():
             txt = f.read_text()
             assert "oracle" not in txt.replace("oracle/_ref", "").replace("oracle\" / \"_ref", "") or f.name == "build.py", f
+
+
+def test_shim_defines_exactly_the_reference_symbols_it_replaces():
+    """libmptrac_b200_shim.so (built where the reference's mptrac.h is available) interposes four symbols of the reference
+     and nothing else, and resolves the C ABI from libmptrac_b200.so next to it"""
+    import shutil
+    import subprocess
+    shim = ROOT / "mptrac_b200" / "_lib" / "libmptrac_b200_shim.so"
+    if not shim.exists() or shutil.which("nm") is None:
+        pytest.skip("shim not built on this machine (needs the reference's mptrac.h)")
+    out = subprocess.run(["nm", "-D", str(shim)], check=True, capture_output=True, text=True).stdout
+    defined = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert defined == {"mptrac_free", "mptrac_run_timestep", "mptrac_update_device", "mptrac_update_host"}
+    undefined = {ln.split()[-1] for ln in out.splitlines() if " U " in ln}
+    used = {s for s in undefined if s.startswith("mpb_")}
+    assert used and used <= set(header_symbols())
+    # the reference modules it delegates to in hybrid mode come from the reference's own library at run time
+    assert {"module_diff_pbl", "module_convection", "module_isosurf", "module_meteo", "module_bound_cond", "module_decay"} <= undefined
