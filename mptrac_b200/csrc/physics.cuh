@@ -16,6 +16,9 @@
 #include <cuda_runtime.h>
 
 #define MPB_HD __host__ __device__ __forceinline__
+#ifndef MPB_LEVEL_CACHE
+#define MPB_LEVEL_CACHE 0   // model-level advection: keep the 8 level records across Runge-Kutta stages (see locate_on_levels)
+#endif
 // rarely executed paths are kept out of line so that they cost neither registers nor instruction-cache lines on the hot path
 #define MPB_COLD __host__ __device__ __noinline__
 
@@ -880,7 +883,8 @@ MPB_HD double level_height(const LevelStencil<L> &s, const typename L::Rec (&r)[
 // guess fails takes the reference's path literally.  Answers are identical, the dependent load rounds drop from ~16 to 3.
 template <class L>
 MPB_HD void locate_on_levels(const MetView &g, const L &lv, double ts, double height, double lon, double lat, LevelStencil<L> &s,
-                             int *hint = nullptr /* [2]: first-column levels of the previous lookup, -1 = none */) {
+                             int *hint = nullptr /* [2]: first-column levels of the previous lookup, -1 = none */,
+                             bool cached = false /* s holds the stencil of the previous lookup (s.iz < 0: nothing) */) {
   double lon2, lat2;
   clamp_horizontal(g, lon, lat, lon2, lat2);
   const int ix = lon_interval(g, lon2);
@@ -888,11 +892,38 @@ MPB_HD void locate_on_levels(const MetView &g, const L &lv, double ts, double he
   const int iy = locate_cell(g.lat, g.latc, g.ny, g.lat_asc, lat2, lat_guess(g, lat2), cy);
   const int n = g.npl;
   const size_t npl = (size_t)n, sx = (size_t)g.ny * npl;
+  const AxisCell cx = load_cell(g.lonc + ix);
+#if MPB_LEVEL_CACHE
+  // Record cache (build flag, off by default until it has been measured): the stencil `s` of the previous Runge-Kutta
+  // stage is still valid when the parcel is in the same four columns and every (column, time) pair still brackets
+  // `height` at level s.iz -- the first column by the bisection's end condition (level_hint_holds), the others by the
+  // reference's guess test (level_guess_holds) --, because then all eight column searches answer s.iz, the minimum and
+  // the maximum coincide and the walk does not move.  Only the weights change: no load at all.
+  if (cached && s.iz >= 0 && s.col[0] == (size_t)ix * sx + (size_t)iy * npl) {
+    bool same = true;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      same = same && level_hint_holds(L::h(s.lo[0], t), L::h(s.hi[0], t), s.iz, n, height);
+#pragma unroll
+      for (int j = 1; j < 4; j++) same = same && level_guess_holds(L::h(s.lo[j], t), L::h(s.hi[j], t), height);
+    }
+    if (same) {
+      if (hint) { hint[0] = s.iz; hint[1] = s.iz; }
+      s.wt = (ts - g.t0) / (g.t1 - g.t0);
+      s.wx = (lon2 - cx.lo) / (cx.hi - cx.lo);
+      s.wy = (lat2 - cy.lo) / (cy.hi - cy.lo);
+      const double bot = level_height<L>(s, s.lo), top = level_height<L>(s, s.hi);
+      s.wz = (height - bot) / (top - bot);
+      return;
+    }
+  }
+#else
+  (void)cached;
+#endif
   s.col[0] = (size_t)ix * sx + (size_t)iy * npl;
   s.col[1] = s.col[0] + npl;
   s.col[2] = s.col[0] + sx;
   s.col[3] = s.col[2] + npl;
-  const AxisCell cx = load_cell(g.lonc + ix);
   const float f0 = lv.height(0, 0), f1 = lv.height(1, 0);          // heights0[0][0][0] vs [0][0][1], 2914-2921
 
   // round 1: first column, guess 0 and the hint, both time levels
@@ -966,10 +997,11 @@ MPB_HD double combine_levels(const LevelStencil<L> &s, const double (&v)[4][2]) 
 
 // u, v and the vertical velocity on model levels: three intpol_met_4d_zeta calls sharing one stencil (3646-3657, 3714-3722)
 MPB_HD void wind_on_levels(const MetView &g, const LevelNode *f, double ts, double height, double lon, double lat,
-                           double &u, double &v, double &w, int *hint = nullptr) {
+                           double &u, double &v, double &w, int *hint = nullptr, LevelStencil<WindLevels> *keep = nullptr) {
   const WindLevels lv = {f};
-  LevelStencil<WindLevels> s;
-  locate_on_levels(g, lv, ts, height, lon, lat, s, hint);
+  LevelStencil<WindLevels> local;
+  LevelStencil<WindLevels> &s = keep ? *keep : local;
+  locate_on_levels(g, lv, ts, height, lon, lat, s, hint, keep != nullptr);
   double a[4][2], b[4][2], c[4][2];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
@@ -1011,6 +1043,10 @@ MPB_HD void advect_on_levels(const MetView &g, int vert_coord, double dt, Parcel
   double um = 0, vm = 0, wm = 0, u = 0, v = 0, w = 0, lat_stage = a.lat;
   int hint[2] = {-1, -1};
   if (level_hint && *level_hint >= 0 && *level_hint <= g.npl - 2) hint[0] = *level_hint;
+#if MPB_LEVEL_CACHE
+  LevelStencil<WindLevels> kept;
+  kept.iz = -1;
+#endif
   // (a rolled stage loop: unrolled, the RK4 kernel is 9 400 instructions = 150 KB and stalls on instruction fetch --
   // ncu r01h: "no instruction" 5.8 stall cycles per issue)
 #pragma unroll 1
@@ -1025,7 +1061,11 @@ MPB_HD void advect_on_levels(const MetView &g, int vert_coord, double dt, Parcel
       z = z0 + dts * w;
     }
     lat_stage = y;
+#if MPB_LEVEL_CACHE
+    wind_on_levels(g, f, a.time + dts, z, x, y, u, v, w, hint, &kept);
+#else
     wind_on_levels(g, f, a.time + dts, z, x, y, u, v, w, hint);
+#endif
     double k = 1.0;
     if (ORDER == 2) k = (i == 0 ? 0.0 : 1.0);
     else if (ORDER == 4) k = (i == 0 || i == 3 ? 1.0 / 6.0 : 2.0 / 6.0);

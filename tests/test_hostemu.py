@@ -20,15 +20,17 @@ class EmuCtl(C.Structure):
                 + [(n, C.c_int) for n in "direction pbl_scheme advect phys".split()] + [("modules", C.c_uint)])
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["cube_f32", "cube_f64"])
+@pytest.fixture(scope="module", params=[(0, 0), (1, 0), (0, 1)], ids=["cube_f32", "cube_f64", "level_cache"])
 def emu(request):
-    """Both cube flavours of the step kernel (build flag MPB_CUBE_F64) must state the same arithmetic."""
+    """Every build flavour of the device physics must state the same arithmetic: both cubes of the step kernel (build flag
+    MPB_CUBE_F64) and the record cache of the model-level advection (MPB_LEVEL_CACHE, off in the shipped library)."""
     if shutil.which("nvcc") is None:
         pytest.skip("nvcc not available")
-    so = EMU_DIR / f"hostemu_{request.param}.so"
+    cube, cache = request.param
+    so = EMU_DIR / (f"hostemu_{cube}.so" if not cache else f"hostemu_{cube}_cache.so")
     src = [EMU_DIR / "hostemu.cu", ROOT / "mptrac_b200" / "csrc" / "physics.cuh", ROOT / "mptrac_b200" / "csrc" / "met_tables.hpp"]
     if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in src):
-        subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", f"-DMPB_CUBE_F64={request.param}",
+        subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", f"-DMPB_CUBE_F64={cube}", f"-DMPB_LEVEL_CACHE={cache}",
                         "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off", "-shared", str(src[0]), "-o", str(so)], check=True)
     return C.CDLL(str(so))
 
