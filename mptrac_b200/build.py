@@ -59,10 +59,17 @@ def build_shim(force: bool = False):
     if not (src.exists() and hdr.exists() and deps_inc.exists()):
         return None
     build_lib()
-    if force or _stale(SHIM, [src, hdr, ROOT / "include" / "mptrac_b200.h"]):
-        _run(["gcc", "-O2", "-g", "-fPIC", "-shared", "-fshort-enums", "-fopenmp", "-DHAVE_INLINE",
+    # the shim reads and writes the driver's atm_t / cache_t / met_t in place: it must see the dimensions (-DNP, -DNQ, -DEX,
+    # -DEY, -DEP) the reference library was compiled with (its build recipe takes them from the same variable); the shim
+    # also checks the layout at run time against the symbol mptrac_ref_layout when the library in front of it exports one
+    defines = os.environ.get("MPTRAC_DEFINES", "").split()
+    stamp = LIBDIR / ".shim_defines"
+    same_defines = stamp.exists() and stamp.read_text() == " ".join(defines)
+    if force or not same_defines or _stale(SHIM, [src, hdr, ROOT / "include" / "mptrac_b200.h"]):
+        _run(["gcc", "-O2", "-g", "-fPIC", "-shared", "-fshort-enums", "-fopenmp", "-DHAVE_INLINE", *defines,
               f"-I{REFERENCE / 'src'}", f"-I{deps_inc}", f"-I{ROOT / 'include'}", src,
               f"-L{LIBDIR}", "-lmptrac_b200", "-Wl,-rpath,$ORIGIN", "-ldl", "-o", SHIM])
+        stamp.write_text(" ".join(defines))
     return SHIM
 
 

@@ -39,35 +39,66 @@ static int verbose(void) {
   return g_verbose;
 }
 
-static void ensure_ctx(const ctl_t *ctl, int np) {
-  if (g_ctx && np <= g_np) return;
-  if (g_ctx) MPB(mpb_destroy(g_ctx));
+/* The reference draws every random number of a process from ONE file-static counter (rng_ctr, src/mptrac.c:35) that
+ * keeps counting across the directories of a `trac` dirlist (mptrac_free / mptrac_alloc per directory, src/trac.c:98-185).
+ * The device counter lives in the context, so it is carried over here whenever a context ends. */
+static unsigned long long g_rng_ctr;
+static const clim_t *g_last_clim;      /* last climatology / cache handed to mptrac_update_device: a re-created context */
+static const cache_t *g_last_cache;    /* (more parcels than before) gets them again */
+
+/* The shim reads and writes the driver's structs in place, so it must have been compiled with the dimensions of the
+ * library behind it.  A libmptrac.so that exports `const long mptrac_ref_layout[8]` = {NP, NQ, EX, EY, EP, sizeof(atm_t),
+ * sizeof(met_t), sizeof(cache_t)} (one extra translation unit) is verified here; one without the symbol
+ * cannot be checked: build both with the same -DNP/-DNQ/-DEX/-DEY/-DEP. */
+static void check_layout(void) {
+  static int done;
+  if (done) return;
+  done = 1;
+  const long *ref = (const long *) dlsym(RTLD_DEFAULT, "mptrac_ref_layout");
+  if (!ref) {
+    if (verbose()) printf("mptrac_b200: the library behind the shim does not export mptrac_ref_layout: struct layout unchecked\n");
+    return;
+  }
+  const long mine[8] = {(long) NP, (long) NQ, (long) EX, (long) EY, (long) EP, (long) sizeof(atm_t), (long) sizeof(met_t), (long) sizeof(cache_t)};
+  const char *what[8] = {"NP", "NQ", "EX", "EY", "EP", "sizeof(atm_t)", "sizeof(met_t)", "sizeof(cache_t)"};
+  for (int i = 0; i < 8; i++)
+    if (ref[i] != mine[i])
+      ERRMSG("mptrac_b200: shim compiled with %s = %ld, libmptrac with %ld -- rebuild both with the same MPTRAC_DEFINES", what[i], mine[i], ref[i]);
+}
+
+/* returns 1 when a context was (re-)created */
+static int ensure_ctx(const ctl_t *ctl, int np) {
+  if (g_ctx && np <= g_np) return 0;
+  check_layout();
+  if (g_ctx) { g_rng_ctr = mpb_get_rng_ctr(g_ctx); MPB(mpb_destroy(g_ctx)); }
   int dev = 0;
   const char *e = getenv("MPTRAC_B200_DEVICE");
   if (e) dev = atoi(e);
   MPB(mpb_create(&g_ctx, dev, np, ctl->nq));
+  MPB(mpb_set_rng_ctr(g_ctx, g_rng_ctr));
   g_slot[0] = g_slot[1] = NULL;
   g_np = np;
   if (verbose()) printf("mptrac_b200: device context for %d parcels, %d quantities on GPU %d\n", np, ctl->nq, dev);
+  return 1;
 }
 
-/* MPTRAC_B200_DEVICE_METEO_FIELDS=1: module_meteo quantities that read further met fields (zg, pv, h2o, o3, cloud and
- * surface fields, rh ...) are computed on the device too; the fields they need are uploaded with each met level.  Off by
- * default in this version: the device code is pinned on the host (tests/test_hostemu.py), its GPU parity run is pending. */
+/* module_meteo quantities that read further met fields (zg, pv, h2o, o3, cloud and surface fields, rh ...) are computed on
+ * the device too; the fields they need are uploaded with each met level.  MPTRAC_B200_DEVICE_METEO_FIELDS=0 keeps them on
+ * the reference's CPU code (hybrid mode: a parcel round trip per step). */
 static int device_meteo_fields(void) {
   static int on = -1;
-  if (on < 0) on = getenv("MPTRAC_B200_DEVICE_METEO_FIELDS") ? atoi(getenv("MPTRAC_B200_DEVICE_METEO_FIELDS")) : 0;
+  if (on < 0) on = getenv("MPTRAC_B200_DEVICE_METEO_FIELDS") ? atoi(getenv("MPTRAC_B200_DEVICE_METEO_FIELDS")) : 1;
   return on;
 }
 static int g_fields, g_need2[MPB_NX2], g_need3[MPB_NX3];
 static int meteo_needs_host(const ctl_t *c);
 
-/* MPTRAC_B200_DEVICE_MODULES=1: module_diff_pbl, module_convection, module_isosurf and -- when nothing else keeps the tail
- * of the step on the host -- module_bound_cond and module_decay run on the device at their places in the dispatcher
- * instead of the reference's CPU code.  Off by default for the same reason as MPTRAC_B200_DEVICE_METEO_FIELDS. */
+/* module_diff_pbl, module_convection, module_isosurf and -- when nothing else keeps the tail of the step on the host --
+ * module_bound_cond and module_decay run on the device at their places in the dispatcher.  MPTRAC_B200_DEVICE_MODULES=0
+ * delegates them to the reference's CPU code instead (hybrid mode). */
 static int device_modules(void) {
   static int on = -1;
-  if (on < 0) on = getenv("MPTRAC_B200_DEVICE_MODULES") ? atoi(getenv("MPTRAC_B200_DEVICE_MODULES")) : 0;
+  if (on < 0) on = getenv("MPTRAC_B200_DEVICE_MODULES") ? atoi(getenv("MPTRAC_B200_DEVICE_MODULES")) : 1;
   return on;
 }
 
@@ -111,8 +142,7 @@ static void put_ctl(const ctl_t *c) {
   k.qnt_meteo[MPB_Q_VZ] = c->qnt_vz; k.qnt_meteo[MPB_Q_THETA] = c->qnt_theta; k.qnt_meteo[MPB_Q_PSAT] = c->qnt_psat;
   k.qnt_meteo[MPB_Q_PSICE] = c->qnt_psice; k.qnt_meteo[MPB_Q_ZETA_D] = c->qnt_zeta_d;
   k.qnt_zeta = c->qnt_zeta; k.qnt_eta = c->qnt_eta;
-  /* module_convection and module_decay stay on the reference's CPU code in this version (their kernels are pinned on the
-     host, the GPU run is pending): switched off on the device side whatever the control file says */
+  /* the rank-4 modules are switched off on the device side here and switched on below when they are routed to it */
   k.conv_cape = k.conv_cin = k.conv_dt = -999; k.conv_pbl_trans = 0; k.conv_mix_pbl = 0;
   k.tdec_trop = k.tdec_strat = 0;
   k.qnt_m = k.qnt_vmr = k.qnt_mloss_decay = k.qnt_loss_rate = -1;
@@ -229,9 +259,14 @@ void mptrac_update_device(const ctl_t *ctl, const cache_t *cache, const clim_t *
   SELECT_TIMER("UPDATE_DEVICE", "MEMORY");
   static const ctl_t *last_ctl;
   if (ctl) last_ctl = ctl;
+  if (clim) g_last_clim = clim;
+  if (cache) g_last_cache = cache;
   if (atm) {
     if (!last_ctl) ERRMSG("mptrac_b200: mptrac_update_device(atm) before the control parameters are known");
-    ensure_ctx(last_ctl, atm->np);
+    if (ensure_ctx(last_ctl, atm->np)) {   /* a fresh context knows nothing yet */
+      if (!clim) clim = g_last_clim;
+      if (!cache) cache = g_last_cache;
+    }
   }
   if (!g_ctx) return;              /* nothing to mirror yet (e.g. tools that never step) */
   if (ctl) put_ctl(ctl);
@@ -264,9 +299,12 @@ void mptrac_update_host(const ctl_t *ctl, const cache_t *cache, const clim_t *cl
 void mptrac_free(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t *met0, met_t *met1, atm_t *atm, depo_t *depo, dd_t *dd) {
   if (g_ctx) {
     if (verbose()) printf("mptrac_b200: %lld kernel launches\n", (long long) mpb_launch_count(g_ctx));
+    g_rng_ctr = mpb_get_rng_ctr(g_ctx);     /* the next directory of the dirlist continues the stream */
     MPB(mpb_destroy(g_ctx));
     g_ctx = NULL; g_np = -1;
   }
+  if (clim == g_last_clim) g_last_clim = NULL;
+  if (cache == g_last_cache) g_last_cache = NULL;
   void (*real)(ctl_t *, cache_t *, clim_t *, met_t *, met_t *, atm_t *, depo_t *, dd_t *) = dlsym(RTLD_NEXT, "mptrac_free");
   if (real) real(ctl, cache, clim, met0, met1, atm, depo, dd);
 }

@@ -53,7 +53,9 @@ if [ "$what" = ref ] || [ "$what" = all ]; then
   RFLAGS="-I$B/include $DEFS -DVERSION=\"oracle\" -O3 -g -DHAVE_INLINE -fno-common -fshort-enums -fopenmp"
   LIBS="-L$B/lib -lnetcdf -lhdf5_hl -lhdf5 -lsz -lz -lgsl -lgslcblas -ldl -lm"
   stamp="$OUT/.stamp_ref"
-  if [ ! -f "$stamp" ] || [ "$SRC/mptrac.c" -nt "$stamp" ] || [ "$0" -nt "$stamp" ] || [ "$HERE/ref_harness.c" -nt "$stamp" ]; then
+  # (the stamp records the -D dimensions: a different MPTRAC_DEFINES rebuilds everything that includes mptrac.h)
+  if [ ! -f "$stamp" ] || [ "$SRC/mptrac.c" -nt "$stamp" ] || [ "$0" -nt "$stamp" ] || [ "$HERE/ref_harness.c" -nt "$stamp" ] \
+     || [ "$HERE/ref_layout.c" -nt "$stamp" ] || [ "$(cat "$stamp" 2>/dev/null)" != "$DEFS" ]; then
     echo "== compiling reference library (static flavour, for timing + goldens)"
     gcc $RFLAGS -c "$SRC/mptrac.c" -o "$OUT/lib/mptrac.o"
     ar rcs "$OUT/lib/libmptrac.a" "$OUT/lib/mptrac.o"
@@ -62,13 +64,13 @@ if [ "$what" = ref ] || [ "$what" = all ]; then
     done
     wait
     echo "== compiling reference library (shared -fPIC flavour: the interposition boundary, SURVEY 8b)"
-    gcc $RFLAGS -fPIC -shared "$SRC/mptrac.c" $LIBS -o "$OUT/lib/libmptrac.so"
+    gcc $RFLAGS -fPIC -shared -I"$SRC" "$SRC/mptrac.c" "$HERE/ref_layout.c" $LIBS -o "$OUT/lib/libmptrac.so"
     gcc $RFLAGS "$SRC/trac.c" -L"$OUT/lib" -lmptrac -Wl,-rpath,'$ORIGIN/../lib' $LIBS -o "$OUT/bin/trac_shared"
     echo "== compiling the in-memory harness around the reference translation unit"
     gcc $RFLAGS -DLOGLEV=0 -fPIC -fno-semantic-interposition -shared -I"$SRC" -I"$HERE" "$HERE/ref_harness.c" $LIBS -o "$OUT/lib/libref_harness.so"
     # headers needed to compile our shim + harness on a box that has no /root/reference are NOT copied:
     # everything that includes mptrac.h is compiled here, now.
-    touch "$stamp"
+    printf '%s' "$DEFS" > "$stamp"
   fi
 fi
 # test data of the reference's own tests that exercise this path (data files, not sources): they let the GPU box

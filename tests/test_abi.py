@@ -103,3 +103,60 @@ def test_shim_defines_exactly_the_reference_symbols_it_replaces():
     assert used and used <= set(header_symbols())
     # the reference modules it delegates to in hybrid mode come from the reference's own library at run time
     assert {"module_diff_pbl", "module_convection", "module_isosurf", "module_meteo", "module_bound_cond", "module_decay"} <= undefined
+
+
+def _trac_env():
+    import os
+    ref = ROOT / "oracle" / "_ref"
+    trac, data = ref / "bin" / "trac_shared", ref / "data"
+    if not (trac.exists() and (data / "ei_2011_06_05_00.nc").exists() and (ref / "deps" / "include").exists()):
+        pytest.skip("oracle/_ref (the built reference) is not present on this machine")
+    return trac, data, dict(os.environ, OMP_NUM_THREADS="2", LANG="C", LC_ALL="C")
+
+
+def _dt_test_dir(tmp_path, data):
+    d = tmp_path / "data"
+    d.mkdir()
+    (d / "trac.ctl").write_text(f"NQ = 0\nMETBASE = {data}/ei\nDT_MOD = 10.0\nDT_MET = 86400.0\nT_STOP = 360547210\nMET_DT_OUT = 0\n")
+    (d / "atm_in.tab").write_bytes((data / "dt_test.ref" / "atm_split.tab").read_bytes())
+    (tmp_path / "dirlist").write_text(str(d) + "\n")
+    return d
+
+
+def test_shim_refuses_a_library_built_with_other_dimensions(tmp_path):
+    """The shim reads and writes atm_t / cache_t / met_t in place, so it must be compiled with the -DNP/-DNQ/-DEX/-DEY/-DEP
+    of the libmptrac.so behind it.  The oracle build exports its dimensions (oracle/ref_layout.c); a shim compiled with a
+    different NP must stop with the reference's ERRMSG convention instead of touching the structs (no GPU needed: the
+    check comes before the device context)."""
+    import subprocess
+    from mptrac_b200 import build as b
+    trac, data, env = _trac_env()
+    if not (b.REFERENCE / "src" / "mptrac.h").exists():
+        pytest.skip("the reference's header is needed to compile a shim")
+    bad = tmp_path / "libshim_np.so"
+    subprocess.run(["gcc", "-O1", "-fPIC", "-shared", "-fshort-enums", "-fopenmp", "-DHAVE_INLINE", "-DNP=123456",
+                    f"-I{b.REFERENCE / 'src'}", f"-I{ROOT / 'oracle' / '_ref' / 'deps' / 'include'}", f"-I{ROOT / 'include'}",
+                    str(b.CSRC / "shim" / "mptrac_shim.c"), f"-L{b.LIBDIR}", "-lmptrac_b200", f"-Wl,-rpath,{b.LIBDIR}", "-ldl", "-o", str(bad)],
+                   check=True)
+    _dt_test_dir(tmp_path, data)
+    r = subprocess.run([str(trac), str(tmp_path / "dirlist"), "trac.ctl", "atm_in.tab"], env=dict(env, LD_PRELOAD=str(bad)),
+                       cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert "shim compiled with NP = 123456" in r.stdout and "MPTRAC_DEFINES" in r.stdout, r.stdout[-2000:]
+
+
+def test_drop_in_fails_loudly_without_a_gpu(tmp_path):
+    """no CPU fallback: on a machine without a CUDA device the unmodified `trac` with the shim pre-loaded stops with an
+    error from mpb_create instead of silently running the reference's CPU path"""
+    import subprocess
+    from mptrac_b200 import build as b
+    if has_gpu():
+        pytest.skip("this machine has a GPU")
+    trac, data, env = _trac_env()
+    shim = b.LIBDIR / "libmptrac_b200_shim.so"
+    if not shim.exists():
+        pytest.skip("shim not built")
+    _dt_test_dir(tmp_path, data)
+    r = subprocess.run([str(trac), str(tmp_path / "dirlist"), "trac.ctl", "atm_in.tab"], env=dict(env, LD_PRELOAD=str(shim)),
+                       cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "mptrac_b200:" in r.stdout, r.stdout[-2000:]

@@ -1,14 +1,13 @@
-"""GPU tests that have NOT run on a B200 yet (the round's GPU budget was spent when the code they cover was written).
-The device source they exercise is bit-exact against the oracle when compiled for the host (tests/test_hostemu.py) and
-the oracle is bit-exact against the reference (tests/test_oracle_vs_reference.py); what is missing is the run on the
-device.  They carry their own marker so that neither `-m gpu` nor `-m "not gpu"` (on a CPU box: skipped) depends on
-them: run `pytest -m gpu_pending` on a GPU box, then move them into tests/test_gpu_parity.py / test_shim_trac.py."""
+"""GPU parity of the widened rows: the remaining module_meteo fields, module_convection, module_decay,
+module_isosurf, module_diff_pbl, module_bound_cond, module_chem_grid -- each inside the dispatcher against the oracle --
+and the reference's own trac_test / interoper_test through the shim with these modules routed to the device.
+First run on a B200: round 2 (profiles/r02_gpu_first_call.txt)."""
 import numpy as np
 import pytest
 
 from conftest import abserr, has_gpu, relerr
 
-pytestmark = [pytest.mark.gpu_pending, pytest.mark.skipif(not has_gpu(), reason="needs a CUDA device")]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_gpu(), reason="needs a CUDA device")]
 
 
 @pytest.mark.parametrize("lat_desc", [False, True])
@@ -62,32 +61,32 @@ def test_module_meteo_field_quantity_without_its_field_fails_loudly():
 
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("levels", ["pl", "ml"])
-def test_trac_trac_test_with_routed_modules(tmp_path, monkeypatch, levels):
-    """tests/trac_test through the shim with MPTRAC_B200_DEVICE_MODULES=1 and MPTRAC_B200_DEVICE_METEO_FIELDS=1: its
-    module_convection (CONV_CAPE 0: cape, cin, pel uploaded with each met level) and its zg / pv / pt run on the device;
-    chemistry and deposition keep the tail of the step -- boundary conditions and decay with it -- on the host"""
+def test_trac_trac_test_hybrid_host_modules(tmp_path, monkeypatch, levels):
+    """tests/trac_test through the shim in full hybrid mode (MPTRAC_B200_DEVICE_MODULES=0, _DEVICE_METEO_FIELDS=0: the
+    shim's defaults route module_convection, zg / pv / pt ... to the device, test_shim_trac.py covers that): convection,
+    the further module_meteo quantities, chemistry and deposition all run through the reference's CPU code between device
+    segments"""
     import test_shim_trac as T
-    monkeypatch.setenv("MPTRAC_B200_DEVICE_MODULES", "1")
-    monkeypatch.setenv("MPTRAC_B200_DEVICE_METEO_FIELDS", "1")
+    monkeypatch.setenv("MPTRAC_B200_DEVICE_MODULES", "0")
+    monkeypatch.setenv("MPTRAC_B200_DEVICE_METEO_FIELDS", "0")
     T.test_trac_trac_test_through_the_shim(tmp_path, levels)
 
 
 @pytest.mark.timeout(900)
-def test_trac_interoper_test_with_routed_modules(tmp_path, monkeypatch):
-    """tests/interoper_test (zeta coordinate) with MPTRAC_B200_DEVICE_MODULES=1: module_decay is the only tail module of
-    that control file besides module_meteo, whose pv keeps it on the host unless the fields go to the device too"""
+def test_trac_interoper_test_hybrid_host_modules(tmp_path, monkeypatch):
+    """tests/interoper_test (zeta coordinate) in full hybrid mode: module_decay and module_meteo (pv) on the host"""
     import test_shim_trac as T
-    monkeypatch.setenv("MPTRAC_B200_DEVICE_MODULES", "1")
-    monkeypatch.setenv("MPTRAC_B200_DEVICE_METEO_FIELDS", "1")
+    monkeypatch.setenv("MPTRAC_B200_DEVICE_MODULES", "0")
+    monkeypatch.setenv("MPTRAC_B200_DEVICE_METEO_FIELDS", "0")
     T.test_trac_interoper_test_zeta_through_the_shim(tmp_path)
 
 
 @pytest.mark.timeout(900)
 def test_trac_trac_test_pl_with_device_meteo_fields(tmp_path, monkeypatch):
-    """tests/trac_test (pressure-level run) through the shim with MPTRAC_B200_DEVICE_METEO_FIELDS=1: zg, pv and pt of its
-    control file come from the device's module_meteo instead of the reference's CPU code"""
+    """tests/trac_test (pressure-level run) through the shim with the modules on the host but zg, pv and pt from the
+    device's module_meteo"""
     import test_shim_trac as T
-    monkeypatch.setenv("MPTRAC_B200_DEVICE_METEO_FIELDS", "1")
+    monkeypatch.setenv("MPTRAC_B200_DEVICE_MODULES", "0")
     T.test_trac_trac_test_through_the_shim(tmp_path, "pl")
 
 

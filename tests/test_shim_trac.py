@@ -254,3 +254,38 @@ def test_trac_interoper_test_zeta_through_the_shim(tmp_path):
     out_dir.mkdir(exist_ok=True)
     (out_dir / "interoper_test_shim.json").write_text(__import__("json").dumps(report, indent=1))
     assert all(v >= 0.999 for v in report.values()), report
+
+
+def test_trac_dirlist_continues_the_random_stream(tmp_path):
+    """Two directories in ONE dirlist (ensemble members, src/trac.c:98-185): the reference's file-static Squares counter
+    (src/mptrac.c:35) keeps counting from the first directory into the second, so the two members get different random
+    numbers.  The shim carries the device counter across mptrac_free / the next context: the second member must match the
+    reference's CPU run of the same dirlist (and differ from the first member)."""
+    _need()
+    ctl = DT_CTL.format(met=DATA).replace("T_STOP = 360547260", "T_STOP = 360547230")
+
+    def run(root, preload):
+        dirs = []
+        for k in range(2):
+            d = root / f"member{k}"
+            d.mkdir(parents=True)
+            (d / "trac.ctl").write_text(ctl)
+            (d / "atm_in.tab").write_bytes((DATA / "dt_test.ref" / "atm_split.tab").read_bytes())
+            dirs.append(d)
+        (root / "dirlist").write_text("".join(f"{d}\n" for d in dirs))
+        env = dict(os.environ, OMP_NUM_THREADS="4", LANG="C", LC_ALL="C", MPTRAC_B200_VERBOSE="1")
+        if preload:
+            env["LD_PRELOAD"] = str(SHIM)
+        r = subprocess.run([str(TRAC), str(root / "dirlist"), "trac.ctl", "atm_in.tab", "ATM_BASENAME", "atm_pl", "MET_DT_OUT", "0"],
+                           env=env, cwd=root, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+        return dirs, r.stdout
+
+    gpu_dirs, out = run(tmp_path / "gpu", True)
+    assert out.count("kernel launches") == 2
+    cpu_dirs, _ = run(tmp_path / "cpu", False)
+    last = "atm_pl_2011_06_05_00_00_30.tab"
+    g0, g1, c1 = _tab(gpu_dirs[0] / last), _tab(gpu_dirs[1] / last), _tab(cpu_dirs[1] / last)
+    assert abserr(g0[:, 2], g1[:, 2]) > 1e-4, "both members drew the same random numbers"
+    for c in range(1, 4):
+        assert relerr(g1[:, c], c1[:, c]) < 2e-5 or abserr(g1[:, c], c1[:, c]) < 1e-9, c
