@@ -188,6 +188,113 @@ def build_inputs(wl, rank, world):
     return ctl, m0, m1, (tm, p, lon, lat, q)
 
 
+def exchange_transport():
+    return os.environ.get("MPB_BENCH_EXCHANGE", "peers")
+
+
+def make_steps(eng, wl, ctl, dev, world):
+    """(full step, the same without its exchange, attached) for a workload"""
+    from mptrac_b200 import dist as mdist
+    from mptrac_b200.host import MOD_ALL, MOD_MIXING
+    attached = False
+    if world > 1 and (wl.get("mixing") or wl.get("out_grid")) and exchange_transport() == "peers":
+        g = wl.get("out_grid")
+        attached = mdist.attach_peers(eng, ctl, g["nx"] * g["ny"] * g["nz"] if g else 0)
+    if wl.get("mixing"):
+        def transport_only(t):
+            eng.run_modules(t, MOD_ALL & ~MOD_MIXING)
+        if attached or world == 1:
+            full = eng.run_timestep              # module_mixing inside: accumulate -> barrier -> apply
+        else:
+            def full(t):
+                eng.run_modules(t, MOD_ALL & ~MOD_MIXING)
+                mdist.mixing_step(eng, t, dev)
+    elif wl.get("out_grid"):
+        transport_only = eng.run_timestep
+
+        def full(t):
+            eng.run_timestep(t)
+            # rank 0 holds the summed boxes on the host after this call
+            mdist.grid_output(eng, dict(wl["out_grid"], t0=t - 0.5 * DT_MOD, t1=t + 0.5 * DT_MOD), dev, attached=attached)
+    else:
+        full = transport_only = eng.run_timestep
+    return full, transport_only, attached
+
+
+def exchange_record(name, rank, world, local, K=12, W=3):
+    """One of the exchange workloads (configs[3] with its gridded output = c4g, configs[4] with its mixing = c5) on the
+    ranks of this run: ms per step with and without the exchange step, max over ranks, CUDA events, L2 flushed."""
+    import torch
+    import torch.distributed as dist
+    from mptrac_b200 import Engine, synth
+    wl = WORKLOADS[name]
+    ctl, m0, m1, (tm, p, lon, lat, q) = build_inputs(wl, rank, world)
+    n = wl["np"]
+    eng = Engine(n, nq=ctl.nq, device=local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_ctl(ctl)
+    eng.set_clim_tropo(*synth.make_clim_tropo())
+    eng.set_met(0, m0)
+    eng.set_met(1, m1)
+    eng.set_shard(rank * n, world * n)
+    eng.set_atm(tm, p, lon, lat, q)
+    dev = torch.device("cuda", local)
+    full, transport_only, attached = make_steps(eng, wl, ctl, dev, world)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    t = [0.0]
+
+    def timed(fn):
+        for _ in range(W):
+            t[0] += DT_MOD
+            fn(t[0])
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for k in range(K):
+            t[0] += DT_MOD
+            flush.zero_()
+            ev[k][0].record(stream)
+            fn(t[0])
+            ev[k][1].record(stream)
+        torch.cuda.synchronize()
+        ms = float(sum(a.elapsed_time(b) for a, b in ev)) / K
+        if world > 1:
+            x = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(x, op=dist.ReduceOp.MAX)
+            ms = float(x.item())
+        return ms
+
+    spinup = int(round(wl["ctl"].get("sort_dt", 0.0) / DT_MOD))
+    for _ in range(spinup):
+        t[0] += DT_MOD
+        full(t[0])
+    ms_full = timed(full)
+    ms_plain = timed(transport_only)
+    eng.sync()
+    if world > 1:
+        dist.barrier()
+    nmix = len([i for i in ctl.mix_qnt if i >= 0]) if wl.get("mixing") else 0
+    if wl.get("mixing"):
+        nbox = ctl.mixing_nx * ctl.mixing_ny * ctl.mixing_nz
+        per_rank = (2 * 8 * (nmix + 1) * n * (world - 1) // world if attached else
+                    2 * 8 * (nmix + 1) * nbox * (world - 1) // world)
+    else:
+        g = wl["out_grid"]
+        per_rank = g["nx"] * g["ny"] * g["nz"] * (16 * max(ctl.nq, 1) + 4) if world > 1 else 0
+    eng.close()
+    del flush
+    return {"workload": f"BASELINE {workload_label(name)}: {wl['desc']}", "parcels_per_gpu": n, "steps": K,
+            "ms_per_step": ms_full, "ms_transport_only": ms_plain, "ms_exchange": ms_full - ms_plain,
+            "exchange_share": (ms_full - ms_plain) / ms_full if ms_full > 0 else None,
+            "value": float(n) * world / (ms_full * 1e-3), "unit": "particle-steps/s",
+            "transport": ("none (one rank)" if world == 1 else
+                          "peer memory: NVLink atomics into the owner's slice of the box records + flag barriers (own kernels)" if attached
+                          else "NCCL: one all-reduce of the dense box records" if wl.get("mixing") else "NCCL reduce of the output boxes"),
+            "exchanged_bytes_per_rank_per_step": int(per_rank)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -257,27 +364,11 @@ def run_ours(args):
 
     model = Model()
 
-    # one model step.  Workloads with an exchange: the box arrays are summed over the ranks by NCCL on the
-    # stream the engine launches on -- mixing between its accumulate and apply kernels, gridded output after the step
+    # one model step.  Workloads with an exchange: by default the ranks are attached through peer memory and
+    # the engine does the exchange itself (NVLink atomics into the owner's slice of the box records + flag barriers);
+    # MPB_BENCH_EXCHANGE=nccl sums the dense box records with ONE all-reduce on the stream the engine launches on
     dev = torch.device("cuda", local)
-    if wl.get("mixing"):
-        from mptrac_b200 import dist as mdist
-        from mptrac_b200.host import MOD_ALL, MOD_MIXING
-
-        def step(t):
-            eng.run_modules(t, MOD_ALL & ~MOD_MIXING)
-            mdist.mixing_step(eng, t, dev)
-    elif wl.get("out_grid"):
-        from mptrac_b200 import dist as mdist
-        grid_seen = []
-
-        def step(t):
-            eng.run_timestep(t)
-            g = mdist.grid_output(eng, dict(wl["out_grid"], t0=t - 0.5 * DT_MOD, t1=t + 0.5 * DT_MOD), dev)
-            if g is not None:
-                grid_seen[:] = [int(g[0].sum())]      # rank 0 holds the reduced boxes on the host
-    else:
-        step = eng.run_timestep
+    step, _, attached = make_steps(eng, wl, ctl, dev, world)
     exchange = bool(wl.get("mixing") or wl.get("out_grid"))
 
     def host_step(t):
@@ -418,8 +509,10 @@ def run_ours(args):
         "config": {"workload": f"BASELINE {workload_label(args.workload)}: {wl['desc']}", "parcels_per_gpu": n,
                    "dt_mod_s": DT_MOD, "l2": "flushed between steps (256 MiB memset outside the per-step events)",
                    "parallelism": f"parcels sharded contiguously over {world} GPU(s), " + (
-                       "one NCCL all-reduce of the mixing boxes per step" if wl.get("mixing") else
-                       "one NCCL reduce of the output-grid boxes per step" if wl.get("out_grid") else "no data-path collective")},
+                       "no data-path collective" if not exchange or world == 1 else
+                       "box records exchanged through peer memory once per step (own kernels over NVLink)" if attached else
+                       "one NCCL all-reduce of the box records per step" if wl.get("mixing") else
+                       "one NCCL reduce of the output-grid boxes per step")},
         "back_to_back": {"value": units / (b2b_ms * 1e-3), "ms_per_step": b2b_ms / K, "met_rolls_inside": b2b_rolls,
                          "note": "no L2 flush, one event bracket around K steps"},
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
@@ -436,7 +529,20 @@ def run_ours(args):
                          "0.51 at best); ncu evidence under profiles/, analysis in DESIGN.md 3.1")},
         "clocks": clk.summary(),
     }
+    if world > 1:
+        dist.barrier()       # (attached ranks: nobody frees its exchange area while a peer may still read it)
     eng.close()
+    del flush
+    # The workloads of BASELINE configs[3] / configs[4], whose step has an exchange between the ranks, measured next to the
+    # headline on the same ranks (the headline workload itself shards without any exchange)
+    if args.workload == "c2" and not args.no_exchange:
+        line["exchange"] = {}
+        for name in ("c5", "c4g"):
+            _log(f"exchange workload {name}")
+            try:
+                line["exchange"][name] = exchange_record(name, rank, world, local)
+            except Exception as exc:      # must never take the headline down with it
+                line["exchange"][name] = {"error": repr(exc)[:300]}
     if rank == 0:
         # CPU arm last, in its own process with a hard deadline: it can never take the GPU numbers down with it
         if world == 1 and not args.no_cpu:
@@ -552,6 +658,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-exchange", action="store_true", help="skip the c5 / c4g exchange sub-records of the default workload")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

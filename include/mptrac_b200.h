@@ -28,8 +28,12 @@ extern "C" {
 
 /* ABI history (mpb_abi_version()): 2 module_meteo quantities of the resident fields; 3 model-level fields and the zeta / eta
  * quantities (ADVECT_VERT_COORD 1, 2, 3); 4 further met fields (x2 / x3), 64 meteo slots, module_convection, module_decay,
- * module_isosurf, module_diff_pbl, module_bound_cond, module_chem_grid (their control fields at the end of mpb_ctl_t, MPB_MOD_* bits) */
-#define MPB_ABI_VERSION 4
+ * module_isosurf, module_diff_pbl, module_bound_cond, module_chem_grid (their control fields at the end of mpb_ctl_t, MPB_MOD_* bits);
+ * 5 module_mixing accumulates all quantities at once (box records), ranks exchange through peer memory (mpb_peer_*), several
+ * devices behind one host thread (mpb_team_*) */
+#define MPB_ABI_VERSION 5
+#define MPB_MAX_RANKS 16         /* ranks / team members that can exchange box records */
+#define MPB_IPC_HANDLE_BYTES 64  /* size of the handle mpb_peer_init exports (a CUDA IPC memory handle) */
 #define MPB_MIX_MAXQ 23  /* number of mixable quantities, src/mptrac.c:5222-5230 */
 
 /* Quantities module_meteo (src/mptrac.c:5062-5165) can set on the device, slot order of mpb_ctl_t::qnt_meteo:
@@ -237,17 +241,72 @@ int mpb_module_meteo(mpb_ctx *ctx);                 /* src/mptrac.c:5062, the MP
 int mpb_module_mixing(mpb_ctx *ctx, double t);      /* src/mptrac.c:5169 (single device) */
 int mpb_module_rng(mpb_ctx *ctx, double *rs_host, int64_t n, int method); /* src/mptrac.c:5753; fills host array, advances counter */
 
-/* --- mixing / gridded output split for multi-GPU runs: accumulate local partial box arrays,
- *     let the caller sum them over ranks (NCCL), then apply. --- */
-int mpb_mixing_begin(mpb_ctx *ctx, double t);                      /* box index per parcel */
-int mpb_mixing_accumulate(mpb_ctx *ctx, int iq);                   /* -> box sum / count    */
-int mpb_mixing_apply(mpb_ctx *ctx, int iq);                        /* mean + relaxation     */
+/* --- module_mixing (src/mptrac.c:5169-5347) and the binning of write_grid (13840-13872) over several ranks ---
+ * The box records of module_mixing -- per box {count, sum of every mixed quantity}, doubles -- are accumulated for ALL mixed
+ * quantities in one pass.  Three ways to run the exchange step:
+ *  (1) ranks attached through peer memory (mpb_peer_init + mpb_peer_attach, one process per GPU): mpb_run_timestep /
+ *      mpb_module_mixing do everything -- each rank adds its parcels' contributions into the slice of the box space its OWNER
+ *      holds (NVLink atomics), one barrier in stream order, each rank reads its parcels' records back;
+ *  (2) a team (mpb_team_*, several devices behind one host thread): the same through mpb_team_run_timestep;
+ *  (3) any other transport: mpb_mixing_accumulate_all, sum mpb_device_ptr("mix_rec") [mpb_mixing_rec_len() doubles] over the
+ *      ranks (one all-reduce), mpb_mixing_apply_all.
+ * Gridded output: mpb_grid_accumulate leaves partial arrays on every rank; mpb_grid_reduce adds them up on rank 0 (attached
+ * ranks; otherwise reduce mpb_device_ptr("grid_cnt" / "grid_sum" / "grid_sq") yourself); mpb_grid_fetch copies them out. */
+int mpb_mixing_accumulate_all(mpb_ctx *ctx, double t);             /* box index per parcel, records zeroed, local contributions */
+int mpb_mixing_apply_all(mpb_ctx *ctx);                            /* box means + relaxation of every mixed quantity */
 int64_t mpb_mixing_nbox(mpb_ctx *ctx);
+int64_t mpb_mixing_rec_len(mpb_ctx *ctx);                          /* (mixed quantities + 1) x boxes */
 int mpb_grid_accumulate(mpb_ctx *ctx, const mpb_grid_t *grid);      /* -> count[nbox], sum[nq][nbox], sumsq[nq][nbox] on device */
+int mpb_grid_reduce(mpb_ctx *ctx);                                  /* attached ranks: sum over ranks onto rank 0 */
 int mpb_grid_fetch(mpb_ctx *ctx, int *count, double *sum, double *sumsq);   /* copy them to the host (any may be NULL) */
 
+/* Ranks that exchange through peer memory.  mpb_peer_init allocates this rank's exchange area -- barrier flags, its slice of
+ * the box records (mix_bytes >= 3 x 8 x (mixed quantities + 1) x ceil(boxes / nranks)), its partial output arrays (grid_bytes
+ * >= boxes x (16 x nq + 4)) -- and exports a handle (MPB_IPC_HANDLE_BYTES) other processes open with mpb_peer_attach (handles
+ * of all ranks, rank order; the caller gathers them, e.g. with its MPI / torch.distributed, and synchronises the ranks once
+ * after attaching).  Contexts of one process attach each other's mpb_peer_area directly.  All ranks must then issue the same
+ * sequence of exchange steps.  A barrier that waits ~5 s for a missing rank gives up; mpb_sync reports it. */
+int mpb_peer_init(mpb_ctx *ctx, int rank, int nranks, int64_t mix_bytes, int64_t grid_bytes, void *ipc_handle_out /* or NULL */);
+int mpb_peer_attach(mpb_ctx *ctx, const void *ipc_handles /* [nranks][MPB_IPC_HANDLE_BYTES] */);
+int mpb_peer_attach_local(mpb_ctx *ctx, void *const *areas /* [nranks] */, const int *devices /* [nranks] */);
+void *mpb_peer_area(mpb_ctx *ctx);
+int mpb_peer_barrier(mpb_ctx *ctx);
+
+/* --- a team: several devices behind ONE host thread, for the reference's single-process driver (device selection:
+ *     src/trac.c:75-80; met broadcast: src/mptrac.c:45-69).  Parcels are cut into contiguous index ranges, one per member;
+ *     the met data is uploaded and packed once and copied device to device; each call below is the per-context call of
+ *     the same name applied to the whole parcel set. --- */
+typedef struct mpb_team mpb_team;
+int mpb_team_create(mpb_team **team, int ndev, const int *devices, int64_t np_max, int nq);
+int mpb_team_destroy(mpb_team *team);
+int mpb_team_size(mpb_team *team);
+mpb_ctx *mpb_team_member(mpb_team *team, int i);
+int mpb_team_set_ctl(mpb_team *team, const mpb_ctl_t *ctl);
+int mpb_team_set_clim_tropo(mpb_team *team, int ntime, int nlat, const double *time, const double *lat, const double *tropo);
+int mpb_team_set_clim_ts(mpb_team *team, int species, int n, const double *time, const double *vmr);
+int mpb_team_set_balloon(mpb_team *team, int n, const double *ts, const double *ps);
+int mpb_team_set_met(mpb_team *team, int slot, const mpb_met_view_t *met);
+int mpb_team_swap_met(mpb_team *team);
+int mpb_team_set_atm(mpb_team *team, int64_t np, const double *time, const double *p, const double *lon, const double *lat,
+                     const double *q, int64_t q_stride);
+int mpb_team_get_atm(mpb_team *team, double *time, double *p, double *lon, double *lat, double *q, int64_t q_stride);
+int mpb_team_set_uvwp(mpb_team *team, const float *uvwp);
+int mpb_team_get_uvwp(mpb_team *team, float *uvwp);
+int mpb_team_get_dt(mpb_team *team, double *dt);
+int mpb_team_set_iso_var(mpb_team *team, const double *iso_var);
+int mpb_team_get_iso_var(mpb_team *team, double *iso_var);
+int64_t mpb_team_get_np(mpb_team *team);
+int mpb_team_set_rng_ctr(mpb_team *team, uint64_t ctr);
+uint64_t mpb_team_get_rng_ctr(mpb_team *team);
+int mpb_team_run_timestep(mpb_team *team, double t);
+int mpb_team_run_modules(mpb_team *team, double t, unsigned mask);
+int mpb_team_sync(mpb_team *team);
+int64_t mpb_team_launch_count(mpb_team *team);
+int mpb_team_grid_accumulate(mpb_team *team, const mpb_grid_t *grid);   /* partial arrays everywhere, summed on member 0 */
+int mpb_team_grid_fetch(mpb_team *team, int *count, double *sum, double *sumsq);
+
 /* --- introspection --- */
-void *mpb_device_ptr(mpb_ctx *ctx, const char *name);   /* "time","p","lon","lat","q","dt","uvwp","mix_sum","mix_cnt","grid_cnt","grid_sum","grid_sq" */
+void *mpb_device_ptr(mpb_ctx *ctx, const char *name);   /* "time","p","lon","lat","q","dt","uvwp","mix_rec","grid_cnt","grid_sum","grid_sq" */
 int64_t mpb_launch_count(mpb_ctx *ctx);                  /* kernels launched by this context so far */
 int mpb_met_bytes(mpb_ctx *ctx, int64_t *bytes);         /* packed device bytes of both met levels */
 

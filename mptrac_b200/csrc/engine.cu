@@ -607,39 +607,132 @@ __global__ void box_index_kernel(BoxArgs b, const double *time, const double *lo
                       b.z0, b.z1, b.nx, b.ny, b.nz);
 }
 
-// src/mptrac.c:5287-5303
-__global__ void mix_accumulate_kernel(const int *box, const double *q, const double *ens, int ngrid,
-                                      double *sum, int *cnt, long long np) {
-  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ip >= np) return;
-  const int b = box[ip];
-  if (b < 0) return;
-  const int idx = (ens ? (int)ens[ip] : 0) * ngrid + b;
-  atomicAdd(sum + idx, q[ip]);
-  atomicAdd(cnt + idx, 1);
+// ------------------------------------------------------------------------------------------------
+// Inter-parcel mixing (src/mptrac.c:5169-5347) -- the one step of the path in which parcels exchange information.
+// Box records: per box (and ensemble member) one record {count, sum_0 .. sum_(nmix-1)} of doubles (counts stay exact:
+// integers below 2^53), ALL mixed quantities at once -- the reference recomputes the same counts for every quantity
+// (5287-5303) -- so a box costs one contiguous read per parcel.  With several ranks the box space is cut into contiguous
+// slices, one per rank; every rank adds its parcels' contributions straight into the OWNER's slice through peer memory
+// (NVLink atomics) and, after one barrier, reads its parcels' records back from there: the exchange moves only the
+// records of occupied boxes (tens of bytes per parcel) instead of all-reducing the dense 5.8 M-box arrays.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = MPB_MAX_RANKS;
+
+struct MixArgs {
+  double *rec[kMaxRanks];     // every rank's slice of the box records (this rank's own: local memory)
+  long long slice;            // boxes per rank
+  int nmix, ngrid;            // mixed quantities; boxes per ensemble member
+  const int *box;             // box of each parcel (-1 = outside)
+  const double *ens;          // ensemble index per parcel (or null)
+  double *q0;                 // quantity 0; quantity k starts k * q_stride further
+  long long q_stride, np;
+  int iq[MPB_MIX_MAXQ];
+};
+
+// Runs of equal records among consecutive lanes are summed inside the warp (parcels arrive cell-sorted, so the lanes of a
+// warp mostly share a few boxes); only the last lane of a run touches memory.  src/mptrac.c:5287-5303
+__global__ void mix_accumulate_kernel(const __grid_constant__ MixArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (the grid covers whole warps: no early return)
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  long long idx = -1;
+  if (ip < A.np) {
+    const int b = A.box[ip];
+    if (b >= 0) idx = (long long)(A.ens ? (int)A.ens[ip] : 0) * A.ngrid + b;
+  }
+  const long long prev = __shfl_up_sync(full, idx, 1);
+  const unsigned heads = __ballot_sync(full, lane == 0 || prev != idx);
+  const int start = 31 - __clz(heads & (full >> (31 - lane)));             // first lane of this lane's run
+  const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+  double *rec = nullptr;
+  if (tail && idx >= 0) {
+    const long long owner = idx / A.slice;
+    rec = A.rec[owner] + (idx - owner * A.slice) * (A.nmix + 1);
+  }
+  int n = 1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int tn = __shfl_up_sync(full, n, d);
+    if (lane - d >= start) n += tn;
+  }
+  if (rec) atomicAdd(rec, (double)n);
+  for (int k = 0; k < A.nmix; k++) {
+    double x = idx >= 0 ? A.q0[(long long)A.iq[k] * A.q_stride + ip] : 0.0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double tx = __shfl_up_sync(full, x, d);
+      if (lane - d >= start) x += tx;
+    }
+    if (rec) atomicAdd(rec + 1 + k, x);
+  }
 }
 
-// src/mptrac.c:5307-5335
-__global__ void mix_apply_kernel(ClimView clim, const int *box, double *q, const double *ens,
-                                 const double *time, const double *lat, const double *p, int ngrid,
-                                 const double *sum, const int *cnt, double mix_trop, double mix_strat,
-                                 int latlon, double utm_ref_lat, long long np) {
+// src/mptrac.c:5307-5335: box mean, then relaxation towards it with the tropopause-weighted mixing parameter
+__global__ void mix_apply_kernel(const __grid_constant__ MixArgs A, ClimView clim, const double *time, const double *lat,
+                                 const double *p, double mix_trop, double mix_strat, int latlon, double utm_ref_lat) {
   const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ip >= np) return;
-  const int b = box[ip];
+  if (ip >= A.np) return;
+  const int b = A.box[ip];
   if (b < 0) return;
-  const int idx = (ens ? (int)ens[ip] : 0) * ngrid + b;
+  const long long idx = (long long)(A.ens ? (int)A.ens[ip] : 0) * A.ngrid + b;
+  const long long owner = idx / A.slice;
+  const double *rec = A.rec[owner] + (idx - owner * A.slice) * (A.nmix + 1);
   double mixparam = 1.0;
   if (mix_trop < 1 || mix_strat < 1) {
     const double pt = tropopause_pressure(clim, time[ip], latlon ? lat[ip] : utm_ref_lat);
     const double w = weight_tropo(pt, p[ip]);
     mixparam = w * mix_trop + (1.0 - w) * mix_strat;
   }
-  const int n = cnt[idx];
-  double mean = sum[idx];
-  if (n > 0) mean /= n;
-  const double qq = q[ip];
-  q[ip] = qq + (mean - qq) * mixparam;
+  const int n = (int)__ldcg(rec);
+  for (int k = 0; k < A.nmix; k++) {
+    double mean = __ldcg(rec + 1 + k);
+    if (n > 0) mean /= n;
+    double *q = A.q0 + (long long)A.iq[k] * A.q_stride + ip;
+    const double qq = *q;
+    *q = qq + (mean - qq) * mixparam;
+  }
+}
+
+// Barrier over the ranks of a multi-process run, in stream order: every rank writes the barrier's number into its slot
+// of every peer's flag array (peer memory) and waits until all peers' numbers have arrived in its own.  The wait is
+// bounded (~5 s): a missing peer raises *err instead of hanging the device.
+struct FlagArgs {
+  unsigned long long *flags[kMaxRanks];
+};
+__global__ void peer_barrier_kernel(const __grid_constant__ FlagArgs F, int rank, int nranks, unsigned long long epoch, int *err) {
+  const int t = threadIdx.x;
+  if (t >= nranks) return;
+  __threadfence_system();
+  unsigned long long *mine = F.flags[t] + rank, *theirs = F.flags[rank] + t;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(mine), "l"(epoch) : "memory");
+  unsigned long long v = 0;
+  for (long long spin = 0; spin < (1ll << 25); spin++) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(theirs) : "memory");
+    if (v >= epoch) break;
+    __nanosleep(128);
+  }
+  if (v < epoch) *err = 1;
+  __threadfence_system();
+}
+
+// Gridded output over ranks: rank 0 adds the peers' partial arrays to its own (read through peer memory)
+struct GridPeers {
+  const double *sum[kMaxRanks], *sq[kMaxRanks];
+  const int *cnt[kMaxRanks];
+};
+__global__ void grid_pull_kernel(const __grid_constant__ GridPeers G, int nranks, long long nbox, long long nval,
+                                 double *sum, double *sq, int *cnt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nval) {
+    double a = sum[i], b = sq[i];
+    for (int r = 1; r < nranks; r++) { a += __ldcg(G.sum[r] + i); b += __ldcg(G.sq[r] + i); }
+    sum[i] = a; sq[i] = b;
+  }
+  if (i < nbox) {
+    int n = cnt[i];
+    for (int r = 1; r < nranks; r++) n += __ldcg(G.cnt[r] + i);
+    cnt[i] = n;
+  }
 }
 
 // src/mptrac.c:13862-13872 with kernel weight 1 (no GRID_KERNEL file)
@@ -702,6 +795,8 @@ __global__ void rng_fill_kernel(unsigned long long ctr0, double *rs, long long n
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+struct mpb_team;
+
 struct MetLevel {
   double time = 0;
   bool valid = false;
@@ -767,12 +862,27 @@ struct mpb_ctx {
 
   // mixing / grid boxes
   int *box = nullptr;
-  double *mix_sum = nullptr;
-  int *mix_cnt = nullptr;
-  long long mix_cap = 0;
+  double *mix_rec = nullptr;            // box records {count, sums} of a single-rank run (dense, zeroed every step)
+  long long mix_cap = 0;                // ... its capacity in doubles
+  int nmix = 0, mix_iq[MPB_MIX_MAXQ] = {};   // quantities mixed by the current step
+  long long mix_total = 0, mix_slice = 0;    // boxes (x ensemble members); boxes per rank
   double *grid_sum = nullptr, *grid_sq = nullptr;
   int *grid_cnt = nullptr;
   long long grid_cap = 0, grid_nbox = 0;
+  bool grid_in_area = false;
+
+  // ranks that exchange box records through peer memory (mpb_peer_*): this rank's exchange area holds the barrier flags,
+  // three sets of its slice of the box records (one per step in rotation, so that ONE barrier per step orders everything)
+  // and its partial arrays of the gridded output; area[r] is rank r's area as mapped into this process
+  int rank = 0, nranks = 1;
+  char *area[kMaxRanks] = {};
+  bool area_ipc[kMaxRanks] = {};
+  size_t area_bytes = 0, area_mix_bytes = 0, area_grid_bytes = 0;
+  int mix_set = 0;
+  long long mix_layout = -1;            // (nmix + 1) * slice the three sets are currently zeroed for
+  unsigned long long epoch = 0;
+  int *peer_err = nullptr;              // device flag raised by a barrier that timed out
+  struct mpb_team *team = nullptr;      // set when a team drives this context (barriers are then stream events)
 
   mpb_ctl_t ctl;
   bool have_ctl = false;
@@ -991,60 +1101,130 @@ static void do_sort(mpb_ctx *c) {
   c->cur ^= 1;
 }
 
-static void mixing_begin(mpb_ctx *c, double t) {
+static long long mixing_total(const mpb_ctx *c) {
+  const mpb_ctl_t &k = c->ctl;
+  return (long long)k.mixing_nx * k.mixing_ny * k.mixing_nz * (k.nens > 0 ? k.nens : 1);
+}
+
+// ---- exchange area of a rank (mpb_peer_init): [flags + error word | three sets of its slice of the box records | its partial
+// arrays of the gridded output] ----
+constexpr size_t kAreaHeader = 4096, kAreaErrOffset = 2048;
+static double *mix_set_ptr(const mpb_ctx *c, int r, int set) {
+  return (double *)(c->area[r] + kAreaHeader + (size_t)set * (c->area_mix_bytes / 3));
+}
+static char *grid_region(const mpb_ctx *c, int r) { return c->area[r] + kAreaHeader + c->area_mix_bytes; }
+
+// stream-ordered barrier over the ranks of a multi-process run (a team of contexts in ONE process uses stream events instead)
+static void peer_barrier(mpb_ctx *c) {
+  if (c->nranks <= 1) return;
+  REQUIRE(c->team == nullptr, "internal: a team context must not use the flag barrier");
+  for (int r = 0; r < c->nranks; r++) REQUIRE(c->area[r] != nullptr, "mpb_peer_attach has not been called");
+  FlagArgs F;
+  for (int r = 0; r < kMaxRanks; r++) F.flags[r] = r < c->nranks ? (unsigned long long *)c->area[r] : nullptr;
+  c->epoch++;
+  peer_barrier_kernel<<<1, 32, 0, c->stream>>>(F, c->rank, c->nranks, c->epoch, c->peer_err);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
+// Box index of every parcel, the list of mixed quantities, the box records.  Returns true when the ranks must pass a
+// barrier before anybody accumulates (the three record sets were just cleared for a new layout).
+static bool mixing_prepare(mpb_ctx *c, double t) {
   const mpb_ctl_t &k = c->ctl;
   ensure_boxes(c);
   BoxArgs b;
   b.t0 = t - 0.5 * k.dt_mod; b.t1 = t + 0.5 * k.dt_mod;
   b.lon0 = k.mixing_lon0; b.lon1 = k.mixing_lon1; b.lat0 = k.mixing_lat0; b.lat1 = k.mixing_lat1;
   b.z0 = k.mixing_z0; b.z1 = k.mixing_z1; b.nx = k.mixing_nx; b.ny = k.mixing_ny; b.nz = k.mixing_nz;
-  const long long total = (long long)k.mixing_nx * k.mixing_ny * k.mixing_nz * (k.nens > 0 ? k.nens : 1);
-  REQUIRE(total > 0 && total < (1ll << 31), "mixing grid size out of range");
-  if (total > c->mix_cap) {
-    if (c->mix_sum) { CK(cudaFree(c->mix_sum)); CK(cudaFree(c->mix_cnt)); }
-    CK(cudaMalloc(&c->mix_sum, sizeof(double) * (size_t)total));
-    CK(cudaMalloc(&c->mix_cnt, sizeof(int) * (size_t)total));
-    c->mix_cap = total;
-  }
-  if (c->np == 0) return;
-  box_index_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(b, c->time(), c->lon(), c->lat(), c->p(), c->box, c->np);
-  CK(cudaGetLastError());
-  c->launches++;
-}
-
-static long long mixing_total(const mpb_ctx *c) {
-  const mpb_ctl_t &k = c->ctl;
-  return (long long)k.mixing_nx * k.mixing_ny * k.mixing_nz * (k.nens > 0 ? k.nens : 1);
-}
-
-static void mixing_accumulate(mpb_ctx *c, int iq) {
-  REQUIRE(iq >= 0 && iq < c->nq, "mixing quantity index out of range");
-  REQUIRE(c->mix_sum != nullptr, "mpb_mixing_begin has not been called");
-  const mpb_ctl_t &k = c->ctl;
   const long long total = mixing_total(c);
-  CK(cudaMemsetAsync(c->mix_sum, 0, sizeof(double) * (size_t)total, c->stream));
-  CK(cudaMemsetAsync(c->mix_cnt, 0, sizeof(int) * (size_t)total, c->stream));
-  if (c->np == 0) return;
-  const double *ens = (k.nens > 0 && k.qnt_ens >= 0) ? c->q(k.qnt_ens) : nullptr;
-  mix_accumulate_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(
-      c->box, c->q(iq), ens, k.mixing_nx * k.mixing_ny * k.mixing_nz, c->mix_sum, c->mix_cnt, c->np);
-  CK(cudaGetLastError());
-  c->launches++;
-}
-
-static void mixing_apply(mpb_ctx *c, int iq) {
-  REQUIRE(iq >= 0 && iq < c->nq, "mixing quantity index out of range");
-  const mpb_ctl_t &k = c->ctl;
-  if (c->np == 0) return;
+  REQUIRE(total > 0 && total < (1ll << 31), "mixing grid size out of range");
   if (k.mixing_trop < 1 || k.mixing_strat < 1)
     REQUIRE(c->cl_tropo != nullptr, "mixing needs the tropopause climatology (mpb_set_clim_tropo)");
-  const double *ens = (k.nens > 0 && k.qnt_ens >= 0) ? c->q(k.qnt_ens) : nullptr;
-  mix_apply_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(
-      clim_view(c), c->box, c->q(iq), ens, c->time(), c->lat(), c->p(),
-      k.mixing_nx * k.mixing_ny * k.mixing_nz, c->mix_sum, c->mix_cnt, k.mixing_trop, k.mixing_strat,
-      k.met_coord_type == 0, k.met_utm_ref_lat, c->np);
+  c->nmix = 0;
+  for (int i = 0; i < k.n_mix_qnt; i++)
+    if (k.mix_qnt[i] >= 0) {
+      REQUIRE(k.mix_qnt[i] < c->nq, "mixing quantity index out of range");
+      c->mix_iq[c->nmix++] = k.mix_qnt[i];
+    }
+  c->mix_total = total;
+  const long long stride = c->nmix + 1;
+  bool barrier = false;
+  if (c->nranks == 1) {
+    c->mix_slice = total;
+    const long long need = stride * total;
+    if (need > c->mix_cap) {
+      if (c->mix_rec) CK(cudaFree(c->mix_rec));
+      CK(cudaMalloc(&c->mix_rec, sizeof(double) * (size_t)need));
+      c->mix_cap = need;
+    }
+    CK(cudaMemsetAsync(c->mix_rec, 0, sizeof(double) * (size_t)need, c->stream));
+  } else {
+    c->mix_slice = (total + c->nranks - 1) / c->nranks;
+    const long long need = stride * c->mix_slice;
+    REQUIRE(c->area[c->rank] != nullptr && sizeof(double) * (size_t)need <= c->area_mix_bytes / 3,
+            "the exchange area is too small for this mixing grid (mpb_peer_init: 3 x (quantities + 1) x boxes per rank doubles)");
+    if (c->mix_layout != need) {
+      CK(cudaMemsetAsync(c->area[c->rank] + kAreaHeader, 0, c->area_mix_bytes, c->stream));
+      c->mix_layout = need; c->mix_set = 0;
+      barrier = true;
+    }
+  }
+  if (c->np > 0) {
+    box_index_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(b, c->time(), c->lon(), c->lat(), c->p(), c->box, c->np);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  return barrier;
+}
+
+static MixArgs mix_args(mpb_ctx *c) {
+  const mpb_ctl_t &k = c->ctl;
+  MixArgs A;
+  for (int r = 0; r < kMaxRanks; r++) A.rec[r] = nullptr;
+  if (c->nranks == 1) A.rec[0] = c->mix_rec;
+  else for (int r = 0; r < c->nranks; r++) {
+    REQUIRE(c->area[r] != nullptr, "mpb_peer_attach has not been called");
+    A.rec[r] = mix_set_ptr(c, r, c->mix_set);
+  }
+  A.slice = c->mix_slice; A.nmix = c->nmix; A.ngrid = k.mixing_nx * k.mixing_ny * k.mixing_nz;
+  A.box = c->box;
+  A.ens = (k.nens > 0 && k.qnt_ens >= 0) ? c->q(k.qnt_ens) : nullptr;
+  A.q0 = c->nq ? c->q(0) : nullptr; A.q_stride = c->np_max; A.np = c->np;
+  for (int i = 0; i < MPB_MIX_MAXQ; i++) A.iq[i] = i < c->nmix ? c->mix_iq[i] : 0;
+  return A;
+}
+
+static void mixing_accumulate_all(mpb_ctx *c) {
+  REQUIRE(c->mix_total > 0, "mixing: the box records have not been prepared");
+  if (c->np == 0 || c->nmix == 0) return;
+  mix_accumulate_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(mix_args(c));
   CK(cudaGetLastError());
   c->launches++;
+}
+
+static void mixing_apply_all(mpb_ctx *c) {
+  const mpb_ctl_t &k = c->ctl;
+  if (c->np > 0 && c->nmix > 0) {
+    mix_apply_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(mix_args(c), clim_view(c), c->time(), c->lat(), c->p(), k.mixing_trop,
+                                                                 k.mixing_strat, k.met_coord_type == 0, k.met_utm_ref_lat);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  if (c->nranks > 1) {
+    // after this step's barrier every rank has finished reading the set of the step before: clear this rank's slice of it
+    // for the step after the next, and move on (the set of the next step was cleared one step ago)
+    const int stale = (c->mix_set + 2) % 3;
+    CK(cudaMemsetAsync(mix_set_ptr(c, c->rank, stale), 0, sizeof(double) * (size_t)c->mix_layout, c->stream));
+    c->mix_set = (c->mix_set + 1) % 3;
+  }
+}
+
+// module_mixing on one context: alone, or as one rank of a multi-process run (barrier in stream order between the phases)
+static void mixing_inline(mpb_ctx *c, double t) {
+  if (mixing_prepare(c, t)) peer_barrier(c);
+  mixing_accumulate_all(c);
+  peer_barrier(c);
+  mixing_apply_all(c);
 }
 
 static bool hits(double t, double every) { return std::fmod(t, every) == 0; }
@@ -1263,6 +1443,56 @@ static void launch_meteo(mpb_ctx *c) {
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
+// Make the context's met arrays, axis tables and (when `staging`) upload buffers fit a grid; a grid that differs from the
+// current one invalidates both met levels (src/mptrac.c:6545-6558 demands identical grids).
+static void ensure_grid(mpb_ctx *c, int nx, int ny, int np, int coord_type, const double *lon, const double *lat, const double *p,
+                        bool staging) {
+  const size_t nnode = (size_t)nx * ny * np, ncol = (size_t)nx * ny;
+  bool same_axes = (nx == c->nx && ny == c->ny && np == c->nz && coord_type == c->coord_type);
+  if (same_axes)
+    same_axes = std::equal(lon, lon + nx, c->h_lon.begin()) && std::equal(lat, lat + ny, c->h_lat.begin()) &&
+                std::equal(p, p + np, c->h_p.begin());
+  if (staging && 4 * nnode > c->stage_cap) {
+    if (c->stage_h) CK(cudaFreeHost(c->stage_h));
+    if (c->stage_d) CK(cudaFree(c->stage_d));
+    CK(cudaMallocHost(&c->stage_h, sizeof(float) * 4 * nnode));
+    CK(cudaMalloc(&c->stage_d, sizeof(float) * 4 * nnode));
+    c->stage_cap = 4 * nnode;
+  }
+  if (same_axes) return;
+  c->lev[0].valid = c->lev[1].valid = false;
+  c->lev_valid[0] = c->lev_valid[1] = false;
+  for (int f = 0; f < MPB_NX2; f++) { if (c->x2[f]) CK(cudaFree(c->x2[f])); c->x2[f] = nullptr; c->x2_valid[0][f] = c->x2_valid[1][f] = false; }
+  for (int f = 0; f < MPB_NX3; f++) { if (c->x3[f]) CK(cudaFree(c->x3[f])); c->x3[f] = nullptr; c->x3_valid[0][f] = c->x3_valid[1][f] = false; }
+  c->nx = nx; c->ny = ny; c->nz = np; c->coord_type = coord_type;
+  if (nnode > c->node_cap) {
+    if (c->nodes) CK(cudaFree(c->nodes));
+    CK(cudaMalloc(&c->nodes, sizeof(Node) * nnode));
+    c->node_cap = nnode;
+  }
+  if (ncol > c->col_cap) {
+    if (c->surf) CK(cudaFree(c->surf));
+    CK(cudaMalloc(&c->surf, sizeof(float4) * ncol));
+    c->col_cap = ncol;
+  }
+  c->h_lon.assign(lon, lon + nx);
+  c->h_lat.assign(lat, lat + ny);
+  c->h_p.assign(p, p + np);
+  c->tables = build_axis_tables(c->h_lon.data(), nx, c->h_lat.data(), ny, c->h_p.data(), np);
+  void **olds[] = {(void **)&c->ax_lon, (void **)&c->ax_lat, (void **)&c->ax_p, (void **)&c->ax_lonc,
+                   (void **)&c->ax_latc, (void **)&c->ax_pc, (void **)&c->p_lut};
+  for (void **o : olds) if (*o) { CK(cudaFree(*o)); *o = nullptr; }
+  auto up = [&](auto **dst, const auto &vec) {
+    using T = typename std::remove_reference<decltype(vec)>::type::value_type;
+    CK(cudaMalloc((void **)dst, sizeof(T) * std::max<size_t>(vec.size(), 1)));
+    CK(cudaMemcpyAsync(*dst, vec.data(), sizeof(T) * vec.size(), cudaMemcpyHostToDevice, c->stream));
+  };
+  up(&c->ax_lon, c->h_lon); up(&c->ax_lat, c->h_lat); up(&c->ax_p, c->h_p);
+  up(&c->ax_lonc, c->tables.lonc); up(&c->ax_latc, c->tables.latc); up(&c->ax_pc, c->tables.pc);
+  up(&c->p_lut, c->tables.p_lut);
+  CK(cudaStreamSynchronize(c->stream));
+}
+
 extern "C" {
 
 const char *mpb_last_error(void) { return g_err.c_str(); }
@@ -1311,9 +1541,11 @@ int mpb_destroy(mpb_ctx *c) {
   CK(cudaStreamSynchronize(c->stream));
   void *ptrs[] = {c->soa[0], c->soa[1], c->dt, c->uvwp, c->keys[0], c->keys[1], c->perm[0], c->perm[1],
                   c->cub_tmp, c->nodes, c->surf, c->ax_lon, c->ax_lat, c->ax_p, c->ax_lonc, c->ax_latc, c->ax_pc,
-                  c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_sum, c->mix_cnt,
-                  c->grid_sum, c->grid_sq, c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz, c->lev_hint, c->iso_var, c->iso_ts, c->iso_ps, c->chem_mass};
+                  c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_rec,
+                  c->grid_in_area ? nullptr : c->grid_sum, c->grid_in_area ? nullptr : c->grid_sq, c->grid_in_area ? nullptr : c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz, c->lev_hint, c->iso_var, c->iso_ts, c->iso_ps, c->chem_mass};
   for (void *p : ptrs) if (p) cudaFree(p);
+  for (int r = 0; r < kMaxRanks; r++)
+    if (c->area[r]) { if (r == c->rank) cudaFree(c->area[r]); else if (c->area_ipc[r]) cudaIpcCloseMemHandle(c->area[r]); }
   for (double *p : c->cts_time) if (p) cudaFree(p);
   for (double *p : c->cts_vmr) if (p) cudaFree(p);
   for (float2 *p : c->x2) if (p) cudaFree(p);
@@ -1341,6 +1573,11 @@ int mpb_sync(mpb_ctx *c) {
   API_BEGIN
   use(c);
   CK(cudaStreamSynchronize(c->stream));
+  if (c->peer_err && c->epoch > 0) {
+    int err = 0;
+    CK(cudaMemcpy(&err, c->peer_err, sizeof(int), cudaMemcpyDeviceToHost));
+    REQUIRE(err == 0, "a barrier over the ranks timed out: a peer did not reach the exchange step");
+  }
   API_END
 }
 
@@ -1380,52 +1617,8 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
   REQUIRE(m && m->lon && m->lat && m->p && m->u && m->v && m->w, "met view lacks axes or wind fields");
   REQUIRE(m->nx >= 2 && m->ny >= 2 && m->np >= 2, "met grid needs at least 2 nodes per axis");
   const size_t nnode = (size_t)m->nx * m->ny * m->np, ncol = (size_t)m->nx * m->ny;
-  bool same_axes = (m->nx == c->nx && m->ny == c->ny && m->np == c->nz && m->coord_type == c->coord_type);
-  if (same_axes)
-    same_axes = std::equal(m->lon, m->lon + m->nx, c->h_lon.begin()) && std::equal(m->lat, m->lat + m->ny, c->h_lat.begin()) &&
-                std::equal(m->p, m->p + m->np, c->h_p.begin());
   CK(cudaStreamSynchronize(c->stream));  // staging buffers are reused
-  if (!same_axes) {
-    // a new grid invalidates the other level too (src/mptrac.c:6545-6558 demands identical grids)
-    c->lev[0].valid = c->lev[1].valid = false;
-    c->lev_valid[0] = c->lev_valid[1] = false;
-    for (int f = 0; f < MPB_NX2; f++) { if (c->x2[f]) CK(cudaFree(c->x2[f])); c->x2[f] = nullptr; c->x2_valid[0][f] = c->x2_valid[1][f] = false; }
-    for (int f = 0; f < MPB_NX3; f++) { if (c->x3[f]) CK(cudaFree(c->x3[f])); c->x3[f] = nullptr; c->x3_valid[0][f] = c->x3_valid[1][f] = false; }
-    c->nx = m->nx; c->ny = m->ny; c->nz = m->np; c->coord_type = m->coord_type;
-    if (nnode > c->node_cap) {
-      if (c->nodes) CK(cudaFree(c->nodes));
-      CK(cudaMalloc(&c->nodes, sizeof(Node) * nnode));
-      c->node_cap = nnode;
-    }
-    if (ncol > c->col_cap) {
-      if (c->surf) CK(cudaFree(c->surf));
-      CK(cudaMalloc(&c->surf, sizeof(float4) * ncol));
-      c->col_cap = ncol;
-    }
-    if (4 * nnode > c->stage_cap) {
-      if (c->stage_h) CK(cudaFreeHost(c->stage_h));
-      if (c->stage_d) CK(cudaFree(c->stage_d));
-      CK(cudaMallocHost(&c->stage_h, sizeof(float) * 4 * nnode));
-      CK(cudaMalloc(&c->stage_d, sizeof(float) * 4 * nnode));
-      c->stage_cap = 4 * nnode;
-    }
-    c->h_lon.assign(m->lon, m->lon + m->nx);
-    c->h_lat.assign(m->lat, m->lat + m->ny);
-    c->h_p.assign(m->p, m->p + m->np);
-    c->tables = build_axis_tables(m->lon, m->nx, m->lat, m->ny, m->p, m->np);
-    void **olds[] = {(void **)&c->ax_lon, (void **)&c->ax_lat, (void **)&c->ax_p, (void **)&c->ax_lonc,
-                     (void **)&c->ax_latc, (void **)&c->ax_pc, (void **)&c->p_lut};
-    for (void **o : olds) if (*o) { CK(cudaFree(*o)); *o = nullptr; }
-    auto up = [&](auto **dst, const auto &vec) {
-      using T = typename std::remove_reference<decltype(vec)>::type::value_type;
-      CK(cudaMalloc((void **)dst, sizeof(T) * std::max<size_t>(vec.size(), 1)));
-      CK(cudaMemcpyAsync(*dst, vec.data(), sizeof(T) * vec.size(), cudaMemcpyHostToDevice, c->stream));
-    };
-    up(&c->ax_lon, c->h_lon); up(&c->ax_lat, c->h_lat); up(&c->ax_p, c->h_p);
-    up(&c->ax_lonc, c->tables.lonc); up(&c->ax_latc, c->tables.latc); up(&c->ax_pc, c->tables.pc);
-    up(&c->p_lut, c->tables.p_lut);
-    CK(cudaStreamSynchronize(c->stream));
-  }
+  ensure_grid(c, m->nx, m->ny, m->np, m->coord_type, m->lon, m->lat, m->p, true);
 
   // compact the strided host fields into the pinned staging area (columns are contiguous runs of np floats)
   const float *src3[4] = {m->u, m->v, m->w, m->t};
@@ -1777,10 +1970,7 @@ static std::vector<Op> plan_modules(const mpb_ctl_t &k, double t, unsigned mask)
   return ops;
 }
 
-static void run_modules(mpb_ctx *c, double t, unsigned mask) {
-  REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
-  const mpb_ctl_t &k = c->ctl;
-  for (const Op &o : plan_modules(k, t, mask)) {
+static void run_op(mpb_ctx *c, double t, const Op &o) {
     switch (o.kind) {
       case Op::STEP: launch_step(c, t, o.advect, o.phys, o.modules); break;
       case Op::SORT: do_sort(c); break;
@@ -1794,13 +1984,14 @@ static void run_modules(mpb_ctx *c, double t, unsigned mask) {
       case Op::BOUND_COND: launch_bound_cond(c); break;
       case Op::DECAY: launch_decay(c); break;
       case Op::CHEM_GRID: launch_chem_grid(c, t); break;
-      case Op::MIXING:
-        mixing_begin(c, t);
-        for (int i = 0; i < k.n_mix_qnt; i++)
-          if (k.mix_qnt[i] >= 0) { mixing_accumulate(c, k.mix_qnt[i]); mixing_apply(c, k.mix_qnt[i]); }
-        break;
+      case Op::MIXING: mixing_inline(c, t); break;
     }
-  }
+}
+
+static void run_modules(mpb_ctx *c, double t, unsigned mask) {
+  REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
+  REQUIRE(c->team == nullptr, "this context belongs to a team: step it through mpb_team_run_modules");
+  for (const Op &o : plan_modules(c->ctl, t, mask)) run_op(c, t, o);
 }
 
 // The plan of mpb_run_modules(ctx, t, mask) for a control structure, as text: one launch per token, e.g.
@@ -2050,34 +2241,33 @@ int mpb_module_sort(mpb_ctx *c) {
   API_END
 }
 
-int mpb_mixing_begin(mpb_ctx *c, double t) {
+// --- module_mixing split in two, for callers that sum the box records over ranks themselves (e.g. one NCCL all-reduce of
+//     mpb_device_ptr("mix_rec"), mpb_mixing_rec_len() doubles, between the two calls) ---
+int mpb_mixing_accumulate_all(mpb_ctx *c, double t) {
   API_BEGIN
   use(c);
   REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
-  mixing_begin(c, t);
+  REQUIRE(c->nranks == 1, "ranks attached through mpb_peer_attach exchange inside mpb_module_mixing / mpb_run_timestep");
+  mixing_prepare(c, t);
+  mixing_accumulate_all(c);
   API_END
 }
-int mpb_mixing_accumulate(mpb_ctx *c, int iq) {
+int mpb_mixing_apply_all(mpb_ctx *c) {
   API_BEGIN
   use(c);
-  mixing_accumulate(c, iq);
-  API_END
-}
-int mpb_mixing_apply(mpb_ctx *c, int iq) {
-  API_BEGIN
-  use(c);
-  mixing_apply(c, iq);
+  REQUIRE(c->nranks == 1 && c->mix_total > 0, "mpb_mixing_accumulate_all has not been called");
+  mixing_apply_all(c);
   API_END
 }
 int64_t mpb_mixing_nbox(mpb_ctx *c) { return c && c->have_ctl ? mixing_total(c) : -1; }
+int64_t mpb_mixing_rec_len(mpb_ctx *c) { return c && c->mix_total > 0 ? (c->nmix + 1) * c->mix_total : -1; }
 
 int mpb_module_mixing(mpb_ctx *c, double t) {
   API_BEGIN
   use(c);
   REQUIRE(c->have_ctl, "mpb_set_ctl has not been called");
-  mixing_begin(c, t);
-  for (int i = 0; i < c->ctl.n_mix_qnt; i++)
-    if (c->ctl.mix_qnt[i] >= 0) { mixing_accumulate(c, c->ctl.mix_qnt[i]); mixing_apply(c, c->ctl.mix_qnt[i]); }
+  REQUIRE(c->team == nullptr, "this context belongs to a team");
+  mixing_inline(c, t);
   API_END
 }
 
@@ -2108,12 +2298,20 @@ int mpb_grid_accumulate(mpb_ctx *c, const mpb_grid_t *g) {
   REQUIRE(nbox < (1ll << 31), "grid too large");
   ensure_boxes(c);
   const long long need = nbox * std::max(c->nq, 1);
-  if (need > c->grid_cap) {
-    if (c->grid_sum) { CK(cudaFree(c->grid_sum)); CK(cudaFree(c->grid_sq)); CK(cudaFree(c->grid_cnt)); }
+  if (c->nranks > 1) {
+    // partial arrays of a multi-rank run live in the exchange area, where rank 0 can read them (mpb_grid_reduce)
+    REQUIRE(c->area[c->rank] != nullptr && (size_t)need * 16 + (size_t)nbox * 4 <= c->area_grid_bytes,
+            "the exchange area is too small for this output grid (mpb_peer_init: boxes x (16 x quantities + 4) bytes)");
+    if (!c->grid_in_area && c->grid_sum) { CK(cudaFree(c->grid_sum)); CK(cudaFree(c->grid_sq)); CK(cudaFree(c->grid_cnt)); c->grid_cap = 0; }
+    char *g0 = grid_region(c, c->rank);
+    c->grid_sum = (double *)g0; c->grid_sq = c->grid_sum + need; c->grid_cnt = (int *)(c->grid_sq + need);
+    c->grid_in_area = true;
+  } else if (need > c->grid_cap || c->grid_in_area) {
+    if (c->grid_sum && !c->grid_in_area) { CK(cudaFree(c->grid_sum)); CK(cudaFree(c->grid_sq)); CK(cudaFree(c->grid_cnt)); }
     CK(cudaMalloc(&c->grid_sum, sizeof(double) * (size_t)need));
     CK(cudaMalloc(&c->grid_sq, sizeof(double) * (size_t)need));
     CK(cudaMalloc(&c->grid_cnt, sizeof(int) * (size_t)need));
-    c->grid_cap = need;
+    c->grid_cap = need; c->grid_in_area = false;
   }
   c->grid_nbox = nbox;
   CK(cudaMemsetAsync(c->grid_sum, 0, sizeof(double) * (size_t)need, c->stream));
@@ -2129,6 +2327,35 @@ int mpb_grid_accumulate(mpb_ctx *c, const mpb_grid_t *g) {
       c->box, c->nq ? c->q(0) : nullptr, c->np_max, c->nq, nbox, c->grid_cnt, c->grid_sum, c->grid_sq, c->np);
   CK(cudaGetLastError());
   c->launches += 2;
+  API_END
+}
+
+// rank 0 adds the partial arrays of all ranks to its own (peer reads), between two barriers; the other ranks only pass the barriers
+static void grid_pull(mpb_ctx *c) {
+  const long long nbox = c->grid_nbox, nval = nbox * std::max(c->nq, 1);
+  GridPeers G;
+  for (int r = 0; r < kMaxRanks; r++) {
+    G.sum[r] = G.sq[r] = nullptr; G.cnt[r] = nullptr;
+    if (r < c->nranks) {
+      REQUIRE(c->area[r] != nullptr, "mpb_peer_attach has not been called");
+      G.sum[r] = (const double *)grid_region(c, r); G.sq[r] = G.sum[r] + nval; G.cnt[r] = (const int *)(G.sq[r] + nval);
+    }
+  }
+  grid_pull_kernel<<<nblocks(std::max(nval, nbox), 256), 256, 0, c->stream>>>(G, c->nranks, nbox, nval, c->grid_sum, c->grid_sq, c->grid_cnt);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
+int mpb_grid_reduce(mpb_ctx *c) {
+  API_BEGIN
+  use(c);
+  REQUIRE(c->grid_nbox > 0, "mpb_grid_accumulate has not been called");
+  REQUIRE(c->team == nullptr, "this context belongs to a team");
+  if (c->nranks > 1) {
+    peer_barrier(c);
+    if (c->rank == 0) grid_pull(c);
+    peer_barrier(c);
+  }
   API_END
 }
 
@@ -2154,8 +2381,7 @@ void *mpb_device_ptr(mpb_ctx *c, const char *name) {
   if (n == "q") return c->nq ? c->q(0) : nullptr;
   if (n == "dt") return c->dt;
   if (n == "uvwp") return c->uvwp;
-  if (n == "mix_sum") return c->mix_sum;
-  if (n == "mix_cnt") return c->mix_cnt;
+  if (n == "mix_rec") return c->mix_rec;
   if (n == "grid_sum") return c->grid_sum;
   if (n == "grid_sq") return c->grid_sq;
   if (n == "grid_cnt") return c->grid_cnt;
@@ -2168,6 +2394,385 @@ int mpb_met_bytes(mpb_ctx *c, int64_t *bytes) {
   API_BEGIN
   REQUIRE(c && bytes, "null argument");
   *bytes = (long long)c->nx * c->ny * c->nz * (long long)sizeof(Node) + (long long)c->nx * c->ny * (long long)sizeof(float4);
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// ranks that exchange through peer memory
+// ------------------------------------------------------------------------------------------------
+int mpb_peer_init(mpb_ctx *c, int rank, int nranks, int64_t mix_bytes, int64_t grid_bytes, void *ipc_handle_out) {
+  API_BEGIN
+  use(c);
+  REQUIRE(nranks >= 1 && nranks <= kMaxRanks && rank >= 0 && rank < nranks, "bad rank / number of ranks");
+  REQUIRE(mix_bytes >= 0 && grid_bytes >= 0, "bad exchange area size");
+  CK(cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < kMaxRanks; r++) {
+    if (c->area[r]) { if (r == c->rank) CK(cudaFree(c->area[r])); else if (c->area_ipc[r]) cudaIpcCloseMemHandle(c->area[r]); }
+    c->area[r] = nullptr; c->area_ipc[r] = false;
+  }
+  if (c->grid_in_area) { c->grid_sum = c->grid_sq = nullptr; c->grid_cnt = nullptr; c->grid_in_area = false; c->grid_cap = 0; c->grid_nbox = 0; }
+  c->rank = rank; c->nranks = nranks;
+  c->mix_layout = -1; c->mix_set = 0; c->epoch = 0; c->peer_err = nullptr;
+  c->area_bytes = c->area_mix_bytes = c->area_grid_bytes = 0;
+  if (nranks == 1) return 0;
+  const size_t unit = 3 * 256;
+  c->area_mix_bytes = ((size_t)mix_bytes + unit - 1) / unit * unit;
+  c->area_grid_bytes = ((size_t)grid_bytes + 255) / 256 * 256;
+  c->area_bytes = kAreaHeader + c->area_mix_bytes + c->area_grid_bytes;
+  CK(cudaMalloc(&c->area[rank], c->area_bytes));
+  CK(cudaMemset(c->area[rank], 0, c->area_bytes));
+  c->peer_err = (int *)(c->area[rank] + kAreaErrOffset);
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->area[rank]));
+    static_assert(sizeof(h) == MPB_IPC_HANDLE_BYTES, "IPC handle size");
+    std::memcpy(ipc_handle_out, &h, sizeof(h));
+  }
+  API_END
+}
+
+int mpb_peer_attach(mpb_ctx *c, const void *ipc_handles) {
+  API_BEGIN
+  use(c);
+  REQUIRE(c->nranks > 1 && c->area[c->rank] != nullptr && ipc_handles != nullptr, "mpb_peer_init comes first");
+  for (int r = 0; r < c->nranks; r++) {
+    if (r == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char *)ipc_handles + (size_t)r * MPB_IPC_HANDLE_BYTES, sizeof(h));
+    void *ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->area[r] = (char *)ptr; c->area_ipc[r] = true;
+  }
+  API_END
+}
+
+int mpb_peer_attach_local(mpb_ctx *c, void *const *areas, const int *devices) {
+  API_BEGIN
+  use(c);
+  REQUIRE(c->nranks > 1 && c->area[c->rank] != nullptr && areas != nullptr && devices != nullptr, "mpb_peer_init comes first");
+  for (int r = 0; r < c->nranks; r++) {
+    if (r == c->rank) continue;
+    REQUIRE(areas[r] != nullptr, "null peer area");
+    if (devices[r] != c->device) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, c->device, devices[r]));
+      REQUIRE(can, "the devices of the team cannot access each other's memory");
+      cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else CK(e);
+    }
+    c->area[r] = (char *)areas[r]; c->area_ipc[r] = false;
+  }
+  API_END
+}
+
+void *mpb_peer_area(mpb_ctx *c) { return c && c->nranks > 1 ? c->area[c->rank] : nullptr; }
+
+int mpb_peer_barrier(mpb_ctx *c) {
+  API_BEGIN
+  use(c);
+  peer_barrier(c);
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// A team: several devices behind ONE host thread (what the reference's single-process driver needs).  Parcels are cut
+// into contiguous index ranges, one per device; every device holds both met levels (packed once, then copied from device
+// to device); steps are launched on all devices before anything is waited for; the phases of the box exchange are
+// ordered with stream events.
+// ------------------------------------------------------------------------------------------------
+struct mpb_team {
+  std::vector<mpb_ctx *> ctx;
+  std::vector<cudaEvent_t> ev;
+  std::vector<long long> off;     // parcel ranges: context i owns [off[i], off[i+1])
+  long long np = 0, np_max = 0;
+  int nq = 0;
+  size_t mix_bytes = 0, grid_bytes = 0;
+};
+
+static void team_barrier(mpb_team *T) {
+  const size_t n = T->ctx.size();
+  if (n < 2) return;
+  for (size_t i = 0; i < n; i++) { use(T->ctx[i]); CK(cudaEventRecord(T->ev[i], T->ctx[i]->stream)); }
+  for (size_t i = 0; i < n; i++) {
+    use(T->ctx[i]);
+    for (size_t j = 0; j < n; j++) if (j != i) CK(cudaStreamWaitEvent(T->ctx[i]->stream, T->ev[j], 0));
+  }
+}
+
+// exchange areas of all members large enough for `mix_bytes` of box records and `grid_bytes` of gridded output
+static void team_ensure_area(mpb_team *T, size_t mix_bytes, size_t grid_bytes) {
+  const int n = (int)T->ctx.size();
+  if (n < 2) return;
+  if (T->ctx[0]->area[0] && mix_bytes <= T->mix_bytes && grid_bytes <= T->grid_bytes) return;
+  mix_bytes = std::max(mix_bytes, T->mix_bytes); grid_bytes = std::max(grid_bytes, T->grid_bytes);
+  for (mpb_ctx *c : T->ctx) { use(c); CK(cudaStreamSynchronize(c->stream)); }
+  std::vector<void *> areas(n);
+  std::vector<int> devs(n);
+  for (int i = 0; i < n; i++) {
+    REQUIRE(mpb_peer_init(T->ctx[i], i, n, (int64_t)mix_bytes, (int64_t)grid_bytes, nullptr) == 0, g_err);
+    areas[i] = T->ctx[i]->area[i]; devs[i] = T->ctx[i]->device;
+  }
+  for (int i = 0; i < n; i++) REQUIRE(mpb_peer_attach_local(T->ctx[i], areas.data(), devs.data()) == 0, g_err);
+  T->mix_bytes = mix_bytes; T->grid_bytes = grid_bytes;
+}
+
+// copy the packed met data (both levels) and its bookkeeping from one context to another device
+static void met_clone(mpb_ctx *d, mpb_ctx *s) {
+  use(d);
+  ensure_grid(d, s->nx, s->ny, s->nz, s->coord_type, s->h_lon.data(), s->h_lat.data(), s->h_p.data(), false);
+  const size_t nnode = (size_t)s->nx * s->ny * s->nz, ncol = (size_t)s->nx * s->ny;
+  auto copy = [&](void *dst, const void *src, size_t bytes) {
+    CK(cudaMemcpyPeerAsync(dst, d->device, src, s->device, bytes, d->stream));
+  };
+  copy(d->nodes, s->nodes, sizeof(Node) * nnode);
+  copy(d->surf, s->surf, sizeof(float4) * ncol);
+  d->lev[0] = s->lev[0]; d->lev[1] = s->lev[1];
+  const size_t nlev = ncol * (size_t)s->npl;
+  if (s->lev_p && nlev > 0) {
+    if (d->npl != s->npl || nlev > d->lev_cap) {
+      for (void *o : {(void *)d->lev_p, (void *)d->lev_z, (void *)d->lev_pz}) if (o) CK(cudaFree(o));
+      CK(cudaMalloc(&d->lev_p, sizeof(LevelNode) * nlev));
+      CK(cudaMalloc(&d->lev_z, sizeof(LevelNode) * nlev));
+      CK(cudaMalloc(&d->lev_pz, sizeof(float4) * nlev));
+      d->lev_cap = nlev; d->npl = s->npl;
+    }
+    copy(d->lev_p, s->lev_p, sizeof(LevelNode) * nlev);
+    copy(d->lev_z, s->lev_z, sizeof(LevelNode) * nlev);
+    copy(d->lev_pz, s->lev_pz, sizeof(float4) * nlev);
+  }
+  d->lev_valid[0] = s->lev_valid[0]; d->lev_valid[1] = s->lev_valid[1];
+  for (int f = 0; f < MPB_NX2; f++) {
+    if (s->x2[f]) {
+      if (!d->x2[f]) CK(cudaMalloc(&d->x2[f], sizeof(float2) * ncol));
+      copy(d->x2[f], s->x2[f], sizeof(float2) * ncol);
+    }
+    d->x2_valid[0][f] = s->x2_valid[0][f]; d->x2_valid[1][f] = s->x2_valid[1][f];
+  }
+  for (int f = 0; f < MPB_NX3; f++) {
+    if (s->x3[f]) {
+      if (!d->x3[f]) CK(cudaMalloc(&d->x3[f], sizeof(float2) * nnode));
+      copy(d->x3[f], s->x3[f], sizeof(float2) * nnode);
+    }
+    d->x3_valid[0][f] = s->x3_valid[0][f]; d->x3_valid[1][f] = s->x3_valid[1][f];
+  }
+}
+
+#define TEAM_EACH(call)                                                      \
+  do {                                                                       \
+    REQUIRE(T != nullptr && !T->ctx.empty(), "null team");                   \
+    for (mpb_ctx *c : T->ctx) REQUIRE((call) == 0, g_err);                   \
+  } while (0)
+
+int mpb_team_create(mpb_team **out, int ndev, const int *devices, int64_t np_max, int nq) {
+  API_BEGIN
+  REQUIRE(out != nullptr && devices != nullptr, "null argument");
+  *out = nullptr;
+  REQUIRE(ndev >= 1 && ndev <= kMaxRanks, "a team has 1 .. MPB_MAX_RANKS members");
+  mpb_team *T = new mpb_team();
+  T->np_max = np_max; T->nq = nq;
+  const int64_t share = np_max / ndev + 1;
+  for (int i = 0; i < ndev; i++) {
+    mpb_ctx *c = nullptr;
+    if (mpb_create(&c, devices[i], share, nq) != 0) {
+      const std::string why = g_err;
+      for (mpb_ctx *x : T->ctx) { x->team = nullptr; mpb_destroy(x); }
+      delete T;
+      throw std::runtime_error(why);
+    }
+    c->team = ndev > 1 ? T : nullptr;
+    T->ctx.push_back(c);
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    T->ev.push_back(e);
+  }
+  T->off.assign(ndev + 1, 0);
+  *out = T;
+  API_END
+}
+
+int mpb_team_destroy(mpb_team *T) {
+  API_BEGIN
+  if (!T) return 0;
+  for (mpb_ctx *c : T->ctx) { use(c); CK(cudaStreamSynchronize(c->stream)); }
+  for (size_t i = 0; i < T->ctx.size(); i++) {
+    use(T->ctx[i]);
+    cudaEventDestroy(T->ev[i]);
+    T->ctx[i]->team = nullptr;
+    mpb_destroy(T->ctx[i]);
+  }
+  delete T;
+  API_END
+}
+
+int mpb_team_size(mpb_team *T) { return T ? (int)T->ctx.size() : -1; }
+mpb_ctx *mpb_team_member(mpb_team *T, int i) { return T && i >= 0 && i < (int)T->ctx.size() ? T->ctx[i] : nullptr; }
+
+int mpb_team_set_ctl(mpb_team *T, const mpb_ctl_t *ctl) {
+  API_BEGIN
+  TEAM_EACH(mpb_set_ctl(c, ctl));
+  if (T->ctx.size() > 1 && ctl->mixing_trop >= 0 && ctl->mixing_strat >= 0) {
+    int nmix = 0;
+    for (int i = 0; i < ctl->n_mix_qnt; i++) nmix += ctl->mix_qnt[i] >= 0;
+    const long long total = mixing_total(T->ctx[0]), n = (long long)T->ctx.size();
+    if (nmix > 0 && total > 0) team_ensure_area(T, 3 * sizeof(double) * (size_t)(nmix + 1) * (size_t)((total + n - 1) / n), T->grid_bytes);
+  }
+  API_END
+}
+
+int mpb_team_set_clim_tropo(mpb_team *T, int ntime, int nlat, const double *time, const double *lat, const double *tropo) {
+  API_BEGIN
+  TEAM_EACH(mpb_set_clim_tropo(c, ntime, nlat, time, lat, tropo));
+  API_END
+}
+int mpb_team_set_clim_ts(mpb_team *T, int species, int n, const double *time, const double *vmr) {
+  API_BEGIN
+  TEAM_EACH(mpb_set_clim_ts(c, species, n, time, vmr));
+  API_END
+}
+int mpb_team_set_balloon(mpb_team *T, int n, const double *ts, const double *ps) {
+  API_BEGIN
+  TEAM_EACH(mpb_set_balloon(c, n, ts, ps));
+  API_END
+}
+
+// one upload + pack on the first device, then device-to-device copies of the packed arrays (NVLink) instead of one host
+// upload per device: the host link is the scarce resource (the reference broadcasts its met data likewise, src/mptrac.c:45-69)
+int mpb_team_set_met(mpb_team *T, int slot, const mpb_met_view_t *met) {
+  API_BEGIN
+  REQUIRE(T != nullptr && !T->ctx.empty(), "null team");
+  REQUIRE(mpb_set_met(T->ctx[0], slot, met) == 0, g_err);
+  for (size_t i = 1; i < T->ctx.size(); i++) {
+    met_clone(T->ctx[i], T->ctx[0]);
+    CK(cudaEventRecord(T->ev[i], T->ctx[i]->stream));          // the source arrays must not change (mpb_team_swap_met, the next
+    use(T->ctx[0]);                                             // upload) before the copies have read them
+    CK(cudaStreamWaitEvent(T->ctx[0]->stream, T->ev[i], 0));
+  }
+  API_END
+}
+int mpb_team_swap_met(mpb_team *T) {
+  API_BEGIN
+  TEAM_EACH(mpb_swap_met(c));
+  API_END
+}
+
+int mpb_team_set_atm(mpb_team *T, int64_t np, const double *time, const double *p, const double *lon, const double *lat,
+                     const double *q, int64_t q_stride) {
+  API_BEGIN
+  REQUIRE(T != nullptr && !T->ctx.empty(), "null team");
+  REQUIRE(np >= 0 && np <= T->np_max, "np exceeds the team's capacity");
+  const long long n = (long long)T->ctx.size();
+  T->np = np;
+  for (long long i = 0; i <= n; i++) T->off[i] = np / n * i + std::min<long long>(i, np % n);   // sizes differ by at most one
+  for (long long i = 0; i < n; i++) {
+    const long long lo = T->off[i], cnt = T->off[i + 1] - lo;
+    REQUIRE(mpb_set_atm(T->ctx[i], cnt, time + lo, p + lo, lon + lo, lat + lo, q ? q + lo : nullptr, q_stride) == 0, g_err);
+    REQUIRE(mpb_set_shard(T->ctx[i], lo, np) == 0, g_err);
+  }
+  API_END
+}
+
+int mpb_team_get_atm(mpb_team *T, double *time, double *p, double *lon, double *lat, double *q, int64_t q_stride) {
+  API_BEGIN
+  REQUIRE(T != nullptr && !T->ctx.empty(), "null team");
+  for (size_t i = 0; i < T->ctx.size(); i++) {
+    const long long lo = T->off[i];
+    REQUIRE(mpb_get_atm(T->ctx[i], time ? time + lo : nullptr, p ? p + lo : nullptr, lon ? lon + lo : nullptr, lat ? lat + lo : nullptr,
+                        q ? q + lo : nullptr, q_stride) == 0, g_err);
+  }
+  API_END
+}
+
+int mpb_team_set_uvwp(mpb_team *T, const float *uvwp) {
+  API_BEGIN
+  REQUIRE(T != nullptr && uvwp != nullptr, "null argument");
+  for (size_t i = 0; i < T->ctx.size(); i++) REQUIRE(mpb_set_uvwp(T->ctx[i], uvwp + 3 * T->off[i]) == 0, g_err);
+  API_END
+}
+int mpb_team_get_uvwp(mpb_team *T, float *uvwp) {
+  API_BEGIN
+  REQUIRE(T != nullptr && uvwp != nullptr, "null argument");
+  for (size_t i = 0; i < T->ctx.size(); i++) REQUIRE(mpb_get_uvwp(T->ctx[i], uvwp + 3 * T->off[i]) == 0, g_err);
+  API_END
+}
+int mpb_team_get_dt(mpb_team *T, double *dt) {
+  API_BEGIN
+  REQUIRE(T != nullptr && dt != nullptr, "null argument");
+  for (size_t i = 0; i < T->ctx.size(); i++) REQUIRE(mpb_get_dt(T->ctx[i], dt + T->off[i]) == 0, g_err);
+  API_END
+}
+int mpb_team_set_iso_var(mpb_team *T, const double *v) {
+  API_BEGIN
+  REQUIRE(T != nullptr && v != nullptr, "null argument");
+  for (size_t i = 0; i < T->ctx.size(); i++) REQUIRE(mpb_set_iso_var(T->ctx[i], v + T->off[i]) == 0, g_err);
+  API_END
+}
+int mpb_team_get_iso_var(mpb_team *T, double *v) {
+  API_BEGIN
+  REQUIRE(T != nullptr && v != nullptr, "null argument");
+  for (size_t i = 0; i < T->ctx.size(); i++) REQUIRE(mpb_get_iso_var(T->ctx[i], v + T->off[i]) == 0, g_err);
+  API_END
+}
+int64_t mpb_team_get_np(mpb_team *T) { return T ? T->np : -1; }
+
+int mpb_team_set_rng_ctr(mpb_team *T, uint64_t ctr) {
+  API_BEGIN
+  TEAM_EACH(mpb_set_rng_ctr(c, ctr));
+  API_END
+}
+uint64_t mpb_team_get_rng_ctr(mpb_team *T) { return T && !T->ctx.empty() ? T->ctx[0]->rng_ctr : 0; }
+
+// every launch of the step goes to all devices before the next one is issued; module_mixing is cut into its phases
+int mpb_team_run_modules(mpb_team *T, double t, unsigned mask) {
+  API_BEGIN
+  REQUIRE(T != nullptr && !T->ctx.empty(), "null team");
+  REQUIRE(T->ctx[0]->have_ctl, "mpb_team_set_ctl has not been called");
+  const bool many = T->ctx.size() > 1;
+  for (const Op &o : plan_modules(T->ctx[0]->ctl, t, mask)) {
+    if (o.kind == Op::MIXING && many) {
+      bool bar = false;
+      for (mpb_ctx *c : T->ctx) { use(c); bar = mixing_prepare(c, t) || bar; }
+      if (bar) team_barrier(T);
+      for (mpb_ctx *c : T->ctx) { use(c); mixing_accumulate_all(c); }
+      team_barrier(T);
+      for (mpb_ctx *c : T->ctx) { use(c); mixing_apply_all(c); }
+    } else {
+      for (mpb_ctx *c : T->ctx) { use(c); run_op(c, t, o); }
+    }
+  }
+  API_END
+}
+int mpb_team_run_timestep(mpb_team *T, double t) { return mpb_team_run_modules(T, t, MPB_MOD_ALL); }
+
+int mpb_team_sync(mpb_team *T) {
+  API_BEGIN
+  TEAM_EACH(mpb_sync(c));
+  API_END
+}
+int64_t mpb_team_launch_count(mpb_team *T) {
+  long long n = 0;
+  if (T) for (mpb_ctx *c : T->ctx) n += c->launches;
+  return n;
+}
+
+// gridded output: partial arrays on every device, added up on the first one (mpb_team_grid_fetch reads them there)
+int mpb_team_grid_accumulate(mpb_team *T, const mpb_grid_t *g) {
+  API_BEGIN
+  REQUIRE(T != nullptr && !T->ctx.empty() && g != nullptr, "null argument");
+  const size_t nbox = (size_t)g->nx * g->ny * g->nz;
+  team_ensure_area(T, T->mix_bytes, nbox * (16 * (size_t)std::max(T->nq, 1) + 4));
+  TEAM_EACH(mpb_grid_accumulate(c, g));
+  if (T->ctx.size() > 1) {
+    team_barrier(T);
+    use(T->ctx[0]);
+    grid_pull(T->ctx[0]);
+    team_barrier(T);
+  }
+  API_END
+}
+int mpb_team_grid_fetch(mpb_team *T, int *count, double *sum, double *sumsq) {
+  API_BEGIN
+  REQUIRE(T != nullptr && !T->ctx.empty(), "null team");
+  REQUIRE(mpb_grid_fetch(T->ctx[0], count, sum, sumsq) == 0, g_err);
   API_END
 }
 

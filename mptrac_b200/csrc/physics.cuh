@@ -354,6 +354,10 @@ MPB_HD bool below_360(double x) { return (hi_word(x) & 0x7fffffffu) < 0x40768000
 static MPB_COLD double mod360_cold(double x) { return mod360(x); }
 MPB_HD double wrap360(double x) { return below_360(x) ? x : mod360_cold(x); }
 
+// the reference's macros, as ternaries in their argument order (what they do with a NaN is part of the contract)
+MPB_HD double max_of(double a, double b) { return a > b ? a : b; }    // MAX, src/mptrac.h:1378
+MPB_HD double min_of(double a, double b) { return a < b ? a : b; }    // MIN :1479
+MPB_HD double clamp_of(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }   // CLAMP :756
 MPB_HD double clamp_to(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }  // MIN(MAX(x, lo), hi)
 
 // horizontal range check before a lookup (2755-2803)
@@ -1205,8 +1209,9 @@ MPB_HD void diffuse_turbulent(const MetView &g, const ClimView &cl, const CtlVie
     const double sigma_z = sqrt(2.0 * Kz * dt_abs) * 1e-3;
     const double p_save = a.p;
     const double eps_km = 0.01;
-    const double p_up = fmax(ptop, fmin(ps, p_save + dz2dp(eps_km, p_save)));
-    const double p_dn = fmax(ptop, fmin(ps, p_save + dz2dp(-eps_km, p_save)));
+    // (MAX / MIN as the reference's ternary macros, src/mptrac.h:1378, 1479: a non-finite ps takes the same side)
+    const double p_up = max_of(ptop, min_of(ps, p_save + dz2dp(eps_km, p_save)));
+    const double p_dn = max_of(ptop, min_of(ps, p_save + dz2dp(-eps_km, p_save)));
 
     // the latitude may just have moved: the tropopause is looked up again (12753-12757)
     if (latlon && Kx > 0) pt = tropopause_pressure(cl, tk, a.lat);
@@ -1233,7 +1238,7 @@ MPB_HD void diffuse_turbulent(const MetView &g, const ClimView &cl, const CtlVie
       else if (ptrial < ptop) ptrial = ptop * ptop / ptrial;
       else break;
     }
-    a.p = fmax(ptop, fmin(ps, ptrial));
+    a.p = max_of(ptop, min_of(ps, ptrial));
   }
 }
 
@@ -1391,8 +1396,6 @@ struct PblFields {
   const float2 *ess, *nss, *shf;   // 2-D (MPB_F2_ESS, _NSS, _SHF), both time levels
   const float2 *h2o;               // 3-D (MPB_F3_H2O)
 };
-MPB_HD double max_of(double a, double b) { return a > b ? a : b; }    // MAX, src/mptrac.h:1378
-MPB_HD double clamp_of(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }   // CLAMP :756
 
 MPB_HD void diffuse_pbl(const MetView &g, const PblFields &f, uint64_t ctr, double dt, uint64_t ig, Parcel &a,
                         float &up, float &vp, float &wp) {

@@ -23,7 +23,7 @@
 #include "mptrac.h"
 #include "mptrac_b200.h"
 
-static mpb_ctx *g_ctx;
+static mpb_team *g_ctx;      /* the device side: one context per GPU behind one handle (a team of one by default) */
 static const met_t *g_slot[2];    /* host met_t mirrored by device slot 0 / 1 */
 static int g_np = -1;             /* parcels on the device */
 static int g_dev_newer;           /* device parcels are newer than the host copy */
@@ -70,15 +70,36 @@ static void check_layout(void) {
 static int ensure_ctx(const ctl_t *ctl, int np) {
   if (g_ctx && np <= g_np) return 0;
   check_layout();
-  if (g_ctx) { g_rng_ctr = mpb_get_rng_ctr(g_ctx); MPB(mpb_destroy(g_ctx)); }
-  int dev = 0;
-  const char *e = getenv("MPTRAC_B200_DEVICE");
-  if (e) dev = atoi(e);
-  MPB(mpb_create(&g_ctx, dev, np, ctl->nq));
-  MPB(mpb_set_rng_ctr(g_ctx, g_rng_ctr));
+  if (g_ctx) { g_rng_ctr = mpb_team_get_rng_ctr(g_ctx); MPB(mpb_team_destroy(g_ctx)); }
+  /* MPTRAC_B200_DEVICES="0,1,2,3" or "0-7": the parcels are cut into contiguous index ranges over these GPUs, the met data
+     is packed once and copied device to device, module_mixing exchanges its box records through peer memory -- all behind
+     this one host thread (the reference selects ONE device per MPI task, src/trac.c:75-80).  MPTRAC_B200_DEVICE=n: one GPU. */
+  int devs[MPB_MAX_RANKS], ndev = 0;
+  const char *list = getenv("MPTRAC_B200_DEVICES");
+  if (list && *list) {
+    const char *q = list;
+    while (*q && ndev < MPB_MAX_RANKS) {
+      char *end;
+      long a = strtol(q, &end, 10), b = a;
+      if (end == q) ERRMSG("mptrac_b200: cannot parse MPTRAC_B200_DEVICES=%s", list);
+      if (*end == '-') { q = end + 1; b = strtol(q, &end, 10); if (end == q || b < a) ERRMSG("mptrac_b200: cannot parse MPTRAC_B200_DEVICES=%s", list); }
+      for (long d = a; d <= b && ndev < MPB_MAX_RANKS; d++) devs[ndev++] = (int) d;
+      q = (*end == ',') ? end + 1 : end;
+      if (*end && *end != ',') ERRMSG("mptrac_b200: cannot parse MPTRAC_B200_DEVICES=%s", list);
+    }
+  } else {
+    const char *e = getenv("MPTRAC_B200_DEVICE");
+    devs[ndev++] = e ? atoi(e) : 0;
+  }
+  MPB(mpb_team_create(&g_ctx, ndev, devs, np, ctl->nq));
+  MPB(mpb_team_set_rng_ctr(g_ctx, g_rng_ctr));
   g_slot[0] = g_slot[1] = NULL;
   g_np = np;
-  if (verbose()) printf("mptrac_b200: device context for %d parcels, %d quantities on GPU %d\n", np, ctl->nq, dev);
+  if (verbose()) {
+    printf("mptrac_b200: device context for %d parcels, %d quantities on GPU", np, ctl->nq);
+    for (int i = 0; i < ndev; i++) printf("%s%d", i ? "," : " ", devs[i]);
+    printf("\n");
+  }
   return 1;
 }
 
@@ -108,6 +129,12 @@ static int tail_needs_host(const ctl_t *c) {
   const int wet = (c->wet_depo_ic_a > 0 || c->wet_depo_ic_h[0] > 0) && (c->wet_depo_bc_a > 0 || c->wet_depo_bc_h[0] > 0);
   return c->oh_chem_reaction != 0 || c->h2o2_chem_reaction != 0 || c->kpp_chem || c->tracer_chem || c->radio_decay || c->radio_depo ||
     wet || c->dry_depo_vdep > 0;
+}
+
+static int module_timers(void) {
+  static int on = -1;
+  if (on < 0) on = getenv("MPTRAC_B200_MODULE_TIMERS") ? atoi(getenv("MPTRAC_B200_MODULE_TIMERS")) : 0;
+  return on;
 }
 
 static int g_levels;   /* the control file advects on model levels: the met uploads carry pl, ul, vl, wl, zetal, zeta_dotl */
@@ -184,7 +211,7 @@ static void put_ctl(const ctl_t *c) {
     for (int f = 0; f < MPB_NX3; f++) { k.qnt_meteo[MPB_Q_ZG + f] = q3[f]; g_need3[f] |= q3[f] >= 0; }
     for (int i = 0; i < 8; i++) { k.qnt_meteo[MPB_Q_PW + i] = qm[i]; if (qm[i] >= 0) g_need3[MPB_F3_H2O] = 1; }
   }
-  MPB(mpb_set_ctl(g_ctx, &k));
+  MPB(mpb_team_set_ctl(g_ctx, &k));
 }
 
 /* Does module_meteo (src/mptrac.c:5062-5165) set any quantity of this control file that the device cannot compute
@@ -236,19 +263,19 @@ static void put_met(met_t *m) {
     for (int f = 0; f < MPB_NX2; f++) if (g_need2[f]) v.x2[f] = f2[f];
     for (int f = 0; f < MPB_NX3; f++) if (g_need3[f]) v.x3[f] = f3[f];
   }
-  MPB(mpb_set_met(g_ctx, s, &v));
+  MPB(mpb_team_set_met(g_ctx, s, &v));
   g_slot[s] = m;
   if (verbose()) printf("mptrac_b200: met level t=%.0f (%d x %d x %d) -> device slot %d\n", m->time, m->nx, m->ny, m->np, s);
 }
 
 static void put_atm(const atm_t *atm) {
-  MPB(mpb_set_atm(g_ctx, atm->np, atm->time, atm->p, atm->lon, atm->lat, &atm->q[0][0], NP));
+  MPB(mpb_team_set_atm(g_ctx, atm->np, atm->time, atm->p, atm->lon, atm->lat, &atm->q[0][0], NP));
   g_dev_newer = 0;
 }
 
 static void get_atm(atm_t *atm) {
   if (!g_ctx || !g_dev_newer) return;
-  MPB(mpb_get_atm(g_ctx, atm->time, atm->p, atm->lon, atm->lat, &atm->q[0][0], NP));
+  MPB(mpb_team_get_atm(g_ctx, atm->time, atm->p, atm->lon, atm->lat, &atm->q[0][0], NP));
   g_dev_newer = 0;
 }
 
@@ -272,16 +299,16 @@ void mptrac_update_device(const ctl_t *ctl, const cache_t *cache, const clim_t *
   if (ctl) put_ctl(ctl);
   else if (atm && last_ctl) put_ctl(last_ctl);
   if (clim && clim->tropo_ntime > 0)
-    MPB(mpb_set_clim_tropo(g_ctx, clim->tropo_ntime, clim->tropo_nlat, clim->tropo_time, clim->tropo_lat, &clim->tropo[0][0]));
+    MPB(mpb_team_set_clim_tropo(g_ctx, clim->tropo_ntime, clim->tropo_nlat, clim->tropo_time, clim->tropo_lat, &clim->tropo[0][0]));
   if (clim && device_modules()) {
     const clim_ts_t *ts[5] = {&clim->ccl4, &clim->ccl3f, &clim->ccl2f2, &clim->n2o, &clim->sf6};
     for (int i = 0; i < 5; i++)
-      if (ts[i]->ntime > 0) MPB(mpb_set_clim_ts(g_ctx, i, ts[i]->ntime, ts[i]->time, ts[i]->vmr));
+      if (ts[i]->ntime > 0) MPB(mpb_team_set_clim_ts(g_ctx, i, ts[i]->ntime, ts[i]->time, ts[i]->vmr));
   }
   if (met0 && *met0) put_met(*met0);
   if (met1 && *met1) put_met(*met1);
   if (atm) put_atm(atm);
-  if (cache && g_np >= 0 && mpb_get_np(g_ctx) > 0) MPB(mpb_set_uvwp(g_ctx, &cache->uvwp[0][0]));
+  if (cache && g_np >= 0 && mpb_team_get_np(g_ctx) > 0) MPB(mpb_team_set_uvwp(g_ctx, &cache->uvwp[0][0]));
 }
 
 void mptrac_update_host(const ctl_t *ctl, const cache_t *cache, const clim_t *clim, met_t **met0, met_t **met1,
@@ -290,17 +317,17 @@ void mptrac_update_host(const ctl_t *ctl, const cache_t *cache, const clim_t *cl
   SELECT_TIMER("UPDATE_HOST", "MEMORY");
   if (!g_ctx) return;
   if (atm) get_atm((atm_t *) atm);
-  if (cache && mpb_get_np(g_ctx) > 0) {
-    MPB(mpb_get_uvwp(g_ctx, (float *) &cache->uvwp[0][0]));
-    MPB(mpb_get_dt(g_ctx, (double *) cache->dt));
+  if (cache && mpb_team_get_np(g_ctx) > 0) {
+    MPB(mpb_team_get_uvwp(g_ctx, (float *) &cache->uvwp[0][0]));
+    MPB(mpb_team_get_dt(g_ctx, (double *) cache->dt));
   }
 }
 
 void mptrac_free(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t *met0, met_t *met1, atm_t *atm, depo_t *depo, dd_t *dd) {
   if (g_ctx) {
-    if (verbose()) printf("mptrac_b200: %lld kernel launches\n", (long long) mpb_launch_count(g_ctx));
-    g_rng_ctr = mpb_get_rng_ctr(g_ctx);     /* the next directory of the dirlist continues the stream */
-    MPB(mpb_destroy(g_ctx));
+    if (verbose()) printf("mptrac_b200: %lld kernel launches\n", (long long) mpb_team_launch_count(g_ctx));
+    g_rng_ctr = mpb_team_get_rng_ctr(g_ctx);     /* the next directory of the dirlist continues the stream */
+    MPB(mpb_team_destroy(g_ctx));
     g_ctx = NULL; g_np = -1;
   }
   if (clim == g_last_clim) g_last_clim = NULL;
@@ -312,7 +339,7 @@ void mptrac_free(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t *met0, met_t *m
 /* bring device slots in line with the (possibly swapped) host pointers, src/mptrac.c:6489-6491 */
 static void align_met(met_t *m0, met_t *m1) {
   if (g_slot[0] == m1 && g_slot[1] == m0) {
-    MPB(mpb_swap_met(g_ctx));
+    MPB(mpb_team_swap_met(g_ctx));
     const met_t *t = g_slot[0]; g_slot[0] = g_slot[1]; g_slot[1] = t;
   }
   if (g_slot[0] != m0) put_met(m0), align_met(m0, m1);
@@ -327,7 +354,7 @@ static void align_met(met_t *m0, met_t *m1) {
 static unsigned long long g_host_rng;    /* what the reference's static counter is right now */
 
 static void host_rng_catch_up(const ctl_t *ctl, cache_t *cache) {
-  const unsigned long long want = mpb_get_rng_ctr(g_ctx);
+  const unsigned long long want = mpb_team_get_rng_ctr(g_ctx);
   while (g_host_rng < want) {
     unsigned long long n = want - g_host_rng;              /* module_rng(n - 1) consumes n counters */
     if (n > 3ull * NP + 1ull) n = 3ull * NP + 1ull;        /* capacity of cache->rs */
@@ -338,22 +365,22 @@ static void host_rng_catch_up(const ctl_t *ctl, cache_t *cache) {
 
 static void host_rng_drew(unsigned long long n) {
   g_host_rng += n;
-  MPB(mpb_set_rng_ctr(g_ctx, g_host_rng));
+  MPB(mpb_team_set_rng_ctr(g_ctx, g_host_rng));
 }
 
 /* run a reference CPU module with the host copy current; the device copy is refreshed afterwards */
 #define ON_HOST(stmt)                                                         \
   do {                                                                        \
     get_atm(atm);                                                             \
-    MPB(mpb_get_uvwp(g_ctx, &cache->uvwp[0][0]));                             \
-    MPB(mpb_get_dt(g_ctx, cache->dt));                                        \
+    MPB(mpb_team_get_uvwp(g_ctx, &cache->uvwp[0][0]));                             \
+    MPB(mpb_team_get_dt(g_ctx, cache->dt));                                        \
     stmt;                                                                     \
     host_dirty = 1;                                                           \
   } while (0)
 
 #define FLUSH_HOST()                                                          \
   do {                                                                        \
-    if (host_dirty) { put_atm(atm); MPB(mpb_set_uvwp(g_ctx, &cache->uvwp[0][0])); host_dirty = 0; } \
+    if (host_dirty) { put_atm(atm); MPB(mpb_team_set_uvwp(g_ctx, &cache->uvwp[0][0])); host_dirty = 0; } \
   } while (0)
 
 void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0, met_t **met1, atm_t *atm,
@@ -390,16 +417,31 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
       module_chem_init(ctl, cache, clim, *met0, *met1, atm);
     });
     FLUSH_HOST();
-    if (dm && ctl->isosurf == 4) MPB(mpb_set_balloon(g_ctx, cache->iso_n, cache->iso_ts, cache->iso_ps));
+    if (dm && ctl->isosurf == 4) MPB(mpb_team_set_balloon(g_ctx, cache->iso_n, cache->iso_ts, cache->iso_ps));
   }
 
-  if (!pbl_cpu && !conv_cpu && !iso_cpu && !tail_cpu) {
-    MPB(mpb_run_timestep(g_ctx, t));            /* the whole step is one fused launch (+ sort / mixing kernels) */
+  if (!pbl_cpu && !conv_cpu && !iso_cpu && !tail_cpu && module_timers()) {
+    /* MPTRAC_B200_MODULE_TIMERS=1: the step in the reference's timer groups (src/mptrac.c:5893, 5071, 5176, ...), each group
+       waited for, so that the reference's own timing report lines (TIMER_MODULE_SORT / _METEO / _MIXING ...) stay comparable;
+       the per-parcel modules between the two position checks remain ONE launch and report as MODULE_B200_STEP */
+    const unsigned parcel = MPB_MOD_POSITION0 | MPB_MOD_ADVECT | MPB_MOD_DIFF_TURB | MPB_MOD_DIFF_PBL | MPB_MOD_DIFF_MESO |
+      MPB_MOD_CONVECTION | MPB_MOD_SEDI | MPB_MOD_ISOSURF | MPB_MOD_POSITION1;
+    const struct { const char *name; unsigned mask; } part[] = {
+      {"MODULE_TIMESTEPS", MPB_MOD_TIMESTEPS}, {"MODULE_SORT", MPB_MOD_SORT}, {"MODULE_B200_STEP", parcel},
+      {"MODULE_METEO", MPB_MOD_METEO}, {"MODULE_BOUND_COND", MPB_MOD_BOUND0}, {"MODULE_DECAY", MPB_MOD_DECAY},
+      {"MODULE_MIXING", MPB_MOD_MIXING}, {"MODULE_CHEM_GRID", MPB_MOD_CHEMGRID}, {"MODULE_BOUND_COND", MPB_MOD_BOUND1}};
+    for (size_t i = 0; i < sizeof(part) / sizeof(part[0]); i++) {
+      SELECT_TIMER(part[i].name, "PHYSICS");
+      MPB(mpb_team_run_modules(g_ctx, t, part[i].mask));
+      MPB(mpb_team_sync(g_ctx));
+    }
+  } else if (!pbl_cpu && !conv_cpu && !iso_cpu && !tail_cpu) {
+    MPB(mpb_team_run_timestep(g_ctx, t));            /* the whole step is one fused launch (+ sort / mixing kernels) */
   } else {
     unsigned seg = MPB_MOD_TIMESTEPS | MPB_MOD_SORT | MPB_MOD_POSITION0 | MPB_MOD_ADVECT | MPB_MOD_DIFF_TURB;
     if (dm) seg |= MPB_MOD_DIFF_PBL;
     if (pbl_cpu) {
-      MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0; g_dev_newer = 1;
+      MPB(mpb_team_run_modules(g_ctx, t, seg)); seg = 0; g_dev_newer = 1;
       ON_HOST({
         host_rng_catch_up(ctl, cache);
         module_diff_pbl(ctl, cache, *met0, *met1, atm);
@@ -410,7 +452,7 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
     seg |= MPB_MOD_DIFF_MESO;
     if (dm) seg |= MPB_MOD_CONVECTION;
     if (conv_cpu) {
-      MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0; g_dev_newer = 1;
+      MPB(mpb_team_run_modules(g_ctx, t, seg)); seg = 0; g_dev_newer = 1;
       ON_HOST({
         host_rng_catch_up(ctl, cache);
         module_convection(ctl, cache, *met0, *met1, atm);
@@ -421,14 +463,14 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
     seg |= MPB_MOD_SEDI;
     if (dm) seg |= MPB_MOD_ISOSURF;
     if (iso_cpu) {
-      MPB(mpb_run_modules(g_ctx, t, seg)); seg = 0; g_dev_newer = 1;
+      MPB(mpb_team_run_modules(g_ctx, t, seg)); seg = 0; g_dev_newer = 1;
       ON_HOST(module_isosurf(ctl, cache, *met0, *met1, atm));
       FLUSH_HOST();
     }
     seg |= MPB_MOD_POSITION1;
     if (!meteo_cpu) seg |= MPB_MOD_METEO;       /* every quantity module_meteo sets here is available on the device */
     if (dm_tail) seg |= MPB_MOD_BOUND0 | MPB_MOD_DECAY;
-    MPB(mpb_run_modules(g_ctx, t, seg));
+    MPB(mpb_team_run_modules(g_ctx, t, seg));
     g_dev_newer = 1;
     if (tail_cpu) {
       /* everything after the final position check runs through the reference's own CPU code, in its order */
@@ -454,9 +496,9 @@ void mptrac_run_timestep(ctl_t *ctl, cache_t *cache, clim_t *clim, met_t **met0,
       FLUSH_HOST();
       g_dev_newer = 0;     /* host and device hold the same parcels now */
     } else {
-      MPB(mpb_run_modules(g_ctx, t, MPB_MOD_MIXING | (dm_tail ? MPB_MOD_BOUND1 : 0u)));
+      MPB(mpb_team_run_modules(g_ctx, t, MPB_MOD_MIXING | (dm_tail ? MPB_MOD_BOUND1 : 0u)));
     }
   }
   if (!tail_cpu) g_dev_newer = 1;
-  if (!getenv("MPTRAC_B200_ASYNC")) MPB(mpb_sync(g_ctx));   /* keeps the reference's wall-clock timers honest */
+  if (!getenv("MPTRAC_B200_ASYNC")) MPB(mpb_team_sync(g_ctx));   /* keeps the reference's wall-clock timers honest */
 }

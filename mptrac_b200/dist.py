@@ -1,8 +1,10 @@
 """Multi-GPU host logic: one process per GPU, parcels sharded contiguously by index, no data-path collective for
-transport; one sum-reduction over the box arrays for inter-parcel mixing and gridded output.
+transport; ONE exchange step per model step for inter-parcel mixing and one for gridded output.
 
-``torch.distributed`` is the plumbing (NCCL on the GPUs; the same functions run on CPU tensors over gloo in
-tests/test_dist_gloo.py).  Nothing here computes physics.
+Two transports for that step: the engines' own kernels over peer memory (``attach_peers``: NVLink atomics into the owner's
+slice of the box records, flag barriers; the default of bench.py) or one ``torch.distributed`` all-reduce of the dense box
+records (``mixing_step``; NCCL on the GPUs, gloo on CPU tensors in tests/test_dist_gloo.py).  ``torch.distributed`` is the
+plumbing either way (rendezvous, handle exchange).  Nothing here computes physics.
 """
 from __future__ import annotations
 
@@ -39,40 +41,74 @@ def device_tensor(ptr: int, n: int, dtype: str, device):
     return torch.as_tensor(_Wrap(), device=device)
 
 
-def reduce_boxes(box_sum, box_cnt, group=None):
-    """Sum the per-rank partial box arrays over all ranks, in place (the one exchange step of the path)."""
+def attach_peers(engine, ctl, grid_boxes: int = 0, group=None) -> bool:
+    """Connect the ranks' engines through peer memory (one process per GPU on one node): every rank allocates its exchange
+    area, the CUDA IPC handles travel over ``torch.distributed``, every rank opens the others'.  Afterwards
+    ``engine.run_timestep`` / ``module_mixing`` / ``grid_reduce`` do their exchange steps themselves (NVLink loads, stores
+    and atomics + flag barriers in stream order; no collective library on the data path).  Returns False (and leaves the
+    engine alone) when there is only one rank."""
     import torch.distributed as dist
+    from .host import exchange_area_bytes
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return
-    dist.all_reduce(box_sum, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(box_cnt, op=dist.ReduceOp.SUM, group=group)
+        return False
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mix_bytes, grid_bytes = exchange_area_bytes(ctl, world, engine.nq, grid_boxes)
+    err = None
+    try:
+        handle = engine.peer_init(rank, world, mix_bytes, grid_bytes)
+    except Exception as exc:           # (e.g. out of memory) -- decided collectively below
+        handle, err = None, repr(exc)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    if err is None and all(h is not None for h in handles):
+        try:
+            engine.peer_attach(handles)
+        except Exception as exc:       # CUDA IPC not permitted between these processes
+            err = repr(exc)
+    errs = [None] * world
+    dist.all_gather_object(errs, err, group=group)   # also the barrier: every rank has zeroed and mapped its area
+    if any(e is not None for e in errs) or any(h is None for h in handles):
+        engine.peer_init(0, 1, 0, 0)   # back to a single, unattached rank on every rank: the caller uses the all-reduce path
+        return False
+    return True
+
+
+def reduce_records(rec, group=None):
+    """Sum the per-rank box records {count, sum of every mixed quantity} over all ranks, in place: ONE all-reduce per model
+    step whatever the number of mixed quantities (counts travel as doubles; integers below 2^53 stay exact)."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(rec, op=dist.ReduceOp.SUM, group=group)
 
 
 def mixing_step(engine, t: float, device, group=None):
-    """module_mixing (src/mptrac.c:5169) across ranks: local accumulate -> all-reduce -> local relaxation."""
-    ctl = engine.ctl
-    engine.mixing_begin(t)
-    nbox = engine.mixing_nbox
-    s = device_tensor(engine.device_ptr("mix_sum"), nbox, "f8", device)
-    c = device_tensor(engine.device_ptr("mix_cnt"), nbox, "i4", device)
-    for iq in ctl.mix_qnt:
-        if iq < 0:
-            continue
-        engine.mixing_accumulate(iq)
-        reduce_boxes(s, c, group)      # same stream as the engine (the caller passed torch's current stream)
-        engine.mixing_apply(iq)
+    """module_mixing (src/mptrac.c:5169) across ranks that are NOT attached through peer memory: local box records of all
+    mixed quantities -> ONE all-reduce -> local relaxation.  (Attached ranks just call ``engine.module_mixing``.)"""
+    import torch.distributed as dist
+    engine.mixing_accumulate_all(t)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        # (same stream as the engine: the caller made torch's current stream the engine's)
+        reduce_records(device_tensor(engine.device_ptr("mix_rec"), engine.mixing_rec_len, "f8", device), group)
+    engine.mixing_apply_all()
 
 
-def grid_output(engine, grid: dict, device, group=None, dst: int = 0):
-    """write_grid binning (src/mptrac.c:13840-13872) across ranks; returns (count, sum, sumsq) on rank ``dst``."""
+def grid_output(engine, grid: dict, device, group=None, dst: int = 0, attached: bool = False):
+    """write_grid binning (src/mptrac.c:13840-13872) across ranks; returns (count, sum, sumsq) on rank ``dst``.
+    ``attached``: the ranks are connected through peer memory -- rank 0 adds up the partial arrays itself."""
     import torch.distributed as dist
     engine.grid_accumulate(**grid)
     nbox = grid["nx"] * grid["ny"] * grid["nz"]
     nq = max(engine.nq, 1)
-    parts = [device_tensor(engine.device_ptr("grid_cnt"), nbox, "i4", device),
-             device_tensor(engine.device_ptr("grid_sum"), nbox * nq, "f8", device),
-             device_tensor(engine.device_ptr("grid_sq"), nbox * nq, "f8", device)]
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    if multi and attached:
+        assert dst == 0
+        engine.grid_reduce()
+        if dist.get_rank(group) != 0:
+            return None
+    elif multi:
+        parts = [device_tensor(engine.device_ptr("grid_cnt"), nbox, "i4", device),
+                 device_tensor(engine.device_ptr("grid_sum"), nbox * nq, "f8", device),
+                 device_tensor(engine.device_ptr("grid_sq"), nbox * nq, "f8", device)]
         for x in parts:
             dist.reduce(x, dst=dst, op=dist.ReduceOp.SUM, group=group)
         if dist.get_rank(group) != dst:

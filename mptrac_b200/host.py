@@ -289,6 +289,18 @@ def plan_modules(ctl: "Ctl", t: float, mask: int = MOD_ALL) -> str:
 
 
 _lib_cache = {}
+IPC_HANDLE_BYTES = 64      # MPB_IPC_HANDLE_BYTES
+MAX_RANKS = 16             # MPB_MAX_RANKS
+
+
+def exchange_area_bytes(ctl: "Ctl", nranks: int, nq: int, grid_boxes: int = 0):
+    """(mix_bytes, grid_bytes) of mpb_peer_init for a control structure: three sets of (mixed quantities + 1) doubles per box
+    of this rank's slice of the mixing grid; count + sum + sum of squares per box of the gridded output"""
+    nmix = sum(1 for i in ctl.mix_qnt if i >= 0)
+    total = ctl.mixing_nx * ctl.mixing_ny * ctl.mixing_nz * max(ctl.nens, 1)
+    mixing = ctl.mixing_trop >= 0 and ctl.mixing_strat >= 0 and nmix > 0
+    mix = 3 * 8 * (nmix + 1) * (-(-total // nranks)) if mixing else 0
+    return mix, grid_boxes * (16 * max(nq, 1) + 4)
 
 
 def load_library(strict: bool = False) -> C.CDLL:
@@ -342,12 +354,44 @@ def load_library(strict: bool = False) -> C.CDLL:
         "mpb_module_meteo": (i32, [vp]),
         "mpb_module_mixing": (i32, [vp, dbl]),
         "mpb_module_rng": (i32, [vp, vp, i64, i32]),
-        "mpb_mixing_begin": (i32, [vp, dbl]),
-        "mpb_mixing_accumulate": (i32, [vp, i32]),
-        "mpb_mixing_apply": (i32, [vp, i32]),
+        "mpb_mixing_accumulate_all": (i32, [vp, dbl]),
+        "mpb_mixing_apply_all": (i32, [vp]),
         "mpb_mixing_nbox": (i64, [vp]),
+        "mpb_mixing_rec_len": (i64, [vp]),
         "mpb_grid_accumulate": (i32, [vp, P(_GridStruct)]),
+        "mpb_grid_reduce": (i32, [vp]),
         "mpb_grid_fetch": (i32, [vp, vp, vp, vp]),
+        "mpb_peer_init": (i32, [vp, i32, i32, i64, i64, vp]),
+        "mpb_peer_attach": (i32, [vp, vp]),
+        "mpb_peer_attach_local": (i32, [vp, P(vp), P(i32)]),
+        "mpb_peer_area": (vp, [vp]),
+        "mpb_peer_barrier": (i32, [vp]),
+        "mpb_team_create": (i32, [P(vp), i32, P(i32), i64, i32]),
+        "mpb_team_destroy": (i32, [vp]),
+        "mpb_team_size": (i32, [vp]),
+        "mpb_team_member": (vp, [vp, i32]),
+        "mpb_team_set_ctl": (i32, [vp, P(_CtlStruct)]),
+        "mpb_team_set_clim_tropo": (i32, [vp, i32, i32, vp, vp, vp]),
+        "mpb_team_set_clim_ts": (i32, [vp, i32, i32, vp, vp]),
+        "mpb_team_set_balloon": (i32, [vp, i32, vp, vp]),
+        "mpb_team_set_met": (i32, [vp, i32, P(_MetViewStruct)]),
+        "mpb_team_swap_met": (i32, [vp]),
+        "mpb_team_set_atm": (i32, [vp, i64, vp, vp, vp, vp, vp, i64]),
+        "mpb_team_get_atm": (i32, [vp, vp, vp, vp, vp, vp, i64]),
+        "mpb_team_set_uvwp": (i32, [vp, vp]),
+        "mpb_team_get_uvwp": (i32, [vp, vp]),
+        "mpb_team_get_dt": (i32, [vp, vp]),
+        "mpb_team_set_iso_var": (i32, [vp, vp]),
+        "mpb_team_get_iso_var": (i32, [vp, vp]),
+        "mpb_team_get_np": (i64, [vp]),
+        "mpb_team_set_rng_ctr": (i32, [vp, u64]),
+        "mpb_team_get_rng_ctr": (u64, [vp]),
+        "mpb_team_run_timestep": (i32, [vp, dbl]),
+        "mpb_team_run_modules": (i32, [vp, dbl, C.c_uint]),
+        "mpb_team_sync": (i32, [vp]),
+        "mpb_team_launch_count": (i64, [vp]),
+        "mpb_team_grid_accumulate": (i32, [vp, P(_GridStruct)]),
+        "mpb_team_grid_fetch": (i32, [vp, vp, vp, vp]),
         "mpb_device_ptr": (vp, [vp, C.c_char_p]),
         "mpb_launch_count": (i64, [vp]),
         "mpb_met_bytes": (i32, [vp, P(i64)]),
@@ -372,6 +416,7 @@ class Engine:
         self._h = C.c_void_p()
         self.nq = int(nq)
         self.np_max = int(np_max)
+        self.device = int(device)
         rc = self._lib.mpb_create(C.byref(self._h), int(device), int(np_max), int(nq))
         if rc:
             self._h = C.c_void_p()
@@ -568,14 +613,41 @@ class Engine:
     def module_mixing(self, t: float):
         self._ck(self._lib.mpb_module_mixing(self._h, float(t)))
 
-    def mixing_begin(self, t: float):
-        self._ck(self._lib.mpb_mixing_begin(self._h, float(t)))
+    def mixing_accumulate_all(self, t: float):
+        """box index per parcel + this rank's contributions of ALL mixed quantities to the box records"""
+        self._ck(self._lib.mpb_mixing_accumulate_all(self._h, float(t)))
 
-    def mixing_accumulate(self, iq: int):
-        self._ck(self._lib.mpb_mixing_accumulate(self._h, int(iq)))
+    def mixing_apply_all(self):
+        self._ck(self._lib.mpb_mixing_apply_all(self._h))
 
-    def mixing_apply(self, iq: int):
-        self._ck(self._lib.mpb_mixing_apply(self._h, int(iq)))
+    @property
+    def mixing_rec_len(self) -> int:
+        return int(self._lib.mpb_mixing_rec_len(self._h))
+
+    # -- ranks that exchange through peer memory ----------------------------------------------------
+    def peer_init(self, rank: int, nranks: int, mix_bytes: int, grid_bytes: int) -> bytes:
+        """allocate this rank's exchange area; returns the handle the other ranks attach"""
+        h = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._ck(self._lib.mpb_peer_init(self._h, int(rank), int(nranks), int(mix_bytes), int(grid_bytes), h))
+        return h.raw
+
+    def peer_attach(self, handles):
+        """handles of all ranks in rank order (other processes' areas are opened through CUDA IPC)"""
+        blob = b"".join(handles)
+        self._ck(self._lib.mpb_peer_attach(self._h, C.c_char_p(blob)))
+
+    def peer_attach_local(self, engines):
+        """contexts of THIS process (rank order): their areas are attached directly"""
+        n = len(engines)
+        areas = (C.c_void_p * n)(*[e._lib.mpb_peer_area(e._h) for e in engines])
+        devs = (C.c_int * n)(*[e.device for e in engines])
+        self._ck(self._lib.mpb_peer_attach_local(self._h, areas, devs))
+
+    def peer_barrier(self):
+        self._ck(self._lib.mpb_peer_barrier(self._h))
+
+    def grid_reduce(self):
+        self._ck(self._lib.mpb_grid_reduce(self._h))
 
     @property
     def mixing_nbox(self) -> int:
@@ -610,3 +682,132 @@ class Engine:
         b = C.c_int64()
         self._ck(self._lib.mpb_met_bytes(self._h, C.byref(b)))
         return int(b.value)
+
+
+class Team:
+    """Several devices behind one host thread (``mpb_team_*``): the whole parcel set is cut into contiguous index ranges, one
+    per device; the calls mirror :class:`Engine`.  ``devices`` may name the same device twice (two contexts on one GPU:
+    how the multi-device logic is exercised on a single-GPU box)."""
+
+    def __init__(self, devices: Sequence[int], np_max: int, nq: int = 0, strict: bool = False):
+        self._lib = load_library(strict)
+        self._h = C.c_void_p()
+        self.nq, self.np_max, self.devices = int(nq), int(np_max), [int(d) for d in devices]
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        rc = self._lib.mpb_team_create(C.byref(self._h), len(self.devices), devs, int(np_max), int(nq))
+        if rc:
+            self._h = C.c_void_p()
+            raise MpbError(self._lib.mpb_last_error().decode())
+
+    def _ck(self, rc: int):
+        if rc:
+            raise MpbError(self._lib.mpb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.mpb_team_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __len__(self):
+        return int(self._lib.mpb_team_size(self._h))
+
+    def set_ctl(self, ctl: Ctl):
+        s = ctl.to_struct()
+        self._ck(self._lib.mpb_team_set_ctl(self._h, C.byref(s)))
+        self.ctl = ctl
+
+    def set_clim_tropo(self, time, lat, tropo):
+        time, lat, tropo = (np.ascontiguousarray(a, np.float64) for a in (time, lat, tropo))
+        self._ck(self._lib.mpb_team_set_clim_tropo(self._h, time.size, lat.size, _ptr(time), _ptr(lat), _ptr(tropo)))
+
+    def set_met(self, slot: int, met: Met):
+        v = met.view()
+        self._ck(self._lib.mpb_team_set_met(self._h, int(slot), C.byref(v)))
+
+    def swap_met(self):
+        self._ck(self._lib.mpb_team_swap_met(self._h))
+
+    def set_atm(self, time, p, lon, lat, q: Optional[np.ndarray] = None):
+        arrs = [np.ascontiguousarray(a, np.float64) for a in (time, p, lon, lat)]
+        n = arrs[0].size
+        stride = 0
+        if self.nq:
+            q = np.ascontiguousarray(q, np.float64)
+            if q.ndim != 2 or q.shape[0] != self.nq or q.shape[1] < n:
+                raise ValueError("q must be [nq][>=np] float64")
+            stride = q.strides[0] // 8
+        self._keep = (arrs, q)
+        self._ck(self._lib.mpb_team_set_atm(self._h, n, *[_ptr(a) for a in arrs], _ptr(q) if self.nq else None, stride))
+
+    @property
+    def np(self) -> int:
+        return int(self._lib.mpb_team_get_np(self._h))
+
+    def get_atm(self):
+        n = self.np
+        out = {k: np.empty(n, np.float64) for k in ("time", "p", "lon", "lat")}
+        out["q"] = np.empty((self.nq, n), np.float64)
+        self._ck(self._lib.mpb_team_get_atm(self._h, _ptr(out["time"]), _ptr(out["p"]), _ptr(out["lon"]), _ptr(out["lat"]),
+                                            _ptr(out["q"]) if self.nq else None, n))
+        return out
+
+    def set_uvwp(self, uvwp):
+        uvwp = np.ascontiguousarray(uvwp, np.float32)
+        self._ck(self._lib.mpb_team_set_uvwp(self._h, _ptr(uvwp)))
+        self.sync()
+
+    def get_uvwp(self) -> np.ndarray:
+        a = np.empty((self.np, 3), np.float32)
+        self._ck(self._lib.mpb_team_get_uvwp(self._h, _ptr(a)))
+        return a
+
+    def get_dt(self) -> np.ndarray:
+        a = np.empty(self.np, np.float64)
+        self._ck(self._lib.mpb_team_get_dt(self._h, _ptr(a)))
+        return a
+
+    @property
+    def rng_ctr(self) -> int:
+        return int(self._lib.mpb_team_get_rng_ctr(self._h))
+
+    @rng_ctr.setter
+    def rng_ctr(self, v: int):
+        self._ck(self._lib.mpb_team_set_rng_ctr(self._h, int(v)))
+
+    def run_timestep(self, t: float):
+        self._ck(self._lib.mpb_team_run_timestep(self._h, float(t)))
+
+    def run_modules(self, t: float, mask: int):
+        self._ck(self._lib.mpb_team_run_modules(self._h, float(t), int(mask)))
+
+    def sync(self):
+        self._ck(self._lib.mpb_team_sync(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mpb_team_launch_count(self._h))
+
+    def grid_accumulate(self, nx, ny, nz, lon0, lon1, lat0, lat1, z0, z1, t0, t1):
+        g = _GridStruct(nx, ny, nz, 0, lon0, lon1, lat0, lat1, z0, z1, t0, t1)
+        self._ck(self._lib.mpb_team_grid_accumulate(self._h, C.byref(g)))
+        self._grid_nbox = nx * ny * nz
+
+    def grid_fetch(self):
+        nb = self._grid_nbox
+        cnt = np.empty(nb, np.int32)
+        s = np.empty((self.nq, nb), np.float64)
+        sq = np.empty((self.nq, nb), np.float64)
+        self._ck(self._lib.mpb_team_grid_fetch(self._h, _ptr(cnt), _ptr(s), _ptr(sq)))
+        return cnt, s, sq

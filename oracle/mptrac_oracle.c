@@ -498,6 +498,8 @@ static double w_tropo(const orc_ctl_t *ctl, const orc_clim_t *cl, double time, d
 /* ---------------------------------------------------------------------------------------------
  * module_diff_turb, 4588-4734
  * ------------------------------------------------------------------------------------------- */
+#define REF_MAX(a, b) (((a) > (b)) ? (a) : (b))
+#define REF_MIN(a, b) (((a) < (b)) ? (a) : (b))
 static double kz_at(const orc_ctl_t *ctl, const orc_clim_t *cl, double time, double lat, double p, double pbl,
                     double ps, double *kx) {
   const double a = w_pbl(ctl, p, pbl, ps);
@@ -533,8 +535,10 @@ void orc_module_diff_turb(const orc_ctl_t *ctl, const orc_clim_t *clim, const or
     if (Kz > 0) {
       const double sz = sqrt(2.0 * Kz * dta) * 1e-3;
       const double p = atm->p[ip], eps = 0.01;
-      const double pu = fmax(ptop, fmin(ps, p + km2hpa(eps, p)));
-      const double pd = fmax(ptop, fmin(ps, p + km2hpa(-eps, p)));
+      /* MAX(ptop, MIN(ps, .)) as the reference's ternary macros (src/mptrac.h:1378, 1479): their treatment of a non-finite
+         ps (a gap in the surface data) is part of the contract */
+      const double pu = REF_MAX(ptop, REF_MIN(ps, p + km2hpa(eps, p)));
+      const double pd = REF_MAX(ptop, REF_MIN(ps, p + km2hpa(-eps, p)));
       const double Ku = kz_at(ctl, clim, atm->time[ip], atm->lat[ip], pu, pbl, ps, NULL);
       const double Kd = kz_at(ctl, clim, atm->time[ip], atm->lat[ip], pd, pbl, ps, NULL);
       const double dKdz = (Ku - Kd) / (2.0 * eps * 1e3);
@@ -546,7 +550,7 @@ void orc_module_diff_turb(const orc_ctl_t *ctl, const orc_clim_t *clim, const or
         else if (pt < ptop) pt = ptop * ptop / pt;
         else break;
       }
-      atm->p[ip] = fmax(ptop, fmin(ps, pt));
+      atm->p[ip] = REF_MAX(ptop, REF_MIN(ps, pt));
     }
   }
 }

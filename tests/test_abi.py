@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 35
     for s in syms:
         assert hasattr(lib, s), f"{s} is declared in include/mptrac_b200.h but not exported"
-    assert lib.mpb_abi_version() == 4
+    assert lib.mpb_abi_version() == 5
 
 
 def test_strict_flavour_exports_the_same_abi():

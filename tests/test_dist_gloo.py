@@ -36,7 +36,7 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from mptrac_b200 import Ctl, synth
-        from mptrac_b200.dist import gather_parcels, reduce_boxes, shard_bounds
+        from mptrac_b200.dist import gather_parcels, reduce_records, shard_bounds
         from oracle.oracle import Oracle, Parcels
         n = 20001
         m0, m1 = synth.make_met_pair(36, 19, 20, t0=0.0, dt_met=21600.0)
@@ -70,16 +70,16 @@ def _worker(rank, world, port, ret):
                     orc.run(mod, ctl, clim, m0, m1, a)
                 ctr += 3 * n + 1
             orc.run("position", ctl, clim, m0, m1, a)
-            # ---- mixing: local partial sums -> reduce_boxes -> local relaxation ----
+            # ---- mixing: local box records -> reduce_records (one all-reduce) -> local relaxation ----
             ngrid = ctl.mixing_nx * ctl.mixing_ny * ctl.mixing_nz
             z = 7.0 * np.log(1013.25 / a.p)
             ok = (np.abs(a.time - t) <= 150.0) & (a.lon >= -180) & (a.lon < 180) & (a.lat >= -90) & (a.lat < 90) & (z >= -5) & (z < 85)
             ix = ((a.lon + 180.0) / (360.0 / 36)).astype(int); iy = ((a.lat + 90.0) / (180.0 / 18)).astype(int); iz = ((z + 5.0) / (90.0 / 15)).astype(int)
             box = np.where(ok, (ix * 18 + iy) * 15 + iz, -1)
-            ssum = np.zeros(ngrid); scnt = np.zeros(ngrid, np.int32)
-            np.add.at(ssum, box[box >= 0], a.q[0][box >= 0]); np.add.at(scnt, box[box >= 0], 1)
-            ts, tc = torch.from_numpy(ssum), torch.from_numpy(scnt)
-            reduce_boxes(ts, tc)
+            rec = np.zeros((ngrid, 2))        # the engine's box records: {count, sum of the mixed quantity}
+            np.add.at(rec[:, 0], box[box >= 0], 1.0); np.add.at(rec[:, 1], box[box >= 0], a.q[0][box >= 0])
+            reduce_records(torch.from_numpy(rec))
+            scnt, ssum = rec[:, 0].astype(np.int64), rec[:, 1]
             mean = np.where(scnt > 0, ssum / np.maximum(scnt, 1), 0.0)
             w = np.array([_tropo_w(orc, clim, a.time[i], a.lat[i], a.p[i]) for i in range(nl)])
             mix = w * ctl.mixing_trop + (1 - w) * ctl.mixing_strat

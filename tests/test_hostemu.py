@@ -91,6 +91,30 @@ def test_device_source_on_host_is_bit_exact(emu, oracle, advect, diffusion, lat_
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
 
 
+def test_surface_gaps_on_host_are_bit_exact(emu, oracle):
+    """non-finite ps / pbl nodes through the device source (bilerp_guarded, time_blend_guarded, the reference's MAX / MIN
+    with a NaN): same bits and same NaN positions as the oracle, which is pinned against the reference for this case"""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    from test_oracle_vs_reference import _with_surface_gaps
+    rng = np.random.default_rng(13)
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    m0, m1 = _with_surface_gaps(m0, rng, 0.10, 0.15), _with_surface_gaps(m1, rng, 0.05, 0.0)
+    n = 20000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.05, zmax=30.0, seed=8)
+    clim = synth.make_clim_tropo()
+    ctl = Ctl(advect=2, diffusion=1, turb_mesox=0.0, turb_mesoz=0.0, turb_dz_trop=0.5, turb_dz_pbl=1.0, turb_dx_pbl=30.0,
+              t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0)
+    a, b = Parcels(tm, p, lon, lat), Parcels(tm, p, lon, lat)
+    oracle.ctr = ctr = 0
+    for s in range(3):
+        ctr = emu_timestep(emu, ctl, clim, m0, m1, a, s * 300.0, ctr)
+    oracle.run("timestep", ctl, clim, m0, m1, b, t=0.0, nsteps=3)
+    for k in ("time", "lon", "lat", "p"):
+        assert np.array_equal(getattr(a, k), getattr(b, k), equal_nan=True), k
+    assert 0 < np.mean(~np.isfinite(b.p)) < 0.5
+
+
 def test_device_sort_key_on_host(emu, oracle):
     from mptrac_b200 import synth
     from oracle.oracle import Parcels, met_struct

@@ -451,3 +451,46 @@ def test_module_chem_grid_bit_exact(oracle, reference, nens):
     oracle.run("chem_grid", ctl, clim, m0, m1, b, t=0.0)
     assert _same(a, b)
     assert 0.5 < np.mean(a.q[qi["Cx"]] > 0) < 0.9
+
+
+def _with_surface_gaps(m, rng, frac_ps, frac_pbl):
+    from dataclasses import replace
+    ps, pbl = m.ps.copy(), m.pbl.copy()
+    ps[rng.uniform(size=ps.shape) < frac_ps] = np.nan
+    pbl[rng.uniform(size=pbl.shape) < frac_pbl] = np.inf
+    ps[1, 1] = m.ps[1, 1]
+    ps[-1], pbl[-1] = ps[0], pbl[0]
+    return replace(m, ps=ps, pbl=pbl)
+
+
+def test_surface_gaps_bit_exact(oracle, reference):
+    """non-finite nodes in ps / pbl: the nearest-neighbour rule of intpol_met_space_2d, the nearer-level rule of
+    intpol_met_time_2d (src/mptrac.c:3084-3107, 3163-3169) and what MAX / MIN / the comparisons of module_diff_turb do with a
+    NaN -- bit for bit (NaN positions included) in module_meteo's ps / pbl and in whole steps with turbulent diffusion"""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    rng = np.random.default_rng(13)
+    m0, m1 = synth.make_met_pair(48, 25, 24, t0=0.0, dt_met=21600.0)
+    m0, m1 = _with_surface_gaps(m0, rng, 0.10, 0.15), _with_surface_gaps(m1, rng, 0.05, 0.0)
+    n = 20000
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.05, zmax=30.0, seed=8)
+    nq = reference.read_ctl(["ps", "pbl"], "")
+    reference.set_met(m0, m1)
+    ctl = Ctl(nq=nq, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0, met_dt_out=300.0, qnt_meteo=reference.qnt_meteo)
+    tmm = tm + rng.uniform(0.0, 21600.0, n)
+    a = Parcels(tmm, p, lon, lat, np.zeros((nq, n)))
+    b = a.copy()
+    reference.run("meteo", ctl, a)
+    oracle.run("meteo", ctl, reference.clim_tropo(), m0, m1, b, t=300.0)
+    assert np.array_equal(a.q, b.q, equal_nan=True)
+    assert 0 < np.mean(~np.isfinite(a.q)) < 0.5
+    reference.read_ctl([], "")
+    ctl = Ctl(advect=2, diffusion=1, turb_mesox=0.0, turb_mesoz=0.0, turb_dz_trop=0.5, turb_dz_pbl=1.0, turb_dx_pbl=30.0,
+              t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0)
+    a, b = Parcels(tm, p, lon, lat), Parcels(tm, p, lon, lat)
+    reference.ctr = oracle.ctr = 0
+    reference.run("timestep", ctl, a, t=0.0, nsteps=3)
+    oracle.run("timestep", ctl, reference.clim_tropo(), m0, m1, b, t=0.0, nsteps=3)
+    for k in ("lon", "lat", "p"):
+        assert np.array_equal(getattr(a, k), getattr(b, k), equal_nan=True), k
+    assert np.mean(np.isfinite(a.p)) > 0.5

@@ -289,3 +289,33 @@ def test_trac_dirlist_continues_the_random_stream(tmp_path):
     assert abserr(g0[:, 2], g1[:, 2]) > 1e-4, "both members drew the same random numbers"
     for c in range(1, 4):
         assert relerr(g1[:, c], c1[:, c]) < 2e-5 or abserr(g1[:, c], c1[:, c]) < 1e-9, c
+
+
+@pytest.mark.parametrize("variant", ["two_devices", "three_contexts_module_timers"])
+def test_trac_dt_test_on_a_team_of_devices_is_bit_identical(tmp_path, variant):
+    """MPTRAC_B200_DEVICES: the unmodified `trac` on several GPUs behind its one host thread (contiguous parcel ranges, met
+    packed once and copied device to device).  The atm files must equal the single-device run byte for byte -- turbulent and
+    mesoscale diffusion included, since random numbers are addressed by global parcel index.  On a one-GPU box the team's
+    contexts all sit on device 0 (same code path, no NVLink)."""
+    _need()
+    from mptrac_b200 import load_library
+    ndev = load_library().mpb_device_count()
+    members = 2 if variant == "two_devices" else 3
+    devices = ",".join(str(i % ndev) for i in range(members))
+    env = {"MPTRAC_B200_DEVICES": devices}
+    if variant != "two_devices":
+        env["MPTRAC_B200_MODULE_TIMERS"] = "1"
+    extra = ["ATM_BASENAME", "atm_pl"]
+    one = tmp_path / "one"
+    one.mkdir()
+    d1, _ = _run_trac(one, DT_CTL.format(met=DATA), DATA / "dt_test.ref" / "atm_split.tab", extra)
+    many = tmp_path / "many"
+    many.mkdir()
+    d2, out = _run_trac(many, DT_CTL.format(met=DATA), DATA / "dt_test.ref" / "atm_split.tab", extra, env_extra=env)
+    assert f"on GPU {devices}" in out
+    if variant != "two_devices":
+        assert "TIMER_MODULE_B200_STEP" in out and "TIMER_MODULE_METEO" in out
+    files = sorted(d1.glob("atm_pl_*.tab"))
+    assert len(files) == 7
+    for f in files:
+        assert (d2 / f.name).read_bytes() == f.read_bytes(), f.name
