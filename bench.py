@@ -188,6 +188,30 @@ def build_inputs(wl, rank, world):
     return ctl, m0, m1, (tm, p, lon, lat, q)
 
 
+def bind_to_gpu_numa_node(local):
+    """Several ranks share the host: keep this rank's threads -- and with them the pinned parcel buffers it is about to
+    allocate (first touch) -- on the NUMA node its GPU hangs off, so that host <-> device copies do not cross the socket
+    interconnect.  Returns a short description for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{dev}/numa_node").read_text())
+        if node < 0:
+            return f"GPU {dev}: no NUMA information"
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"GPU {dev} on NUMA node {node}: none of its CPUs is available to this process"
+        os.sched_setaffinity(0, cpus)
+        return f"GPU {dev} on NUMA node {node}: rank bound to {len(cpus)} CPUs of that node"
+    except Exception as exc:      # affinity is an optimisation, never a requirement
+        return f"not bound ({exc!r})"
+
+
 def exchange_transport():
     return os.environ.get("MPB_BENCH_EXCHANGE", "peers")
 
@@ -313,6 +337,7 @@ def run_ours(args):
     os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     wl = WORKLOADS[args.workload]
     if os.environ.get("MPB_BENCH_SORT_DT"):      # tuning aid: cell-sort cadence of the workload [s]
         wl = dict(wl, ctl=dict(wl["ctl"], sort_dt=float(os.environ["MPB_BENCH_SORT_DT"])))
@@ -463,7 +488,14 @@ def run_ours(args):
 
         pc = {"h2d_gbs": round(timed(lambda: db.copy_(hb, non_blocking=True)), 1),
               "d2h_gbs": round(timed(lambda: hb.copy_(db, non_blocking=True)), 1),
-              "both_gbs_per_direction": round(timed(both), 1)}
+              "both_gbs_per_direction": round(timed(both), 1), "numa": numa}
+        if world > 1:
+            # what the box gives when ALL ranks copy both ways at once: the ceiling of the host-resident (e2e) number
+            dist.barrier()
+            mine = timed(both, reps=10)
+            tsum = torch.tensor([mine], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            pc["all_ranks_at_once_gbs_per_direction"] = {"this_rank": round(mine, 1), "sum_over_ranks": round(float(tsum.item()), 1)}
         del hb, hb2, db, db2
     except Exception as exc:   # context only
         pc = {"error": repr(exc)}

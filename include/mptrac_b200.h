@@ -147,6 +147,7 @@ typedef struct mpb_grid {
 const char *mpb_last_error(void);
 int mpb_abi_version(void);
 int mpb_device_count(void);
+int mpb_warmup(int device);   /* create the device's CUDA context now (thread-safe): lets a driver hide it behind its file input */
 
 /* --- lifetime: stands in for mptrac_alloc / mptrac_free (src/mptrac.c:6294, :6377) --- */
 int mpb_create(mpb_ctx **ctx, int device, int64_t np_max, int nq);

@@ -31,6 +31,7 @@
 #include "../../include/mptrac_b200.h"
 #include "met_tables.hpp"
 #include "physics.cuh"
+#include "quad.cuh"
 
 using namespace mpb;
 
@@ -268,6 +269,95 @@ __global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The lane-per-coordinate step kernel (quad.cuh), a measured variant (MPTRAC_B200_STEP=quad): timesteps -> position ->
+// advect -> position for groups of G lanes.  Persistent: every warp walks the parcels 32 / G at a time.  The diffusion
+// modules and sedimentation stay in step_kernel (a second launch reading dt from memory, MPTRAC_B200_QUAD_SPLIT=1).
+// ------------------------------------------------------------------------------------------------
+#ifndef MPB_QUAD_MINBLOCKS
+#define MPB_QUAD_MINBLOCKS 6      // 128-thread blocks per SM the kernel is compiled for (85 registers per thread)
+#endif
+template <int ORDER, int G>
+__global__ void __launch_bounds__(128, MPB_QUAD_MINBLOCKS) quad_step_kernel(const __grid_constant__ StepArgs A) {
+  const MetView &g = A.met;
+  const QuadLane<G> q;
+  constexpr int kPerWarp = 32 / G;
+  const unsigned full = 0xffffffffu;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  LaneAxis ax;
+  ax.cells = q.j == 0 ? g.lonc : (q.j == 1 ? g.latc : g.pc);
+  ax.xx = q.j == 0 ? g.lon : (q.j == 1 ? g.lat : g.p);
+  ax.n = q.j == 0 ? g.nx : (q.j == 1 ? g.ny : g.nz);
+  ax.asc = q.j == 0 ? g.lon_asc : (q.j == 1 ? g.lat_asc : g.p_asc);
+  // the lane's coordinate array: read from the host mapping when the parcels live there (zero-copy stepping)
+  const double *src = A.in_time ? (q.j == 0 ? A.in_lon : (q.j == 1 ? A.in_lat : A.in_p)) : (q.j == 0 ? A.lon : (q.j == 1 ? A.lat : A.p));
+  double *dst = q.j == 0 ? A.lon : (q.j == 1 ? A.lat : A.p);
+  double *hdst = q.j == 0 ? A.host_lon : (q.j == 1 ? A.host_lat : A.host_p);
+  const double *tsrc = A.in_time ? A.in_time : A.time;
+  const double ptop = ldg(g.p + g.nz - 1);
+  const bool owner = q.j < 3 && q.lane < kPerWarp * G;      // this lane owns a coordinate of a parcel
+
+  for (long long first = warp0 * kPerWarp; first < A.np; first += nwarps * kPerWarp) {   // (warp-uniform)
+    const long long ip = first + q.lane / G;
+    const bool valid = owner && ip < A.np;
+    const double x_in = valid ? src[ip] : (q.j == 2 ? 500.0 : 0.0);
+    double x = x_in;
+    double time = (ip < A.np) ? tsrc[ip] : 0.0;
+    double dt;
+    if (A.modules & MOD_TIMESTEPS) {
+      Parcel a;
+      a.time = time; a.lon = a.lat = a.p = 0;      // (global met domain: the position does not enter, 5999-6042)
+      dt = parcel_dt(g, A.ctl, a);
+      if ((A.modules & MOD_STORE_DT) && valid && q.j == 0) A.dt[ip] = dt;
+    } else {
+      dt = ip < A.np ? A.dt[ip] : 0.0;
+    }
+    const bool active = valid && dt != 0;             // PARTICLE_LOOP(check_dt = 1), src/mptrac.h:1754-1759
+    if (A.modules & MOD_POS_PRE) quad_fix_position(g, q, time, ptop, x);
+
+    if (ORDER > 0) {
+      AxisCell cell;
+      cell.lo = cell.hi = cell.d = cell.rd = 0;
+      int ci = -1, hx = -1, hy = -1, hz = -1;
+      FieldCube cube;
+      // the metre -> degree divisor of the longitude lane belongs to the latitude the step starts at (3659-3673)
+      const double lat0 = __shfl_sync(full, x, q.base + 1);
+      const LonScale ks = lon_scale(0, lat0);
+      double acc = 0, f = 0, wt = 0, lat_stage = lat0;
+#pragma unroll
+      for (int i = 0; i < ORDER; i++) {
+        double xs = x, dts = 0.0;
+        if (i > 0) {
+          dts = (i == 3 ? 1.0 : 0.5) * dt;
+          xs = x + quad_convert(q.j, ks, dts * f);
+        }
+        if (ORDER == 2) lat_stage = __shfl_sync(full, xs, q.base + 1);
+        if (i != 2) wt = time_weight(g, time + dts);
+        f = quad_lookup(g, q, ax, xs, wt, cell, ci, hx, hy, hz, cube);
+        double k = 1.0;
+        if (ORDER == 2) k = (i == 0 ? 0.0 : 1.0);
+        else if (ORDER == 4) k = (i == 0 || i == 3 ? 1.0 / 6.0 : 2.0 / 6.0);
+        acc += k * f;
+      }
+      time += dt;
+      // (midpoint: the final longitude update takes the stage latitude, 3672-3673)
+      x += quad_convert(q.j, ORDER == 2 ? lon_scale(0, lat_stage) : ks, dt * acc);
+    }
+    if (A.modules & MOD_POS_POST) quad_fix_position(g, q, time, ptop, x);
+
+    if (active) {
+      dst[ip] = x;
+      if (hdst) hdst[ip] = x;
+      if (q.j == 0 && (ORDER > 0 || A.in_time)) A.time[ip] = time;
+      if (q.j == 0 && ORDER > 0 && A.host_time) A.host_time[ip] = time;
+    } else if (valid && A.in_time) {
+      dst[ip] = x_in;                                 // keep the device mirror of host-resident parcels complete
+      if (q.j == 0) A.time[ip] = time;
+    }
+  }
+}
+
 typedef void (*step_fn)(const StepArgs);
 
 template <int ADVECT>
@@ -294,7 +384,14 @@ static step_fn pick_step(int advect, unsigned phys) {
   }
 }
 
-// write four dense fields [n] into time-level `slot` (0 / 1) of the interleaved nodes
+// write four dense fields [n] into time-level `slot` (0 / 1) of the met nodes {u0,u1, v0,v1, w0,w1, t0,t1}
+__global__ void pack_met_nodes_kernel(const float *u, const float *v, const float *w, const float *t, float *nodes, int slot, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float *o = nodes + 8 * i + slot;
+  o[0] = u[i]; o[2] = v[i]; o[4] = w[i]; o[6] = t ? t[i] : 0.f;
+}
+// the same for records that keep the four values of a time level together (model-level records {h,a,b,c}0 {h,a,b,c}1)
 __global__ void pack_nodes_kernel(const float *u, const float *v, const float *w, const float *t,
                                   float4 *nodes, int slot, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -888,6 +985,7 @@ struct mpb_ctx {
   bool have_ctl = false;
 
   std::vector<std::pair<step_fn, unsigned>> resident;   // blocks the device holds at once, per step kernel
+  bool quad = false, quad_split = false;                // form of the step kernel (MPTRAC_B200_STEP, MPTRAC_B200_QUAD_SPLIT)
 
   // host-resident stepping (mpb_run_timestep_host): streams that each carry whole chunks
   cudaStream_t lane[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -999,6 +1097,26 @@ static unsigned resident_blocks(mpb_ctx *c, step_fn fn) {
   return n;
 }
 
+// Which form of the step kernel?  The default keeps one thread per parcel (step_kernel); MPTRAC_B200_STEP=quad gives every
+// coordinate of a parcel its own lane (quad.cuh) wherever that form exists: advection on a global longitude / latitude grid.
+// Measured on B200 (C2, RK4, 1 M parcels): 196 us per step against 114 us -- the lane split removes three quarters of the
+// f32 -> f64 conversions and raises issue utilisation from 38 % to 53 %, but it executes 2.7x the warp instructions (the
+// search / range check / position bookkeeping of a stage is replicated in every lane while only the 66 interpolation
+// operations are divided), profiles/r02b_*.  Kept as a tested variant, not the default.
+// (read when a context is created; MPTRAC_B200_QUAD_SPLIT=1: with diffusion / sedimentation on, advect in the quad kernel and
+// run the other modules in a second, classic launch)
+static bool quad_enabled(const mpb_ctx *c) { return c->quad; }
+static bool quad_split_enabled(const mpb_ctx *c) { return c->quad_split; }
+
+static step_fn pick_quad(int advect) {
+  switch (advect) {
+    case 1: return quad_step_kernel<1, 3>;
+    case 2: return quad_step_kernel<2, 3>;
+    case 4: return quad_step_kernel<4, 3>;
+    default: throw std::runtime_error("ADVECT must be 1, 2 or 4");
+  }
+}
+
 // launch the step kernel for parcels [off, off + cnt) on `stream`
 static void launch_range(mpb_ctx *c, StepArgs A, int advect, unsigned phys, long long off, long long cnt, cudaStream_t stream) {
   if (cnt <= 0) return;
@@ -1007,6 +1125,20 @@ static void launch_range(mpb_ctx *c, StepArgs A, int advect, unsigned phys, long
   if (A.host_time) { A.host_time += off; A.host_lon += off; A.host_lat += off; A.host_p += off; }
   if (A.rp) { A.rp += off; A.rhop += off; }
   A.np = cnt; A.ig0 += off;
+  const bool quad_ok = quad_enabled(c) && advect > 0 && A.met.coord_type == 0 && !A.met.local;
+  if (quad_ok && (phys == 0 || (quad_split_enabled(c) && !A.in_time))) {
+    step_fn qf = pick_quad(advect);
+    StepArgs Q = A;
+    if (phys != 0) Q.modules = (A.modules & (MOD_TIMESTEPS | MOD_POS_PRE)) | MOD_STORE_DT;   // the second launch reads dt from memory
+    const long long warps = (cnt + 9) / 10;            // 10 parcels per warp (groups of 3 lanes)
+    unsigned qgrid = (unsigned)std::min<long long>((warps + 3) / 4, (long long)resident_blocks(c, qf));
+    qf<<<qgrid, 128, 0, stream>>>(Q);
+    CK(cudaGetLastError());
+    c->launches++;
+    if (phys == 0) return;
+    advect = 0;
+    A.modules &= ~(MOD_TIMESTEPS | MOD_STORE_DT | MOD_POS_PRE);
+  }
   step_fn fn = pick_step(advect, phys);
   unsigned grid = nblocks(cnt, kBlock);
 #if MPB_PERSIST
@@ -1504,6 +1636,19 @@ int mpb_device_count(void) {
   return n;
 }
 
+// Create the CUDA context of `device` ahead of time (a few hundred milliseconds on a cold process).  Thread-safe; a host
+// driver can call it from a helper thread while it is still reading its input files.
+int mpb_warmup(int device) {
+  API_BEGIN
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); throw std::runtime_error("no CUDA device: mptrac_b200 has no CPU fallback"); }
+  REQUIRE(device >= 0 && device < ndev, "device index out of range");
+  CK(cudaSetDevice(device));
+  CK(cudaFree(nullptr));
+  API_END
+}
+
 int mpb_create(mpb_ctx **out, int device, int64_t np_max, int nq) {
   API_BEGIN
   REQUIRE(out != nullptr, "null output pointer");
@@ -1523,6 +1668,8 @@ int mpb_create(mpb_ctx **out, int device, int64_t np_max, int nq) {
   // partial) last tile stays inside the allocation
   c->device = device; c->np_max = (std::max<long long>(np_max, 1) + 31) / 32 * 32; c->nq = nq;
   std::memset(&c->ctl, 0, sizeof(c->ctl));
+  if (const char *e = std::getenv("MPTRAC_B200_STEP")) c->quad = std::strcmp(e, "quad") == 0;
+  if (const char *e = std::getenv("MPTRAC_B200_QUAD_SPLIT")) c->quad_split = std::atoi(e) != 0;
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   CK(cudaMalloc(&c->soa[0], sizeof(double) * (size_t)c->np_max * (size_t)(4 + nq)));
@@ -1632,8 +1779,8 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
         std::memcpy(dst + ((size_t)ix * m->ny + iy) * m->np, src3[f] + (size_t)ix * m->sx + (size_t)iy * m->sy, row);
     CK(cudaMemcpyAsync(c->stage_d + (size_t)f * nnode, dst, sizeof(float) * nnode, cudaMemcpyHostToDevice, c->stream));
   }
-  pack_nodes_kernel<<<nblocks((long long)nnode, 256), 256, 0, c->stream>>>(
-      c->stage_d, c->stage_d + nnode, c->stage_d + 2 * nnode, m->t ? c->stage_d + 3 * nnode : nullptr, (float4 *)c->nodes, slot, nnode);
+  pack_met_nodes_kernel<<<nblocks((long long)nnode, 256), 256, 0, c->stream>>>(
+      c->stage_d, c->stage_d + nnode, c->stage_d + 2 * nnode, m->t ? c->stage_d + 3 * nnode : nullptr, (float *)c->nodes, slot, nnode);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
 
@@ -1741,9 +1888,10 @@ int mpb_swap_met(mpb_ctx *c) {
   std::swap(c->lev[0], c->lev[1]);
   const size_t nnode = (size_t)c->nx * c->ny * c->nz, ncol = (size_t)c->nx * c->ny;
   if (nnode > 0 && c->nodes) {
-    swap_levels_kernel<<<nblocks((long long)nnode, 256), 256, 0, c->stream>>>((float4 *)c->nodes, nnode, (float2 *)c->surf, ncol);
+    swap_pairs_kernel<<<nblocks((long long)(4 * nnode), 256), 256, 0, c->stream>>>((float2 *)c->nodes, 4 * nnode);   // {x0, x1} -> {x1, x0}
+    swap_levels_kernel<<<nblocks((long long)ncol, 256), 256, 0, c->stream>>>(nullptr, 0, (float2 *)c->surf, ncol);
     CK(cudaGetLastError());
-    c->launches++;
+    c->launches += 2;
   }
   for (int f = 0; f < MPB_NX2; f++) {
     std::swap(c->x2_valid[0][f], c->x2_valid[1][f]);

@@ -19,6 +19,8 @@
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
+#include <pthread.h>
+#include <time.h>
 
 #include "mptrac.h"
 #include "mptrac_b200.h"
@@ -33,6 +35,50 @@ static int g_verbose = -1;
   do {                                                                   \
     if ((call) != 0) ERRMSG("mptrac_b200: %s", mpb_last_error());         \
   } while (0)
+
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+
+/* The device list of this run: MPTRAC_B200_DEVICES="0,1,2,3" or "0-7" (one simulation over several GPUs), else
+ * MPTRAC_B200_DEVICE=n, else GPU 0 (the reference selects ONE device per MPI task, src/trac.c:75-80). */
+static int device_list(int *devs) {
+  int ndev = 0;
+  const char *list = getenv("MPTRAC_B200_DEVICES");
+  if (list && *list) {
+    const char *q = list;
+    while (*q && ndev < MPB_MAX_RANKS) {
+      char *end;
+      long a = strtol(q, &end, 10), b = a;
+      if (end == q) return -1;
+      if (*end == '-') { q = end + 1; b = strtol(q, &end, 10); if (end == q || b < a) return -1; }
+      for (long d = a; d <= b && ndev < MPB_MAX_RANKS; d++) devs[ndev++] = (int) d;
+      if (*end && *end != ',') return -1;
+      q = (*end == ',') ? end + 1 : end;
+    }
+  } else {
+    const char *e = getenv("MPTRAC_B200_DEVICE");
+    devs[ndev++] = e ? atoi(e) : 0;
+  }
+  return ndev;
+}
+
+/* Creating a CUDA context takes a few hundred milliseconds on a cold process -- as long as `trac` needs to read its control
+ * file, parcels and first met files.  A helper thread does it while the driver reads (started when the shim is loaded). */
+static void *warmup_thread(void *arg) {
+  (void) arg;
+  int devs[MPB_MAX_RANKS];
+  const int n = device_list(devs);
+  for (int i = 0; i < n; i++) mpb_warmup(devs[i]);     /* errors surface later, where they can be reported properly */
+  return NULL;
+}
+__attribute__((constructor)) static void shim_loaded(void) {
+  if (getenv("MPTRAC_B200_NO_WARMUP")) return;
+  pthread_t th;
+  if (pthread_create(&th, NULL, warmup_thread, NULL) == 0) pthread_detach(th);
+}
 
 static int verbose(void) {
   if (g_verbose < 0) g_verbose = getenv("MPTRAC_B200_VERBOSE") ? atoi(getenv("MPTRAC_B200_VERBOSE")) : 0;
@@ -74,24 +120,12 @@ static int ensure_ctx(const ctl_t *ctl, int np) {
   /* MPTRAC_B200_DEVICES="0,1,2,3" or "0-7": the parcels are cut into contiguous index ranges over these GPUs, the met data
      is packed once and copied device to device, module_mixing exchanges its box records through peer memory -- all behind
      this one host thread (the reference selects ONE device per MPI task, src/trac.c:75-80).  MPTRAC_B200_DEVICE=n: one GPU. */
-  int devs[MPB_MAX_RANKS], ndev = 0;
-  const char *list = getenv("MPTRAC_B200_DEVICES");
-  if (list && *list) {
-    const char *q = list;
-    while (*q && ndev < MPB_MAX_RANKS) {
-      char *end;
-      long a = strtol(q, &end, 10), b = a;
-      if (end == q) ERRMSG("mptrac_b200: cannot parse MPTRAC_B200_DEVICES=%s", list);
-      if (*end == '-') { q = end + 1; b = strtol(q, &end, 10); if (end == q || b < a) ERRMSG("mptrac_b200: cannot parse MPTRAC_B200_DEVICES=%s", list); }
-      for (long d = a; d <= b && ndev < MPB_MAX_RANKS; d++) devs[ndev++] = (int) d;
-      q = (*end == ',') ? end + 1 : end;
-      if (*end && *end != ',') ERRMSG("mptrac_b200: cannot parse MPTRAC_B200_DEVICES=%s", list);
-    }
-  } else {
-    const char *e = getenv("MPTRAC_B200_DEVICE");
-    devs[ndev++] = e ? atoi(e) : 0;
-  }
+  int devs[MPB_MAX_RANKS];
+  const int ndev = device_list(devs);
+  if (ndev < 1) ERRMSG("mptrac_b200: cannot parse MPTRAC_B200_DEVICES=%s", getenv("MPTRAC_B200_DEVICES"));
+  const double t0 = now_s();
   MPB(mpb_team_create(&g_ctx, ndev, devs, np, ctl->nq));
+  if (verbose()) printf("mptrac_b200: context(s) created in %.3f s\n", now_s() - t0);
   MPB(mpb_team_set_rng_ctr(g_ctx, g_rng_ctr));
   g_slot[0] = g_slot[1] = NULL;
   g_np = np;
@@ -263,14 +297,17 @@ static void put_met(met_t *m) {
     for (int f = 0; f < MPB_NX2; f++) if (g_need2[f]) v.x2[f] = f2[f];
     for (int f = 0; f < MPB_NX3; f++) if (g_need3[f]) v.x3[f] = f3[f];
   }
+  const double t0 = now_s();
   MPB(mpb_team_set_met(g_ctx, s, &v));
   g_slot[s] = m;
-  if (verbose()) printf("mptrac_b200: met level t=%.0f (%d x %d x %d) -> device slot %d\n", m->time, m->nx, m->ny, m->np, s);
+  if (verbose()) printf("mptrac_b200: met level t=%.0f (%d x %d x %d) -> device slot %d in %.3f s\n", m->time, m->nx, m->ny, m->np, s, now_s() - t0);
 }
 
 static void put_atm(const atm_t *atm) {
+  const double t0 = now_s();
   MPB(mpb_team_set_atm(g_ctx, atm->np, atm->time, atm->p, atm->lon, atm->lat, &atm->q[0][0], NP));
   g_dev_newer = 0;
+  if (verbose() > 1) { MPB(mpb_team_sync(g_ctx)); printf("mptrac_b200: %d parcels -> device in %.3f s\n", atm->np, now_s() - t0); }
 }
 
 static void get_atm(atm_t *atm) {

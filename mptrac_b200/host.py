@@ -319,6 +319,7 @@ def load_library(strict: bool = False) -> C.CDLL:
         "mpb_last_error": (C.c_char_p, []),
         "mpb_abi_version": (i32, []),
         "mpb_device_count": (i32, []),
+        "mpb_warmup": (i32, [i32]),
         "mpb_create": (i32, [P(vp), i32, i64, i32]),
         "mpb_destroy": (i32, [vp]),
         "mpb_set_stream": (i32, [vp, vp]),

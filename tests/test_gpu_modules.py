@@ -219,7 +219,9 @@ def test_diff_pbl_in_the_step_vs_oracle(oracle):
     assert ctr == oracle.ctr
     assert abserr(out["lat"], ref.lat) < 1e-7 and abserr(out["time"], ref.time) == 0
     # the closure switches regime and the reflection switches side at thresholds: a few parcels may fall on the other side
-    bad = np.abs(out["p"] - ref.p) > 1e-6 * ref.p
+    # (diff_pbl keeps a velocity in m/s in the uvwp slot that diff_meso then moves the pressure with as hPa/s -- the
+    # reference shares cache->uvwp between the two modules likewise -- so some pressures of this configuration are negative)
+    bad = np.abs(out["p"] - ref.p) > 1e-6 * np.abs(ref.p)
     assert bad.mean() < 2e-3, bad.mean()
     assert np.mean(np.abs(uv - ref.uvwp) > 1e-4 * (1 + np.abs(ref.uvwp))) < 2e-3
 

@@ -23,7 +23,7 @@ class EmuCtl(C.Structure):
 @pytest.fixture(scope="module", params=[(0, 0), (1, 0), (0, 1)], ids=["cube_f32", "cube_f64", "level_cache"])
 def emu(request):
     """Every build flavour of the device physics must state the same arithmetic: both cubes of the step kernel (build flag
-    MPB_CUBE_F64) and the record cache of the model-level advection (MPB_LEVEL_CACHE, off in the shipped library)."""
+    MPB_CUBE_F64) and the model-level advection with and without its record cache (MPB_LEVEL_CACHE, on in the shipped library)."""
     if shutil.which("nvcc") is None:
         pytest.skip("nvcc not available")
     cube, cache = request.param
