@@ -256,13 +256,13 @@ int mpb_module_rng(mpb_ctx *ctx, double *rs_host, int64_t n, int method); /* src
 int mpb_mixing_accumulate_all(mpb_ctx *ctx, double t);             /* box index per parcel, records zeroed, local contributions */
 int mpb_mixing_apply_all(mpb_ctx *ctx);                            /* box means + relaxation of every mixed quantity */
 int64_t mpb_mixing_nbox(mpb_ctx *ctx);
-int64_t mpb_mixing_rec_len(mpb_ctx *ctx);                          /* (mixed quantities + 1) x boxes */
+int64_t mpb_mixing_rec_len(mpb_ctx *ctx);                          /* boxes x (mixed quantities + 1, rounded up to even) doubles */
 int mpb_grid_accumulate(mpb_ctx *ctx, const mpb_grid_t *grid);      /* -> count[nbox], sum[nq][nbox], sumsq[nq][nbox] on device */
 int mpb_grid_reduce(mpb_ctx *ctx);                                  /* attached ranks: sum over ranks onto rank 0 */
 int mpb_grid_fetch(mpb_ctx *ctx, int *count, double *sum, double *sumsq);   /* copy them to the host (any may be NULL) */
 
 /* Ranks that exchange through peer memory.  mpb_peer_init allocates this rank's exchange area -- barrier flags, its slice of
- * the box records (mix_bytes >= 3 x 8 x (mixed quantities + 1) x ceil(boxes / nranks)), its partial output arrays (grid_bytes
+ * the box records (mix_bytes >= 3 x 8 x R x ceil(boxes / nranks), R = mixed quantities + 1 rounded up to even), its partial output arrays (grid_bytes
  * >= boxes x (16 x nq + 4)) -- and exports a handle (MPB_IPC_HANDLE_BYTES) other processes open with mpb_peer_attach (handles
  * of all ranks, rank order; the caller gathers them, e.g. with its MPI / torch.distributed, and synchronises the ranks once
  * after attaching).  Contexts of one process attach each other's mpb_peer_area directly.  All ranks must then issue the same

@@ -16,6 +16,7 @@
 // every warp walks the parcels 32 at a time with the next chunk's state staged asynchronously in shared memory.
 // module_meteo (meteo_kernel), the cell sort and the box reductions are separate launches.
 #include <cub/device/device_radix_sort.cuh>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -114,25 +115,28 @@ constexpr long long kHostChunkMax = 1 << 20;    // ... at most 8 MiB
 #endif
 
 // One parcel, one model step: timesteps -> position -> advect -> diff_turb -> diff_meso -> sedi -> position, in registers.
-template <int ADVECT, unsigned PHYS>
-__device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Parcel a) {
-  double dt;
+// First part: the time step of the parcel (false = nothing to do, PARTICLE_LOOP(check_dt = 1), src/mptrac.h:1754-1759) and the
+// first position check.
+__device__ __forceinline__ bool parcel_begin(const StepArgs &A, long long ip, Parcel &a, double &dt) {
   if (A.modules & MOD_TIMESTEPS) {
     dt = parcel_dt(A.met, A.ctl, a);
     if (A.modules & MOD_STORE_DT) A.dt[ip] = dt;
   } else {
     dt = A.dt[ip];
   }
-  if (dt == 0) {  // PARTICLE_LOOP(check_dt = 1), src/mptrac.h:1754-1759
+  if (dt == 0) {
     if (A.in_time) { A.time[ip] = a.time; A.lon[ip] = a.lon; A.lat[ip] = a.lat; A.p[ip] = a.p; }   // keep the device mirror
-    return;
+    return false;
   }
-
-  const unsigned long long ig = (unsigned long long)(A.ig0 + ip);
-
-  CubeT<!(PHYS & PHYS_MESO)> cube;   // the met cell this parcel sits in, shared by every lookup of the step
-  cube_reset(cube);
   if (A.modules & MOD_POS_PRE) fix_position(A.met, a);
+  return true;
+}
+
+// Second part: the modules that look the met data up, the final position check, the stores.  `cube` = the met cell the
+// parcel sits in, shared by every lookup of the step.
+template <int ADVECT, unsigned PHYS>
+__device__ __forceinline__ void parcel_finish(const StepArgs &A, long long ip, Parcel &a, double dt, CubeT<!(PHYS & PHYS_MESO)> &cube) {
+  const unsigned long long ig = (unsigned long long)(A.ig0 + ip);
 #if MPB_CUBE_F64
   if (ADVECT > 0) {
     WindCube wc;
@@ -162,6 +166,15 @@ __device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Par
     A.host_lat[ip] = a.lat;
     A.host_p[ip] = a.p;
   }
+}
+
+template <int ADVECT, unsigned PHYS>
+__device__ __forceinline__ void step_parcel(const StepArgs &A, long long ip, Parcel a) {
+  double dt;
+  if (!parcel_begin(A, ip, a, dt)) return;
+  CubeT<!(PHYS & PHYS_MESO)> cube;
+  cube_reset(cube);
+  parcel_finish<ADVECT, PHYS>(A, ip, a, dt, cube);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -355,6 +368,104 @@ __global__ void __launch_bounds__(128, MPB_QUAD_MINBLOCKS) quad_step_kernel(cons
       dst[ip] = x_in;                                 // keep the device mirror of host-resident parcels complete
       if (q.j == 0) A.time[ip] = time;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The TMA-tile form of the step kernel (MPTRAC_B200_STEP=tile), a measured variant.  One block owns 128 consecutive parcels.
+// After a cell sort they sit in a few neighbouring grid columns, so the block (1) finds the cell of each of its parcels, (2)
+// takes the minimum cell indices as the origin of a window of TX x TY x TZ met nodes, (3) has ONE thread fetch that window
+// into shared memory with a single bulk tensor copy (cp.async.bulk.tensor.4d over the node array seen as [nx][ny][nz][8
+// floats]; completion on an mbarrier), and (4) runs the step with every cube fetch inside the window served from shared
+// memory (two 16-byte loads per node) instead of a 32-byte gather from L1 / L2 / HBM; cells outside the window -- parcels
+// that drifted since the sort, very sparse blocks -- still take the global path.
+// ------------------------------------------------------------------------------------------------
+struct TileShape {
+  int nx, ny, nz;
+};
+template <int ADVECT, unsigned PHYS>
+__global__ void __launch_bounds__(128, 4) tile_step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ CUtensorMap tmap,
+                                                           const TileShape shape) {
+  extern __shared__ __align__(128) unsigned char tile_mem[];
+  __shared__ TileRef tref;
+  __shared__ alignas(8) unsigned long long bar;
+  __shared__ int lo[3];
+  const MetView &g = A.met;
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (threadIdx.x == 0) {
+    lo[0] = lo[1] = lo[2] = 0x7fffffff;
+    mbar_init(smem_u32(&bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  Parcel a;
+  double dt = 0;
+  bool active = false;
+  CubeT<!(PHYS & PHYS_MESO)> cube;
+  cube_reset(cube);
+  if (ip < A.np) {
+    a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
+    active = parcel_begin(A, ip, a, dt);
+  }
+  // the cell the parcel starts the step in (the searches leave their intervals in the cube's axis cache)
+  int ix = 0x7fffffff, iy = 0x7fffffff, iz = 0x7fffffff;
+  if (active) {
+    double lon2, lat2;
+    clamp_horizontal(g, a.lon, a.lat, lon2, lat2);
+    ix = lon_cell(g, lon2, cube.ax);
+    iy = lat_cell(g, lat2, cube.ax);
+    iz = p_cell(g, a.p, cube.ax);
+  }
+  const unsigned full = 0xffffffffu;
+  int mx = ix, my = iy, mz = iz;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    mx = min(mx, __shfl_xor_sync(full, mx, d)); my = min(my, __shfl_xor_sync(full, my, d)); mz = min(mz, __shfl_xor_sync(full, mz, d));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&lo[0], mx); atomicMin(&lo[1], my); atomicMin(&lo[2], mz); }
+  __syncthreads();
+  const bool any = lo[0] != 0x7fffffff;      // (block-uniform)
+  if (any && threadIdx.x == 0) {
+    const int x0 = lo[0], y0 = lo[1], z0 = max(0, min(lo[2], g.nz - shape.nz));
+    tref.nodes = reinterpret_cast<const Node *>(tile_mem);
+    tref.x0 = x0; tref.y0 = y0; tref.z0 = z0; tref.nx = shape.nx; tref.ny = shape.ny; tref.nz = shape.nz;
+    const unsigned bytes = (unsigned)(shape.nx * shape.ny * shape.nz) * (unsigned)sizeof(Node);
+    mbar_expect(smem_u32(&bar), bytes);
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(tile_mem)), "l"(&tmap), "r"(0), "r"(z0), "r"(y0), "r"(x0), "r"(smem_u32(&bar)) : "memory");
+  }
+  __syncthreads();                             // tref is visible
+  if (!any) return;
+  mbar_wait(smem_u32(&bar), 0);
+  if (active) {
+    cube.tile = &tref;
+    Stencil s;
+    s.ix = ix; s.iy = iy; s.iz = iz; s.wx = s.wy = s.wz = 0;
+    fetch_cube(g, s, cube);                    // the axis cache names this cell: the cube must hold it (invariant of locate)
+    parcel_finish<ADVECT, PHYS>(A, ip, a, dt, cube);
+  }
+}
+
+typedef void (*tile_fn)(const StepArgs, const CUtensorMap, const TileShape);
+template <int ADVECT>
+static tile_fn pick_tile_phys(unsigned phys) {
+  switch (phys) {
+    case 0: return tile_step_kernel<ADVECT, 0>;
+    case 1: return tile_step_kernel<ADVECT, 1>;
+    case 2: return tile_step_kernel<ADVECT, 2>;
+    case 3: return tile_step_kernel<ADVECT, 3>;
+    case 4: return tile_step_kernel<ADVECT, 4>;
+    case 5: return tile_step_kernel<ADVECT, 5>;
+    case 6: return tile_step_kernel<ADVECT, 6>;
+    default: return tile_step_kernel<ADVECT, 7>;
+  }
+}
+static tile_fn pick_tile(int advect, unsigned phys) {
+  switch (advect) {
+    case 1: return pick_tile_phys<1>(phys);
+    case 2: return pick_tile_phys<2>(phys);
+    case 4: return pick_tile_phys<4>(phys);
+    default: throw std::runtime_error("the tile form needs ADVECT 1, 2 or 4");
   }
 }
 
@@ -719,6 +830,7 @@ struct MixArgs {
   double *rec[kMaxRanks];     // every rank's slice of the box records (this rank's own: local memory)
   long long slice;            // boxes per rank
   int nmix, ngrid;            // mixed quantities; boxes per ensemble member
+  int stride;                 // doubles per record: nmix + 1 rounded up to an even number (records are 16-byte aligned)
   const int *box;             // box of each parcel (-1 = outside)
   const double *ens;          // ensemble index per parcel (or null)
   double *q0;                 // quantity 0; quantity k starts k * q_stride further
@@ -744,7 +856,7 @@ __global__ void mix_accumulate_kernel(const __grid_constant__ MixArgs A) {
   double *rec = nullptr;
   if (tail && idx >= 0) {
     const long long owner = idx / A.slice;
-    rec = A.rec[owner] + (idx - owner * A.slice) * (A.nmix + 1);
+    rec = A.rec[owner] + (idx - owner * A.slice) * A.stride;
   }
   int n = 1;
 #pragma unroll
@@ -773,16 +885,19 @@ __global__ void mix_apply_kernel(const __grid_constant__ MixArgs A, ClimView cli
   if (b < 0) return;
   const long long idx = (long long)(A.ens ? (int)A.ens[ip] : 0) * A.ngrid + b;
   const long long owner = idx / A.slice;
-  const double *rec = A.rec[owner] + (idx - owner * A.slice) * (A.nmix + 1);
+  const double2 *rec = reinterpret_cast<const double2 *>(A.rec[owner] + (idx - owner * A.slice) * A.stride);
   double mixparam = 1.0;
   if (mix_trop < 1 || mix_strat < 1) {
     const double pt = tropopause_pressure(clim, time[ip], latlon ? lat[ip] : utm_ref_lat);
     const double w = weight_tropo(pt, p[ip]);
     mixparam = w * mix_trop + (1.0 - w) * mix_strat;
   }
-  const int n = (int)__ldcg(rec);
+  // (a record may live on another GPU: 16-byte loads, {count, sum_0} {sum_1, sum_2} ..., halve the requests over NVLink)
+  double2 v = __ldcg(rec);
+  const int n = (int)v.x;
   for (int k = 0; k < A.nmix; k++) {
-    double mean = __ldcg(rec + 1 + k);
+    if (k > 0 && (k & 1)) v = __ldcg(rec + (k + 1) / 2);
+    double mean = (k & 1) ? v.x : v.y;
     if (n > 0) mean /= n;
     double *q = A.q0 + (long long)A.iq[k] * A.q_stride + ip;
     const double qq = *q;
@@ -986,6 +1101,10 @@ struct mpb_ctx {
 
   std::vector<std::pair<step_fn, unsigned>> resident;   // blocks the device holds at once, per step kernel
   bool quad = false, quad_split = false;                // form of the step kernel (MPTRAC_B200_STEP, MPTRAC_B200_QUAD_SPLIT)
+  bool tile = false;                                    // MPTRAC_B200_STEP=tile: met window staged in shared memory by TMA
+  CUtensorMap tmap;                                     // the node array as a 4-D tensor [nx][ny][nz][8 floats] (tile form)
+  bool tmap_ok = false;
+  TileShape tshape = {0, 0, 0};
 
   // host-resident stepping (mpb_run_timestep_host): streams that each carry whole chunks
   cudaStream_t lane[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1125,6 +1244,15 @@ static void launch_range(mpb_ctx *c, StepArgs A, int advect, unsigned phys, long
   if (A.host_time) { A.host_time += off; A.host_lon += off; A.host_lat += off; A.host_p += off; }
   if (A.rp) { A.rp += off; A.rhop += off; }
   A.np = cnt; A.ig0 += off;
+  if (c->tile && c->tmap_ok && advect > 0 && !A.in_time && !A.host_time) {
+    tile_fn tf = pick_tile(advect, phys);
+    const size_t bytes = (size_t)c->tshape.nx * c->tshape.ny * c->tshape.nz * sizeof(Node);
+    if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    tf<<<nblocks(cnt, 128), 128, bytes, stream>>>(A, c->tmap, c->tshape);
+    CK(cudaGetLastError());
+    c->launches++;
+    return;
+  }
   const bool quad_ok = quad_enabled(c) && advect > 0 && A.met.coord_type == 0 && !A.met.local;
   if (quad_ok && (phys == 0 || (quad_split_enabled(c) && !A.in_time))) {
     step_fn qf = pick_quad(advect);
@@ -1279,7 +1407,7 @@ static bool mixing_prepare(mpb_ctx *c, double t) {
       c->mix_iq[c->nmix++] = k.mix_qnt[i];
     }
   c->mix_total = total;
-  const long long stride = c->nmix + 1;
+  const long long stride = (c->nmix + 2) / 2 * 2;      // {count, sums} padded to 16-byte records
   bool barrier = false;
   if (c->nranks == 1) {
     c->mix_slice = total;
@@ -1319,6 +1447,7 @@ static MixArgs mix_args(mpb_ctx *c) {
     A.rec[r] = mix_set_ptr(c, r, c->mix_set);
   }
   A.slice = c->mix_slice; A.nmix = c->nmix; A.ngrid = k.mixing_nx * k.mixing_ny * k.mixing_nz;
+  A.stride = (c->nmix + 2) / 2 * 2;
   A.box = c->box;
   A.ens = (k.nens > 0 && k.qnt_ens >= 0) ? c->q(k.qnt_ens) : nullptr;
   A.q0 = c->nq ? c->q(0) : nullptr; A.q_stride = c->np_max; A.np = c->np;
@@ -1575,6 +1704,35 @@ static void launch_meteo(mpb_ctx *c) {
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
+// The node array as a tensor for bulk tensor copies (tile form of the step kernel): float32 [nx][ny][nz][8], box = a window of
+// TX x TY x TZ whole nodes.  MPTRAC_B200_TILE="tx,ty,tz" overrides the window (default 3 x 4 x min(nz, 32): 12 KB).
+static void build_tensor_map(mpb_ctx *c) {
+  c->tmap_ok = false;
+  if (!c->tile || !c->nodes) return;
+  int tx = 3, ty = 4, tz = std::min(c->nz, 32);
+  if (const char *e = std::getenv("MPTRAC_B200_TILE")) REQUIRE(std::sscanf(e, "%d,%d,%d", &tx, &ty, &tz) == 3, "MPTRAC_B200_TILE must be tx,ty,tz");
+  REQUIRE(tx >= 2 && ty >= 2 && tz >= 2 && tx <= 256 && ty <= 256 && tz <= 256, "tile window out of range");
+  tz = std::min(tz, c->nz);
+  REQUIRE((size_t)tx * ty * tz * sizeof(Node) <= 200 * 1024, "tile window does not fit shared memory");
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+  REQUIRE(fn != nullptr && qr == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+  const cuuint64_t dims[4] = {8, (cuuint64_t)c->nz, (cuuint64_t)c->ny, (cuuint64_t)c->nx};
+  const cuuint64_t strides[3] = {sizeof(Node), sizeof(Node) * (cuuint64_t)c->nz, sizeof(Node) * (cuuint64_t)c->nz * (cuuint64_t)c->ny};
+  const cuuint32_t box[4] = {8, (cuuint32_t)tz, (cuuint32_t)ty, (cuuint32_t)tx};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = ((encode_fn)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->nodes, dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+  c->tshape = TileShape{tx, ty, tz};
+  c->tmap_ok = true;
+}
+
 // Make the context's met arrays, axis tables and (when `staging`) upload buffers fit a grid; a grid that differs from the
 // current one invalidates both met levels (src/mptrac.c:6545-6558 demands identical grids).
 static void ensure_grid(mpb_ctx *c, int nx, int ny, int np, int coord_type, const double *lon, const double *lat, const double *p,
@@ -1623,6 +1781,7 @@ static void ensure_grid(mpb_ctx *c, int nx, int ny, int np, int coord_type, cons
   up(&c->ax_lonc, c->tables.lonc); up(&c->ax_latc, c->tables.latc); up(&c->ax_pc, c->tables.pc);
   up(&c->p_lut, c->tables.p_lut);
   CK(cudaStreamSynchronize(c->stream));
+  build_tensor_map(c);
 }
 
 extern "C" {
@@ -1668,7 +1827,7 @@ int mpb_create(mpb_ctx **out, int device, int64_t np_max, int nq) {
   // partial) last tile stays inside the allocation
   c->device = device; c->np_max = (std::max<long long>(np_max, 1) + 31) / 32 * 32; c->nq = nq;
   std::memset(&c->ctl, 0, sizeof(c->ctl));
-  if (const char *e = std::getenv("MPTRAC_B200_STEP")) c->quad = std::strcmp(e, "quad") == 0;
+  if (const char *e = std::getenv("MPTRAC_B200_STEP")) { c->quad = std::strcmp(e, "quad") == 0; c->tile = std::strcmp(e, "tile") == 0; }
   if (const char *e = std::getenv("MPTRAC_B200_QUAD_SPLIT")) c->quad_split = std::atoi(e) != 0;
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
@@ -2408,7 +2567,7 @@ int mpb_mixing_apply_all(mpb_ctx *c) {
   API_END
 }
 int64_t mpb_mixing_nbox(mpb_ctx *c) { return c && c->have_ctl ? mixing_total(c) : -1; }
-int64_t mpb_mixing_rec_len(mpb_ctx *c) { return c && c->mix_total > 0 ? (c->nmix + 1) * c->mix_total : -1; }
+int64_t mpb_mixing_rec_len(mpb_ctx *c) { return c && c->mix_total > 0 ? (long long)((c->nmix + 2) / 2 * 2) * c->mix_total : -1; }
 
 int mpb_module_mixing(mpb_ctx *c, double t) {
   API_BEGIN
@@ -2762,7 +2921,7 @@ int mpb_team_set_ctl(mpb_team *T, const mpb_ctl_t *ctl) {
     int nmix = 0;
     for (int i = 0; i < ctl->n_mix_qnt; i++) nmix += ctl->mix_qnt[i] >= 0;
     const long long total = mixing_total(T->ctx[0]), n = (long long)T->ctx.size();
-    if (nmix > 0 && total > 0) team_ensure_area(T, 3 * sizeof(double) * (size_t)(nmix + 1) * (size_t)((total + n - 1) / n), T->grid_bytes);
+    if (nmix > 0 && total > 0) team_ensure_area(T, 3 * sizeof(double) * (size_t)((nmix + 2) / 2 * 2) * (size_t)((total + n - 1) / n), T->grid_bytes);
   }
   API_END
 }

@@ -513,23 +513,61 @@ MPB_HD Node load_node(const Node *ptr) {
 // DIFF = true: the lower-level nodes are replaced, once per fetch, by the fp32 differences "lower - upper" every vertical
 // lerp starts with (3023-3038), which takes those subtractions off the per-stage path; the mesoscale statistics need the
 // raw corner values, so kernels that include them use DIFF = false.
+// A window of the met grid staged in shared memory (the TMA-tile form of the step kernel, engine.cu tile_step_kernel): nodes
+// [x0, x0 + nx) x [y0, y0 + ny) x [z0, z0 + nz), z fastest, as the bulk tensor copy lays them down.
+struct TileRef {
+  const Node *nodes;
+  int x0, y0, z0, nx, ny, nz;
+};
 template <bool DIFF>
 struct CubeT {
   Node n000, n001, n010, n011, n100, n101, n110, n111;  // index order: x, y, z
   int ix, iy, iz;                                        // the cell held; ix < 0 = nothing yet
   CellAxes ax;                                           // its axis intervals
+  const TileRef *tile;                                   // cells inside this window are fetched from shared memory (or null)
 };
 using Cube = CubeT<false>;
 template <bool DIFF>
-MPB_HD void cube_reset(CubeT<DIFF> &c) { c.ix = -1; c.iy = -1; c.iz = -1; axes_reset(c.ax); }
+MPB_HD void cube_reset(CubeT<DIFF> &c) { c.ix = -1; c.iy = -1; c.iz = -1; axes_reset(c.ax); c.tile = nullptr; }
 
 MPB_HD void node_diff(Node &lo, const Node &hi) {
   lo.u0 = f_sub(lo.u0, hi.u0); lo.v0 = f_sub(lo.v0, hi.v0); lo.w0 = f_sub(lo.w0, hi.w0); lo.t0 = f_sub(lo.t0, hi.t0);
   lo.u1 = f_sub(lo.u1, hi.u1); lo.v1 = f_sub(lo.v1, hi.v1); lo.w1 = f_sub(lo.w1, hi.w1); lo.t1 = f_sub(lo.t1, hi.t1);
 }
 
+MPB_HD Node load_node_staged(const Node *ptr) {   // a node of the shared-memory window: two 16-byte loads (LDS.128)
+  Node n;
+#ifdef __CUDA_ARCH__
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(ptr);
+  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(n.u0), "=f"(n.u1), "=f"(n.v0), "=f"(n.v1) : "r"(addr));
+  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(n.w0), "=f"(n.w1), "=f"(n.t0), "=f"(n.t1) : "r"(addr));
+#else
+  n = *ptr;
+#endif
+  return n;
+}
+
 template <bool DIFF>
 MPB_HD void load_cube(const MetView &g, const Stencil &s, CubeT<DIFF> &c) {
+  if (c.tile) {
+    const TileRef &t = *c.tile;
+    const int lx = s.ix - t.x0, ly = s.iy - t.y0, lz = s.iz - t.z0;
+    if (lx >= 0 && lx < t.nx - 1 && ly >= 0 && ly < t.ny - 1 && lz >= 0 && lz < t.nz - 1) {
+      const int sy = t.nz, sx = t.ny * t.nz;
+      const Node *b = t.nodes + (lx * sx + ly * sy + lz);
+      c.n000 = load_node_staged(b);
+      c.n001 = load_node_staged(b + 1);
+      c.n010 = load_node_staged(b + sy);
+      c.n011 = load_node_staged(b + sy + 1);
+      c.n100 = load_node_staged(b + sx);
+      c.n101 = load_node_staged(b + sx + 1);
+      c.n110 = load_node_staged(b + sx + sy);
+      c.n111 = load_node_staged(b + sx + sy + 1);
+      if (DIFF) { node_diff(c.n000, c.n001); node_diff(c.n010, c.n011); node_diff(c.n100, c.n101); node_diff(c.n110, c.n111); }
+      c.ix = s.ix; c.iy = s.iy; c.iz = s.iz;
+      return;
+    }
+  }
   const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * (size_t)g.nz;
   const Node *b = g.f + ((size_t)s.ix * sx + (size_t)s.iy * sy + (size_t)s.iz);
   c.n000 = load_node(b);
@@ -1179,69 +1217,72 @@ MPB_HD double weight_tropo(double pt, double p) { return ramp_weight(fdiv(pt, 0.
 // ----------------------------------------------------------------------------------------------
 // module_diff_turb (4588-4734)
 // ----------------------------------------------------------------------------------------------
+// The layer structure of the parcel's column (surface, boundary-layer top, tropopause) and the diffusivities it implies at a
+// pressure: the control file's coefficients of the three layers blended with the two transition weights (4627-4640).  The
+// blend is evaluated at the parcel and -- for the vertical gradient of Kz -- 10 m above and below it (4664-4690): one
+// function, three pressures.  The ORDER of the floating-point operations is the reference's (it decides the last bit).
+struct Column {
+  double ps, pbl, tropopause;
+};
+struct Diffusivity {
+  double horizontal, vertical;   // Kx, Kz [m2/s]
+};
+MPB_HD Diffusivity layer_blend(const CtlView &c, const Column &col, double p) {
+  const double in_pbl = weight_pbl(c, p, col.pbl, col.ps);
+  const double in_trop = weight_tropo(col.tropopause, p) * (1.0 - in_pbl);
+  const double in_strat = 1.0 - in_pbl - in_trop;
+  Diffusivity k;
+  k.horizontal = in_pbl * c.dx_pbl + in_trop * c.dx_trop + in_strat * c.dx_strat;
+  k.vertical = in_pbl * c.dz_pbl + in_trop * c.dz_trop + in_strat * c.dz_strat;
+  return k;
+}
+
 MPB_HD void diffuse_turbulent(const MetView &g, const ClimView &cl, const CtlView &c, double dt,
                               uint64_t ig, Parcel &a) {
-  double ps, pbl;
+  Column col;
   CellAxes ax;            // a 2-D lookup of its own: the cube's axes must only move together with the cube (see locate)
   axes_reset(ax);
-  surface_at(g, a.time, a.lon, a.lat, ax, ps, pbl);
-  if (c.pbl_scheme > 0 && a.p >= pbl) return;
+  surface_at(g, a.time, a.lon, a.lat, ax, col.ps, col.pbl);
+  if (c.pbl_scheme > 0 && a.p >= col.pbl) return;      // a boundary-layer closure owns the parcels inside the PBL (4612)
 
   const double ptop = ldg(g.p + g.nz - 1);
-  const bool latlon = (g.coord_type == 0);
+  const bool on_sphere = (g.coord_type == 0);
+  const TropoTime season = tropopause_time(cl, a.time);
+  col.tropopause = tropopause_pressure(cl, season, on_sphere ? a.lat : c.utm_ref_lat);
+  const Diffusivity here = layer_blend(c, col, a.p);
+  const double span = fabs(dt);
 
-  const TropoTime tk = tropopause_time(cl, a.time);
-  double pt = tropopause_pressure(cl, tk, latlon ? a.lat : c.utm_ref_lat);
-  const double wpbl = weight_pbl(c, a.p, pbl, ps);
-  const double wtrop = weight_tropo(pt, a.p) * (1.0 - wpbl);
-  const double wstrat = 1.0 - wpbl - wtrop;
-  const double Kx = wpbl * c.dx_pbl + wtrop * c.dx_trop + wstrat * c.dx_strat;
-  const double Kz = wpbl * c.dz_pbl + wtrop * c.dz_trop + wstrat * c.dz_strat;
-  const double dt_abs = fabs(dt);
+  double g_lon, g_lat, g_p;      // the parcel's three normals of this module_rng call
+  normals3(c.ctr_turb, ig, g_lon, g_lat, g_p);
 
-  double r0, r1, r2;
-  normals3(c.ctr_turb, ig, r0, r1, r2);
-
-  if (Kx > 0) {
-    const double sigma_h = sqrt(2.0 * Kx * dt_abs);
-    a.lon += dx2coord(g.coord_type, r0 * sigma_h, a.lat);
-    a.lat += dy2coord(g.coord_type, r1 * sigma_h);
+  if (here.horizontal > 0) {
+    const double spread = sqrt(2.0 * here.horizontal * span);          // [m]
+    a.lon += dx2coord(g.coord_type, g_lon * spread, a.lat);
+    a.lat += dy2coord(g.coord_type, g_lat * spread);
   }
 
-  if (Kz > 0) {
-    const double sigma_z = sqrt(2.0 * Kz * dt_abs) * 1e-3;
-    const double p_save = a.p;
-    const double eps_km = 0.01;
+  if (here.vertical > 0) {
+    const double spread_km = sqrt(2.0 * here.vertical * span) * 1e-3;
+    const double p0 = a.p;
+    const double probe = 0.01;                                          // [km]: Kz is differenced over +-10 m
     // (MAX / MIN as the reference's ternary macros, src/mptrac.h:1378, 1479: a non-finite ps takes the same side)
-    const double p_up = max_of(ptop, min_of(ps, p_save + dz2dp(eps_km, p_save)));
-    const double p_dn = max_of(ptop, min_of(ps, p_save + dz2dp(-eps_km, p_save)));
-
+    const double p_above = max_of(ptop, min_of(col.ps, p0 + dz2dp(probe, p0)));
+    const double p_below = max_of(ptop, min_of(col.ps, p0 + dz2dp(-probe, p0)));
     // the latitude may just have moved: the tropopause is looked up again (12753-12757)
-    if (latlon && Kx > 0) pt = tropopause_pressure(cl, tk, a.lat);
+    if (on_sphere && here.horizontal > 0) col.tropopause = tropopause_pressure(cl, season, a.lat);
+    const double kz_above = layer_blend(c, col, p_above).vertical, kz_below = layer_blend(c, col, p_below).vertical;
+    // well-mixed criterion: the parcel drifts with dKz/dz + Kz dln(rho)/dz, rho ~ exp(-z / H0) (4692-4712)
+    const double gradient = fdiv(kz_above - kz_below, 2.0 * probe * 1e3);
+    const double drift = gradient + here.vertical * (-1.0 / (1e3 * kH0));
+    const double dz = g_p * spread_km + drift * span * 1e-3;            // [km]
 
-    const double wpbl_up = weight_pbl(c, p_up, pbl, ps);
-    const double wtrop_up = weight_tropo(pt, p_up) * (1.0 - wpbl_up);
-    const double wstrat_up = 1.0 - wpbl_up - wtrop_up;
-    const double Kz_up = wpbl_up * c.dz_pbl + wtrop_up * c.dz_trop + wstrat_up * c.dz_strat;
-
-    const double wpbl_dn = weight_pbl(c, p_dn, pbl, ps);
-    const double wtrop_dn = weight_tropo(pt, p_dn) * (1.0 - wpbl_dn);
-    const double wstrat_dn = 1.0 - wpbl_dn - wtrop_dn;
-    const double Kz_dn = wpbl_dn * c.dz_pbl + wtrop_dn * c.dz_trop + wstrat_dn * c.dz_strat;
-
-    const double dKz_dz = fdiv(Kz_up - Kz_dn, 2.0 * eps_km * 1e3);
-    const double dlnrho_dz = -1.0 / (1e3 * kH0);
-    const double w_drift = dKz_dz + Kz * dlnrho_dz;
-    const double dz_drift = w_drift * dt_abs * 1e-3;
-    const double dz_tot = r2 * sigma_z + dz_drift;
-
-    double ptrial = p_save + dz2dp(dz_tot, p_save);
-    for (int iter = 0; iter < 10; iter++) {
-      if (ptrial > ps) ptrial = ps * ps / ptrial;
-      else if (ptrial < ptop) ptrial = ptop * ptop / ptrial;
+    double p_new = p0 + dz2dp(dz, p0);
+    for (int bounce = 0; bounce < 10; bounce++) {                       // reflect at the surface and at the model top
+      if (p_new > col.ps) p_new = col.ps * col.ps / p_new;
+      else if (p_new < ptop) p_new = ptop * ptop / p_new;
       else break;
     }
-    a.p = max_of(ptop, min_of(ps, ptrial));
+    a.p = max_of(ptop, min_of(col.ps, p_new));
   }
 }
 
@@ -1400,9 +1441,91 @@ struct PblFields {
   const float2 *h2o;               // 3-D (MPB_F3_H2O)
 };
 
+// What the closure yields at a height: standard deviations of the three velocity components, the vertical derivative of
+// sigma_w, and the Lagrangian time scales.  One function per stability regime (4421-4531); the operation order inside each
+// formula is the reference's, everything else -- names, grouping, control flow -- is this file's.
+struct PblTurbulence {
+  double su, sv, sw;        // sigma_u, sigma_v, sigma_w [m/s]
+  double dsw_dz;            // d sigma_w / dz [1/s]
+  double tu, tv, tw;        // time scales [s]
+};
+struct PblState {
+  double depth;             // PBL depth zi [m]
+  double height;            // parcel height above ground, at least 1 m
+  double rel;               // height / depth, kept inside (0, 1)
+  double ustar;             // friction velocity, at least 1e-4 m/s
+  double obukhov;           // Monin-Obukhov length [m] (1e12 = neutral)
+};
+MPB_HD PblTurbulence pbl_neutral(const PblState &b) {
+  PblTurbulence t;
+  const double ratio = b.height / b.ustar;
+  const double sw0 = 1.3 * b.ustar * exp(-2e-4 * ratio);
+  t.su = max_of(2.0 * b.ustar * exp(-3e-4 * ratio), 1e-5);
+  t.sv = max_of(sw0, 1e-5);
+  t.sw = max_of(sw0, 1e-5);
+  t.dsw_dz = -2e-4 * sw0 / b.ustar;
+  t.tu = 0.5 * b.height / t.sw / (1.0 + 1.5e-3 * ratio);
+  t.tv = t.tu;
+  t.tw = t.tu;
+  return t;
+}
+MPB_HD PblTurbulence pbl_unstable(const PblState &b, double wstar) {
+  PblTurbulence t;
+  const double zi = b.depth, ol = b.obukhov, zeta = b.rel;
+  double dsw2_dz = 0.0;      // d sigma_w^2 / dz
+  t.su = max_of(b.ustar * pow(max_of(12.0 - 0.5 * zi / ol, 0.0), 1.0 / 3.0), 1e-6);
+  t.sv = t.su;
+  if (zeta < 0.03) {
+    const double arg = max_of(3.0 * zeta - ol / zi, 1e-12);
+    t.sw = 0.96 * wstar * pow(arg, 1.0 / 3.0);
+    dsw2_dz = 1.8432 * (wstar * wstar) / zi * pow(arg, -1.0 / 3.0);
+  } else if (zeta < 0.4) {
+    const double arg = max_of(3.0 * zeta - ol / zi, 1e-12);
+    const double surface_form = 0.96 * pow(arg, 1.0 / 3.0), mixed_form = 0.763 * pow(zeta, 0.175);
+    if (surface_form < mixed_form) {
+      t.sw = wstar * surface_form;
+      dsw2_dz = 1.8432 * (wstar * wstar) / zi * pow(arg, -1.0 / 3.0);
+    } else {
+      t.sw = wstar * mixed_form;
+      dsw2_dz = 0.203759 * (wstar * wstar) / zi * pow(zeta, -0.65);
+    }
+  } else if (zeta < 0.96) {
+    t.sw = 0.722 * wstar * pow(1.0 - zeta, 0.207);
+    dsw2_dz = -0.215812 * (wstar * wstar) / zi * pow(1.0 - zeta, -0.586);
+  } else {
+    t.sw = 0.37 * wstar;
+    dsw2_dz = 0.0;
+  }
+  t.sw = max_of(t.sw, 1e-6);
+  t.dsw_dz = t.sw > 1e-12 ? 0.5 * dsw2_dz / t.sw : 0.0;
+  t.tu = 0.15 * zi / max_of(t.su, 1e-12);
+  t.tv = t.tu;
+  if (b.height < fabs(ol)) {
+    const double denom = 0.55 - 0.38 * fabs(b.height / ol);
+    t.tw = 0.1 * b.height / (t.sw * max_of(denom, 0.05));
+  } else if (zeta < 0.1) {
+    t.tw = 0.59 * b.height / t.sw;
+  } else {
+    t.tw = 0.15 * zi / t.sw * (1.0 - exp(-5.0 * zeta));
+  }
+  return t;
+}
+MPB_HD PblTurbulence pbl_stable(const PblState &b) {
+  PblTurbulence t;
+  const double fade = 1.0 - b.rel;
+  t.su = max_of(2.0 * b.ustar * fade, 1e-6);
+  t.sv = max_of(1.3 * b.ustar * fade, 1e-6);
+  t.sw = max_of(1.3 * b.ustar * fade, 1e-6);
+  t.dsw_dz = -1.3 * b.ustar / b.depth;
+  t.tu = 0.15 * b.depth / t.su * sqrt(b.rel);
+  t.tv = 0.467 * t.tu;
+  t.tw = 0.1 * b.depth / t.sw * pow(b.rel, 0.8);
+  return t;
+}
+
 MPB_HD void diffuse_pbl(const MetView &g, const PblFields &f, uint64_t ctr, double dt, uint64_t ig, Parcel &a,
                         float &up, float &vp, float &wp) {
-  double dsigw_dz = 0.0, sig_u = 0.0, sig_v = 0.0, sig_w = 0.0, tau_u = 0.0, tau_v = 0.0, tau_w = 0.0;
+  // where is the parcel inside the boundary layer?  (4367-4393)
   CellAxes ax;
   axes_reset(ax);
   double ps, pbl;
@@ -1410,13 +1533,15 @@ MPB_HD void diffuse_pbl(const MetView &g, const PblFields &f, uint64_t ctr, doub
   if (a.p < pbl) return;
   if (!(ps > 0.0 && pbl > 0.0 && ps > pbl)) return;
   const double p = a.p < ps ? a.p : ps;
-  const double zs = altitude(ps);
-  const double z_raw = 1e3 * (altitude(p) - zs);
-  const double zi = 1e3 * (altitude(pbl) - zs);
-  if (!(zi > 1.0)) return;
-  const double z = clamp_of(z_raw, 0.0, zi);
-  const double zeta = clamp_of(z / zi, 1e-6, 1.0 - 1e-6);
-  const double z_m = max_of(z, 1.0);
+  const double z_ground = altitude(ps);                              // [km]
+  const double z_raw = 1e3 * (altitude(p) - z_ground);               // [m]
+  PblState b;
+  b.depth = 1e3 * (altitude(pbl) - z_ground);
+  if (!(b.depth > 1.0)) return;
+  const double z = clamp_of(z_raw, 0.0, b.depth);
+  b.rel = clamp_of(z / b.depth, 1e-6, 1.0 - 1e-6);
+  b.height = max_of(z, 1.0);
+  // surface stress, air density and heat flux at the parcel -> friction velocity and Obukhov length (4395-4419)
   Stencil s2;
   stencil_2d(g, a.lon, a.lat, ax, s2);
   const double wt = time_weight(g, a.time);
@@ -1431,94 +1556,48 @@ MPB_HD void diffuse_pbl(const MetView &g, const PblFields &f, uint64_t ctr, doub
   const double tv = t * (1. + (1. - kEps) * hh);                                    // TVIRT
   const double thetav = potential_temperature(p, t) * (1. + (1. - kEps) * max_of(hh, 0.1e-6));   // THETAVIRT :2153
   const double rho = 100. * p / (kRA * tv);                                         // RHO
-  const double tau = sqrt(ess * ess + nss * nss);
+  const double stress = sqrt(ess * ess + nss * nss);
   if (!(rho > 0.0)) return;
-  const double ustar = sqrt(max_of(tau / rho, 0.0));
-  const double ust = max_of(1e-4, ustar);
+  b.ustar = max_of(1e-4, sqrt(max_of(stress / rho, 0.0)));
   const double shf = field2_at(g, f.shf, s2, wt);
-  double ol = 1e12;
-  if (fabs(shf) > 1e-6) ol = thetav * rho * kCpd * (ust * ust) * ust / (0.40 * kG0 * shf);   // KARMAN = 0.40
-  if (zi / fabs(ol) < 1.0) {            // neutral
-    const double corr = z_m / ust;
-    const double sigw0 = 1.3 * ust * exp(-2e-4 * corr);
-    sig_u = max_of(2.0 * ust * exp(-3e-4 * corr), 1e-5);
-    sig_v = max_of(sigw0, 1e-5);
-    sig_w = max_of(sigw0, 1e-5);
-    dsigw_dz = -2e-4 * sigw0 / ust;
-    tau_u = 0.5 * z_m / sig_w / (1.0 + 1.5e-3 * corr);
-    tau_v = tau_u;
-    tau_w = tau_u;
-  } else if (ol < 0.0) {                // unstable
-    const double wstar_arg = -kG0 / thetav * shf / (rho * kCpd) * zi;
-    const double wstar = pow(max_of(wstar_arg, 0.0), 1.0 / 3.0);
-    double dsigw2_dz = 0.0;
-    sig_u = max_of(ust * pow(max_of(12.0 - 0.5 * zi / ol, 0.0), 1.0 / 3.0), 1e-6);
-    sig_v = sig_u;
-    if (zeta < 0.03) {
-      const double arg = max_of(3.0 * zeta - ol / zi, 1e-12);
-      sig_w = 0.96 * wstar * pow(arg, 1.0 / 3.0);
-      dsigw2_dz = 1.8432 * (wstar * wstar) / zi * pow(arg, -1.0 / 3.0);
-    } else if (zeta < 0.4) {
-      const double arg = max_of(3.0 * zeta - ol / zi, 1e-12);
-      const double s1 = 0.96 * pow(arg, 1.0 / 3.0);
-      const double sb = 0.763 * pow(zeta, 0.175);
-      if (s1 < sb) {
-        sig_w = wstar * s1;
-        dsigw2_dz = 1.8432 * (wstar * wstar) / zi * pow(arg, -1.0 / 3.0);
-      } else {
-        sig_w = wstar * sb;
-        dsigw2_dz = 0.203759 * (wstar * wstar) / zi * pow(zeta, -0.65);
-      }
-    } else if (zeta < 0.96) {
-      sig_w = 0.722 * wstar * pow(1.0 - zeta, 0.207);
-      dsigw2_dz = -0.215812 * (wstar * wstar) / zi * pow(1.0 - zeta, -0.586);
-    } else {
-      sig_w = 0.37 * wstar;
-      dsigw2_dz = 0.0;
-    }
-    sig_w = max_of(sig_w, 1e-6);
-    dsigw_dz = sig_w > 1e-12 ? 0.5 * dsigw2_dz / sig_w : 0.0;
-    tau_u = 0.15 * zi / max_of(sig_u, 1e-12);
-    tau_v = tau_u;
-    if (z_m < fabs(ol)) {
-      const double denom = 0.55 - 0.38 * fabs(z_m / ol);
-      tau_w = 0.1 * z_m / (sig_w * max_of(denom, 0.05));
-    } else if (zeta < 0.1)
-      tau_w = 0.59 * z_m / sig_w;
-    else
-      tau_w = 0.15 * zi / sig_w * (1.0 - exp(-5.0 * zeta));
-  } else {                              // stable
-    sig_u = max_of(2.0 * ust * (1.0 - zeta), 1e-6);
-    sig_v = max_of(1.3 * ust * (1.0 - zeta), 1e-6);
-    sig_w = max_of(1.3 * ust * (1.0 - zeta), 1e-6);
-    dsigw_dz = -1.3 * ust / zi;
-    tau_u = 0.15 * zi / sig_u * sqrt(zeta);
-    tau_v = 0.467 * tau_u;
-    tau_w = 0.1 * zi / sig_w * pow(zeta, 0.8);
+  b.obukhov = 1e12;
+  if (fabs(shf) > 1e-6) b.obukhov = thetav * rho * kCpd * (b.ustar * b.ustar) * b.ustar / (0.40 * kG0 * shf);   // KARMAN = 0.40
+  // the closure of the stability regime
+  PblTurbulence k;
+  if (b.depth / fabs(b.obukhov) < 1.0) {
+    k = pbl_neutral(b);
+  } else if (b.obukhov < 0.0) {
+    const double wstar_cubed = -kG0 / thetav * shf / (rho * kCpd) * b.depth;
+    k = pbl_unstable(b, pow(max_of(wstar_cubed, 0.0), 1.0 / 3.0));
+  } else {
+    k = pbl_stable(b);
   }
-  tau_u = max_of(tau_u, 10.0);
-  tau_v = max_of(tau_v, 10.0);
-  tau_w = max_of(tau_w, 30.0);
-  if (!(sig_u > 0.0 && sig_v > 0.0 && sig_w > 0.0 && tau_u > 0.0 && tau_v > 0.0 && tau_w > 0.0)) return;
+  k.tu = max_of(k.tu, 10.0);
+  k.tv = max_of(k.tv, 10.0);
+  k.tw = max_of(k.tw, 30.0);
+  if (!(k.su > 0.0 && k.sv > 0.0 && k.sw > 0.0 && k.tu > 0.0 && k.tv > 0.0 && k.tw > 0.0)) return;
 
+  // Langevin update of the three velocity perturbations with the well-mixed drift term, then the displacement (4545-4583)
   double n0, n1, n2;
   normals3(ctr, ig, n0, n1, n2);
-  const double dt_abs = fabs(dt);
-  const double ru = exp(-dt_abs / tau_u), ru2 = sqrt(max_of(0.0, 1.0 - ru * ru));
-  const double rv = exp(-dt_abs / tau_v), rv2 = sqrt(max_of(0.0, 1.0 - rv * rv));
-  up = (float)(up * ru + sig_u * ru2 * n0);
-  vp = (float)(vp * rv + sig_v * rv2 * n1);
-  const double rw = exp(-dt_abs / tau_w), rw2 = sqrt(max_of(0.0, 1.0 - rw * rw));
-  const double rhoaux = -1.0 / (1e3 * kH0);
-  wp = (float)(wp * rw + sig_w * rw2 * n2 + tau_w * (1.0 - rw) * (2.0 * sig_w * dsigw_dz + rhoaux * (sig_w * sig_w)));
+  const double span = fabs(dt);
+  const double keep_u = exp(-span / k.tu), kick_u = sqrt(max_of(0.0, 1.0 - keep_u * keep_u));
+  const double keep_v = exp(-span / k.tv), kick_v = sqrt(max_of(0.0, 1.0 - keep_v * keep_v));
+  up = (float)(up * keep_u + k.su * kick_u * n0);
+  vp = (float)(vp * keep_v + k.sv * kick_v * n1);
+  const double keep_w = exp(-span / k.tw), kick_w = sqrt(max_of(0.0, 1.0 - keep_w * keep_w));
+  const double dlnrho_dz = -1.0 / (1e3 * kH0);
+  wp = (float)(wp * keep_w + k.sw * kick_w * n2 + k.tw * (1.0 - keep_w) * (2.0 * k.sw * k.dsw_dz + dlnrho_dz * (k.sw * k.sw)));
   a.lon += dx2coord(g.coord_type, up * dt, a.lat);
   a.lat += dy2coord(g.coord_type, vp * dt);
-  double znew = z + wp * dt;
-  while (znew < 0.0 || znew > zi) {
-    if (znew < 0.0) { znew = -znew; wp = -wp; }
-    if (znew > zi) { znew = 2.0 * zi - znew; wp = -wp; }
+  double z_new = z + wp * dt;
+  // reflect at the ground and at the PBL top (the reference's loop has no bound: an infinite displacement would never leave
+  // it; a kernel must return, so the reflections are counted)
+  for (int bounce = 0; bounce < 4096 && (z_new < 0.0 || z_new > b.depth); bounce++) {
+    if (z_new < 0.0) { z_new = -z_new; wp = -wp; }
+    if (z_new > b.depth) { z_new = 2.0 * b.depth - z_new; wp = -wp; }
   }
-  a.p = kP0 * exp(-(zs + znew / 1000.0) / kH0);    // P(z), src/mptrac.h:1784
+  a.p = kP0 * exp(-(z_ground + z_new / 1000.0) / kH0);    // P(z), src/mptrac.h:1784
   a.p = clamp_of(a.p, pbl, ps);
 }
 

@@ -299,7 +299,7 @@ def exchange_area_bytes(ctl: "Ctl", nranks: int, nq: int, grid_boxes: int = 0):
     nmix = sum(1 for i in ctl.mix_qnt if i >= 0)
     total = ctl.mixing_nx * ctl.mixing_ny * ctl.mixing_nz * max(ctl.nens, 1)
     mixing = ctl.mixing_trop >= 0 and ctl.mixing_strat >= 0 and nmix > 0
-    mix = 3 * 8 * (nmix + 1) * (-(-total // nranks)) if mixing else 0
+    mix = 3 * 8 * ((nmix + 2) // 2 * 2) * (-(-total // nranks)) if mixing else 0     # records are padded to 16 bytes
     return mix, grid_boxes * (16 * max(nq, 1) + 4)
 
 
