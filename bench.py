@@ -569,12 +569,24 @@ def run_ours(args):
     # headline on the same ranks (the headline workload itself shards without any exchange)
     if args.workload == "c2" and not args.no_exchange:
         line["exchange"] = {}
+
+        def give_up():
+            # a rank that failed on its own would leave the others waiting in a collective for ever: after the deadline every
+            # rank leaves; rank 0 still prints the headline it has measured
+            if rank == 0:
+                line["exchange"]["error"] = "the exchange workloads did not finish within their deadline"
+                os.write(real_stdout, (json.dumps(line) + "\n").encode())
+            os._exit(0)
+        watchdog = threading.Timer(float(os.environ.get("MPB_BENCH_EXCHANGE_DEADLINE", "240")), give_up)
+        watchdog.daemon = True
+        watchdog.start()
         for name in ("c5", "c4g"):
             _log(f"exchange workload {name}")
             try:
                 line["exchange"][name] = exchange_record(name, rank, world, local)
             except Exception as exc:      # must never take the headline down with it
                 line["exchange"][name] = {"error": repr(exc)[:300]}
+        watchdog.cancel()
     if rank == 0:
         # CPU arm last, in its own process with a hard deadline: it can never take the GPU numbers down with it
         if world == 1 and not args.no_cpu:

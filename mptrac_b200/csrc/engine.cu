@@ -1100,6 +1100,7 @@ struct mpb_ctx {
   bool have_ctl = false;
 
   std::vector<std::pair<step_fn, unsigned>> resident;   // blocks the device holds at once, per step kernel
+  bool q_stale = false;   // mpb_run_timestep_host moved only the quantities the path reads: the device copy of q[] is not current
   bool quad = false, quad_split = false;                // form of the step kernel (MPTRAC_B200_STEP, MPTRAC_B200_QUAD_SPLIT)
   bool tile = false;                                    // MPTRAC_B200_STEP=tile: met window staged in shared memory by TMA
   CUtensorMap tmap;                                     // the node array as a 4-D tensor [nx][ny][nz][8 floats] (tile form)
@@ -1391,6 +1392,7 @@ static void peer_barrier(mpb_ctx *c) {
 // barrier before anybody accumulates (the three record sets were just cleared for a new layout).
 static bool mixing_prepare(mpb_ctx *c, double t) {
   const mpb_ctl_t &k = c->ctl;
+  REQUIRE(!c->q_stale, "mixing: the device copy of the quantities is not current (mpb_run_timestep_host): call mpb_set_atm");
   ensure_boxes(c);
   BoxArgs b;
   b.t0 = t - 0.5 * k.dt_mod; b.t1 = t + 0.5 * k.dt_mod;
@@ -2081,6 +2083,7 @@ int mpb_set_atm(mpb_ctx *c, int64_t np, const double *time, const double *p, con
   REQUIRE(np == 0 || (time && p && lon && lat), "null parcel array");
   REQUIRE(c->nq == 0 || np == 0 || q != nullptr, "null quantity array");
   c->np = np;
+  c->q_stale = false;
   const size_t bytes = sizeof(double) * (size_t)np;
   if (np > 0) {
     CK(cudaMemcpyAsync(c->time(), time, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -2158,9 +2161,12 @@ int mpb_get_atm(mpb_ctx *c, double *time, double *p, double *lon, double *lat, d
     if (p) CK(cudaMemcpyAsync(p, c->p(), bytes, cudaMemcpyDeviceToHost, c->stream));
     if (lon) CK(cudaMemcpyAsync(lon, c->lon(), bytes, cudaMemcpyDeviceToHost, c->stream));
     if (lat) CK(cudaMemcpyAsync(lat, c->lat(), bytes, cudaMemcpyDeviceToHost, c->stream));
-    if (q)
+    if (q && c->nq > 0) {
+      REQUIRE(!c->q_stale, "the device copy of the quantities is not current after mpb_run_timestep_host (it moves only rp / rhop): "
+                           "the caller's arrays hold them; mpb_set_atm makes the device copy current again");
       for (int iq = 0; iq < c->nq; iq++)
         CK(cudaMemcpyAsync(q + (size_t)iq * q_stride, c->q(iq), bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
   }
   CK(cudaStreamSynchronize(c->stream));
   API_END
@@ -2355,6 +2361,7 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
     return 0;
   }
   c->np = np;
+  c->q_stale = c->nq > 0;      // only rp / rhop cross the link below; everything that reads q[] on the device wants mpb_set_atm first
   unsigned phys = 0;
   if (turb_enabled(k)) phys |= PHYS_TURB;
   if (meso_enabled(k)) phys |= PHYS_MESO;
@@ -2538,6 +2545,7 @@ int mpb_module_sedi(mpb_ctx *c) {
 int mpb_module_meteo(mpb_ctx *c) {
   API_BEGIN
   use(c);
+  REQUIRE(c->have_ctl && meteo_wanted(c->ctl), "module_meteo: the control structure names no quantity the device computes (qnt_meteo)");
   launch_meteo(c);
   API_END
 }
@@ -2601,6 +2609,7 @@ int mpb_grid_accumulate(mpb_ctx *c, const mpb_grid_t *g) {
   API_BEGIN
   use(c);
   REQUIRE(g && g->nx > 0 && g->ny > 0 && g->nz > 0, "bad grid");
+  REQUIRE(!c->q_stale, "gridded output: the device copy of the quantities is not current (mpb_run_timestep_host): call mpb_set_atm");
   const long long nbox = (long long)g->nx * g->ny * g->nz;
   REQUIRE(nbox < (1ll << 31), "grid too large");
   ensure_boxes(c);

@@ -199,6 +199,18 @@ MPB_HD double fdiv(double a, double b) {
 #endif
 }
 
+// The quotient for an INDEX (a cell of a regular axis, the truncated quotient of FMOD).  div_by yields the correctly rounded
+// quotient for all but rare operand pairs (division by a constant through its rounded reciprocal: Markstein's condition);
+// a last-bit error only matters when the quotient sits within a few ulps of an integer, where it could move a parcel into the
+// neighbouring cell.  There -- and only there -- a true division decides, so the index is the reference's for every input.
+static MPB_COLD double div_true(double x, double d) { return x / d; }
+MPB_HD double div_for_index(double x, double d, double rd) {
+  const double q = div_by(x, d, rd);
+  const double r = rint(q);
+  if (fabs(q - r) <= 1e-15 * fabs(r)) return div_true(x, d);
+  return q;
+}
+
 constexpr double kR360 = 1.0 / 360.0;
 constexpr double kR1000 = 1.0 / 1000.0;
 constexpr double kRH0 = 1.0 / kH0;
@@ -206,7 +218,7 @@ constexpr double kPiRE = kPi * kRE;
 constexpr double kRPiRE = 1.0 / (kPi * kRE);
 
 // x - trunc(x / 360) * 360 with the quotient truncated through int (FMOD, src/mptrac.h:1121-1122)
-MPB_HD double mod360(double x) { return x - (int)div_by(x, 360., kR360) * 360.; }
+MPB_HD double mod360(double x) { return x - (int)div_for_index(x, 360., kR360) * 360.; }
 // general form (cold paths)
 MPB_HD double mod_trunc(double x, double y) { return x - (int)(x / y) * y; }
 
@@ -340,7 +352,7 @@ MPB_HD unsigned hi_word(double x) {
 
 // Regular-axis index by division, clamped to [0, n-2] (3559-3574)
 MPB_HD int find_regular(double x0, double dx, double rdx, int n, double x) {
-  const int i = (int)div_by(x - x0, dx, rdx);
+  const int i = (int)div_for_index(x - x0, dx, rdx);
   return i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
 }
 // the same with a true division (cold paths: climatology axis)

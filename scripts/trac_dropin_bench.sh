@@ -35,18 +35,27 @@ done
 $R/atm_init $W/data/trac.ctl $W/data/atm_init.tab INIT_T0 0 INIT_T1 0 INIT_LON0 -180 INIT_LON1 179 INIT_DLON 1 \
    INIT_LAT0 -89.5 INIT_LAT1 89.5 INIT_DLAT 1 INIT_Z0 2 INIT_Z1 30 INIT_DZ 2 > $W/init.log 2>&1
 grep -i "number of\|np =" $W/init.log | tail -2 || true
-run() {  # name, binary, preload
-  mkdir -p $W/$1; cp $W/data/trac.ctl $W/data/atm_init.tab $W/$1/; ln -sf $W/data/wind_*.nc $W/$1/ 2>/dev/null || true
-  sed -i "s|METBASE = .*|METBASE = $W/data/wind|" $W/$1/trac.ctl
-  echo $W/$1 > $W/dirlist_$1
+run() {  # name, binary, preload, [VAR=value ...]
+  local name=$1 bin=$2 pre=$3; shift 3
+  mkdir -p $W/$name; cp $W/data/trac.ctl $W/data/atm_init.tab $W/$name/; ln -sf $W/data/wind_*.nc $W/$name/ 2>/dev/null || true
+  sed -i "s|METBASE = .*|METBASE = $W/data/wind|" $W/$name/trac.ctl
+  echo $W/$name > $W/dirlist_$name
   local t0=$(date +%s.%N)
-  ( if [ -n "$3" ]; then export LD_PRELOAD=$3 MPTRAC_B200_VERBOSE=1; fi; $2 $W/dirlist_$1 trac.ctl atm_init.tab ATM_BASENAME atm > $W/$1.log 2>&1 ) || { echo "$1 FAILED"; tail -5 $W/$1.log; }
+  ( for kv in "$@"; do export "$kv"; done; if [ -n "$pre" ]; then export LD_PRELOAD=$pre MPTRAC_B200_VERBOSE=1; fi
+    $bin $W/dirlist_$name trac.ctl atm_init.tab ATM_BASENAME atm > $W/$name.log 2>&1 ) || { echo "$name FAILED"; tail -5 $W/$name.log; }
+  set -- $name
   local t1=$(date +%s.%N)
   echo "== $1: wall $(python -c "print(f'{$t1 - $t0:.2f}')") s"
   grep -E "SIZE_NP|TIMER_GROUP_PHYSICS|TIMER_GROUP_INPUT|TIMER_GROUP_MEMORY|TIMER_MODULE_ADVECT|TIMER_MODULE_B200_STEP|TIMER_MODULE_METEO|TIMER_MODULE_SORT|TIMER_TOTAL|kernel launches" $W/$1.log || tail -5 $W/$1.log
 }
 run cpu $R/trac ""
+run gpu_cold $R/trac_shared $SHIM          # first CUDA process on a fresh box: the driver itself is still being paged in
 run gpu $R/trac_shared $SHIM
+run gpu_no_warmup $R/trac_shared $SHIM MPTRAC_B200_NO_WARMUP=1   # context created when the parcels arrive, not while trac reads
+# the strict arithmetic flavour (-fmad=false, correctly rounded quotients) behind the same shim
+mkdir -p $W/strictlib; cp $SHIM $W/strictlib/; cp $PWD/mptrac_b200/_lib/libmptrac_b200_strict.so $W/strictlib/libmptrac_b200.so
+run gpu_strict $R/trac_shared $W/strictlib/libmptrac_b200_shim.so
+compare() {
 python - <<PY
 import numpy as np, glob
 def rd(f):
@@ -55,7 +64,8 @@ def rd(f):
     hdr = np.frombuffer(a[:8].tobytes(), dtype=np.int32); n = int(hdr[1])
     d = np.frombuffer(a[8:8 + 8 * (4 + $NQ) * n].tobytes(), dtype=np.float64).reshape(4 + $NQ, n)
     return n, d[:, np.argsort(d[4])]          # ordered by parcel index
-fc = sorted(glob.glob("$W/cpu/atm_2*.bin"))[-1]; fg = sorted(glob.glob("$W/gpu/atm_2*.bin"))[-1]
+fc = sorted(glob.glob("$W/cpu/atm_2*.bin"))[-1]; fg = sorted(glob.glob("$W/$1/atm_2*.bin"))[-1]
+print("-- $1 against the reference's CPU run")
 n, c = rd(fc); m, g = rd(fg)
 assert n == m and np.array_equal(c[4], g[4])
 dlon = ((c[2] - g[2] + 180.0) % 360.0 - 180.0) * np.cos(np.deg2rad(c[3]))
@@ -70,5 +80,13 @@ if $NQ > 1:
     ok = ~bad
     print(f"  quantities (parcels that agree in position): max rel-to-scale {np.max(np.abs(c[5:, ok]-g[5:, ok]) / np.max(np.abs(c[5:]), axis=1, keepdims=True)):.2e}")
 PY
-cp $W/cpu.log gpurun_out/trac_dropin_cpu.log; cp $W/gpu.log gpurun_out/trac_dropin_gpu.log
+}
+compare gpu
+compare gpu_strict
+NG=$(nvidia-smi -L 2>/dev/null | wc -l)
+if [ "$NG" -gt 1 ]; then    # the same simulation cut over all GPUs of the box behind trac's one host thread
+  run gpu_team$NG $R/trac_shared $SHIM MPTRAC_B200_DEVICES=0-$((NG-1))
+  compare gpu_team$NG
+fi
+cp $W/cpu.log gpurun_out/trac_dropin_cpu.log; cp $W/gpu.log gpurun_out/trac_dropin_gpu.log; cp $W/gpu_strict.log gpurun_out/trac_dropin_gpu_strict.log
 rm -rf $W
