@@ -314,7 +314,8 @@ def exchange_record(name, rank, world, local, K=12, W=3):
             "exchange_share": (ms_full - ms_plain) / ms_full if ms_full > 0 else None,
             "value": float(n) * world / (ms_full * 1e-3), "unit": "particle-steps/s",
             "transport": ("none (one rank)" if world == 1 else
-                          "peer memory: NVLink atomics into the owner's slice of the box records + flag barriers (own kernels)" if attached
+                          "peer memory: contributions routed to the owner of each box and answers routed back as coalesced stores over NVLink, "
+                          "local atomics, flag barriers (own kernels)" if attached
                           else "NCCL: one all-reduce of the dense box records" if wl.get("mixing") else "NCCL reduce of the output boxes"),
             "exchanged_bytes_per_rank_per_step": int(per_rank)}
 
@@ -390,7 +391,7 @@ def run_ours(args):
     model = Model()
 
     # one model step.  Workloads with an exchange: by default the ranks are attached through peer memory and
-    # the engine does the exchange itself (NVLink atomics into the owner's slice of the box records + flag barriers);
+    # the engine does the exchange itself (contributions routed to the owner of each box over NVLink + flag barriers);
     # MPB_BENCH_EXCHANGE=nccl sums the dense box records with ONE all-reduce on the stream the engine launches on
     dev = torch.device("cuda", local)
     step, _, attached = make_steps(eng, wl, ctl, dev, world)
@@ -526,11 +527,12 @@ def run_ours(args):
     kern_ms = total_ms / K
     peak, peak_src = peaks()
     achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_src = None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get(args.workload)
+            tj = json.loads(tf.read_text())
+            traffic, traffic_src = tj.get(args.workload), tj.get("_source_" + args.workload)
         except Exception:
             traffic = None
 
@@ -553,12 +555,15 @@ def run_ours(args):
                 "host_checksum": checksum, "host_link": pc},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": (f"from the ncu capture {traffic_src} (not re-measured in this run)" if traffic_src else None),
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel": wl.get("kernel", "step_kernel"), "peak_source": peak_src,
                      "note": wl.get("roofline_note") or (
                          "not HBM-bound: DRAM traffic is below the algorithmic bytes; the kernel is limited by latency at 16 "
                          "resident warps/SM (about 100 live fp64 registers per parcel) and by the 192 f32->f64 conversions per "
                          "RK4 step the reference's arithmetic needs (XU pipe 45 % busy: floor 47 us per 1M parcels, i.e. frac "
-                         "0.51 at best); ncu evidence under profiles/, analysis in DESIGN.md 3.1")},
+                         "0.51 at best); two re-designs were built and measured in round 2 -- one lane per coordinate (196 us) "
+                         "and a TMA-staged met window (148 us) against 110-114 us of this kernel; ncu evidence under "
+                         "profiles/, analysis in DESIGN.md 3.1 and 3.3")},
         "clocks": clk.summary(),
     }
     if world > 1:

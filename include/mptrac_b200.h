@@ -246,8 +246,10 @@ int mpb_module_rng(mpb_ctx *ctx, double *rs_host, int64_t n, int method); /* src
  * The box records of module_mixing -- per box {count, sum of every mixed quantity}, doubles -- are accumulated for ALL mixed
  * quantities in one pass.  Three ways to run the exchange step:
  *  (1) ranks attached through peer memory (mpb_peer_init + mpb_peer_attach, one process per GPU): mpb_run_timestep /
- *      mpb_module_mixing do everything -- each rank adds its parcels' contributions into the slice of the box space its OWNER
- *      holds (NVLink atomics), one barrier in stream order, each rank reads its parcels' records back;
+ *      mpb_module_mixing do everything -- the box space is cut into one slice per rank; every parcel's contribution is
+ *      routed into the inbox of its box's OWNER (coalesced stores over NVLink), the owner folds its inboxes into its
+ *      records (local atomics) and routes the finished record back to each contribution's sender; two barriers in stream
+ *      order; 8 x (quantities + 1) bytes per parcel and direction cross the link;
  *  (2) a team (mpb_team_*, several devices behind one host thread): the same through mpb_team_run_timestep;
  *  (3) any other transport: mpb_mixing_accumulate_all, sum mpb_device_ptr("mix_rec") [mpb_mixing_rec_len() doubles] over the
  *      ranks (one all-reduce), mpb_mixing_apply_all.
@@ -261,9 +263,10 @@ int mpb_grid_accumulate(mpb_ctx *ctx, const mpb_grid_t *grid);      /* -> count[
 int mpb_grid_reduce(mpb_ctx *ctx);                                  /* attached ranks: sum over ranks onto rank 0 */
 int mpb_grid_fetch(mpb_ctx *ctx, int *count, double *sum, double *sumsq);   /* copy them to the host (any may be NULL) */
 
-/* Ranks that exchange through peer memory.  mpb_peer_init allocates this rank's exchange area -- barrier flags, its slice of
- * the box records (mix_bytes >= 3 x 8 x R x ceil(boxes / nranks), R = mixed quantities + 1 rounded up to even), its partial output arrays (grid_bytes
- * >= boxes x (16 x nq + 4)) -- and exports a handle (MPB_IPC_HANDLE_BYTES) other processes open with mpb_peer_attach (handles
+/* Ranks that exchange through peer memory.  mpb_peer_init allocates this rank's exchange area -- barrier flags, the inboxes and
+ * outboxes of the mixing exchange (mix_bytes >= 256 + 16 x nranks x P x (mixed quantities + 1), P = the largest number of
+ * parcels any rank holds; the SAME value on every rank), its partial output arrays (grid_bytes >= boxes x (16 x nq + 4)) --
+ * and exports a handle (MPB_IPC_HANDLE_BYTES) other processes open with mpb_peer_attach (handles
  * of all ranks, rank order; the caller gathers them, e.g. with its MPI / torch.distributed, and synchronises the ranks once
  * after attaching).  Contexts of one process attach each other's mpb_peer_area directly.  All ranks must then issue the same
  * sequence of exchange steps.  A barrier that waits ~5 s for a missing rank gives up; mpb_sync reports it. */

@@ -905,6 +905,118 @@ __global__ void mix_apply_kernel(const __grid_constant__ MixArgs A, ClimView cli
   }
 }
 
+// ---- several ranks: the routed exchange ----
+// Remote atomics (one NVLink transaction per contribution) measured no better than NCCL's dense all-reduce (8 GPUs: 0.39 ms
+// against 0.42 ms per step for configs[4]).  Instead every contribution travels ONCE as part of a coalesced store stream:
+//   route   each parcel's {box, q_0 ..} goes into the inbox its box's OWNER keeps for this sender (peer memory), at a slot the
+//           sender allocates with one warp-aggregated atomic per (warp, owner); the parcel remembers (owner, slot);
+//   -- barrier --
+//   serve   the owner folds all its inboxes into its slice of the box records (LOCAL atomics), then answers every entry with
+//           the finished record {count, sum_0 ..} into the sender's outbox, same slot (coalesced stores to peer memory);
+//   -- barrier --
+//   apply   every parcel reads its answer from its own outbox (local memory) and relaxes.
+// Per parcel 8 (1 + quantities) bytes cross NVLink in each direction, all of it as streaming stores.
+struct RouteArgs {
+  double *inbox[kMaxRanks];            // rank r's inbox region for THIS sender: [cap][E]
+  unsigned long long *counts_at[kMaxRanks];   // rank r's table of entry counts, this sender's cell
+  unsigned int *alloc;                 // [nranks] slots handed out so far (local)
+  int2 *route;                         // [np] (owner, slot) per parcel (local)
+  long long slice, np, q_stride;
+  int nmix, ngrid, nranks, E;
+  const int *box;
+  const double *ens;
+  const double *q0;
+  int iq[MPB_MIX_MAXQ];
+};
+
+__global__ void mix_route_kernel(const __grid_constant__ RouteArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (the grid covers whole warps)
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int owner = -1;
+  long long local = 0;
+  if (ip < A.np) {
+    const int b = A.box[ip];
+    if (b >= 0) {
+      const long long idx = (long long)(A.ens ? (int)A.ens[ip] : 0) * A.ngrid + b;
+      owner = (int)(idx / A.slice);
+      local = idx - (long long)owner * A.slice;
+    }
+  }
+  // one slot allocation per (warp, owner): the lanes that share an owner take consecutive slots
+  const unsigned peers = __match_any_sync(full, owner);
+  int slot = -1;
+  if (owner >= 0) {
+    const int leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(A.alloc + owner, (unsigned)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    slot = (int)(base + (unsigned)__popc(peers & ((1u << lane) - 1u)));
+    double *e = A.inbox[owner] + (size_t)slot * A.E;
+    e[0] = (double)local;
+    for (int k = 0; k < A.nmix; k++) e[1 + k] = A.q0[(long long)A.iq[k] * A.q_stride + ip];
+  }
+  if (ip < A.np) A.route[ip] = make_int2(owner, slot);
+}
+
+// tell every owner how many entries this sender left in its inbox
+__global__ void mix_publish_kernel(const __grid_constant__ RouteArgs A) {
+  const int r = threadIdx.x;
+  if (r < A.nranks) *A.counts_at[r] = (unsigned long long)A.alloc[r];
+}
+
+struct ServeArgs {
+  const double *inbox;                 // this rank's inboxes [nranks][cap][E]
+  const unsigned long long *counts;    // [nranks] entries per sender
+  double *outbox_at[kMaxRanks];        // sender s's outbox region for THIS owner: [cap][E]
+  double *rec;                         // this rank's slice of the box records [slice][E] (local)
+  long long cap;
+  int E;
+};
+__global__ void mix_fold_kernel(const __grid_constant__ ServeArgs A) {     // src/mptrac.c:5287-5303 for the boxes this rank owns
+  const int s = blockIdx.y;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)A.counts[s]) return;
+  const double *in = A.inbox + ((size_t)s * A.cap + (size_t)e) * A.E;
+  double *rec = A.rec + (size_t)in[0] * A.E;
+  atomicAdd(rec, 1.0);
+  for (int k = 1; k < A.E; k++) atomicAdd(rec + k, in[k]);
+}
+__global__ void mix_answer_kernel(const __grid_constant__ ServeArgs A) {
+  const int s = blockIdx.y;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)A.counts[s]) return;
+  const double *in = A.inbox + ((size_t)s * A.cap + (size_t)e) * A.E;
+  const double *rec = A.rec + (size_t)in[0] * A.E;
+  double *out = A.outbox_at[s] + (size_t)e * A.E;
+  for (int k = 0; k < A.E; k++) out[k] = rec[k];
+}
+
+// src/mptrac.c:5307-5335 with the box record taken from this rank's outbox
+__global__ void mix_apply_routed_kernel(const double *outbox, long long cap, int E, const int2 *route, int nmix, MixArgs A, ClimView clim,
+                                        const double *time, const double *lat, const double *p, double mix_trop, double mix_strat,
+                                        int latlon, double utm_ref_lat) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np) return;
+  const int2 r = route[ip];
+  if (r.x < 0) return;
+  const double *rec = outbox + ((size_t)r.x * cap + (size_t)r.y) * E;
+  double mixparam = 1.0;
+  if (mix_trop < 1 || mix_strat < 1) {
+    const double pt = tropopause_pressure(clim, time[ip], latlon ? lat[ip] : utm_ref_lat);
+    const double w = weight_tropo(pt, p[ip]);
+    mixparam = w * mix_trop + (1.0 - w) * mix_strat;
+  }
+  const int n = (int)rec[0];
+  for (int k = 0; k < nmix; k++) {
+    double mean = rec[1 + k];
+    if (n > 0) mean /= n;
+    double *q = A.q0 + (long long)A.iq[k] * A.q_stride + ip;
+    const double qq = *q;
+    *q = qq + (mean - qq) * mixparam;
+  }
+}
+
 // Barrier over the ranks of a multi-process run, in stream order: every rank writes the barrier's number into its slot
 // of every peer's flag array (peer memory) and waits until all peers' numbers have arrived in its own.  The wait is
 // bounded (~5 s): a missing peer raises *err instead of hanging the device.
@@ -1083,15 +1195,16 @@ struct mpb_ctx {
   long long grid_cap = 0, grid_nbox = 0;
   bool grid_in_area = false;
 
-  // ranks that exchange box records through peer memory (mpb_peer_*): this rank's exchange area holds the barrier flags,
-  // three sets of its slice of the box records (one per step in rotation, so that ONE barrier per step orders everything)
-  // and its partial arrays of the gridded output; area[r] is rank r's area as mapped into this process
+  // ranks that exchange box records through peer memory (mpb_peer_*): this rank's exchange area holds the barrier flags, the
+  // inboxes (contributions of every rank to the boxes this rank owns) and outboxes (the owners' answers to this rank's
+  // parcels) of the routed mixing exchange, and its partial arrays of the gridded output; area[r] is rank r's area as
+  // mapped into this process
   int rank = 0, nranks = 1;
   char *area[kMaxRanks] = {};
   bool area_ipc[kMaxRanks] = {};
   size_t area_bytes = 0, area_mix_bytes = 0, area_grid_bytes = 0;
-  int mix_set = 0;
-  long long mix_layout = -1;            // (nmix + 1) * slice the three sets are currently zeroed for
+  unsigned int *mix_alloc = nullptr;    // routed exchange: slots handed out per owner this step [kMaxRanks]
+  int2 *mix_route = nullptr;            // ... (owner, slot) of every parcel [np_max]
   unsigned long long epoch = 0;
   int *peer_err = nullptr;              // device flag raised by a barrier that timed out
   struct mpb_team *team = nullptr;      // set when a team drives this context (barriers are then stream events)
@@ -1370,8 +1483,19 @@ static long long mixing_total(const mpb_ctx *c) {
 // ---- exchange area of a rank (mpb_peer_init): [flags + error word | three sets of its slice of the box records | its partial
 // arrays of the gridded output] ----
 constexpr size_t kAreaHeader = 4096, kAreaErrOffset = 2048;
-static double *mix_set_ptr(const mpb_ctx *c, int r, int set) {
-  return (double *)(c->area[r] + kAreaHeader + (size_t)set * (c->area_mix_bytes / 3));
+// mixing region of an area: [entry counts per sender, 256 B | inboxes [nranks][cap][E] | outboxes [nranks][cap][E]], E = mixed
+// quantities + 1 doubles per entry, cap = parcels one rank may send (the same on every rank: equal area sizes)
+constexpr size_t kRouteHeader = 256;
+static long long route_cap(const mpb_ctx *c) {
+  if (c->area_mix_bytes <= kRouteHeader) return 0;
+  return (long long)((c->area_mix_bytes - kRouteHeader) / (2 * (size_t)c->nranks * (size_t)(c->nmix + 1) * sizeof(double)));
+}
+static unsigned long long *route_counts(const mpb_ctx *c, int owner) { return (unsigned long long *)(c->area[owner] + kAreaHeader); }
+static double *route_inbox(const mpb_ctx *c, int owner, int sender) {
+  return (double *)(c->area[owner] + kAreaHeader + kRouteHeader) + (size_t)sender * (size_t)route_cap(c) * (size_t)(c->nmix + 1);
+}
+static double *route_outbox(const mpb_ctx *c, int holder, int owner) {
+  return (double *)(c->area[holder] + kAreaHeader + kRouteHeader) + ((size_t)c->nranks + (size_t)owner) * (size_t)route_cap(c) * (size_t)(c->nmix + 1);
 }
 static char *grid_region(const mpb_ctx *c, int r) { return c->area[r] + kAreaHeader + c->area_mix_bytes; }
 
@@ -1388,9 +1512,8 @@ static void peer_barrier(mpb_ctx *c) {
   c->launches++;
 }
 
-// Box index of every parcel, the list of mixed quantities, the box records.  Returns true when the ranks must pass a
-// barrier before anybody accumulates (the three record sets were just cleared for a new layout).
-static bool mixing_prepare(mpb_ctx *c, double t) {
+// Box index of every parcel, the list of mixed quantities, the (zeroed) box records this rank keeps.
+static void mixing_prepare(mpb_ctx *c, double t) {
   const mpb_ctl_t &k = c->ctl;
   REQUIRE(!c->q_stale, "mixing: the device copy of the quantities is not current (mpb_run_timestep_host): call mpb_set_atm");
   ensure_boxes(c);
@@ -1410,7 +1533,6 @@ static bool mixing_prepare(mpb_ctx *c, double t) {
     }
   c->mix_total = total;
   const long long stride = (c->nmix + 2) / 2 * 2;      // {count, sums} padded to 16-byte records
-  bool barrier = false;
   if (c->nranks == 1) {
     c->mix_slice = total;
     const long long need = stride * total;
@@ -1421,33 +1543,36 @@ static bool mixing_prepare(mpb_ctx *c, double t) {
     }
     CK(cudaMemsetAsync(c->mix_rec, 0, sizeof(double) * (size_t)need, c->stream));
   } else {
+    // routed exchange: this rank keeps the records of its slice of the box space locally and zeroes them every step
     c->mix_slice = (total + c->nranks - 1) / c->nranks;
-    const long long need = stride * c->mix_slice;
-    REQUIRE(c->area[c->rank] != nullptr && sizeof(double) * (size_t)need <= c->area_mix_bytes / 3,
-            "the exchange area is too small for this mixing grid (mpb_peer_init: 3 x (quantities + 1) x boxes per rank doubles)");
-    if (c->mix_layout != need) {
-      CK(cudaMemsetAsync(c->area[c->rank] + kAreaHeader, 0, c->area_mix_bytes, c->stream));
-      c->mix_layout = need; c->mix_set = 0;
-      barrier = true;
+    const long long E = c->nmix + 1, need = E * c->mix_slice;
+    for (int r = 0; r < c->nranks; r++) REQUIRE(c->area[r] != nullptr, "mpb_peer_attach has not been called");
+    REQUIRE(c->np <= route_cap(c), "the exchange area is too small for this rank's parcels (mpb_peer_init: mix_bytes >= 256 + 16 x nranks x "
+                                   "parcels per rank x (mixed quantities + 1))");
+    if (need > c->mix_cap) {
+      if (c->mix_rec) CK(cudaFree(c->mix_rec));
+      CK(cudaMalloc(&c->mix_rec, sizeof(double) * (size_t)need));
+      c->mix_cap = need;
     }
+    if (!c->mix_alloc) {
+      CK(cudaMalloc(&c->mix_alloc, sizeof(unsigned int) * kMaxRanks));
+      CK(cudaMalloc(&c->mix_route, sizeof(int2) * (size_t)c->np_max));
+    }
+    CK(cudaMemsetAsync(c->mix_rec, 0, sizeof(double) * (size_t)need, c->stream));
+    CK(cudaMemsetAsync(c->mix_alloc, 0, sizeof(unsigned int) * kMaxRanks, c->stream));
   }
   if (c->np > 0) {
     box_index_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(b, c->time(), c->lon(), c->lat(), c->p(), c->box, c->np);
     CK(cudaGetLastError());
     c->launches++;
   }
-  return barrier;
 }
 
 static MixArgs mix_args(mpb_ctx *c) {
   const mpb_ctl_t &k = c->ctl;
   MixArgs A;
   for (int r = 0; r < kMaxRanks; r++) A.rec[r] = nullptr;
-  if (c->nranks == 1) A.rec[0] = c->mix_rec;
-  else for (int r = 0; r < c->nranks; r++) {
-    REQUIRE(c->area[r] != nullptr, "mpb_peer_attach has not been called");
-    A.rec[r] = mix_set_ptr(c, r, c->mix_set);
-  }
+  A.rec[0] = c->mix_rec;      // (single rank: the dense records; several ranks use the routed exchange below)
   A.slice = c->mix_slice; A.nmix = c->nmix; A.ngrid = k.mixing_nx * k.mixing_ny * k.mixing_nz;
   A.stride = (c->nmix + 2) / 2 * 2;
   A.box = c->box;
@@ -1459,6 +1584,7 @@ static MixArgs mix_args(mpb_ctx *c) {
 
 static void mixing_accumulate_all(mpb_ctx *c) {
   REQUIRE(c->mix_total > 0, "mixing: the box records have not been prepared");
+  REQUIRE(c->nranks == 1, "internal: attached ranks use the routed exchange");
   if (c->np == 0 || c->nmix == 0) return;
   mix_accumulate_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(mix_args(c));
   CK(cudaGetLastError());
@@ -1473,21 +1599,69 @@ static void mixing_apply_all(mpb_ctx *c) {
     CK(cudaGetLastError());
     c->launches++;
   }
-  if (c->nranks > 1) {
-    // after this step's barrier every rank has finished reading the set of the step before: clear this rank's slice of it
-    // for the step after the next, and move on (the set of the next step was cleared one step ago)
-    const int stale = (c->mix_set + 2) % 3;
-    CK(cudaMemsetAsync(mix_set_ptr(c, c->rank, stale), 0, sizeof(double) * (size_t)c->mix_layout, c->stream));
-    c->mix_set = (c->mix_set + 1) % 3;
-  }
 }
 
-// module_mixing on one context: alone, or as one rank of a multi-process run (barrier in stream order between the phases)
+// the three phases of the routed exchange (several ranks); a barrier over the ranks separates them
+static void mixing_route(mpb_ctx *c) {
+  const mpb_ctl_t &k = c->ctl;
+  RouteArgs A;
+  for (int r = 0; r < kMaxRanks; r++) {
+    A.inbox[r] = r < c->nranks ? route_inbox(c, r, c->rank) : nullptr;
+    A.counts_at[r] = r < c->nranks ? route_counts(c, r) + c->rank : nullptr;
+  }
+  A.alloc = c->mix_alloc; A.route = c->mix_route;
+  A.slice = c->mix_slice; A.np = c->np; A.q_stride = c->np_max;
+  A.nmix = c->nmix; A.ngrid = k.mixing_nx * k.mixing_ny * k.mixing_nz; A.nranks = c->nranks; A.E = c->nmix + 1;
+  A.box = c->box;
+  A.ens = (k.nens > 0 && k.qnt_ens >= 0) ? c->q(k.qnt_ens) : nullptr;
+  A.q0 = c->nq ? c->q(0) : nullptr;
+  for (int i = 0; i < MPB_MIX_MAXQ; i++) A.iq[i] = i < c->nmix ? c->mix_iq[i] : 0;
+  if (c->np > 0 && c->nmix > 0) {
+    mix_route_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(A);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  mix_publish_kernel<<<1, 32, 0, c->stream>>>(A);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+static void mixing_serve(mpb_ctx *c) {
+  ServeArgs A;
+  A.inbox = route_inbox(c, c->rank, 0);
+  A.counts = route_counts(c, c->rank);
+  for (int r = 0; r < kMaxRanks; r++) A.outbox_at[r] = r < c->nranks ? route_outbox(c, r, c->rank) : nullptr;
+  A.rec = c->mix_rec; A.cap = route_cap(c); A.E = c->nmix + 1;
+  if (A.cap <= 0 || c->nmix == 0) return;
+  const dim3 grid(nblocks(A.cap, 256), (unsigned)c->nranks);
+  mix_fold_kernel<<<grid, 256, 0, c->stream>>>(A);
+  mix_answer_kernel<<<grid, 256, 0, c->stream>>>(A);
+  CK(cudaGetLastError());
+  c->launches += 2;
+}
+static void mixing_apply_routed(mpb_ctx *c) {
+  const mpb_ctl_t &k = c->ctl;
+  if (c->np == 0 || c->nmix == 0) return;
+  MixArgs A = mix_args(c);
+  mix_apply_routed_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(
+      route_outbox(c, c->rank, 0), route_cap(c), c->nmix + 1, c->mix_route, c->nmix, A, clim_view(c), c->time(), c->lat(), c->p(),
+      k.mixing_trop, k.mixing_strat, k.met_coord_type == 0, k.met_utm_ref_lat);
+  CK(cudaGetLastError());
+  c->launches++;
+}
+
+// module_mixing on one context: alone, or as one rank of a multi-process run (barriers in stream order between the phases)
 static void mixing_inline(mpb_ctx *c, double t) {
-  if (mixing_prepare(c, t)) peer_barrier(c);
-  mixing_accumulate_all(c);
-  peer_barrier(c);
-  mixing_apply_all(c);
+  mixing_prepare(c, t);
+  if (c->nranks == 1) {
+    mixing_accumulate_all(c);
+    mixing_apply_all(c);
+  } else {
+    mixing_route(c);
+    peer_barrier(c);
+    mixing_serve(c);
+    peer_barrier(c);
+    mixing_apply_routed(c);
+  }
 }
 
 static bool hits(double t, double every) { return std::fmod(t, every) == 0; }
@@ -1849,7 +2023,7 @@ int mpb_destroy(mpb_ctx *c) {
   CK(cudaStreamSynchronize(c->stream));
   void *ptrs[] = {c->soa[0], c->soa[1], c->dt, c->uvwp, c->keys[0], c->keys[1], c->perm[0], c->perm[1],
                   c->cub_tmp, c->nodes, c->surf, c->ax_lon, c->ax_lat, c->ax_p, c->ax_lonc, c->ax_latc, c->ax_pc,
-                  c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_rec,
+                  c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_rec, c->mix_alloc, c->mix_route,
                   c->grid_in_area ? nullptr : c->grid_sum, c->grid_in_area ? nullptr : c->grid_sq, c->grid_in_area ? nullptr : c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz, c->lev_hint, c->iso_var, c->iso_ts, c->iso_ps, c->chem_mass};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int r = 0; r < kMaxRanks; r++)
@@ -2728,11 +2902,10 @@ int mpb_peer_init(mpb_ctx *c, int rank, int nranks, int64_t mix_bytes, int64_t g
   }
   if (c->grid_in_area) { c->grid_sum = c->grid_sq = nullptr; c->grid_cnt = nullptr; c->grid_in_area = false; c->grid_cap = 0; c->grid_nbox = 0; }
   c->rank = rank; c->nranks = nranks;
-  c->mix_layout = -1; c->mix_set = 0; c->epoch = 0; c->peer_err = nullptr;
+  c->epoch = 0; c->peer_err = nullptr;
   c->area_bytes = c->area_mix_bytes = c->area_grid_bytes = 0;
   if (nranks == 1) return 0;
-  const size_t unit = 3 * 256;
-  c->area_mix_bytes = ((size_t)mix_bytes + unit - 1) / unit * unit;
+  c->area_mix_bytes = ((size_t)mix_bytes + 255) / 256 * 256;
   c->area_grid_bytes = ((size_t)grid_bytes + 255) / 256 * 256;
   c->area_bytes = kAreaHeader + c->area_mix_bytes + c->area_grid_bytes;
   CK(cudaMalloc(&c->area[rank], c->area_bytes));
@@ -2930,7 +3103,8 @@ int mpb_team_set_ctl(mpb_team *T, const mpb_ctl_t *ctl) {
     int nmix = 0;
     for (int i = 0; i < ctl->n_mix_qnt; i++) nmix += ctl->mix_qnt[i] >= 0;
     const long long total = mixing_total(T->ctx[0]), n = (long long)T->ctx.size();
-    if (nmix > 0 && total > 0) team_ensure_area(T, 3 * sizeof(double) * (size_t)((nmix + 2) / 2 * 2) * (size_t)((total + n - 1) / n), T->grid_bytes);
+    if (nmix > 0 && total > 0)
+      team_ensure_area(T, kRouteHeader + 2 * sizeof(double) * (size_t)n * (size_t)T->ctx[0]->np_max * (size_t)(nmix + 1), T->grid_bytes);
   }
   API_END
 }
@@ -3045,12 +3219,11 @@ int mpb_team_run_modules(mpb_team *T, double t, unsigned mask) {
   const bool many = T->ctx.size() > 1;
   for (const Op &o : plan_modules(T->ctx[0]->ctl, t, mask)) {
     if (o.kind == Op::MIXING && many) {
-      bool bar = false;
-      for (mpb_ctx *c : T->ctx) { use(c); bar = mixing_prepare(c, t) || bar; }
-      if (bar) team_barrier(T);
-      for (mpb_ctx *c : T->ctx) { use(c); mixing_accumulate_all(c); }
+      for (mpb_ctx *c : T->ctx) { use(c); mixing_prepare(c, t); mixing_route(c); }
       team_barrier(T);
-      for (mpb_ctx *c : T->ctx) { use(c); mixing_apply_all(c); }
+      for (mpb_ctx *c : T->ctx) { use(c); mixing_serve(c); }
+      team_barrier(T);
+      for (mpb_ctx *c : T->ctx) { use(c); mixing_apply_routed(c); }
     } else {
       for (mpb_ctx *c : T->ctx) { use(c); run_op(c, t, o); }
     }

@@ -44,15 +44,19 @@ def device_tensor(ptr: int, n: int, dtype: str, device):
 def attach_peers(engine, ctl, grid_boxes: int = 0, group=None) -> bool:
     """Connect the ranks' engines through peer memory (one process per GPU on one node): every rank allocates its exchange
     area, the CUDA IPC handles travel over ``torch.distributed``, every rank opens the others'.  Afterwards
-    ``engine.run_timestep`` / ``module_mixing`` / ``grid_reduce`` do their exchange steps themselves (NVLink loads, stores
-    and atomics + flag barriers in stream order; no collective library on the data path).  Returns False (and leaves the
+    ``engine.run_timestep`` / ``module_mixing`` / ``grid_reduce`` do their exchange steps themselves (contributions routed to
+    the owner of each box as coalesced stores over NVLink, answers routed back, flag barriers in stream order; no collective
+    library on the data path).  Returns False (and leaves the
     engine alone) when there is only one rank."""
     import torch.distributed as dist
     from .host import exchange_area_bytes
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return False
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    mix_bytes, grid_bytes = exchange_area_bytes(ctl, world, engine.nq, grid_boxes)
+    # (every rank must size its area for the LARGEST shard: the capacity of an inbox is derived from the area size)
+    sizes = [None] * world
+    dist.all_gather_object(sizes, int(engine.np_max), group=group)
+    mix_bytes, grid_bytes = exchange_area_bytes(ctl, world, engine.nq, max(sizes), grid_boxes)
     err = None
     try:
         handle = engine.peer_init(rank, world, mix_bytes, grid_bytes)

@@ -293,13 +293,13 @@ IPC_HANDLE_BYTES = 64      # MPB_IPC_HANDLE_BYTES
 MAX_RANKS = 16             # MPB_MAX_RANKS
 
 
-def exchange_area_bytes(ctl: "Ctl", nranks: int, nq: int, grid_boxes: int = 0):
-    """(mix_bytes, grid_bytes) of mpb_peer_init for a control structure: three sets of (mixed quantities + 1) doubles per box
-    of this rank's slice of the mixing grid; count + sum + sum of squares per box of the gridded output"""
+def exchange_area_bytes(ctl: "Ctl", nranks: int, nq: int, np_max: int, grid_boxes: int = 0):
+    """(mix_bytes, grid_bytes) of mpb_peer_init for a control structure and ``np_max`` parcels per rank (the same value on every
+    rank): inboxes + outboxes of the routed mixing exchange -- one entry of (mixed quantities + 1) doubles per parcel and
+    peer --; count + sum + sum of squares per box of the gridded output"""
     nmix = sum(1 for i in ctl.mix_qnt if i >= 0)
-    total = ctl.mixing_nx * ctl.mixing_ny * ctl.mixing_nz * max(ctl.nens, 1)
     mixing = ctl.mixing_trop >= 0 and ctl.mixing_strat >= 0 and nmix > 0
-    mix = 3 * 8 * ((nmix + 2) // 2 * 2) * (-(-total // nranks)) if mixing else 0     # records are padded to 16 bytes
+    mix = 256 + 2 * 8 * nranks * int(np_max) * (nmix + 1) if mixing else 0
     return mix, grid_boxes * (16 * max(nq, 1) + 4)
 
 
