@@ -500,8 +500,9 @@ def run_ours(args):
         del hb, hb2, db, db2
     except Exception as exc:   # context only
         pc = {"error": repr(exc)}
-    h2d_bytes = 32 * n + (16 * n if ctl.nq else 0)     # time, p, lon, lat (+ rp, rhop when sedimentation is on)
-    d2h_bytes = 32 * n
+    # what the last host-resident step moved across the link, as counted by the engine: p, lon, lat both ways (+ rp, rhop in when
+    # sedimentation is on); time[] only when the parcels do not all carry the same time (mpb_host_step_bytes)
+    h2d_bytes, d2h_bytes = (32 * n, 32 * n) if exchange else eng.host_step_bytes
     if exchange:                                       # set_atm / get_atm move every quantity both ways
         h2d_bytes = d2h_bytes = (32 + 8 * ctl.nq) * n
         if wl.get("out_grid") and rank == 0:
@@ -551,7 +552,8 @@ def run_ours(args):
                          "note": "no L2 flush, one event bracket around K steps"},
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / K, "api": ("mpb_set_atm + step with its exchange + mpb_get_atm (pinned host arrays, every step)" if exchange else
-                        "mpb_run_timestep_host (pinned host arrays in, same arrays out, every step)"),
+                        "mpb_run_timestep_host (pinned host arrays in, same arrays out, every step; all parcels carry one time, so "
+                        "time[] is filled on the host instead of crossing the link)"),
                 "host_checksum": checksum, "host_link": pc},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -200,6 +200,10 @@ int mpb_run_timestep(mpb_ctx *ctx, double t);
  * Only the quantities the path reads (rp, rhop) are transferred; none is written back (the path modifies none). */
 int mpb_run_timestep_host(mpb_ctx *ctx, double t, int64_t np, double *time, double *p, double *lon, double *lat,
                           double *q, int64_t q_stride);
+/* bytes the last mpb_run_timestep_host call moved across the host link in each direction (when all parcels carry the same
+ * time -- the usual case -- time[] does not travel: every parcel takes the same time step, the host array is filled with the
+ * common result by the host itself; 24 instead of 32 bytes per parcel and direction) */
+int mpb_host_step_bytes(mpb_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
 
 /* A sub-sequence of the step, for callers that interleave modules of their own (the shim does this for
  * reference modules that are not on the device path).  `mask` selects modules, which still run in the

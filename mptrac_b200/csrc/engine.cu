@@ -76,6 +76,10 @@ struct StepArgs {
   // by the kernel itself; the device arrays above still receive the result.  Null = parcels live on the device.
   const double *in_time, *in_lon, *in_lat, *in_p;
   double *host_time, *host_lon, *host_lat, *host_p;
+  // host-resident parcels that all carry the SAME time (the common case): the time array does not cross the link at all --
+  // every parcel starts at time_in, and the host fills its own array with the common result (mpb_run_timestep_host)
+  double time_in;
+  int uniform_time;
   long long np;
   long long ig0;  // global index of local parcel 0
   unsigned modules;
@@ -160,8 +164,8 @@ __device__ __forceinline__ void parcel_finish(const StepArgs &A, long long ip, P
   A.lon[ip] = a.lon;
   A.lat[ip] = a.lat;
   A.p[ip] = a.p;
-  if (A.host_time) {
-    if (ADVECT > 0) A.host_time[ip] = a.time;
+  if (A.host_lon) {
+    if (ADVECT > 0 && A.host_time) A.host_time[ip] = a.time;
     A.host_lon[ip] = a.lon;
     A.host_lat[ip] = a.lat;
     A.host_p[ip] = a.p;
@@ -244,7 +248,8 @@ __global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
         const unsigned dst = smem_u32(&stage[b][0][threadIdx.x]);
         const long long i = first + lane;
         const bool host = A.in_time != nullptr;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"((host ? A.in_time : A.time) + i) : "memory");
+        if (!A.uniform_time)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"((host ? A.in_time : A.time) + i) : "memory");
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + kBlock * 8), "l"((host ? A.in_lon : A.lon) + i) : "memory");
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 2 * kBlock * 8), "l"((host ? A.in_lat : A.lat) + i) : "memory");
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 3 * kBlock * 8), "l"((host ? A.in_p : A.p) + i) : "memory");
@@ -269,7 +274,7 @@ __global__ void MPB_BOUNDS step_kernel(const __grid_constant__ StepArgs A) {
     else asm volatile("cp.async.wait_group 0;" ::: "memory");   // a lane only reads the slots it filled itself
     const long long ip = w0 + lane;
     Parcel a;
-    a.time = stage[buf][0][threadIdx.x]; a.lon = stage[buf][1][threadIdx.x];
+    a.time = A.uniform_time ? A.time_in : stage[buf][0][threadIdx.x]; a.lon = stage[buf][1][threadIdx.x];
     a.lat = stage[buf][2][threadIdx.x]; a.p = stage[buf][3][threadIdx.x];
     w0 += stride;
     const bool more = w0 < A.np;          // (warp-uniform)
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(128, MPB_QUAD_MINBLOCKS) quad_step_kernel(cons
     const bool valid = owner && ip < A.np;
     const double x_in = valid ? src[ip] : (q.j == 2 ? 500.0 : 0.0);
     double x = x_in;
-    double time = (ip < A.np) ? tsrc[ip] : 0.0;
+    double time = A.uniform_time ? A.time_in : ((ip < A.np) ? tsrc[ip] : 0.0);
     double dt;
     if (A.modules & MOD_TIMESTEPS) {
       Parcel a;
@@ -1062,36 +1067,66 @@ __global__ void grid_pull_kernel(const __grid_constant__ GridPeers G, int nranks
 // src/mptrac.c:13862-13872 with kernel weight 1 (no GRID_KERNEL file)
 // Gridded output: count, sum and sum of squares per box (src/mptrac.c:13840-13872).  Parcels arrive cell-sorted, so the
 // lanes of a warp mostly fall into one or two boxes: each run of equal box indices is summed inside the warp (segmented
-// scan over shuffles) and only the last lane of a run touches memory -- ~200 parcels per box would otherwise serialise
-// on the same three addresses in L2.  Runs need not be maximal (an unsorted stream just issues more atomics).
-__global__ void grid_accumulate_kernel(const int *box, const double *q, long long q_stride, int nq,
-                                       long long nbox, int *cnt, double *sum, double *sq, long long np) {
-  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (the grid covers whole warps: no early return)
+// scan over shuffles) and only the last lane of a run touches memory.  Runs need not be maximal (an unsorted stream just
+// issues more atomics).
+// ONE pass over the parcels (no box array in memory) and few atomics: a warp owns 8 x 32
+// consecutive parcels, computes their boxes once, and carries the run that is still open at the end of a round of 32 into
+// the next round, so a run of ~200 parcels of one output box (parcels arrive cell-sorted; the reference's default output
+// grid has ONE level) costs one atomic per array instead of one per warp.  Measured on the configs[3] share (12.5 M
+// parcels, 360x180x1 boxes): box_index_kernel 126 us + grid_accumulate_kernel 286 us before.
+constexpr int kBinRounds = 8;
+__global__ void __launch_bounds__(256) grid_bin_kernel(BoxArgs g, const double *time, const double *lon, const double *lat, const double *p,
+                                                       const double *q, long long q_stride, int nq, long long nbox, int *cnt, double *sum,
+                                                       double *sq, long long np) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int b = ip < np ? box[ip] : -1;
-  const int prev = __shfl_up_sync(full, b, 1);
-  const unsigned heads = __ballot_sync(full, lane == 0 || prev != b);
-  const int start = 31 - __clz(heads & (full >> (31 - lane)));             // first lane of this lane's run
-  const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-  int n = 1;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long first = warp * 32 * kBinRounds;
+  if (first >= np) return;                                  // (warp-uniform)
+  int bx[kBinRounds];
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int tn = __shfl_up_sync(full, n, d);
-    if (lane - d >= start) n += tn;
+  for (int r = 0; r < kBinRounds; r++) {
+    const long long ip = first + r * 32 + lane;
+    bx[r] = ip < np ? box_index(time[ip], lon[ip], lat[ip], p[ip], g.t0, g.t1, g.lon0, g.lon1, g.lat0, g.lat1, g.z0, g.z1, g.nx, g.ny, g.nz) : -1;
   }
-  if (tail && b >= 0) atomicAdd(cnt + b, n);
-  for (int iq = 0; iq < nq; iq++) {
-    const double x = b >= 0 ? q[iq * q_stride + ip] : 0.0;
-    double s1 = x, s2 = x * x;
+  // pass -1: counts; pass iq >= 0: sum and sum of squares of quantity iq
+  for (int iq = -1; iq < nq; iq++) {
+    int carry_box = -1;
+    double carry_a = 0, carry_b = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const double t1 = __shfl_up_sync(full, s1, d), t2 = __shfl_up_sync(full, s2, d);
-      if (lane - d >= start) { s1 += t1; s2 += t2; }
+    for (int r = 0; r < kBinRounds; r++) {
+      const int b = bx[r];
+      const long long ip = first + r * 32 + lane;
+      const double x = iq < 0 ? 1.0 : (b >= 0 ? q[(long long)iq * q_stride + ip] : 0.0);
+      double a = x, bb = x * x;
+      const int prev = __shfl_up_sync(full, b, 1);
+      const unsigned heads = __ballot_sync(full, lane == 0 || prev != b);
+      const int start = 31 - __clz(heads & (full >> (31 - lane)));
+      const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double ta = __shfl_up_sync(full, a, d), tb = __shfl_up_sync(full, bb, d);
+        if (lane - d >= start) { a += ta; bb += tb; }
+      }
+      const int head_box = __shfl_sync(full, b, 0);
+      if (carry_box >= 0) {
+        if (carry_box == head_box) { if (start == 0) { a += carry_a; bb += carry_b; } }      // the open run continues
+        else if (lane == 0) {                                                                  // it ended with the last round
+          if (iq < 0) atomicAdd(cnt + carry_box, (int)carry_a);
+          else { atomicAdd(sum + iq * nbox + carry_box, carry_a); atomicAdd(sq + iq * nbox + carry_box, carry_b); }
+        }
+      }
+      if (tail && lane != 31 && b >= 0) {
+        if (iq < 0) atomicAdd(cnt + b, (int)a);
+        else { atomicAdd(sum + iq * nbox + b, a); atomicAdd(sq + iq * nbox + b, bb); }
+      }
+      carry_box = __shfl_sync(full, b, 31);
+      carry_a = __shfl_sync(full, a, 31);
+      carry_b = __shfl_sync(full, bb, 31);
     }
-    if (tail && b >= 0) {
-      atomicAdd(sum + iq * nbox + b, s1);
-      atomicAdd(sq + iq * nbox + b, s2);
+    if (carry_box >= 0 && lane == 0) {
+      if (iq < 0) atomicAdd(cnt + carry_box, (int)carry_a);
+      else { atomicAdd(sum + iq * nbox + carry_box, carry_a); atomicAdd(sq + iq * nbox + carry_box, carry_b); }
     }
   }
 }
@@ -1213,6 +1248,7 @@ struct mpb_ctx {
   bool have_ctl = false;
 
   std::vector<std::pair<step_fn, unsigned>> resident;   // blocks the device holds at once, per step kernel
+  long long host_h2d = 0, host_d2h = 0;   // bytes the last mpb_run_timestep_host moved across the host link
   bool q_stale = false;   // mpb_run_timestep_host moved only the quantities the path reads: the device copy of q[] is not current
   bool quad = false, quad_split = false;                // form of the step kernel (MPTRAC_B200_STEP, MPTRAC_B200_QUAD_SPLIT)
   bool tile = false;                                    // MPTRAC_B200_STEP=tile: met window staged in shared memory by TMA
@@ -1309,6 +1345,7 @@ static StepArgs step_args(mpb_ctx *c, double t, int advect, unsigned phys, unsig
   A.rp = A.rhop = nullptr;
   A.in_time = A.in_lon = A.in_lat = A.in_p = nullptr;
   A.host_time = A.host_lon = A.host_lat = A.host_p = nullptr;
+  A.time_in = 0; A.uniform_time = 0;
   if (phys & PHYS_SEDI) {
     REQUIRE(c->ctl.qnt_rp >= 0 && c->ctl.qnt_rp < c->nq && c->ctl.qnt_rhop >= 0 && c->ctl.qnt_rhop < c->nq,
             "sedimentation needs quantities rp and rhop");
@@ -1320,10 +1357,18 @@ static StepArgs step_args(mpb_ctx *c, double t, int advect, unsigned phys, unsig
 }
 
 // blocks of `fn` the device holds at once (cached per kernel instantiation)
+// (measurement aid: MPTRAC_B200_PAD_SMEM=<bytes> of unused dynamic shared memory per block lowers the number of resident
+// blocks of the step kernel -- how sensitive is it to occupancy? -- DESIGN.md 3.1)
+static size_t pad_smem() {
+  static long long v = -1;
+  if (v < 0) { const char *e = std::getenv("MPTRAC_B200_PAD_SMEM"); v = e ? std::atoll(e) : 0; }
+  return (size_t)v;
+}
 static unsigned resident_blocks(mpb_ctx *c, step_fn fn) {
   for (auto &e : c->resident) if (e.first == fn) return e.second;
   int per_sm = 0, sms = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0));
+  if (pad_smem() > 40 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad_smem()));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, pad_smem()));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
   const unsigned n = (unsigned)std::max(1, per_sm * sms);
   c->resident.emplace_back(fn, n);
@@ -1355,10 +1400,10 @@ static void launch_range(mpb_ctx *c, StepArgs A, int advect, unsigned phys, long
   if (cnt <= 0) return;
   A.time += off; A.lon += off; A.lat += off; A.p += off; A.dt += off; A.uvwp += 3 * off;
   if (A.in_time) { A.in_time += off; A.in_lon += off; A.in_lat += off; A.in_p += off; }
-  if (A.host_time) { A.host_time += off; A.host_lon += off; A.host_lat += off; A.host_p += off; }
+  if (A.host_lon) { if (A.host_time) A.host_time += off; A.host_lon += off; A.host_lat += off; A.host_p += off; }
   if (A.rp) { A.rp += off; A.rhop += off; }
   A.np = cnt; A.ig0 += off;
-  if (c->tile && c->tmap_ok && advect > 0 && !A.in_time && !A.host_time) {
+  if (c->tile && c->tmap_ok && advect > 0 && !A.in_time && !A.host_lon) {
     tile_fn tf = pick_tile(advect, phys);
     const size_t bytes = (size_t)c->tshape.nx * c->tshape.ny * c->tshape.nz * sizeof(Node);
     if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -1386,7 +1431,7 @@ static void launch_range(mpb_ctx *c, StepArgs A, int advect, unsigned phys, long
 #if MPB_PERSIST
   grid = std::min(grid, resident_blocks(c, fn));
 #endif
-  fn<<<grid, kBlock, 0, stream>>>(A);
+  fn<<<grid, kBlock, pad_smem(), stream>>>(A);
   CK(cudaGetLastError());
   c->launches++;
 }
@@ -2532,6 +2577,7 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
     REQUIRE(mpb_set_atm(c, np, time, p, lon, lat, q, q_stride) == 0, g_err);
     run_modules(c, t, MPB_MOD_ALL);
     REQUIRE(mpb_get_atm(c, time, p, lon, lat, q, q_stride) == 0, g_err);
+    c->host_h2d = c->host_d2h = (32 + 8 * (long long)c->nq) * np;
     return 0;
   }
   c->np = np;
@@ -2579,10 +2625,43 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
     A.in_time = (const double *)d[0]; A.in_p = (const double *)d[1]; A.in_lon = (const double *)d[2]; A.in_lat = (const double *)d[3];
     A.host_time = (double *)d[0]; A.host_p = (double *)d[1]; A.host_lon = (double *)d[2]; A.host_lat = (double *)d[3];
     if (phys & PHYS_SEDI) { A.rp = (const double *)d[4]; A.rhop = (const double *)d[5]; }
+    // Do all parcels carry the same time (they do unless they were released at different times)?  Then module_timesteps
+    // takes the same decision for every parcel of a global met domain (src/mptrac.c:6019-6024 depends on the time only) and
+    // all of them end at the same time: neither direction of time[] needs the link -- the kernel starts every parcel at
+    // that value and the host writes the common result into its own array while the kernel runs.  A quarter of the traffic.
+    // (MPTRAC_B200_HOST_TIME=explicit always moves the array.)
+    bool uniform = np > 0 && !A.met.local && !(std::getenv("MPTRAC_B200_HOST_TIME") && !std::strcmp(std::getenv("MPTRAC_B200_HOST_TIME"), "explicit"));
+    if (uniform) {
+      long long differ = 0;
+      unsigned long long first_bits;
+      std::memcpy(&first_bits, time, sizeof(first_bits));
+      const unsigned long long *bits = reinterpret_cast<const unsigned long long *>(time);
+#pragma omp parallel for reduction(+ : differ) schedule(static)
+      for (long long i = 0; i < np; i++) differ += bits[i] != first_bits;
+      uniform = differ == 0;
+    }
+    double t_out = 0;
+    bool moves = false;
+    if (uniform) {
+      A.uniform_time = 1; A.time_in = time[0]; A.host_time = nullptr;
+      Parcel a0;
+      a0.time = time[0]; a0.lon = a0.lat = a0.p = 0;
+      const double dt0 = parcel_dt(A.met, A.ctl, a0);
+      moves = dt0 != 0 && k.advect > 0;          // (module_advect is what advances a parcel's time, src/mptrac.c:3671)
+      t_out = a0.time + dt0;
+    }
+    c->host_h2d = (uniform ? 24 : 32) * np + ((phys & PHYS_SEDI) ? 16 * np : 0);
+    c->host_d2h = ((uniform || k.advect == 0) ? 24 : 32) * np;
     launch_range(c, A, k.advect, phys, 0, np, c->stream);
+    if (moves) {
+#pragma omp parallel for schedule(static)
+      for (long long i = 0; i < np; i++) time[i] = t_out;
+    }
     CK(cudaStreamSynchronize(c->stream));   // the host arrays are valid on return
     return 0;
   }
+  c->host_h2d = 32 * np + ((phys & PHYS_SEDI) ? 16 * np : 0);
+  c->host_d2h = 32 * np;
   const bool dma_in = mode != HM_DMA_OUT, dma_out = mode != HM_DMA_IN;
   if (!dma_in) {
     A.in_time = (const double *)d[0]; A.in_p = (const double *)d[1]; A.in_lon = (const double *)d[2]; A.in_lat = (const double *)d[3];
@@ -2668,6 +2747,13 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
     std::fprintf(stderr, "  (us since call: after H2D, after kernel, after D2H per chunk)\n");
     for (cudaEvent_t e : tev) cudaEventDestroy(e);
   }
+  API_END
+}
+
+int mpb_host_step_bytes(mpb_ctx *c, int64_t *h2d, int64_t *d2h) {
+  API_BEGIN
+  REQUIRE(c && h2d && d2h, "null argument");
+  *h2d = c->host_h2d; *d2h = c->host_d2h;
   API_END
 }
 
@@ -2811,12 +2897,10 @@ int mpb_grid_accumulate(mpb_ctx *c, const mpb_grid_t *g) {
   BoxArgs b;
   b.t0 = g->t0; b.t1 = g->t1; b.lon0 = g->lon0; b.lon1 = g->lon1; b.lat0 = g->lat0; b.lat1 = g->lat1;
   b.z0 = g->z0; b.z1 = g->z1; b.nx = g->nx; b.ny = g->ny; b.nz = g->nz;
-  box_index_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(b, c->time(), c->lon(), c->lat(), c->p(), c->box, c->np);
+  grid_bin_kernel<<<nblocks(c->np, 256 * kBinRounds), 256, 0, c->stream>>>(
+      b, c->time(), c->lon(), c->lat(), c->p(), c->nq ? c->q(0) : nullptr, c->np_max, c->nq, nbox, c->grid_cnt, c->grid_sum, c->grid_sq, c->np);
   CK(cudaGetLastError());
-  grid_accumulate_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(
-      c->box, c->nq ? c->q(0) : nullptr, c->np_max, c->nq, nbox, c->grid_cnt, c->grid_sum, c->grid_sq, c->np);
-  CK(cudaGetLastError());
-  c->launches += 2;
+  c->launches++;
   API_END
 }
 

@@ -344,6 +344,7 @@ def load_library(strict: bool = False) -> C.CDLL:
         "mpb_get_rng_ctr": (u64, [vp]),
         "mpb_run_timestep": (i32, [vp, dbl]),
         "mpb_run_timestep_host": (i32, [vp, dbl, i64, vp, vp, vp, vp, vp, i64]),
+        "mpb_host_step_bytes": (i32, [vp, P(i64), P(i64)]),
         "mpb_run_modules": (i32, [vp, dbl, C.c_uint]),
         "mpb_module_timesteps": (i32, [vp, dbl]),
         "mpb_module_position": (i32, [vp]),
@@ -583,6 +584,13 @@ class Engine:
             stride = q.strides[0] // 8
         self._ck(self._lib.mpb_run_timestep_host(self._h, float(t), n, *[_ptr(a) for a in arrs],
                                                  _ptr(q) if self.nq else None, stride))
+
+    @property
+    def host_step_bytes(self):
+        """(host -> device, device -> host) bytes of the last run_timestep_host call"""
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self._lib.mpb_host_step_bytes(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def module_meteo(self):
         self._ck(self._lib.mpb_module_meteo(self._h))

@@ -491,17 +491,26 @@ def test_tma_staging_strict_library(oracle):
     assert abserr(outs[0]["lat"], lat) > 1e-3
 
 
-@pytest.mark.parametrize("layout", ["separate_arrays", "atm_t_layout", "pinned", "pinned:dma_in", "pinned:dma_out", "pinned:copy"])
+@pytest.mark.parametrize("layout", ["separate_arrays", "atm_t_layout", "pinned", "pinned:staggered", "pinned:explicit_time", "pinned:dma_in",
+                                    "pinned:dma_out", "pinned:copy"])
 def test_host_resident_step_equals_three_calls(layout, monkeypatch):
     """mpb_run_timestep_host (chunked upload / step / download pipeline) == set_atm + run_timestep + get_atm, bit for bit,
     including steps that fall back because a cell sort is due, with diffusion (random numbers addressed per chunk) and
     sedimentation (rp / rhop uploaded per chunk)."""
     from mptrac_b200 import Ctl
+    staggered = False
     if ":" in layout:   # how pinned arrays cross the host link (MPTRAC_B200_HOST_MODE); the default is zerocopy
         layout, mode = layout.split(":")
-        monkeypatch.setenv("MPTRAC_B200_HOST_MODE", mode)
+        if mode == "staggered":            # parcels released at different times: time[] has to travel (default zero-copy path)
+            staggered = True
+        elif mode == "explicit_time":      # one common time, but the array is moved anyway
+            monkeypatch.setenv("MPTRAC_B200_HOST_TIME", "explicit")
+        else:
+            monkeypatch.setenv("MPTRAC_B200_HOST_MODE", mode)
     m0, m1, tm, p, lon, lat, clim = _case(n=300_000, grid=(72, 37, 30))
     n = tm.size
+    if staggered:
+        tm = np.where(np.arange(n) % 5 == 0, 6000.0, 0.0)    # (still waiting at the last step: the times never become one)
     q = np.stack([np.full(n, 2.0), np.full(n, 1500.0)])
     ctl = Ctl(nq=2, qnt_rp=0, qnt_rhop=1, advect=4, diffusion=1, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0,
               turb_dz_trop=0.5, turb_dx_strat=20.0, sort_dt=900.0)
@@ -525,6 +534,11 @@ def test_host_resident_step_equals_three_calls(layout, monkeypatch):
         ref = a.get_atm()
         assert a.rng_ctr == b.rng_ctr
         uva, uvb = a.get_uvwp(), b.get_uvwp()
+        if layout == "pinned" and "MPTRAC_B200_HOST_MODE" not in os.environ:
+            # the last step was a plain zero-copy step: time[] stays at home when (and only when) all parcels share one time
+            moved = b.host_step_bytes
+            uniform = not staggered and "MPTRAC_B200_HOST_TIME" not in os.environ
+            assert moved == ((24 + 16) * n, 24 * n) if uniform else moved == ((32 + 16) * n, 32 * n), moved
     for k in ("time", "p", "lon", "lat"):
         assert np.array_equal(ref[k], h[k]), k
     assert np.array_equal(uva, uvb)
