@@ -922,13 +922,14 @@ __global__ void mix_apply_kernel(const __grid_constant__ MixArgs A, ClimView cli
 //   apply   every parcel reads its answer from its own outbox (local memory) and relaxes.
 // Per parcel 8 (1 + quantities) bytes cross NVLink in each direction, all of it as streaming stores.
 struct RouteArgs {
+  BoxArgs grid;                        // the mixing grid (the box of a parcel is computed here: no box array in memory)
+  const double *time, *lon, *lat, *p;
   double *inbox[kMaxRanks];            // rank r's inbox region for THIS sender: [cap][E]
   unsigned long long *counts_at[kMaxRanks];   // rank r's table of entry counts, this sender's cell
   unsigned int *alloc;                 // [nranks] slots handed out so far (local)
   int2 *route;                         // [np] (owner, slot) per parcel (local)
   long long slice, np, q_stride;
   int nmix, ngrid, nranks, E;
-  const int *box;
   const double *ens;
   const double *q0;
   int iq[MPB_MIX_MAXQ];
@@ -941,7 +942,8 @@ __global__ void mix_route_kernel(const __grid_constant__ RouteArgs A) {
   int owner = -1;
   long long local = 0;
   if (ip < A.np) {
-    const int b = A.box[ip];
+    const BoxArgs &g = A.grid;
+    const int b = box_index(A.time[ip], A.lon[ip], A.lat[ip], A.p[ip], g.t0, g.t1, g.lon0, g.lon1, g.lat0, g.lat1, g.z0, g.z1, g.nx, g.ny, g.nz);
     if (b >= 0) {
       const long long idx = (long long)(A.ens ? (int)A.ens[ip] : 0) * A.ngrid + b;
       owner = (int)(idx / A.slice);
@@ -978,23 +980,26 @@ struct ServeArgs {
   long long cap;
   int E;
 };
+// (the number of entries a sender left is only known on the device: a fixed grid strides over them)
 __global__ void mix_fold_kernel(const __grid_constant__ ServeArgs A) {     // src/mptrac.c:5287-5303 for the boxes this rank owns
   const int s = blockIdx.y;
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)A.counts[s]) return;
-  const double *in = A.inbox + ((size_t)s * A.cap + (size_t)e) * A.E;
-  double *rec = A.rec + (size_t)in[0] * A.E;
-  atomicAdd(rec, 1.0);
-  for (int k = 1; k < A.E; k++) atomicAdd(rec + k, in[k]);
+  const long long n = (long long)A.counts[s], stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    const double *in = A.inbox + ((size_t)s * A.cap + (size_t)e) * A.E;
+    double *rec = A.rec + (size_t)in[0] * A.E;
+    atomicAdd(rec, 1.0);
+    for (int k = 1; k < A.E; k++) atomicAdd(rec + k, in[k]);
+  }
 }
 __global__ void mix_answer_kernel(const __grid_constant__ ServeArgs A) {
   const int s = blockIdx.y;
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)A.counts[s]) return;
-  const double *in = A.inbox + ((size_t)s * A.cap + (size_t)e) * A.E;
-  const double *rec = A.rec + (size_t)in[0] * A.E;
-  double *out = A.outbox_at[s] + (size_t)e * A.E;
-  for (int k = 0; k < A.E; k++) out[k] = rec[k];
+  const long long n = (long long)A.counts[s], stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    const double *in = A.inbox + ((size_t)s * A.cap + (size_t)e) * A.E;
+    const double *rec = A.rec + (size_t)in[0] * A.E;
+    double *out = A.outbox_at[s] + (size_t)e * A.E;
+    for (int k = 0; k < A.E; k++) out[k] = rec[k];
+  }
 }
 
 // src/mptrac.c:5307-5335 with the box record taken from this rank's outbox
@@ -1238,6 +1243,7 @@ struct mpb_ctx {
   char *area[kMaxRanks] = {};
   bool area_ipc[kMaxRanks] = {};
   size_t area_bytes = 0, area_mix_bytes = 0, area_grid_bytes = 0;
+  BoxArgs mix_grid;                     // the mixing grid of the current step
   unsigned int *mix_alloc = nullptr;    // routed exchange: slots handed out per owner this step [kMaxRanks]
   int2 *mix_route = nullptr;            // ... (owner, slot) of every parcel [np_max]
   unsigned long long epoch = 0;
@@ -1606,7 +1612,8 @@ static void mixing_prepare(mpb_ctx *c, double t) {
     CK(cudaMemsetAsync(c->mix_rec, 0, sizeof(double) * (size_t)need, c->stream));
     CK(cudaMemsetAsync(c->mix_alloc, 0, sizeof(unsigned int) * kMaxRanks, c->stream));
   }
-  if (c->np > 0) {
+  c->mix_grid = b;
+  if (c->np > 0 && c->nranks == 1) {      // (the routed exchange computes the box while it routes)
     box_index_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(b, c->time(), c->lon(), c->lat(), c->p(), c->box, c->np);
     CK(cudaGetLastError());
     c->launches++;
@@ -1654,10 +1661,11 @@ static void mixing_route(mpb_ctx *c) {
     A.inbox[r] = r < c->nranks ? route_inbox(c, r, c->rank) : nullptr;
     A.counts_at[r] = r < c->nranks ? route_counts(c, r) + c->rank : nullptr;
   }
+  A.grid = c->mix_grid;
+  A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p();
   A.alloc = c->mix_alloc; A.route = c->mix_route;
   A.slice = c->mix_slice; A.np = c->np; A.q_stride = c->np_max;
   A.nmix = c->nmix; A.ngrid = k.mixing_nx * k.mixing_ny * k.mixing_nz; A.nranks = c->nranks; A.E = c->nmix + 1;
-  A.box = c->box;
   A.ens = (k.nens > 0 && k.qnt_ens >= 0) ? c->q(k.qnt_ens) : nullptr;
   A.q0 = c->nq ? c->q(0) : nullptr;
   for (int i = 0; i < MPB_MIX_MAXQ; i++) A.iq[i] = i < c->nmix ? c->mix_iq[i] : 0;
@@ -1677,7 +1685,8 @@ static void mixing_serve(mpb_ctx *c) {
   for (int r = 0; r < kMaxRanks; r++) A.outbox_at[r] = r < c->nranks ? route_outbox(c, r, c->rank) : nullptr;
   A.rec = c->mix_rec; A.cap = route_cap(c); A.E = c->nmix + 1;
   if (A.cap <= 0 || c->nmix == 0) return;
-  const dim3 grid(nblocks(A.cap, 256), (unsigned)c->nranks);
+  // every sender holds about 1 / nranks of its parcels' boxes in this rank's slice: size the grid for twice that share
+  const dim3 grid(std::max(1u, std::min(nblocks(A.cap, 256), nblocks(2 * A.cap / c->nranks + 1, 256))), (unsigned)c->nranks);
   mix_fold_kernel<<<grid, 256, 0, c->stream>>>(A);
   mix_answer_kernel<<<grid, 256, 0, c->stream>>>(A);
   CK(cudaGetLastError());

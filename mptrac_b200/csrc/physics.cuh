@@ -894,6 +894,26 @@ struct LevelStencil {
   double wx, wy, wz, wt;         // weights of the upper-index node / of time level 1
 };
 
+// The four weights of the model-level lookup (2857-2861, 2940): quotients by grid constants and by the level spacing.  The
+// production device build multiplies by the reciprocal (interval records, rcp + Newton), like the pressure-level path: a
+// last-ulp difference in a weight enters the position continuously; the host and the strict build divide.
+MPB_HD double level_weight(double num, double den, double rden) {
+#if MPB_FAST_QUOT
+  (void)den;
+  return num * rden;
+#else
+  (void)rden;
+  return num / den;
+#endif
+}
+MPB_HD double level_ratio(double num, double den) {
+#if MPB_FAST_QUOT
+  return fdiv(num, den);
+#else
+  return num / den;
+#endif
+}
+
 // t * (v1 - v0) + v0 with the difference taken in fp32 (2870-2873)
 MPB_HD double time_lerp_f32(double wt, float v0, float v1) { return wt * (double)f_sub(v1, v0) + (double)v0; }
 MPB_HD double up_lerp(double w, double lo, double hi) { return w * (hi - lo) + lo; }
@@ -966,11 +986,11 @@ MPB_HD void locate_on_levels(const MetView &g, const L &lv, double ts, double he
     }
     if (same) {
       if (hint) { hint[0] = s.iz; hint[1] = s.iz; }
-      s.wt = (ts - g.t0) / (g.t1 - g.t0);
-      s.wx = (lon2 - cx.lo) / (cx.hi - cx.lo);
-      s.wy = (lat2 - cy.lo) / (cy.hi - cy.lo);
+      s.wt = level_weight(ts - g.t0, g.t1 - g.t0, g.r_dt01);
+      s.wx = level_weight(lon2 - cx.lo, cx.hi - cx.lo, cx.rd);
+      s.wy = level_weight(lat2 - cy.lo, cy.hi - cy.lo, cy.rd);
       const double bot = level_height<L>(s, s.lo), top = level_height<L>(s, s.hi);
-      s.wz = (height - bot) / (top - bot);
+      s.wz = level_ratio(height - bot, top - bot);
       return;
     }
   }
@@ -1026,9 +1046,9 @@ MPB_HD void locate_on_levels(const MetView &g, const L &lv, double ts, double he
   }
   // round 3: the eight records, then the walk up to the level that brackets `height` on the interpolated coordinate
   s.iz = kmin;
-  s.wt = (ts - g.t0) / (g.t1 - g.t0);
-  s.wx = (lon2 - cx.lo) / (cx.hi - cx.lo);
-  s.wy = (lat2 - cy.lo) / (cy.hi - cy.lo);
+  s.wt = level_weight(ts - g.t0, g.t1 - g.t0, g.r_dt01);
+  s.wx = level_weight(lon2 - cx.lo, cx.hi - cx.lo, cx.rd);
+  s.wy = level_weight(lat2 - cy.lo, cy.hi - cy.lo, cy.rd);
 #pragma unroll
   for (int j = 0; j < 4; j++) { s.lo[j] = lv.load(s.col[j] + s.iz); s.hi[j] = lv.load(s.col[j] + s.iz + 1); }
   double bot = level_height<L>(s, s.lo), top = level_height<L>(s, s.hi);
@@ -1041,7 +1061,7 @@ MPB_HD void locate_on_levels(const MetView &g, const L &lv, double ts, double he
     for (int j = 0; j < 4; j++) { s.lo[j] = s.hi[j]; s.hi[j] = lv.load(s.col[j] + s.iz + 1); }
     top = level_height<L>(s, s.hi);
   }
-  s.wz = (height - bot) / (top - bot);
+  s.wz = level_ratio(height - bot, top - bot);
 }
 
 // one field at the 8 corners: longitude, then latitude, then level (2941-2980); v[column][0 = iz, 1 = iz + 1]
@@ -1100,6 +1120,7 @@ MPB_HD void advect_on_levels(const MetView &g, int vert_coord, double dt, Parcel
   double um = 0, vm = 0, wm = 0, u = 0, v = 0, w = 0, lat_stage = a.lat;
   int hint[2] = {-1, -1};
   if (level_hint && *level_hint >= 0 && *level_hint <= g.npl - 2) hint[0] = *level_hint;
+  const LonScale ks = lon_scale(g.coord_type, a.lat);   // metre -> degree divisor of the step's start latitude, shared by the stages
 #if MPB_LEVEL_CACHE
   LevelStencil<WindLevels> kept;
   kept.iz = -1;
@@ -1113,8 +1134,8 @@ MPB_HD void advect_on_levels(const MetView &g, int vert_coord, double dt, Parcel
       dts = 0.0; x = a.lon; y = a.lat; z = z0;
     } else {
       dts = (i == 3 ? 1.0 : 0.5) * dt;
-      x = a.lon + dx2coord_exact(g.coord_type, dts * u, a.lat);
-      y = a.lat + dy2coord_exact(g.coord_type, dts * v);
+      x = a.lon + dx2coord(ks, dts * u);
+      y = a.lat + dy2coord(g.coord_type, dts * v);
       z = z0 + dts * w;
     }
     lat_stage = y;
@@ -1130,8 +1151,8 @@ MPB_HD void advect_on_levels(const MetView &g, int vert_coord, double dt, Parcel
   }
   if (level_hint) *level_hint = hint[0];
   a.time += dt;
-  a.lon += dx2coord_exact(g.coord_type, dt * um, ORDER == 2 ? lat_stage : a.lat);
-  a.lat += dy2coord_exact(g.coord_type, dt * vm);
+  a.lon += (ORDER == 2) ? dx2coord(g.coord_type, dt * um, lat_stage) : dx2coord(ks, dt * um);
+  a.lat += dy2coord(g.coord_type, dt * vm);
   if (zq) {
     *zq = z0 + dt * wm;
     a.p = pressure_of_zeta(g, a.time, *zq, a.lon, a.lat);

@@ -13,8 +13,6 @@ GOLDEN = ROOT / "tests" / "golden"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
-    config.addinivalue_line("markers", "gpu_pending: GPU test of device code that is pinned on the host (tests/test_hostemu.py) "
-                            "but has not had its run on a B200 yet; run with `pytest -m gpu_pending`, then promote to `gpu`")
 
 
 def has_gpu() -> bool:

@@ -144,3 +144,32 @@ def test_two_processes_match_single(transport):
     full["q"] = np.stack([full.pop("q0"), full.pop("q1")])
     one, one_grid, q0 = _single()
     _check(full, grid, one, one_grid, q0)
+
+
+def test_team_with_cell_sort_moves_every_parcel_like_the_single_run():
+    """SORT_DT > 0 on a team: every member sorts ITS index range (no global order is needed), so the array order
+    differs from the single-context run -- but without diffusion each parcel's trajectory does not depend on its slot, so
+    matched by an identity quantity the positions must be bit-identical.  (With diffusion on, random numbers and uvwp are
+    attached to the slot: a sharded run with SORT_DT > 0 then agrees in distribution only -- DESIGN.md 4.)"""
+    from mptrac_b200 import Ctl, Engine, Team, load_library, synth
+    ndev = load_library().mpb_device_count()
+    n = 150_001
+    m0, m1 = synth.make_met_pair(72, 37, 30, t0=0.0, dt_met=21600.0)
+    tm, p, lon, lat = synth.make_parcels(n, t0=0.0, zmin=0.1, zmax=40.0, seed=3)
+    ident = np.arange(n, dtype=np.float64)[None, :]
+    ctl = Ctl(nq=1, advect=4, diffusion=0, sort_dt=600.0, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0)
+    clim = synth.make_clim_tropo()
+    outs = []
+    for make in (lambda: Team([i % ndev for i in range(3)], n, nq=1), lambda: Engine(n, nq=1, device=0)):
+        with make() as eng:
+            eng.set_ctl(ctl); eng.set_clim_tropo(*clim); eng.set_met(0, m0); eng.set_met(1, m1)
+            eng.set_atm(tm, p, lon, lat, ident)
+            for s in range(6):
+                eng.run_timestep(300.0 * s)
+            outs.append(eng.get_atm())
+    a, b = outs
+    ia, ib = np.argsort(a["q"][0]), np.argsort(b["q"][0])
+    assert np.array_equal(a["q"][0][ia], np.arange(n)) and np.array_equal(b["q"][0][ib], np.arange(n))
+    assert not np.array_equal(a["q"][0], b["q"][0])          # the two runs do order the parcels differently
+    for k in ("time", "lon", "lat", "p"):
+        assert np.array_equal(a[k][ia], b[k][ib]), k
