@@ -160,6 +160,10 @@ int mpb_set_ctl(mpb_ctx *ctx, const mpb_ctl_t *ctl);
 int mpb_set_clim_tropo(mpb_ctx *ctx, int ntime, int nlat, const double *time,
                        const double *lat, const double *tropo /* [ntime][nlat] */);
 int mpb_set_met(mpb_ctx *ctx, int slot /* 0 = met0, 1 = met1 */, const mpb_met_view_t *met);
+/* A met level straight from one of the reference's uncompressed binary files (MET_TYPE 1: write_met_bin src/mptrac.c:14204,
+ * read_met_bin :8887-9181) into the device layout, without a met_t in between; 3-D fields are clamped like read_met_bin_3d
+ * does; all_fields != 0 also uploads the further fields (mpb_met_view_t::x2 / x3).  Needs mpb_set_ctl first (MET_COORD_TYPE). */
+int mpb_set_met_bin(mpb_ctx *ctx, int slot, const char *path, int all_fields);
 int mpb_swap_met(mpb_ctx *ctx);   /* the pointer swap of mptrac_get_met, src/mptrac.c:6489-6491 */
 int mpb_set_atm(mpb_ctx *ctx, int64_t np, const double *time, const double *p,
                 const double *lon, const double *lat, const double *q, int64_t q_stride);

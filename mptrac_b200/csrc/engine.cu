@@ -500,6 +500,15 @@ static step_fn pick_step(int advect, unsigned phys) {
   }
 }
 
+// bounds of read_met_bin_3d (src/mptrac.c:9168-9178): values below / above are set to the bound (NaN stays NaN)
+__global__ void clamp_field_kernel(float *f, size_t n, float lo, float hi) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = f[i];
+  if (v < lo) f[i] = lo;
+  else if (v > hi) f[i] = hi;
+}
+
 // write four dense fields [n] into time-level `slot` (0 / 1) of the met nodes {u0,u1, v0,v1, w0,w1, t0,t1}
 __global__ void pack_met_nodes_kernel(const float *u, const float *v, const float *w, const float *t, float *nodes, int slot, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2267,6 +2276,115 @@ int mpb_set_met(mpb_ctx *c, int slot, const mpb_met_view_t *m) {
     if (m->x3[f]) { put_field(m->x3[f], &c->x3[f], nnode, true); c->x3_valid[slot][f] = true; }
   }
   c->lev[slot].time = m->time;
+  c->lev[slot].valid = true;
+  API_END
+}
+
+// A met level straight from one of the reference's binary files (MET_TYPE 1, uncompressed; written by write_met_bin,
+// src/mptrac.c:14204 ff., read by read_met_bin, :8887-9181) into the packed device layout.  The file holds dense arrays --
+// [nx][ny] and [nx][ny][np], the level index fastest -- i.e. exactly what the pack kernels take: every field goes from the
+// file into the pinned staging buffer and from there to the device, without the detour through a 10.7 GB met_t and without
+// any strided compaction.  Like the reference, nothing is pre-processed (binary files hold finished fields, :7769-7773), and
+// 3-D fields are clamped to read_met_bin_3d's bounds.  all_fields != 0 also uploads the further 2-D / 3-D fields of
+// module_meteo and of the boundary-layer / convection modules.
+int mpb_set_met_bin(mpb_ctx *c, int slot, const char *path, int all_fields) {
+  API_BEGIN
+  use(c);
+  REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  REQUIRE(path != nullptr, "null path");
+  REQUIRE(c->have_ctl, "mpb_set_ctl comes first (MET_COORD_TYPE)");
+  FILE *in = std::fopen(path, "rb");
+  REQUIRE(in != nullptr, std::string("cannot open ") + path);
+  struct Closer { FILE *f; ~Closer() { if (f) std::fclose(f); } } closer{in};
+  auto rd = [&](void *dst, size_t size, size_t count, const char *what) {
+    REQUIRE(std::fread(dst, size, count, in) == count, std::string("binary met file ends early (") + what + ")");
+  };
+  int met_type = 0, version = 0, nx = 0, ny = 0, np = 0;
+  double time = 0;
+  rd(&met_type, sizeof(int), 1, "type");
+  REQUIRE(met_type == 1, "only uncompressed binary met files (MET_TYPE 1) can be read directly");
+  rd(&version, sizeof(int), 1, "version");
+  REQUIRE(version == 104, "wrong version of binary met data (104 expected)");
+  rd(&time, sizeof(double), 1, "time");
+  rd(&nx, sizeof(int), 1, "nx"); rd(&ny, sizeof(int), 1, "ny"); rd(&np, sizeof(int), 1, "np");
+  REQUIRE(nx >= 2 && ny >= 2 && np >= 2 && nx < (1 << 20) && ny < (1 << 20) && np < (1 << 16), "binary met file: dimensions out of range");
+  std::vector<double> lon(nx), lat(ny), p(np);
+  rd(lon.data(), sizeof(double), (size_t)nx, "lon"); rd(lat.data(), sizeof(double), (size_t)ny, "lat"); rd(p.data(), sizeof(double), (size_t)np, "p");
+  const size_t nnode = (size_t)nx * ny * np, ncol = (size_t)nx * ny;
+  CK(cudaStreamSynchronize(c->stream));
+  ensure_grid(c, nx, ny, np, c->ctl.met_coord_type, lon.data(), lat.data(), p.data(), true);
+
+  auto further = [&](float2 **dst, size_t n) {          // stage_h[0 .. n) -> one further field (mpb_met_view_t::x2 / x3)
+    if (!*dst) {
+      CK(cudaMalloc(dst, sizeof(float2) * n));
+      CK(cudaMemsetAsync(*dst, 0, sizeof(float2) * n, c->stream));
+    }
+    CK(cudaMemcpyAsync(c->stage_d, c->stage_h, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+  };
+  // ---- the 24 surface fields, file order of read_met_bin (:8994-9017) ----
+  // PS TS ZS US VS ESS NSS SHF LSM SST PBL PT TT ZT H2OT PCT PCB CL PLCL PLFC PEL CAPE CIN O3C
+  static const int f2_of_file[24] = {-1, MPB_F2_TS, MPB_F2_ZS, MPB_F2_US, MPB_F2_VS, MPB_F2_ESS, MPB_F2_NSS, MPB_F2_SHF, MPB_F2_LSM, MPB_F2_SST,
+                                     -2, MPB_F2_PT, MPB_F2_TT, MPB_F2_ZT, MPB_F2_H2OT, MPB_F2_PCT, MPB_F2_PCB, MPB_F2_CL, MPB_F2_PLCL,
+                                     MPB_F2_PLFC, MPB_F2_PEL, MPB_F2_CAPE, MPB_F2_CIN, MPB_F2_O3C};
+  float *ps_pbl = c->stage_h + 2 * nnode;                 // kept aside until both have been read
+  for (int k = 0; k < 24; k++) {
+    const int f = f2_of_file[k];
+    if (f < 0) { rd(ps_pbl + (f == -1 ? 0 : ncol), sizeof(float), ncol, "surface field"); continue; }
+    if (!all_fields) { REQUIRE(std::fseek(in, (long)(sizeof(float) * ncol), SEEK_CUR) == 0, "binary met file ends early (surface field)"); continue; }
+    rd(c->stage_h, sizeof(float), ncol, "surface field");
+    further(&c->x2[f], ncol);
+    pack_scalar_kernel<<<nblocks((long long)ncol, 256), 256, 0, c->stream>>>(c->stage_d, (float *)c->x2[f], slot, ncol);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    c->launches++;
+    c->x2_valid[slot][f] = true;
+  }
+  if (!all_fields) for (int f = 0; f < MPB_NX2; f++) c->x2_valid[slot][f] = false;
+  CK(cudaMemcpyAsync(c->stage_d, ps_pbl, sizeof(float) * 2 * ncol, cudaMemcpyHostToDevice, c->stream));
+  pack_surface_kernel<<<nblocks((long long)ncol, 256), 256, 0, c->stream>>>(c->stage_d, c->stage_d + ncol, (float2 *)c->surf, slot, ncol);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  c->launches++;
+  // ---- the 13 level fields (:9020-9032): Z T U V W PV H2O O3 LWC RWC IWC SWC CC, with read_met_bin_3d's bounds ----
+  static const int f3_of_file[13] = {MPB_F3_Z, -1, -1, -1, -1, MPB_F3_PV, MPB_F3_H2O, MPB_F3_O3, MPB_F3_LWC, MPB_F3_RWC, MPB_F3_IWC, MPB_F3_SWC, MPB_F3_CC};
+  static const float lo3[13] = {-1e34f, 0.f, -1e34f, -1e34f, -1e34f, -1e34f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  static const float hi3[13] = {1e34f, 1e34f, 1e34f, 1e34f, 1e34f, 1e34f, 1e34f, 1e34f, 1e34f, 1e34f, 1e34f, 1e34f, 1.f};
+  static const int node_slot[13] = {-1, 3, 0, 1, 2, -1, -1, -1, -1, -1, -1, -1, -1};   // T, U, V, W -> staging order u, v, w, t
+  const unsigned gn = nblocks((long long)nnode, 256);
+  for (int k = 0; k < 13; k++) {
+    const int f = f3_of_file[k];
+    if (node_slot[k] >= 0) {
+      float *h = c->stage_h + (size_t)node_slot[k] * nnode, *d = c->stage_d + (size_t)node_slot[k] * nnode;
+      rd(h, sizeof(float), nnode, "level field");
+      CK(cudaMemcpyAsync(d, h, sizeof(float) * nnode, cudaMemcpyHostToDevice, c->stream));
+      clamp_field_kernel<<<gn, 256, 0, c->stream>>>(d, nnode, lo3[k], hi3[k]);
+      CK(cudaGetLastError());
+      c->launches++;
+      if (k == 4) {      // W was the last of the four: pack the nodes, then the staging area is free again
+        pack_met_nodes_kernel<<<gn, 256, 0, c->stream>>>(c->stage_d, c->stage_d + nnode, c->stage_d + 2 * nnode, c->stage_d + 3 * nnode,
+                                                         (float *)c->nodes, slot, nnode);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->stream));
+        c->launches++;
+      }
+      continue;
+    }
+    if (!all_fields) { REQUIRE(std::fseek(in, (long)(sizeof(float) * nnode), SEEK_CUR) == 0, "binary met file ends early (level field)"); continue; }
+    rd(c->stage_h, sizeof(float), nnode, "level field");
+    further(&c->x3[f], nnode);
+    clamp_field_kernel<<<gn, 256, 0, c->stream>>>(c->stage_d, nnode, lo3[k], hi3[k]);
+    pack_scalar_kernel<<<gn, 256, 0, c->stream>>>(c->stage_d, (float *)c->x3[f], slot, nnode);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    c->launches += 2;
+    c->x3_valid[slot][f] = true;
+  }
+  if (!all_fields) for (int f = 0; f < MPB_NX3; f++) c->x3_valid[slot][f] = false;
+  int final_flag = 0;
+  rd(&final_flag, sizeof(int), 1, "final flag");
+  REQUIRE(final_flag == 999, "binary met file: final flag missing");
+  c->lev_valid[slot] = false;       // (binary files carry no model-level fields)
+  c->lev[slot].time = time;
   c->lev[slot].valid = true;
   API_END
 }

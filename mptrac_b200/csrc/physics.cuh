@@ -276,9 +276,12 @@ MPB_HD LonScale lon_scale(int coord_type, double lat) {
   if (lat < -89.999 || lat > 89.999) { k.mode = 1; return k; }
   k.mode = 2;
   k.d = kPiRE * cos_quarter(lat * (kPi / 180.0));   // |lat| <= 89.999 here
+#if MPB_FAST_QUOT && !defined(MPB_LONSCALE_IEEE_RCP)
+  k.rd = fdiv(0.18, k.d);   // metres -> degrees in one multiply: dx / 1000 * 180 / d (reciprocal estimate + two Newton steps)
+#elif MPB_FAST_QUOT
+  k.rd = 1.0 / k.d * 0.18;
+#else
   k.rd = 1.0 / k.d;
-#if MPB_FAST_QUOT
-  k.rd *= 0.18;   // metres -> degrees in one multiply: dx / 1000 * 180 / d
 #endif
   return k;
 }

@@ -327,6 +327,7 @@ def load_library(strict: bool = False) -> C.CDLL:
         "mpb_set_ctl": (i32, [vp, P(_CtlStruct)]),
         "mpb_set_clim_tropo": (i32, [vp, i32, i32, vp, vp, vp]),
         "mpb_set_met": (i32, [vp, i32, P(_MetViewStruct)]),
+        "mpb_set_met_bin": (i32, [vp, i32, C.c_char_p, i32]),
         "mpb_swap_met": (i32, [vp]),
         "mpb_set_atm": (i32, [vp, i64, vp, vp, vp, vp, vp, i64]),
         "mpb_set_uvwp": (i32, [vp, vp]),
@@ -471,6 +472,10 @@ class Engine:
     def set_met(self, slot: int, met: Met):
         v = met.view()
         self._ck(self._lib.mpb_set_met(self._h, int(slot), C.byref(v)))
+
+    def set_met_bin(self, slot: int, path, all_fields: bool = False):
+        """a met level straight from one of the reference's uncompressed binary files (MET_TYPE 1)"""
+        self._ck(self._lib.mpb_set_met_bin(self._h, int(slot), str(path).encode(), int(bool(all_fields))))
 
     def swap_met(self):
         self._ck(self._lib.mpb_swap_met(self._h))

@@ -166,3 +166,32 @@ def add_meteo_fields(met: Met, seed=11, with_gaps=True) -> Met:
         out[k] = a
     assert set(out) == set(MET_X2) | set(MET_X3)
     return replace(met, extra=out)
+
+
+MET_BIN_2D = ("ps", "ts", "zs", "us", "vs", "ess", "nss", "shf", "lsm", "sst", "pbl", "pt", "tt", "zt", "h2ot", "pct", "pcb", "cl",
+              "plcl", "plfc", "pel", "cape", "cin", "o3c")
+MET_BIN_3D = ("z", "t", "u", "v", "w", "pv", "h2o", "o3", "lwc", "rwc", "iwc", "swc", "cc")
+
+
+def write_met_bin(path, met: Met):
+    """Write ``met`` in the reference's uncompressed binary met format (MET_TYPE 1, version 104: write_met_bin,
+    src/mptrac.c:14204 ff.): type, version, time, nx, ny, np, the three axes, 24 surface fields [nx][ny], 13 level fields
+    [nx][ny][np], the final flag 999.  Fields the Met does not carry (``Met.extra``) are written as zeros."""
+    nx, ny, nz = met.u.shape
+    extra = getattr(met, "extra", None) or {}
+
+    def field(name, shape):
+        a = getattr(met, name, None) if name in ("u", "v", "w", "t", "ps", "pbl") else extra.get(name)
+        return np.zeros(shape, np.float32) if a is None else np.ascontiguousarray(a, np.float32).reshape(shape)
+
+    with open(path, "wb") as f:
+        f.write(np.array([1, 104], np.int32).tobytes())
+        f.write(np.array([met.time], np.float64).tobytes())
+        f.write(np.array([nx, ny, nz], np.int32).tobytes())
+        for ax in (met.lon, met.lat, met.p):
+            f.write(np.ascontiguousarray(ax, np.float64).tobytes())
+        for name in MET_BIN_2D:
+            f.write(field(name, (nx, ny)).tobytes())
+        for name in MET_BIN_3D:
+            f.write(field(name, (nx, ny, nz)).tobytes())
+        f.write(np.array([999], np.int32).tobytes())

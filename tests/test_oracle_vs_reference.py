@@ -494,3 +494,23 @@ def test_surface_gaps_bit_exact(oracle, reference):
     for k in ("lon", "lat", "p"):
         assert np.array_equal(getattr(a, k), getattr(b, k), equal_nan=True), k
     assert np.mean(np.isfinite(a.p)) > 0.5
+
+
+def test_binary_met_file_as_the_reference_reads_it(reference, tmp_path):
+    """synth.write_met_bin writes the reference's uncompressed binary met format (MET_TYPE 1): the reference's own
+    read_met_bin (src/mptrac.c:8887-9181, through mptrac_read_met) must recover exactly the fields that were written --
+    with its bounds applied (negative temperatures become 0)"""
+    from mptrac_b200 import Met, synth
+    m = synth.add_meteo_fields(synth.make_met(48, 25, 24, time=360547200.0), with_gaps=False)
+    m.t[3, 4, 5] = -7.0            # read_met_bin_3d clamps T to [0, 1e34]
+    f = tmp_path / "met_2011_06_05_00.bin"
+    synth.write_met_bin(f, m)
+    reference.read_ctl([], "MET_TYPE 1")
+    got = reference.read_met(f, 0, Met)
+    assert got.time == m.time and got.u.shape == m.u.shape
+    for k in ("lon", "lat", "p", "u", "v", "w", "ps", "pbl"):
+        assert np.array_equal(getattr(got, k), getattr(m, k)), k
+    want_t = m.t.copy()
+    want_t[3, 4, 5] = 0.0
+    assert np.array_equal(got.t, want_t)
+    reference.read_ctl([], "")
