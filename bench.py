@@ -316,7 +316,7 @@ def exchange_record(name, rank, world, local, K=12, W=3):
             "transport": ("none (one rank)" if world == 1 else
                           "peer memory: contributions routed to the owner of each box and answers routed back as coalesced stores over NVLink, "
                           "local atomics, flag barriers (own kernels)" if attached
-                          else "NCCL: one all-reduce of the dense box records" if wl.get("mixing") else "NCCL reduce of the output boxes"),
+                          else "NCCL: one all-reduce of the dense box records" if wl.get("mixing") else "NCCL all-reduce of the output boxes"),
             "exchanged_bytes_per_rank_per_step": int(per_rank)}
 
 

@@ -113,8 +113,8 @@ def grid_output(engine, grid: dict, device, group=None, dst: int = 0, attached: 
         parts = [device_tensor(engine.device_ptr("grid_cnt"), nbox, "i4", device),
                  device_tensor(engine.device_ptr("grid_sum"), nbox * nq, "f8", device),
                  device_tensor(engine.device_ptr("grid_sq"), nbox * nq, "f8", device)]
-        for x in parts:
-            dist.reduce(x, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        for x in parts:      # (an all-reduce: 1.3 MB, and unlike reduce it is available for device tensors on every backend)
+            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
         if dist.get_rank(group) != dst:
             return None
     return engine.grid_fetch()

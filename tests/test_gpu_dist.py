@@ -3,10 +3,11 @@ with ONE exchange step each -- against a single-context run of all parcels.  Thr
 
   team   several contexts behind one host thread (mpb_team_*), box records exchanged through peer memory, stream events;
   peers  one process per rank attached through CUDA IPC (mpb_peer_*): NVLink atomics + flag barriers in stream order;
-  nccl   one process per rank, ONE all-reduce of the dense box records (needs two GPUs; skipped on a one-GPU box).
+  allreduce  one process per rank, ONE all-reduce of the dense box records: NCCL with one GPU per rank, gloo (which moves CUDA
+         tensors through the host) when both ranks have to share device 0.
 
-team and peers also run on a single GPU (two contexts / two processes on device 0), so the exchange logic is exercised by
-every run of the suite; with two or more GPUs the same tests use distinct devices (real peer traffic)."""
+All three also run on a single GPU (two contexts / two processes on device 0), so the exchange logic is exercised by every
+run of the suite; with two or more GPUs the same tests use distinct devices (real peer traffic, NCCL)."""
 import os
 import socket
 
@@ -88,7 +89,7 @@ def _worker(rank, world, port, ret, transport, ndev):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     device = rank % ndev
     torch.cuda.set_device(device)
-    if transport == "nccl":
+    if transport == "allreduce" and ndev >= world:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", device))
     else:
         dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -102,7 +103,7 @@ def _worker(rank, world, port, ret, transport, ndev):
         stream = torch.cuda.Stream()
         torch.cuda.set_stream(stream)
         with Engine(hi - lo, nq=ctl.nq, device=device) as eng:
-            eng.set_stream(stream.cuda_stream)      # NCCL runs on torch's current stream: the engine shares it
+            eng.set_stream(stream.cuda_stream)      # the collective runs on torch's current stream: the engine shares it
             eng.set_ctl(ctl); eng.set_clim_tropo(*clim); eng.set_met(0, m0); eng.set_met(1, m1)
             eng.set_atm(tm[lo:hi], p[lo:hi], lon[lo:hi], lat[lo:hi], np.ascontiguousarray(q[:, lo:hi]))
             eng.set_shard(lo, n)
@@ -118,7 +119,7 @@ def _worker(rank, world, port, ret, transport, ndev):
             eng.sync()
             out = eng.get_atm()
             dist.barrier()                          # nobody frees its exchange area while a peer may still read it
-        side = dist.new_group(backend="gloo") if transport == "nccl" else None
+        side = dist.new_group(backend="gloo") if dist.get_backend() == "nccl" else None
         full = mdist.gather_parcels({"lon": out["lon"], "lat": out["lat"], "p": out["p"], "q0": out["q"][0], "q1": out["q"][1]},
                                     n, group=side)
         if rank == 0:
@@ -129,13 +130,11 @@ def _worker(rank, world, port, ret, transport, ndev):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("transport", ["peers", "nccl"])
+@pytest.mark.parametrize("transport", ["peers", "allreduce"])
 def test_two_processes_match_single(transport):
     import torch
     import torch.multiprocessing as mp
     ndev = torch.cuda.device_count()
-    if transport == "nccl" and ndev < 2:
-        pytest.skip("NCCL needs one GPU per rank")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     with mp.Manager() as mgr:
         ret = mgr.dict()
