@@ -73,6 +73,13 @@ WORKLOADS = {
                                "levels, then the 8 records) at 16 resident warps/SM, ~890 instructions per stage; ncu r01h under "
                                "profiles/, DESIGN.md 7",
                  desc="1M parcels, 1x1 deg x 60 model levels, RK4 advection with omega on model levels (ADVECT_VERT_COORD 2)"),
+    # probes, not BASELINE configurations: the module mixes of c3 and c4 exchanged between their grids (to tell an effect of
+    # the instruction mix from an effect of the grid size when a build flag helps one of the two)
+    "x3t": dict(np=10_000_000, grid=(720, 361, 137), ctl=dict(advect=4, diffusion=1, sort_dt=3600.0), state_bytes=88, met_fields=3,
+                label="probe", desc="probe: c3's parcels and grid with c4's modules (RK4 + turbulent + mesoscale diffusion)"),
+    "x4s": dict(np=12_500_000, grid=(360, 181, 60), ctl=dict(advect=4, diffusion=1, turb_dx_pbl=0, turb_dx_trop=0, turb_dz_strat=0,
+                                                              qnt_rp=0, qnt_rhop=1, nq=2, sort_dt=3600.0), state_bytes=104, met_fields=4,
+                label="probe", desc="probe: c4's parcels and grid with c3's modules (RK4 + mesoscale diffusion + sedimentation)"),
 }
 DT_MOD = 300.0
 DT_MET = 21600.0

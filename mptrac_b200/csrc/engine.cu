@@ -101,6 +101,11 @@ constexpr unsigned PHYS_TURB = 1, PHYS_MESO = 2, PHYS_SEDI = 4;
 #endif                   // with bulk copies (four copies serialised in one lane + mbarrier polling against four issued by all lanes at
                          // once), and 120 us with both paths compiled in (the unrolled RK4 loop sits at the instruction-cache edge:
                          // stall_no_instruction doubles).  The strict library is built with 1, so both paths are in the GPU test suite.
+#ifndef MPB_ROLL_SEDI     // 1: the Runge-Kutta stage loop stays rolled in the kernels that also carry sedimentation.  Measured
+#define MPB_ROLL_SEDI 1   // (same box, rolled against unrolled): configs[2] (0.5 deg grid, mesoscale diffusion + sedimentation)
+#endif                    // 2.496 against 2.635 ms; the same modules on the 1 deg grid 2.690 against 2.670; rolled in the
+                          // turbulent + mesoscale kernel: configs[3] 2.727 against 2.648, on the 0.5 deg grid 2.443 against 2.408;
+                          // advection alone: no difference.  profiles/r02o_roll_stage_loop.txt
 #ifndef MPB_PERSIST      // 1: grid = SMs x resident blocks, threads loop over parcels; 0: one block per kBlock parcels
 #define MPB_PERSIST 1    // (measured: 126 us vs 135 us)
 #endif
@@ -148,7 +153,7 @@ __device__ __forceinline__ void parcel_finish(const StepArgs &A, long long ip, P
     advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, wc);
   }
 #else
-  if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1)>(A.met, dt, a, cube);
+  if (ADVECT > 0) advect<(ADVECT > 0 ? ADVECT : 1), (PHYS & PHYS_SEDI) != 0 && (MPB_ROLL_SEDI != 0)>(A.met, dt, a, cube);
 #endif
   if (PHYS & PHYS_TURB) diffuse_turbulent(A.met, A.clim, A.ctl, dt, ig, a);
   if constexpr ((PHYS & PHYS_MESO) != 0) {

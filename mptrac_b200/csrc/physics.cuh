@@ -849,15 +849,17 @@ MPB_HD void prefetch_ahead(const MetView &g, const Parcel &a, double dt, double 
 #endif
 }
 
-template <int ORDER, class CubeT>
+// ROLL: keep the stage loop rolled (same arithmetic, a quarter fewer instructions in the kernels that carry diffusion).  For
+// advection alone both forms run at the same speed; which of the two is faster with the other modules compiled in was
+// measured per module mix and grid (engine.cu MPB_ROLL_SEDI).
+template <int ORDER, bool ROLL = false, class CubeT>
 MPB_HD void advect(const MetView &g, double dt, Parcel &a, CubeT &c) {
   double um = 0, vm = 0, wm = 0;
   double u = 0, v = 0, w = 0;
   double lat_stage = a.lat;
   const LonScale ks = lon_scale(g.coord_type, a.lat);   // the stages and (Euler, RK4) the final update share it
   double wt = 0;
-#pragma unroll   // (measured: a rolled stage loop -- 1600 instead of 2850 SASS instructions -- runs at the same speed)
-  for (int i = 0; i < ORDER; i++) {
+  auto stage = [&](int i) {
     double x, y, z, dts;
     if (i == 0) {
       dts = 0.0; x = a.lon; y = a.lat; z = a.p;
@@ -875,6 +877,13 @@ MPB_HD void advect(const MetView &g, double dt, Parcel &a, CubeT &c) {
     if (ORDER == 2) k = (i == 0 ? 0.0 : 1.0);
     else if (ORDER == 4) k = (i == 0 || i == 3 ? 1.0 / 6.0 : 2.0 / 6.0);
     um += k * u; vm += k * v; wm += k * w;
+  };
+  if (ROLL) {
+#pragma unroll 1
+    for (int i = 0; i < ORDER; i++) stage(i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < ORDER; i++) stage(i);
   }
   a.time += dt;
   a.lon += (ORDER == 2) ? dx2coord(g.coord_type, dt * um, lat_stage) : dx2coord(ks, dt * um);
