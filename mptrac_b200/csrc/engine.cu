@@ -115,7 +115,11 @@ constexpr long long kHostChunkMin = 16384;      // parcels per chunk: at least 1
 constexpr long long kHostChunkMax = 1 << 20;    // ... at most 8 MiB
 
 #ifndef MPB_LEVEL_MINBLOCKS
-#define MPB_LEVEL_MINBLOCKS 4   // resident blocks per SM the model-level advection kernel is compiled for
+#define MPB_LEVEL_MINBLOCKS 16  // resident blocks per SM the model-level advection kernel is compiled for
+#endif
+#ifndef MPB_LEVEL_BLOCK
+#define MPB_LEVEL_BLOCK 32      // ... and its block size: one warp, so that a finished warp is replaced at once (measured 128 / 64 / 32
+                                // threads: 0.290 / 0.284 / 0.281 ms per step of c2ml, profiles/r02p_sweep_level_near.jsonl)
 #endif
 #ifdef MPB_NO_BOUNDS   // register budget given by -maxrregcount instead (variant sweeps)
 #define MPB_BOUNDS
@@ -800,7 +804,7 @@ struct LevelArgs {
 };
 
 template <int ORDER>
-__global__ void __launch_bounds__(128, MPB_LEVEL_MINBLOCKS) advect_levels_kernel(const __grid_constant__ LevelArgs A) {
+__global__ void __launch_bounds__(MPB_LEVEL_BLOCK, MPB_LEVEL_MINBLOCKS) advect_levels_kernel(const __grid_constant__ LevelArgs A) {
   const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (ip >= A.np) return;
   const double dt = A.dt[ip];
@@ -924,6 +928,16 @@ __global__ void mix_apply_kernel(const __grid_constant__ MixArgs A, ClimView cli
   }
 }
 
+__global__ void mix_clear_kernel(const MixArgs A) {
+  const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= A.np) return;
+  const int b = A.box[ip];
+  if (b < 0) return;
+  const long long idx = (long long)(A.ens ? (int)A.ens[ip] : 0) * A.ngrid + b;
+  double2 *rec = reinterpret_cast<double2 *>(A.rec[0] + idx * A.stride);
+  for (int k = 0; k < A.stride / 2; k++) rec[k] = make_double2(0.0, 0.0);
+}
+
 // ---- several ranks: the routed exchange ----
 // Remote atomics (one NVLink transaction per contribution) measured no better than NCCL's dense all-reduce (8 GPUs: 0.39 ms
 // against 0.42 ms per step for configs[4]).  Instead every contribution travels ONCE as part of a coalesced store stream:
@@ -949,7 +963,15 @@ struct RouteArgs {
   int iq[MPB_MIX_MAXQ];
 };
 
-__global__ void mix_route_kernel(const __grid_constant__ RouteArgs A) {
+constexpr int kRouteBlock = 1024;
+__global__ void __launch_bounds__(kRouteBlock) mix_route_kernel(const __grid_constant__ RouteArgs A) {
+  // Slot allocation in two levels: the lanes of a warp that share an owner reserve consecutive places in the BLOCK's count
+  // for that owner (shared-memory atomic), one thread per owner then reserves the block's range with ONE global atomic.
+  // (One global atomic per (warp, owner) put ~60 000 atomics per launch on at most `nranks` addresses, which serialise in L2:
+  // the kernel took 69 us for 1.25 M parcels on 2 ranks, three times the single-rank accumulation.)
+  __shared__ unsigned s_cnt[kMaxRanks], s_base[kMaxRanks];
+  if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
   const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (the grid covers whole warps)
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -964,18 +986,26 @@ __global__ void mix_route_kernel(const __grid_constant__ RouteArgs A) {
       local = idx - (long long)owner * A.slice;
     }
   }
-  // one slot allocation per (warp, owner): the lanes that share an owner take consecutive slots
   const unsigned peers = __match_any_sync(full, owner);
-  int slot = -1;
+  unsigned place = 0;
   if (owner >= 0) {
     const int leader = __ffs(peers) - 1;
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(A.alloc + owner, (unsigned)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    slot = (int)(base + (unsigned)__popc(peers & ((1u << lane) - 1u)));
+    if (lane == leader) place = atomicAdd(&s_cnt[owner], (unsigned)__popc(peers));
+    place = __shfl_sync(peers, place, leader) + (unsigned)__popc(peers & ((1u << lane) - 1u));
+  }
+  __syncthreads();
+  if (threadIdx.x < A.nranks && s_cnt[threadIdx.x] > 0) s_base[threadIdx.x] = atomicAdd(A.alloc + threadIdx.x, s_cnt[threadIdx.x]);
+  __syncthreads();
+  int slot = -1;
+  if (owner >= 0) {
+    slot = (int)(s_base[owner] + place);
     double *e = A.inbox[owner] + (size_t)slot * A.E;
-    e[0] = (double)local;
-    for (int k = 0; k < A.nmix; k++) e[1 + k] = A.q0[(long long)A.iq[k] * A.q_stride + ip];
+    if (A.E == 2) {     // one mixed quantity: the entry is one 16-byte store
+      *reinterpret_cast<double2 *>(e) = make_double2((double)local, A.q0[(long long)A.iq[0] * A.q_stride + ip]);
+    } else {
+      e[0] = (double)local;
+      for (int k = 0; k < A.nmix; k++) e[1 + k] = A.q0[(long long)A.iq[k] * A.q_stride + ip];
+    }
   }
   if (ip < A.np) A.route[ip] = make_int2(owner, slot);
 }
@@ -1012,7 +1042,8 @@ __global__ void mix_answer_kernel(const __grid_constant__ ServeArgs A) {
     const double *in = A.inbox + ((size_t)s * A.cap + (size_t)e) * A.E;
     const double *rec = A.rec + (size_t)in[0] * A.E;
     double *out = A.outbox_at[s] + (size_t)e * A.E;
-    for (int k = 0; k < A.E; k++) out[k] = rec[k];
+    if (A.E == 2) *reinterpret_cast<double2 *>(out) = *reinterpret_cast<const double2 *>(rec);
+    else for (int k = 0; k < A.E; k++) out[k] = rec[k];
   }
 }
 
@@ -1188,6 +1219,10 @@ struct mpb_ctx {
   long long ig0 = 0, global_np = -1;
   unsigned long long rng_ctr = 0;
   long long launches = 0;
+  long long mix_clean = 0;   // the first mix_clean doubles of mix_rec are known to be zero (single rank: the records are cleared
+                             // behind the parcels that touched them instead of zeroing all 5.8 M boxes every step)
+  double mix_trace_ms[6] = {0, 0, 0, 0, 0, 0};   // MPTRAC_B200_TRACE_MIXING: summed phase times of mixing_inline
+  long long mix_trace_n = 0;
 
   // parcels: [time | p | lon | lat | q0 .. q(nq-1)] each np_max doubles, two copies
   double *soa[2] = {nullptr, nullptr};
@@ -1485,11 +1520,11 @@ static LevelArgs level_args(mpb_ctx *c) {
 static void launch_advect_levels(mpb_ctx *c) {
   if (c->np == 0) return;
   const LevelArgs A = level_args(c);
-  const unsigned grid = nblocks(c->np, 128);
+  const unsigned grid = nblocks(c->np, MPB_LEVEL_BLOCK);
   switch (c->ctl.advect) {
-    case 1: advect_levels_kernel<1><<<grid, 128, 0, c->stream>>>(A); break;
-    case 2: advect_levels_kernel<2><<<grid, 128, 0, c->stream>>>(A); break;
-    case 4: advect_levels_kernel<4><<<grid, 128, 0, c->stream>>>(A); break;
+    case 1: advect_levels_kernel<1><<<grid, MPB_LEVEL_BLOCK, 0, c->stream>>>(A); break;
+    case 2: advect_levels_kernel<2><<<grid, MPB_LEVEL_BLOCK, 0, c->stream>>>(A); break;
+    case 4: advect_levels_kernel<4><<<grid, MPB_LEVEL_BLOCK, 0, c->stream>>>(A); break;
     default: REQUIRE(false, "ADVECT must be 0, 1, 2 or 4");
   }
   CK(cudaGetLastError());
@@ -1605,8 +1640,10 @@ static void mixing_prepare(mpb_ctx *c, double t) {
       if (c->mix_rec) CK(cudaFree(c->mix_rec));
       CK(cudaMalloc(&c->mix_rec, sizeof(double) * (size_t)need));
       c->mix_cap = need;
+      c->mix_clean = 0;
     }
-    CK(cudaMemsetAsync(c->mix_rec, 0, sizeof(double) * (size_t)need, c->stream));
+    if (c->mix_clean != need) CK(cudaMemsetAsync(c->mix_rec, 0, sizeof(double) * (size_t)need, c->stream));
+    c->mix_clean = 0;     // dirty until mixing_inline has cleared behind its parcels
   } else {
     // routed exchange: this rank keeps the records of its slice of the box space locally and zeroes them every step
     c->mix_slice = (total + c->nranks - 1) / c->nranks;
@@ -1619,6 +1656,7 @@ static void mixing_prepare(mpb_ctx *c, double t) {
       CK(cudaMalloc(&c->mix_rec, sizeof(double) * (size_t)need));
       c->mix_cap = need;
     }
+    c->mix_clean = 0;
     if (!c->mix_alloc) {
       CK(cudaMalloc(&c->mix_alloc, sizeof(unsigned int) * kMaxRanks));
       CK(cudaMalloc(&c->mix_route, sizeof(int2) * (size_t)c->np_max));
@@ -1667,6 +1705,18 @@ static void mixing_apply_all(mpb_ctx *c) {
   }
 }
 
+// Single rank: zero the records of the boxes this call's parcels fell into, which are all the records that are not zero,
+// so that the next call finds clean records without a memset of the whole grid (reference default: 5.8 M boxes = 93 MB
+// for one quantity, against 1.25 M parcels in configs[4]'s share).
+static void mixing_clear_touched(mpb_ctx *c) {
+  if (c->np > 0 && c->nmix > 0) {
+    mix_clear_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(mix_args(c));
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  c->mix_clean = (c->nmix + 2) / 2 * 2 * c->mix_total;
+}
+
 // the three phases of the routed exchange (several ranks); a barrier over the ranks separates them
 static void mixing_route(mpb_ctx *c) {
   const mpb_ctl_t &k = c->ctl;
@@ -1684,7 +1734,7 @@ static void mixing_route(mpb_ctx *c) {
   A.q0 = c->nq ? c->q(0) : nullptr;
   for (int i = 0; i < MPB_MIX_MAXQ; i++) A.iq[i] = i < c->nmix ? c->mix_iq[i] : 0;
   if (c->np > 0 && c->nmix > 0) {
-    mix_route_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(A);
+    mix_route_kernel<<<nblocks(c->np, kRouteBlock), kRouteBlock, 0, c->stream>>>(A);
     CK(cudaGetLastError());
     c->launches++;
   }
@@ -1719,16 +1769,46 @@ static void mixing_apply_routed(mpb_ctx *c) {
 
 // module_mixing on one context: alone, or as one rank of a multi-process run (barriers in stream order between the phases)
 static void mixing_inline(mpb_ctx *c, double t) {
+  // MPTRAC_B200_TRACE_MIXING=1 (diagnostics): events around the phases, read back after a stream synchronisation per call;
+  // the averages are printed by mpb_destroy.  Phases: prepare | route (accumulate) | barrier | serve | barrier | apply
+  static const bool trace = std::getenv("MPTRAC_B200_TRACE_MIXING") != nullptr;
+  cudaEvent_t ev[7];
+  int ne = 0;
+  auto mark = [&]() {
+    if (!trace) return;
+    CK(cudaEventCreate(&ev[ne]));
+    CK(cudaEventRecord(ev[ne], c->stream));
+    ne++;
+  };
+  mark();
   mixing_prepare(c, t);
+  mark();
   if (c->nranks == 1) {
     mixing_accumulate_all(c);
+    mark(); mark(); mark(); mark();
     mixing_apply_all(c);
+    mixing_clear_touched(c);
   } else {
     mixing_route(c);
+    mark();
     peer_barrier(c);
+    mark();
     mixing_serve(c);
+    mark();
     peer_barrier(c);
+    mark();
     mixing_apply_routed(c);
+  }
+  mark();
+  if (trace) {
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 6; i++) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      c->mix_trace_ms[i] += ms;
+    }
+    for (int i = 0; i < 7; i++) CK(cudaEventDestroy(ev[i]));
+    c->mix_trace_n++;
   }
 }
 
@@ -2089,6 +2169,15 @@ int mpb_destroy(mpb_ctx *c) {
   if (!c) return 0;
   use(c);
   CK(cudaStreamSynchronize(c->stream));
+  if (c->mix_trace_n > 0) {
+    const double n = (double)c->mix_trace_n;
+    const double *m = c->mix_trace_ms;
+    char line[512];
+    std::snprintf(line, sizeof(line), "[mptrac_b200] mixing trace, rank %d of %d, %lld calls, ms per call: prepare %.4f  route %.4f  barrier %.4f  "
+                  "serve %.4f  barrier %.4f  apply %.4f  (sum %.4f)\n", c->rank, c->nranks, c->mix_trace_n, m[0] / n, m[1] / n, m[2] / n, m[3] / n,
+                  m[4] / n, m[5] / n, (m[0] + m[1] + m[2] + m[3] + m[4] + m[5]) / n);
+    std::fputs(line, stderr);     // (one write: the ranks of a run share the terminal)
+  }
   void *ptrs[] = {c->soa[0], c->soa[1], c->dt, c->uvwp, c->keys[0], c->keys[1], c->perm[0], c->perm[1],
                   c->cub_tmp, c->nodes, c->surf, c->ax_lon, c->ax_lat, c->ax_p, c->ax_lonc, c->ax_latc, c->ax_pc,
                   c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_rec, c->mix_alloc, c->mix_route,

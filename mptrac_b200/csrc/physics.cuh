@@ -990,10 +990,31 @@ MPB_HD bool level_hint_holds(float h0, float h1, int hint, int n, double x) {
   const bool first = hint == 0, last = hint == n - 2;
   return h0 < h1 ? ((first || h0 <= x) && (last || h1 > x)) : ((first || h0 > x) && (last || h1 <= x));
 }
+// A failed guess at level k (bounds a = h[k], b = h[k+1] already loaded): neighbouring columns and consecutive
+// Runge-Kutta stages differ by one level far more often than by several, so the two adjacent intervals are tried against
+// the bisection's end condition (one more load each, independent of one another) before the ~log2(npl) dependent loads
+// of the bisection itself.  Same answer by the argument above.
+#ifndef MPB_LEVEL_NEAR
+#define MPB_LEVEL_NEAR 1
+#endif
+template <class L>
+static MPB_COLD int locate_after_miss(const L &lv, size_t col, int n, int t, double x, int k, float a, float b) {
+#if MPB_LEVEL_NEAR
+  const bool has_below = k > 0, has_above = k + 2 <= n - 1;
+  const float below = has_below ? lv.height(col + k - 1, t) : a;
+  const float above = has_above ? lv.height(col + k + 2, t) : b;
+  if (has_below && level_hint_holds(below, a, k - 1, n, x)) return k - 1;
+  if (has_above && level_hint_holds(b, above, k + 1, n, x)) return k + 1;
+#else
+  (void)k; (void)a; (void)b;
+#endif
+  return bisect_level(lv, col, n, t, x);
+}
 template <class L>
 static MPB_COLD int locate_level(const L &lv, size_t col, int n, int t, double x, int ig) {
-  if (level_guess_holds(lv.height(col + ig, t), lv.height(col + ig + 1, t), x)) return ig;
-  return bisect_level(lv, col, n, t, x);
+  const float a = lv.height(col + ig, t), b = lv.height(col + ig + 1, t);
+  if (level_guess_holds(a, b, x)) return ig;
+  return locate_after_miss(lv, col, n, t, x, ig, a, b);
 }
 
 // search coordinate at one level of the four columns: time first, then latitude, then longitude (2866-2889)
@@ -1070,6 +1091,7 @@ MPB_HD void locate_on_levels(const MetView &g, const L &lv, double ts, double he
     else if (hint && hint[t] >= 0 && level_hint_holds(q0[t], q1[t], hk[t], n, height)) k0[t] = hk[t];
     else if (t == 1 && level_hint_holds(lv.height(s.col[0] + k0[0], 1), lv.height(s.col[0] + k0[0] + 1, 1), k0[0], n, height))
       k0[t] = k0[0];   // the two time levels of a column nearly always agree
+    else if (hint && hint[t] >= 0) k0[t] = locate_after_miss(lv, s.col[0], n, t, height, hk[t], q0[t], q1[t]);
     else k0[t] = bisect_level(lv, s.col[0], n, t, height);
     if (hint) hint[t] = k0[t];
   }
@@ -1089,7 +1111,7 @@ MPB_HD void locate_on_levels(const MetView &g, const L &lv, double ts, double he
     int k = k0[t], lo = k, hi = k;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-      if (k == k0[t]) { if (!level_guess_holds(a[t][j], b[t][j], height)) k = bisect_level(lv, s.col[order[j]], n, t, height); }
+      if (k == k0[t]) { if (!level_guess_holds(a[t][j], b[t][j], height)) k = locate_after_miss(lv, s.col[order[j]], n, t, height, k, a[t][j], b[t][j]); }
       else k = locate_level(lv, s.col[order[j]], n, t, height, k);
       lo = k < lo ? k : lo; hi = k > hi ? k : hi;
     }
