@@ -64,14 +64,14 @@ WORKLOADS = {
                desc="1.25M parcels per GPU (10M / 8), 1x1 deg x 60 levels, RK4, cell sort and inter-parcel mixing (360x180x90 boxes, "
                     "all-reduced over the ranks) every step"),
     # configs[1] on model levels: omega on 60 model levels, the reference's trac_test "ml" setting.
-    # Three launches per step (timesteps + position | model-level advection | position); per parcel-step the advection
-    # reads time, lon, lat, p, dt and writes time, lon, lat, p (72 B), the two segments around it 64 B + 8 B and 64 B
+    # ONE launch per step (timesteps + position + model-level advection + position, folded by the plan); per parcel-step it
+    # reads time, lon, lat, p and writes them (64 B), stores dt (8 B) and reads / writes the 2-byte level hint: 76 B
     "c2ml": dict(np=1_000_000, grid=(360, 181, 60), levels=60, ctl=dict(advect=4, advect_vert_coord=2, diffusion=0, sort_dt=7200.0),
-                 state_bytes=208, met_fields=4, kernel="advect_levels_kernel (+ 2 step_kernel segments)", label="configs[1] on model levels",
-                 roofline_note="bytes and time of the whole step (3 launches; advect_levels_kernel is 91 % of it).  Not HBM-bound: the "
-                               "model-level lookup is four dependent load rounds per Runge-Kutta stage (column searches on both time "
-                               "levels, then the 8 records) at 16 resident warps/SM, ~890 instructions per stage; ncu r01h under "
-                               "profiles/, DESIGN.md 7",
+                 state_bytes=76, met_fields=4, kernel="advect_levels_kernel (timesteps and position checks folded in)",
+                 label="configs[1] on model levels",
+                 roofline_note="Not HBM-bound: the model-level lookup is four dependent load rounds per Runge-Kutta stage (column "
+                               "searches on both time levels, then the 8 records) at 16 resident warps/SM, ~800 instructions per stage; "
+                               "ncu r02p under profiles/, DESIGN.md 7",
                  desc="1M parcels, 1x1 deg x 60 model levels, RK4 advection with omega on model levels (ADVECT_VERT_COORD 2)"),
     # probes, not BASELINE configurations: the module mixes of c3 and c4 exchanged between their grids (to tell an effect of
     # the instruction mix from an effect of the grid size when a build flag helps one of the two)

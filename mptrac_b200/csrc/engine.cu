@@ -791,29 +791,42 @@ __global__ void __launch_bounds__(128) decay_kernel(const __grid_constant__ Deca
 }
 
 // module_advect on model levels (src/mptrac.c:3646-3657, 3680-3757) and module_advect_init (3762-3785): one parcel per
-// thread, dt from the cache (the fused kernel's timesteps segment ran before)
+// thread.  `modules`: the per-parcel modules around the advection that the plan folded into this launch -- timesteps and
+// the first position check before it, the second position check after it, when nothing else runs in between (a plain
+// model-level configuration is then ONE launch per step instead of three; c2ml 0.281 -> see DESIGN.md 7) -- otherwise dt
+// comes from the cache (a step segment ran before).
 struct LevelArgs {
   MetView met;
+  CtlView ctl;
   double *time, *lon, *lat, *p;
-  const double *dt;
+  double *dt;
   double *zq;           // the parcel's zeta / eta (null for ADVECT_VERT_COORD 2)
   unsigned short *hint; // per array slot: level + 1 found by the previous step's first lookup (0 = none); a search hint
                         // that is verified before use, so stale values (after a cell sort) only cost the bisection
   long long np;
   int vert_coord;
+  unsigned modules;
 };
 
 template <int ORDER>
 __global__ void __launch_bounds__(MPB_LEVEL_BLOCK, MPB_LEVEL_MINBLOCKS) advect_levels_kernel(const __grid_constant__ LevelArgs A) {
   const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (ip >= A.np) return;
-  const double dt = A.dt[ip];
-  if (dt == 0) return;
   Parcel a;
   a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
+  double dt;
+  if (A.modules & MOD_TIMESTEPS) {
+    dt = parcel_dt(A.met, A.ctl, a);
+    if (A.modules & MOD_STORE_DT) A.dt[ip] = dt;
+  } else {
+    dt = A.dt[ip];
+  }
+  if (dt == 0) return;
+  if (A.modules & MOD_POS_PRE) fix_position(A.met, a);
   double z = 0;
   int hint = (int)A.hint[ip] - 1;
   advect_on_levels<ORDER>(A.met, A.vert_coord, dt, a, A.zq ? &z : nullptr, A.zq ? nullptr : &hint);
+  if (A.modules & MOD_POS_POST) fix_position(A.met, a);
   A.time[ip] = a.time; A.lon[ip] = a.lon; A.lat[ip] = a.lat; A.p[ip] = a.p;
   if (A.zq) A.zq[ip] = z;
   else A.hint[ip] = (unsigned short)(hint + 1);
@@ -1496,10 +1509,12 @@ static void launch_step(mpb_ctx *c, double t, int advect, unsigned phys, unsigne
   launch_range(c, A, advect, phys, 0, c->np, c->stream);
 }
 
-static LevelArgs level_args(mpb_ctx *c) {
+static LevelArgs level_args(mpb_ctx *c, double t = 0, unsigned modules = 0) {
   const mpb_ctl_t &k = c->ctl;
   LevelArgs A;
   A.met = met_view(c);
+  A.ctl = ctl_view(c, t);
+  A.modules = modules;
   REQUIRE(A.met.npl >= 2, "ADVECT_VERT_COORD 1, 2 and 3 need the model-level fields of both met levels (mpb_met_view_t::pl ...)");
   A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p(); A.dt = c->dt;
   A.np = c->np; A.vert_coord = k.advect_vert_coord;
@@ -1517,9 +1532,9 @@ static LevelArgs level_args(mpb_ctx *c) {
   return A;
 }
 
-static void launch_advect_levels(mpb_ctx *c) {
+static void launch_advect_levels(mpb_ctx *c, double t, unsigned modules) {
   if (c->np == 0) return;
-  const LevelArgs A = level_args(c);
+  const LevelArgs A = level_args(c, t, modules);
   const unsigned grid = nblocks(c->np, MPB_LEVEL_BLOCK);
   switch (c->ctl.advect) {
     case 1: advect_levels_kernel<1><<<grid, MPB_LEVEL_BLOCK, 0, c->stream>>>(A); break;
@@ -2712,6 +2727,22 @@ static std::vector<Op> plan_modules(const mpb_ctl_t &k, double t, unsigned mask)
   if (iso_now) { flush(); op(Op::ISOSURF); }
   seg.modules |= modules & MOD_POS_POST;
   flush();
+  // The model-level advection takes its neighbours in: a segment right before it that only carries timesteps / the first
+  // position check, and one right after it that only carries the second position check.
+  static const bool fold = std::getenv("MPTRAC_B200_NO_LEVEL_FOLD") == nullptr;   // (measurement aid: three launches as before)
+  for (size_t i = 0; fold && i < ops.size(); i++) {
+    if (ops[i].kind != Op::ADVECT_LEVELS) continue;
+    if (i + 1 < ops.size() && ops[i + 1].kind == Op::STEP && !ops[i + 1].advect && !ops[i + 1].phys && ops[i + 1].modules == MOD_POS_POST) {
+      ops[i].modules |= MOD_POS_POST;
+      ops.erase(ops.begin() + (long)i + 1);
+    }
+    if (i > 0 && ops[i - 1].kind == Op::STEP && !ops[i - 1].advect && !ops[i - 1].phys &&
+        !(ops[i - 1].modules & ~(MOD_TIMESTEPS | MOD_STORE_DT | MOD_POS_PRE))) {
+      ops[i].modules |= ops[i - 1].modules;
+      ops.erase(ops.begin() + (long)i - 1);
+    }
+    break;
+  }
   if ((mask & MPB_MOD_METEO) && meteo_wanted(k) && k.met_dt_out > 0 && (k.met_dt_out < k.dt_mod || hits(t, k.met_dt_out)))   // :7921-7924
     op(Op::METEO);
   if (bound0) op(Op::BOUND_COND);     // :7926-7929
@@ -2729,7 +2760,7 @@ static void run_op(mpb_ctx *c, double t, const Op &o) {
       case Op::SORT: do_sort(c); break;
       case Op::ISOSURF_INIT: launch_isosurf(c, true); break;
       case Op::ADVECT_INIT: launch_advect_init(c); break;
-      case Op::ADVECT_LEVELS: launch_advect_levels(c); break;
+      case Op::ADVECT_LEVELS: launch_advect_levels(c, t, o.modules); break;
       case Op::DIFF_PBL: launch_diff_pbl(c); break;
       case Op::CONVECTION: launch_convection(c); break;
       case Op::ISOSURF: launch_isosurf(c, false); break;
@@ -2761,6 +2792,10 @@ int mpb_plan_modules(const mpb_ctl_t *ctl, double t, unsigned mask, char *buf, i
     if (o.kind == Op::STEP) {
       char tmp[64];
       std::snprintf(tmp, sizeof(tmp), "(advect=%d,phys=0x%x,mod=0x%x)", o.advect, o.phys, o.modules);
+      out += tmp;
+    } else if (o.kind == Op::ADVECT_LEVELS && o.modules) {
+      char tmp[32];
+      std::snprintf(tmp, sizeof(tmp), "(mod=0x%x)", o.modules);
       out += tmp;
     }
   }

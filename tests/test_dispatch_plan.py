@@ -54,13 +54,24 @@ def test_hybrid_segments_of_the_shim():
     assert plan_modules(c, 300.0, MOD_ALL & ~MOD_MIXING) == step(4, TURB | MESO | SEDI, TS | PRE | POST) + " meteo"
 
 
-def test_model_level_advection_runs_between_two_segments():
+def levels(modules):
+    return f"advect_levels(mod=0x{modules:x})" if modules else "advect_levels"
+
+
+def test_model_level_advection_takes_the_plain_segments_around_it_in():
+    """the advection on model levels is its own kernel; segments around it that only carry timesteps / position checks are
+    folded into its launch, segments with diffusion modules are not"""
     c = Ctl(advect=4, advect_vert_coord=2, diffusion=1, turb_dz_trop=0.5, **BASE)       # (TURB_MESOX / Z default to 0.16: on)
-    assert plan_modules(c, 300.0) == " ".join([step(0, 0, TS | STORE | PRE), "advect_levels", step(0, TURB | MESO, POST)])
-    assert plan_modules(c, 0.0) == " ".join([step(0, 0, TS | STORE | PRE), "advect_levels", step(0, TURB | MESO, POST)])
+    assert plan_modules(c, 300.0) == " ".join([levels(TS | STORE | PRE), step(0, TURB | MESO, POST)])
+    assert plan_modules(c, 0.0) == " ".join([levels(TS | STORE | PRE), step(0, TURB | MESO, POST)])
     c = Ctl(advect=2, advect_vert_coord=1, nq=1, qnt_zeta=0, **BASE)
-    assert plan_modules(c, 0.0) == " ".join(["advect_init", step(0, 0, TS | STORE | PRE), "advect_levels", step(0, 0, POST)])
-    assert plan_modules(c, 300.0) == " ".join([step(0, 0, TS | STORE | PRE), "advect_levels", step(0, 0, POST)])
+    assert plan_modules(c, 0.0) == " ".join(["advect_init", levels(TS | STORE | PRE | POST)])
+    assert plan_modules(c, 300.0) == levels(TS | STORE | PRE | POST)
+    # a cell sort keeps the dt-only launch in front of it (the reference computes dt before it permutes the parcels)
+    c = Ctl(advect=4, advect_vert_coord=2, diffusion=0, sort_dt=300.0, **BASE)
+    assert plan_modules(c, 300.0) == " ".join([step(0, 0, TS | STORE), "sort", levels(PRE | POST)])
+    # the shim's per-module masks (module timers) leave the advection alone
+    assert plan_modules(c, 300.0, MOD_ADVECT) == "advect_levels"
 
 
 def test_modules_with_their_own_kernel_split_the_fused_step_in_the_reference_order():
