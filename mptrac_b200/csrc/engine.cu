@@ -958,10 +958,10 @@ __global__ void mix_clear_kernel(const MixArgs A) {
 //           sender allocates with one warp-aggregated atomic per (warp, owner); the parcel remembers (owner, slot);
 //   -- barrier --
 //   serve   the owner folds all its inboxes into its slice of the box records (LOCAL atomics), then answers every entry with
-//           the finished record {count, sum_0 ..} into the sender's outbox, same slot (coalesced stores to peer memory);
+//           the finished box means into the sender's outbox, same slot (coalesced stores to peer memory);
 //   -- barrier --
 //   apply   every parcel reads its answer from its own outbox (local memory) and relaxes.
-// Per parcel 8 (1 + quantities) bytes cross NVLink in each direction, all of it as streaming stores.
+// Per parcel 8 (1 + quantities) bytes cross NVLink on the way out and 8 x quantities on the way back, all of it as streaming stores.
 struct RouteArgs {
   BoxArgs grid;                        // the mixing grid (the box of a parcel is computed here: no box array in memory)
   const double *time, *lon, *lat, *p;
@@ -1054,9 +1054,11 @@ __global__ void mix_answer_kernel(const __grid_constant__ ServeArgs A) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
     const double *in = A.inbox + ((size_t)s * A.cap + (size_t)e) * A.E;
     const double *rec = A.rec + (size_t)in[0] * A.E;
-    double *out = A.outbox_at[s] + (size_t)e * A.E;
-    if (A.E == 2) *reinterpret_cast<double2 *>(out) = *reinterpret_cast<const double2 *>(rec);
-    else for (int k = 0; k < A.E; k++) out[k] = rec[k];
+    // the answer is the box MEAN per quantity (src/mptrac.c:5314-5316; the count of a box that holds an entry is >= 1): one
+    // double per quantity crosses NVLink instead of {count, sums}
+    double *out = A.outbox_at[s] + (size_t)e * (A.E - 1);
+    const int n = (int)rec[0];
+    for (int k = 1; k < A.E; k++) out[k - 1] = rec[k] / n;
   }
 }
 
@@ -1068,17 +1070,15 @@ __global__ void mix_apply_routed_kernel(const double *outbox, long long cap, int
   if (ip >= A.np) return;
   const int2 r = route[ip];
   if (r.x < 0) return;
-  const double *rec = outbox + ((size_t)r.x * cap + (size_t)r.y) * E;
+  const double *mean_of = outbox + (size_t)r.x * cap * E + (size_t)r.y * nmix;    // (owner r.x's region, packed means)
   double mixparam = 1.0;
   if (mix_trop < 1 || mix_strat < 1) {
     const double pt = tropopause_pressure(clim, time[ip], latlon ? lat[ip] : utm_ref_lat);
     const double w = weight_tropo(pt, p[ip]);
     mixparam = w * mix_trop + (1.0 - w) * mix_strat;
   }
-  const int n = (int)rec[0];
   for (int k = 0; k < nmix; k++) {
-    double mean = rec[1 + k];
-    if (n > 0) mean /= n;
+    const double mean = mean_of[k];
     double *q = A.q0 + (long long)A.iq[k] * A.q_stride + ip;
     const double qq = *q;
     *q = qq + (mean - qq) * mixparam;
