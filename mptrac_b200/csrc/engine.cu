@@ -838,17 +838,13 @@ __global__ void __launch_bounds__(128) advect_init_kernel(const __grid_constant_
   A.p[ip] = pressure_of_zeta(A.met, A.time[ip], A.zq[ip], A.lon[ip], A.lat[ip]);
 }
 
-struct BoxArgs {
-  double t0, t1, lon0, lon1, lat0, lat1, z0, z1;
-  int nx, ny, nz;
-};
+typedef BoxGrid BoxArgs;   // (physics.cuh; the host fills the bounds and calls box_cells)
 
 __global__ void box_index_kernel(BoxArgs b, const double *time, const double *lon, const double *lat,
                                  const double *p, int *box, long long np) {
   const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (ip >= np) return;
-  box[ip] = box_index(time[ip], lon[ip], lat[ip], p[ip], b.t0, b.t1, b.lon0, b.lon1, b.lat0, b.lat1,
-                      b.z0, b.z1, b.nx, b.ny, b.nz);
+  box[ip] = box_index(b, time[ip], lon[ip], lat[ip], p[ip]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -992,7 +988,7 @@ __global__ void __launch_bounds__(kRouteBlock) mix_route_kernel(const __grid_con
   long long local = 0;
   if (ip < A.np) {
     const BoxArgs &g = A.grid;
-    const int b = box_index(A.time[ip], A.lon[ip], A.lat[ip], A.p[ip], g.t0, g.t1, g.lon0, g.lon1, g.lat0, g.lat1, g.z0, g.z1, g.nx, g.ny, g.nz);
+    const int b = box_index(g, A.time[ip], A.lon[ip], A.lat[ip], A.p[ip]);
     if (b >= 0) {
       const long long idx = (long long)(A.ens ? (int)A.ens[ip] : 0) * A.ngrid + b;
       owner = (int)(idx / A.slice);
@@ -1132,65 +1128,109 @@ __global__ void grid_pull_kernel(const __grid_constant__ GridPeers G, int nranks
 // lanes of a warp mostly fall into one or two boxes: each run of equal box indices is summed inside the warp (segmented
 // scan over shuffles) and only the last lane of a run touches memory.  Runs need not be maximal (an unsorted stream just
 // issues more atomics).
-// ONE pass over the parcels (no box array in memory) and few atomics: a warp owns 8 x 32
-// consecutive parcels, computes their boxes once, and carries the run that is still open at the end of a round of 32 into
-// the next round, so a run of ~200 parcels of one output box (parcels arrive cell-sorted; the reference's default output
-// grid has ONE level) costs one atomic per array instead of one per warp.  Measured on the configs[3] share (12.5 M
-// parcels, 360x180x1 boxes): box_index_kernel 126 us + grid_accumulate_kernel 286 us before.
+// ONE pass over the parcels (no box array in memory), few atomics and few shuffles: a warp owns 8 x 32 consecutive parcels
+// and computes their boxes once.  A round of 32 whose lanes all fall into ONE box (the common case: ~200 parcels per output
+// box in configs[3], parcels cell-sorted) only adds to lane-private partial sums of the open run -- no shuffle, no atomic;
+// the partials are reduced over the warp and added to memory when the box changes.  A round that holds several runs closes
+// the open run and sums each of its runs by a segmented scan.  Measured on the configs[3] share (12.5 M parcels, 360x180x1
+// boxes; ncu): box_index_kernel 126 us + grid_accumulate_kernel 286 us (round 1), one kernel with a scan in every round 340 us,
+// this form: see profiles/r02r_*.
 constexpr int kBinRounds = 8;
+#ifndef MPB_BIN_SCATTER
+#define MPB_BIN_SCATTER 1
+#endif
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+// (Measured and dropped: a shared-memory table of partial sums per block, to take the contention off the few boxes that the
+// blocks in flight share when the parcels are sorted -- the reference's sort key clamps longitudes below the met grid's first
+// column into that column (src/mptrac.c:5905, 3565-3573), so on a 0..360 grid the western half of the parcels is ordered by
+// latitude and level only and every such parcel is a run of its own.  335 against 355 us sorted, 470 against 302 us unsorted:
+// the fp64 shared-memory atomics are compare-and-swap loops.  profiles/r02r_binning.txt)
 __global__ void __launch_bounds__(256) grid_bin_kernel(BoxArgs g, const double *time, const double *lon, const double *lat, const double *p,
                                                        const double *q, long long q_stride, int nq, long long nbox, int *cnt, double *sum,
                                                        double *sq, long long np) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // Blocks take the chunks of the parcel array in a scattered order (a bijection of the block index: 2^31 - 1 is prime):
+  // cell-sorted parcels put the blocks that run at the same time onto the same few output boxes, and atomics to one address
+  // serialise (measured: the kernel was SLOWER on sorted parcels than on unsorted ones, 355 against 301 us).
+  const unsigned long long chunk = MPB_BIN_SCATTER ? ((unsigned long long)blockIdx.x * 2147483647ull) % gridDim.x : blockIdx.x;
+  const long long warp = ((long long)chunk * blockDim.x + threadIdx.x) >> 5;
   const long long first = warp * 32 * kBinRounds;
   if (first >= np) return;                                  // (warp-uniform)
+  // the runs of equal boxes of every round, found once: box, first lane of the lane's run, "last lane of its run"
   int bx[kBinRounds];
-#pragma unroll
+  unsigned char start[kBinRounds];
+  unsigned tails = 0, single = 0, crowded = 0;              // bit r: this lane ends a run in round r / round r is one run /
+#pragma unroll                                              //        round r has (nearly) as many runs as lanes
   for (int r = 0; r < kBinRounds; r++) {
     const long long ip = first + r * 32 + lane;
-    bx[r] = ip < np ? box_index(time[ip], lon[ip], lat[ip], p[ip], g.t0, g.t1, g.lon0, g.lon1, g.lat0, g.lat1, g.z0, g.z1, g.nx, g.ny, g.nz) : -1;
+    bx[r] = ip < np ? box_index(g, time[ip], lon[ip], lat[ip], p[ip]) : -1;
+    const int prev = __shfl_up_sync(full, bx[r], 1);
+    const unsigned heads = __ballot_sync(full, lane == 0 || prev != bx[r]);
+    start[r] = (unsigned char)(31 - __clz(heads & (full >> (31 - lane))));
+    if (lane == 31 || ((heads >> (lane + 1)) & 1u)) tails |= 1u << r;
+    if (heads == 1u) single |= 1u << r;
+    if (__popc(heads) >= 24) crowded |= 1u << r;
   }
-  // pass -1: counts; pass iq >= 0: sum and sum of squares of quantity iq
-  for (int iq = -1; iq < nq; iq++) {
-    int carry_box = -1;
-    double carry_a = 0, carry_b = 0;
+  {  // counts: run lengths (no arithmetic on values)
+    int open_box = -1, open_n = 0;                          // warp-uniform
+#pragma unroll
+    for (int r = 0; r < kBinRounds; r++) {
+      const int b = bx[r];
+      if ((single >> r) & 1u) {
+        if (b != open_box) {
+          if (open_box >= 0 && lane == 0) atomicAdd(cnt + open_box, open_n);
+          open_box = b; open_n = 0;
+        }
+        open_n += 32;
+      } else {
+        if (open_box >= 0 && lane == 0) atomicAdd(cnt + open_box, open_n);
+        open_box = -1; open_n = 0;
+        if (((tails >> r) & 1u) && b >= 0) atomicAdd(cnt + b, lane - start[r] + 1);
+      }
+    }
+    if (open_box >= 0 && lane == 0) atomicAdd(cnt + open_box, open_n);
+  }
+  for (int iq = 0; iq < nq; iq++) {      // sum and sum of squares of quantity iq
+    double *const sum_q = sum + iq * nbox, *const sq_q = sq + iq * nbox;
+    int open_box = -1;                   // warp-uniform
+    double part_a = 0, part_b = 0;       // this lane's share of the open run
+    auto close = [&]() {
+      if (open_box >= 0) {
+        const double a = warp_sum(part_a), bb = warp_sum(part_b);
+        if (lane == 0) { atomicAdd(sum_q + open_box, a); atomicAdd(sq_q + open_box, bb); }
+      }
+      open_box = -1; part_a = 0; part_b = 0;
+    };
 #pragma unroll
     for (int r = 0; r < kBinRounds; r++) {
       const int b = bx[r];
       const long long ip = first + r * 32 + lane;
-      const double x = iq < 0 ? 1.0 : (b >= 0 ? q[(long long)iq * q_stride + ip] : 0.0);
-      double a = x, bb = x * x;
-      const int prev = __shfl_up_sync(full, b, 1);
-      const unsigned heads = __ballot_sync(full, lane == 0 || prev != b);
-      const int start = 31 - __clz(heads & (full >> (31 - lane)));
-      const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+      const double x = b >= 0 ? q[(long long)iq * q_stride + ip] : 0.0;
+      if ((single >> r) & 1u) {
+        if (b != open_box) { close(); open_box = b; }
+        part_a += x; part_b += x * x;
+      } else {
+        close();
+        double a = x, bb = x * x;
+        if ((crowded >> r) & 1u) {       // (nearly) every lane its own box: no point in a scan
+          if (b >= 0) { atomicAdd(sum_q + b, a); atomicAdd(sq_q + b, bb); }
+        } else {
+          const int st = start[r];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const double ta = __shfl_up_sync(full, a, d), tb = __shfl_up_sync(full, bb, d);
-        if (lane - d >= start) { a += ta; bb += tb; }
-      }
-      const int head_box = __shfl_sync(full, b, 0);
-      if (carry_box >= 0) {
-        if (carry_box == head_box) { if (start == 0) { a += carry_a; bb += carry_b; } }      // the open run continues
-        else if (lane == 0) {                                                                  // it ended with the last round
-          if (iq < 0) atomicAdd(cnt + carry_box, (int)carry_a);
-          else { atomicAdd(sum + iq * nbox + carry_box, carry_a); atomicAdd(sq + iq * nbox + carry_box, carry_b); }
+          for (int d = 1; d < 32; d <<= 1) {
+            const double ta = __shfl_up_sync(full, a, d), tb = __shfl_up_sync(full, bb, d);
+            if (lane - d >= st) { a += ta; bb += tb; }
+          }
+          if (((tails >> r) & 1u) && b >= 0) { atomicAdd(sum_q + b, a); atomicAdd(sq_q + b, bb); }
         }
       }
-      if (tail && lane != 31 && b >= 0) {
-        if (iq < 0) atomicAdd(cnt + b, (int)a);
-        else { atomicAdd(sum + iq * nbox + b, a); atomicAdd(sq + iq * nbox + b, bb); }
-      }
-      carry_box = __shfl_sync(full, b, 31);
-      carry_a = __shfl_sync(full, a, 31);
-      carry_b = __shfl_sync(full, bb, 31);
     }
-    if (carry_box >= 0 && lane == 0) {
-      if (iq < 0) atomicAdd(cnt + carry_box, (int)carry_a);
-      else { atomicAdd(sum + iq * nbox + carry_box, carry_a); atomicAdd(sq + iq * nbox + carry_box, carry_b); }
-    }
+    close();
   }
 }
 
@@ -1260,6 +1300,8 @@ struct mpb_ctx {
   int nx = 0, ny = 0, nz = 0, coord_type = 0;
   size_t node_cap = 0, col_cap = 0;
   float *stage_h = nullptr;  // pinned, 4 dense fields (6 model-level fields)
+  char *grid_stage_h = nullptr;      // pinned landing area of mpb_grid_fetch (a copy into pageable memory is staged by the
+  size_t grid_stage_bytes = 0;       // driver in synchronous pieces: 0.15 ms for the 1.3 MB of the reference's default grid)
   float *stage_d = nullptr;
   size_t stage_cap = 0;
   // model levels (ADVECT_VERT_COORD 1 / 2 / 3): both time levels interleaved like the nodes
@@ -1636,6 +1678,7 @@ static void mixing_prepare(mpb_ctx *c, double t) {
   b.t0 = t - 0.5 * k.dt_mod; b.t1 = t + 0.5 * k.dt_mod;
   b.lon0 = k.mixing_lon0; b.lon1 = k.mixing_lon1; b.lat0 = k.mixing_lat0; b.lat1 = k.mixing_lat1;
   b.z0 = k.mixing_z0; b.z1 = k.mixing_z1; b.nx = k.mixing_nx; b.ny = k.mixing_ny; b.nz = k.mixing_nz;
+  box_cells(b);
   const long long total = mixing_total(c);
   REQUIRE(total > 0 && total < (1ll << 31), "mixing grid size out of range");
   if (k.mixing_trop < 1 || k.mixing_strat < 1)
@@ -2205,6 +2248,7 @@ int mpb_destroy(mpb_ctx *c) {
   for (float2 *p : c->x2) if (p) cudaFree(p);
   for (float2 *p : c->x3) if (p) cudaFree(p);
   if (c->stage_h) cudaFreeHost(c->stage_h);
+  if (c->grid_stage_h) cudaFreeHost(c->grid_stage_h);
   for (int i = 0; i < kLanes; i++) {
     if (c->lane[i]) cudaStreamDestroy(c->lane[i]);
     if (c->lane_done[i]) cudaEventDestroy(c->lane_done[i]);
@@ -3153,6 +3197,7 @@ int mpb_grid_accumulate(mpb_ctx *c, const mpb_grid_t *g) {
   BoxArgs b;
   b.t0 = g->t0; b.t1 = g->t1; b.lon0 = g->lon0; b.lon1 = g->lon1; b.lat0 = g->lat0; b.lat1 = g->lat1;
   b.z0 = g->z0; b.z1 = g->z1; b.nx = g->nx; b.ny = g->ny; b.nz = g->nz;
+  box_cells(b);
   grid_bin_kernel<<<nblocks(c->np, 256 * kBinRounds), 256, 0, c->stream>>>(
       b, c->time(), c->lon(), c->lat(), c->p(), c->nq ? c->q(0) : nullptr, c->np_max, c->nq, nbox, c->grid_cnt, c->grid_sum, c->grid_sq, c->np);
   CK(cudaGetLastError());
@@ -3193,11 +3238,23 @@ int mpb_grid_fetch(mpb_ctx *c, int *count, double *sum, double *sq) {
   API_BEGIN
   use(c);
   REQUIRE(c->grid_nbox > 0, "mpb_grid_accumulate has not been called");
-  const size_t nb = (size_t)c->grid_nbox;
-  if (count) CK(cudaMemcpyAsync(count, c->grid_cnt, sizeof(int) * nb, cudaMemcpyDeviceToHost, c->stream));
-  if (sum) CK(cudaMemcpyAsync(sum, c->grid_sum, sizeof(double) * nb * c->nq, cudaMemcpyDeviceToHost, c->stream));
-  if (sq) CK(cudaMemcpyAsync(sq, c->grid_sq, sizeof(double) * nb * c->nq, cudaMemcpyDeviceToHost, c->stream));
+  const size_t nb = (size_t)c->grid_nbox, nv = nb * (size_t)c->nq;
+  const size_t need = 2 * sizeof(double) * nv + sizeof(int) * nb;
+  if (need > c->grid_stage_bytes) {
+    if (c->grid_stage_h) CK(cudaFreeHost(c->grid_stage_h));
+    c->grid_stage_h = nullptr; c->grid_stage_bytes = 0;
+    CK(cudaMallocHost(&c->grid_stage_h, need));
+    c->grid_stage_bytes = need;
+  }
+  double *h_sum = reinterpret_cast<double *>(c->grid_stage_h), *h_sq = h_sum + nv;
+  int *h_cnt = reinterpret_cast<int *>(h_sq + nv);
+  if (count) CK(cudaMemcpyAsync(h_cnt, c->grid_cnt, sizeof(int) * nb, cudaMemcpyDeviceToHost, c->stream));
+  if (sum && nv) CK(cudaMemcpyAsync(h_sum, c->grid_sum, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+  if (sq && nv) CK(cudaMemcpyAsync(h_sq, c->grid_sq, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (count) std::memcpy(count, h_cnt, sizeof(int) * nb);
+  if (sum && nv) std::memcpy(sum, h_sum, sizeof(double) * nv);
+  if (sq && nv) std::memcpy(sq, h_sq, sizeof(double) * nv);
   API_END
 }
 

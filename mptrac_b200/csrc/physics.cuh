@@ -1845,18 +1845,63 @@ MPB_HD int cell_key(const MetView &g, double lon, double lat, double p) {
 // altitude of a pressure (src/mptrac.h:2243)
 
 // box index of module_mixing / write_grid (5201-5218, 13844-13860); -1 = outside
+// The regular lon x lat x log-pressure-altitude grid of module_mixing, module_chem_grid and write_grid
+// (src/mptrac.c:5195-5217, 3951-3972, 13826-13860) with its cell sizes and their reciprocals, set once per launch on the host
+// (box_cells): the three per-parcel quotients below are then quotients by grid constants (div_for_index: the reference's
+// truncated index for every input, without the IEEE division sequence).
+struct BoxGrid {
+  double t0, t1, lon0, lon1, lat0, lat1, z0, z1;
+  int nx, ny, nz;
+  double dlon, dlat, dz, rdlon, rdlat, rdz;
+};
+MPB_HD void box_cells(BoxGrid &g) {
+  g.dlon = (g.lon1 - g.lon0) / g.nx; g.dlat = (g.lat1 - g.lat0) / g.ny; g.dz = (g.z1 - g.z0) / g.nz;
+  g.rdlon = 1.0 / g.dlon; g.rdlat = 1.0 / g.dlat; g.rdz = 1.0 / g.dz;
+}
+// The vertical index needs Z(p) = H0 log(P0 / p) (src/mptrac.h:2243) only to decide a cell.  Production device build: a
+// single-precision altitude (|error| < 2e-4 km for |Z| < 1000 km: two roundings of the argument, 1 ulp of logf, one multiply)
+// decides whenever it is further than kZMargin
+// from the grid's bottom, top and cell faces -- all but ~2e-3 of the parcels on 1 km boxes -- and the double-precision
+// sequence (a division, a logarithm, a quotient: ~130 instructions) runs only for the rest.  Same index for every input.
+constexpr float kZMargin = 1e-3f;   // [km]
+MPB_HD int box_level(const BoxGrid &g, double p) {   // -1: outside [z0, z1) or beyond the last cell
+#if MPB_FAST_QUOT
+  {
+    const float zf = 7.0f * logf(1013.25f / (float)p);                   // (NaN for p <= 0 or non-finite p: falls through)
+    const float lo = (float)g.z0, hi = (float)g.z1, m = kZMargin + 1e-6f * (fabsf(lo) + fabsf(hi));
+    if (!(fabsf(zf) < 1e3f)) {
+      // (outside the range the error bound was derived for, or not a number: the exact sequence decides)
+    } else if (zf > lo + m && zf < hi - m) {
+      const float t = (zf - lo) * (float)g.rdz;
+      const float k = floorf(t), mt = m * (float)g.rdz + 4e-7f * t;       // (margin in cells, plus the rounding of t itself)
+      if (t - k > mt && k + 1.0f - t > mt) return k < (float)g.nz ? (int)k : -1;
+    } else if (zf < lo - m || zf > hi + m) {
+      return -1;
+    }
+  }
+#endif
+  const double z = altitude(p);
+  if (z < g.z0 || z >= g.z1) return -1;
+  const int iz = (int)div_for_index(z - g.z0, g.dz, g.rdz);
+  return iz < g.nz ? iz : -1;
+}
+MPB_HD int box_index(const BoxGrid &g, double time, double lon, double lat, double p) {
+  if (time < g.t0 || time > g.t1 || lon < g.lon0 || lon >= g.lon1 || lat < g.lat0 || lat >= g.lat1) return -1;
+  const int iz = box_level(g, p);
+  if (iz < 0) return -1;
+  const int ix = (int)div_for_index(lon - g.lon0, g.dlon, g.rdlon);
+  const int iy = (int)div_for_index(lat - g.lat0, g.dlat, g.rdlat);
+  if (ix >= g.nx || iy >= g.ny) return -1;
+  return (ix * g.ny + iy) * g.nz + iz;
+}
 MPB_HD int box_index(double time, double lon, double lat, double p, double t0, double t1,
                      double lon0, double lon1, double lat0, double lat1, double z0, double z1,
                      int nx, int ny, int nz) {
-  const double z = altitude(p);
-  if (time < t0 || time > t1 || lon < lon0 || lon >= lon1 || lat < lat0 || lat >= lat1 || z < z0 || z >= z1)
-    return -1;
-  const double dlon = (lon1 - lon0) / nx, dlat = (lat1 - lat0) / ny, dz = (z1 - z0) / nz;
-  const int ix = (int)((lon - lon0) / dlon);
-  const int iy = (int)((lat - lat0) / dlat);
-  const int iz = (int)((z - z0) / dz);
-  if (ix >= nx || iy >= ny || iz >= nz) return -1;
-  return (ix * ny + iy) * nz + iz;
+  BoxGrid g;
+  g.t0 = t0; g.t1 = t1; g.lon0 = lon0; g.lon1 = lon1; g.lat0 = lat0; g.lat1 = lat1; g.z0 = z0; g.z1 = z1;
+  g.nx = nx; g.ny = ny; g.nz = nz;
+  box_cells(g);
+  return box_index(g, time, lon, lat, p);
 }
 
 }  // namespace mpb
