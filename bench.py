@@ -181,6 +181,11 @@ def build_inputs(wl, rank, world):
     m0, m1 = synth.make_met_pair(nlon, nlat, nlev, t0=0.0, dt_met=DT_MET)
     if wl.get("levels"):
         m0, m1 = synth.add_model_levels(m0, npl=wl["levels"]), synth.add_model_levels(m1, npl=wl["levels"])
+    if os.environ.get("MPB_BENCH_LON_AXIS") == "-180":
+        # probe (not a BASELINE setting: the reference's `wind` tool writes 0..360): a met grid labelled -180..180, on which the
+        # reference's sort key orders ALL parcels by column instead of clamping the western half into column 0
+        m0.lon = m0.lon - 180.0
+        m1.lon = m1.lon - 180.0
     n = wl["np"]
     tm, p, lon, lat = synth.make_parcels(n, t0=0.0, seed=123 + rank)
     kw = dict(nq=0, t_start=0.0, t_stop=1e9, dt_mod=DT_MOD, dt_met=DT_MET)
