@@ -443,6 +443,61 @@ def test_mixing_and_grid_vs_oracle(oracle):
     assert relerr(s + 1e-300, s0 + 1e-300) < 1e-11 and relerr(sq + 1e-300, sq0 + 1e-300) < 1e-11
 
 
+def test_binning_at_the_cell_faces(oracle):
+    """the production library decides the level of a parcel from a single-precision altitude wherever that is decisive and
+    from the reference's double-precision sequence elsewhere (physics.cuh box_level); longitudes and latitudes go through
+    quotients by grid constants (div_for_index).  Parcels ON every face of the output grid and 1e-15 .. 1e-2 beside it must
+    fall into the boxes the reference puts them in -- counts exact, in sorted-looking and in shuffled order.  Vertically
+    the claim starts 1e-11 km from a face: closer than that the device's `log` (1 ulp) and glibc's may differ in the last bit
+    of Z(p), which is a property of the two math libraries, not of the kernel; those parcels must only be counted somewhere."""
+    from oracle.oracle import Parcels
+    from mptrac_b200 import Ctl
+    m0, m1, tm, p, lon, lat, clim = _case(n=1000, seed=9)
+    nx, ny, nz, z0, z1 = 36, 18, 40, -2.0, 38.0
+    mag = np.concatenate([[0.0], 10.0 ** np.arange(-15.0, -1.5, 0.5)])
+    eps = np.concatenate([-mag[::-1], mag])
+    faces_z = z0 + (z1 - z0) / nz * np.arange(nz + 1)
+    far = eps[np.abs(eps) >= 1e-11]
+    near = eps[np.abs(eps) < 1e-11]
+    pz_far = (1013.25 * np.exp(-(faces_z[:, None] + far[None, :]) / 7.0)).ravel()
+    pz_near = (1013.25 * np.exp(-(faces_z[1:-1, None] + near[None, :]) / 7.0)).ravel()      # (inner faces: inside either way)
+    xf = ((-180.0 + 360.0 / nx * np.arange(nx + 1))[:, None] + 10.0 * eps[None, :]).ravel()
+    yf = ((-90.0 + 180.0 / ny * np.arange(ny + 1))[:, None] + 10.0 * eps[None, :]).ravel()
+    rng = np.random.default_rng(5)
+    m = 40000
+    ctl = Ctl(nq=1, advect=0, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0)
+
+    def binned(P, X, Y, order):
+        n = P.size
+        q = rng.uniform(0.0, 1.0, (1, n))
+        t_, p_, x_, y_, q_ = np.zeros(n), P[order], X[order], Y[order], np.ascontiguousarray(q[:, order])
+        with _engine(n, 1) as eng:
+            _setup(eng, ctl, clim, m0, m1, t_, p_, x_, y_, q_)
+            eng.grid_accumulate(nx, ny, nz, -180, 180, -90, 90, z0, z1, -150.0, 150.0)
+            got = eng.grid_fetch()
+        want = oracle.grid_bin(Parcels(t_, p_, x_, y_, q_), nx, ny, nz, -180, 180, -90, 90, z0, z1, -150.0, 150.0)
+        return got, want
+
+    sets = {
+        "levels": (rng.choice(pz_far, m), rng.uniform(-180, 180, m), rng.uniform(-90, 90, m)),
+        "columns": (rng.uniform(1.0, 1100.0, m), rng.choice(xf, m), rng.choice(yf, m)),
+        "both": (rng.choice(pz_far, m), rng.choice(xf, m), rng.choice(yf, m)),
+    }
+    for name, (P, X, Y) in sets.items():
+        for order in (np.lexsort((P, Y, X)), rng.permutation(m)):
+            (cnt, s, sq), (c0, s0, sq0) = binned(P, X, Y, order)
+            bad = np.flatnonzero(cnt != c0)
+            assert bad.size == 0, f"{name}: {bad.size} boxes differ, first {bad[:5]}: {cnt[bad[:5]]} against {c0[bad[:5]]}"
+            assert 0.3 * m < cnt.sum() <= m
+            assert relerr(s + 1e-300, s0 + 1e-300) < 1e-11 and relerr(sq + 1e-300, sq0 + 1e-300) < 1e-11
+    # on the faces themselves (vertically): every parcel is counted once, in one of the two boxes that share the face
+    P, X, Y = rng.choice(pz_near, m), rng.uniform(-179, 179, m), rng.uniform(-89, 89, m)
+    (cnt, s, sq), (c0, s0, sq0) = binned(P, X, Y, rng.permutation(m))
+    assert cnt.sum() == m == c0.sum()
+    col = lambda c: c.reshape(nx, ny, nz).sum(axis=2)
+    assert np.array_equal(col(cnt), col(c0))
+
+
 def test_inactive_and_ragged_parcels(oracle):
     """parcels that start later / are already past t_stop keep dt = 0 and must not be touched; np < np_max"""
     from mptrac_b200 import Ctl
