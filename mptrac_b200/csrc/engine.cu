@@ -542,12 +542,20 @@ __global__ void swap_levels_kernel(float4 *nodes, size_t n, float2 *surf, size_t
   if (i < ncol) { const float2 a = surf[2 * i], b = surf[2 * i + 1]; surf[2 * i] = b; surf[2 * i + 1] = a; }
 }
 
-__global__ void sort_keys_kernel(MetView met, const double *lon, const double *lat, const double *p,
-                                 int *keys, int *idx, long long np) {
+// (dt_out: module_timesteps folded into this pass -- the reference computes dt BEFORE it permutes the parcels and leaves
+// cache->dt in slot order, src/mptrac.c:7877-7881, so on a sort step dt cannot come from the fused launch after the sort)
+__global__ void sort_keys_kernel(MetView met, CtlView ctl, const double *time, const double *lon, const double *lat, const double *p,
+                                 int *keys, int *idx, double *dt_out, long long np) {
   const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (ip >= np) return;
-  keys[ip] = cell_key(met, lon[ip], lat[ip], p[ip]);
+  Parcel a;
+  a.lon = lon[ip]; a.lat = lat[ip]; a.p = p[ip];
+  keys[ip] = cell_key(met, a.lon, a.lat, a.p);
   idx[ip] = (int)ip;
+  if (dt_out) {
+    a.time = time[ip];
+    dt_out[ip] = parcel_dt(met, ctl, a);
+  }
 }
 
 // dst[a][ip] = src[a][perm[ip]] for narr arrays spaced `stride` doubles apart
@@ -1600,7 +1608,7 @@ static void ensure_boxes(mpb_ctx *c) {
   if (!c->box) CK(cudaMalloc(&c->box, sizeof(int) * (size_t)std::max<long long>(c->np_max, 1)));
 }
 
-static void do_sort(mpb_ctx *c) {
+static void do_sort(mpb_ctx *c, double t = 0, unsigned modules = 0) {
   if (c->np == 0) return;
   const long long np = c->np;
   MetView g = met_view(c);
@@ -1611,7 +1619,8 @@ static void do_sort(mpb_ctx *c) {
     }
     if (!c->soa[1]) CK(cudaMalloc(&c->soa[1], sizeof(double) * (size_t)c->np_max * (size_t)(4 + c->nq)));
   }
-  sort_keys_kernel<<<nblocks(np, 256), 256, 0, c->stream>>>(g, c->lon(), c->lat(), c->p(), c->keys[0], c->perm[0], np);
+  sort_keys_kernel<<<nblocks(np, 256), 256, 0, c->stream>>>(g, ctl_view(c, t), c->time(), c->lon(), c->lat(), c->p(), c->keys[0], c->perm[0],
+                                                            (modules & MOD_TIMESTEPS) ? c->dt : nullptr, np);
   CK(cudaGetLastError());
   c->launches++;
   const long long ncell = (long long)g.nx * g.ny * g.nz;
@@ -2742,10 +2751,10 @@ static std::vector<Op> plan_modules(const mpb_ctl_t &k, double t, unsigned mask)
   if (mask & MPB_MOD_TIMESTEPS) {
     if (sort_now) {
       // the reference computes dt BEFORE it permutes the parcels and leaves cache->dt in slot order
-      // (src/mptrac.c:7877-7881): a dt-only launch (active parcels are rewritten unchanged), then the sort,
-      // then the fused launch reads dt from memory
-      ops.push_back(Op{Op::STEP, 0, 0u, MOD_TIMESTEPS | MOD_STORE_DT});
-      op(Op::SORT);
+      // (src/mptrac.c:7877-7881): dt is computed and stored first, then the parcels are sorted, then the fused launch
+      // reads dt from memory
+      // -- folded into the sort's key pass
+      ops.push_back(Op{Op::SORT, 0, 0u, MOD_TIMESTEPS | MOD_STORE_DT});
     } else {
       modules |= MOD_TIMESTEPS;
       if (!whole) modules |= MOD_STORE_DT;   // later segments read cache->dt from memory
@@ -2801,7 +2810,7 @@ static std::vector<Op> plan_modules(const mpb_ctl_t &k, double t, unsigned mask)
 static void run_op(mpb_ctx *c, double t, const Op &o) {
     switch (o.kind) {
       case Op::STEP: launch_step(c, t, o.advect, o.phys, o.modules); break;
-      case Op::SORT: do_sort(c); break;
+      case Op::SORT: do_sort(c, t, o.modules); break;
       case Op::ISOSURF_INIT: launch_isosurf(c, true); break;
       case Op::ADVECT_INIT: launch_advect_init(c); break;
       case Op::ADVECT_LEVELS: launch_advect_levels(c, t, o.modules); break;
@@ -2837,7 +2846,7 @@ int mpb_plan_modules(const mpb_ctl_t *ctl, double t, unsigned mask, char *buf, i
       char tmp[64];
       std::snprintf(tmp, sizeof(tmp), "(advect=%d,phys=0x%x,mod=0x%x)", o.advect, o.phys, o.modules);
       out += tmp;
-    } else if (o.kind == Op::ADVECT_LEVELS && o.modules) {
+    } else if ((o.kind == Op::ADVECT_LEVELS || o.kind == Op::SORT) && o.modules) {
       char tmp[32];
       std::snprintf(tmp, sizeof(tmp), "(mod=0x%x)", o.modules);
       out += tmp;

@@ -28,7 +28,8 @@ def test_plain_step_is_one_fused_launch():
 def test_sort_step_computes_dt_before_the_permutation():
     c = Ctl(advect=4, sort_dt=7200.0, **BASE)
     assert plan_modules(c, 300.0) == step(4, 0, TS | PRE | POST)
-    assert plan_modules(c, 7200.0) == " ".join([step(0, 0, TS | STORE), "sort", step(4, 0, PRE | POST)])
+    # on a sort step dt is computed in the sort's key pass (the reference computes it before it permutes the parcels)
+    assert plan_modules(c, 7200.0) == " ".join([f"sort(mod=0x{TS | STORE:x})", step(4, 0, PRE | POST)])
 
 
 def test_meteo_and_mixing_follow_the_step():
@@ -67,9 +68,9 @@ def test_model_level_advection_takes_the_plain_segments_around_it_in():
     c = Ctl(advect=2, advect_vert_coord=1, nq=1, qnt_zeta=0, **BASE)
     assert plan_modules(c, 0.0) == " ".join(["advect_init", levels(TS | STORE | PRE | POST)])
     assert plan_modules(c, 300.0) == levels(TS | STORE | PRE | POST)
-    # a cell sort keeps the dt-only launch in front of it (the reference computes dt before it permutes the parcels)
+    # a cell sort computes dt in its key pass (the reference computes dt before it permutes the parcels)
     c = Ctl(advect=4, advect_vert_coord=2, diffusion=0, sort_dt=300.0, **BASE)
-    assert plan_modules(c, 300.0) == " ".join([step(0, 0, TS | STORE), "sort", levels(PRE | POST)])
+    assert plan_modules(c, 300.0) == " ".join([f"sort(mod=0x{TS | STORE:x})", levels(PRE | POST)])
     # the shim's per-module masks (module timers) leave the advection alone
     assert plan_modules(c, 300.0, MOD_ADVECT) == "advect_levels"
 
