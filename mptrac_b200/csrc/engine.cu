@@ -82,6 +82,8 @@ struct StepArgs {
   int uniform_time;
   long long np;
   long long ig0;  // global index of local parcel 0
+  const int *slot; // array slot (the reference's index) of the parcel at each position, or null = the position itself:
+                   // the random numbers of a parcel belong to its slot (src/mptrac.c:5797-5826), see do_sort
   unsigned modules;
 };
 
@@ -149,7 +151,7 @@ __device__ __forceinline__ bool parcel_begin(const StepArgs &A, long long ip, Pa
 // parcel sits in, shared by every lookup of the step.
 template <int ADVECT, unsigned PHYS>
 __device__ __forceinline__ void parcel_finish(const StepArgs &A, long long ip, Parcel &a, double dt, CubeT<!(PHYS & PHYS_MESO)> &cube) {
-  const unsigned long long ig = (unsigned long long)(A.ig0 + ip);
+  const unsigned long long ig = (unsigned long long)(A.ig0 + (A.slot ? A.slot[ip] : ip));
 #if MPB_CUBE_F64
   if (ADVECT > 0) {
     WindCube wc;
@@ -567,6 +569,73 @@ __global__ void gather_kernel(const double *__restrict__ src, double *__restrict
   for (int a = 0; a < narr; a++) dst[a * stride + ip] = src[a * stride + j];
 }
 
+// ---- the engine's own parcel order (do_sort) ----
+// the cell a parcel's lookups fall into: longitude wrapped and clamped as the interpolation does it (module_sort's own key
+// takes the raw longitude, src/mptrac.c:5905)
+__device__ __forceinline__ int lookup_cell_key(const MetView &g, double lon, double lat, double p) {
+  double lon2, lat2;
+  clamp_horizontal(g, lon, lat, lon2, lat2);
+  return (lon_interval(g, lon2) * g.ny + lat_interval(g, lat2)) * g.nz + p_interval(g, p);
+}
+__global__ void invert_kernel(const int *__restrict__ slot, int *__restrict__ inv, long long np) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < np) inv[slot[i]] = (int)i;
+}
+// both keys of the parcel at every position, one streaming pass: module_sort's (raw longitude) and the engine's (the cell the
+// lookups fall into); dt when module_timesteps rides along (the reference computes it before it permutes, src/mptrac.c:7877-7881)
+__global__ void two_keys_kernel(MetView met, CtlView ctl, const double *time, const double *lon, const double *lat, const double *p,
+                                int *key_ref, int *key_own, double *dt_out, long long np) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  Parcel a;
+  a.lon = lon[i]; a.lat = lat[i]; a.p = p[i];
+  key_ref[i] = cell_key(met, a.lon, a.lat, a.p);
+  key_own[i] = lookup_cell_key(met, a.lon, a.lat, a.p);
+  if (dt_out) {
+    a.time = time[i];
+    dt_out[i] = parcel_dt(met, ctl, a);
+  }
+}
+// keys[s] = key_at[at[s]] (at = null: the identity), vals[s] = at[s] or s
+__global__ void pick_keys_kernel(const int *key_at, const int *at, int *keys, int *vals, bool vals_are_positions, long long np) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= np) return;
+  const int a = at ? at[s] : (int)s;
+  keys[s] = key_at[a];
+  vals[s] = vals_are_positions ? a : (int)s;
+}
+// position i of the new order holds the parcel of (new) slot order[i], which sits at position from[order[i]] now
+__global__ void compose_kernel(const int *order, const int *from, int *slot_new, int *src, long long np) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const int s = order[i];
+  slot_new[i] = s;
+  src[i] = from[s];
+}
+// What belongs to the SLOT in the reference (cache_t::uvwp, ::dt, ::iso_var: module_sort leaves them where they are,
+// src/mptrac.c:5944-5949) travels with the parcel here and is handed over at a sort: the parcel that takes slot s gets what
+// the previous holder of slot s had.  held_at[s] = position of that previous holder (null: position s).  The level hint
+// belongs to the parcel (src[i] = its old position).
+struct StateArgs {
+  const int *slot_new, *held_at, *src;
+  const float *uvwp_old; float *uvwp_new;
+  const double *dt_old, *dt_of_slot; double *dt_new;
+  const double *iso_old; double *iso_new;
+  const unsigned short *hint_old; unsigned short *hint_new;
+  long long np;
+};
+__global__ void hand_over_kernel(const StateArgs A) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.np) return;
+  const int s = A.slot_new ? A.slot_new[i] : (int)i;
+  const int a = A.held_at ? A.held_at[s] : s;
+  A.uvwp_new[3 * i] = A.uvwp_old[3 * (long long)a]; A.uvwp_new[3 * i + 1] = A.uvwp_old[3 * (long long)a + 1];
+  A.uvwp_new[3 * i + 2] = A.uvwp_old[3 * (long long)a + 2];
+  A.dt_new[i] = A.dt_of_slot ? A.dt_of_slot[s] : A.dt_old[a];
+  if (A.iso_old) A.iso_new[i] = A.iso_old[a];
+  if (A.hint_old) A.hint_new[i] = A.hint_old[A.src ? A.src[i] : a];
+}
+
 // module_meteo for the quantities the resident fields give (src/mptrac.c:5062-5165): every parcel, dt or not
 struct MeteoArgs {
   MetView met;
@@ -666,6 +735,7 @@ struct PblArgs {
   float *uvwp;
   unsigned long long ctr;
   long long ig0, np;
+  const int *slot;      // as StepArgs::slot
 };
 __global__ void __launch_bounds__(128) diff_pbl_kernel(const __grid_constant__ PblArgs A) {
   const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -676,7 +746,7 @@ __global__ void __launch_bounds__(128) diff_pbl_kernel(const __grid_constant__ P
   a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
   float *s = A.uvwp + 3 * ip;
   float up = s[0], vp = s[1], wp = s[2];
-  diffuse_pbl(A.met, A.f, A.ctr, dt, (unsigned long long)(A.ig0 + ip), a, up, vp, wp);
+  diffuse_pbl(A.met, A.f, A.ctr, dt, (unsigned long long)(A.ig0 + (A.slot ? A.slot[ip] : ip)), a, up, vp, wp);
   s[0] = up; s[1] = vp; s[2] = wp;
   A.lon[ip] = a.lon; A.lat[ip] = a.lat; A.p[ip] = a.p;
 }
@@ -690,13 +760,14 @@ struct ConvArgs {
   double *p;
   unsigned long long ctr;
   long long ig0, np;
+  const int *slot;      // as StepArgs::slot
 };
 __global__ void __launch_bounds__(128) convection_kernel(const __grid_constant__ ConvArgs A) {
   const long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (ip >= A.np || A.dt[ip] == 0) return;
   Parcel a;
   a.time = A.time[ip]; a.lon = A.lon[ip]; a.lat = A.lat[ip]; a.p = A.p[ip];
-  convect(A.met, A.conv, squares_uniform(A.ctr + (unsigned long long)(A.ig0 + ip)), a);
+  convect(A.met, A.conv, squares_uniform(A.ctr + (unsigned long long)(A.ig0 + (A.slot ? A.slot[ip] : ip))), a);
   A.p[ip] = a.p;
 }
 
@@ -1295,6 +1366,14 @@ struct mpb_ctx {
   int *keys[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
   void *cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
+  // The order of the parcels in memory is the engine's own between two cell sorts (do_sort): slot[i] = the reference's array
+  // slot of the parcel at position i.  Everything that leaves or enters by slot (mpb_get_atm, mpb_set_uvwp ...) first
+  // restores the reference's order (unscramble).
+  bool scrambled = false, leaving_soon = false;
+  int *slot = nullptr, *slot2 = nullptr, *inv = nullptr, *perm2 = nullptr, *src = nullptr;
+  float *uvwp2 = nullptr;
+  double *dt2 = nullptr, *iso_var2 = nullptr;
+  unsigned short *lev_hint2 = nullptr;
 
   // met
   MetLevel lev[2];
@@ -1470,6 +1549,7 @@ static StepArgs step_args(mpb_ctx *c, double t, int advect, unsigned phys, unsig
     A.rp = c->q(c->ctl.qnt_rp); A.rhop = c->q(c->ctl.qnt_rhop);
   }
   A.np = c->np; A.ig0 = c->ig0; A.modules = modules;
+  A.slot = c->scrambled ? c->slot : nullptr;
   if (advect > 0) REQUIRE(c->ctl.advect_vert_coord == 0, "the fused step advects on pressure levels only");
   return A;
 }
@@ -1521,6 +1601,7 @@ static void launch_range(mpb_ctx *c, StepArgs A, int advect, unsigned phys, long
   if (A.host_lon) { if (A.host_time) A.host_time += off; A.host_lon += off; A.host_lat += off; A.host_p += off; }
   if (A.rp) { A.rp += off; A.rhop += off; }
   A.np = cnt; A.ig0 += off;
+  if (A.slot) A.slot += off;
   if (c->tile && c->tmap_ok && advect > 0 && !A.in_time && !A.host_lon) {
     tile_fn tf = pick_tile(advect, phys);
     const size_t bytes = (size_t)c->tshape.nx * c->tshape.ny * c->tshape.nz * sizeof(Node);
@@ -1608,37 +1689,140 @@ static void ensure_boxes(mpb_ctx *c) {
   if (!c->box) CK(cudaMalloc(&c->box, sizeof(int) * (size_t)std::max<long long>(c->np_max, 1)));
 }
 
-static void do_sort(mpb_ctx *c, double t = 0, unsigned modules = 0) {
-  if (c->np == 0) return;
-  const long long np = c->np;
-  MetView g = met_view(c);
-  if (!c->keys[0]) {
-    for (int i = 0; i < 2; i++) {
-      CK(cudaMalloc(&c->keys[i], sizeof(int) * (size_t)c->np_max));
-      CK(cudaMalloc(&c->perm[i], sizeof(int) * (size_t)c->np_max));
-    }
-    if (!c->soa[1]) CK(cudaMalloc(&c->soa[1], sizeof(double) * (size_t)c->np_max * (size_t)(4 + c->nq)));
-  }
-  sort_keys_kernel<<<nblocks(np, 256), 256, 0, c->stream>>>(g, ctl_view(c, t), c->time(), c->lon(), c->lat(), c->p(), c->keys[0], c->perm[0],
-                                                            (modules & MOD_TIMESTEPS) ? c->dt : nullptr, np);
-  CK(cudaGetLastError());
-  c->launches++;
-  const long long ncell = (long long)g.nx * g.ny * g.nz;
-  int bits = 1;
-  while ((1ll << bits) < ncell && bits < 31) bits++;
+static void radix_sort_pairs(mpb_ctx *c, const int *keys_in, int *keys_out, const int *vals_in, int *vals_out, long long np, int bits) {
   size_t need = 0;
-  CK(cub::DeviceRadixSort::SortPairs(nullptr, need, c->keys[0], c->keys[1], c->perm[0], c->perm[1], (int)np, 0, bits, c->stream));
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, need, keys_in, keys_out, vals_in, vals_out, (int)np, 0, bits, c->stream));
   if (need > c->cub_tmp_bytes) {
     if (c->cub_tmp) CK(cudaFree(c->cub_tmp));
     CK(cudaMalloc(&c->cub_tmp, need));
     c->cub_tmp_bytes = need;
   }
-  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, need, c->keys[0], c->keys[1], c->perm[0], c->perm[1], (int)np, 0, bits, c->stream));
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, need, keys_in, keys_out, vals_in, vals_out, (int)np, 0, bits, c->stream));
   c->launches += 3;  // cub: histogram + onesweep passes (>= 3 launches)
-  gather_kernel<<<nblocks(np, 256), 256, 0, c->stream>>>(c->soa[c->cur], c->soa[c->cur ^ 1], c->perm[1], np, c->np_max, 4 + c->nq);
+}
+
+static void ensure_sort_buffers(mpb_ctx *c) {
+  if (!c->keys[0]) {
+    for (int i = 0; i < 2; i++) {
+      CK(cudaMalloc(&c->keys[i], sizeof(int) * (size_t)c->np_max));
+      CK(cudaMalloc(&c->perm[i], sizeof(int) * (size_t)c->np_max));
+    }
+  }
+  if (!c->soa[1]) CK(cudaMalloc(&c->soa[1], sizeof(double) * (size_t)c->np_max * (size_t)(4 + c->nq)));
+}
+static void ensure_order_buffers(mpb_ctx *c) {
+  ensure_sort_buffers(c);
+  if (c->slot) return;
+  const size_t n = (size_t)std::max<long long>(c->np_max, 1);
+  for (int **b : {&c->slot, &c->slot2, &c->inv, &c->perm2, &c->src}) CK(cudaMalloc(b, sizeof(int) * n));
+  CK(cudaMalloc(&c->uvwp2, sizeof(float) * 3 * n));
+  CK(cudaMalloc(&c->dt2, sizeof(double) * n));
+}
+
+// hand the slot-bound state over and swap the buffers
+static void hand_over(mpb_ctx *c, const int *slot_new, const int *held_at, const int *src, const double *dt_of_slot) {
+  const size_t n = (size_t)std::max<long long>(c->np_max, 1);
+  if (c->iso_var && !c->iso_var2) CK(cudaMalloc(&c->iso_var2, sizeof(double) * n));
+  if (c->lev_hint && !c->lev_hint2) CK(cudaMalloc(&c->lev_hint2, sizeof(unsigned short) * n));
+  StateArgs A;
+  A.slot_new = slot_new; A.held_at = held_at; A.src = src;
+  A.uvwp_old = c->uvwp; A.uvwp_new = c->uvwp2;
+  // (dt_of_slot may live in dt2: then the new dt goes into the old array, whose values are dead once every dt is recomputed)
+  A.dt_old = c->dt; A.dt_of_slot = dt_of_slot; A.dt_new = dt_of_slot ? c->dt : c->dt2;
+  A.iso_old = c->iso_var; A.iso_new = c->iso_var2;
+  A.hint_old = c->lev_hint; A.hint_new = c->lev_hint2;
+  A.np = c->np;
+  hand_over_kernel<<<nblocks(c->np, 256), 256, 0, c->stream>>>(A);
   CK(cudaGetLastError());
   c->launches++;
+  std::swap(c->uvwp, c->uvwp2);
+  if (!dt_of_slot) std::swap(c->dt, c->dt2);
+  if (c->iso_var) std::swap(c->iso_var, c->iso_var2);
+  if (c->lev_hint) std::swap(c->lev_hint, c->lev_hint2);
+}
+
+// back to the reference's order: position = slot
+static void unscramble(mpb_ctx *c) {
+  if (!c->scrambled) return;
+  c->scrambled = false;
+  if (c->np == 0) return;
+  const long long np = c->np;
+  invert_kernel<<<nblocks(np, 256), 256, 0, c->stream>>>(c->slot, c->inv, np);
+  gather_kernel<<<nblocks(np, 256), 256, 0, c->stream>>>(c->soa[c->cur], c->soa[c->cur ^ 1], c->inv, np, c->np_max, 4 + c->nq);
+  CK(cudaGetLastError());
+  c->launches += 2;
   c->cur ^= 1;
+  hand_over(c, nullptr, c->inv, c->inv, nullptr);      // slot s takes what sits at position inv[s], hint included
+}
+
+// Does this configuration sort rarely enough for a second sort per event to pay?  (MPTRAC_B200_PRIVATE_ORDER=0: never)
+static bool own_order_wanted(const mpb_ctx *c) {
+  if (c->leaving_soon) return false;
+  const char *e = std::getenv("MPTRAC_B200_PRIVATE_ORDER");
+  if (e && std::atoi(e) == 0) return false;
+  if (e && std::atoi(e) == 2) return true;             // (tests: whatever the cadence and the size)
+  // Measured (profiles/r02v_*): a sort event costs ~1 ms more per 10 M parcels; the step gains 6-15 % where the met grid does not
+  // sit in L2 or the parcels are dense, 3 % on configs[1] (1 M parcels on a grid that fits L2), where the event costs more
+  // than 24 steps gain.
+  return c->ctl.sort_dt >= 6 * std::fabs(c->ctl.dt_mod) && c->np >= 4000000;
+}
+
+// module_sort (src/mptrac.c:5887-5995).  The reference orders the parcels by the met cell of their RAW longitude: on a grid
+// that runs 0..360 every parcel west of Greenwich (module_position keeps longitudes in [-180, 180)) falls into column 0 of the
+// key and is ordered by latitude and level only -- half a sort (measured: DESIGN.md 9).  The engine therefore keeps TWO
+// orders.  The reference's sort is carried out on the SLOTS: which parcel sits in which slot of atm_t afterwards, stable like
+// the oracle's, with dt computed per slot before the permutation (src/mptrac.c:7877-7881).  The parcels themselves are
+// then laid out by the cell their lookups fall into (wrapped longitude); slot[i] remembers the slot of the parcel at position
+// i for its random numbers, and what the reference leaves in the slot (uvwp, dt, iso_var) is handed to the slot's new parcel.
+// Everything that addresses parcels by slot from outside restores the reference's order first (unscramble).
+static void do_sort(mpb_ctx *c, double t = 0, unsigned modules = 0, bool own_order = false) {
+  if (c->np == 0) return;
+  const long long np = c->np;
+  MetView g = met_view(c);
+  const long long ncell = (long long)g.nx * g.ny * g.nz;
+  int bits = 1;
+  while ((1ll << bits) < ncell && bits < 31) bits++;
+  const unsigned grid = nblocks(np, 256);
+  if (!own_order) {
+    unscramble(c);
+    ensure_sort_buffers(c);
+    sort_keys_kernel<<<grid, 256, 0, c->stream>>>(g, ctl_view(c, t), c->time(), c->lon(), c->lat(), c->p(), c->keys[0], c->perm[0],
+                                                  (modules & MOD_TIMESTEPS) ? c->dt : nullptr, np);
+    CK(cudaGetLastError());
+    c->launches++;
+    radix_sort_pairs(c, c->keys[0], c->keys[1], c->perm[0], c->perm[1], np, bits);
+    gather_kernel<<<grid, 256, 0, c->stream>>>(c->soa[c->cur], c->soa[c->cur ^ 1], c->perm[1], np, c->np_max, 4 + c->nq);
+    CK(cudaGetLastError());
+    c->launches++;
+    c->cur ^= 1;
+    return;
+  }
+  ensure_order_buffers(c);
+  const int *held_at = nullptr;                 // position of the parcel that holds slot s now (null: s)
+  if (c->scrambled) {
+    invert_kernel<<<grid, 256, 0, c->stream>>>(c->slot, c->inv, np);
+    held_at = c->inv;
+    c->launches++;
+  }
+  // both keys per position (and dt: per position = per parcel = per slot before the permutation, handed over below like uvwp)
+  two_keys_kernel<<<grid, 256, 0, c->stream>>>(g, ctl_view(c, t), c->time(), c->lon(), c->lat(), c->p(), c->perm2, c->src,
+                                               (modules & MOD_TIMESTEPS) ? c->dt : nullptr, np);
+  // 1. the reference's sort, on the slots: perm[1][s] = position (now) of the parcel that takes slot s
+  pick_keys_kernel<<<grid, 256, 0, c->stream>>>(c->perm2, held_at, c->keys[0], c->perm[0], true, np);
+  CK(cudaGetLastError());
+  radix_sort_pairs(c, c->keys[0], c->keys[1], c->perm[0], c->perm[1], np, bits);
+  // 2. the engine's order: perm2[i] = slot of the parcel that goes to position i
+  pick_keys_kernel<<<grid, 256, 0, c->stream>>>(c->src, c->perm[1], c->keys[0], c->perm[0], false, np);
+  CK(cudaGetLastError());
+  radix_sort_pairs(c, c->keys[0], c->keys[1], c->perm[0], c->perm2, np, bits);
+  compose_kernel<<<grid, 256, 0, c->stream>>>(c->perm2, c->perm[1], c->slot2, c->src, np);
+  gather_kernel<<<grid, 256, 0, c->stream>>>(c->soa[c->cur], c->soa[c->cur ^ 1], c->src, np, c->np_max, 4 + c->nq);
+  CK(cudaGetLastError());
+  c->launches += 5;
+  c->cur ^= 1;
+  hand_over(c, c->slot2, held_at, c->src, nullptr);
+  std::swap(c->slot, c->slot2);
+  c->scrambled = true;
 }
 
 static long long mixing_total(const mpb_ctx *c) {
@@ -1906,7 +2090,7 @@ static void launch_diff_pbl(mpb_ctx *c) {
           "module_diff_pbl needs the met field h2o of both levels (mpb_met_view_t::x3)");
   A.f.ess = c->x2[MPB_F2_ESS]; A.f.nss = c->x2[MPB_F2_NSS]; A.f.shf = c->x2[MPB_F2_SHF]; A.f.h2o = c->x3[MPB_F3_H2O];
   A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p(); A.dt = c->dt; A.uvwp = c->uvwp;
-  A.ctr = ctr; A.ig0 = c->ig0; A.np = c->np;
+  A.ctr = ctr; A.ig0 = c->ig0; A.np = c->np; A.slot = c->scrambled ? c->slot : nullptr;
   diff_pbl_kernel<<<nblocks(c->np, 128), 128, 0, c->stream>>>(A);
   CK(cudaGetLastError());
   c->launches++;
@@ -1930,7 +2114,7 @@ static void launch_convection(mpb_ctx *c) {
     A.conv.fcape = c->x2[MPB_F2_CAPE]; A.conv.fcin = c->x2[MPB_F2_CIN]; A.conv.fpel = c->x2[MPB_F2_PEL];
   }
   A.time = c->time(); A.lon = c->lon(); A.lat = c->lat(); A.p = c->p(); A.dt = c->dt;
-  A.ctr = ctr; A.ig0 = c->ig0; A.np = c->np;
+  A.ctr = ctr; A.ig0 = c->ig0; A.np = c->np; A.slot = c->scrambled ? c->slot : nullptr;
   convection_kernel<<<nblocks(c->np, 128), 128, 0, c->stream>>>(A);
   CK(cudaGetLastError());
   c->launches++;
@@ -2248,7 +2432,8 @@ int mpb_destroy(mpb_ctx *c) {
   void *ptrs[] = {c->soa[0], c->soa[1], c->dt, c->uvwp, c->keys[0], c->keys[1], c->perm[0], c->perm[1],
                   c->cub_tmp, c->nodes, c->surf, c->ax_lon, c->ax_lat, c->ax_p, c->ax_lonc, c->ax_latc, c->ax_pc,
                   c->p_lut, c->stage_d, c->cl_time, c->cl_lat, c->cl_tropo, c->box, c->mix_rec, c->mix_alloc, c->mix_route,
-                  c->grid_in_area ? nullptr : c->grid_sum, c->grid_in_area ? nullptr : c->grid_sq, c->grid_in_area ? nullptr : c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz, c->lev_hint, c->iso_var, c->iso_ts, c->iso_ps, c->chem_mass};
+                  c->grid_in_area ? nullptr : c->grid_sum, c->grid_in_area ? nullptr : c->grid_sq, c->grid_in_area ? nullptr : c->grid_cnt, c->lev_p, c->lev_z, c->lev_pz, c->lev_hint, c->iso_var, c->iso_ts, c->iso_ps, c->chem_mass,
+                  c->slot, c->slot2, c->inv, c->perm2, c->src, c->uvwp2, c->dt2, c->iso_var2, c->lev_hint2};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int r = 0; r < kMaxRanks; r++)
     if (c->area[r]) { if (r == c->rank) cudaFree(c->area[r]); else if (c->area_ipc[r]) cudaIpcCloseMemHandle(c->area[r]); }
@@ -2587,11 +2772,15 @@ int mpb_set_atm(mpb_ctx *c, int64_t np, const double *time, const double *p, con
                 const double *lat, const double *q, int64_t q_stride) {
   API_BEGIN
   use(c);
+  unscramble(c);
   REQUIRE(np >= 0 && np <= c->np_max, "np exceeds the context capacity");
   REQUIRE(np == 0 || (time && p && lon && lat), "null parcel array");
   REQUIRE(c->nq == 0 || np == 0 || q != nullptr, "null quantity array");
   c->np = np;
   c->q_stale = false;
+  if (c->have_ctl && c->ctl.sort_dt > 0 && np > 0) {      // the sort's buffers now, not at the first sort in the middle of the run
+    if (own_order_wanted(c)) ensure_order_buffers(c); else ensure_sort_buffers(c);
+  }
   const size_t bytes = sizeof(double) * (size_t)np;
   if (np > 0) {
     CK(cudaMemcpyAsync(c->time(), time, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -2607,6 +2796,7 @@ int mpb_set_atm(mpb_ctx *c, int64_t np, const double *time, const double *p, con
 int mpb_set_uvwp(mpb_ctx *c, const float *uvwp) {
   API_BEGIN
   use(c);
+  unscramble(c);
   REQUIRE(uvwp != nullptr, "null uvwp");
   if (c->np > 0) CK(cudaMemcpyAsync(c->uvwp, uvwp, sizeof(float) * 3 * (size_t)c->np, cudaMemcpyHostToDevice, c->stream));
   API_END
@@ -2615,6 +2805,7 @@ int mpb_set_uvwp(mpb_ctx *c, const float *uvwp) {
 int mpb_set_iso_var(mpb_ctx *c, const double *iso_var) {
   API_BEGIN
   use(c);
+  unscramble(c);
   REQUIRE(iso_var != nullptr, "null iso_var");
   if (!c->iso_var) CK(cudaMalloc(&c->iso_var, sizeof(double) * (size_t)std::max<long long>(c->np_max, 1)));
   if (c->np > 0) CK(cudaMemcpyAsync(c->iso_var, iso_var, sizeof(double) * (size_t)c->np, cudaMemcpyHostToDevice, c->stream));
@@ -2624,6 +2815,7 @@ int mpb_set_iso_var(mpb_ctx *c, const double *iso_var) {
 int mpb_get_iso_var(mpb_ctx *c, double *iso_var) {
   API_BEGIN
   use(c);
+  unscramble(c);
   REQUIRE(iso_var != nullptr && c->iso_var != nullptr, "no iso_var on the device");
   if (c->np > 0) CK(cudaMemcpyAsync(iso_var, c->iso_var, sizeof(double) * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -2663,6 +2855,7 @@ int mpb_set_balloon(mpb_ctx *c, int n, const double *ts, const double *ps) {
 int mpb_get_atm(mpb_ctx *c, double *time, double *p, double *lon, double *lat, double *q, int64_t q_stride) {
   API_BEGIN
   use(c);
+  unscramble(c);
   const size_t bytes = sizeof(double) * (size_t)c->np;
   if (c->np > 0) {
     if (time) CK(cudaMemcpyAsync(time, c->time(), bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -2683,6 +2876,7 @@ int mpb_get_atm(mpb_ctx *c, double *time, double *p, double *lon, double *lat, d
 int mpb_get_uvwp(mpb_ctx *c, float *uvwp) {
   API_BEGIN
   use(c);
+  unscramble(c);
   if (c->np > 0) CK(cudaMemcpyAsync(uvwp, c->uvwp, sizeof(float) * 3 * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   API_END
@@ -2691,6 +2885,7 @@ int mpb_get_uvwp(mpb_ctx *c, float *uvwp) {
 int mpb_get_dt(mpb_ctx *c, double *dt) {
   API_BEGIN
   use(c);
+  unscramble(c);
   if (c->np > 0) CK(cudaMemcpyAsync(dt, c->dt, sizeof(double) * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   API_END
@@ -2810,7 +3005,7 @@ static std::vector<Op> plan_modules(const mpb_ctl_t &k, double t, unsigned mask)
 static void run_op(mpb_ctx *c, double t, const Op &o) {
     switch (o.kind) {
       case Op::STEP: launch_step(c, t, o.advect, o.phys, o.modules); break;
-      case Op::SORT: do_sort(c, t, o.modules); break;
+      case Op::SORT: do_sort(c, t, o.modules, own_order_wanted(c)); break;
       case Op::ISOSURF_INIT: launch_isosurf(c, true); break;
       case Op::ADVECT_INIT: launch_advect_init(c); break;
       case Op::ADVECT_LEVELS: launch_advect_levels(c, t, o.modules); break;
@@ -2884,11 +3079,14 @@ int mpb_run_timestep_host(mpb_ctx *c, double t, int64_t np, double *time, double
     // steps with a global phase (cell sort, box means), steps that write quantities (meteo) and tiny problems take the
     // plain sequence
     REQUIRE(mpb_set_atm(c, np, time, p, lon, lat, q, q_stride) == 0, g_err);
-    run_modules(c, t, MPB_MOD_ALL);
+    c->leaving_soon = true;      // (the parcels go back to the host right away: no point in an order of the engine's own)
+    try { run_modules(c, t, MPB_MOD_ALL); } catch (...) { c->leaving_soon = false; throw; }
+    c->leaving_soon = false;
     REQUIRE(mpb_get_atm(c, time, p, lon, lat, q, q_stride) == 0, g_err);
     c->host_h2d = c->host_d2h = (32 + 8 * (long long)c->nq) * np;
     return 0;
   }
+  unscramble(c);
   c->np = np;
   c->q_stale = c->nq > 0;      // only rp / rhop cross the link below; everything that reads q[] on the device wants mpb_set_atm first
   unsigned phys = 0;
@@ -3270,6 +3468,9 @@ int mpb_grid_fetch(mpb_ctx *c, int *count, double *sum, double *sq) {
 void *mpb_device_ptr(mpb_ctx *c, const char *name) {
   if (!c || !name) return nullptr;
   const std::string n(name);
+  if (c->scrambled && (n == "time" || n == "p" || n == "lon" || n == "lat" || n == "q" || n == "dt" || n == "uvwp")) {
+    try { use(c); unscramble(c); } catch (const std::exception &ex) { g_err = ex.what(); return nullptr; }
+  }
   if (n == "time") return c->time();
   if (n == "p") return c->p();
   if (n == "lon") return c->lon();

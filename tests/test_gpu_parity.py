@@ -498,6 +498,49 @@ def test_binning_at_the_cell_faces(oracle):
     assert np.array_equal(col(cnt), col(c0))
 
 
+@pytest.mark.parametrize("levels", [False, True], ids=["pressure_levels", "model_levels"])
+def test_the_engines_own_parcel_order_is_invisible(oracle, monkeypatch, levels):
+    """Between two cell sorts the engine lays the parcels out by the cell their lookups fall into, not by the reference's sort
+    key (engine.cu do_sort): slots, random numbers per slot, the slot-bound uvwp / dt handed to the slot's new parcel,
+    the reference's order restored whenever parcels are addressed from outside.  With that order forced on at every sort
+    (MPTRAC_B200_PRIVATE_ORDER=2) and switched off (=0) every array the API returns must be the same bit for bit --
+    diffusion, mesoscale memory and sedimentation on, sorts every second step, a read-back in the middle of the run,
+    np < np_max; and both must agree with the oracle like every other run."""
+    from mptrac_b200 import Ctl, synth
+    from oracle.oracle import Parcels
+    m0, m1, tm, p, lon, lat, clim = _case(n=20011, grid=(48, 25, 24), seed=13)
+    if levels:
+        m0, m1 = synth.add_model_levels(m0, npl=24), synth.add_model_levels(m1, npl=24)
+    n = tm.size
+    q = np.stack([np.full(n, 2.0), np.full(n, 1500.0)])
+    kw = dict(nq=2, qnt_rp=0, qnt_rhop=1, advect=4, diffusion=1, t_start=0.0, t_stop=1e6, dt_mod=300.0, dt_met=21600.0,
+              turb_dz_trop=0.5, turb_dx_strat=20.0, sort_dt=600.0)
+    if levels:
+        kw.update(advect_vert_coord=2)
+    ctl = Ctl(**kw)
+    runs = {}
+    for mode in ("2", "0"):
+        monkeypatch.setenv("MPTRAC_B200_PRIVATE_ORDER", mode)
+        with _engine(n + 77, 2) as eng:
+            _setup(eng, ctl, clim, m0, m1, tm, p, lon, lat, q)
+            for s in range(5):
+                eng.run_timestep(300.0 * s)
+            mid = eng.get_atm()                               # restores the reference's order; the run goes on from there
+            for s in range(5, 11):
+                eng.run_timestep(300.0 * s)
+            runs[mode] = dict(mid=mid, end=eng.get_atm(), uvwp=eng.get_uvwp(), dt=eng.get_dt())
+    a, b = runs["2"], runs["0"]
+    for when in ("mid", "end"):
+        for k in ("time", "lon", "lat", "p", "q"):
+            assert np.array_equal(a[when][k], b[when][k]), f"{when}: {k} depends on the order in memory"
+    assert np.array_equal(a["uvwp"], b["uvwp"]) and np.array_equal(a["dt"], b["dt"])
+    assert np.abs(a["uvwp"]).max() > 0
+    ref = Parcels(tm, p, lon, lat, q)
+    oracle.ctr = 0
+    oracle.run("timestep", ctl, clim, m0, m1, ref, t=0.0, nsteps=11)
+    _compare("own_order", a["end"], ref, TOL_POS_DEG_DIFF, TOL_P_REL_DIFF)
+
+
 def test_inactive_and_ragged_parcels(oracle):
     """parcels that start later / are already past t_stop keep dt = 0 and must not be touched; np < np_max"""
     from mptrac_b200 import Ctl
