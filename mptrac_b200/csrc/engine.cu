@@ -1770,8 +1770,8 @@ static bool own_order_wanted(const mpb_ctx *c) {
 // module_sort (src/mptrac.c:5887-5995).  The reference orders the parcels by the met cell of their RAW longitude: on a grid
 // that runs 0..360 every parcel west of Greenwich (module_position keeps longitudes in [-180, 180)) falls into column 0 of the
 // key and is ordered by latitude and level only -- half a sort (measured: DESIGN.md 9).  The engine therefore keeps TWO
-// orders.  The reference's sort is carried out on the SLOTS: which parcel sits in which slot of atm_t afterwards, stable like
-// the oracle's, with dt computed per slot before the permutation (src/mptrac.c:7877-7881).  The parcels themselves are
+// orders.  The reference's sort is carried out on the SLOTS: which parcel sits in which slot of atm_t afterwards (a stable
+// sort in slot order), with dt computed per slot before the permutation (src/mptrac.c:7877-7881).  The parcels themselves are
 // then laid out by the cell their lookups fall into (wrapped longitude); slot[i] remembers the slot of the parcel at position
 // i for its random numbers, and what the reference leaves in the slot (uvwp, dt, iso_var) is handed to the slot's new parcel.
 // Everything that addresses parcels by slot from outside restores the reference's order first (unscramble).
