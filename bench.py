@@ -314,7 +314,7 @@ def exchange_record(name, rank, world, local, K=12, W=3):
     nmix = len([i for i in ctl.mix_qnt if i >= 0]) if wl.get("mixing") else 0
     if wl.get("mixing"):
         nbox = ctl.mixing_nx * ctl.mixing_ny * ctl.mixing_nz
-        per_rank = (2 * 8 * (nmix + 1) * n * (world - 1) // world if attached else
+        per_rank = (8 * (2 * nmix + 1) * n * (world - 1) // world if attached else      # {box, q ..} out, box means back
                     2 * 8 * (nmix + 1) * nbox * (world - 1) // world)
     else:
         g = wl["out_grid"]
