@@ -514,3 +514,50 @@ def test_binary_met_file_as_the_reference_reads_it(reference, tmp_path):
     want_t[3, 4, 5] = 0.0
     assert np.array_equal(got.t, want_t)
     reference.read_ctl([], "")
+
+
+def test_grid_binning_is_what_the_reference_tool_writes(oracle, tmp_path):
+    """write_grid's binning (src/mptrac.c:13840-13918) has no entry point of its own in the harness: the oracle's `orc_grid_bin`
+    is pinned here against the reference's own `atm2grid` tool run on a binary particle file (raw doubles in, counts and
+    17-digit means / standard deviations out) -- parcels on and beside the faces of the grid included."""
+    import os
+    import subprocess
+    from oracle.oracle import Parcels
+    tool = ROOT / "oracle" / "_ref" / "bin" / "atm2grid"
+    if not tool.exists():
+        pytest.skip("oracle/_ref is not built here")
+    rng = np.random.default_rng(21)
+    nx, ny, nz, z0, z1 = 24, 12, 10, -2.0, 38.0
+    n = 60000
+    mag = np.concatenate([[0.0], 10.0 ** np.arange(-15.0, -2.0, 1.0)])
+    eps = np.concatenate([-mag[::-1], mag])
+    xf = ((-180.0 + 360.0 / nx * np.arange(nx + 1))[:, None] + eps[None, :]).ravel()
+    yf = ((-90.0 + 180.0 / ny * np.arange(ny + 1))[:, None] + eps[None, :]).ravel()
+    lon = np.concatenate([rng.uniform(-180, 180, n // 2), rng.choice(xf, n // 2)])
+    lat = np.concatenate([rng.uniform(-90, 90, n // 2), rng.choice(yf, n // 2)])
+    p = 1013.25 * np.exp(-rng.uniform(z0 - 2, z1 + 2, n) / 7.0)
+    tm = np.where(rng.uniform(size=n) < 0.9, 0.0, rng.choice([-151.0, -150.0, 150.0, 151.0], n))   # the window is [t - dt/2, t + dt/2]
+    q = rng.uniform(0.5, 2.0, (1, n))
+    with open(tmp_path / "atm_2000_01_01_00_00_00.bin", "wb") as f:
+        np.array([100, n], np.int32).tofile(f)                       # read_atm_bin: version, np, arrays, final flag (:8422-8470)
+        for a in (tm, p, lon, lat, q[0]):
+            a.astype(np.float64).tofile(f)
+        np.array([999], np.int32).tofile(f)
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run([str(tool), "-", "atm_2000_01_01_00_00_00.bin", "ATM_TYPE", "1", "NQ", "1", "QNT_NAME[0]", "zeta",
+                        "QNT_FORMAT[0]", "%.17g", "GRID_BASENAME", "grid", "GRID_STDDEV", "1", "DT_MOD", "300",
+                        "GRID_NX", str(nx), "GRID_NY", str(ny), "GRID_NZ", str(nz), "GRID_Z0", str(z0), "GRID_Z1", str(z1),
+                        "GRID_LON0", "-180", "GRID_LON1", "180", "GRID_LAT0", "-90", "GRID_LAT1", "90"],
+                       cwd=tmp_path, env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    tab = np.loadtxt(tmp_path / "grid_2000_01_01_00_00_00.tab")
+    assert tab.shape == (nx * ny * nz, 11)                                # rows in box order: ix, then iy, then iz (:14026-14052)
+    cnt_ref, mean_ref, sig_ref = tab[:, 8].astype(np.int64), tab[:, 9], tab[:, 10]
+    cnt, s, sq = oracle.grid_bin(Parcels(tm, p, lon, lat, q), nx, ny, nz, -180, 180, -90, 90, z0, z1, -150.0, 150.0)
+    assert np.array_equal(cnt, cnt_ref) and 0.5 * n < cnt.sum() < n
+    full = cnt > 0
+    mean = s[0][full] / cnt[full]
+    var = sq[0][full] / cnt[full] - mean ** 2
+    assert np.array_equal(mean, mean_ref[full])                            # same sums in the same order, same division
+    assert np.array_equal(np.where(var > 0, np.sqrt(np.where(var > 0, var, 0.0)), 0.0), sig_ref[full])
+    assert np.all(np.isnan(mean_ref[~full]))
